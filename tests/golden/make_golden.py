@@ -1,0 +1,161 @@
+"""Mint golden vectors by running the REAL reference (adelacvg/ttts @ /root/reference) on CPU, fp32, eval mode.
+
+Run in the build container only (the GPU box has no /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, vq.npz, mel.npz.  Weights are NOT stored: they are regenerated from
+numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
+state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
+/root/reference is modified or copied.
+"""
+import os
+import sys
+import types
+import importlib.machinery as im
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+import numpy as np
+import torch
+
+
+def import_reference():
+    s = types.ModuleType("transformers.utils.model_parallel_utils")
+    s.get_device_map = s.assert_device_map = lambda *a, **k: None
+    sys.modules["transformers.utils.model_parallel_utils"] = s
+    t = types.ModuleType("ttts.utils.typical_sampling")
+    t.TypicalLogitsWarper = object
+    sys.modules["ttts.utils.typical_sampling"] = t
+    import ttts.gpt.model as gm  # noqa: must precede the librosa stub
+    import torchaudio
+    lb = types.ModuleType("librosa"); lb.__spec__ = im.ModuleSpec("librosa", None)
+    lu = types.ModuleType("librosa.util"); lu.normalize = lu.pad_center = lu.tiny = None
+    lf = types.ModuleType("librosa.filters")
+    lf.mel = lambda sr, n_fft, n_mels, fmin, fmax: torchaudio.functional.melscale_fbanks(
+        n_fft // 2 + 1, fmin, fmax or sr / 2, n_mels, sr, norm="slaney", mel_scale="slaney").T.numpy()
+    lb.util, lb.filters = lu, lf
+    sys.modules.update({"librosa": lb, "librosa.util": lu, "librosa.filters": lf})
+    e = types.ModuleType("encodec"); e.EncodecModel = object; sys.modules["encodec"] = e
+    import logging
+    logging.disable(logging.CRITICAL)
+    return gm
+
+
+def gpt_case(gm, name, cfg_over, B, TL, CL, text_lengths=None, wav_lengths=None, seed=0):
+    from oracle import gpt_oracle as O
+    cfg = O.default_config(**cfg_over)
+    params = O.init_params(cfg, seed=seed)
+    ref_kwargs = {k: cfg[k] for k in ("layers", "model_dim", "heads", "max_text_tokens", "max_mel_tokens", "number_text_tokens",
+                                     "start_text_token", "number_mel_codes", "start_mel_token", "stop_mel_token")}
+    model = gm.UnifiedVoice(**ref_kwargs, use_mel_codes_as_input=True, train_solo_embeddings=False).eval()
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(params.keys()), (set(sd.keys()) ^ set(params.keys()))
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(params[k].shape), (k, sd[k].shape, params[k].shape)
+    model.load_state_dict({k: v.clone() for k, v in params.items()})
+    text, tl, codes, wl = O.synthetic_batch(B, TL, CL, seed=1234)
+    if text_lengths is not None:
+        tl = torch.tensor(text_lengths, dtype=torch.int64)
+    if wav_lengths is not None:
+        wl = torch.tensor(wav_lengths, dtype=torch.int64)
+    codes_in = codes.clone()
+    loss_text, loss_mel, mel_logits = model(text, tl, codes_in, wl)
+    loss = 0.01 * loss_text + 1.0 * loss_mel
+    loss.backward()
+    grads = {k: p.grad.detach().numpy() for k, p in model.named_parameters()}
+    latent = model(text, tl, codes.clone(), wl, return_latent=True).detach()
+    out = dict(
+        cfg_json=np.array(repr(cfg)), B=B, TL=TL, CL=CL, seed=seed,
+        text=text.numpy(), text_lengths=tl.numpy(), codes=codes.numpy(), wav_lengths=wl.numpy(),
+        codes_after=codes_in.numpy(),          # set_mel_padding mutates the caller's tensor (Appendix E #4)
+        loss_text=loss_text.detach().numpy(), loss_mel=loss_mel.detach().numpy(),
+        mel_logits=mel_logits.detach().numpy(), latent=latent.numpy(),
+    )
+    for k, g in grads.items():
+        out["grad/" + k] = g
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss_text %.6f loss_mel %.6f" % (float(loss_text), float(loss_mel)), "->", path, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+def vq_case():
+    """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
+    from ttts.vqvae.quantize import ResidualVectorQuantizer
+    rs = np.random.RandomState(7)
+    D, K, B, N = 192, 1024, 6, 18
+    E = rs.standard_normal((K, D)).astype(np.float32)
+    x = (rs.standard_normal((B, D, N)) * 1.0).astype(np.float32)
+    # a few exact duplicates of codebook rows and duplicate codebook rows (first-max-wins, core_vq.py:181)
+    E[700] = E[13]
+    x[0, :, 0] = E[13]
+    x[1, :, 3] = E[999]
+    out = {"E": E, "x": x}
+    for mode in ("eval", "train"):
+        q = ResidualVectorQuantizer(dimension=D, n_q=1, bins=K)
+        cb = q.vq.layers[0]._codebook
+        cb.embed.copy_(torch.tensor(E)); cb.embed_avg.copy_(torch.tensor(E) * 3.0)
+        cs = torch.tensor(rs.uniform(2.5, 9.0, size=(K,)).astype(np.float32))
+        cb.cluster_size.copy_(cs); cb.inited.fill_(1)
+        out[mode + "/cluster_size_in"] = cs.numpy()
+        q.train(mode == "train")
+        xt = torch.tensor(x, requires_grad=True)
+        quantized, codes, commit, qlist = q(xt, layers=[0])
+        if mode == "train":   # eval: output is a buffer gather, nothing requires grad (core_vq.py:310-318)
+            w = torch.tensor(rs.standard_normal(quantized.shape).astype(np.float32))
+            out["train/dquantized"] = w.numpy()
+            ((quantized * w).sum() + commit * 3.0).backward()
+        out[mode + "/quantized"] = quantized.detach().numpy()
+        out[mode + "/codes"] = codes.numpy()
+        out[mode + "/commit"] = commit.detach().numpy()
+        if mode == "train":
+            out[mode + "/dx"] = xt.grad.numpy()
+        out[mode + "/embed_out"] = cb.embed.numpy().copy()
+        out[mode + "/embed_avg_out"] = cb.embed_avg.numpy().copy()
+        out[mode + "/cluster_size_out"] = cb.cluster_size.numpy().copy()
+        enc = q.encode(torch.tensor(x))
+        out[mode + "/encode"] = enc.numpy()
+        out[mode + "/decode"] = q.decode(enc).detach().numpy()
+    path = os.path.join(ROOT, "tests", "golden", "vq.npz")
+    np.savez_compressed(path, **out)
+    print("vq ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+def mel_case():
+    """spectrogram_torch / spec_to_mel_torch / mel_spectrogram_torch (ttts/utils/data_utils.py:52-156) and
+    MelSpectrogramFeatures (ttts/vocoder/feature_extractors.py:28-49)."""
+    from ttts.utils.data_utils import spectrogram_torch, spec_to_mel_torch, mel_spectrogram_torch
+    from ttts.vocoder.feature_extractors import MelSpectrogramFeatures
+    g = torch.Generator().manual_seed(1234)
+    wav = torch.clamp(0.1 * torch.randn(3, 24000, generator=g), -1, 1)
+    t = torch.arange(24000) / 24000.0
+    wav[1] = 0.5 * torch.sin(2 * math.pi * 440.0 * t) + 0.1 * torch.sin(2 * math.pi * 3000.0 * t)
+    wav32 = wav[:, :23040].contiguous()
+    spec = spectrogram_torch(wav32, 2048, 640, 2048, center=False)
+    mel = spec_to_mel_torch(spec, 2048, 128, 32000, 0, None)
+    mel2 = mel_spectrogram_torch(wav32, 2048, 128, 32000, 640, 2048, 0, None, center=False)
+    feats = MelSpectrogramFeatures()(wav)
+    # librosa is absent in the build container: the Slaney basis comes from torchaudio; store it so the
+    # oracle / CUDA path can be checked against the exact basis the reference multiplied with.
+    import librosa
+    basis = librosa.filters.mel(sr=32000, n_fft=2048, n_mels=128, fmin=0, fmax=None)
+    fb24 = MelSpectrogramFeatures().mel_spec.mel_scale.fb.numpy()
+    path = os.path.join(ROOT, "tests", "golden", "mel.npz")
+    np.savez_compressed(path, wav=wav.numpy(), spec=spec.numpy().astype(np.float32), mel=mel.numpy(), mel2=mel2.numpy(),
+                        feats24=feats.numpy(), basis32=np.asarray(basis, dtype=np.float32), fb24=fb24)
+    print("mel ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), spec.shape, mel.shape, feats.shape)
+
+
+if __name__ == "__main__":
+    import math
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    gm = import_reference()
+    tiny = dict(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
+    gpt_case(gm, "gpt_tiny", tiny, B=2, TL=12, CL=24)
+    # ragged: clipping + set_mel_padding paths (wav_lengths//1024+1 < CL for some rows)
+    gpt_case(gm, "gpt_ragged", tiny, B=3, TL=16, CL=30, text_lengths=[9, 14, 5], wav_lengths=[20 * 1024 + 17, 27 * 1024, 6 * 1024 + 1000], seed=3)
+    vq_case()
+    mel_case()

@@ -1,0 +1,118 @@
+#include "host_util.h"
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace ttts {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return TTTS_ERR_CUDA;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* p; int eb; uint64_t inner, outer, ld; uint32_t bi, bo; bool sw; int dev;
+    bool operator==(const TmapKey& o) const {
+        return p == o.p && eb == o.eb && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo &&
+               sw == o.sw && dev == o.dev;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.p * 0x9E3779B97F4A7C15ULL;
+        h ^= k.inner * 0xff51afd7ed558ccdULL + k.outer * 0xc4ceb9fe1a85ec53ULL + k.ld * 31 + k.bi * 131 + k.bo * 17 + k.eb + (k.sw ? 7 : 0) + k.dev * 1315423911ULL;
+        return (size_t)h;
+    }
+};
+
+int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    TmapKey key{gptr, elem_bytes, inner, outer, ld_elems, box_inner, box_outer, swizzle128, dev};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return TTTS_OK; }
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)"); return TTTS_ERR_CUDA; }
+    TTTS_CHECK_ARG(((uintptr_t)gptr & 15) == 0, "TMA base pointer %p not 16B aligned", gptr);
+    TTTS_CHECK_ARG((ld_elems * (uint64_t)elem_bytes) % 16 == 0, "TMA row stride %llu B not a multiple of 16", (unsigned long long)(ld_elems * elem_bytes));
+    TTTS_CHECK_ARG(box_inner <= 256 && box_outer <= 256, "TMA box too large");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r, (unsigned long long)inner,
+                  (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer);
+        return TTTS_ERR_CUDA;
+    }
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 65536) cache.clear();
+        cache[key] = *out;
+    }
+    return TTTS_OK;
+}
+
+}  // namespace ttts
+
+extern "C" {
+
+int ttts_version(void) { return 100; }
+const char* ttts_last_error(void) { return ttts::g_err; }
+
+int ttts_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+}

@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, launch checks,
+// device properties, TMA tensor-map encoding (driver entry point resolved at run time so the
+// library has no link-time dependency on libcuda and builds on GPU-less boxes).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/ttts_b200.h"
+
+namespace ttts {
+
+void set_error(const char* fmt, ...);
+int fail_cuda(cudaError_t e, const char* what);
+int num_sms();
+
+#define TTTS_CHECK_ARG(cond, ...)                    \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::ttts::set_error(__VA_ARGS__);          \
+            return TTTS_ERR_INVALID;                 \
+        }                                            \
+    } while (0)
+
+#define TTTS_CUDA(expr)                                           \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return ::ttts::fail_cuda(_e, #expr); \
+    } while (0)
+
+#define TTTS_LAUNCH_CHECK(name)                                   \
+    do {                                                          \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return ::ttts::fail_cuda(_e, name); \
+    } while (0)
+
+// 2-D bf16/fp32 tiled tensor map with 128B swizzle (or none).
+//   inner/outer: tensor extents in elements (inner = contiguous dim); ld_elems: row stride in elements
+//   box_inner/box_outer: box extents in elements
+int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+
+}  // namespace ttts
