@@ -67,6 +67,114 @@ typedef struct {
 
 int ttts_gemm_bf16(const ttts_gemm_args* args, void* stream);
 
+
+/* --------------------------------------------------------------------------------------------
+ * UnifiedVoice GPT train step (ttts/gpt/model.py:453-510 driven by ttts/gpt/train.py:99-121).
+ *
+ * Parameters live in ONE flat fp32 buffer (plus a bf16 shadow at the same element offsets that feeds the
+ * tensor cores, and a flat fp32 gradient buffer laid out identically so that data-parallel training is a
+ * single NCCL all-reduce).  ttts_gpt_param_offset() gives the element offset of every reference
+ * state_dict tensor inside those buffers; the Python module exposes them as nn.Parameter
+ * views with the reference's names and shapes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t layers, model_dim, heads;
+    int32_t max_text_tokens, max_mel_tokens;     /* position tables hold max+2 rows (gpt/model.py:339)   */
+    int32_t n_text_vocab, n_mel_vocab;           /* 257 = number_text_tokens*types+1 ; 1026               */
+    int32_t start_text_token, stop_text_token;   /* 255, 0                                                */
+    int32_t start_mel_token, stop_mel_token;     /* 1024, 1025                                            */
+    int32_t mel_length_compression;              /* 1024                                                  */
+} ttts_gpt_config;
+
+typedef enum {
+    TTTS_P_TEXT_EMB = 0, TTTS_P_MEL_EMB, TTTS_P_TEXT_POS, TTTS_P_MEL_POS,
+    /* per layer */
+    TTTS_P_LN1_W, TTTS_P_LN1_B, TTTS_P_ATTN_W, TTTS_P_ATTN_B, TTTS_P_PROJ_W, TTTS_P_PROJ_B,
+    TTTS_P_LN2_W, TTTS_P_LN2_B, TTTS_P_FC_W, TTTS_P_FC_B, TTTS_P_PR_W, TTTS_P_PR_B,
+    /* top */
+    TTTS_P_LNF_W, TTTS_P_LNF_B, TTTS_P_FN_W, TTTS_P_FN_B,
+    TTTS_P_TEXT_HEAD_W, TTTS_P_TEXT_HEAD_B, TTTS_P_MEL_HEAD_W, TTTS_P_MEL_HEAD_B,
+    TTTS_P_COUNT
+} ttts_gpt_tensor;
+
+/* element offset of a tensor in the flat buffers (layer ignored for non-layer tensors); <0 on error */
+int64_t ttts_gpt_param_offset(const ttts_gpt_config* cfg, int32_t tensor, int32_t layer);
+/* number of elements of that tensor */
+int64_t ttts_gpt_param_numel(const ttts_gpt_config* cfg, int32_t tensor);
+/* total elements of the flat buffers (every tensor padded to a multiple of 64 elements) */
+int64_t ttts_gpt_param_count(const ttts_gpt_config* cfg);
+/* [begin,end) element range of backward stage s (0 = heads+final norms, 1..L = layer L-s, L+1 = embeddings):
+ * the gradients of that range are final once ttts_gpt_backward has run stages 0..s. */
+int32_t ttts_gpt_stage_range(const ttts_gpt_config* cfg, int32_t stage, int64_t* begin, int64_t* end);
+
+/* activations / scratch; save_acts=1 keeps what backward needs (training), 0 reuses one layer's buffers */
+int64_t ttts_gpt_workspace_bytes(const ttts_gpt_config* cfg, int32_t B, int32_t TL, int32_t CL, int32_t save_acts);
+
+typedef enum {
+    TTTS_WS_MEL_LOGITS = 0,   /* bf16 [B*(CL+2), ld_mel]   (ld via ttts_gpt_logits_ld)   */
+    TTTS_WS_TEXT_LOGITS = 1,  /* bf16 [B*(TL+2), ld_text]                                 */
+    TTTS_WS_LATENT = 2,       /* fp32 [B*T, d] final_norm output (return_latent)          */
+    TTTS_WS_RESID = 3,        /* fp32 [B*T, d] residual stream entering layer `layer` (layer==L: input of ln_f) */
+    TTTS_WS_TOKENS = 4        /* int32 text_in | text_tgt | mel_in | mel_tgt              */
+} ttts_gpt_ws_item;
+int64_t ttts_gpt_workspace_offset(const ttts_gpt_config* cfg, int32_t B, int32_t TL, int32_t CL, int32_t save_acts,
+                                  int32_t item, int32_t layer);   /* byte offset, <0 on error */
+int32_t ttts_gpt_logits_ld(int32_t vocab);
+
+typedef struct {
+    ttts_gpt_config cfg;
+    int32_t B, TL, CL;                 /* (clipped) text / code lengths; T = TL + CL + 4                        */
+    const int64_t* text; int32_t ld_text;        /* [B, >=TL] raw text tokens                                     */
+    int64_t* codes; int32_t ld_codes;            /* [B, >=CL] raw mel codes -- mutated in place (set_mel_padding) */
+    const int64_t* wav_lengths;                  /* [B]                                                            */
+    const float* params;               /* flat fp32 parameters                                                   */
+    const void* params16;              /* flat bf16 shadow (ttts_cast_bf16 or ttts_adamw_step keep it fresh)     */
+    float* grads;                      /* flat fp32 gradients (backward ACCUMULATES)                             */
+    void* workspace; int64_t workspace_bytes;
+    float* losses;                     /* device [2]: loss_text, loss_mel                                        */
+    int32_t save_acts;                 /* 1: keep activations for backward                                       */
+    int32_t want_latent;               /* 1: also write TTTS_WS_LATENT and skip heads/losses                     */
+    float drop_p; uint64_t seed;       /* dropout (embd, attn-prob, attn-out, mlp-out); 0 = eval                 */
+    /* backward only */
+    const float* gscale_text; const float* gscale_mel;  /* device scalars dL/dloss_* (NULL = 1)                   */
+    float weight_text, weight_mel;                       /* host-side multipliers of the two losses               */
+} ttts_gpt_io;
+
+int ttts_gpt_forward(const ttts_gpt_io* io, void* stream);
+/* runs backward stages [stage_begin, stage_end) ; see ttts_gpt_stage_range */
+int ttts_gpt_backward(const ttts_gpt_io* io, int32_t stage_begin, int32_t stage_end, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * step tail: get_grad_norm + clip_grad_norm_(1.0) + AdamW (ttts/gpt/train.py:22-31,114-118)
+ * ------------------------------------------------------------------------------------------ */
+int ttts_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* norm_out[0] = ||g||_2 ; scratch: >= 1024 floats */
+int ttts_grad_norm(const float* grads, int64_t n, float* scratch, float* norm_out, void* stream);
+/* p, m, v updated in place; p16 (optional) receives the bf16 shadow.  grad is scaled by grad_scale (1/world for a
+ * summed all-reduce) and clipped to max_norm using *norm (the norm of the UNSCALED buffer); max_norm<=0 disables. */
+int ttts_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params16, int64_t n,
+                    const float* norm, float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * individual kernels (exported for the per-kernel parity tests)
+ * ------------------------------------------------------------------------------------------ */
+/* y = LN(x) (dbl=0) or LN2(LN1(x)) (dbl=1); stats: [M,2] or [M,4] (mean,rstd)            (HF:modeling_gpt2.py:273,304,628) */
+int ttts_layernorm_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, void* y,
+                       float* stats, int32_t M, int32_t d, int32_t dbl, int32_t out_bf16, void* stream);
+int ttts_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const float* stats, const float* w1, const float* b1,
+                       const float* w2, const float* g_in, float* g_out, void* g16_out, float* dw1, float* db1, float* dw2,
+                       float* db2, float* dbias_next, int32_t M, int32_t d, int32_t dbl, void* stream);
+/* causal flash attention on the packed c_attn output [B*T, 3d] (HF:modeling_gpt2.py:144-226) */
+int ttts_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);
+int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_scratch, void* dqkv,
+                  int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);
+/* mean cross-entropy over rows of bf16 logits [rows, ld] (ttts/gpt/model.py:508-509) */
+int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, float* row_loss, float* row_lse,
+                float* loss_out, void* stream);
+int ttts_ce_bwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, const float* row_lse,
+                const float* gscale, float weight, void* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,275 @@
+"""`UnifiedVoice` -- drop-in for ttts/gpt/model.py:292-510 whose arithmetic runs in hand-written sm_100a CUDA.
+
+Same constructor kwargs (ttts/gpt/model.py:293-297; called as `UnifiedVoice(**cfg['gpt'])`, ttts/gpt/train.py:45), same
+`forward` signature and returns `(loss_text, loss_mel, mel_logits[B,1026,CL+2])` (or latents with `return_latent`), same
+`state_dict()` keys / shapes so checkpoints interchange, ordinary `nn.Parameter`s so `AdamW(model.parameters())`,
+`clip_grad_norm_` and `loss.backward()` work unchanged.  Every parameter is a view into ONE flat fp32 buffer; the gradients
+autograd receives are views into one flat fp32 gradient buffer (a single NCCL all-reduce under data parallelism).
+
+No CPU fallback: calling forward on a non-CUDA / non-sm_100 device raises.  Inference-only paths of the reference that are not on
+the training hot path (`text_first=False`, `raw_mels`, `return_attentions`, `inference_speech`) raise NotImplementedError.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from . import engine as E
+
+
+class _Holder(nn.Module):
+    """A module that only owns parameters (keeps the reference's state_dict nesting)."""
+
+    def __init__(self, **params):
+        super().__init__()
+        for k, v in params.items():
+            if isinstance(v, nn.Module):
+                self.add_module(k, v)
+            else:
+                self.register_parameter(k, v)
+
+
+class _GPTStepFn(torch.autograd.Function):
+    """forward = ttts_gpt_forward, backward = ttts_gpt_backward; parameters enter as inputs so autograd routes
+    their gradients (views of the flat gradient buffer) to `.grad` / DDP hooks."""
+
+    @staticmethod
+    def forward(ctx, model, text, codes, wav_lengths, TL, CL, drop_p, seed, need_grad, *params):
+        eng = model._engine()
+        eng.refresh_shadow(force=not eng.trust_version)
+        eng.forward(text, codes, wav_lengths, TL, CL, save=need_grad, drop_p=drop_p, seed=seed)
+        B = text.shape[0]
+        ld = L.lib().ttts_gpt_logits_ld(model.number_mel_codes)
+        logits = eng.ws_view(E.WS_MEL_LOGITS, B, TL, CL, need_grad, torch.bfloat16, (B, CL + 2, ld))
+        mel_logits = logits[:, :, :model.number_mel_codes].clone()
+        losses = eng.losses.clone()
+        ctx.model = model
+        ctx.need_grad = need_grad
+        ctx.nparams = len(params)
+        ctx.mark_non_differentiable(mel_logits)
+        return losses[0], losses[1], mel_logits
+
+    @staticmethod
+    def backward(ctx, g_text, g_mel, _g_logits):
+        model = ctx.model
+        eng = model._engine()
+        params = [model._params_by_name[n] for n in model._param_names]
+        gviews = model._grad_views()
+        # If autograd previously stole our views as .grad (zero_grad(set_to_none=True) path), they alias the flat
+        # gradient buffer: accumulate in place.  Otherwise start from zero and hand the views to autograd.
+        aliased = [p.grad is not None and p.grad.data_ptr() == gv.data_ptr() for p, gv in zip(params, gviews)]
+        in_place = all(aliased)
+        if not in_place:
+            for p, a in zip(params, aliased):
+                if a:
+                    p.grad = p.grad.clone()
+            eng.grads.zero_()
+        gt = g_text.contiguous().float() if g_text is not None else torch.zeros((), device=eng.device)
+        gm = g_mel.contiguous().float() if g_mel is not None else torch.zeros((), device=eng.device)
+        eng.backward(gscale_text=gt, gscale_mel=gm)
+        model._after_backward()
+        if in_place:
+            return (None,) * (9 + ctx.nparams)
+        return (None,) * 9 + tuple(gviews)
+
+
+class UnifiedVoice(nn.Module):
+    def __init__(self, layers=8, model_dim=512, heads=8, max_text_tokens=120, max_mel_tokens=250, max_conditioning_inputs=1,
+                 mel_length_compression=1024, number_text_tokens=256, start_text_token=None, number_mel_codes=8194,
+                 start_mel_token=8192, stop_mel_token=8193, train_solo_embeddings=False, use_mel_codes_as_input=True,
+                 checkpointing=True, types=1):
+        super().__init__()
+        self._ctor_kwargs = dict(layers=layers, model_dim=model_dim, heads=heads, max_text_tokens=max_text_tokens,
+                                 max_mel_tokens=max_mel_tokens, max_conditioning_inputs=max_conditioning_inputs,
+                                 mel_length_compression=mel_length_compression, number_text_tokens=number_text_tokens,
+                                 start_text_token=start_text_token, number_mel_codes=number_mel_codes, start_mel_token=start_mel_token,
+                                 stop_mel_token=stop_mel_token, train_solo_embeddings=train_solo_embeddings,
+                                 use_mel_codes_as_input=use_mel_codes_as_input, checkpointing=checkpointing, types=types)
+        if not use_mel_codes_as_input:
+            raise NotImplementedError("use_mel_codes_as_input=False (MelEncoder input) is not on the hot path")
+        if train_solo_embeddings:
+            raise NotImplementedError("train_solo_embeddings=True is not on the hot path")
+        self.number_text_tokens = number_text_tokens
+        self.start_text_token = number_text_tokens * types if start_text_token is None else start_text_token
+        self.stop_text_token = 0
+        self.number_mel_codes = number_mel_codes
+        self.start_mel_token = start_mel_token
+        self.stop_mel_token = stop_mel_token
+        self.layers = layers
+        self.heads = heads
+        self.max_mel_tokens = max_mel_tokens
+        self.max_text_tokens = max_text_tokens
+        self.model_dim = model_dim
+        self.max_conditioning_inputs = max_conditioning_inputs
+        self.mel_length_compression = mel_length_compression
+        self.checkpointing = checkpointing      # accepted for API parity; activations fit in HBM, nothing is recomputed
+        self.mel_solo_embedding = 0
+        self.text_solo_embedding = 0
+        # dropout probability of the four GPT-2 sites (HF GPT2Config defaults embd/attn/resid_pdrop = 0.1; the reference
+        # exposes no knob).  Active only in train() mode, like nn.Dropout.
+        self.dropout_p = 0.1
+        self._seed_counter = 0
+        self._base_seed = 0x5DEECE66D
+
+        cfg = E.GptConfig()
+        cfg.layers, cfg.model_dim, cfg.heads = layers, model_dim, heads
+        cfg.max_text_tokens, cfg.max_mel_tokens = max_text_tokens, max_mel_tokens
+        cfg.n_text_vocab, cfg.n_mel_vocab = number_text_tokens * types + 1, number_mel_codes
+        cfg.start_text_token, cfg.stop_text_token = self.start_text_token, self.stop_text_token
+        cfg.start_mel_token, cfg.stop_mel_token = start_mel_token, stop_mel_token
+        cfg.mel_length_compression = mel_length_compression
+        self._cfg = cfg
+        self._layout = E.Layout(cfg)
+        self._flat = torch.zeros(self._layout.total, dtype=torch.float32)
+        self._eng = None
+        self._gviews = None
+
+        views = self._layout.views(self._flat)
+        P = {name: nn.Parameter(v) for name, v in views.items()}
+        self._param_names = [name for name, _, _, _ in self._layout.entries]
+        # module tree with the reference's state_dict nesting / registration order
+        self.text_embedding = _Holder(weight=P["text_embedding.weight"])
+        self.mel_embedding = _Holder(weight=P["mel_embedding.weight"])
+        blocks = []
+        for i in range(layers):
+            p = "gpt.h.%d." % i
+            blocks.append(_Holder(
+                ln_1=_Holder(weight=P[p + "ln_1.weight"], bias=P[p + "ln_1.bias"]),
+                attn=_Holder(c_attn=_Holder(weight=P[p + "attn.c_attn.weight"], bias=P[p + "attn.c_attn.bias"]),
+                             c_proj=_Holder(weight=P[p + "attn.c_proj.weight"], bias=P[p + "attn.c_proj.bias"])),
+                ln_2=_Holder(weight=P[p + "ln_2.weight"], bias=P[p + "ln_2.bias"]),
+                mlp=_Holder(c_fc=_Holder(weight=P[p + "mlp.c_fc.weight"], bias=P[p + "mlp.c_fc.bias"]),
+                            c_proj=_Holder(weight=P[p + "mlp.c_proj.weight"], bias=P[p + "mlp.c_proj.bias"]))))
+        self.gpt = _Holder(h=nn.ModuleList(blocks), ln_f=_Holder(weight=P["gpt.ln_f.weight"], bias=P["gpt.ln_f.bias"]))
+        self.mel_pos_embedding = _Holder(emb=_Holder(weight=P["mel_pos_embedding.emb.weight"]))
+        self.text_pos_embedding = _Holder(emb=_Holder(weight=P["text_pos_embedding.emb.weight"]))
+        self.final_norm = _Holder(weight=P["final_norm.weight"], bias=P["final_norm.bias"])
+        self.text_head = _Holder(weight=P["text_head.weight"], bias=P["text_head.bias"])
+        self.mel_head = _Holder(weight=P["mel_head.weight"], bias=P["mel_head.bias"])
+        self._params_by_name = P
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ init (reference statistics)
+    @torch.no_grad()
+    def reset_parameters(self):
+        """Embeddings N(0,.02) (ttts/gpt/model.py:235,356); GPT-2 block init (HF _init_weights: N(0,.02), c_proj
+        N(0,.02/sqrt(2L)), LN 1/0, biases 0); heads / final_norm torch defaults (nn.Linear kaiming-uniform, LN 1/0)."""
+        L_ = self.layers
+        for name, p in self._params_by_name.items():
+            if name.endswith("ln_1.weight") or name.endswith("ln_2.weight") or name in ("gpt.ln_f.weight", "final_norm.weight"):
+                p.fill_(1.0)
+            elif name in ("text_head.weight", "mel_head.weight"):
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+            elif name in ("text_head.bias", "mel_head.bias"):
+                bound = 1.0 / math.sqrt(self.model_dim)
+                p.uniform_(-bound, bound)
+            elif name.endswith(".bias"):
+                p.zero_()
+            elif name.endswith("c_proj.weight"):
+                p.normal_(0.0, 0.02 / math.sqrt(2 * L_))
+            else:
+                p.normal_(0.0, 0.02)
+
+    # ------------------------------------------------------------------ flat-buffer plumbing
+    def _apply(self, fn, recurse=True):
+        """`.to()/.cuda()` move the ONE flat buffer and re-point every parameter at its slice."""
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise L.TTTSError("UnifiedVoice keeps fp32 master parameters; mixed precision is handled inside the kernels")
+        if new_flat is not self._flat:
+            self._flat = new_flat
+            for name, v in self._layout.views(self._flat).items():
+                p = self._params_by_name[name]
+                p.data = v
+                p.grad = None
+            self._eng = None
+            self._gviews = None
+        return self
+
+    def __deepcopy__(self, memo):
+        # parameters are views of one flat buffer: rebuild rather than copying tensor by tensor (ema copy, train.py:64-69)
+        new = UnifiedVoice(**self._ctor_kwargs)
+        new.to(self._flat.device)
+        with torch.no_grad():
+            new._flat.copy_(self._flat)
+        for pn, po in zip(new.parameters(), self.parameters()):
+            pn.requires_grad_(po.requires_grad)
+        new.train(self.training)
+        new.dropout_p = self.dropout_p
+        return new
+
+    def _engine(self):
+        if self._eng is None:
+            if not self._flat.is_cuda:
+                raise L.TTTSError("UnifiedVoice runs on sm_100a only: move the module to a CUDA device (no CPU fallback)")
+            with torch.cuda.device(self._flat.device):
+                self._eng = E.Engine(self._cfg, self._flat)
+        return self._eng
+
+    def _grad_views(self):
+        if self._gviews is None:
+            gv = self._layout.views(self._engine().grads)
+            self._gviews = [gv[n] for n in self._param_names]
+        return self._gviews
+
+    def _after_backward(self):
+        pass   # hook point for the data-parallel wrapper (ttts_b200.gpt.train)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        # older HF versions stored causal-mask buffers in the checkpoint; they carry no information
+        sd = {k: v for k, v in state_dict.items() if not (k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"))}
+        return super().load_state_dict(sd, strict=strict)
+
+    # ------------------------------------------------------------------ reference helpers kept for API parity
+    def build_aligned_inputs_and_targets(self, input, start_token, stop_token):
+        inp = torch.nn.functional.pad(input, (1, 0), value=start_token)
+        tar = torch.nn.functional.pad(input, (0, 1), value=stop_token)
+        return inp, tar
+
+    def set_mel_padding(self, mel_input_tokens, wav_lengths):
+        """ttts/gpt/model.py:402-414 (vectorised; in place on the caller's tensor like the reference)."""
+        mel_lengths = torch.div(wav_lengths, self.mel_length_compression, rounding_mode="trunc")
+        pos = torch.arange(mel_input_tokens.shape[-1], device=mel_input_tokens.device)[None, :]
+        mel_input_tokens.masked_fill_(pos >= (mel_lengths[:, None] + 1), self.stop_mel_token)
+        return mel_input_tokens
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, text_inputs, text_lengths, mel_codes, wav_lengths, types=None, text_first=True, raw_mels=None,
+                return_attentions=False, return_latent=False, clip_inputs=True):
+        if not text_first or raw_mels is not None or return_attentions:
+            raise NotImplementedError("only the text_first / mel-code training path of the reference is implemented")
+        L.require_cuda(text_inputs, text_lengths, mel_codes, wav_lengths)
+        if types is not None:
+            text_inputs = text_inputs * (1 + types).unsqueeze(-1)
+        TL, CL = text_inputs.shape[1], mel_codes.shape[1]
+        if clip_inputs:
+            # same host sync as the reference (ttts/gpt/model.py:477-480)
+            TL = min(TL, int(text_lengths.max()))
+            CL = min(CL, int(wav_lengths.max()) // self.mel_length_compression)
+        if TL + 2 > self.max_text_tokens + 2 or CL + 2 > self.max_mel_tokens + 2:
+            raise IndexError("sequence longer than the position tables (max_text_tokens=%d, max_mel_tokens=%d)"
+                             % (self.max_text_tokens, self.max_mel_tokens))
+        text_inputs = text_inputs if (text_inputs.dtype == torch.int64 and text_inputs.stride(-1) == 1) else text_inputs.long().contiguous()
+        if mel_codes.dtype != torch.int64 or mel_codes.stride(-1) != 1:
+            raise TypeError("mel_codes must be a contiguous int64 tensor (it is padded in place, like the reference)")
+        wav_lengths = wav_lengths.long().contiguous()
+        eng = self._engine()
+        if return_latent:
+            with torch.no_grad():
+                eng.refresh_shadow(force=not eng.trust_version)
+                eng.forward(text_inputs, mel_codes, wav_lengths, TL, CL, save=False, want_latent=True)
+                B = text_inputs.shape[0]
+                T = TL + CL + 4
+                lat = eng.ws_view(E.WS_LATENT, B, TL, CL, False, torch.float32, (B, T, self.model_dim))
+                return lat[:, -(CL + 2):][:, :-2].clone()
+        drop_p = self.dropout_p if self.training else 0.0
+        self._seed_counter += 1
+        seed = (self._base_seed * 6364136223846793005 + self._seed_counter * 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        params = [self._params_by_name[n] for n in self._param_names]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        loss_text, loss_mel, mel_logits = _GPTStepFn.apply(self, text_inputs, mel_codes, wav_lengths, TL, CL, drop_p, seed, need_grad, *params)
+        return loss_text, loss_mel, mel_logits.permute(0, 2, 1)
+
+    def inference_speech(self, *a, **k):
+        raise NotImplementedError("autoregressive sampling (ttts/gpt/model.py:533-562) is out of scope of the training hot path")
