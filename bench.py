@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- GPT-step audio-frames/sec of the UnifiedVoice train step (BASELINE.json north_star).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a CUDA engine)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload (config.workload "cfg3"): UnifiedVoice 24L / d1024 / 16 heads, per-GPU batch 32, text 128, codes 1024 (T = 1156),
+bf16 tensor-core operands with fp32 accumulate / residual / optimizer, dropout 0.1 active (training mode), synthetic tokens,
+random-init weights.  A step = forward + backward + gradient all-reduce (N > 1) + global-norm clip + AdamW.
+One "audio frame" = one VQ code position: frames/step = N * 32 * 1024.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same step driven through the
+public `Trainer.train_step` with pinned HOST batches (H2D copies + loss D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(layers=24, model_dim=1024, heads=16, B=32, TL=128, CL=1024),
+    "cfg2": dict(layers=12, model_dim=512, heads=8, B=8, TL=128, CL=512),
+}
+GPT_KW = dict(max_text_tokens=800, max_mel_tokens=1600, number_text_tokens=256, start_text_token=255, number_mel_codes=1026,
+              start_mel_token=1024, stop_mel_token=1025)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_step_time(wl, B, steps, warm, threads):
+    """The reference's CPU path (oracle port, fp32): fwd + bwd + clip + AdamW on a bounded sample (batch B of the workload)."""
+    import torch
+    from oracle import gpt_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.default_config(layers=wl["layers"], model_dim=wl["model_dim"], heads=wl["heads"])
+    params = O.init_params(cfg, seed=0)
+    state = {}
+    text, tl, codes, wlens = O.synthetic_batch(B, wl["TL"], wl["CL"], seed=1234)
+    times = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        _, _, _, grads = O.loss_and_grads(params, cfg, text, tl, codes, wlens)
+        O.clip_and_adamw(params, grads, state, O.warmup_lr(i), i + 1)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference(args, wl):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    Bs = 1
+    t = cpu_oracle_step_time(wl, Bs, args.steps, min(args.warmup, 1), threads)
+    fps = Bs * wl["CL"] / t
+    out = {
+        "impl": "reference", "metric": "gpt_step_audio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d" % (wl["layers"], wl["model_dim"]),
+                                       "per_gpu_batch": wl["B"], "text_len": wl["TL"], "code_len": wl["CL"], "sample_batch": Bs},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "oracle port (fp32, no grad-ckpt) of the reference step at batch %d of the %s shape, %d timed steps" % (Bs, args.workload, args.steps)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ttts_b200 import _lib as L
+    from ttts_b200.gpt.model import UnifiedVoice
+    from ttts_b200.gpt.train import FusedStep, Trainer
+    from ttts_b200.gpt import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+
+    cfg_json = {"train": {"train_steps": 10 ** 9, "val_freq": 10 ** 9, "save_freq": 10 ** 9, "keep_ckpts": 0, "lr": 1e-4, "logs_folder": "/tmp/ttts_b200_logs",
+                          "text_weight": 0.01, "mel_weight": 1, "accumulate_num": 1},
+                "gpt": dict(GPT_KW, layers=wl["layers"], model_dim=wl["model_dim"], heads=wl["heads"])}
+    B, TL, CL = wl["B"], wl["TL"], wl["CL"]
+    torch.manual_seed(0)
+
+    # host batches (pinned) -- a few distinct ones, rank-dependent
+    def host_batch(i):
+        text, tl, codes, wlens = synth.synthetic_batch(B, TL, CL, seed=1234 + 1000 * rank + i)
+        return {"padded_text": text.pin_memory(), "text_lengths": tl.pin_memory(), "padded_qmel": codes.pin_memory(), "wav_lens": wlens.pin_memory()}
+    batches = [host_batch(i) for i in range(4)]
+    trainer = Trainer(cfg=cfg_json, dataloader=[batches[0]], device=dev, logs=False)
+    model = trainer.gpt
+    model.train()
+    model.dropout_p = args.dropout
+    fused = trainer.fused
+    dev_batches = [[b[k].to(dev) for k in ("padded_text", "text_lengths", "padded_qmel", "wav_lens")] for b in batches]
+    lib = L.lib()
+    lib.ttts_launch_count.restype = __import__("ctypes").c_ulonglong
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timed region ----------------
+    for i in range(warm):
+        fused(*dev_batches[i % 4], clip_inputs=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    import ctypes
+    lib.ttts_prof_gemm_enable(1)
+    l0 = lib.ttts_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        fused(*dev_batches[i % 4], clip_inputs=False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    l1 = lib.ttts_launch_count()
+    gms, gfl, gn = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.ttts_prof_gemm_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gn))
+    lib.ttts_prof_gemm_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    frames_step = world * B * CL
+    value = frames_step / (ms_step * 1e-3)
+
+    # ---------------- end-to-end through the public Trainer API, host batches ----------------
+    e2e = None
+    if not args.no_e2e:
+        for i in range(2):
+            trainer.train_step(batches[i % 4])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            trainer.train_step(batches[i % 4])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item() / args.steps
+        h2d = sum(v.numel() * v.element_size() for v in batches[0].values())
+        e2e = {"value": frames_step / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    fl_step = synth.flops_per_step(wl["layers"], wl["model_dim"], B, TL, CL)     # per GPU, algorithmic
+    gemm_tflops = (gfl.value / (gms.value * 1e-3)) / 1e12 if gms.value > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05.mma, TMA, TMEM)",
+        "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None, "traffic": None,
+        "peak_source": pk["src"] + " (sustained bf16 cuBLAS, MEASURED_PEAKS.json)",
+        "launches": int(gn.value), "kernel_ms_per_step": gms.value / args.steps,
+        "kernel_share_of_step": (gms.value / args.steps) / ms_step,
+        "step_tflops": fl_step / (ms_step * 1e-3) / 1e12, "step_frac": fl_step / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"],
+    }
+    out = {
+        "metric": "gpt_step_audio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d/H%d" % (wl["layers"], wl["model_dim"], wl["heads"]), "per_gpu_batch": B,
+                   "global_batch": B * world, "text_len": TL, "code_len": CL, "seq_len": TL + CL + 4, "parallelism": "dp%d" % world,
+                   "dropout": args.dropout, "l2": "working set (~33 GB activations + 5 GB optimizer state per step) far exceeds the 126 MB L2; no flush needed",
+                   "step": "fwd+bwd+allreduce+clip+AdamW"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(l1 - l0), "roofline": roofline,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        tcpu = cpu_oracle_step_time(wl, 1, 1, 0, threads)
+        out["cpu_baseline"] = {"value": CL / tcpu, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": "1 step (fwd+bwd+clip+AdamW, fp32, no grad-ckpt) of the oracle port at batch 1 of the %s shape" % args.workload}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,11 @@ int ttts_version(void);
 const char* ttts_last_error(void);
 /* 1 if the current device can run the sm_100a kernels */
 int ttts_device_ok(void);
+/* number of kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+unsigned long long ttts_launch_count(void);
+/* bracket every tcgen05 GEMM launch with CUDA events on its stream (bench.py's live roofline measurement) */
+void ttts_prof_gemm_enable(int on);
+int ttts_prof_gemm_read(double* ms_total, double* flops_total, long long* launches);
 
 /* --------------------------------------------------------------------------------------------
  * GEMM on the 5th-gen tensor cores (tcgen05.mma, TMA-fed, TMEM accumulators).
@@ -174,6 +179,38 @@ int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* target
                 float* loss_out, void* stream);
 int ttts_ce_bwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, const float* row_lse,
                 const float* gscale, float weight, void* dlogits, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * VQ-VAE encode front end
+ * ------------------------------------------------------------------------------------------ */
+/* RVQ (n_q=1) lookup: EuclideanCodebook.quantize/forward, ttts/vqvae/core_vq.py:174-230, VectorQuantization.forward 303-322.
+ *   x: fp32, layout_bdn=1 -> [B, D, Nn] (the module's "b d n"), vector v = b*Nn+n ; layout_bdn=0 -> [B, D] rows (Nn ignored)
+ *   codes: int64 [N] ; quantized (optional): same layout as x, = E[code] or the straight-through value x + (q - x)
+ *   commit_out (optional): mean((q - x)^2) ; hist [K], embed_sum [K,D] (optional, must be zeroed): EMA statistics
+ *   workspace: ttts_vq_workspace_floats(N, K) floats */
+int64_t ttts_vq_workspace_floats(int32_t N, int32_t K);
+int ttts_vq_forward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t layout_bdn, const float* embed, int32_t K, int64_t* codes,
+                    float* quantized, int32_t straight_through, float* commit_out, float* hist, float* embed_sum, float* workspace,
+                    void* stream);
+/* cluster_size/embed_avg EMA + Laplace-smoothed renormalisation of embed (core_vq.py:217-228); scratch1: 1 float */
+int ttts_vq_ema_update(float* embed, float* embed_avg, float* cluster_size, const float* hist, const float* embed_sum, int32_t K,
+                       int32_t D, float decay, float eps, float* scratch1, void* stream);
+/* dx = dquantized + dcommit * 2 (x - q) / (N*D)  (dquantized / dcommit may be NULL) */
+int ttts_vq_backward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t layout_bdn, const float* embed, const int64_t* codes,
+                     const float* dquantized, const float* dcommit, float* dx, void* stream);
+
+/* Framed rFFT + magnitude (+ sparse mel + log) : spectrogram_torch / spec_to_mel_torch / mel_spectrogram_torch
+ * (ttts/utils/data_utils.py:52-156) and MelSpectrogramFeatures (ttts/vocoder/feature_extractors.py:28-49).
+ *   wav [B, L] fp32 ; frames are taken from the reflect-padded signal (pad samples each side), hop apart, n_fft long
+ *   window [n_fft] ; twiddle [n_fft/2+1] complex (re,im) = exp(-2 pi i k / n_fft)
+ *   spec_out (optional) [B, n_fft/2+1, F] = sqrt(re^2 + im^2 + eps_inside)
+ *   mel_out (optional) [B, n_mels, F] = log(max(basis @ spec, log_floor)); the basis is sparse: band m covers bins
+ *   band_lo[m] .. band_lo[m] + (band_off[m+1]-band_off[m]) with weights band_w[band_off[m] ..] */
+int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t pad, const float* window,
+                  const float* twiddle, float eps_inside, float* spec_out, int32_t n_mels, const int32_t* band_lo,
+                  const int32_t* band_off, const float* band_w, float log_floor, float* mel_out, int32_t n_frames, void* stream);
+int ttts_logmel(const float* spec, int32_t B, int32_t bins, int32_t F, int32_t n_mels, const int32_t* band_lo, const int32_t* band_off,
+                const float* band_w, float log_floor, float* mel_out, void* stream);
 
 #ifdef __cplusplus
 }

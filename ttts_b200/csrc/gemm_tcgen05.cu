@@ -331,7 +331,9 @@ static int launch_gemm(const ttts_gemm_args& a, const GemmParams& p, int grid, c
         TTTS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
         attr_set = true;
     }
+    prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
     kern<<<grid, GEMM_THREADS, S::kTotalBytes, stream>>>(tmA, tmB, p);
+    prof_gemm_end(stream);
     TTTS_LAUNCH_CHECK("gemm_bf16_kernel");
     return TTTS_OK;
 }

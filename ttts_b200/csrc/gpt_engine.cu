@@ -173,7 +173,7 @@ static int validate_io(const ttts_gpt_io* io, Workspace& w, ParamLayout& P) {
     TTTS_CHECK_ARG(io->params && io->params16 && io->workspace, "gpt: null buffer");
     w = carve(io->cfg, io->B, io->TL, io->CL, io->save_acts != 0);
     TTTS_CHECK_ARG(io->workspace_bytes >= w.total, "gpt: workspace too small (%lld < %lld)", (long long)io->workspace_bytes, (long long)w.total);
-    TTTS_CHECK_ARG(((uintptr_t)io->workspace & 1023) == 0, "gpt: workspace must be 1024B aligned");
+    TTTS_CHECK_ARG(((uintptr_t)io->workspace & 255) == 0, "gpt: workspace must be 256B aligned");
     P = make_layout(io->cfg);
     return TTTS_OK;
 }

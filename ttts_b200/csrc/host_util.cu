@@ -3,6 +3,8 @@
 #include <string.h>
 #include <mutex>
 #include <unordered_map>
+#include <atomic>
+#include <vector>
 
 namespace ttts {
 
@@ -18,6 +20,28 @@ void set_error(const char* fmt, ...) {
 int fail_cuda(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return TTTS_ERR_CUDA;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_prof_recs;
+static size_t g_prof_used = 0;
+bool prof_enabled() { return g_prof; }
+void prof_gemm_begin(cudaStream_t st, double flops) {
+    if (!g_prof) return;
+    if (g_prof_used == g_prof_recs.size()) {
+        ProfRec r; cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); r.flops = 0; g_prof_recs.push_back(r);
+    }
+    g_prof_recs[g_prof_used].flops = flops;
+    cudaEventRecord(g_prof_recs[g_prof_used].e0, st);
+}
+void prof_gemm_end(cudaStream_t st) {
+    if (!g_prof) return;
+    cudaEventRecord(g_prof_recs[g_prof_used].e1, st);
+    ++g_prof_used;
 }
 
 int num_sms() {
@@ -108,6 +132,25 @@ extern "C" {
 
 int ttts_version(void) { return 100; }
 const char* ttts_last_error(void) { return ttts::g_err; }
+
+unsigned long long ttts_launch_count(void) { return ttts::g_launches.load(); }
+
+void ttts_prof_gemm_enable(int on) { ttts::g_prof = on != 0; if (on) ttts::g_prof_used = 0; }
+/* synchronises the device, sums the bracketed GEMM launches since enable: total ms, total FLOPs, launch count */
+int ttts_prof_gemm_read(double* ms_total, double* flops_total, long long* launches) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return ttts::fail_cuda(e, "prof sync");
+    double ms = 0, fl = 0;
+    for (size_t i = 0; i < ttts::g_prof_used; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ttts::g_prof_recs[i].e0, ttts::g_prof_recs[i].e1);
+        ms += t; fl += ttts::g_prof_recs[i].flops;
+    }
+    if (ms_total) *ms_total = ms;
+    if (flops_total) *flops_total = fl;
+    if (launches) *launches = (long long)ttts::g_prof_used;
+    return TTTS_OK;
+}
 
 int ttts_device_ok(void) {
     int dev = 0, major = 0;

@@ -14,6 +14,11 @@ namespace ttts {
 void set_error(const char* fmt, ...);
 int fail_cuda(cudaError_t e, const char* what);
 int num_sms();
+void count_launch();
+// GEMM profiling (bench.py roofline): when enabled, every GEMM launch is bracketed by CUDA events on its stream
+bool prof_enabled();
+void prof_gemm_begin(cudaStream_t st, double flops);
+void prof_gemm_end(cudaStream_t st);
 
 #define TTTS_CHECK_ARG(cond, ...)                    \
     do {                                             \
@@ -33,6 +38,7 @@ int num_sms();
     do {                                                          \
         cudaError_t _e = cudaGetLastError();                      \
         if (_e != cudaSuccess) return ::ttts::fail_cuda(_e, name); \
+        ::ttts::count_launch();                                   \
     } while (0)
 
 // 2-D bf16/fp32 tiled tensor map with 128B swizzle (or none).
