@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--profile-run", action="store_true", help="for ncu runs only: honour --warmup < 3 (numbers printed are not bench values)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -160,7 +161,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    warm = max(args.warmup, 3)
+    warm = args.warmup if args.profile_run else max(args.warmup, 3)
 
     cfg_json = {"train": {"train_steps": 10 ** 9, "val_freq": 10 ** 9, "save_freq": 10 ** 9, "keep_ckpts": 0, "lr": 1e-4, "logs_folder": "/tmp/ttts_b200_logs",
                           "text_weight": 0.01, "mel_weight": 1, "accumulate_num": 1},
