@@ -75,7 +75,7 @@ def test_oracle_same_inputs(layers, d, heads, B, TL, CL):
     lt16, lm16, logits16 = O.forward(params, cfg, batch[0], batch[1], batch[2].clone(), batch[3], emulate_bf16=True)
     with torch.no_grad():
         _, glm, glogits = m(*[t.cuda() for t in batch])
-    assert abs(glm.item() - lm16.item()) < 1e-3 and rel(glogits, logits16) < 8e-3
+    assert abs(glm.item() - lm16.item()) < 1e-3 and rel(glogits, logits16) < 1.2e-2
 
 
 def test_gradient_accumulation_and_zero_grad_paths():

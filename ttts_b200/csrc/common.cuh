@@ -54,6 +54,22 @@ TTTS_DEVICE float gelu_new_grad_f(float x) {
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// Same functions on the SFU (tanh.approx.f32, rel. error ~2^-11): used in the GEMM epilogues, whose results are rounded to
+// bf16 (rel. 2^-9) anyway; the exact versions above stay for fp32 consumers.
+TTTS_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+TTTS_DEVICE float gelu_new_fast(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float u = k0 * x * fmaf(k1 * x, x, 1.0f);
+    return 0.5f * x * (1.0f + tanh_fast(u));
+}
+TTTS_DEVICE float gelu_new_grad_fast(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float x2 = x * x;
+    const float t = tanh_fast(k0 * x * fmaf(k1, x2, 1.0f));
+    const float du = k0 * fmaf(3.0f * k1, x2, 1.0f);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
 // Counter-based dropout generator: one 64-bit mix -> 4 keep-decisions of 16 bits each.
 // keep iff u16 >= thresh16 where thresh16 = round(p*65536).
 TTTS_DEVICE uint64_t mix64(uint64_t z) {
@@ -141,6 +157,50 @@ TTTS_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 TTTS_DEVICE void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
+// ----------------------------------------------------------------------------------------
+// thread-block clusters / CTA pairs (cta_group::2)
+// ----------------------------------------------------------------------------------------
+TTTS_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+TTTS_DEVICE void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+TTTS_DEVICE void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+TTTS_DEVICE void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+// In a CTA pair the shared::cluster address of the same offset in the EVEN (leader) CTA is the local address with bit 24
+// cleared (the convention CUTLASS' Sm100MmaPeerBitMask encodes).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// arrive on the barrier at the same offset in the leader CTA (valid from either CTA of the pair)
+TTTS_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's smem, completion bytes are signalled on the LEADER CTA's barrier
+TTTS_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+TTTS_DEVICE void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {  // one whole warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+TTTS_DEVICE void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA) * B (N/2 rows from each CTA); issued by the leader CTA only
+TTTS_DEVICE void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit: arrive (once) on the barrier at this offset in BOTH CTAs of the pair when the issued MMAs have completed
+TTTS_DEVICE void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread).

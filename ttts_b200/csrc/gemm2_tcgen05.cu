@@ -1,0 +1,268 @@
+// CTA-pair (cta_group::2) variant of the persistent tcgen05 GEMM: a cluster of two CTAs on one TPC computes a 256x256
+// output tile.  Each CTA TMA-loads its own 128 rows of A and HALF of the B tile (128 of the 256 n-rows); the leader CTA
+// issues tcgen05.mma.cta_group::2 (M=256, N=256, K=16) which reads A/B from both CTAs' shared memory and writes 128x256
+// fp32 accumulators into each CTA's TMEM.  Versus the 1-CTA kernel this cuts L2->SM and shared-memory operand traffic per
+// FLOP by 1/3 (32 KB instead of 48 KB per 128x256x64 MAC block per SM), which is what limits the 1-CTA kernel
+// (profiles/r1_notes.md).
+//
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM alloc, warps 2-9 =
+// epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 2:
+// leader's arrive.expect_tx + the peer's remote arrive; both CTAs' TMA bytes complete_tx there), empty[] / tmem_full[] are
+// per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 256 epilogue threads).
+#include "common.cuh"
+#include "host_util.h"
+#include "gemm_epilogue.cuh"
+#include "kernels.h"
+
+namespace ttts {
+
+constexpr int G2_BM = 128;          // rows per CTA (256 per pair)
+constexpr int G2_BN = 256;          // columns per pair tile
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_THREADS = 320;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB (this CTA's half)
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_SMEM_BYTES = G2_BAR_OFFSET + 256 + 2 * 256 * 4 + 1024;   // barriers + bias staging + alignment slack
+
+TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n_blk, int& split) {
+    const int tiles = p.num_m_blocks * p.num_n_blocks;      // num_m_blocks counts 256-row pairs here
+    split = item / tiles;
+    const int t = item - split * tiles;
+    const int group_size = p.group_m * p.num_n_blocks;
+    const int g = t / group_size;
+    const int r = t - g * group_size;
+    const int m_first = g * p.group_m;
+    const int gm = min(p.group_m, p.num_m_blocks - m_first);
+    n_blk = r / gm;
+    m_pair = m_first + (r - n_blk * gm);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + G2_STAGES;
+    uint64_t* tfull_bar = empty_bar + G2_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int total_items = p.num_m_blocks * p.num_n_blocks * p.split_k;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 512); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer (both CTAs) =================
+            int stage = 0; uint32_t phase = 0;
+            for (int item = cluster_id; item < total_items; item += num_clusters) {
+                int m_pair, n_blk, split;
+                decode_item2(p, item, m_pair, n_blk, split);
+                const int m0 = m_pair * (2 * G2_BM) + (int)rank * G2_BM;
+                const int n0 = n_blk * G2_BN + (int)rank * (G2_BN / 2);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+                    uint8_t* sb = sa + G2_A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    else mbar_arrive_leader(&full_bar[stage]);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < G2_BM / 64; ++j) tma_load_2d_2sm(sa + j * (G2_BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * G2_BK);
+                    } else {
+                        tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * G2_BK, m0);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < G2_BN / 128; ++j) tma_load_2d_2sm(sb + j * (G2_BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * G2_BK);
+                    } else {
+                        tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * G2_BK, n0);
+                    }
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ================= MMA issuer (leader CTA only) =================
+            constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, G2_BN, A_MN, B_MN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+                int m_pair, n_blk, split;
+                decode_item2(p, item, m_pair, n_blk, split);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * G2_BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+                    const uint32_t sb = sa + G2_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < G2_BK / 16; ++k) {
+                        const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull_bar[as]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        // ================= epilogue (both CTAs, 8 warps) =================
+        // Software-pipelined: the tile's bias is staged in smem and the first chunk's residual / pre-activation loads are
+        // issued BEFORE waiting for the accumulator (overlapping the main loop); inside the tile the TMEM load and the
+        // global prefetch of chunk c+1 are in flight while chunk c is processed; TMEM is released right after the last load.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
+        float* sbias_all = reinterpret_cast<float*>(smem + G2_BAR_OFFSET + 256);   // [2][256]
+        int it = 0;
+        for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+            int m_pair, n_blk, split;
+            decode_item2(p, item, m_pair, n_blk, split);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int n0 = n_blk * G2_BN;
+            {
+                const int c = n0 + et;
+                sbias_all[as * 256 + et] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int row = m_pair * (2 * G2_BM) + (int)rank * G2_BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
+            const int c0 = half * 4;
+            EpiAux x;
+            epi_prefetch(p, row, n0 + c0 * 32, x);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + c0 * 32, r);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = c0 + cc;
+                tmem_ld_wait();
+                uint32_t rc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rc[j] = r[j];
+                const EpiAux xc = x;
+                if (cc < 3) {
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + (c + 1) * 32, r);
+                    epi_prefetch(p, row, n0 + (c + 1) * 32, x);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive_leader(&tempty_bar[as]);       // accumulator stage drained: the MMA warp may reuse it
+                }
+                epi_apply(p, row, n0 + c * 32, rc, sbias_all + as * 256 + c * 32, xc);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // the peer may still be reading this CTA's smem / arriving on its barriers until here
+    tc_fence_after();
+    if (warp == 1) { __syncwarp(); tmem_dealloc_2sm(tmem_base, 512); }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p, int grid, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (A_MN) rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, G2_BK, true);
+    else      rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, G2_BK, G2_BM, true);
+    if (rc) return rc;
+    if (B_MN) rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
+    else      rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, G2_BK, G2_BN / 2, true);
+    if (rc) return rc;
+    auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TTTS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        attr_set = true;
+    }
+    prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
+    kern<<<grid, G2_THREADS, G2_SMEM_BYTES, stream>>>(tmA, tmB, p);
+    prof_gemm_end(stream);
+    TTTS_LAUNCH_CHECK("gemm2_bf16_kernel");
+    return TTTS_OK;
+}
+
+// caller (gemm_bf16) has validated the arguments
+int gemm2_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
+    GemmParams p;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.num_m_blocks = (a.M + 2 * G2_BM - 1) / (2 * G2_BM);
+    p.num_n_blocks = (a.N + G2_BN - 1) / G2_BN;
+    const int clusters = num_sms() / 2;
+    p.group_m = clusters / p.num_n_blocks;
+    if (p.group_m < 1) p.group_m = 1;
+    if (p.group_m > p.num_m_blocks) p.group_m = p.num_m_blocks;
+    p.num_k_blocks = (a.K + G2_BK - 1) / G2_BK;
+    int split = a.split_k < 1 ? 1 : a.split_k;
+    if (split > p.num_k_blocks) split = p.num_k_blocks;
+    p.kb_per_split = (p.num_k_blocks + split - 1) / split;
+    p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.epi = a.epi;
+    p.out = a.out; p.ldo = a.ldo; p.bias = a.bias;
+    p.aux = a.aux; p.ldaux = a.ldaux; p.aux_out = a.aux_out; p.ldaux_out = a.ldaux_out;
+    p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
+    const int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
+    const int grid = 2 * (items < clusters ? items : clusters);
+    if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false>(a, p, grid, stream);
+    if (!a.a_mn && a.b_mn) return launch_gemm2<false, true>(a, p, grid, stream);
+    if (a.a_mn && a.b_mn) return launch_gemm2<true, true>(a, p, grid, stream);
+    return launch_gemm2<true, false>(a, p, grid, stream);
+}
+
+int pick_split_k2(int M, int N, int K) {
+    const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+    const int kblocks = (K + G2_BK - 1) / G2_BK;
+    const int clusters = num_sms() / 2;
+    int best = 1; double best_eff = -1.0;
+    for (int s = 1; s <= 32 && s <= kblocks; ++s) {
+        if (kblocks / s < 8 && s > 1) break;
+        const long items = (long)tiles * s;
+        const long waves = (items + clusters - 1) / clusters;
+        const double eff = (double)items / (double)(waves * clusters);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+}  // namespace ttts

@@ -10,8 +10,11 @@
 //
 // Warp roles (256 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM
 // alloc/dealloc, warps 2-3 idle, warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
+#include "gemm_epilogue.cuh"
+#include "kernels.h"
 
 namespace ttts {
 
@@ -20,17 +23,6 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
 
-struct GemmParams {
-    int M, N, K;
-    int num_m_blocks, num_n_blocks, group_m;
-    int num_k_blocks, kb_per_split, split_k;
-    int epi;
-    void* out; int ldo;
-    const float* bias;
-    const void* aux; int ldaux;
-    void* aux_out; int ldaux_out;
-    uint32_t drop_thresh16; float drop_scale; uint64_t drop_seed;
-};
 
 template <int BN>
 struct GemmSmem {
@@ -84,7 +76,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      if (lane == 0) {
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -113,7 +106,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
         int stage = 0; uint32_t phase = 0;
@@ -146,6 +142,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             umma_commit(&tfull_bar[as]);
         }
+      }
+      __syncwarp();
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int q = warp & 3;
@@ -158,7 +156,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const int row = m_blk * BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -166,142 +163,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 tmem_ld_32x32(taddr + c * 32, r);
                 tmem_ld_wait();
-                const int col0 = n_blk * BN + c * 32;
-                if (!row_ok || col0 >= p.N) continue;
-                const bool full = (col0 + 32 <= p.N);
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias != nullptr && p.epi != TTTS_EPI_F32_ADD) {
-                    if (full) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 b = __ldg(b4 + j);
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-                    }
-                }
-                switch (p.epi) {
-                case TTTS_EPI_BF16: {
-                    bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
-                    if (full) {
-                        uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
-                    }
-                } break;
-                case TTTS_EPI_GELU: {
-                    // pre = bf16(acc + bias) ; h = bf16(gelu_new(pre))   (reference: bf16 autocast, HF: modeling_gpt2.py:239-240)
-                    bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
-                    bf16* a = p.aux_out ? reinterpret_cast<bf16*>(p.aux_out) + (size_t)row * p.ldaux_out + col0 : nullptr;
-                    float h[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = bf16_round(v[j]); h[j] = gelu_new_f(v[j]); }
-                    if (full) {
-                        uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            o4[j] = make_uint4(pack_bf16(h[8 * j], h[8 * j + 1]), pack_bf16(h[8 * j + 2], h[8 * j + 3]),
-                                               pack_bf16(h[8 * j + 4], h[8 * j + 5]), pack_bf16(h[8 * j + 6], h[8 * j + 7]));
-                        if (a) {
-                            uint4* a4 = reinterpret_cast<uint4*>(a);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                a4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) { o[j] = __float2bfloat16_rn(h[j]); if (a) a[j] = __float2bfloat16_rn(v[j]); }
-                    }
-                } break;
-                case TTTS_EPI_RESID: {
-                    // x_out = x_in + dropout(bf16(acc + bias))     (HF: modeling_gpt2.py:224,282 / 242,307)
-                    const float* xin = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col0;
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-                    if (p.drop_thresh16) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            uint64_t e4 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + 4 * j4)) >> 2;
-                            uint64_t bits = dropout_bits4(p.drop_seed, e4);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                v[4 * j4 + j] = dropout_keep(bits, j, p.drop_thresh16) ? v[4 * j4 + j] * p.drop_scale : 0.f;
-                        }
-                    }
-                    if (full) {
-                        const float4* x4 = reinterpret_cast<const float4*>(xin);
-                        float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 x = x4[j];
-                            o4[j] = make_float4(x.x + v[4 * j], x.y + v[4 * j + 1], x.z + v[4 * j + 2], x.w + v[4 * j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = xin[j] + v[j];
-                    }
-                } break;
-                case TTTS_EPI_DGELU: {
-                    const bf16* pre = reinterpret_cast<const bf16*>(p.aux) + (size_t)row * p.ldaux + col0;
-                    bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
-                    if (full) {
-                        const uint4* p4 = reinterpret_cast<const uint4*>(pre);
-                        uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 pp = p4[j];
-                            uint32_t w[4] = {pp.x, pp.y, pp.z, pp.w};
-                            uint32_t ow[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                float g0 = v[8 * j + 2 * t] * gelu_new_grad_f(bf16_lo(w[t]));
-                                float g1 = v[8 * j + 2 * t + 1] * gelu_new_grad_f(bf16_hi(w[t]));
-                                ow[t] = pack_bf16(g0, g1);
-                            }
-                            o4[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j] * gelu_new_grad_f(__bfloat162float(pre[j])));
-                    }
-                } break;
-                case TTTS_EPI_F32_ADD: {
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(o + j, v[j]);
-                    }
-                } break;
-                default: {  // TTTS_EPI_F32
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-                    if (full) {
-                        float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = v[j];
-                    }
-                } break;
-                }
+                gemm_epilogue_chunk(p, row, n_blk * BN + c * 32, r);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[as]);
@@ -338,6 +200,13 @@ static int launch_gemm(const ttts_gemm_args& a, const GemmParams& p, int grid, c
     return TTTS_OK;
 }
 
+// CTA-pair kernel for everything with a full 256-wide tile; TTTS_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing).
+bool use_2cta(int M, int N) {
+    static int force1 = -1;
+    if (force1 < 0) { const char* e = getenv("TTTS_GEMM_1CTA"); force1 = (e && e[0] == '1') ? 1 : 0; }
+    return !force1 && N > 128 && M > 128;
+}
+
 int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     TTTS_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape %d %d %d", a.M, a.N, a.K);
     TTTS_CHECK_ARG(a.A && a.B && a.out, "gemm: null pointer");
@@ -353,6 +222,7 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     if (a.epi == TTTS_EPI_GELU && a.aux_out) TTTS_CHECK_ARG((a.ldaux_out * 2) % 16 == 0 && ((uintptr_t)a.aux_out & 15) == 0, "gemm: aux_out not aligned");
     if (a.bias) TTTS_CHECK_ARG(((uintptr_t)a.bias & 15) == 0, "gemm: bias not 16B aligned");
 
+    if (use_2cta(a.M, a.N)) return gemm2_bf16(a, stream);
     const int BN = (a.N > 128) ? 256 : 128;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
@@ -385,6 +255,7 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
 
 // Pick the split-K factor (1..16) that fills the SMs best for a weight-gradient GEMM.
 int pick_split_k(int M, int N, int K) {
+    if (use_2cta(M, N)) return pick_split_k2(M, N, K);
     const int BN = (N > 128) ? 256 : 128;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int kblocks = (K + BK - 1) / BK;

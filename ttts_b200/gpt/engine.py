@@ -61,7 +61,7 @@ def _setup_prototypes(lib):
     lib.ttts_gpt_backward.argtypes = [ctypes.POINTER(GptIO), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.ttts_cast_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.ttts_grad_norm.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    lib.ttts_adamw_step.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 8 + [ctypes.c_int32, ctypes.c_void_p]
+    lib.ttts_adamw_step.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 7 + [ctypes.c_int32, ctypes.c_void_p]
     lib._gpt_protos = True
 
 
