@@ -170,7 +170,9 @@ int ttts_layernorm_fwd(const float* x, const float* w1, const float* b1, const f
 int ttts_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const float* stats, const float* w1, const float* b1,
                        const float* w2, const float* g_in, float* g_out, void* g16_out, float* dw1, float* db1, float* dw2,
                        float* db2, float* dbias_next, int32_t M, int32_t d, int32_t dbl, void* stream);
-/* causal flash attention on the packed c_attn output [B*T, 3d] (HF:modeling_gpt2.py:144-226) */
+/* causal flash attention on the packed c_attn output [B*T, 3d] (HF:modeling_gpt2.py:144-226).
+ * ttts_attn_bwd scratch: ttts_attn_bwd_scratch_floats(B,T,H) floats (row dots + the fp32 dQ accumulator). */
+int64_t ttts_attn_bwd_scratch_floats(int32_t B, int32_t T, int32_t H);
 int ttts_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);
 int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_scratch, void* dqkv,
                   int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);

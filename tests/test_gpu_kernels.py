@@ -109,7 +109,7 @@ def test_attention_fwd_bwd(L, B, T, H):
     ref.backward(dout.float())
     dref = torch.cat([t.grad.transpose(1, 2).reshape(B * T, d) for t in (q, k, v)], dim=1)
     dqkv = torch.full_like(qkv, 5.0)
-    delta = torch.zeros(B * H * T, device="cuda")
+    delta = torch.zeros(B * H * T + 64 + B * T * d, device="cuda")
     L.check(lib.ttts_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta), L.ptr(dqkv), B, T, H, ctypes.c_float(0.0),
                               ctypes.c_uint64(0), L.stream_ptr()))
     for i in range(3):
@@ -143,7 +143,7 @@ def test_attention_dropout_statistics(L):
     assert rel((acc / n)[late], o0[late]) < 0.05
     # backward consistency with the same mask
     dout = (torch.randn(B * T, d, device="cuda") * 0.5).bfloat16()
-    dqkv = torch.zeros_like(qkv); delta = torch.zeros(B * H * T, device="cuda")
+    dqkv = torch.zeros_like(qkv); delta = torch.zeros(B * H * T + 64 + B * T * d, device="cuda")
     L.check(lib.ttts_attn_bwd(L.ptr(qkv), L.ptr(o1), L.ptr(dout), L.ptr(lse1), L.ptr(delta), L.ptr(dqkv), B, T, H, ctypes.c_float(0.1),
                               ctypes.c_uint64(11), L.stream_ptr()))
     direction = torch.randn_like(qkv.float())

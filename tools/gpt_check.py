@@ -47,7 +47,7 @@ def check_attention(B, T, H, drop_p=0.0):
     ref.backward(dout.float())
     dref = torch.cat([t.grad.transpose(1, 2).reshape(B * T, d) for t in (q, k, v)], dim=1)
     dqkv = torch.zeros_like(qkv)
-    delta = torch.zeros(B * H * T, device=dev)
+    delta = torch.zeros(B * H * T + 64 + B * T * d, device=dev)
     L.check(lib.ttts_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta), L.ptr(dqkv), B, T, H, ctypes.c_float(0.0),
                               ctypes.c_uint64(0), L.stream_ptr()), "attn_bwd")
     torch.cuda.synchronize()

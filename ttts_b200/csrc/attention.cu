@@ -514,9 +514,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
     }
 }
 
+// attention_tc.cu (tcgen05 path)
+bool attn_use_tc();
+int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropCfg drop, cudaStream_t st);
+int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv, int B, int T, int H, DropCfg drop,
+                cudaStream_t st);
+
+int attn_delta(const bf16* o, const bf16* dout, float* delta, int B, int T, int H, cudaStream_t st) {
+    const int total_warps = B * T * H;
+    attn_delta_kernel<<<(total_warps + 7) / 8, 256, 0, st>>>(o, dout, delta, B, T, H);
+    TTTS_LAUNCH_CHECK("attn_delta");
+    return TTTS_OK;
+}
+
 int attn_fwd(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropCfg drop, cudaStream_t st) {
     TTTS_CHECK_ARG(B > 0 && T > 0 && H > 0, "attn: bad shape");
     TTTS_CHECK_ARG((size_t)B * H <= 65535, "attn: B*H too large for grid.y");
+    if (attn_use_tc()) return attn_fwd_tc(qkv, o, lse, B, T, H, drop, st);
     dim3 grid((T + BQ - 1) / BQ, B * H);
     attn_fwd_kernel<<<grid, ATT_THREADS, 0, st>>>(qkv, o, lse, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_fwd");
@@ -527,9 +541,8 @@ int attn_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse,
              cudaStream_t st) {
     TTTS_CHECK_ARG(B > 0 && T > 0 && H > 0, "attn: bad shape");
     TTTS_CHECK_ARG((size_t)B * H <= 65535, "attn: B*H too large for grid.y");
-    const int total_warps = B * T * H;
-    attn_delta_kernel<<<(total_warps + 7) / 8, 256, 0, st>>>(o, dout, delta, B, T, H);
-    TTTS_LAUNCH_CHECK("attn_delta");
+    if (attn_use_tc()) return attn_bwd_tc(qkv, o, dout, lse, delta, dqkv, B, T, H, drop, st);
+    { int rc = attn_delta(o, dout, delta, B, T, H, st); if (rc) return rc; }
     dim3 grid((T + BQ - 1) / BQ, B * H);
     const int smem_kv = 6 * 8192 + 4 * 64 * 4;
     const int smem_q = 6 * 8192;

@@ -200,11 +200,12 @@ static int launch_gemm(const ttts_gemm_args& a, const GemmParams& p, int grid, c
     return TTTS_OK;
 }
 
-// CTA-pair kernel for everything with a full 256-wide tile; TTTS_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing).
+// The CTA-pair kernel (gemm2_tcgen05.cu) is correct but measured SLOWER than this one in round 1 (profiles/r1_notes.md), so
+// it is opt-in: TTTS_GEMM_2CTA=1.
 bool use_2cta(int M, int N) {
-    static int force1 = -1;
-    if (force1 < 0) { const char* e = getenv("TTTS_GEMM_1CTA"); force1 = (e && e[0] == '1') ? 1 : 0; }
-    return !force1 && N > 128 && M > 128;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_GEMM_2CTA"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on && N > 128 && M > 128;
 }
 
 int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {

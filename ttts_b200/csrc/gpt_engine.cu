@@ -121,7 +121,7 @@ static Workspace carve(const ttts_gpt_config& c, int B, int TL, int CL, bool sav
         w.dlog_t = put((int64_t)B * w.Tt * w.ldt * 2);
         w.dlog_m = put((int64_t)B * w.Tm * w.ldm * 2);
         w.denc = put(M * d * 2);
-        w.delta = put((int64_t)B * w.H * w.T * 4);
+        w.delta = put(((int64_t)B * w.H * w.T + 64 + M * d) * 4);     // attention bwd scratch: delta | fp32 dQ accumulator
     }
     w.total = o;
     return w;
@@ -447,6 +447,7 @@ static DropCfg user_drop(float p, uint64_t seed) {
     if (p > 0.f) { dc.thresh16 = (uint32_t)(p * 65536.0f + 0.5f); dc.scale = 1.0f / (1.0f - (float)dc.thresh16 / 65536.0f); dc.seed = seed; }
     return dc;
 }
+int64_t ttts_attn_bwd_scratch_floats(int32_t B, int32_t T, int32_t H) { return (int64_t)B * H * T + 64 + (int64_t)B * T * H * 64; }
 int ttts_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream) {
     return attn_fwd((const bf16*)qkv, (bf16*)out, lse, B, T, H, user_drop(drop_p, seed), (cudaStream_t)stream);
 }
