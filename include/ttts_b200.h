@@ -214,6 +214,26 @@ int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t
 int ttts_logmel(const float* spec, int32_t B, int32_t bins, int32_t F, int32_t n_mels, const int32_t* band_lo, const int32_t* band_off,
                 const float* band_w, float log_floor, float* mel_out, void* stream);
 
+/* fp32 Conv1d with the reference blocks' elementwise work fused (PosteriorAudioEncoder / WN / MelStyleEncoder,
+ * ttts/vqvae/vq2.py:667-745, modules.py:136-318,560-566,686-764).  x [B,Cin,Tin], w [Cout,Cin,K] (torch layout), y [B,Cout',Tout]
+ *   pre_lrelu: leaky_relu(0.1) on the input ; y = (post(conv + bias) + resid) * out_scale * mask ; accumulate: y += instead of =
+ *   post: 0 none | 1 GLU (Cout = 2C -> C channels: a * sigmoid(b)) | 2 Mish | 3 WN gate tanh(a+cond_a) * sigmoid(b+cond_b) */
+int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                    int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                    const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream);
+/* torch weight_norm (dim 0): w[co,:] = g[co] * v[co,:] / ||v[co,:]|| */
+int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream);
+/* Activation1d(SnakeBeta(alpha_logscale)) : 2x kaiser-sinc upsample, x + sin^2(e^a x)/e^b, 2x low-pass downsample
+ * (alias_free_torch/act.py:8-28, activations.py:62-119); filt12 = kaiser_sinc_filter1d(0.25, 0.3, 12) */
+int ttts_snake_aa(const float* x, const float* log_alpha, const float* log_beta, const float* filt12, float* y, int32_t B, int32_t C, int32_t T,
+                  void* stream);
+/* MelStyleEncoder pieces: small masked multi-head attention over T <= 64 frames ([B,C,T] channel-major), masked temporal mean */
+int ttts_mha_small(const float* q, const float* k, const float* v, const int64_t* lens, float* out, int32_t B, int32_t C, int32_t T, int32_t heads,
+                   float temperature, void* stream);
+int ttts_masked_mean(const float* x, const int64_t* lens, float* y, int32_t B, int32_t C, int32_t T, void* stream);
+/* z = (m + eps * exp(logs)) * mask with stats = [B, 2C, T] (m | logs)  (vq2.py:742-744; eps NULL = 0) */
+int ttts_posterior_sample(const float* stats, const float* eps, const float* mask, float* z, int32_t B, int32_t C, int32_t T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,14 +148,75 @@ def mel_case():
     print("mel ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), spec.shape, mel.shape, feats.shape)
 
 
+def encoder_case():
+    """Encode half of SynthesizerTrn with the REAL reference modules (vq2.py:826-836, 843-852): MelStyleEncoder, PosteriorAudioEncoder,
+    proj, quantizer.  Weights come from oracle.encoder_oracle.init_params (numpy-seeded) through load_state_dict."""
+    from oracle import encoder_oracle as EO
+    from ttts.vqvae import modules
+    from ttts.vqvae.vq2 import PosteriorAudioEncoder
+    from ttts.vqvae.quantize import ResidualVectorQuantizer
+    from ttts.utils.data_utils import spectrogram_torch
+
+    class Half(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc_p = PosteriorAudioEncoder(1025, 192, 192, 5, 1, 16, gin_channels=512)
+            self.ref_enc = modules.MelStyleEncoder(1025, style_vector_dim=512)
+            self.quantizer = ResidualVectorQuantizer(dimension=192, n_q=1, bins=1024)
+            self.proj = torch.nn.Conv1d(192, 192, 2, stride=2)
+
+    net = Half().eval()
+    P = EO.init_params(seed=5)
+    sd = net.state_dict()
+    learn = {k for k in sd if not k.startswith("quantizer.") and not k.endswith(".filter")}
+    assert learn == set(P.keys()), sorted(learn ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P, strict=False)
+    rs = np.random.RandomState(11)
+    E = rs.standard_normal((1024, 192)).astype(np.float32)
+    cb = net.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(torch.tensor(E)); cb.embed_avg.copy_(torch.tensor(E)); cb.cluster_size.fill_(10); cb.inited.fill_(1)
+    g = torch.Generator().manual_seed(77)
+    wav = torch.clamp(0.1 * torch.randn(3, 23040, generator=g), -1, 1)
+    lengths = torch.tensor([36, 30, 17])
+    eps = torch.randn(3, 192, 36, generator=g)
+    spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
+    y_mask = (torch.arange(36)[None, :] < lengths[:, None]).float().unsqueeze(1)
+    with torch.no_grad():
+        ge = net.ref_enc(spec * y_mask, y_mask)
+        torch.manual_seed(0)
+        _, m, logs = net.enc_p(spec, wav.unsqueeze(1), y_mask, g=ge)
+        z = (m + eps * torch.exp(logs)) * y_mask                      # vq2.py:744 with the noise fixed
+        x = net.proj(z)
+        quantized, codes, commit, _ = net.quantizer(x, layers=[0])
+        # intermediate anchors for bring-up
+        a = net.enc_p.down_pre(wav.unsqueeze(1))
+        a1 = net.enc_p.downs[0](a)
+        r0 = net.enc_p.resblocks[0](a1)
+    path = os.path.join(ROOT, "tests", "golden", "encoder.npz")
+    np.savez_compressed(path, wav=wav.numpy(), lengths=lengths.numpy(), eps=eps.numpy(), E=E, ge=ge.numpy(), m=m.numpy(), logs=logs.numpy(),
+                        z=z.numpy(), x=x.numpy(), codes=codes.numpy(), quantized=quantized.numpy(),
+                        down0=a1.numpy()[:, :, :64], res0=r0.numpy()[:, :, :64],
+                        filt=net.enc_p.activation_post.upsample.filter.numpy().reshape(-1))
+    print("encoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "codes", codes.shape, codes.flatten()[:8].tolist())
+
+
 if __name__ == "__main__":
     import math
     torch.manual_seed(0)
     torch.set_num_threads(8)
     gm = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        encoder_case()
+        sys.exit(0)
     tiny = dict(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
     gpt_case(gm, "gpt_tiny", tiny, B=2, TL=12, CL=24)
     # ragged: clipping + set_mel_padding paths (wav_lengths//1024+1 < CL for some rows)
     gpt_case(gm, "gpt_ragged", tiny, B=3, TL=16, CL=30, text_lengths=[9, 14, 5], wav_lengths=[20 * 1024 + 17, 27 * 1024, 6 * 1024 + 1000], seed=3)
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        encoder_case()
+        sys.exit(0)
     vq_case()
     mel_case()
+    encoder_case()

@@ -1,0 +1,96 @@
+"""GPU (-m gpu): the VQ-VAE encode front end (MelStyleEncoder + PosteriorAudioEncoder + proj + quantizer on sm_100a) against
+golden vectors from the REAL reference modules and against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import encoder_oracle as EO
+from oracle import vq_mel_oracle as V
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-20)
+
+
+@pytest.fixture(scope="module")
+def enc(golden_dir):
+    return np.load(os.path.join(golden_dir, "encoder.npz"))
+
+
+@pytest.fixture(scope="module")
+def model(enc):
+    from ttts_b200.vqvae.encoder import VQEncoder
+    m = VQEncoder()
+    P = EO.init_params(seed=5)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected
+    assert all(k.startswith("quantizer.") or k.endswith(".filter") for k in missing), missing
+    m = m.cuda().eval()
+    cb = m.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(torch.tensor(enc["E"])); cb.inited.fill_(1)
+    return m
+
+
+def test_state_dict_names_match_reference():
+    from ttts_b200.vqvae.encoder import VQEncoder
+    sd = VQEncoder().state_dict()
+    learn = {k for k in sd if not k.startswith("quantizer.") and not k.endswith(".filter")}
+    assert learn == set(EO.param_shapes().keys())
+    for k, shp in EO.param_shapes().items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    assert "enc_p.activation_post.upsample.filter" in sd and "enc_p.activation_post.downsample.lowpass.filter" in sd
+
+
+def test_conv1d_kernel_vs_torch():
+    from ttts_b200.vqvae.encoder import conv1d
+    torch.manual_seed(0)
+    for (B, Cin, T, Cout, K, stride, dil) in [(2, 1, 2300, 16, 7, 1, 1), (3, 16, 2304, 32, 16, 10, 1), (2, 96, 144, 96, 11, 1, 5), (2, 1025, 36, 192, 1, 1, 1),
+                                             (2, 192, 36, 192, 2, 2, 1)]:
+        pad = (K * dil - dil) // 2 if stride == 1 else (K - 1) // 2
+        if K == 2:
+            pad = 0
+        x = torch.randn(B, Cin, T, device="cuda"); w = torch.randn(Cout, Cin, K, device="cuda") / (Cin * K) ** 0.5; b = torch.randn(Cout, device="cuda")
+        ref = torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x, 0.1), w, b, stride=stride, dilation=dil, padding=pad)
+        got = conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=True)
+        assert got.shape == ref.shape and rel(got.cpu(), ref.cpu()) < 1e-5
+
+
+def test_encoder_vs_reference_golden(model, enc):
+    wav = torch.tensor(enc["wav"]).cuda()
+    out = model(wav, lengths=torch.tensor(enc["lengths"]).cuda(), eps=torch.tensor(enc["eps"]).cuda())
+    assert rel(out["ge"].cpu(), enc["ge"]) < 2e-4
+    assert rel(out["m"].cpu(), enc["m"]) < 5e-4
+    assert rel(out["logs"].cpu(), enc["logs"]) < 5e-4
+    assert rel(out["z"].cpu(), enc["z"]) < 5e-4
+    assert rel(out["x"].cpu(), enc["x"]) < 5e-4
+    codes = out["codes"].cpu().numpy()
+    assert codes.shape == enc["codes"].shape
+    xn = np.ascontiguousarray(enc["x"].transpose(0, 2, 1)).reshape(-1, 192)
+    margin = V.vq_margin(xn, enc["E"], enc["codes"].reshape(-1))
+    flips = codes.reshape(-1) != enc["codes"].reshape(-1)
+    assert not np.any(flips & (margin > 2e-3)), "code mismatch away from a near-tie of the reference's own encoder output"
+    assert flips.sum() <= 2
+    # given the encoder output, the lookup itself is bit-exact vs the oracle
+    xg = out["x"].cpu().numpy()
+    want = V.vq_quantize(np.ascontiguousarray(xg.transpose(0, 2, 1)).reshape(-1, 192), enc["E"])
+    assert np.array_equal(codes.reshape(-1), want)
+
+
+def test_encoder_batch64_properties(model):
+    """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    wav = torch.clamp(0.1 * torch.randn(64, 23040, device="cuda", generator=g), -1, 1)
+    o = model(wav)
+    assert o["codes"].shape == (1, 64, 18) and o["z"].shape == (64, 192, 36)
+    o1 = model(wav[5:6])
+    assert torch.allclose(o["z"][5:6], o1["z"], atol=1e-5) and torch.equal(o["codes"][:, 5:6], o1["codes"])
+    o2 = model(wav)
+    assert torch.equal(o["codes"], o2["codes"]) and torch.equal(o["z"], o2["z"])
+    lens = torch.full((64,), 36, device="cuda"); lens[3] = 20
+    o3 = model(wav, lengths=lens)
+    assert float(o3["z"][3, :, 20:].abs().max()) == 0.0

@@ -480,15 +480,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         // dK, dV of this key block (complete once the last iteration's commit has fired: dq_full of that iteration)
         const int kj = k0 + r;
-        if (kj < T) {
-            bf16* dkp = dqkv + (size_t)(row_base + kj) * ld3 + d + h * 64;
-            bf16* dvp = dkp + d;
+        bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64;
+        bf16* dvp = dkp + d;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t a[32], v[32];
-                tmem_ld_32x32(tDK + lane_off + c * 32, a);
-                tmem_ld_32x32(tDV + lane_off + c * 32, v);
-                tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+            uint32_t a[32], v[32];
+            __syncwarp();                                   // .aligned TMEM loads: whole warp, unconditionally
+            tmem_ld_32x32(tDK + lane_off + c * 32, a);
+            tmem_ld_32x32(tDV + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (kj < T) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     reinterpret_cast<uint4*>(dkp + c * 32)[g] =
@@ -498,15 +499,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                         make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
                                    pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
                 }
-            }
-        } else {
-            // keep the warp converged around the .aligned TMEM loads
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t a[32], v[32];
-                tmem_ld_32x32(tDK + lane_off + c * 32, a);
-                tmem_ld_32x32(tDV + lane_off + c * 32, v);
-                tmem_ld_wait();
             }
         }
     }

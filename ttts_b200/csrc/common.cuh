@@ -110,12 +110,15 @@ TTTS_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a kernel bug must not hang the GPU box (that is a "strike"); after ~2^28 polls
-// (seconds) we trap so the launch fails loudly instead.
+// Bounded wait: a kernel bug must not hang the GPU box (that is a "strike"); after 2 s of wall clock (%globaltimer)
+// we trap so the launch fails loudly instead.
+TTTS_DEVICE uint64_t global_timer_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 TTTS_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) { asm volatile("trap;"); }
+        if ((++spins & 0xffu) == 0 && global_timer_ns() - t0 > 2000000000ull) { asm volatile("trap;"); }
     }
 }
 

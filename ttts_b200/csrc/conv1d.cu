@@ -1,0 +1,361 @@
+// fp32 Conv1d family for the VQ-VAE encode front end (PosteriorAudioEncoder / MelStyleEncoder / WN):
+//   y[b, co, t] = bias[co] + sum_{ci, k} w[co, ci, k] * pre(x[b, ci, t*stride + k*dil - pad])
+// with the elementwise work of the reference's blocks fused in:
+//   pre   : identity | leaky_relu(0.1)                        (ResBlock1: modules.py:302-309)
+//   post  : + residual, * out_scale (accumulating the mean of 3 ResBlock1 branches, vq2.py:723-729), * time mask,
+//           GLU (x1 * sigmoid(x2), modules.py:560-566), Mish (modules.py Mish), gated tanh*sigmoid with a per-batch
+//           conditioning vector (WN: commons.fused_add_tanh_sigmoid_multiply, modules.py:196-203)
+// The reference runs these layers in fp32 (fp16_run=false, vqvae/config.json:21); to keep the downstream "bit-exact VQ
+// indices" contract meaningful this stays on the FP32 FMA pipe.  Channel counts are tiny (16..192, 1025 for the 1x1 `pre`),
+// so a register-tiled direct convolution (implicit GEMM on CUDA cores) is the right tool: CTA tile = 64 output channels x
+// 64 time steps, input window and weight slab staged through shared memory per 16-input-channel chunk, 4x4 outputs/thread.
+#include "common.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace ttts {
+
+constexpr int CV_CO = 64, CV_T = 64, CV_CI = 16, CV_THREADS = 256;
+
+struct ConvParams {
+    const float* x; const float* w; const float* bias; float* y;
+    int B, Cin, Tin, Cout, Tout, K, stride, dil, pad;
+    int pre_lrelu;            // leaky_relu(0.1) on the input
+    const float* resid;       // [B, Cout_eff, Tout] added to the result (may alias y)
+    float out_scale;          // y = (conv + resid) * out_scale
+    int accumulate;           // y += ... instead of y = ...
+    const float* mask;        // [B, Tout] multiplied in (or null)
+    int post;                 // 0 none, 1 GLU (Cout = 2*C: y[C] = a * sigmoid(b) (+resid)), 2 Mish, 3 WN gate (Cout = 2*C with cond)
+    const float* cond;        // post==3: [B, 2*C] per-batch conditioning added before tanh/sigmoid (or null)
+    int cond_ld;
+};
+
+TTTS_DEVICE float mish_f(float x) {
+    const float sp = x > 20.f ? x : log1pf(expf(x));
+    return x * tanhf(sp);
+}
+
+// For the gated posts (GLU / WN) a CTA computes BOTH halves of 32 gate channels: output-channel tile of 64 = 32 "a" + 32 "b".
+__global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvParams p) {
+    extern __shared__ float cv_smem[];
+    const int gated = (p.post == 1 || p.post == 3);
+    const int Chalf = p.Cout >> 1;
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * CV_T;
+    const int co0 = blockIdx.y * (gated ? CV_CO / 2 : CV_CO);
+    const int win = (CV_T - 1) * p.stride + (p.K - 1) * p.dil + 1;       // input window length per channel
+    float* sx = cv_smem;                                                 // [CV_CI][win]
+    float* sw = cv_smem + CV_CI * win;                                   // [CV_CI][K][CV_CO]
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;                              // tx: 4 time steps each, ty: 4 channels each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int in0 = t0 * p.stride - p.pad;
+
+    for (int c0 = 0; c0 < p.Cin; c0 += CV_CI) {
+        __syncthreads();
+        for (int i = tid; i < CV_CI * win; i += CV_THREADS) {
+            const int ci = i / win, u = i - ci * win;
+            const int c = c0 + ci, ti = in0 + u;
+            float v = 0.f;
+            if (c < p.Cin && ti >= 0 && ti < p.Tin) {
+                v = p.x[((size_t)b * p.Cin + c) * p.Tin + ti];
+                if (p.pre_lrelu) v = v > 0.f ? v : 0.1f * v;
+            }
+            sx[i] = v;
+        }
+        for (int i = tid; i < CV_CI * p.K * CV_CO; i += CV_THREADS) {
+            const int col = i % CV_CO, rk = i / CV_CO;
+            const int k = rk % p.K, ci = rk / p.K;
+            int co;
+            if (gated) co = (col < CV_CO / 2) ? co0 + col : Chalf + co0 + (col - CV_CO / 2);
+            else co = co0 + col;
+            const int c = c0 + ci;
+            const bool ok = gated ? ((col < CV_CO / 2 ? co0 + col : co0 + col - CV_CO / 2) < Chalf) : (co < p.Cout);
+            sw[i] = (ok && c < p.Cin) ? __ldg(p.w + ((size_t)co * p.Cin + c) * p.K + k) : 0.f;
+        }
+        __syncthreads();
+        const int cimax = min(CV_CI, p.Cin - c0);
+        for (int ci = 0; ci < cimax; ++ci) {
+            for (int k = 0; k < p.K; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(sw + (ci * p.K + k) * CV_CO + ty * 4);
+                const float* xr = sx + ci * win + k * p.dil + (tx * 4) * p.stride;
+                const float x0 = xr[0], x1 = xr[p.stride], x2 = xr[2 * p.stride], x3 = xr[3 * p.stride];
+                const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(wa[i], x0, acc[i][0]);
+                    acc[i][1] = fmaf(wa[i], x1, acc[i][1]);
+                    acc[i][2] = fmaf(wa[i], x2, acc[i][2]);
+                    acc[i][3] = fmaf(wa[i], x3, acc[i][3]);
+                }
+            }
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    if (!gated) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int co = co0 + ty * 4 + i;
+            if (co >= p.Cout) continue;
+            const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = t0 + tx * 4 + j;
+                if (t >= p.Tout) continue;
+                float v = acc[i][j] + bv;
+                if (p.post == 2) v = mish_f(v);
+                const size_t o = ((size_t)b * p.Cout + co) * p.Tout + t;
+                if (p.resid) v += p.resid[o];
+                v *= p.out_scale;
+                if (p.mask) v *= p.mask[(size_t)b * p.Tout + t];
+                p.y[o] = p.accumulate ? p.y[o] + v : v;
+            }
+        }
+    } else {
+        // thread rows ty*4..+3 of the 64-wide tile: rows < 32 are "a" channels, rows >= 32 the matching "b" channels -> exchange via smem
+        __syncthreads();
+        float* sg = cv_smem;                               // [64][64] accumulators
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sg[(ty * 4 + i) * CV_T + tx * 4 + j] = acc[i][j];
+        __syncthreads();
+        for (int i = tid; i < (CV_CO / 2) * CV_T; i += CV_THREADS) {
+            const int cl = i / CV_T, tl = i - cl * CV_T;
+            const int c = co0 + cl, t = t0 + tl;
+            if (c >= Chalf || t >= p.Tout) continue;
+            float a = sg[cl * CV_T + tl] + (p.bias ? __ldg(p.bias + c) : 0.f);
+            float g = sg[(cl + CV_CO / 2) * CV_T + tl] + (p.bias ? __ldg(p.bias + Chalf + c) : 0.f);
+            float v;
+            if (p.post == 1) {
+                v = a * (1.f / (1.f + expf(-g)));                                         // GLU
+            } else {
+                if (p.cond) { a += p.cond[(size_t)b * p.cond_ld + c]; g += p.cond[(size_t)b * p.cond_ld + Chalf + c]; }
+                v = tanhf(a) * (1.f / (1.f + expf(-g)));                                  // WN gate
+            }
+            const size_t o = ((size_t)b * Chalf + c) * p.Tout + t;
+            if (p.resid) v += p.resid[o];
+            v *= p.out_scale;
+            if (p.mask) v *= p.mask[(size_t)b * p.Tout + t];
+            p.y[o] = p.accumulate ? p.y[o] + v : v;
+        }
+    }
+}
+
+// weight norm: w[co, :] = g[co] * v[co, :] / ||v[co, :]||      (torch.nn.utils.weight_norm, dim=0)
+__global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int Cout, int n) {
+    const int co = blockIdx.x;
+    const float* vr = v + (size_t)co * n;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += vr[i] * vr[i];
+    __shared__ float sm[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) sm[0] = g[co] / sqrtf(s);
+    }
+    __syncthreads();
+    const float sc = sm[0];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) w[(size_t)co * n + i] = vr[i] * sc;
+}
+
+// SnakeBeta through the anti-aliased Activation1d (alias_free_torch/act.py:8-28): 2x kaiser-sinc upsample (12 taps, replicate
+// pad), x + sin^2(alpha x)/beta with alpha = exp(log_alpha), beta = exp(log_beta) (activations.py:62-119), 2x low-pass downsample.
+// filt: the 12-tap kaiser-sinc filter (same for up and down; up output is scaled by ratio=2).
+__global__ void snake_aa_kernel(const float* __restrict__ x, const float* __restrict__ log_alpha, const float* __restrict__ log_beta,
+                                const float* __restrict__ filt, float* __restrict__ y, int C, int T) {
+    // one block per (b, c) row; T is small (36) on the hot path
+    extern __shared__ float sn[];
+    const int row = blockIdx.x;
+    const int c = row % C;
+    const float* xr = x + (size_t)row * T;
+    float* xp = sn;                    // padded input: T + 10 (pad 5 each side, replicate)
+    float* up = sn + (T + 10);         // upsampled + activated: 2T, then padded replicate 5/6 for the down filter
+    const float alpha = expf(log_alpha[c]), beta = expf(log_beta[c]);
+    for (int i = threadIdx.x; i < T + 10; i += blockDim.x) xp[i] = xr[min(max(i - 5, 0), T - 1)];
+    __syncthreads();
+    // UpSample1d: conv_transpose1d(x_pad, filter*ratio, stride 2), then crop [pad_left : -pad_right], pad_left = 15, pad_right = 15
+    // out_full[n] = 2 * sum_k xp[(n - k)/2] * f[k] over k with (n-k) even ; kept n in [15, 15 + 2T)
+    for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) {
+        const int n = i + 15;
+        float s = 0.f;
+        for (int k = 0; k < 12; ++k) {
+            const int m = n - k;
+            if (m >= 0 && (m & 1) == 0 && (m >> 1) < T + 10) s += xp[m >> 1] * filt[k];
+        }
+        s *= 2.f;
+        const float sv = sinf(alpha * s);
+        up[5 + i] = s + (1.f / (beta + 1e-9f)) * sv * sv;
+    }
+    __syncthreads();
+    // DownSample1d = LowPassFilter1d(stride 2, pad replicate left 5 right 6, 12 taps)
+    for (int i = threadIdx.x; i < 5; i += blockDim.x) up[i] = up[5];
+    for (int i = threadIdx.x; i < 6; i += blockDim.x) up[5 + 2 * T + i] = up[5 + 2 * T - 1];
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < 12; ++k) s += up[2 * t + k] * filt[k];
+        y[(size_t)row * T + t] = s;
+    }
+}
+
+}  // namespace ttts
+
+using namespace ttts;
+
+extern "C" {
+
+int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                    int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                    const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    TTTS_CHECK_ARG(x && w && y, "conv1d: null pointer");
+    TTTS_CHECK_ARG(B > 0 && Cin > 0 && Tin > 0 && Cout > 0 && K > 0 && stride > 0 && dil > 0 && pad >= 0, "conv1d: bad shape");
+    const int Tout = (Tin + 2 * pad - dil * (K - 1) - 1) / stride + 1;
+    TTTS_CHECK_ARG(Tout > 0, "conv1d: empty output");
+    const bool gated = (post == 1 || post == 3);
+    TTTS_CHECK_ARG(!gated || Cout % 2 == 0, "conv1d: gated post needs an even channel count");
+    ConvParams p;
+    p.x = x; p.w = w; p.bias = bias; p.y = y; p.B = B; p.Cin = Cin; p.Tin = Tin; p.Cout = Cout; p.Tout = Tout; p.K = K; p.stride = stride;
+    p.dil = dil; p.pad = pad; p.pre_lrelu = pre_lrelu; p.resid = resid; p.out_scale = out_scale; p.accumulate = accumulate; p.mask = mask;
+    p.post = post; p.cond = cond; p.cond_ld = cond_ld;
+    const int win = (CV_T - 1) * stride + (K - 1) * dil + 1;
+    size_t smem = ((size_t)CV_CI * win + (size_t)CV_CI * K * CV_CO) * sizeof(float);
+    if (smem < (size_t)CV_CO * CV_T * sizeof(float)) smem = (size_t)CV_CO * CV_T * sizeof(float);
+    TTTS_CHECK_ARG(smem <= 200 * 1024, "conv1d: window too large for shared memory");
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        TTTS_CUDA(cudaFuncSetAttribute(conv1d_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int cg = gated ? (Cout / 2 + CV_CO / 2 - 1) / (CV_CO / 2) : (Cout + CV_CO - 1) / CV_CO;
+    dim3 grid((Tout + CV_T - 1) / CV_T, cg, B);
+    conv1d_f32_kernel<<<grid, CV_THREADS, smem, st>>>(p);
+    TTTS_LAUNCH_CHECK("conv1d_f32");
+    return TTTS_OK;
+}
+
+int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream) {
+    TTTS_CHECK_ARG(v && g && w && Cout > 0 && n_per_out > 0, "weight_norm: bad args");
+    weight_norm_kernel<<<Cout, 128, 0, (cudaStream_t)stream>>>(v, g, w, Cout, n_per_out);
+    TTTS_LAUNCH_CHECK("weight_norm");
+    return TTTS_OK;
+}
+
+int ttts_snake_aa(const float* x, const float* log_alpha, const float* log_beta, const float* filt12, float* y, int32_t B, int32_t C, int32_t T,
+                  void* stream) {
+    TTTS_CHECK_ARG(x && log_alpha && log_beta && filt12 && y && B > 0 && C > 0 && T > 0, "snake_aa: bad args");
+    const size_t smem = ((size_t)(T + 10) + (size_t)(2 * T + 11)) * sizeof(float);
+    TTTS_CHECK_ARG(smem <= 48 * 1024, "snake_aa: T too large");
+    snake_aa_kernel<<<B * C, 64, smem, (cudaStream_t)stream>>>(x, log_alpha, log_beta, filt12, y, C, T);
+    TTTS_LAUNCH_CHECK("snake_aa");
+    return TTTS_OK;
+}
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MelStyleEncoder helpers (ttts/vqvae/modules.py:600-764): tiny multi-head self-attention over T <= 64 frames with a key
+// padding mask, and the masked temporal mean.  Activations are channel-major [B, C, T] (the layout the conv kernels write).
+// ------------------------------------------------------------------------------------------------------------
+namespace ttts {
+
+// out[b, h*dk + j, tq] = sum_tk softmax_tk(q[:, tq] . k[:, tk] / temperature) v[j, tk]   (keys tk >= len[b] masked to -inf)
+__global__ void __launch_bounds__(64) mha_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                       const int64_t* __restrict__ lens, float* __restrict__ out, int C, int T, int dk,
+                                                       float inv_temp) {
+    extern __shared__ float ms[];
+    const int b = blockIdx.y, h = blockIdx.x;
+    float* sq = ms;                 // [dk][T]
+    float* sk = sq + dk * T;
+    float* sv = sk + dk * T;
+    const size_t base = ((size_t)b * C + (size_t)h * dk) * T;
+    for (int i = threadIdx.x; i < dk * T; i += blockDim.x) { sq[i] = q[base + i]; sk[i] = k[base + i]; sv[i] = v[base + i]; }
+    __syncthreads();
+    const int len = lens ? (int)min((int64_t)T, lens[b]) : T;
+    const int tq = threadIdx.x;
+    if (tq >= T) return;
+    float s[64];
+    float mx = -INFINITY;
+    for (int tk = 0; tk < T; ++tk) {
+        float a = 0.f;
+        for (int j = 0; j < dk; ++j) a = fmaf(sq[j * T + tq], sk[j * T + tk], a);
+        a = (tk < len) ? a * inv_temp : -INFINITY;
+        s[tk] = a;
+        mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+    for (int tk = 0; tk < T; ++tk) { s[tk] = expf(s[tk] - mx); sum += s[tk]; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < dk; ++j) {
+        float a = 0.f;
+        for (int tk = 0; tk < T; ++tk) a = fmaf(s[tk], sv[j * T + tk], a);
+        out[base + (size_t)j * T + tq] = a * inv;
+    }
+}
+
+// y[b, c] = sum_{t < len[b]} x[b, c, t] / len[b]
+__global__ void masked_mean_kernel(const float* __restrict__ x, const int64_t* __restrict__ lens, float* __restrict__ y, int C, int T) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int len = lens ? (int)min((int64_t)T, lens[b]) : T;
+    float s = 0.f;
+    for (int t = 0; t < len; ++t) s += x[((size_t)b * C + c) * T + t];
+    y[(size_t)b * C + c] = s / (float)len;
+}
+
+// z = (m + eps * exp(logs)) * mask        (PosteriorAudioEncoder tail, vq2.py:742-744); stats = [B, 2C, T] (m | logs)
+__global__ void posterior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ eps, const float* __restrict__ mask,
+                                        float* __restrict__ z, int C, int T, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bt = i / ((size_t)C * T);
+        const size_t r = i - bt * C * T;
+        const int t = (int)(r % T);
+        const float m = stats[bt * 2 * C * T + r];
+        const float ls = stats[bt * 2 * C * T + (size_t)C * T + r];
+        const float e = eps ? eps[i] : 0.f;
+        z[i] = (m + e * expf(ls)) * (mask ? mask[bt * T + t] : 1.f);
+    }
+}
+
+}  // namespace ttts
+
+extern "C" {
+
+int ttts_mha_small(const float* q, const float* k, const float* v, const int64_t* lens, float* out, int32_t B, int32_t C, int32_t T, int32_t heads,
+                   float temperature, void* stream) {
+    TTTS_CHECK_ARG(q && k && v && out && B > 0 && C > 0 && heads > 0 && C % heads == 0, "mha_small: bad args");
+    TTTS_CHECK_ARG(T >= 1 && T <= 64, "mha_small: T must be <= 64 (got %d)", T);
+    const int dk = C / heads;
+    const size_t smem = (size_t)3 * dk * T * sizeof(float);
+    TTTS_CHECK_ARG(smem <= 48 * 1024, "mha_small: head too large");
+    ttts::mha_small_kernel<<<dim3(heads, B), 64, smem, (cudaStream_t)stream>>>(q, k, v, lens, out, C, T, dk, 1.0f / temperature);
+    TTTS_LAUNCH_CHECK("mha_small");
+    return TTTS_OK;
+}
+
+int ttts_masked_mean(const float* x, const int64_t* lens, float* y, int32_t B, int32_t C, int32_t T, void* stream) {
+    TTTS_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0, "masked_mean: bad args");
+    ttts::masked_mean_kernel<<<dim3((C + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(x, lens, y, C, T);
+    TTTS_LAUNCH_CHECK("masked_mean");
+    return TTTS_OK;
+}
+
+int ttts_posterior_sample(const float* stats, const float* eps, const float* mask, float* z, int32_t B, int32_t C, int32_t T, void* stream) {
+    TTTS_CHECK_ARG(stats && z && B > 0 && C > 0 && T > 0, "posterior_sample: bad args");
+    const size_t n = (size_t)B * C * T;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ttts::posterior_sample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(stats, eps, mask, z, C, T, n);
+    TTTS_LAUNCH_CHECK("posterior_sample");
+    return TTTS_OK;
+}
+}
