@@ -9,6 +9,7 @@
 // epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 2:
 // leader's arrive.expect_tx + the peer's remote arrive; both CTAs' TMA bytes complete_tx there), empty[] / tmem_full[] are
 // per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 256 epilogue threads).
+#include <string.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "gemm_epilogue.cuh"
@@ -17,15 +18,24 @@
 namespace ttts {
 
 constexpr int G2_BM = 128;          // rows per CTA (256 per pair)
-constexpr int G2_BN = 256;          // columns per pair tile
+constexpr int G2_BN = 256;          // columns per tile
 constexpr int G2_BK = 64;
-constexpr int G2_STAGES = 6;
 constexpr int G2_THREADS = 320;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
-constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB (this CTA's half)
-constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_SMEM_BYTES = G2_BAR_OFFSET + 256 + 2 * 256 * 4 + 1024;   // barriers + bias staging + alignment slack
+
+// PAIR = true : CTA pair (cta_group::2), each CTA stages half of B (16 KB), 6 stages
+// PAIR = false: single CTA (cta_group::1), full B tile (32 KB), 4 stages -- same warp-specialised pipelined epilogue
+template <bool PAIR>
+struct G2Cfg {
+    static constexpr int kStages = PAIR ? 6 : 4;
+    static constexpr int kBRows = PAIR ? G2_BN / 2 : G2_BN;
+    static constexpr int kBBytes = kBRows * G2_BK * 2;
+    static constexpr int kStageBytes = G2_A_BYTES + kBBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kBarOffset + 256 + 2 * 256 * 4 + 1024;   // barriers + bias staging + alignment slack
+    static constexpr int kTileM = PAIR ? 2 * G2_BM : G2_BM;
+    static constexpr int kCtas = PAIR ? 2 : 1;
+};
 
 TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n_blk, int& split) {
     const int tiles = p.num_m_blocks * p.num_n_blocks;      // num_m_blocks counts 256-row pairs here
@@ -40,9 +50,13 @@ TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n
     m_pair = m_first + (r - n_blk * gm);
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+template <bool A_MN, bool B_MN, bool PAIR>
+__global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using C = G2Cfg<PAIR>;
+    constexpr int G2_STAGES = C::kStages;
+    constexpr int G2_STAGE_BYTES = C::kStageBytes;
+    constexpr int G2_BAR_OFFSET = C::kBarOffset;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);
@@ -53,23 +67,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
+    const int cluster_id = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+    const int num_clusters = PAIR ? (gridDim.x >> 1) : gridDim.x;
     const int total_items = p.num_m_blocks * p.num_n_blocks * p.split_k;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 512); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], C::kCtas); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 256 * C::kCtas); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_2sm(tmem_holder, 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_holder, 512); else tmem_alloc(tmem_holder, 512); }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();
+    if (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -80,7 +94,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int item = cluster_id; item < total_items; item += num_clusters) {
                 int m_pair, n_blk, split;
                 decode_item2(p, item, m_pair, n_blk, split);
-                const int m0 = m_pair * (2 * G2_BM) + (int)rank * G2_BM;
+                const int m0 = m_pair * C::kTileM + (int)rank * G2_BM;
                 const int n0 = n_blk * G2_BN + (int)rank * (G2_BN / 2);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
@@ -88,19 +102,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * G2_STAGE_BYTES;
                     uint8_t* sb = sa + G2_A_BYTES;
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::kCtas * G2_STAGE_BYTES);
                     else mbar_arrive_leader(&full_bar[stage]);
+                    auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+                        if (PAIR) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
+                        else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+                    };
                     if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < G2_BM / 64; ++j) tma_load_2d_2sm(sa + j * (G2_BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * G2_BK);
+                        for (int j = 0; j < G2_BM / 64; ++j) load(sa + j * (G2_BK * 128), &tmA, m0 + 64 * j, kb * G2_BK);
                     } else {
-                        tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * G2_BK, m0);
+                        load(sa, &tmA, kb * G2_BK, m0);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < G2_BN / 128; ++j) tma_load_2d_2sm(sb + j * (G2_BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * G2_BK);
+                        for (int j = 0; j < C::kBRows / 64; ++j) load(sb + j * (G2_BK * 128), &tmB, n0 + 64 * j, kb * G2_BK);
                     } else {
-                        tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * G2_BK, n0);
+                        load(sb, &tmB, kb * G2_BK, n0);
                     }
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -110,7 +128,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             // ================= MMA issuer (leader CTA only) =================
-            constexpr uint32_t idesc = make_idesc_bf16(2 * G2_BM, G2_BN, A_MN, B_MN);
+            constexpr uint32_t idesc = make_idesc_bf16(C::kTileM, G2_BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
@@ -132,12 +150,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int k = 0; k < G2_BK / 16; ++k) {
                         const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit_2sm(&empty_bar[stage]);
+                    if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(&tfull_bar[as]);
+                if (PAIR) umma_commit_2sm(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
             }
         }
         __syncwarp();
@@ -162,74 +181,87 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 sbias_all[as * 256 + et] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int row = m_pair * (2 * G2_BM) + (int)rank * G2_BM + q * 32 + lane;
+            const int row = m_pair * C::kTileM + (int)rank * G2_BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
             const int c0 = half * 4;
-            EpiAux x;
-            epi_prefetch(p, row, n0 + c0 * 32, x);
+            EpiAux xA, xB;
+            uint32_t rA[32], rB[32];
+            epi_prefetch(p, row, n0 + c0 * 32, xA);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            uint32_t r[32];
+            const float* sb = sbias_all + as * 256 + c0 * 32;
             __syncwarp();
-            tmem_ld_32x32(taddr + c0 * 32, r);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = c0 + cc;
-                tmem_ld_wait();
-                uint32_t rc[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) rc[j] = r[j];
-                const EpiAux xc = x;
-                if (cc < 3) {
-                    __syncwarp();
-                    tmem_ld_32x32(taddr + (c + 1) * 32, r);
-                    epi_prefetch(p, row, n0 + (c + 1) * 32, x);
-                } else {
-                    tc_fence_before();
-                    mbar_arrive_leader(&tempty_bar[as]);       // accumulator stage drained: the MMA warp may reuse it
-                }
-                epi_apply(p, row, n0 + c * 32, rc, sbias_all + as * 256 + c * 32, xc);
-            }
+            tmem_ld_32x32(taddr + c0 * 32, rA);
+            // chunk 0 (registers A) while chunk 1 loads into B, and so on: explicit ping-pong, no register copies
+            tmem_ld_wait();
+            __syncwarp();
+            tmem_ld_32x32(taddr + (c0 + 1) * 32, rB);
+            epi_prefetch(p, row, n0 + (c0 + 1) * 32, xB);
+            epi_apply(p, row, n0 + c0 * 32, rA, sb, xA);
+            tmem_ld_wait();
+            __syncwarp();
+            tmem_ld_32x32(taddr + (c0 + 2) * 32, rA);
+            epi_prefetch(p, row, n0 + (c0 + 2) * 32, xA);
+            epi_apply(p, row, n0 + (c0 + 1) * 32, rB, sb + 32, xB);
+            tmem_ld_wait();
+            __syncwarp();
+            tmem_ld_32x32(taddr + (c0 + 3) * 32, rB);
+            epi_prefetch(p, row, n0 + (c0 + 3) * 32, xB);
+            epi_apply(p, row, n0 + (c0 + 2) * 32, rA, sb + 64, xA);
+            tmem_ld_wait();
+            tc_fence_before();
+            if (PAIR) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);   // accumulator stage drained
+            epi_apply(p, row, n0 + (c0 + 3) * 32, rB, sb + 96, xB);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();      // the peer may still be reading this CTA's smem / arriving on its barriers until here
+    if (PAIR) cluster_sync_all();      // the peer may still be reading this CTA's smem / arriving on its barriers until here
     tc_fence_after();
-    if (warp == 1) { __syncwarp(); tmem_dealloc_2sm(tmem_base, 512); }
+    if (warp == 1) { __syncwarp(); if (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PAIR>
 static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p, int grid, cudaStream_t stream) {
+    using C = G2Cfg<PAIR>;
     CUtensorMap tmA, tmB;
     int rc;
     if (A_MN) rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, G2_BK, true);
     else      rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, G2_BK, G2_BM, true);
     if (rc) return rc;
     if (B_MN) rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
-    else      rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, G2_BK, G2_BN / 2, true);
+    else      rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, G2_BK, C::kBRows, true);
     if (rc) return rc;
-    auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+    auto kern = gemm2_bf16_kernel<A_MN, B_MN, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        TTTS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        TTTS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
-    kern<<<grid, G2_THREADS, G2_SMEM_BYTES, stream>>>(tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
     prof_gemm_end(stream);
+    if (e != cudaSuccess) return fail_cuda(e, "gemm2_bf16_kernel launch");
     TTTS_LAUNCH_CHECK("gemm2_bf16_kernel");
     return TTTS_OK;
 }
 
-// caller (gemm_bf16) has validated the arguments
-int gemm2_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
+template <bool PAIR>
+static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
+    using C = G2Cfg<PAIR>;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
-    p.num_m_blocks = (a.M + 2 * G2_BM - 1) / (2 * G2_BM);
+    p.num_m_blocks = (a.M + C::kTileM - 1) / C::kTileM;
     p.num_n_blocks = (a.N + G2_BN - 1) / G2_BN;
-    const int clusters = num_sms() / 2;
+    const int clusters = num_sms() / C::kCtas;
     p.group_m = clusters / p.num_n_blocks;
     if (p.group_m < 1) p.group_m = 1;
     if (p.group_m > p.num_m_blocks) p.group_m = p.num_m_blocks;
@@ -243,17 +275,23 @@ int gemm2_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     p.aux = a.aux; p.ldaux = a.ldaux; p.aux_out = a.aux_out; p.ldaux_out = a.ldaux_out;
     p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
     const int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
-    const int grid = 2 * (items < clusters ? items : clusters);
-    if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false>(a, p, grid, stream);
-    if (!a.a_mn && a.b_mn) return launch_gemm2<false, true>(a, p, grid, stream);
-    if (a.a_mn && a.b_mn) return launch_gemm2<true, true>(a, p, grid, stream);
-    return launch_gemm2<true, false>(a, p, grid, stream);
+    const int grid = C::kCtas * (items < clusters ? items : clusters);
+    if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false, PAIR>(a, p, grid, stream);
+    if (!a.a_mn && a.b_mn) return launch_gemm2<false, true, PAIR>(a, p, grid, stream);
+    if (a.a_mn && a.b_mn) return launch_gemm2<true, true, PAIR>(a, p, grid, stream);
+    return launch_gemm2<true, false, PAIR>(a, p, grid, stream);
 }
 
-int pick_split_k2(int M, int N, int K) {
-    const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+// caller (gemm_bf16) has validated the arguments
+int gemm2_bf16(const ttts_gemm_args& a, bool pair, cudaStream_t stream) {
+    return pair ? gemm2_impl<true>(a, stream) : gemm2_impl<false>(a, stream);
+}
+
+int pick_split_k2(int M, int N, int K, bool pair) {
+    const int tm = pair ? 2 * G2_BM : G2_BM;
+    const int tiles = ((M + tm - 1) / tm) * ((N + G2_BN - 1) / G2_BN);
     const int kblocks = (K + G2_BK - 1) / G2_BK;
-    const int clusters = num_sms() / 2;
+    const int clusters = num_sms() / (pair ? 2 : 1);
     int best = 1; double best_eff = -1.0;
     for (int s = 1; s <= 32 && s <= kblocks; ++s) {
         if (kblocks / s < 8 && s > 1) break;

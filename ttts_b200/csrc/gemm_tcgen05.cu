@@ -208,6 +208,12 @@ bool use_2cta(int M, int N) {
     return on && N > 128 && M > 128;
 }
 
+bool use_legacy_gemm() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_GEMM_LEGACY"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on != 0;
+}
+
 int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     TTTS_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape %d %d %d", a.M, a.N, a.K);
     TTTS_CHECK_ARG(a.A && a.B && a.out, "gemm: null pointer");
@@ -223,7 +229,9 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     if (a.epi == TTTS_EPI_GELU && a.aux_out) TTTS_CHECK_ARG((a.ldaux_out * 2) % 16 == 0 && ((uintptr_t)a.aux_out & 15) == 0, "gemm: aux_out not aligned");
     if (a.bias) TTTS_CHECK_ARG(((uintptr_t)a.bias & 15) == 0, "gemm: bias not 16B aligned");
 
-    if (use_2cta(a.M, a.N)) return gemm2_bf16(a, stream);
+    // N > 128: the pipelined-epilogue kernel (gemm2_tcgen05.cu), single CTA by default, CTA pair with TTTS_GEMM_2CTA=1;
+    // TTTS_GEMM_LEGACY=1 keeps everything on the simple kernel below (A/B testing).
+    if (a.N > 128 && !use_legacy_gemm()) return gemm2_bf16(a, use_2cta(a.M, a.N), stream);
     const int BN = (a.N > 128) ? 256 : 128;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
@@ -256,7 +264,7 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
 
 // Pick the split-K factor (1..16) that fills the SMs best for a weight-gradient GEMM.
 int pick_split_k(int M, int N, int K) {
-    if (use_2cta(M, N)) return pick_split_k2(M, N, K);
+    if (N > 128 && !use_legacy_gemm()) return pick_split_k2(M, N, K, use_2cta(M, N));
     const int BN = (N > 128) ? 256 : 128;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int kblocks = (K + BK - 1) / BK;

@@ -24,8 +24,9 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream);
 int pick_split_k(int M, int N, int K);
 bool use_2cta(int M, int N);
 // gemm2_tcgen05.cu (CTA-pair kernel)
-int gemm2_bf16(const ttts_gemm_args& a, cudaStream_t stream);
-int pick_split_k2(int M, int N, int K);
+int gemm2_bf16(const ttts_gemm_args& a, bool pair, cudaStream_t stream);
+int pick_split_k2(int M, int N, int K, bool pair);
+bool use_legacy_gemm();
 
 // elementwise.cu
 int prep_tokens(const int64_t* text, int ld_text, int64_t* codes, int ld_codes, const int64_t* wav_lengths, int B, int TL, int CL,
