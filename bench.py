@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-vq-encode", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--profile-run", action="store_true", help="for ncu runs only: honour --warmup < 3 (numbers printed are not bench values)")
     args = ap.parse_args()
@@ -292,6 +293,14 @@ def main():
         tcpu = cpu_oracle_step_time(wl, 1, 1, 0, threads)
         out["cpu_baseline"] = {"value": CL / tcpu, "unit": "frames/s", "cores": threads, "kind": "port",
                                "sample": "1 step (fwd+bwd+clip+AdamW, fp32, no grad-ckpt) of the oracle port at batch 1 of the %s shape" % args.workload}
+    if world == 1 and not args.no_vq_encode:
+        # second BASELINE.json metric: VQ-encode Msamples/s (stft -> ref_enc -> enc_p -> proj -> codes, B = 64 clips)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import vq_encode_bench
+            out["vq_encode"] = vq_encode_bench.run(hbm_gbs=pk["hbm_gbs"], with_cpu=not args.no_cpu_baseline)
+        except Exception as e:            # the GPT line must still be printed
+            out["vq_encode"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,8 @@ def test_state_dict_names_match_reference():
 def test_conv1d_kernel_vs_torch():
     from ttts_b200.vqvae.encoder import conv1d
     torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False          # the torch reference must be true fp32 (cuDNN defaults to TF32 convs)
+    torch.backends.cuda.matmul.allow_tf32 = False
     for (B, Cin, T, Cout, K, stride, dil) in [(2, 1, 2300, 16, 7, 1, 1), (3, 16, 2304, 32, 16, 10, 1), (2, 96, 144, 96, 11, 1, 5), (2, 1025, 36, 192, 1, 1, 1),
                                              (2, 192, 36, 192, 2, 2, 1)]:
         pad = (K * dil - dil) // 2 if stride == 1 else (K - 1) // 2
@@ -57,7 +59,9 @@ def test_conv1d_kernel_vs_torch():
         x = torch.randn(B, Cin, T, device="cuda"); w = torch.randn(Cout, Cin, K, device="cuda") / (Cin * K) ** 0.5; b = torch.randn(Cout, device="cuda")
         ref = torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x, 0.1), w, b, stride=stride, dilation=dil, padding=pad)
         got = conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=True)
-        assert got.shape == ref.shape and rel(got.cpu(), ref.cpu()) < 1e-5
+        ref64 = torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x.double().cpu(), 0.1), w.double().cpu(), b.double().cpu(), stride=stride,
+                                           dilation=dil, padding=pad)
+        assert got.shape == ref.shape and rel(got.cpu(), ref64) < 2e-6
 
 
 def test_encoder_vs_reference_golden(model, enc):

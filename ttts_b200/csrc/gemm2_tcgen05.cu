@@ -12,7 +12,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "host_util.h"
-#include "gemm_epilogue.cuh"
+#include "gemm_epilogue_staged.cuh"
 #include "kernels.h"
 
 namespace ttts {
@@ -32,7 +32,8 @@ struct G2Cfg {
     static constexpr int kBBytes = kBRows * G2_BK * 2;
     static constexpr int kStageBytes = G2_A_BYTES + kBBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kBarOffset + 256 + 2 * 256 * 4 + 1024;   // barriers + bias staging + alignment slack
+    static constexpr int kStageOff = kBarOffset + 256 + 2 * 256 * 4;            // barriers | bias[2][256] | per-warp store staging
+    static constexpr int kSmemBytes = kStageOff + 8 * ST_BYTES + 1024;          // + alignment slack
     static constexpr int kTileM = PAIR ? 2 * G2_BM : G2_BM;
     static constexpr int kCtas = PAIR ? 2 : 1;
 };
@@ -51,7 +52,7 @@ TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
-__global__ void __launch_bounds__(G2_THREADS, 1)
+__global__ void __maxnreg__(200)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using C = G2Cfg<PAIR>;
     constexpr int G2_STAGES = C::kStages;
@@ -184,9 +185,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int row = m_pair * C::kTileM + (int)rank * G2_BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
             const int c0 = half * 4;
-            EpiAux xA, xB;
+            EpiAuxC xA, xB;
             uint32_t rA[32], rB[32];
-            epi_prefetch(p, row, n0 + c0 * 32, xA);
+            const int row0w = row - lane;                                  // first row of this warp's 32-row slab
+            const uint32_t S = smem_u32(smem + C::kStageOff + (warp - 2) * ST_BYTES);
+            epi_prefetch_c(p, row0w, n0 + c0 * 32, lane, xA);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const float* sb = sbias_all + as * 256 + c0 * 32;
@@ -196,22 +199,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 1) * 32, rB);
-            epi_prefetch(p, row, n0 + (c0 + 1) * 32, xB);
-            epi_apply(p, row, n0 + c0 * 32, rA, sb, xA);
+            epi_prefetch_c(p, row0w, n0 + (c0 + 1) * 32, lane, xB);
+            epi_apply_staged(p, row0w, n0 + c0 * 32, lane, rA, sb, xA, S);
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 2) * 32, rA);
-            epi_prefetch(p, row, n0 + (c0 + 2) * 32, xA);
-            epi_apply(p, row, n0 + (c0 + 1) * 32, rB, sb + 32, xB);
+            epi_prefetch_c(p, row0w, n0 + (c0 + 2) * 32, lane, xA);
+            epi_apply_staged(p, row0w, n0 + (c0 + 1) * 32, lane, rB, sb + 32, xB, S);
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 3) * 32, rB);
-            epi_prefetch(p, row, n0 + (c0 + 3) * 32, xB);
-            epi_apply(p, row, n0 + (c0 + 2) * 32, rA, sb + 64, xA);
+            epi_prefetch_c(p, row0w, n0 + (c0 + 3) * 32, lane, xB);
+            epi_apply_staged(p, row0w, n0 + (c0 + 2) * 32, lane, rA, sb + 64, xA, S);
             tmem_ld_wait();
             tc_fence_before();
             if (PAIR) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);   // accumulator stage drained
-            epi_apply(p, row, n0 + (c0 + 3) * 32, rB, sb + 96, xB);
+            epi_apply_staged(p, row0w, n0 + (c0 + 3) * 32, lane, rB, sb + 96, xB, S);
         }
     }
 
