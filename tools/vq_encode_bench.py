@@ -43,6 +43,13 @@ def run(hbm_gbs=6570.3, with_cpu=False):
     ms = _time(lambda: enc(wav), iters=10)
     out["encode_ms_per_batch"] = ms
     out["encode_msamples_per_s"] = B * Lw / ms / 1e3
+    try:
+        msg = _time(lambda: enc.encode_graphed(wav), iters=20)
+        out["encode_graphed_ms_per_batch"] = msg
+        out["encode_graphed_msamples_per_s"] = B * Lw / msg / 1e3
+        assert torch.equal(enc.encode_graphed(wav), enc(wav)["codes"])
+    except Exception as e:
+        out["encode_graphed_error"] = repr(e)[:200]
     out["batch"] = B
     out["samples_per_clip"] = Lw
     # STFT + mel (v2 front end): per frame 640*4 B in, (1025 + 128)*4 B out
@@ -71,7 +78,8 @@ def run(hbm_gbs=6570.3, with_cpu=False):
     if with_cpu:
         from oracle import encoder_oracle as EO
         from oracle import vq_mel_oracle as V
-        torch.set_num_threads(os.cpu_count() or 1)
+        nthr = min(32, os.cpu_count() or 1)       # small convs: the full thread pool of a many-core host is slower (see bench.pick_cpu_threads)
+        torch.set_num_threads(nthr)
         P = EO.init_params(seed=5)
         wc = wav[:8].cpu()
         spec = torch.tensor(V.spectrogram(wc.numpy()))
@@ -82,7 +90,7 @@ def run(hbm_gbs=6570.3, with_cpu=False):
             spec = torch.tensor(V.spectrogram(wc.numpy()))
             EO.encode(P, spec, wc, codebook=Ec)
             dt = time.perf_counter() - t0
-        out["cpu_oracle"] = {"msamples_per_s": 8 * Lw / dt / 1e6, "clips": 8, "cores": os.cpu_count(), "kind": "port"}
+        out["cpu_oracle"] = {"msamples_per_s": 8 * Lw / dt / 1e6, "clips": 8, "cores": nthr, "kind": "port"}
     return out
 
 

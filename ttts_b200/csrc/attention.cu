@@ -96,7 +96,9 @@ TTTS_DEVICE void c_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
 
 // dropout on a pair of adjacent probabilities (row i, cols j, j+1) of head-batch bh
 TTTS_DEVICE void drop_pair(const DropCfg& drop, uint64_t bh, int T, int i, int j, float& p0, float& p1) {
-    const uint64_t e = (bh * (uint64_t)T + (uint64_t)i) * (uint64_t)T + (uint64_t)j;
+    // mask element (row i, col j) of head-batch bh lives at (bh*T + i) * Tpad + j with Tpad = T rounded up to 4, so that groups of 4
+    // consecutive columns share one 64-bit mix and never straddle rows (same definition in attention_tc.cu)
+    const uint64_t e = (bh * (uint64_t)T + (uint64_t)i) * (uint64_t)((T + 3) & ~3) + (uint64_t)j;
     const uint64_t bits = dropout_bits4(drop.seed, e >> 2);
     const int o = (int)(e & 3);   // j is even and T*.. may be odd: o in {0,1,2,3}; pair may straddle -> use two lookups
     p0 = dropout_keep(bits, o, drop.thresh16) ? p0 * drop.scale : 0.f;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkdv_kernel(const bf16* 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int qi = qc + (e & 1), kj = (e < 2) ? key_a : key_b;
-                    const uint64_t idx = ((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)T + (uint64_t)kj;
+                    const uint64_t idx = ((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)kj;
                     const uint64_t bits = dropout_bits4(drop.seed, idx >> 2);
                     const float mk = dropout_keep(bits, (int)(idx & 3), drop.thresh16) ? drop.scale : 0.f;
                     q4[e] *= mk;

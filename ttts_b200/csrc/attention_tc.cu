@@ -16,7 +16,9 @@
 //             dK += dS^T Q      A=dS (MN-maj) B=Q  (MN-maj) 128x64x128
 //             dQ  = dS K        A=dS (K-maj)  B=K  (MN-maj) 128x64x128 -> TMEM -> red.global.add.f32 into an fp32 dQ buffer
 //
-// Warp roles (192 threads): warp 0 = TMA loader, warp 1 = MMA issuer + TMEM alloc, warps 2-5 = softmax / gradient math.
+// Warp roles (320 threads): warp 0 = TMA loader, warp 1 = MMA issuer + TMEM alloc, warps 2-9 = softmax / gradient math: two warps
+// per TMEM lane quadrant, each owning half of the tile's columns (64 keys, 32 of the 64 output dims), so every SM sub-partition has
+// two math warps to hide latency (the first version with one warp per sub-partition issued 0.19 instr/cycle, profiles/r1_notes.md).
 #include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
@@ -27,10 +29,11 @@ namespace ttts {
 constexpr int AT_BM = 128;            // queries per tile
 constexpr int AT_BN = 128;            // keys per tile
 constexpr int AT_TILE = 128 * 128;    // bytes of a [128 x 64] bf16 tile
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9: two warps per TMEM lane quadrant (each takes half of the columns)
 constexpr float kLog2eF = 1.4426950408889634f;
 
 TTTS_DEVICE void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+TTTS_DEVICE float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // K-major descriptor for k-step kk (16 elements of K) inside a [rows x 64] tile (or the 2-atom [rows x 128] P/dS buffers)
 TTTS_DEVICE uint64_t desc_kmajor(uint32_t base, int kk) { return make_smem_desc_sw128(base + (kk >> 2) * AT_TILE + (kk & 3) * 32, 16, 1024); }
@@ -52,7 +55,8 @@ struct FwdSmem {
     static constexpr int oKV = AT_TILE;                                 // [stages][K | V]
     static constexpr int oP = oKV + kKvStages * 2 * AT_TILE;            // [2][2 atoms]
     static constexpr int oBar = oP + 2 * 2 * AT_TILE;
-    static constexpr int kBytes = oBar + 256 + 1024;
+    static constexpr int oXch = oBar + 256;                             // row-max / row-sum exchange between the two column halves: [2][2][128] floats
+    static constexpr int kBytes = oXch + 3 * 2 * 128 * 4 + 1024;       // 2 max buffers + 1 sum buffer
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -86,9 +90,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         mbar_init(q_full, 1);
         for (int s = 0; s < S::kKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128);
-            mbar_init(&p_full[s], 128); mbar_init(&p_empty[s], 1);
-            mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 128);
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 256);
+            mbar_init(&p_full[s], 256); mbar_init(&p_empty[s], 1);
+            mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 256);
         }
         fence_barrier_init();
     }
@@ -157,73 +161,85 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         }
         __syncwarp();
     } else {
-        // ---------------- softmax warps: thread = query row = TMEM lane ----------------
+        // ---------------- softmax warps: thread = (query row = TMEM lane, column half) ----------------
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                    // 0: keys 0-63 / out dims 0-31 ; 1: keys 64-127 / out dims 32-63
         const int r = quad * 32 + lane;
         const int qi = q0 + r;                               // query index within the sequence
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * kLog2eF;
-        float m_run = -INFINITY, l_run = 0.f;
-        float o[64];
+        float* xch = reinterpret_cast<float*>(smem + S::oXch);               // [buf][half][row]
+        float m_run = -INFINITY, l_run = 0.f;                // l_run: partial row sum over THIS thread's keys
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) o[i] = 0.f;
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
 
         for (int j = 0; j < nkv; ++j) {
             const int k0 = j * AT_BN;
             const bool need_mask = (j == qb) || (k0 + AT_BN > T);
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t ts = tS + (j & 1) * 128 + lane_off;
-            // pass 1: row max
-            float mx = m_run;
+            const uint32_t ts = tS + (j & 1) * 128 + lane_off + half * 64;
+            const int kc0 = k0 + half * 64;
+            // pass 1: row max over this thread's 64 keys
+            float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld_32x32(ts + c * 32, v);
                 tmem_ld_wait();
+                if (need_mask) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int kj = k0 + c * 32 + i;
-                    const bool ok = !need_mask || (kj <= qi && kj < T);
-                    if (ok) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        const int kj = kc0 + c * 32 + i;
+                        if (kj <= qi && kj < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
             }
+            xch[((j & 1) * 2 + half) * 128 + r] = mx;
+            named_bar_sync(2, 256);
+            mx = fmaxf(fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]), m_run);
             const float msc = (mx == -INFINITY) ? 0.f : mx * sl2;
-            const float corr = exp2f(m_run * sl2 - msc);        // 0 when m_run = -inf
+            const float corr = ex2_fast(m_run * sl2 - msc);       // 0 when m_run = -inf
             // pass 2: probabilities -> bf16 P tile in smem
             mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
             const uint32_t sP = smem_u32(smem + S::oP + (j & 1) * 2 * AT_TILE);
             float rs = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld_32x32(ts + c * 32, v);
                 tmem_ld_wait();
                 float pv[32];
+                if (need_mask) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int kj = k0 + c * 32 + i;
-                    const bool ok = !need_mask || (kj <= qi && kj < T);
-                    pv[i] = ok ? exp2f(__uint_as_float(v[i]) * sl2 - msc) : 0.f;
-                    rs += pv[i];
+                    for (int i = 0; i < 32; ++i) {
+                        const int kj = kc0 + c * 32 + i;
+                        pv[i] = (kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
+                        rs += pv[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc)); rs += pv[i]; }
                 }
                 if (drop.thresh16) {
+                    // one 64-bit mix per 4 consecutive keys (rows are padded to a multiple of 4 in the mask index space)
+                    const uint64_t e0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)(kc0 + c * 32)) >> 2;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const uint64_t e = ((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)T + (uint64_t)(k0 + c * 32 + i4 * 4);
+                        const uint64_t bits = dropout_bits4(drop.seed, e0 + i4);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint64_t ei = e + i;
-                            const uint64_t bits = dropout_bits4(drop.seed, ei >> 2);
-                            pv[i4 * 4 + i] = dropout_keep(bits, (int)(ei & 3), drop.thresh16) ? pv[i4 * 4 + i] * drop.scale : 0.f;
-                        }
+                        for (int i = 0; i < 4; ++i) pv[i4 * 4 + i] = dropout_keep(bits, i, drop.thresh16) ? pv[i4 * 4 + i] * drop.scale : 0.f;
                     }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                    st_tile_chunk(sP, r, c * 4 + g,
+                    st_tile_chunk(sP, r, (half * 2 + c) * 4 + g,
                                   make_uint4(pack_bf16(pv[8 * g], pv[8 * g + 1]), pack_bf16(pv[8 * g + 2], pv[8 * g + 3]),
                                              pack_bf16(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16(pv[8 * g + 6], pv[8 * g + 7])));
             }
@@ -236,45 +252,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
             if (j >= 1) {        // fold in P_{j-1} V_{j-1}, which the tensor core finished while we did the softmax of block j
                 mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                const uint32_t to = tO + ((j - 1) & 1) * 64 + lane_off;
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(tO + ((j - 1) & 1) * 64 + lane_off + half * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld_32x32(to + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
-                }
+                for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
                 tc_fence_before();
                 mbar_arrive(&o_empty[(j - 1) & 1]);
             }
 #pragma unroll
-            for (int i = 0; i < 64; ++i) o[i] *= corr;
+            for (int i = 0; i < 32; ++i) o[i] *= corr;
         }
         {
             const int jl = nkv - 1;
             mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
             tc_fence_after();
-            const uint32_t to = tO + (jl & 1) * 64 + lane_off;
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(tO + (jl & 1) * 64 + lane_off + half * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(to + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
-            }
+            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
             tc_fence_before();
             mbar_arrive(&o_empty[jl & 1]);
         }
+        // total row sum = the two halves' partial sums
+        xch[(4 + half) * 128 + r] = l_run;
+        named_bar_sync(2, 256);
+        const float l_tot = l_run + xch[(4 + (half ^ 1)) * 128 + r];
         if (qi < T) {
-            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-            lse_out[(size_t)bh * T + qi] = m_run * scale + logf(l_run);
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64);
+            const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+            if (half == 0) lse_out[(size_t)bh * T + qi] = m_run * scale + logf(l_tot);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + half * 32);
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < 4; ++g)
                 dst[g] = make_uint4(pack_bf16(o[8 * g] * inv, o[8 * g + 1] * inv), pack_bf16(o[8 * g + 2] * inv, o[8 * g + 3] * inv),
                                     pack_bf16(o[8 * g + 4] * inv, o[8 * g + 5] * inv), pack_bf16(o[8 * g + 6] * inv, o[8 * g + 7] * inv));
         }
@@ -329,9 +341,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tma_prefetch_desc(&tmDO);
         mbar_init(kv_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 128);
-        mbar_init(pds_full, 128); mbar_init(pds_empty, 1);
-        mbar_init(dq_full, 1); mbar_init(dq_empty, 128);
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 256);
+        mbar_init(pds_full, 256); mbar_init(pds_empty, 1);
+        mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -395,6 +407,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         __syncwarp();
     } else {
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                    // column half: keys 0-63 / 64-127 of the tile, 32 of the 64 head dims
         const int r = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * kLog2eF;
@@ -407,49 +420,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             const float lse2 = q_ok ? lse[(size_t)bh * T + qi] * kLog2eF : 0.f;
             const float dlt = q_ok ? delta[(size_t)bh * T + qi] : 0.f;
             const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
+            const int kc0 = k0 + half * 64;
             mbar_wait(sdp_full, ph);
             tc_fence_after();
             mbar_wait(pds_empty, ph ^ 1);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t sv[32], gv[32];
                 __syncwarp();
-                tmem_ld_32x32(tS + lane_off + c * 32, sv);
-                tmem_ld_32x32(tDP + lane_off + c * 32, gv);
+                tmem_ld_32x32(tS + lane_off + half * 64 + c * 32, sv);
+                tmem_ld_32x32(tDP + lane_off + half * 64 + c * 32, gv);
                 tmem_ld_wait();
                 float p[32], ds[32];
+                if (need_mask) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int kj = k0 + c * 32 + e;
-                    const bool ok = !need_mask || (q_ok && kj <= qi && kj < T);
-                    p[e] = ok ? exp2f(__uint_as_float(sv[e]) * sl2 - lse2) : 0.f;
-                    ds[e] = __uint_as_float(gv[e]);
+                    for (int e = 0; e < 32; ++e) {
+                        const int kj = kc0 + c * 32 + e;
+                        p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
                 }
                 if (drop.thresh16) {
+                    const uint64_t e0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)(kc0 + c * 32)) >> 2;
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
-                        const uint64_t eb = ((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)T + (uint64_t)(k0 + c * 32 + e4 * 4);
+                        const uint64_t bits = dropout_bits4(drop.seed, e0 + e4);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint64_t ei = eb + e;
-                            const uint64_t bits = dropout_bits4(drop.seed, ei >> 2);
-                            const float mk = dropout_keep(bits, (int)(ei & 3), drop.thresh16) ? drop.scale : 0.f;
-                            ds[e4 * 4 + e] *= mk;                           // dP = mask * (dO V^T)
-                            const float pd = p[e4 * 4 + e] * mk;            // dropped P feeds dV
-                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (ds[e4 * 4 + e] - dlt) * scale;
+                            const float mk = dropout_keep(bits, e, drop.thresh16) ? drop.scale : 0.f;
+                            const float pd = p[e4 * 4 + e] * mk;                                                         // dropped P feeds dV
+                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (__uint_as_float(gv[e4 * 4 + e]) * mk - dlt) * scale;       // dP = mask * (dO V^T)
                             p[e4 * 4 + e] = pd;
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) ds[e] = p[e] * (ds[e] - dlt) * scale;
+                    for (int e = 0; e < 32; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt) * scale;
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    st_tile_chunk(sP, r, c * 4 + g,
+                    st_tile_chunk(sP, r, (half * 2 + c) * 4 + g,
                                   make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
                                              pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7])));
-                    st_tile_chunk(sDS, r, c * 4 + g,
+                    st_tile_chunk(sDS, r, (half * 2 + c) * 4 + g,
                                   make_uint4(pack_bf16(ds[8 * g], ds[8 * g + 1]), pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
                                              pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16(ds[8 * g + 6], ds[8 * g + 7])));
                 }
@@ -458,20 +473,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             mbar_arrive(sdp_empty);
             fence_proxy_async();
             mbar_arrive(pds_full);
-            // dQ tile of this (query block, key block) pair -> fp32 accumulation buffer
+            // dQ tile of this (query block, key block) pair -> fp32 accumulation buffer (this thread: 32 of the 64 dims)
             mbar_wait(dq_full, ph);
             tc_fence_after();
-            float* dst = dq_acc + (size_t)(row_base + qi) * d + h * 64;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            float* dst = dq_acc + (size_t)(row_base + qi) * d + h * 64 + half * 32;
+            {
                 uint32_t v[32];
                 __syncwarp();
-                tmem_ld_32x32(tDQ + lane_off + c * 32, v);
+                tmem_ld_32x32(tDQ + lane_off + half * 32, v);
                 tmem_ld_wait();
                 if (q_ok) {
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + 4 * g), "f"(__uint_as_float(v[4 * g])),
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(v[4 * g])),
                                      "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3])) : "memory");
                 }
             }
@@ -480,22 +494,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         // dK, dV of this key block (complete once the last iteration's commit has fired: dq_full of that iteration)
         const int kj = k0 + r;
-        bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64;
+        bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64 + half * 32;
         bf16* dvp = dkp + d;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
             uint32_t a[32], v[32];
             __syncwarp();                                   // .aligned TMEM loads: whole warp, unconditionally
-            tmem_ld_32x32(tDK + lane_off + c * 32, a);
-            tmem_ld_32x32(tDV + lane_off + c * 32, v);
+            tmem_ld_32x32(tDK + lane_off + half * 32, a);
+            tmem_ld_32x32(tDV + lane_off + half * 32, v);
             tmem_ld_wait();
             if (kj < T) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    reinterpret_cast<uint4*>(dkp + c * 32)[g] =
+                    reinterpret_cast<uint4*>(dkp)[g] =
                         make_uint4(pack_bf16(__uint_as_float(a[8 * g]), __uint_as_float(a[8 * g + 1])), pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3])),
                                    pack_bf16(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5])), pack_bf16(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7])));
-                    reinterpret_cast<uint4*>(dvp + c * 32)[g] =
+                    reinterpret_cast<uint4*>(dvp)[g] =
                         make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
                                    pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
                 }

@@ -52,7 +52,7 @@ TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using C = G2Cfg<PAIR>;
     constexpr int G2_STAGES = C::kStages;
