@@ -135,6 +135,13 @@ TTTS_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* b
         : "memory");
 }
 
+TTTS_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 // leader's arrive.expect_tx + the peer's remote arrive; both CTAs' TMA bytes complete_tx there), empty[] / tmem_full[] are
 // per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 256 epilogue threads).
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "gemm_epilogue_staged.cuh"
@@ -52,7 +53,7 @@ TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(G2_THREADS, 1)   // 10 warps: 3 on one sub-partition -> 16384/3/32 = 168 registers per thread
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using C = G2Cfg<PAIR>;
     constexpr int G2_STAGES = C::kStages;
@@ -110,14 +111,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
                     };
                     if (A_MN) {
+                        if (!PAIR && p.a3d) {
+                            tma_load_3d(sa, &tmA, &full_bar[stage], 0, kb * G2_BK, m0 >> 6);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < G2_BM / 64; ++j) load(sa + j * (G2_BK * 128), &tmA, m0 + 64 * j, kb * G2_BK);
+                            for (int j = 0; j < G2_BM / 64; ++j) load(sa + j * (G2_BK * 128), &tmA, m0 + 64 * j, kb * G2_BK);
+                        }
                     } else {
                         load(sa, &tmA, kb * G2_BK, m0);
                     }
                     if (B_MN) {
+                        if (!PAIR && p.b3d) {
+                            tma_load_3d(sb, &tmB, &full_bar[stage], 0, kb * G2_BK, n0 >> 6);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < C::kBRows / 64; ++j) load(sb + j * (G2_BK * 128), &tmB, n0 + 64 * j, kb * G2_BK);
+                            for (int j = 0; j < C::kBRows / 64; ++j) load(sb + j * (G2_BK * 128), &tmB, n0 + 64 * j, kb * G2_BK);
+                        }
                     } else {
                         load(sb, &tmB, kb * G2_BK, n0);
                     }
@@ -226,14 +235,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
-static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p, int grid, cudaStream_t stream) {
+static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int grid, cudaStream_t stream) {
     using C = G2Cfg<PAIR>;
+    GemmParams p = p_in;
     CUtensorMap tmA, tmB;
     int rc;
-    if (A_MN) rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, G2_BK, true);
+    static int use3d = -1;
+    if (use3d < 0) { const char* e = getenv("TTTS_GEMM_NO3D"); use3d = (e && e[0] == '1') ? 0 : 1; }
+    p.a3d = (A_MN && !PAIR && use3d && a.M % 64 == 0) ? 1 : 0;
+    p.b3d = (B_MN && !PAIR && use3d && a.N % 64 == 0) ? 1 : 0;
+    if (A_MN) rc = p.a3d ? make_tmap_mn3d(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, G2_BK, G2_BM / 64)
+                         : make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, G2_BK, true);
     else      rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, G2_BK, G2_BM, true);
     if (rc) return rc;
-    if (B_MN) rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
+    if (B_MN) rc = p.b3d ? make_tmap_mn3d(&tmB, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, G2_BK, C::kBRows / 64)
+                         : make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
     else      rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, G2_BK, C::kBRows, true);
     if (rc) return rc;
     auto kern = gemm2_bf16_kernel<A_MN, B_MN, PAIR>;
@@ -277,6 +293,7 @@ static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
     p.out = a.out; p.ldo = a.ldo; p.bias = a.bias;
     p.aux = a.aux; p.ldaux = a.ldaux; p.aux_out = a.aux_out; p.ldaux_out = a.ldaux_out;
     p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
+    p.a3d = p.b3d = 0;
     const int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
     const int grid = C::kCtas * (items < clusters ? items : clusters);
     if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false, PAIR>(a, p, grid, stream);

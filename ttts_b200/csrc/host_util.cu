@@ -126,6 +126,40 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t in
     return TTTS_OK;
 }
 
+int make_tmap_mn3d(CUtensorMap* out, const void* gptr, uint64_t mn, uint64_t k_rows, uint64_t ld_elems, uint32_t box_k, uint32_t atoms) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    TmapKey key{gptr, 3, mn, k_rows, ld_elems, box_k, atoms, true, dev};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return TTTS_OK; }
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)"); return TTTS_ERR_CUDA; }
+    TTTS_CHECK_ARG(mn % 64 == 0, "3-D MN-major tensor map needs MN %% 64 == 0");
+    TTTS_CHECK_ARG(((uintptr_t)gptr & 15) == 0 && (ld_elems * 2) % 16 == 0, "TMA alignment");
+    cuuint64_t dims[3] = {64, k_rows, mn / 64};
+    cuuint64_t strides[2] = {ld_elems * 2, 128};
+    cuuint32_t box[3] = {64, box_k, atoms};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed: %d (mn=%llu k=%llu ld=%llu box_k=%u atoms=%u)", (int)r, (unsigned long long)mn,
+                  (unsigned long long)k_rows, (unsigned long long)ld_elems, box_k, atoms);
+        return TTTS_ERR_CUDA;
+    }
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 65536) cache.clear();
+        cache[key] = *out;
+    }
+    return TTTS_OK;
+}
+
 }  // namespace ttts
 
 extern "C" {

@@ -47,4 +47,8 @@ void prof_gemm_end(cudaStream_t st);
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                  uint32_t box_inner, uint32_t box_outer, bool swizzle128);
 
+// 3-D view of an MN-major operand [K rows][MN contiguous] as {64 (mn), K, MN/64 atoms}: one TMA box {64, box_k, atoms}
+// lands in shared memory as [atom][k][64] -- exactly the MN-major 128B-swizzle UMMA layout.  Requires MN % 64 == 0.
+int make_tmap_mn3d(CUtensorMap* out, const void* gptr, uint64_t mn, uint64_t k_rows, uint64_t ld_elems, uint32_t box_k, uint32_t atoms);
+
 }  // namespace ttts
