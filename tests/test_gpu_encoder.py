@@ -98,3 +98,12 @@ def test_encoder_batch64_properties(model):
     lens = torch.full((64,), 36, device="cuda"); lens[3] = 20
     o3 = model(wav, lengths=lens)
     assert float(o3["z"][3, :, 20:].abs().max()) == 0.0
+
+
+def test_encode_graphed_matches_eager(model):
+    """The CUDA-graph replay of the eval encode (weight-norm cached, static buffers) returns exactly the eager codes, also after replays
+    with different inputs and after a shape change (re-capture)."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for B in (4, 4, 7):
+        wav = torch.clamp(0.1 * torch.randn(B, 23040, device="cuda", generator=g), -1, 1)
+        assert torch.equal(model.encode_graphed(wav), model(wav)["codes"])

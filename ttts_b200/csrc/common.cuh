@@ -84,6 +84,38 @@ TTTS_DEVICE bool dropout_keep(uint64_t bits, int j, uint32_t thresh16) {
     return ((uint32_t)(bits >> (16 * j)) & 0xffffu) >= thresh16;
 }
 
+// Attention-probability dropout (B*H*T*T decisions per layer: the hash must cost ~2 instructions per element, not ~5 like mix64).
+// Row key = mix64(seed, b*h*T + query) once per row; then per group of 4 consecutive keys three rounds of a 32x32->64 multiply-fold
+// (one IMAD.WIDE + one LOP3 each) give two 32-bit words = four 16-bit uniform fields.  keep <=> field >= thresh16.
+// Statistical checks (keep rate, key/row/diagonal correlations, 2-D spectrum) are in tests/test_oracle_golden.py::test_attn_dropout_hash.
+struct AttnDropRow { uint32_t k0, k1; };
+TTTS_DEVICE AttnDropRow attn_drop_row(uint64_t seed, uint64_t row) {
+    const uint64_t z = mix64(seed + row * 0x9E3779B97F4A7C15ULL);
+    AttnDropRow k; k.k0 = (uint32_t)z; k.k1 = (uint32_t)(z >> 32);
+    return k;
+}
+TTTS_DEVICE void attn_drop_words(const AttnDropRow k, uint32_t g, uint32_t& w0, uint32_t& w1) {
+    const uint32_t a = g * 0x9E3779B1u + k.k0;
+    const uint64_t m1 = (uint64_t)a * 0x85EBCA6Bu;
+    const uint32_t x = (uint32_t)m1 ^ (uint32_t)(m1 >> 32) ^ k.k1;
+    const uint64_t m2 = (uint64_t)x * 0xC2B2AE35u;
+    const uint32_t y = (uint32_t)m2 ^ (uint32_t)(m2 >> 32);
+    const uint64_t m3 = (uint64_t)y * 0x27D4EB2Fu;
+    w0 = (uint32_t)(m3 >> 32) ^ (uint32_t)m2;
+    w1 = (uint32_t)m3 ^ (uint32_t)(m2 >> 32);
+}
+// keep decisions of keys 4g .. 4g+3 against t32 = thresh16 << 16 (fields: w0 hi, w0 lo, w1 hi, w1 lo)
+TTTS_DEVICE bool attn_drop_keep(uint32_t w0, uint32_t w1, int j, uint32_t t32) {
+    const uint32_t w = (j & 2) ? w1 : w0;
+    return ((j & 1) ? (w << 16) : w) >= t32;
+}
+// slow generic form (legacy kernels, mask dump): one element
+TTTS_DEVICE bool attn_drop_keep1(uint64_t seed, uint64_t row, int kj, uint32_t thresh16) {
+    uint32_t w0, w1;
+    attn_drop_words(attn_drop_row(seed, row), (uint32_t)kj >> 2, w0, w1);
+    return attn_drop_keep(w0, w1, kj & 3, thresh16 << 16);
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
