@@ -176,6 +176,9 @@ int64_t ttts_attn_bwd_scratch_floats(int32_t B, int32_t T, int32_t H);
 int ttts_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);
 int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_scratch, void* dqkv,
                   int32_t B, int32_t T, int32_t H, float drop_p, uint64_t seed, void* stream);
+/* keep mask [BH, T, T] (1 = kept) of the attention-probability dropout for (drop_p, seed): with it torch can reproduce
+ * ttts_attn_fwd/bwd under dropout exactly (HF:modeling_gpt2.py:216 attn_dropout; the hash is ours) */
+int ttts_attn_dropout_mask(uint8_t* mask, int32_t BH, int32_t T, float drop_p, uint64_t seed, void* stream);
 /* mean cross-entropy over rows of bf16 logits [rows, ld] (ttts/gpt/model.py:508-509) */
 int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, float* row_loss, float* row_lse,
                 float* loss_out, void* stream);

@@ -243,3 +243,39 @@ def flops_per_step(cfg, B, TL, CL):
     vm = cfg["number_mel_codes"]
     fwd = L * (24 * d * d * T + 2 * T * T * d) + 2 * d * vm * (CL + 2) + 2 * d * vt * (TL + 2)
     return 3 * B * fwd
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Attention-probability dropout mask (HF: modeling_gpt2.py:216 `attn_dropout`).  torch's Philox stream cannot be matched by a
+# fused kernel, so the CUDA path defines its own counter-based keep function (ttts_b200/csrc/common.cuh attn_drop_*); this is
+# its numpy restatement.  With the mask in hand, plain torch reproduces the dropped attention exactly, and the statistical
+# quality of the hash (keep rate, correlations, spectrum) is checked on the CPU in tests/test_oracle_golden.py.
+# ---------------------------------------------------------------------------------------------------------------------
+def attn_dropout_thresh16(p):
+    return int(p * 65536.0 + 0.5)
+
+
+def attn_dropout_keep_mask(seed, rows, T, p):
+    """keep[r, kj] for mask rows `rows` (= (b*H + h)*T + query index, any integer array) and keys 0..T-1; bool [len(rows), T]."""
+    import numpy as np
+    U = np.uint64
+    lo32 = U(0xFFFFFFFF)
+    rows = np.asarray(rows, dtype=U)
+    with np.errstate(over="ignore"):
+        z = U(seed) + rows * U(0x9E3779B97F4A7C15)
+        z ^= z >> U(33); z *= U(0xFF51AFD7ED558CCD)
+        z ^= z >> U(33); z *= U(0xC4CEB9FE1A85EC53)
+        z ^= z >> U(33)
+        k0, k1 = (z & lo32)[:, None], (z >> U(32))[:, None]
+        g = np.arange((T + 3) // 4, dtype=U)[None, :]
+        a = (g * U(0x9E3779B1) + k0) & lo32
+        m1 = a * U(0x85EBCA6B)
+        x = (m1 & lo32) ^ (m1 >> U(32)) ^ k1
+        m2 = x * U(0xC2B2AE35)
+        y = (m2 & lo32) ^ (m2 >> U(32))
+        m3 = y * U(0x27D4EB2F)
+        w0 = (m3 >> U(32)) ^ (m2 & lo32)
+        w1 = (m3 & lo32) ^ (m2 >> U(32))
+        t32 = U(attn_dropout_thresh16(p) << 16)
+        f = np.stack([w0, (w0 << U(16)) & lo32, w1, (w1 << U(16)) & lo32], axis=-1)
+    return (f >= t32).reshape(len(rows), -1)[:, :T]

@@ -116,6 +116,53 @@ def test_attention_fwd_bwd(L, B, T, H):
         assert rel(dqkv[:, i * d:(i + 1) * d], dref[:, i * d:(i + 1) * d]) < 8e-3
 
 
+@pytest.mark.parametrize("legacy", [0, 1])
+@pytest.mark.parametrize("B,T,H", [(2, 200, 2), (1, 389, 4)])
+def test_attention_dropout_exact_with_mask(L, B, T, H, legacy):
+    """Attention-probability dropout, exactly: the device keep mask equals the oracle's numpy restatement of the hash bit for bit, and
+    with that mask plain torch reproduces forward and backward (HF: modeling_gpt2.py:207-222: softmax -> dropout -> @ V)."""
+    import subprocess, sys, os
+    if legacy:      # the mma.sync kernels are selected per process (env read once): run this case in a child process
+        env = dict(os.environ, TTTS_ATTN_LEGACY="1", TTTS_TEST_CHILD="1")
+        if os.environ.get("TTTS_TEST_CHILD") != "1":
+            r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                                "%s::test_attention_dropout_exact_with_mask[%d-%d-%d-1]" % (__file__, B, T, H)], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            return
+    import numpy as np
+    from oracle import gpt_oracle as O
+    lib = L.lib()
+    lib.ttts_attn_dropout_mask.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_void_p]
+    lib.ttts_attn_dropout_mask.restype = ctypes.c_int
+    d = H * 64
+    p, seed = 0.1, 2 ** 40 + 17
+    torch.manual_seed(5)
+    qkv = (torch.randn(B * T, 3 * d, device="cuda") * 0.7).bfloat16()
+    mask = torch.zeros(B * H, T, T, device="cuda", dtype=torch.uint8)
+    L.check(lib.ttts_attn_dropout_mask(L.ptr(mask), B * H, T, ctypes.c_float(p), ctypes.c_uint64(seed), L.stream_ptr()))
+    want = O.attn_dropout_keep_mask(seed, np.arange(B * H * T), T, p).reshape(B * H, T, T)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), want)
+    keep_scale = 1.0 / (1.0 - O.attn_dropout_thresh16(p) / 65536.0)
+    out = torch.zeros(B * T, d, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B * H * T, device="cuda")
+    L.check(lib.ttts_attn_fwd(L.ptr(qkv), L.ptr(out), L.ptr(lse), B, T, H, ctypes.c_float(p), ctypes.c_uint64(seed), L.stream_ptr()))
+    q, k, v = [t.view(B, T, H, 64).transpose(1, 2).float().requires_grad_(True) for t in qkv.float().split(d, dim=1)]
+    att = (q @ k.transpose(-1, -2)) * 0.125
+    att = att.masked_fill(~torch.ones(T, T, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+    pm = torch.softmax(att, -1) * mask.view(B, H, T, T).float() * keep_scale
+    ref = (pm @ v).transpose(1, 2).reshape(B * T, d)
+    assert rel(out, ref) < 6e-3
+    dout = (torch.randn(B * T, d, device="cuda") * 0.5).bfloat16()
+    ref.backward(dout.float())
+    dref = torch.cat([t.grad.transpose(1, 2).reshape(B * T, d) for t in (q, k, v)], dim=1)
+    dqkv = torch.full_like(qkv, 5.0)
+    delta = torch.zeros(B * H * T + 64 + B * T * d, device="cuda")
+    L.check(lib.ttts_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta), L.ptr(dqkv), B, T, H, ctypes.c_float(p),
+                              ctypes.c_uint64(seed), L.stream_ptr()))
+    for i in range(3):
+        assert rel(dqkv[:, i * d:(i + 1) * d], dref[:, i * d:(i + 1) * d]) < 1e-2
+
+
 def test_attention_dropout_statistics(L):
     """attn-prob dropout cannot be bit-matched to torch's Philox stream; check it is unbiased, seed-deterministic, and that
     backward uses the forward's mask (directional derivative vs finite difference of the SAME masked function)."""

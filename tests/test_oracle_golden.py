@@ -70,3 +70,29 @@ def test_adamw_matches_torch():
         O.clip_and_adamw(p, g, state, 1e-3, step)
     for t, v in zip(tp, p.values()):
         assert torch.allclose(t.detach(), v, atol=1e-6)
+
+
+def test_attn_dropout_hash_statistics():
+    """The counter-based keep function used for attention-probability dropout (csrc/common.cuh attn_drop_*, numpy restatement in the
+    oracle): exact keep rate, no visible correlation along keys / queries / diagonals / seeds, flat 2-D spectrum."""
+    rows = np.arange(2048)
+    T = 1156
+    for seed in (0, 7, 2 ** 63 + 12345):
+        m = O.attn_dropout_keep_mask(seed, rows, T, 0.1).astype(np.float64)
+        n = m.size
+        assert abs(m.mean() - (1 - 6554 / 65536)) < 4 * np.sqrt(0.09 / n)
+        c = m - m.mean(); v = (c * c).mean()
+        for (dr, dk) in ((0, 1), (0, 2), (0, 3), (0, 4), (0, 8), (1, 0), (1, 1), (2, 0), (16, 0)):
+            r = (c[dr:, dk:] * c[:c.shape[0] - dr, :c.shape[1] - dk]).mean() / v
+            assert abs(r) < 5 / np.sqrt(n), (seed, dr, dk, r)
+        assert abs(m.mean(1).std() - np.sqrt(0.09 / T)) < 0.1 * np.sqrt(0.09 / T)            # per-row keep rates: binomial spread, no more
+        assert abs(m.mean(0).std() - np.sqrt(0.09 / len(rows))) < 0.15 * np.sqrt(0.09 / len(rows))
+    a = O.attn_dropout_keep_mask(5, rows, T, 0.1).astype(np.float64); b = O.attn_dropout_keep_mask(6, rows, T, 0.1).astype(np.float64)
+    assert abs(((a - a.mean()) * (b - b.mean())).mean() / 0.09) < 5 / np.sqrt(a.size)
+    h = O.attn_dropout_keep_mask(9, np.arange(1024), 1024, 0.5).astype(np.float64) - 0.5
+    spec = np.abs(np.fft.fft2(h)) ** 2 / (1024 * 1024 * 0.25)
+    spec[0, 0] = 0
+    assert spec.max() < 25 and abs(spec.mean() - 1) < 0.01          # exponential(1) bins: max over 1M bins ~ 14
+    # p = 0 keeps everything; the mask depends on the row id only through (seed, row)
+    assert O.attn_dropout_keep_mask(1, rows[:4], 9, 0.0).all()
+    assert np.array_equal(O.attn_dropout_keep_mask(3, [77], 64, 0.3)[0], O.attn_dropout_keep_mask(3, [5, 77], 64, 0.3)[1])

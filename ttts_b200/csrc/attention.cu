@@ -94,20 +94,14 @@ TTTS_DEVICE void c_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
     }
 }
 
-// dropout on a pair of adjacent probabilities (row i, cols j, j+1) of head-batch bh
+// dropout on a pair of adjacent probabilities (row i, cols j, j+1; j even) of head-batch bh: same keep function as the tcgen05
+// kernels (common.cuh attn_drop_*: row key from (seed, bh*T + i), one 3-round multiply-fold per group of 4 keys)
 TTTS_DEVICE void drop_pair(const DropCfg& drop, uint64_t bh, int T, int i, int j, float& p0, float& p1) {
-    // mask element (row i, col j) of head-batch bh lives at (bh*T + i) * Tpad + j with Tpad = T rounded up to 4, so that groups of 4
-    // consecutive columns share one 64-bit mix and never straddle rows (same definition in attention_tc.cu)
-    const uint64_t e = (bh * (uint64_t)T + (uint64_t)i) * (uint64_t)((T + 3) & ~3) + (uint64_t)j;
-    const uint64_t bits = dropout_bits4(drop.seed, e >> 2);
-    const int o = (int)(e & 3);   // j is even and T*.. may be odd: o in {0,1,2,3}; pair may straddle -> use two lookups
-    p0 = dropout_keep(bits, o, drop.thresh16) ? p0 * drop.scale : 0.f;
-    if (o < 3) {
-        p1 = dropout_keep(bits, o + 1, drop.thresh16) ? p1 * drop.scale : 0.f;
-    } else {
-        const uint64_t bits2 = dropout_bits4(drop.seed, (e + 1) >> 2);
-        p1 = dropout_keep(bits2, 0, drop.thresh16) ? p1 * drop.scale : 0.f;
-    }
+    uint32_t w0, w1;
+    attn_drop_words(attn_drop_row(drop.seed, bh * (uint64_t)T + (uint64_t)i), (uint32_t)j >> 2, w0, w1);
+    const uint32_t t32 = drop.thresh16 << 16;
+    p0 = attn_drop_keep(w0, w1, j & 3, t32) ? p0 * drop.scale : 0.f;
+    p1 = attn_drop_keep(w0, w1, (j & 3) + 1, t32) ? p1 * drop.scale : 0.f;      // j even -> j+1 is in the same group of 4
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,9 +359,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkdv_kernel(const bf16* 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int qi = qc + (e & 1), kj = (e < 2) ? key_a : key_b;
-                    const uint64_t idx = ((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)kj;
-                    const uint64_t bits = dropout_bits4(drop.seed, idx >> 2);
-                    const float mk = dropout_keep(bits, (int)(idx & 3), drop.thresh16) ? drop.scale : 0.f;
+                    const float mk = attn_drop_keep1(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi, kj, drop.thresh16) ? drop.scale : 0.f;
                     q4[e] *= mk;
                     g4[e] *= mk;
                 }
@@ -558,6 +550,19 @@ int attn_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse,
     TTTS_LAUNCH_CHECK("attn_bwd_dkdv");
     attn_bwd_dq_kernel<<<grid, ATT_THREADS, smem_q, st>>>(qkv, dout, lse, delta, dqkv, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_bwd_dq");
+    return TTTS_OK;
+}
+
+// keep mask of the attention-probability dropout, [BH, T, T] bytes (tests: lets torch reproduce the dropped attention exactly)
+__global__ void attn_dropout_mask_kernel(uint8_t* __restrict__ mask, int T, DropCfg drop) {
+    const int qi = blockIdx.x, bh = blockIdx.y;
+    for (int kj = threadIdx.x; kj < T; kj += blockDim.x)
+        mask[((size_t)bh * T + qi) * T + kj] = (!drop.thresh16 || attn_drop_keep1(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi, kj, drop.thresh16)) ? 1 : 0;
+}
+int attn_dropout_mask(uint8_t* mask, int BH, int T, DropCfg drop, cudaStream_t st) {
+    TTTS_CHECK_ARG(mask != nullptr && BH > 0 && T > 0, "attn_dropout_mask: bad arguments");
+    attn_dropout_mask_kernel<<<dim3(T, BH), 128, 0, st>>>(mask, T, drop);
+    TTTS_LAUNCH_CHECK("attn_dropout_mask");
     return TTTS_OK;
 }
 

@@ -170,6 +170,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         const float sl2 = scale * kLog2eF;
         float* xch = reinterpret_cast<float*>(smem + S::oXch);               // [buf][half][row]
         float m_run = -INFINITY, l_run = 0.f;                // l_run: partial row sum over THIS thread's keys
+        const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
+        const uint32_t t32 = drop.thresh16 << 16;
         float o[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = 0.f;
@@ -228,13 +230,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
                     for (int i = 0; i < 32; ++i) { pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc)); rs += pv[i]; }
                 }
                 if (drop.thresh16) {
-                    // one 64-bit mix per 4 consecutive keys (rows are padded to a multiple of 4 in the mask index space)
-                    const uint64_t e0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)(kc0 + c * 32)) >> 2;
+                    // keep decisions of 4 consecutive keys per multiply-fold hash (common.cuh); the 1/(1-p) scale is applied once, to O
+                    const uint32_t g0 = (uint32_t)(kc0 + c * 32) >> 2;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const uint64_t bits = dropout_bits4(drop.seed, e0 + i4);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) pv[i4 * 4 + i] = dropout_keep(bits, i, drop.thresh16) ? pv[i4 * 4 + i] * drop.scale : 0.f;
+                        uint32_t w0, w1;
+                        attn_drop_words(rk, g0 + i4, w0, w1);
+                        pv[i4 * 4 + 0] = (w0 >= t32) ? pv[i4 * 4 + 0] : 0.f;
+                        pv[i4 * 4 + 1] = ((w0 << 16) >= t32) ? pv[i4 * 4 + 1] : 0.f;
+                        pv[i4 * 4 + 2] = (w1 >= t32) ? pv[i4 * 4 + 2] : 0.f;
+                        pv[i4 * 4 + 3] = ((w1 << 16) >= t32) ? pv[i4 * 4 + 3] : 0.f;
                     }
                 }
 #pragma unroll
@@ -282,7 +287,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         named_bar_sync(2, 256);
         const float l_tot = l_run + xch[(4 + (half ^ 1)) * 128 + r];
         if (qi < T) {
-            const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+            const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;      // dropout's 1/(1-p) folded in here (scale = 1 when off)
             if (half == 0) lse_out[(size_t)bh * T + qi] = m_run * scale + logf(l_tot);
             uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + half * 32);
 #pragma unroll
@@ -412,6 +417,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * kLog2eF;
         const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
+        const uint32_t t32 = drop.thresh16 << 16;
         int it = 0;
         for (int i = jb; i < nq; ++i, ++it) {
             const uint32_t ph = it & 1 ? 1u : 0u;
@@ -420,6 +426,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             const float lse2 = q_ok ? lse[(size_t)bh * T + qi] * kLog2eF : 0.f;
             const float dlt = q_ok ? delta[(size_t)bh * T + qi] : 0.f;
             const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
+            const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
             const int kc0 = k0 + half * 64;
             mbar_wait(sdp_full, ph);
             tc_fence_after();
@@ -442,22 +449,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 32; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
                 }
+                // The softmax scale (a power of two) and the dropout scale are applied to the OUTPUTS (dQ, dK resp. dV), not per element:
+                //   ds = P (mask * dP / (1-p) - delta)      pd = mask * P
                 if (drop.thresh16) {
-                    const uint64_t e0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)qi) * (uint64_t)((T + 3) & ~3) + (uint64_t)(kc0 + c * 32)) >> 2;
+                    const uint32_t g0 = (uint32_t)(kc0 + c * 32) >> 2;
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
-                        const uint64_t bits = dropout_bits4(drop.seed, e0 + e4);
+                        uint32_t w0, w1;
+                        attn_drop_words(rk, g0 + e4, w0, w1);
+                        const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float mk = dropout_keep(bits, e, drop.thresh16) ? drop.scale : 0.f;
-                            const float pd = p[e4 * 4 + e] * mk;                                                         // dropped P feeds dV
-                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (__uint_as_float(gv[e4 * 4 + e]) * mk - dlt) * scale;       // dP = mask * (dO V^T)
-                            p[e4 * 4 + e] = pd;
+                            const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
+                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
+                            p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt) * scale;
+                    for (int e = 0; e < 32; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -504,6 +514,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             tmem_ld_wait();
             if (kj < T) {
 #pragma unroll
+                for (int e = 0; e < 32; ++e) { a[e] = __float_as_uint(__uint_as_float(a[e]) * scale); v[e] = __float_as_uint(__uint_as_float(v[e]) * drop.scale); }
+#pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     reinterpret_cast<uint4*>(dkp)[g] =
                         make_uint4(pack_bf16(__uint_as_float(a[8 * g]), __uint_as_float(a[8 * g + 1])), pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3])),
@@ -522,14 +534,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 }
 
 // fp32 dQ accumulation buffer [B*T, d] -> bf16 dqkv[:, 0:d]
-__global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, size_t rows, int d) {
+__global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, size_t rows, int d, float scale) {
     const size_t n4 = rows * (size_t)d / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 4;
         const size_t row = e / d;
         const int c = (int)(e - row * d);
         const float4 v = reinterpret_cast<const float4*>(dq_acc)[i];
-        *reinterpret_cast<uint2*>(dqkv + row * 3 * d + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        *reinterpret_cast<uint2*>(dqkv + row * 3 * d + c) = make_uint2(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale));
     }
 }
 
@@ -575,7 +587,7 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
     const size_t n4 = (size_t)B * T * d / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>(dq_acc, dqkv, (size_t)B * T, d);
+    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>(dq_acc, dqkv, (size_t)B * T, d, 0.125f);     // dQ = scale * dS K
     TTTS_LAUNCH_CHECK("attn_dq_convert");
     return TTTS_OK;
 }

@@ -146,11 +146,14 @@ TTTS_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // we trap so the launch fails loudly instead.
 TTTS_DEVICE uint64_t global_timer_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 TTTS_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0xffu) == 0 && global_timer_ns() - t0 > 2000000000ull) { asm volatile("trap;"); }
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {          // try_wait itself suspends the thread for a HW-defined window
+        if ((++spins & 0x3ffu) == 0) {
+            const uint64_t t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) { asm volatile("trap;"); }
+        }
     }
 }
 
@@ -214,7 +217,9 @@ TTTS_DEVICE void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 // arrive on the barrier at the same offset in the leader CTA (valid from either CTA of the pair)
 TTTS_DEVICE void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    // default semantics (.release at CTA scope): the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of
+    // every arrive (ncu: the peer's producer spent its time there and the CTA-pair GEMM ran at half speed, profiles/r1_notes.md)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 // 2-CTA TMA load: data lands in THIS CTA's smem, completion bytes are signalled on the LEADER CTA's barrier
 TTTS_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {

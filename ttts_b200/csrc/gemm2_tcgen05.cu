@@ -6,9 +6,9 @@
 // (profiles/r1_notes.md).
 //
 // Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM alloc, warps 2-9 =
-// epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 2:
-// leader's arrive.expect_tx + the peer's remote arrive; both CTAs' TMA bytes complete_tx there), empty[] / tmem_full[] are
-// per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 256 epilogue threads).
+// epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 1:
+// the leader's arrive.expect_tx covers both CTAs' bytes; both CTAs' TMA complete_tx there), empty[] / tmem_full[] are
+// per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 8 epilogue warps).
 #include <string.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -78,8 +78,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], C::kCtas); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 256 * C::kCtas); }
+        // full[]: ONE arrival (the leader's arrive.expect_tx for both CTAs' bytes); the peer's TMA only complete_tx's there
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * C::kCtas); }     // one arrival per epilogue warp
         fence_barrier_init();
     }
     if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_holder, 512); else tmem_alloc(tmem_holder, 512); }
@@ -105,7 +106,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     uint8_t* sa = smem + stage * G2_STAGE_BYTES;
                     uint8_t* sb = sa + G2_A_BYTES;
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::kCtas * G2_STAGE_BYTES);
-                    else mbar_arrive_leader(&full_bar[stage]);
                     auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
                         if (PAIR) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
                         else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
@@ -222,7 +222,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             epi_apply_staged(p, row0w, n0 + (c0 + 2) * 32, lane, rA, sb + 64, xA, S);
             tmem_ld_wait();
             tc_fence_before();
-            if (PAIR) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);   // accumulator stage drained
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }   // accumulator stage drained
             epi_apply_staged(p, row0w, n0 + (c0 + 3) * 32, lane, rB, sb + 96, xB, S);
         }
     }

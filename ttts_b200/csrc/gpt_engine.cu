@@ -456,6 +456,9 @@ int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
     return attn_bwd((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, delta, (bf16*)dqkv, B, T, H, user_drop(drop_p, seed),
                     (cudaStream_t)stream);
 }
+int ttts_attn_dropout_mask(uint8_t* mask, int32_t BH, int32_t T, float drop_p, uint64_t seed, void* stream) {
+    return attn_dropout_mask(mask, BH, T, user_drop(drop_p, seed), (cudaStream_t)stream);
+}
 int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, float* row_loss, float* row_lse, float* loss_out,
                 void* stream) {
     return ce_fwd((const bf16*)logits, ld, V, targets, rows, row_loss, row_lse, loss_out, (cudaStream_t)stream);
