@@ -190,6 +190,17 @@ TTTS_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
 TTTS_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 TTTS_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One elected lane of a fully converged warp.  The single-thread instructions (tcgen05.mma / commit, TMA) take their operands from
+// UNIFORM registers: issued from inside `if (lane == 0)` the compiler must move every operand there with ELECT + R2UR.BROADCAST inside
+// a BRA.U.ANY retry loop (~21 SASS instructions and ~200 cycles per MMA: ncu showed that loop, not the tensor pipe, bounding the GEMM and
+// the attention kernels).  With the whole warp running the role loop and only the instruction itself predicated on elect_one(), the
+// descriptors are computed on the uniform datapath and an MMA costs a handful of instructions.
+TTTS_DEVICE bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, single CTA.
 TTTS_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -264,6 +275,23 @@ TTTS_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 TTTS_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-column forms (one TMEM lane per thread, 16 consecutive fp32 columns) + the matching store
+TTTS_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+TTTS_DEVICE void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+TTTS_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format, version=1, SWIZZLE_128B).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

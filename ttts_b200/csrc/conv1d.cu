@@ -9,6 +9,7 @@
 // indices" contract meaningful this stays on the FP32 FMA pipe.  Channel counts are tiny (16..192, 1025 for the 1x1 `pre`),
 // so a register-tiled direct convolution (implicit GEMM on CUDA cores) is the right tool: CTA tile = 64 output channels x
 // 64 time steps, input window and weight slab staged through shared memory per 16-input-channel chunk, 4x4 outputs/thread.
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "kernels.h"
@@ -147,6 +148,153 @@ __global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Implicit-GEMM form (default):  Y[co, p] = sum_r W[co, r] * Xcol[r, p],  r = ci*K + k,  p = b*Tout + t  (batch and time FLATTENED,
+// so T = 36 frames or T = 1 pack into full 64-position tiles, and any K / stride / dilation is a runtime property of the loader, not of
+// the inner loop).  CTA tile = CO_T (64 or 32) output channels x 64 positions, 16 r-rows per chunk, double-buffered shared memory with
+// the next chunk's global loads in flight during the FMAs, 4x4 outputs per thread.  The accumulation order over r is the same as in the
+// window kernel above, so both produce bit-identical results.
+// Why: the encoder launch list (profiles/r1c_launches_vqenc_summary.txt) showed the window kernel at ~5.6 TFLOP/s: 64x64 tiles half
+// empty for Cout = 32 or T = 36, tiny grids, runtime-K inner loops.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int IG_P = 64, IG_R = 16;
+
+template <int CO_T>
+__global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_kernel(const ConvParams p) {
+    constexpr int NT = CO_T * 4;                 // threads: (CO_T/4) x 16
+    constexpr int LDA = CO_T + 4, LDB = IG_P + 4;
+    constexpr int NB = IG_R * IG_P / NT;         // B-tile elements per thread (4 or 8)
+    __shared__ __align__(16) float sA[2][IG_R][LDA];
+    __shared__ __align__(16) float sB[2][IG_R][LDB];
+    const int gated = (p.post == 1 || p.post == 3);
+    const int Chalf = p.Cout >> 1;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int p0 = blockIdx.x * IG_P;
+    const int co0 = blockIdx.y * (gated ? CO_T / 2 : CO_T);
+    const int R = p.Cin * p.K;
+    const int Ptot = p.B * p.Tout;
+    const int nchunks = (R + IG_R - 1) / IG_R;
+
+    // ---- B loader: this thread always loads column cb (one output position), rows rb0 + (NT/64)*i
+    const int cb = tid & 63, rb0 = tid >> 6;
+    const int posb = p0 + cb;
+    const bool pos_ok = posb < Ptot;
+    const int bb = pos_ok ? posb / p.Tout : 0;
+    const int tb = pos_ok ? posb - bb * p.Tout : 0;
+    const float* xb = p.x + (size_t)bb * p.Cin * p.Tin;
+    const int ti0 = tb * p.stride - p.pad;
+    // ---- A loader: row (output channel) ca, r-columns ra4..ra4+3
+    const int ca = tid >> 2, ra4 = (tid & 3) * 4;
+    int coa; bool coa_ok;
+    if (gated) { const int cl = ca < CO_T / 2 ? ca : ca - CO_T / 2; coa_ok = (co0 + cl) < Chalf; coa = (ca < CO_T / 2 ? 0 : Chalf) + co0 + cl; }
+    else { coa = co0 + ca; coa_ok = coa < p.Cout; }
+    const float* wa = p.w + (size_t)coa * R;
+
+    float ra[4], rbv[NB];
+    auto gload = [&](int chunk) {
+        const int r0 = chunk * IG_R;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const int rr = r0 + ra4 + i; ra[i] = (coa_ok && rr < R) ? __ldg(wa + rr) : 0.f; }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int rr = r0 + rb0 + (NT / 64) * i;
+            const int ci = rr / p.K, k = rr - ci * p.K;
+            const int ti = ti0 + k * p.dil;
+            float v = 0.f;
+            if (pos_ok && rr < R && ti >= 0 && ti < p.Tin) {
+                v = __ldg(xb + (size_t)ci * p.Tin + ti);
+                if (p.pre_lrelu) v = v > 0.f ? v : 0.1f * v;
+            }
+            rbv[i] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sA[buf][ra4 + i][ca] = ra[i];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) sB[buf][rb0 + (NT / 64) * i][cb] = rbv[i];
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) gload(c + 1);
+#pragma unroll
+        for (int r = 0; r < IG_R; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&sA[buf][r][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[buf][r][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        if (c + 1 < nchunks) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---------------- epilogue ----------------
+    if (!gated) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = p0 + tx * 4 + j;
+            if (pos >= Ptot) continue;
+            const int b = pos / p.Tout, t = pos - b * p.Tout;
+            const float mk = p.mask ? p.mask[(size_t)b * p.Tout + t] : 1.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = co0 + ty * 4 + i;
+                if (co >= p.Cout) continue;
+                float v = acc[i][j] + (p.bias ? __ldg(p.bias + co) : 0.f);
+                if (p.post == 2) v = mish_f(v);
+                const size_t o = ((size_t)b * p.Cout + co) * p.Tout + t;
+                if (p.resid) v += p.resid[o];
+                v *= p.out_scale;
+                if (p.mask) v *= mk;
+                p.y[o] = p.accumulate ? p.y[o] + v : v;
+            }
+        }
+    } else {
+        // rows < CO_T/2 of the tile are "a" channels, rows >= CO_T/2 the matching "b" channels -> exchange through shared memory
+        __shared__ float sgate[CO_T][IG_P + 1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sgate[ty * 4 + i][tx * 4 + j] = acc[i][j];
+        __syncthreads();
+        for (int i = tid; i < (CO_T / 2) * IG_P; i += NT) {
+            const int cl = i / IG_P, pl = i - cl * IG_P;
+            const int c = co0 + cl, pos = p0 + pl;
+            if (c >= Chalf || pos >= Ptot) continue;
+            const int b = pos / p.Tout, t = pos - b * p.Tout;
+            float a = sgate[cl][pl] + (p.bias ? __ldg(p.bias + c) : 0.f);
+            float g = sgate[cl + CO_T / 2][pl] + (p.bias ? __ldg(p.bias + Chalf + c) : 0.f);
+            float v;
+            if (p.post == 1) {
+                v = a * (1.f / (1.f + expf(-g)));                                         // GLU
+            } else {
+                if (p.cond) { a += p.cond[(size_t)b * p.cond_ld + c]; g += p.cond[(size_t)b * p.cond_ld + Chalf + c]; }
+                v = tanhf(a) * (1.f / (1.f + expf(-g)));                                  // WN gate
+            }
+            const size_t o = ((size_t)b * Chalf + c) * p.Tout + t;
+            if (p.resid) v += p.resid[o];
+            v *= p.out_scale;
+            if (p.mask) v *= p.mask[(size_t)b * p.Tout + t];
+            p.y[o] = p.accumulate ? p.y[o] + v : v;
+        }
+    }
+}
+
 // weight norm: w[co, :] = g[co] * v[co, :] / ||v[co, :]||      (torch.nn.utils.weight_norm, dim=0)
 __global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int Cout, int n) {
     const int co = blockIdx.x;
@@ -227,6 +375,25 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
     p.x = x; p.w = w; p.bias = bias; p.y = y; p.B = B; p.Cin = Cin; p.Tin = Tin; p.Cout = Cout; p.Tout = Tout; p.K = K; p.stride = stride;
     p.dil = dil; p.pad = pad; p.pre_lrelu = pre_lrelu; p.resid = resid; p.out_scale = out_scale; p.accumulate = accumulate; p.mask = mask;
     p.post = post; p.cond = cond; p.cond_ld = cond_ld;
+    static int use_v1 = -1;
+    if (use_v1 < 0) { const char* e = getenv("TTTS_CONV_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (!use_v1) {
+        const long long Ptot = (long long)B * Tout;
+        TTTS_CHECK_ARG(Ptot < (1ll << 31) && (long long)Cin * K < (1ll << 31), "conv1d: problem too large");
+        const int ceff = gated ? Cout / 2 : Cout;                  // channels a CTA row tile is cut from
+        // 32-channel tiles when the layer has few output channels (or few CTAs): no half-empty tiles, more CTAs in flight
+        const long long ctas64 = ((Ptot + IG_P - 1) / IG_P) * ((ceff + (gated ? 31 : 63)) / (gated ? 32 : 64));
+        const bool small = (gated ? ceff <= 16 : ceff <= 32) || ctas64 < 2 * num_sms();
+        if (small) {
+            dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 15 : 31)) / (gated ? 16 : 32));
+            conv1d_igemm_kernel<32><<<grid, 128, 0, st>>>(p);
+        } else {
+            dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 31 : 63)) / (gated ? 32 : 64));
+            conv1d_igemm_kernel<64><<<grid, 256, 0, st>>>(p);
+        }
+        TTTS_LAUNCH_CHECK("conv1d_igemm");
+        return TTTS_OK;
+    }
     const int win = (CV_T - 1) * stride + (K - 1) * dil + 1;
     size_t smem = ((size_t)CV_CI * win + (size_t)CV_CI * K * CV_CO) * sizeof(float);
     if (smem < (size_t)CV_CO * CV_T * sizeof(float)) smem = (size_t)CV_CO * CV_T * sizeof(float);

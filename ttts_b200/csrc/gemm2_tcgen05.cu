@@ -91,20 +91,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer (both CTAs) =================
-            int stage = 0; uint32_t phase = 0;
-            for (int item = cluster_id; item < total_items; item += num_clusters) {
-                int m_pair, n_blk, split;
-                decode_item2(p, item, m_pair, n_blk, split);
-                const int m0 = m_pair * C::kTileM + (int)rank * G2_BM;
-                const int n0 = n_blk * G2_BN + (int)rank * (G2_BN / 2);
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-                    uint8_t* sb = sa + G2_A_BYTES;
+        // ================= TMA producer (both CTAs): the whole warp runs the loop, one elected lane issues =================
+        int stage = 0; uint32_t phase = 0;
+        for (int item = cluster_id; item < total_items; item += num_clusters) {
+            int m_pair, n_blk, split;
+            decode_item2(p, item, m_pair, n_blk, split);
+            const int m0 = m_pair * C::kTileM + (int)rank * G2_BM;
+            const int n0 = n_blk * G2_BN + (int)rank * (G2_BN / 2);
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+                uint8_t* sb = sa + G2_A_BYTES;
+                if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::kCtas * G2_STAGE_BYTES);
                     auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
                         if (PAIR) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
@@ -130,15 +130,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     } else {
                         load(sb, &tmB, kb * G2_BK, n0);
                     }
-                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ================= MMA issuer (leader CTA only) =================
+        if (leader) {
+            // ================= MMA issuer (leader CTA only): warp-uniform loop, elected lane issues =================
             constexpr uint32_t idesc = make_idesc_bf16(C::kTileM, G2_BN, A_MN, B_MN);
+            constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4);      // descriptor start-address step per K=16 slice
+            constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
+            const uint32_t smem_base = smem_u32(smem);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
@@ -154,22 +157,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
                     const uint32_t sb = sa + G2_A_BYTES;
+                    const uint64_t adesc0 = A_MN ? make_smem_desc_sw128(sa, G2_BK * 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc0 = B_MN ? make_smem_desc_sw128(sb, G2_BK * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < G2_BK / 16; ++k) {
-                        const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, G2_BK * 128, 1024) : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < G2_BK / 16; ++k) {
+                            if (PAIR) umma_bf16_2sm(tmem_d, adesc0 + k * kStepA, bdesc0 + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(tmem_d, adesc0 + k * kStepA, bdesc0 + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     }
-                    if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (PAIR) umma_commit_2sm(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+                if (elect_one()) { if (PAIR) umma_commit_2sm(&tfull_bar[as]); else umma_commit(&tfull_bar[as]); }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp >= 2) {
         // ================= epilogue (both CTAs, 8 warps) =================
         // Software-pipelined: the tile's bias is staged in smem and the first chunk's residual / pre-activation loads are

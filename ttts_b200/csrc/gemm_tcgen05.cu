@@ -76,8 +76,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
+    // role warps: all 32 lanes run the loop, one elected lane issues the TMA / tcgen05 instructions (common.cuh elect_one)
     if (warp == 0) {
-      if (lane == 0) {
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -90,28 +90,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * S::kStageBytes;
                 uint8_t* sb = sa + S::kABytes;
-                mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-                if (A_MN) {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                    if (A_MN) {
 #pragma unroll
-                    for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
-                } else {
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-                }
-                if (B_MN) {
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
-                } else {
-                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                    } else {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                    }
                 }
+                __syncwarp();
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
         }
-      }
-      __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+        constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4);
+        constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
+        const uint32_t smem_base = smem_u32(smem);
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -127,23 +130,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+                const uint32_t sa = smem_base + stage * S::kStageBytes;
                 const uint32_t sb = sa + S::kABytes;
+                const uint64_t adesc0 = A_MN ? make_smem_desc_sw128(sa, BK * 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+                const uint64_t bdesc0 = B_MN ? make_smem_desc_sw128(sb, BK * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                                          : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                    uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                                          : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_d, adesc0 + k * kStepA, bdesc0 + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
                 }
-                umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull_bar[as]);
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
         }
-      }
-      __syncwarp();
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int q = warp & 3;
