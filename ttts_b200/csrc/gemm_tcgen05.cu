@@ -202,11 +202,12 @@ static int launch_gemm(const ttts_gemm_args& a, const GemmParams& p, int grid, c
     return TTTS_OK;
 }
 
-// The CTA-pair kernel (gemm2_tcgen05.cu) is correct but measured SLOWER than this one in round 1 (profiles/r1_notes.md), so
-// it is opt-in: TTTS_GEMM_2CTA=1.
+// The CTA-pair kernel (gemm2_tcgen05.cu, 256x256 tile per SM pair) is the default: it moves 1/3 less operand traffic L2 -> SM per
+// FLOP than a 128x256 single-CTA tile, and L2 -> SM bandwidth is what bounds these GEMMs (ncu: 5.8 kB/clk chip-wide against a
+// ~6.3 kB/clk cap, profiles/r1_notes.md).  TTTS_GEMM_2CTA=0 selects the single-CTA variant of the same kernel (A/B testing).
 bool use_2cta(int M, int N) {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("TTTS_GEMM_2CTA"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on < 0) { const char* e = getenv("TTTS_GEMM_2CTA"); on = (e && e[0] == '0') ? 0 : 1; }
     return on && N > 128 && M > 128;
 }
 
@@ -231,7 +232,7 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     if (a.epi == TTTS_EPI_GELU && a.aux_out) TTTS_CHECK_ARG((a.ldaux_out * 2) % 16 == 0 && ((uintptr_t)a.aux_out & 15) == 0, "gemm: aux_out not aligned");
     if (a.bias) TTTS_CHECK_ARG(((uintptr_t)a.bias & 15) == 0, "gemm: bias not 16B aligned");
 
-    // N > 128: the pipelined-epilogue kernel (gemm2_tcgen05.cu), single CTA by default, CTA pair with TTTS_GEMM_2CTA=1;
+    // N > 128: the pipelined-epilogue kernel (gemm2_tcgen05.cu), CTA pair by default, single CTA with TTTS_GEMM_2CTA=0;
     // TTTS_GEMM_LEGACY=1 keeps everything on the simple kernel below (A/B testing).
     if (a.N > 128 && !use_legacy_gemm()) return gemm2_bf16(a, use_2cta(a.M, a.N), stream);
     const int BN = (a.N > 128) ? 256 : 128;
