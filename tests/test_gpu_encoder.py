@@ -107,3 +107,19 @@ def test_encode_graphed_matches_eager(model):
     for B in (4, 4, 7):
         wav = torch.clamp(0.1 * torch.randn(B, 23040, device="cuda", generator=g), -1, 1)
         assert torch.equal(model.encode_graphed(wav), model(wav)["codes"])
+
+
+def test_batched_extractor_equals_per_clip(model, tmp_path):
+    """ttts_b200.prepare.extract_vq on the real sm_100a encoder: codes written by the batched, CUDA-graph path are bit-identical to encoding
+    every clip alone (the reference's one-file-at-a-time extraction), and the files hold list[int] (ttts/prepare/extract_vq.py:22-24)."""
+    from ttts_b200.prepare import extract_vq as X
+    g = torch.Generator().manual_seed(9)
+    lens = [640 * 36, 640 * 36, 640 * 37 + 100, 640 * 50, 640 * 36, 640 * 50 + 7]
+    clips = {str(tmp_path / ("c%d" % i)): torch.clamp(0.2 * torch.randn(n, generator=g), -1.5, 1.5) for i, n in enumerate(lens)}
+    done = X.extract_vq(list(clips), model, load_fn=lambda p: clips[p], batch_size=4, device="cuda")
+    assert set(done) == set(clips)
+    for p, w in clips.items():
+        got = torch.load(p + ".vq.pth")
+        cw = X.condition_wav(w).cuda().unsqueeze(0)
+        alone = model(cw)["codes"][0, 0].tolist()
+        assert isinstance(got, list) and got == alone and len(got) == cw.shape[1] // 1280

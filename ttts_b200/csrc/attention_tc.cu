@@ -1047,6 +1047,571 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Version 4 = version 3 made PERSISTENT: one CTA per SM walks a list of (query block, head) items, heavy items first.  TMEM is
+// allocated once, the barrier phases run on across items, the TMA warp prefetches the next item's Q / K / V while the current item is
+// still being processed, and the MMA warp issues S of the next item's first key block before the last P V of the current one: the
+// per-CTA prologue / epilogue that cost ~1 000 (forward) - 2 600 (backward) cycles per 128x128 block pair at T = 1 156 (5.5 block pairs
+// per CTA on average, profiles/r1_notes.md) is overlapped instead of exposed.
+// ------------------------------------------------------------------------------------------------------------
+struct Fwd4Smem {
+    static constexpr int kKvStages = 3;
+    static constexpr int oQ = 0;                                        // [2]
+    static constexpr int oKV = 2 * AT_TILE;                             // [stages][K | V]
+    static constexpr int oP = oKV + kKvStages * 2 * AT_TILE;            // [2][2 atoms]
+    static constexpr int oBar = oP + 2 * 2 * AT_TILE;
+    static constexpr int oXch = oBar + 256;                             // row max [2][4][128] + row sum [4][128] floats
+    static constexpr int kBytes = oXch + (2 * 4 * 128 + 4 * 128) * 4 + 1024;
+};
+
+__global__ void __maxnreg__(96)
+attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, int BH, float scale,
+                    DropCfg drop) {
+    using S = Fwd4Smem;
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
+    uint64_t* q_full = bars;                       // [2]
+    uint64_t* q_empty = bars + 2;                  // [2] commit: every S MMA of the item has read Q
+    uint64_t* kv_full = bars + 4;                  // [3]
+    uint64_t* kv_empty = bars + 7;                 // [3]
+    uint64_t* s_full = bars + 10;                  // [2]
+    uint64_t* s_empty = bars + 12;                 // [2]  16
+    uint64_t* p_full = bars + 14;                  // [2]  16
+    uint64_t* p_empty = bars + 16;                 // [2]
+    uint64_t* o_full = bars + 18;                  // completes once per key block, phases counted over the whole item list
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = H * 64;
+    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int total = nq * BH;
+    // Items are numbered head-major (all query blocks of a head are neighbours, late = heavy blocks first) and dealt out in rounds of
+    // gridDim.x: in round n this CTA takes position (blockIdx.x + n) mod gridDim.x.  CTAs running at the same time therefore work on
+    // ~gridDim.x / nq neighbouring heads (their K/V stay in L2), and the rotation walks every CTA through all block weights.
+    const int rounds = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)((blockIdx.x + n) % gridDim.x); return idx < total ? idx : -1; };
+    auto item_qb = [&](int idx) { return nq - 1 - idx % nq; };
+    auto item_bh = [&](int idx) { return idx / nq; };
+    auto item_nkv = [&](int qb) { return min(qb + 1, (T + AT_BN - 1) / AT_BN); };
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQKV);
+        for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        for (int s = 0; s < S::kKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 16);
+            mbar_init(&p_full[s], 16); mbar_init(&p_empty[s], 1);
+        }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tS = tmem_base;              // [2] x 128 cols
+    const uint32_t tO = tmem_base + 256;        // 64 cols
+
+    if (warp == 0) {
+        // ---------------- TMA: Q per item (double-buffered), K/V ring across items ----------------
+        uint32_t kvc = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int qb = item_qb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int row_base = b * T, nkv = item_nkv(qb);
+            mbar_wait(&q_empty[n & 1], ((n >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&q_full[n & 1], AT_TILE);
+                tma_load_2d(smem + S::oQ + (n & 1) * AT_TILE, &tmQKV, &q_full[n & 1], h * 64, row_base + qb * AT_BM);
+            }
+            __syncwarp();
+            for (int j = 0; j < nkv; ++j, ++kvc) {
+                const int st = kvc % S::kKvStages; const uint32_t ph = (kvc / S::kKvStages) & 1;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                uint8_t* sk = smem + S::oKV + st * 2 * AT_TILE;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
+                    tma_load_2d(sk, &tmQKV, &kv_full[st], d + h * 64, row_base + j * AT_BN);
+                    tma_load_2d(sk + AT_TILE, &tmQKV, &kv_full[st], 2 * d + h * 64, row_base + j * AT_BN);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA: S runs exactly one key block ahead of P V, across item boundaries ----------------
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+        const uint32_t smem_base = smem_u32(smem);
+        // S cursor
+        int nS = 0, jS = 0, idxS = item_at(0), nkvS = idxS >= 0 ? item_nkv(item_qb(idxS)) : 0;
+        uint32_t gS = 0;
+        auto issue_next_s = [&]() {
+            if (idxS < 0) return;
+            if (jS == 0) mbar_wait(&q_full[nS & 1], (nS >> 1) & 1);
+            const int st = gS % S::kKvStages;
+            mbar_wait(&kv_full[st], (gS / S::kKvStages) & 1);
+            mbar_wait(&s_empty[gS & 1], ((gS >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t dQ = desc_kmajor(smem_base + S::oQ + (nS & 1) * AT_TILE, 0);
+            const uint64_t dK = desc_kmajor(smem_base + S::oKV + st * 2 * AT_TILE, 0);
+            const bool last = (jS == nkvS - 1);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tS + (gS & 1) * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[gS & 1]);
+                if (last) umma_commit(&q_empty[nS & 1]);
+            }
+            __syncwarp();
+            ++gS; ++jS;
+            if (last) { ++nS; idxS = item_at(nS); jS = 0; nkvS = idxS >= 0 ? item_nkv(item_qb(idxS)) : 0; }
+        };
+        issue_next_s();
+        uint32_t g = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int nkv = item_nkv(item_qb(idx));
+            for (int j = 0; j < nkv; ++j, ++g) {
+                issue_next_s();
+                const int st = g % S::kKvStages;
+                mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P in smem, any rescale of O done, (j == 0) previous item's O read out
+                tc_fence_after();
+                const uint64_t dP = desc_kmajor(smem_base + S::oP + (g & 1) * 2 * AT_TILE, 0);
+                const uint64_t dV = desc_mnmajor(smem_base + S::oKV + st * 2 * AT_TILE + AT_TILE, 0);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tO, dP + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), dV + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(o_full);
+                    umma_commit(&p_empty[g & 1]);
+                    umma_commit(&kv_empty[st]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int qtr = (warp - 2) >> 2;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * kLog2eF;
+        float* xmax = reinterpret_cast<float*>(smem + S::oXch);               // [buf][qtr][row]
+        float* xsum = xmax + 2 * 4 * 128;                                     // [qtr][row]
+        const uint32_t t32 = drop.thresh16 << 16;
+        uint32_t g = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int qb = item_qb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int row_base = b * T, nkv = item_nkv(qb);
+            const int qi = qb * AT_BM + r;
+            float m_used = -INFINITY, l_run = 0.f;
+            const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int k0 = j * AT_BN;
+                const bool need_mask = (j == qb) || (k0 + AT_BN > T);
+                const int kc0 = k0 + qtr * 32;
+                uint32_t v[32];
+                mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                __syncwarp();
+                tmem_ld_32x32(tS + (g & 1) * 128 + lane_off + qtr * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[g & 1]);
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+                if (need_mask) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int kj = kc0 + i;
+                        if (!(kj <= qi && kj < T)) v[i] = 0xff800000u;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
+                xmax[((g & 1) * 4 + qtr) * 128 + r] = fmaxf(mx0, mx1);
+                named_bar_sync(2, 512);
+                const float* xm = xmax + (g & 1) * 4 * 128 + r;
+                const float m_new = fmaxf(fmaxf(fmaxf(xm[0], xm[128]), fmaxf(xm[256], xm[384])), m_used);
+                if (j == 0) {
+                    m_used = m_new;
+                } else {
+                    const bool grow = (m_new - m_used) * sl2 > 8.f;
+                    if (__any_sync(0xffffffffu, grow)) {
+                        const float f = grow ? ex2_fast((m_used - m_new) * sl2) : 1.f;
+                        mbar_wait(o_full, (g - 1) & 1);
+                        tc_fence_after();
+                        uint32_t o[16];
+                        __syncwarp();
+                        tmem_ld_32x16(tO + lane_off + qtr * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                        tmem_st_32x16(tO + lane_off + qtr * 16, o);
+                        tmem_st_wait();
+                        l_run *= f;
+                        if (grow) m_used = m_new;
+                    }
+                }
+                const float msc = m_used * sl2;
+                float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc));
+                    const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
+                    const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -msc));
+                    const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -msc));
+                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                    v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
+                }
+                l_run += (rs0 + rs1) + (rs2 + rs3);
+                if (drop.thresh16) {
+                    const uint32_t g0 = (uint32_t)kc0 >> 2;
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        uint32_t w0, w1;
+                        attn_drop_words(rk, g0 + i4, w0, w1);
+                        v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
+                        v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
+                        v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
+                        v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
+                    }
+                }
+                mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                const uint32_t sP = smem_u32(smem + S::oP + (g & 1) * 2 * AT_TILE);
+#pragma unroll
+                for (int gg = 0; gg < 4; ++gg)
+                    st_tile_chunk(sP, r, qtr * 4 + gg,
+                                  make_uint4(pack_bf16(__uint_as_float(v[8 * gg]), __uint_as_float(v[8 * gg + 1])),
+                                             pack_bf16(__uint_as_float(v[8 * gg + 2]), __uint_as_float(v[8 * gg + 3])),
+                                             pack_bf16(__uint_as_float(v[8 * gg + 4]), __uint_as_float(v[8 * gg + 5])),
+                                             pack_bf16(__uint_as_float(v[8 * gg + 6]), __uint_as_float(v[8 * gg + 7]))));
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g & 1]);
+            }
+            // item epilogue: O / l (dropout's 1/(1-p) folded in), lse.  The next item's first P V (which overwrites O) cannot be issued
+            // before every softmax warp has passed this point and arrived on that block's p_full.
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            uint32_t o[16];
+            __syncwarp();
+            tmem_ld_32x16(tO + lane_off + qtr * 16, o);
+            tmem_ld_wait();
+            tc_fence_before();
+            xsum[qtr * 128 + r] = l_run;
+            named_bar_sync(2, 512);
+            const float l_tot = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
+            if (qi < T) {
+                const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;
+                if (qtr == 0) lse_out[(size_t)bh * T + qi] = m_used * scale + logf(l_tot);
+                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + qtr * 16);
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg)
+                    dst[gg] = make_uint4(pack_bf16(__uint_as_float(o[8 * gg]) * inv, __uint_as_float(o[8 * gg + 1]) * inv),
+                                         pack_bf16(__uint_as_float(o[8 * gg + 2]) * inv, __uint_as_float(o[8 * gg + 3]) * inv),
+                                         pack_bf16(__uint_as_float(o[8 * gg + 4]) * inv, __uint_as_float(o[8 * gg + 5]) * inv),
+                                         pack_bf16(__uint_as_float(o[8 * gg + 6]) * inv, __uint_as_float(o[8 * gg + 7]) * inv));
+            }
+            // xsum is rewritten only after the next item's row-max barriers: no extra sync needed (every item has >= 1 key block)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// backward, persistent (see the forward above).  Items = (key block, head), heavy (early) key blocks first; K/V double-buffered so the
+// next item's tiles arrive while the current one finishes; S/dP run one query block ahead of the gradient GEMMs across item boundaries.
+struct Bwd4Smem {
+    static constexpr int oKV = 0;                             // [2][K | V]
+    static constexpr int oQdO = 2 * 2 * AT_TILE;              // [2 stages][Q | dO]
+    static constexpr int oP = oQdO + 2 * 2 * AT_TILE;         // 2 atoms
+    static constexpr int oDS = oP + 2 * AT_TILE;              // 2 atoms
+    static constexpr int oBar = oDS + 2 * AT_TILE;
+    static constexpr int kBytes = oBar + 256 + 1024;
+};
+
+__global__ void __maxnreg__(96)
+attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
+                    const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, int BH, float scale,
+                    DropCfg drop) {
+    using S = Bwd4Smem;
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
+    uint64_t* kv_full = bars;                 // [2]
+    uint64_t* kv_empty = bars + 2;            // [2] commit after the item's last gradient MMA
+    uint64_t* qdo_full = bars + 4;            // [2]
+    uint64_t* qdo_empty = bars + 6;           // [2]
+    uint64_t* sdp_full = bars + 8;            // commit
+    uint64_t* sdp_empty = bars + 9;           // 16
+    uint64_t* pds_full = bars + 10;           // 16
+    uint64_t* pds_empty = bars + 11;          // commit
+    uint64_t* dq_full = bars + 12;            // commit
+    uint64_t* dq_empty = bars + 13;           // 16
+    uint64_t* dkv_empty = bars + 14;          // 16: dK / dV of the finished item have been read out of TMEM
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = H * 64, ld3 = 3 * d;
+    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int total = nq * BH;
+    // head-major items dealt out in rotating rounds (see the forward kernel): concurrent CTAs share a few heads, so Q / dO / K / V and the
+    // fp32 dQ accumulator rows they red.add into stay in L2 (with key-block-major items the accumulator traffic went to HBM)
+    const int rounds = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)((blockIdx.x + n) % gridDim.x); return idx < total ? idx : -1; };
+    auto item_jb = [&](int idx) { return idx % nq; };
+    auto item_bh = [&](int idx) { return idx / nq; };
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1);
+        }
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 16);
+        mbar_init(pds_full, 16); mbar_init(pds_empty, 1);
+        mbar_init(dq_full, 1); mbar_init(dq_empty, 16);
+        mbar_init(dkv_empty, 16);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+    if (warp == 0) {
+        uint32_t c = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int jb = item_jb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int row_base = b * T, k0 = jb * AT_BN, nit = nq - jb;
+            mbar_wait(&kv_empty[n & 1], ((n >> 1) & 1) ^ 1);
+            uint8_t* sk = smem + S::oKV + (n & 1) * 2 * AT_TILE;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&kv_full[n & 1], 2 * AT_TILE);
+                tma_load_2d(sk, &tmQKV, &kv_full[n & 1], d + h * 64, row_base + k0);
+                tma_load_2d(sk + AT_TILE, &tmQKV, &kv_full[n & 1], 2 * d + h * 64, row_base + k0);
+            }
+            __syncwarp();
+            for (int it = 0; it < nit; ++it, ++c) {
+                const int st = c & 1, i = jb + it;
+                mbar_wait(&qdo_empty[st], ((c >> 1) & 1) ^ 1);
+                uint8_t* sq = smem + S::oQdO + st * 2 * AT_TILE;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&qdo_full[st], 2 * AT_TILE);
+                    tma_load_2d(sq, &tmQKV, &qdo_full[st], h * 64, row_base + i * AT_BM);
+                    tma_load_2d(sq + AT_TILE, &tmDO, &qdo_full[st], h * 64, row_base + i * AT_BM);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);    // S, dP
+        constexpr uint32_t idesc_g = make_idesc_bf16(128, 64, true, true);       // dV, dK
+        constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);      // dQ
+        const uint32_t smem_base = smem_u32(smem);
+        const uint64_t dP_mn = desc_mnmajor(smem_base + S::oP, 0), dDS_mn = desc_mnmajor(smem_base + S::oDS, 0);
+        const uint64_t dDS_k = desc_kmajor(smem_base + S::oDS, 0);
+        // S / dP cursor: one query block ahead of the gradient MMAs
+        int n1 = 0, it1 = 0, idx1 = item_at(0), nit1 = idx1 >= 0 ? nq - item_jb(idx1) : 0;
+        uint32_t c1 = 0;
+        auto issue_next_sdp = [&]() {
+            if (idx1 < 0) return;
+            if (it1 == 0) mbar_wait(&kv_full[n1 & 1], (n1 >> 1) & 1);
+            mbar_wait(&qdo_full[c1 & 1], (c1 >> 1) & 1);
+            mbar_wait(sdp_empty, (c1 & 1) ^ 1);                 // S / dP of iteration c1 - 1 are in registers
+            tc_fence_after();
+            const uint32_t sKV = smem_base + S::oKV + (n1 & 1) * 2 * AT_TILE;
+            const uint32_t sQ = smem_base + S::oQdO + (c1 & 1) * 2 * AT_TILE;
+            const uint64_t dK_k = desc_kmajor(sKV, 0), dV_k = desc_kmajor(sKV + AT_TILE, 0);
+            const uint64_t dQ_k = desc_kmajor(sQ, 0), dDO_k = desc_kmajor(sQ + AT_TILE, 0);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tS, dQ_k + 2 * k, dK_k + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tDP, dDO_k + 2 * k, dV_k + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(sdp_full);
+            }
+            __syncwarp();
+            ++c1; ++it1;
+            if (it1 == nit1) { ++n1; idx1 = item_at(n1); it1 = 0; nit1 = idx1 >= 0 ? nq - item_jb(idx1) : 0; }
+        };
+        issue_next_sdp();
+        uint32_t c = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int nit = nq - item_jb(idx);
+            const uint32_t sKV = smem_base + S::oKV + (n & 1) * 2 * AT_TILE;
+            const uint64_t dK_mn = desc_mnmajor(sKV, 0);
+            for (int it = 0; it < nit; ++it, ++c) {
+                issue_next_sdp();
+                mbar_wait(pds_full, c & 1);
+                mbar_wait(dq_empty, (c & 1) ^ 1);                   // dQ of iteration c - 1 has been read out
+                if (it == 0 && n > 0) mbar_wait(dkv_empty, (n - 1) & 1);     // previous item's dK / dV have been read out
+                tc_fence_after();
+                const uint32_t sQ = smem_base + S::oQdO + (c & 1) * 2 * AT_TILE;
+                const uint64_t dQ_mn = desc_mnmajor(sQ, 0), dDO_mn = desc_mnmajor(sQ + AT_TILE, 0);
+                const bool last = (it == nit - 1);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) umma_bf16(tDV, dP_mn + (uint64_t)(k * 128), dDO_mn + (uint64_t)(k * 128), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) umma_bf16(tDK, dDS_mn + (uint64_t)(k * 128), dQ_mn + (uint64_t)(k * 128), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tDQ, dDS_k + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), dK_mn + (uint64_t)(k * 128), idesc_q, k > 0 ? 1u : 0u);
+                    umma_commit(dq_full);
+                    umma_commit(pds_empty);
+                    umma_commit(&qdo_empty[c & 1]);
+                    if (last) umma_commit(&kv_empty[n & 1]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int qtr = (warp - 2) >> 2;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * kLog2eF;
+        const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
+        const uint32_t t32 = drop.thresh16 << 16;
+
+        // dQ tile of global iteration cc -> fp32 accumulator rows starting at dst (nullptr: row beyond T)
+        auto dq_out = [&](uint32_t cc, float* dst) {
+            mbar_wait(dq_full, cc & 1);
+            tc_fence_after();
+            uint32_t v[16];
+            __syncwarp();
+            tmem_ld_32x16(tDQ + lane_off + qtr * 16, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+            if (dst != nullptr) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(v[4 * g])),
+                                 "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3])) : "memory");
+            }
+        };
+
+        uint32_t c = 0;
+        for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
+            const int jb = item_jb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int row_base = b * T, k0 = jb * AT_BN, nit = nq - jb;
+            const int kc0 = k0 + qtr * 32;
+            float* prev_dst = nullptr;
+            for (int it = 0; it < nit; ++it, ++c) {
+                const int i = jb + it;
+                const uint32_t ph = c & 1;
+                const int qi = i * AT_BM + r;
+                const bool q_ok = qi < T;
+                const float lse2 = q_ok ? lse[(size_t)bh * T + qi] * kLog2eF : 0.f;
+                const float dlt = q_ok ? delta[(size_t)bh * T + qi] : 0.f;
+                const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
+                const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
+                float* cur_dst = q_ok ? dq_acc + (size_t)(row_base + qi) * d + h * 64 + qtr * 16 : nullptr;
+                uint32_t pp[16], dd[16];
+                mbar_wait(sdp_full, ph);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t sv[16], gv[16];
+                    __syncwarp();
+                    tmem_ld_32x16(tS + lane_off + qtr * 32 + cc * 16, sv);
+                    tmem_ld_32x16(tDP + lane_off + qtr * 32 + cc * 16, gv);
+                    tmem_ld_wait();
+                    if (cc == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(sdp_empty);
+                    }
+                    float p[16];
+                    if (need_mask) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int kj = kc0 + cc * 16 + e;
+                            p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
+                    }
+                    float ds[16];
+                    if (drop.thresh16) {
+                        const uint32_t g0 = (uint32_t)(kc0 + cc * 16) >> 2;
+#pragma unroll
+                        for (int e4 = 0; e4 < 4; ++e4) {
+                            uint32_t w0, w1;
+                            attn_drop_words(rk, g0 + e4, w0, w1);
+                            const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
+                                ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
+                                p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { pp[cc * 8 + e] = pack_bf16(p[2 * e], p[2 * e + 1]); dd[cc * 8 + e] = pack_bf16(ds[2 * e], ds[2 * e + 1]); }
+                }
+                mbar_wait(pds_empty, ph ^ 1);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    st_tile_chunk(sP, r, qtr * 4 + g, make_uint4(pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]));
+                    st_tile_chunk(sDS, r, qtr * 4 + g, make_uint4(dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]));
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pds_full);
+                if (it > 0) dq_out(c - 1, prev_dst);
+                prev_dst = cur_dst;
+            }
+            dq_out(c - 1, prev_dst);                                   // last query block of the item; all gradient MMAs are complete after this
+            // dK (x softmax scale), dV (x dropout scale) of this key block
+            const int kj = k0 + r;
+            bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64 + qtr * 16;
+            bf16* dvp = dkp + d;
+            uint32_t a[16], v[16];
+            __syncwarp();
+            tmem_ld_32x16(tDK + lane_off + qtr * 16, a);
+            tmem_ld_32x16(tDV + lane_off + qtr * 16, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_empty);
+            if (kj < T) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    reinterpret_cast<uint4*>(dkp)[g] =
+                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * scale, __uint_as_float(a[8 * g + 1]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * scale, __uint_as_float(a[8 * g + 3]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * scale, __uint_as_float(a[8 * g + 5]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * scale, __uint_as_float(a[8 * g + 7]) * scale));
+                    reinterpret_cast<uint4*>(dvp)[g] =
+                        make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * drop.scale, __uint_as_float(v[8 * g + 1]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 2]) * drop.scale, __uint_as_float(v[8 * g + 3]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 4]) * drop.scale, __uint_as_float(v[8 * g + 5]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 6]) * drop.scale, __uint_as_float(v[8 * g + 7]) * drop.scale));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
 // fp32 dQ accumulation buffer [B*T, d] -> bf16 dqkv[:, 0:d]
 __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, size_t rows, int d, float scale) {
     const size_t n4 = rows * (size_t)d / 4;
@@ -1065,10 +1630,10 @@ bool attn_use_tc() {
     return !legacy;
 }
 
-// TTTS_ATTN_V2=1 selects the previous (8 softmax warps) kernels, for A/B measurements
+// TTTS_ATTN_VER=2|3 selects the earlier kernels (2: 8 softmax warps; 3: 16 warps, one CTA per item) for A/B measurements; default 4 (persistent)
 static int attn_tc_version() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("TTTS_ATTN_V2"); v = (e && e[0] == '1') ? 2 : 3; }
+    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 4; }
     return v;
 }
 
@@ -1084,7 +1649,12 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
         attr = true;
     }
     dim3 grid((T + AT_BM - 1) / AT_BM, B * H);
-    if (attn_tc_version() >= 3) attn_fwd_tc3_kernel<<<grid, AT3_THREADS, Fwd3Smem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
+    if (attn_tc_version() >= 4) {
+        static bool attr4 = false;
+        if (!attr4) { TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes)); attr4 = true; }
+        const int items = (int)grid.x * B * H;
+        attn_fwd_tc4_kernel<<<items < num_sms() ? items : num_sms(), AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
+    } else if (attn_tc_version() >= 3) attn_fwd_tc3_kernel<<<grid, AT3_THREADS, Fwd3Smem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     else attn_fwd_tc_kernel<<<grid, AT_THREADS, FwdSmem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
     return TTTS_OK;
@@ -1112,7 +1682,13 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
         attr = true;
     }
     dim3 grid((T + AT_BN - 1) / AT_BN, B * H);
-    if (attn_tc_version() >= 3) attn_bwd_tc3_kernel<<<grid, AT3_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
+    if (attn_tc_version() >= 4) {
+        static bool attr4 = false;
+        if (!attr4) { TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes)); attr4 = true; }
+        const int items = (int)grid.x * B * H;
+        attn_bwd_tc4_kernel<<<items < num_sms() ? items : num_sms(), AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f,
+                                                                                                      drop);
+    } else if (attn_tc_version() >= 3) attn_bwd_tc3_kernel<<<grid, AT3_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     else attn_bwd_tc_kernel<<<grid, AT_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_bwd_tc");
     const size_t n4 = (size_t)B * T * d / 4;

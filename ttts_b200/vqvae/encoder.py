@@ -164,6 +164,18 @@ class _Wrap(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ blocks
+_SIDE = {}
+
+
+def _side_streams(device, n):
+    """Per-device pool of auxiliary streams for the fork/join sections of the encoder (created once, reused, also under graph capture)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    st = _SIDE.get(key)
+    if st is None or len(st) < n:
+        st = _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return st
+
+
 class ResBlock1(nn.Module):
     """ttts/vqvae/modules.py:224-318: 3 x [lrelu -> conv(k, d_i) -> lrelu -> conv(k, 1) -> + x]."""
 
@@ -328,20 +340,46 @@ class PosteriorAudioEncoder(nn.Module):
         lib = L.lib(); _protos(lib)
         B, _, T = x.shape
         mask2 = x_mask.reshape(B, T).contiguous()
+        # Two independent branches meet at `cat`: the spectrogram branch (pre -> 16 gated WN layers, T = 36 frames: small launches) and
+        # the waveform branch (strided convs + 15 ResBlocks).  They run on two streams, and inside the waveform branch the three
+        # ResBlocks of a level (kernel sizes 3/7/11, same input) run on three streams: streams (and the CUDA graph captured from them)
+        # instead of one serial chain of ~350 under-filled launches.  The sums keep the serial order ((r0 + r1) + r2): same bits.
+        main = torch.cuda.current_stream()
+        side = _side_streams(x.device, 3)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        cat = torch.empty(B, 2 * self.hidden_channels, T, dtype=torch.float32, device=x.device)
+        with torch.cuda.stream(side[2]):
+            side[2].wait_event(fork)
+            h = conv1d(x.contiguous(), self.pre.weight, self.pre.bias, mask=mask2)
+            hb = self.enc(h, x_mask, g=g)
+            if not torch.cuda.is_current_stream_capturing():
+                hb.record_stream(main)                       # consumed on the main stream after the join
         a = conv1d(x_audio.contiguous(), self.down_pre.weight, self.down_pre.bias, pad=3)
+        nk = self.num_kernels
         for i in range(5):
             dn = self.downs[i]
             a = conv1d(a, dn.weight(), dn.bias, stride=dn.stride, pad=dn.pad)
-            xs = torch.empty_like(a)
-            for j in range(self.num_kernels):
-                self.resblocks[i * self.num_kernels + j](a, out=xs, out_scale=1.0 / self.num_kernels, accumulate=j > 0)
+            outs = [torch.empty_like(a) for _ in range(nk)]          # allocated on the main stream, written by the branch streams
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for j in range(nk):
+                st = main if j == 0 else side[j - 1]
+                with torch.cuda.stream(st):
+                    if j > 0:
+                        st.wait_event(ev)
+                    self.resblocks[i * nk + j](a, out=outs[j], out_scale=1.0 / nk, accumulate=False)
+            for j in range(1, nk):
+                main.wait_stream(side[j - 1])
+            xs = outs[0]
+            for j in range(1, nk):
+                xs = xs.add_(outs[j])
             a = xs
         a = self.activation_post(a)
         assert a.shape[-1] == T, "audio / spectrogram frame mismatch (%d vs %d)" % (a.shape[-1], T)
-        cat = torch.empty(B, 2 * self.hidden_channels, T, dtype=torch.float32, device=x.device)
-        h = conv1d(x.contiguous(), self.pre.weight, self.pre.bias, mask=mask2)
-        cat[:, :self.hidden_channels] = self.enc(h, x_mask, g=g)
         cat[:, self.hidden_channels:] = conv1d(a, self.conv_post.weight, self.conv_post.bias, pad=3, mask=mask2)
+        main.wait_stream(side[2])
+        cat[:, :self.hidden_channels] = hb
         stats = conv1d(cat, self.proj.weight, self.proj.bias, mask=mask2)
         m, logs = torch.split(stats, self.out_channels, dim=1)
         z = torch.empty(B, self.out_channels, T, dtype=torch.float32, device=x.device)
@@ -362,12 +400,17 @@ class VQEncoder(nn.Module):
         self.proj = _Conv(inter_channels, inter_channels, 2, stride=2)
 
     @torch.no_grad()
-    def forward(self, wav, lengths=None, eps=None):
-        """wav [B, L] fp32 (L a multiple of hop).  Returns dict(spec, ge, z, m, logs, x, codes [1,B,N], quantized)."""
+    def forward(self, wav, lengths=None, eps=None, sample=False):
+        """wav [B, L] fp32 (L a multiple of hop).  Returns dict(spec, ge, z, m, logs, x, codes [1,B,N], quantized).
+        Posterior noise: the reference draws `randn_like(m)` even in eval (vq2.py:744).  Pass `eps` [B,192,T] to fix it (parity tests),
+        `sample=True` to draw it here with torch's generator (reference behaviour), or neither for the deterministic z = m encode
+        (extraction default: the same clip always maps to the same codes)."""
         L.require_cuda(wav)
         B = wav.shape[0]
         spec = spectrogram_torch(wav, self.n_fft, self.hop, self.n_fft, center=False)
         T = spec.shape[-1]
+        if eps is None and sample:
+            eps = torch.randn(B, self.enc_p.out_channels, T, dtype=torch.float32, device=wav.device)
         if lengths is None:
             mask = torch.ones(B, 1, T, dtype=torch.float32, device=wav.device)
         else:
