@@ -39,6 +39,25 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
+def ncu_dram_bytes_per_launch():
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r1d_gemm2_pair_ncu_full.txt: the QKV GEMM, M 36 992 x N 3 072 x K 1 024, whose algorithmic
+    operand + output bytes are 309 MB).  Measured under ncu, so it is read from the committed summary, never produced by this run."""
+    path = os.path.join(ROOT, "profiles", "r1d_gemm2_pair_ncu_full.txt")
+    try:
+        rd = wr = None
+        for line in open(path):
+            if line.startswith("dram__bytes_read.sum [Mbyte]"):
+                rd = float(line.split("]")[1].split("|")[0])
+            if line.startswith("dram__bytes_write.sum [Mbyte]"):
+                wr = float(line.split("]")[1].split("|")[0])
+        if rd is None or wr is None:
+            return None, None
+        return (rd + wr) * 1e6, "profiles/r1d_gemm2_pair_ncu_full.txt (QKV GEMM launch: 309 MB algorithmic)"
+    except OSError:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -227,11 +246,16 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    step_ev = []
     for i in range(args.steps):
         fused(*dev_batches[i % 4], clip_inputs=False)
+        ev = torch.cuda.Event(enable_timing=True); ev.record(); step_ev.append(ev)      # per-step marks (no sync): p10 / median / p90
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    marks = [e0] + step_ev
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    pct = lambda q: per_step[min(len(per_step) - 1, int(q * len(per_step)))]
     l1 = lib.ttts_launch_count()
     gms, gfl, gn = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     lib.ttts_prof_gemm_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gn))
@@ -270,10 +294,11 @@ def main():
     pk = peaks()
     fl_step = synth.flops_per_step(wl["layers"], wl["model_dim"], B, TL, CL)     # per GPU, algorithmic
     gemm_tflops = (gfl.value / (gms.value * 1e-3)) / 1e12 if gms.value > 0 else None
+    traffic, traffic_src = ncu_dram_bytes_per_launch()
     roofline = {
-        "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05.mma, TMA, TMEM)",
+        "bound": "tensor", "kernel": "gemm2_bf16_kernel<A_MN,B_MN,PAIR> (tcgen05.mma cta_group::2, TMA, TMEM; all GEMMs of the step)",
         "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None, "traffic": None,
+        "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": pk["src"] + " (sustained bf16 cuBLAS, MEASURED_PEAKS.json)",
         "launches": int(gn.value), "kernel_ms_per_step": gms.value / args.steps,
         "kernel_share_of_step": (gms.value / args.steps) / ms_step,
@@ -281,7 +306,7 @@ def main():
     }
     out = {
         "metric": "gpt_step_audio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "ms_per_step": ms_step, "step_ms_rank0": {"p10": pct(0.1), "median": pct(0.5), "p90": pct(0.9)}, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d/H%d" % (wl["layers"], wl["model_dim"], wl["heads"]), "per_gpu_batch": B,
                    "global_batch": B * world, "text_len": TL, "code_len": CL, "seq_len": TL + CL + 4, "parallelism": "dp%d" % world,
                    "dropout": args.dropout, "l2": "working set (~33 GB activations + 5 GB optimizer state per step) far exceeds the 126 MB L2; no flush needed",
@@ -293,6 +318,31 @@ def main():
         tcpu = cpu_oracle_step_time(wl, 1, 1, 0, threads)
         out["cpu_baseline"] = {"value": CL / tcpu, "unit": "frames/s", "cores": threads, "kind": "port",
                                "sample": "1 step (fwd+bwd+clip+AdamW, fp32, no grad-ckpt) of the oracle port at batch 1 of the %s shape" % args.workload}
+    if world == 1 and not args.profile_run and args.workload == "cfg3":
+        # secondary: BASELINE config 2 (12L/d512, batch 8, 512 codes) -- too small to fill the machine, reported for completeness
+        try:
+            del trainer, fused, model
+            torch.cuda.empty_cache()
+            w2 = WORKLOADS["cfg2"]
+            cfg2 = {"train": cfg_json["train"], "gpt": dict(GPT_KW, layers=w2["layers"], model_dim=w2["model_dim"], heads=w2["heads"])}
+            b2 = [t.to(dev) for t in synth.synthetic_batch(w2["B"], w2["TL"], w2["CL"], seed=77)]
+            tr2 = Trainer(cfg=cfg2, dataloader=[None], device=dev, logs=False)
+            tr2.gpt.train(); tr2.gpt.dropout_p = args.dropout
+            for _ in range(5):
+                tr2.fused(*b2, clip_inputs=False)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                tr2.fused(*b2, clip_inputs=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 20
+            fl2 = synth.flops_per_step(w2["layers"], w2["model_dim"], w2["B"], w2["TL"], w2["CL"])
+            out["cfg2"] = {"ms_per_step": ms2, "frames_per_s": w2["B"] * w2["CL"] / (ms2 * 1e-3), "step_tflops": fl2 / (ms2 * 1e-3) / 1e12,
+                           "config": "UnifiedVoice 12L/d512/H8, batch 8, text 128, codes 512, 20 steps after 5 warm-up"}
+            del tr2
+        except Exception as e:
+            out["cfg2"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_vq_encode:
         # second BASELINE.json metric: VQ-encode Msamples/s (stft -> ref_enc -> enc_p -> proj -> codes, B = 64 clips)
         try:

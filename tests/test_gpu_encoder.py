@@ -123,3 +123,14 @@ def test_batched_extractor_equals_per_clip(model, tmp_path):
         cw = X.condition_wav(w).cuda().unsqueeze(0)
         alone = model(cw)["codes"][0, 0].tolist()
         assert isinstance(got, list) and got == alone and len(got) == cw.shape[1] // 1280
+
+
+def test_extract_latent_api(model):
+    """vq2.py:912-920 surface: codes [B, n_q, N], equal to forward()'s codes; a mismatching spectrogram argument is rejected."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    wav = torch.clamp(0.1 * torch.randn(3, 23040, device="cuda", generator=g), -1, 1)
+    o = model(wav)
+    c = model.extract_latent(wav, o["spec"])
+    assert c.shape == (3, 1, 18) and torch.equal(c, o["codes"].transpose(0, 1))
+    with pytest.raises(ValueError):
+        model.extract_latent(wav, o["spec"][:, :, :-1])

@@ -255,18 +255,34 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                                          int B, int T, int H) {
-    // one warp per (token, head): 64 dims = 32 lanes x 2
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int total = B * T * H;
-    if (warp >= total) return;
-    const int tok = warp / H, h = warp - tok * H;
-    const int b = tok / T, t = tok - b * T;
-    const size_t off = (size_t)tok * (H * HD) + h * HD + lane * 2;
-    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + off);
-    const uint32_t g = *reinterpret_cast<const uint32_t*>(dout + off);
-    float s = bf16_lo(a) * bf16_lo(g) + bf16_hi(a) * bf16_hi(g);
-    s = warp_sum(s);
-    if (lane == 0) delta[((size_t)b * H + h) * T + t] = s;
+    // 8 lanes per (token, head): one 16-byte load of O and of dO each (8 dims), 3 shuffle steps; 2 pairs per thread for loads in flight
+    const size_t total = (size_t)B * T * H;
+    const size_t pair0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const size_t half = (total + 1) / 2;
+    float s[2] = {0.f, 0.f};
+    size_t pr[2] = {pair0, pair0 + half};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (pair0 >= half || pr[u] >= total) continue;
+        const size_t off = pr[u] * HD + sub * 8;          // pairs are (token, head) row-major: token * (H*64) + h*64
+        const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+        const uint4 g = *reinterpret_cast<const uint4*>(dout + off);
+        s[u] = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y) +
+               bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) + bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        float v = s[u];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == 0 && pair0 < half && pr[u] < total) {
+            const size_t tok = pr[u] / H; const int h = (int)(pr[u] - tok * H);
+            const size_t b = tok / T; const int t = (int)(tok - b * T);
+            delta[(b * H + h) * T + t] = v;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,8 +531,8 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
                 cudaStream_t st);
 
 int attn_delta(const bf16* o, const bf16* dout, float* delta, int B, int T, int H, cudaStream_t st) {
-    const int total_warps = B * T * H;
-    attn_delta_kernel<<<(total_warps + 7) / 8, 256, 0, st>>>(o, dout, delta, B, T, H);
+    const size_t half = ((size_t)B * T * H + 1) / 2;                       // each thread group of 8 lanes handles pairs p and p + half
+    attn_delta_kernel<<<(unsigned)((half * 8 + 255) / 256), 256, 0, st>>>(o, dout, delta, B, T, H);
     TTTS_LAUNCH_CHECK("attn_delta");
     return TTTS_OK;
 }

@@ -70,6 +70,33 @@ TTTS_DEVICE float gelu_new_grad_fast(float x) {
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// Packed bf16x2 forms for the GEMM epilogues (two elements per instruction, tanh on the SFU at two per MUFU op).  The reference runs
+// gelu_new as a chain of bf16 elementwise kernels under autocast (every intermediate rounded to bf16, HF: activations.py:59-66), so bf16
+// intermediates are its own precision; constants are the bf16 roundings of k0 = sqrt(2/pi), k0*0.044715, 3*k0*0.044715.
+TTTS_DEVICE uint32_t bf2_mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+TTTS_DEVICE uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+TTTS_DEVICE uint32_t bf2_tanh(uint32_t a) { uint32_t d; asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+constexpr uint32_t kBf2K0 = 0x3F4C3F4Cu, kBf2K0K1 = 0x3D123D12u, kBf2K0K1x3 = 0x3DDB3DDBu, kBf2Half = 0x3F003F00u, kBf2One = 0x3F803F80u;
+// gelu_new of two packed bf16 values
+TTTS_DEVICE uint32_t gelu_new_bf2(uint32_t x) {
+    const uint32_t x2 = bf2_mul(x, x);
+    const uint32_t u = bf2_mul(x, bf2_fma(x2, kBf2K0K1, kBf2K0));      // k0 x (1 + k1 x^2)
+    const uint32_t t = bf2_tanh(u);
+    const uint32_t hx = bf2_mul(x, kBf2Half);
+    return bf2_fma(hx, t, hx);                                          // 0.5 x (1 + t)
+}
+// d gelu_new / dx of two packed bf16 values
+TTTS_DEVICE uint32_t gelu_new_grad_bf2(uint32_t x) {
+    const uint32_t x2 = bf2_mul(x, x);
+    const uint32_t u = bf2_mul(x, bf2_fma(x2, kBf2K0K1, kBf2K0));
+    const uint32_t t = bf2_tanh(u);
+    const uint32_t du = bf2_fma(x2, kBf2K0K1x3, kBf2K0);              // k0 (1 + 3 k1 x^2)
+    const uint32_t a = bf2_fma(t, kBf2Half, kBf2Half);                  // 0.5 (1 + t)
+    const uint32_t omt2 = bf2_fma(t ^ 0x80008000u, t, kBf2One);         // 1 - t^2
+    const uint32_t b = bf2_mul(bf2_mul(x, kBf2Half), omt2);             // 0.5 x (1 - t^2)
+    return bf2_fma(b, du, a);
+}
+
 // Counter-based dropout generator: one 64-bit mix -> 4 keep-decisions of 16 bits each.
 // keep iff u16 >= thresh16 where thresh16 = round(p*65536).
 TTTS_DEVICE uint64_t mix64(uint64_t z) {

@@ -258,8 +258,9 @@ int ln_fwd(const float* x, const float* w1, const float* b1, const float* w2, co
 
 // Backward of y = LN(x)*w + b given dy, for one row held in registers.
 //   dx = rstd * (dyw - mean(dyw) - xhat * mean(dyw*xhat)),  dyw = dy*w
-// The per-row contributions to dgamma (dy*xhat) and dbeta (dy) are parked in shared memory rows (sdg, sdb); the block
-// sums them over its 8 rows afterwards, so the column accumulators cost 4 registers per thread instead of d/32.
+// The per-row contributions to dgamma (dy*xhat) and dbeta (dy) are ACCUMULATED into this warp's own shared-memory rows (sdg, sdb):
+// no block-level synchronisation in the row loop (the first version synchronised twice per 8 rows to reduce them, which kept the
+// kernel at 58 % of HBM bandwidth), and the column accumulators do not live in registers (d/32 per array would be 96+).
 template <int NCH>
 TTTS_DEVICE void ln_bwd_row(const float (&xv)[NCH * 4], float mean, float rstd, const float* __restrict__ w, int lane, int d,
                             float (&dy)[NCH * 4] /* in: dy ; out: dx */, float* __restrict__ sdg, float* __restrict__ sdb) {
@@ -277,8 +278,11 @@ TTTS_DEVICE void ln_bwd_row(const float (&xv)[NCH * 4], float mean, float rstd, 
             xh[k] = (xv[k] - mean) * rstd;
             pg[j] = dy[k] * xh[k];
         }
-        *reinterpret_cast<float4*>(sdg + c) = make_float4(pg[0], pg[1], pg[2], pg[3]);
-        *reinterpret_cast<float4*>(sdb + c) = make_float4(dy[4 * i], dy[4 * i + 1], dy[4 * i + 2], dy[4 * i + 3]);
+        float4 ag = *reinterpret_cast<const float4*>(sdg + c), ab = *reinterpret_cast<const float4*>(sdb + c);
+        ag.x += pg[0]; ag.y += pg[1]; ag.z += pg[2]; ag.w += pg[3];
+        ab.x += dy[4 * i]; ab.y += dy[4 * i + 1]; ab.z += dy[4 * i + 2]; ab.w += dy[4 * i + 3];
+        *reinterpret_cast<float4*>(sdg + c) = ag;
+        *reinterpret_cast<float4*>(sdb + c) = ab;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = 4 * i + j;
@@ -317,10 +321,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
 
-    const int row_iters = (M + gridDim.x * 8 - 1) / (gridDim.x * 8);
-    for (int itr = 0; itr < row_iters; ++itr) {
-        const int row = (itr * gridDim.x + blockIdx.x) * 8 + warp;
-        if (row < M) {
+#pragma unroll
+    for (int a = 0; a < NARR; ++a)
+        for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(s_row[a] + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        {
             float xv[NCH * 4], dy[NCH * 4];
             const float* xr = x + (size_t)row * d;
             const int drow = map_row(map, row);
@@ -366,7 +372,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                     o[0] += gi.x; o[1] += gi.y; o[2] += gi.z; o[3] += gi.w;
                 }
                 *reinterpret_cast<float4*>(g_out + (size_t)row * d + c) = make_float4(o[0], o[1], o[2], o[3]);
-                float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g16_out) {
                     if (drop.thresh16) {
                         uint64_t bits = dropout_bits4(drop.seed, ((uint64_t)row * d + c) >> 2);
@@ -375,27 +380,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                     }
                     uint2 pk = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
                     *reinterpret_cast<uint2*>(g16_out + (size_t)row * d + c) = pk;
-                    bn = make_float4(bf16_lo(pk.x), bf16_hi(pk.x), bf16_lo(pk.y), bf16_hi(pk.y));
-                }
-                *reinterpret_cast<float4*>(s_row[2] + c) = bn;
-            }
-        } else {
-#pragma unroll
-            for (int a = 0; a < NARR; ++a)
-                for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(s_row[a] + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        if (threadIdx.x * 4 < d) {
-#pragma unroll
-            for (int a = 0; a < NARR; ++a) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float4 t = *reinterpret_cast<const float4*>(ln_smem + ((size_t)a * 8 + r) * d + threadIdx.x * 4);
-                    acc[a][0] += t.x; acc[a][1] += t.y; acc[a][2] += t.z; acc[a][3] += t.w;
+                    float4 bn = *reinterpret_cast<const float4*>(s_row[2] + c);
+                    bn.x += bf16_lo(pk.x); bn.y += bf16_hi(pk.x); bn.z += bf16_lo(pk.y); bn.w += bf16_hi(pk.y);
+                    *reinterpret_cast<float4*>(s_row[2] + c) = bn;
                 }
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x * 4 < d) {
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float4 t = *reinterpret_cast<const float4*>(ln_smem + ((size_t)a * 8 + r) * d + threadIdx.x * 4);
+                acc[a][0] += t.x; acc[a][1] += t.y; acc[a][2] += t.z; acc[a][3] += t.w;
+            }
+        }
     }
     if (threadIdx.x * 4 < d) {
         float* dst[5] = {dw1, db1, dbias_next, dw2, db2};
@@ -520,33 +521,48 @@ int ce_bwd(const bf16* logits, int ld, int V, const int32_t* tgt, int rows, cons
 // column sums of a bf16 matrix [M, ld] (N columns) -> out[N] += sum_rows   (bias gradients)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ a, int ld, int M, int N, float* __restrict__ out) {
-    // block = 32 column-pairs x 8 row lanes ; grid.x over column tiles of 64, grid.y over row chunks
+    // block = 32 column groups of 8 (one 16-byte load each) x 8 row lanes ; grid.x over column tiles of 256, grid.y over row chunks.
+    // Four independent 16-byte loads per thread in flight (the first version moved 4 bytes per load with one load in flight).
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int col = blockIdx.x * 64 + cx * 2;
+    const int col = blockIdx.x * 256 + cx * 8;
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    float s0 = 0.f, s1 = 0.f;
-    if (col < N) {
-        for (int r = r0 + ry; r < r1; r += 8) {
-            uint32_t u = *reinterpret_cast<const uint32_t*>(a + (size_t)r * ld + col);
-            s0 += bf16_lo(u);
-            s1 += bf16_hi(u);
-        }
-    }
-    __shared__ float sm[8][64];
-    sm[ry][cx * 2] = s0; sm[ry][cx * 2 + 1] = s1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float s = 0.f;
+    float s[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
-        const int c = blockIdx.x * 64 + threadIdx.x;
-        if (c < N) atomicAdd(out + c, s);
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    auto add8 = [&](const uint4 u) {
+        s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x); s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
+        s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z); s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w);
+    };
+    if (col + 8 <= N) {
+        int r = r0 + ry;
+        for (; r + 24 < r1; r += 32) {
+            const uint4 u0 = *reinterpret_cast<const uint4*>(a + (size_t)r * ld + col);
+            const uint4 u1 = *reinterpret_cast<const uint4*>(a + (size_t)(r + 8) * ld + col);
+            const uint4 u2 = *reinterpret_cast<const uint4*>(a + (size_t)(r + 16) * ld + col);
+            const uint4 u3 = *reinterpret_cast<const uint4*>(a + (size_t)(r + 24) * ld + col);
+            add8(u0); add8(u1); add8(u2); add8(u3);
+        }
+        for (; r < r1; r += 8) add8(*reinterpret_cast<const uint4*>(a + (size_t)r * ld + col));
+    } else if (col < N) {                                   // ragged last column group
+        for (int r = r0 + ry; r < r1; r += 8)
+            for (int k = 0; k < 8 && col + k < N; ++k) s[k] += __bfloat162float(a[(size_t)r * ld + col + k]);
+    }
+    __shared__ float sm[8][256 + 8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[ry][cx * 8 + k] = s[k];
+    __syncthreads();
+    {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        const int c = blockIdx.x * 256 + threadIdx.x;
+        if (c < N) atomicAdd(out + c, t);
     }
 }
 int colsum_bf16(const bf16* a, int ld, int M, int N, float* out, cudaStream_t st) {
-    TTTS_CHECK_ARG(ld % 2 == 0, "colsum: ld must be even");
-    int gx = (N + 63) / 64;
+    TTTS_CHECK_ARG(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "colsum: ld must be a multiple of 8 and the matrix 16-byte aligned");
+    int gx = (N + 255) / 256;
     int gy = (num_sms() * 8 + gx - 1) / gx;
     if (gy > (M + 63) / 64) gy = (M + 63) / 64;
     if (gy < 1) gy = 1;

@@ -112,17 +112,21 @@ TTTS_DEVICE void epi_apply_staged(const GemmParams& p, const int row0, const int
         __syncwarp();
     } break;
     case TTTS_EPI_GELU: {
-        float h[32];
+        // pre = bf16(acc + bias) ; h = gelu_new(pre) in packed bf16x2 (common.cuh): 3 instructions per element instead of 13
+        uint4 qp[4];
+        pack16(v, qp);
+        {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(qp);
+            uint32_t* wh = reinterpret_cast<uint32_t*>(q);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = bf16_round(v[j]); h[j] = gelu_new_fast(v[j]); }
-        pack16(h, q);
+            for (int t = 0; t < 16; ++t) wh[t] = gelu_new_bf2(wp[t]);
+        }
         stage_put_row(S, lane, q);
         __syncwarp();
         stage_store64(S, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(p.out) + (size_t)row0 * p.ldo + col0), (size_t)p.ldo * 2, nrows, lane);
         __syncwarp();
         if (p.aux_out) {
-            pack16(v, q);
-            stage_put_row(S, lane, q);
+            stage_put_row(S, lane, qp);
             __syncwarp();
             stage_store64(S, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(p.aux_out) + (size_t)row0 * p.ldaux_out + col0), (size_t)p.ldaux_out * 2, nrows, lane);
             __syncwarp();
@@ -164,12 +168,14 @@ TTTS_DEVICE void epi_apply_staged(const GemmParams& p, const int row0, const int
         stage_get_row(S, lane, q);
         __syncwarp();
         const uint32_t w[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w, q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            v[2 * t] *= gelu_new_grad_fast(bf16_lo(w[t]));
-            v[2 * t + 1] *= gelu_new_grad_fast(bf16_hi(w[t]));
-        }
+        // out = bf16(acc) * gelu'(pre), both factors packed bf16x2 (the reference's autocast backward rounds the dgrad output and every
+        // elementwise factor to bf16 as well)
         pack16(v, q);
+        {
+            uint32_t* wo = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) wo[t] = bf2_mul(wo[t], gelu_new_grad_bf2(w[t]));
+        }
         stage_put_row(S, lane, q);
         __syncwarp();
         stage_store64(S, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(p.out) + (size_t)row0 * p.ldo + col0), (size_t)p.ldo * 2, nrows, lane);

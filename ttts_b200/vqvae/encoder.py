@@ -423,6 +423,16 @@ class VQEncoder(nn.Module):
         return dict(spec=spec, ge=ge, z=z, m=m, logs=logs, x=x, codes=codes, quantized=quantized)
 
     @torch.no_grad()
+    def extract_latent(self, wav, y=None, y_lengths=None, sample=False):
+        """SynthesizerTrn.extract_latent (vq2.py:912-920): codes [B, n_q, N].  The reference reads an undefined `y_lengths` there (it only
+        works through a global); here it is an explicit optional argument (None = all frames valid).  `y` (the linear spectrogram) is
+        recomputed from `wav` by the fused STFT kernel, so a caller-supplied `y` is only shape-checked."""
+        out = self.forward(wav, lengths=y_lengths, sample=sample)
+        if y is not None and tuple(y.shape) != tuple(out["spec"].shape):
+            raise ValueError("extract_latent: spectrogram shape %s does not match the waveform (%s)" % (tuple(y.shape), tuple(out["spec"].shape)))
+        return out["codes"].transpose(0, 1)
+
+    @torch.no_grad()
     def encode_graphed(self, wav):
         """Extraction fast path: the whole wav -> codes forward (≈ 350 small launches) captured once per input shape in a
         CUDA graph and replayed (streams + graphs instead of a tracing compiler).  Returns codes [1, B, N] (a static buffer)."""
