@@ -266,6 +266,25 @@ TTTS_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, multicast: the box lands at the same smem offset in every CTA of `mask` (cluster ranks), and each destination's bytes are
+// signalled on the barrier at this offset in the LEADER of that destination's CTA pair.
+TTTS_DEVICE void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// arrive on the barrier at this offset in cluster rank `target`
+TTTS_DEVICE void mbar_arrive_rank(uint64_t* bar, uint32_t target) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(target));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// commit with an explicit multicast mask (cluster ranks whose barrier at this offset gets one arrival)
+TTTS_DEVICE void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 TTTS_DEVICE void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {  // one whole warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");

@@ -9,6 +9,7 @@
 // epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 1:
 // the leader's arrive.expect_tx covers both CTAs' bytes; both CTAs' TMA complete_tx there), empty[] / tmem_full[] are
 // per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 8 epilogue warps).
+#include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -69,17 +70,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    // cluster = 1 CTA, one CTA pair, or (p.quad) two CTA pairs on neighbouring n-blocks that share their A rows by TMA multicast:
+    // the GEMM is bound by L2 -> SM operand delivery (profiles/r1_notes.md), and a 256 x 512 cluster tile moves 24 KB per CTA and k-block
+    // instead of 32 KB.
+    const bool quad = PAIR && p.quad;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // 0..1 (pair) or 0..3 (quad)
+    const uint32_t rank = crank & 1u;                          // position inside the CTA pair
+    const uint32_t pidx = quad ? (crank >> 1) : 0u;            // which pair of the cluster
     const bool leader = rank == 0;
-    const int cluster_id = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
-    const int num_clusters = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    const int ncta = PAIR ? (quad ? 4 : 2) : 1;
+    const int cluster_id = blockIdx.x / ncta;
+    const int num_clusters = gridDim.x / ncta;
+    const int nmul = quad ? 2 : 1;                             // n-blocks per item
     const int total_items = p.num_m_blocks * p.num_n_blocks * p.split_k;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         // full[]: ONE arrival (the leader's arrive.expect_tx for both CTAs' bytes); the peer's TMA only complete_tx's there
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], quad ? 2 : 1); }   // quad: both pairs' MMAs release a stage
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * C::kCtas); }     // one arrival per epilogue warp
         fence_barrier_init();
     }
@@ -97,7 +106,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int m_pair, n_blk, split;
             decode_item2(p, item, m_pair, n_blk, split);
             const int m0 = m_pair * C::kTileM + (int)rank * G2_BM;
-            const int n0 = n_blk * G2_BN + (int)rank * (G2_BN / 2);
+            const int n0 = (n_blk * nmul + (int)pidx) * G2_BN + (int)rank * (G2_BN / 2);
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -110,7 +119,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (PAIR) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
                         else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
                     };
-                    if (A_MN) {
+                    if (quad) {
+                        // this CTA fetches 64 of the 128 A rows its pair position needs and multicasts them to the CTA at the same position in
+                        // the other pair; that CTA fetches the other 64 rows
+                        const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+                        if (A_MN) tma_load_2d_2sm_mc(sa + pidx * (G2_BK * 128), &tmA, &full_bar[stage], m0 + 64 * (int)pidx, kb * G2_BK, mask);
+                        else tma_load_2d_2sm_mc(sa + pidx * (G2_BK * 128), &tmA, &full_bar[stage], kb * G2_BK, m0 + 64 * (int)pidx, mask);
+                    } else if (A_MN) {
                         if (!PAIR && p.a3d) {
                             tma_load_3d(sa, &tmA, &full_bar[stage], 0, kb * G2_BK, m0 >> 6);
                         } else {
@@ -167,12 +182,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if (PAIR) umma_bf16_2sm(tmem_d, adesc0 + k * kStepA, bdesc0 + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                             else umma_bf16(tmem_d, adesc0 + k * kStepA, bdesc0 + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         }
-                        if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                        if (PAIR) umma_commit_2sm_mask(&empty_bar[stage], quad ? (uint16_t)0xF : (uint16_t)0x3); else umma_commit(&empty_bar[stage]);
                     }
                     __syncwarp();
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) { if (PAIR) umma_commit_2sm(&tfull_bar[as]); else umma_commit(&tfull_bar[as]); }
+                if (elect_one()) { if (PAIR) umma_commit_2sm_mask(&tfull_bar[as], (uint16_t)(0x3u << (2 * pidx))); else umma_commit(&tfull_bar[as]); }
                 __syncwarp();
             }
         }
@@ -191,7 +206,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             decode_item2(p, item, m_pair, n_blk, split);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int n0 = n_blk * G2_BN;
+            const int n0 = (n_blk * nmul + (int)pidx) * G2_BN;
             {
                 const int c = n0 + et;
                 sbias_all[as * 256 + et] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
@@ -229,7 +244,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }   // accumulator stage drained
+            if (lane == 0) { if (PAIR) mbar_arrive_rank(&tempty_bar[as], crank & ~1u); else mbar_arrive(&tempty_bar[as]); }   // accumulator stage drained
             epi_apply_staged(p, row0w, n0 + (c0 + 3) * 32, lane, rB, sb + 96, xB, S);
         }
     }
@@ -253,7 +268,7 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
     p.b3d = (B_MN && !PAIR && use3d && a.N % 64 == 0) ? 1 : 0;
     if (A_MN) rc = p.a3d ? make_tmap_mn3d(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, G2_BK, G2_BM / 64)
                          : make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, G2_BK, true);
-    else      rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, G2_BK, G2_BM, true);
+    else      rc = make_tmap_2d(&tmA, a.A, 2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, G2_BK, p.quad ? G2_BM / 2 : G2_BM, true);   // quad: 64-row halves
     if (rc) return rc;
     if (B_MN) rc = p.b3d ? make_tmap_mn3d(&tmB, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, G2_BK, C::kBRows / 64)
                          : make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
@@ -270,7 +285,7 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = PAIR ? (p.quad ? 4 : 2) : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
@@ -278,6 +293,34 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
     if (e != cudaSuccess) return fail_cuda(e, "gemm2_bf16_kernel launch");
     TTTS_LAUNCH_CHECK("gemm2_bf16_kernel");
     return TTTS_OK;
+}
+
+// TTTS_GEMM_QUAD=1: clusters of 4 CTAs (two pairs) with the A tile multicast to both pairs
+static bool use_quad() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_GEMM_QUAD"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on != 0;
+}
+// how many 4-CTA clusters of the pair kernel the device can hold at once (0: do not use quad mode)
+static int quad_clusters() {
+    static int n = -1;
+    if (n < 0) {
+        using C = G2Cfg<true>;
+        auto kern = gemm2_bf16_kernel<false, true, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(4 * (num_sms() / 4)); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = C::kSmemBytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int c = 0;
+        if (cudaOccupancyMaxActiveClusters(&c, kern, &cfg) != cudaSuccess) { cudaGetLastError(); c = 0; }
+        n = (c * 4 >= num_sms() * 9 / 10) ? c : 0;            // worth it only if (nearly) every SM can be part of a cluster
+        if (getenv("TTTS_GEMM_QUAD_VERBOSE")) fprintf(stderr, "[ttts] quad clusters: occupancy query says %d -> using %d\n", c, n);
+    }
+    return n;
 }
 
 template <bool PAIR>
@@ -301,8 +344,22 @@ static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
     p.aux = a.aux; p.ldaux = a.ldaux; p.aux_out = a.aux_out; p.ldaux_out = a.ldaux_out;
     p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
     p.a3d = p.b3d = 0;
-    const int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
-    const int grid = C::kCtas * (items < clusters ? items : clusters);
+    p.quad = 0;
+    int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
+    int grid = C::kCtas * (items < clusters ? items : clusters);
+    if (PAIR && use_quad() && p.num_n_blocks >= 2) {
+        // clusters of two pairs: items cover two neighbouring n-blocks (an odd last block leaves the second pair idle on an out-of-range block)
+        const int q = quad_clusters();
+        if (q > 0) {
+            p.quad = 1;
+            p.num_n_blocks = (p.num_n_blocks + 1) / 2;
+            p.group_m = q / p.num_n_blocks;
+            if (p.group_m < 1) p.group_m = 1;
+            if (p.group_m > p.num_m_blocks) p.group_m = p.num_m_blocks;
+            items = p.num_m_blocks * p.num_n_blocks * p.split_k;
+            grid = 4 * (items < q ? items : q);
+        }
+    }
     if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false, PAIR>(a, p, grid, stream);
     if (!a.a_mn && a.b_mn) return launch_gemm2<false, true, PAIR>(a, p, grid, stream);
     if (a.a_mn && a.b_mn) return launch_gemm2<true, true, PAIR>(a, p, grid, stream);

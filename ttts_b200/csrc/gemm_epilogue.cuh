@@ -19,6 +19,7 @@ struct GemmParams {
     void* aux_out; int ldaux_out;
     uint32_t drop_thresh16; float drop_scale; uint64_t drop_seed;
     int a3d, b3d;               // MN-major operand fetched with ONE 3-D TMA box per stage (extent % 64 == 0)
+    int quad;                   // CTA-pair kernel in clusters of 4: two pairs on neighbouring n-blocks share the A tile by TMA multicast
 };
 
 struct EpiAux { uint4 q[8]; };     // RESID: 32 fp32 (8 x float4) ; DGELU: 32 bf16 (first 4 x uint4)
