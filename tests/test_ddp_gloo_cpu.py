@@ -47,3 +47,38 @@ def test_chunked_allreduce_equals_whole():
     port = 29000 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, lay.total, ranges, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _vq_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ttts_b200.vqvae.quantize import EuclideanCodebook
+    g = torch.Generator().manual_seed(7 + rank)
+    hist = torch.randint(0, 5, (1024,), generator=g).float()
+    esum = torch.randn(1024, 192, generator=g)
+    h_all = [torch.zeros_like(hist) for _ in range(world)]
+    e_all = [torch.zeros_like(esum) for _ in range(world)]
+    dist.all_gather(h_all, hist); dist.all_gather(e_all, esum)
+    h1, e1 = EuclideanCodebook.sync_stats(hist.clone(), esum.clone(), "allreduce")
+    ok = torch.equal(h1, sum(h_all)) and torch.allclose(e1, sum(e_all), atol=1e-6)          # global-batch statistics on every rank
+    h2, e2 = EuclideanCodebook.sync_stats(hist.clone(), esum.clone(), "rank0")
+    ok = ok and torch.equal(h2, h_all[0]) and torch.equal(e2, e_all[0])                       # the reference's broadcast_buffers semantics
+    h3, e3 = EuclideanCodebook.sync_stats(hist.clone(), esum.clone(), None)
+    ok = ok and torch.equal(h3, hist) and torch.equal(e3, esum)
+    try:
+        EuclideanCodebook.sync_stats(hist.clone(), esum.clone(), "bogus")
+        ok = False
+    except ValueError:
+        pass
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_codebook_statistics_sync_modes():
+    """the VQ codebook EMA under data parallelism -- all-reduce of (histogram, embedding sums) or rank-0 broadcast."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31000 + (os.getpid() % 2000)
+    mp.spawn(_vq_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

@@ -317,7 +317,7 @@ static int quad_clusters() {
         cfg.attrs = attr; cfg.numAttrs = 1;
         int c = 0;
         if (cudaOccupancyMaxActiveClusters(&c, kern, &cfg) != cudaSuccess) { cudaGetLastError(); c = 0; }
-        n = (c * 4 >= num_sms() * 9 / 10) ? c : 0;            // worth it only if (nearly) every SM can be part of a cluster
+        n = (c * 4 >= num_sms() * 85 / 100) ? c : 0;         // B200: 33 clusters of 4 = 132 of 148 SMs (GPC granularity)
         if (getenv("TTTS_GEMM_QUAD_VERBOSE")) fprintf(stderr, "[ttts] quad clusters: occupancy query says %d -> using %d\n", c, n);
     }
     return n;

@@ -159,8 +159,38 @@ class EuclideanCodebook(nn.Module):
         flat = batch_samples.reshape(-1, batch_samples.shape[-1])
         self.embed.data.copy_(torch.where(expired[:, None], _sample_vectors(flat, self.codebook_size), self.embed))
 
+    # ---- data-parallel training ----
+    # The reference keeps replicas consistent only through DDP's broadcast_buffers (rank 0's codebook overwrites the others before every
+    # forward; the Encodec broadcast_tensors calls are commented out, core_vq.py:150,168), i.e. only rank 0's batch ever trains the codebook.
+    # `sync="allreduce"` (default under an initialised process group) instead sums the per-rank code histogram and embedding sums
+    # (1024 + 1024*192 floats = 0.79 MB) before the EMA update, so every rank applies the identical update computed from the global
+    # batch (Tortoise's dvae.py:116-118 does the same).  `sync="rank0"` reproduces the reference: every rank takes rank 0's statistics.
+    # `sync=None` leaves replicas to DDP.
+    sync = "allreduce"
+
+    @staticmethod
+    def sync_stats(hist, embed_sum, mode, group=None):
+        """In-place synchronisation of the EMA statistics across ranks (host logic; tested on gloo in tests/test_ddp_gloo_cpu.py)."""
+        import torch.distributed as dist
+        if mode is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return hist, embed_sum
+        if mode == "allreduce":
+            flat = torch.cat([hist.reshape(-1), embed_sum.reshape(-1)])            # one collective, not two
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            hist.copy_(flat[:hist.numel()].view_as(hist))
+            embed_sum.copy_(flat[hist.numel():].view_as(embed_sum))
+        elif mode == "rank0":
+            flat = torch.cat([hist.reshape(-1), embed_sum.reshape(-1)])
+            dist.broadcast(flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            hist.copy_(flat[:hist.numel()].view_as(hist))
+            embed_sum.copy_(flat[hist.numel():].view_as(embed_sum))
+        else:
+            raise ValueError("EuclideanCodebook.sync must be 'allreduce', 'rank0' or None, got %r" % (mode,))
+        return hist, embed_sum
+
     @torch.no_grad()
     def _ema_update(self, hist, embed_sum):
+        self.sync_stats(hist, embed_sum, self.sync)
         lib = L.lib(); _protos(lib)
         if self._scratch is None or self._scratch.device != self.embed.device:
             self._scratch = torch.zeros(4, dtype=torch.float32, device=self.embed.device)
