@@ -363,14 +363,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                 const float mean = stats[(size_t)row * 2], rstd = stats[(size_t)row * 2 + 1];
                 ln_bwd_row<NCH>(xv, mean, rstd, w1, lane, d, dy, s_row[0], s_row[1]);
             }
+            // g_in may alias g_out: with the load inside the store loop the compiler must keep load(i + 1) behind store(i) -- NCH dependent
+            // round trips to HBM per row.  All loads of the row are issued before its first store instead (xv is dead, its registers are reused).
+            if (g_in) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const float4 gi = *reinterpret_cast<const float4*>(g_in + (size_t)row * d + (i * 32 + lane) * 4);
+                    dy[4 * i] += gi.x; dy[4 * i + 1] += gi.y; dy[4 * i + 2] += gi.z; dy[4 * i + 3] += gi.w;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < NCH; ++i) {
                 const int c = (i * 32 + lane) * 4;
                 float o[4] = {dy[4 * i], dy[4 * i + 1], dy[4 * i + 2], dy[4 * i + 3]};
-                if (g_in) {
-                    float4 gi = *reinterpret_cast<const float4*>(g_in + (size_t)row * d + c);
-                    o[0] += gi.x; o[1] += gi.y; o[2] += gi.z; o[3] += gi.w;
-                }
                 *reinterpret_cast<float4*>(g_out + (size_t)row * d + c) = make_float4(o[0], o[1], o[2], o[3]);
                 if (g16_out) {
                     if (drop.thresh16) {

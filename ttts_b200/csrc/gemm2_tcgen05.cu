@@ -6,7 +6,8 @@
 // (profiles/r1_notes.md).
 //
 // Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM alloc, warps 2-9 =
-// epilogue (two warps per TMEM lane quadrant, splitting the 256 columns).  Barriers: full[] live in the leader (count 1:
+// epilogue (two warps per TMEM lane quadrant, splitting the 256 columns; outputs and auxiliary inputs go through the TMA unit,
+// gemm_epilogue_tma.cuh).  Barriers: full[] live in the leader (count 1:
 // the leader's arrive.expect_tx covers both CTAs' bytes; both CTAs' TMA complete_tx there), empty[] / tmem_full[] are
 // per CTA and signalled by one multicast tcgen05.commit, tmem_empty[] lives in the leader (2 x 8 epilogue warps).
 #include <stdio.h>
@@ -14,7 +15,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
-#include "gemm_epilogue_staged.cuh"
+#include "gemm_epilogue_tma.cuh"
 #include "kernels.h"
 
 namespace ttts {
@@ -34,8 +35,8 @@ struct G2Cfg {
     static constexpr int kBBytes = kBRows * G2_BK * 2;
     static constexpr int kStageBytes = G2_A_BYTES + kBBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kStageOff = kBarOffset + 256 + 2 * 256 * 4;            // barriers | bias[2][256] | per-warp store staging
-    static constexpr int kSmemBytes = kStageOff + 8 * ST_BYTES + 1024;          // + alignment slack
+    static constexpr int kStageOff = kBarOffset + 1024;                          // barriers | per-warp epilogue staging units (1 KB aligned)
+    static constexpr int kSmemBytes = kStageOff + 8 * EPI_WARP_BYTES + 1024;    // + alignment slack
     static constexpr int kTileM = PAIR ? 2 * G2_BM : G2_BM;
     static constexpr int kCtas = PAIR ? 2 : 1;
 };
@@ -53,9 +54,10 @@ TTTS_DEVICE void decode_item2(const GemmParams& p, int item, int& m_pair, int& n
     m_pair = m_first + (r - n_blk * gm);
 }
 
-template <bool A_MN, bool B_MN, bool PAIR>
+template <bool A_MN, bool B_MN, bool PAIR, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)   // 10 warps: 3 on one sub-partition -> 16384/3/32 = 168 registers per thread
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmAuxOut, const GemmParams p) {
     using C = G2Cfg<PAIR>;
     constexpr int G2_STAGES = C::kStages;
     constexpr int G2_STAGE_BYTES = C::kStageBytes;
@@ -66,7 +68,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* empty_bar = full_bar + G2_STAGES;
     uint64_t* tfull_bar = empty_bar + G2_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* epi_ld_bar = tempty_bar + 2;                     // [8] one per epilogue warp: aux-input TMA loads
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(epi_ld_bar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,6 +90,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        tma_prefetch_desc(&tmAux);
+        tma_prefetch_desc(&tmAuxOut);
+        for (int w = 0; w < 8; ++w) mbar_init(&epi_ld_bar[w], 1);
         // full[]: ONE arrival (the leader's arrive.expect_tx for both CTAs' bytes); the peer's TMA only complete_tx's there
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], quad ? 2 : 1); }   // quad: both pairs' MMAs release a stage
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * C::kCtas); }     // one arrival per epilogue warp
@@ -193,13 +200,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp >= 2) {
         // ================= epilogue (both CTAs, 8 warps) =================
-        // Software-pipelined: the tile's bias is staged in smem and the first chunk's residual / pre-activation loads are
-        // issued BEFORE waiting for the accumulator (overlapping the main loop); inside the tile the TMEM load and the
-        // global prefetch of chunk c+1 are in flight while chunk c is processed; TMEM is released right after the last load.
+        // Software-pipelined: this warp's 128 bias values (4 per lane) and the first chunk's residual / pre-activation TMA load are
+        // issued BEFORE waiting for the accumulator (overlapping the main loop); inside the tile the TMEM load of chunk c+1 and the
+        // aux load of chunk c+1 are in flight while chunk c is processed; TMEM is released right after the last load.
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int et = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
-        float* sbias_all = reinterpret_cast<float*>(smem + G2_BAR_OFFSET + 256);   // [2][256]
+        EpiTmaCtx ec;
+        ec.tm_out = &tmOut; ec.tm_aux = &tmAux; ec.tm_aux_out = &tmAuxOut;
+        ec.U = smem_u32(smem + C::kStageOff + (warp - 2) * EPI_WARP_BYTES);
+        ec.ldbar = &epi_ld_bar[warp - 2];
+        ec.ld_phase = 0; ec.nstore = 0;
         int it = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
             int m_pair, n_blk, split;
@@ -207,46 +217,56 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int n0 = (n_blk * nmul + (int)pidx) * G2_BN;
-            {
-                const int c = n0 + et;
-                sbias_all[as * 256 + et] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int row = m_pair * C::kTileM + (int)rank * G2_BM + q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
             const int c0 = half * 4;
-            EpiAuxC xA, xB;
+            const int row0w = m_pair * C::kTileM + (int)rank * G2_BM + q * 32;     // first row of this warp's 32-row slab
+            const int colw = n0 + c0 * 32;                                         // first of this warp's 128 columns
+            epi_tma_issue_load<EPI>(p, ec, row0w, colw, lane);
+            if (epi_has_load<EPI>(p)) {
+                if (it == 0) epi_l2_prefetch<EPI>(p, row0w, colw, lane);
+                const int nitem = item + num_clusters;
+                if (nitem < total_items) {
+                    int m2, n2, s2;
+                    decode_item2(p, nitem, m2, n2, s2);
+                    epi_l2_prefetch<EPI>(p, m2 * C::kTileM + (int)rank * G2_BM + q * 32, (n2 * nmul + (int)pidx) * G2_BN + c0 * 32, lane);
+                }
+            }
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) {
+                const int c = colw + lane * 4;
+                if (c + 3 < p.N) bq = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                else {
+                    if (c < p.N) bq.x = __ldg(p.bias + c);
+                    if (c + 1 < p.N) bq.y = __ldg(p.bias + c + 1);
+                    if (c + 2 < p.N) bq.z = __ldg(p.bias + c + 2);
+                }
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
             uint32_t rA[32], rB[32];
-            const int row0w = row - lane;                                  // first row of this warp's 32-row slab
-            const uint32_t S = smem_u32(smem + C::kStageOff + (warp - 2) * ST_BYTES);
-            epi_prefetch_c(p, row0w, n0 + c0 * 32, lane, xA);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const float* sb = sbias_all + as * 256 + c0 * 32;
             __syncwarp();
             tmem_ld_32x32(taddr + c0 * 32, rA);
             // chunk 0 (registers A) while chunk 1 loads into B, and so on: explicit ping-pong, no register copies
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 1) * 32, rB);
-            epi_prefetch_c(p, row0w, n0 + (c0 + 1) * 32, lane, xB);
-            epi_apply_staged(p, row0w, n0 + c0 * 32, lane, rA, sb, xA, S);
+            epi_tma_apply<EPI>(p, ec, row0w, colw, lane, rA, bq, 0, colw + 32);
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 2) * 32, rA);
-            epi_prefetch_c(p, row0w, n0 + (c0 + 2) * 32, lane, xA);
-            epi_apply_staged(p, row0w, n0 + (c0 + 1) * 32, lane, rB, sb + 32, xB, S);
+            epi_tma_apply<EPI>(p, ec, row0w, colw + 32, lane, rB, bq, 1, colw + 64);
             tmem_ld_wait();
             __syncwarp();
             tmem_ld_32x32(taddr + (c0 + 3) * 32, rB);
-            epi_prefetch_c(p, row0w, n0 + (c0 + 3) * 32, lane, xB);
-            epi_apply_staged(p, row0w, n0 + (c0 + 2) * 32, lane, rA, sb + 64, xA, S);
+            epi_tma_apply<EPI>(p, ec, row0w, colw + 64, lane, rA, bq, 2, colw + 96);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_rank(&tempty_bar[as], crank & ~1u); else mbar_arrive(&tempty_bar[as]); }   // accumulator stage drained
-            epi_apply_staged(p, row0w, n0 + (c0 + 3) * 32, lane, rB, sb + 96, xB, S);
+            epi_tma_apply<EPI>(p, ec, row0w, colw + 96, lane, rB, bq, 3, -1);
         }
+        if (lane == 0) bulk_wait_all<0>();       // this warp's TMA stores have left shared memory and are globally performed
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -256,7 +276,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) { __syncwarp(); if (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
-template <bool A_MN, bool B_MN, bool PAIR>
+template <bool A_MN, bool B_MN, bool PAIR, int EPI = -1>
 static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int grid, cudaStream_t stream) {
     using C = G2Cfg<PAIR>;
     GemmParams p = p_in;
@@ -274,7 +294,18 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
                          : make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, G2_BK, true);
     else      rc = make_tmap_2d(&tmB, a.B, 2, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, G2_BK, C::kBRows, true);
     if (rc) return rc;
-    auto kern = gemm2_bf16_kernel<A_MN, B_MN, PAIR>;
+    // epilogue tensor maps: [32 rows x 64 B] boxes in the 64-byte swizzle (32 bf16 or 16 fp32 columns), true extents so ragged edges clip
+    CUtensorMap tmOut, tmAux, tmAuxOut;
+    const bool out_f32 = (a.epi == TTTS_EPI_RESID || a.epi == TTTS_EPI_F32_ADD || a.epi == TTTS_EPI_F32);
+    rc = make_tmap_2d(&tmOut, a.out, out_f32 ? 4 : 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldo, out_f32 ? 16 : 32, 32, 2);
+    if (rc) return rc;
+    tmAux = tmOut; tmAuxOut = tmOut;
+    if (a.epi == TTTS_EPI_RESID) rc = make_tmap_2d(&tmAux, a.aux, 4, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldaux, 16, 32, 2);
+    else if (a.epi == TTTS_EPI_DGELU) rc = make_tmap_2d(&tmAux, a.aux, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldaux, 32, 32, 2);
+    if (rc) return rc;
+    if (a.epi == TTTS_EPI_GELU && a.aux_out) rc = make_tmap_2d(&tmAuxOut, a.aux_out, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldaux_out, 32, 32, 2);
+    if (rc) return rc;
+    auto kern = gemm2_bf16_kernel<A_MN, B_MN, PAIR, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         TTTS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -288,7 +319,7 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
     attr[0].val.clusterDim.x = PAIR ? (p.quad ? 4 : 2) : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, tmAuxOut, p);
     prof_gemm_end(stream);
     if (e != cudaSuccess) return fail_cuda(e, "gemm2_bf16_kernel launch");
     TTTS_LAUNCH_CHECK("gemm2_bf16_kernel");
@@ -306,7 +337,7 @@ static int quad_clusters() {
     static int n = -1;
     if (n < 0) {
         using C = G2Cfg<true>;
-        auto kern = gemm2_bf16_kernel<false, true, true>;
+        auto kern = gemm2_bf16_kernel<false, true, true, -1>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -345,6 +376,9 @@ static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
     p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
     p.a3d = p.b3d = 0;
     p.quad = 0;
+    static int l2pf = -1;
+    if (l2pf < 0) { const char* e = getenv("TTTS_GEMM_L2PF"); l2pf = (e && e[0] == '0') ? 0 : 1; }
+    p.l2pf = l2pf;
     int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
     int grid = C::kCtas * (items < clusters ? items : clusters);
     if (PAIR && use_quad() && p.num_n_blocks >= 2) {
@@ -358,6 +392,21 @@ static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
             if (p.group_m > p.num_m_blocks) p.group_m = p.num_m_blocks;
             items = p.num_m_blocks * p.num_n_blocks * p.split_k;
             grid = 4 * (items < q ? items : q);
+        }
+    }
+    // the step's hot (operand majors, epilogue) combinations run kernels with the epilogue fixed at compile time (TTTS_GEMM_DYN_EPI=1: off)
+    static int dyn = -1;
+    if (dyn < 0) { const char* e = getenv("TTTS_GEMM_DYN_EPI"); dyn = (e && e[0] == '1') ? 1 : 0; }
+    if constexpr (PAIR) if (!dyn && !p.quad) {
+        if (!a.a_mn && a.b_mn) {
+            if (a.epi == TTTS_EPI_BF16) return launch_gemm2<false, true, PAIR, TTTS_EPI_BF16>(a, p, grid, stream);
+            if (a.epi == TTTS_EPI_RESID) return launch_gemm2<false, true, PAIR, TTTS_EPI_RESID>(a, p, grid, stream);
+            if (a.epi == TTTS_EPI_GELU) return launch_gemm2<false, true, PAIR, TTTS_EPI_GELU>(a, p, grid, stream);
+        } else if (!a.a_mn && !a.b_mn) {
+            if (a.epi == TTTS_EPI_BF16) return launch_gemm2<false, false, PAIR, TTTS_EPI_BF16>(a, p, grid, stream);
+            if (a.epi == TTTS_EPI_DGELU) return launch_gemm2<false, false, PAIR, TTTS_EPI_DGELU>(a, p, grid, stream);
+        } else if (a.a_mn && a.b_mn) {
+            if (a.epi == TTTS_EPI_F32_ADD) return launch_gemm2<true, true, PAIR, TTTS_EPI_F32_ADD>(a, p, grid, stream);
         }
     }
     if (!a.a_mn && !a.b_mn) return launch_gemm2<false, false, PAIR>(a, p, grid, stream);

@@ -19,6 +19,7 @@ struct GemmParams {
     void* aux_out; int ldaux_out;
     uint32_t drop_thresh16; float drop_scale; uint64_t drop_seed;
     int a3d, b3d;               // MN-major operand fetched with ONE 3-D TMA box per stage (extent % 64 == 0)
+    int l2pf;                   // TMA epilogue: L2-prefetch the next tile's residual / pre-activation slab (TTTS_GEMM_L2PF=0: off)
     int quad;                   // CTA-pair kernel in clusters of 4: two pairs on neighbouring n-blocks share the A tile by TMA multicast
 };
 
@@ -40,13 +41,16 @@ TTTS_DEVICE void epi_prefetch(const GemmParams& p, const int row, const int col0
 }
 
 // sbias: 32 floats for this chunk's columns in shared memory (zeros when there is no bias), or nullptr -> read p.bias
-TTTS_DEVICE void epi_apply(const GemmParams& p, const int row, const int col0, const uint32_t (&r)[32], const float* sbias, const EpiAux& x) {
+// epi_static >= 0: the epilogue is a compile-time constant of the calling kernel (the switch below folds away)
+TTTS_DEVICE void epi_apply(const GemmParams& p, const int row, const int col0, const uint32_t (&r)[32], const float* sbias, const EpiAux& x,
+                           const int epi_static = -1) {
     if (row >= p.M || col0 >= p.N) return;
+    const int epi = epi_static >= 0 ? epi_static : p.epi;
     const bool full = (col0 + 32 <= p.N);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.epi != TTTS_EPI_F32_ADD) {
+    if (epi != TTTS_EPI_F32_ADD) {
         if (sbias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -58,7 +62,7 @@ TTTS_DEVICE void epi_apply(const GemmParams& p, const int row, const int col0, c
             for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
         }
     }
-    switch (p.epi) {
+    switch (epi) {
     case TTTS_EPI_BF16: {
         bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
         if (full) {

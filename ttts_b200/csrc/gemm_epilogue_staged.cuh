@@ -68,34 +68,40 @@ TTTS_DEVICE void pack16(const float* v, uint4 (&q)[4]) {     // 32 floats -> 32 
 }
 
 // issue the global loads the NEXT chunk needs (coalesced mapping); a no-op for epilogues without an auxiliary input
+// EPI >= 0: epilogue fixed at compile time (hot shapes get their own kernel: no switch, no registers for the other variants); -1: p.epi
+template <int EPI>
 TTTS_DEVICE void epi_prefetch_c(const GemmParams& p, int row0, int col0, int lane, EpiAuxC& x) {
+    const int epi = EPI >= 0 ? EPI : p.epi;
+    if (epi != TTTS_EPI_RESID && epi != TTTS_EPI_DGELU) return;
     if (row0 >= p.M || col0 + 32 > p.N) return;
     const int nrows = p.M - row0;
-    if (p.epi == TTTS_EPI_RESID) {
+    if (epi == TTTS_EPI_RESID) {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(p.aux) + (size_t)row0 * p.ldaux + col0);
         gload64(g, (size_t)p.ldaux * 4, nrows, lane, x.q);
         gload64(g + 64, (size_t)p.ldaux * 4, nrows, lane, x.q + 4);
-    } else if (p.epi == TTTS_EPI_DGELU) {
+    } else {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(reinterpret_cast<const bf16*>(p.aux) + (size_t)row0 * p.ldaux + col0);
         gload64(g, (size_t)p.ldaux * 2, nrows, lane, x.q);
     }
 }
 
 // Warp-collective: all 32 lanes must call it (it contains __syncwarp).  row0 = first row of this warp's 32-row slab.
+template <int EPI>
 TTTS_DEVICE void epi_apply_staged(const GemmParams& p, const int row0, const int col0, const int lane, const uint32_t (&r)[32], const float* sbias,
                                   const EpiAuxC& x, const uint32_t S) {
     if (row0 >= p.M || col0 >= p.N) return;                     // warp-uniform
     const int row = row0 + lane;
+    const int epi = EPI >= 0 ? EPI : p.epi;
     if (col0 + 32 > p.N) {                                        // ragged column tail (heads only): simple per-thread path
         EpiAux dummy;
-        epi_apply(p, row, col0, r, sbias, dummy);
+        epi_apply(p, row, col0, r, sbias, dummy, EPI);
         return;
     }
     const int nrows = p.M - row0;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.epi != TTTS_EPI_F32_ADD) {
+    if (epi != TTTS_EPI_F32_ADD) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);
@@ -103,7 +109,7 @@ TTTS_DEVICE void epi_apply_staged(const GemmParams& p, const int row0, const int
         }
     }
     uint4 q[4];
-    switch (p.epi) {
+    switch (epi) {
     case TTTS_EPI_BF16: {
         pack16(v, q);
         stage_put_row(S, lane, q);

@@ -253,7 +253,7 @@ int gemm_bf16(const ttts_gemm_args& a, cudaStream_t stream) {
     p.out = a.out; p.ldo = a.ldo; p.bias = a.bias;
     p.aux = a.aux; p.ldaux = a.ldaux; p.aux_out = a.aux_out; p.ldaux_out = a.ldaux_out;
     p.drop_thresh16 = a.drop_thresh16; p.drop_scale = a.drop_scale; p.drop_seed = a.drop_seed;
-    p.a3d = p.b3d = 0;
+    p.a3d = p.b3d = 0; p.quad = 0; p.l2pf = 0;
     const int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
     const int grid = items < sms ? items : sms;
 

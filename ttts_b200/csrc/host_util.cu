@@ -74,7 +74,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 struct TmapKey {
-    const void* p; int eb; uint64_t inner, outer, ld; uint32_t bi, bo; bool sw; int dev;
+    const void* p; int eb; uint64_t inner, outer, ld; uint32_t bi, bo; int sw; int dev;
     bool operator==(const TmapKey& o) const {
         return p == o.p && eb == o.eb && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo &&
                sw == o.sw && dev == o.dev;
@@ -83,18 +83,18 @@ struct TmapKey {
 struct TmapKeyHash {
     size_t operator()(const TmapKey& k) const {
         uint64_t h = (uint64_t)(uintptr_t)k.p * 0x9E3779B97F4A7C15ULL;
-        h ^= k.inner * 0xff51afd7ed558ccdULL + k.outer * 0xc4ceb9fe1a85ec53ULL + k.ld * 31 + k.bi * 131 + k.bo * 17 + k.eb + (k.sw ? 7 : 0) + k.dev * 1315423911ULL;
+        h ^= k.inner * 0xff51afd7ed558ccdULL + k.outer * 0xc4ceb9fe1a85ec53ULL + k.ld * 31 + k.bi * 131 + k.bo * 17 + k.eb + k.sw * 7 + k.dev * 1315423911ULL;
         return (size_t)h;
     }
 };
 
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                 uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+                 uint32_t box_inner, uint32_t box_outer, int swizzle) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    TmapKey key{gptr, elem_bytes, inner, outer, ld_elems, box_inner, box_outer, swizzle128, dev};
+    TmapKey key{gptr, elem_bytes, inner, outer, ld_elems, box_inner, box_outer, swizzle, dev};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -111,7 +111,7 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t in
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = enc(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r, (unsigned long long)inner,

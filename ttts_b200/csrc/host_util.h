@@ -41,11 +41,11 @@ void prof_gemm_end(cudaStream_t st);
         ::ttts::count_launch();                                   \
     } while (0)
 
-// 2-D bf16/fp32 tiled tensor map with 128B swizzle (or none).
+// 2-D bf16/fp32 tiled tensor map; swizzle: 0 = none, 1 (true) = 128B, 2 = 64B.
 //   inner/outer: tensor extents in elements (inner = contiguous dim); ld_elems: row stride in elements
 //   box_inner/box_outer: box extents in elements
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                 uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+                 uint32_t box_inner, uint32_t box_outer, int swizzle);
 
 // 3-D view of an MN-major operand [K rows][MN contiguous] as {64 (mn), K, MN/64 atoms}: one TMA box {64, box_k, atoms}
 // lands in shared memory as [atom][k][64] -- exactly the MN-major 128B-swizzle UMMA layout.  Requires MN % 64 == 0.
