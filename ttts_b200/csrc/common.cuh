@@ -364,6 +364,10 @@ TTTS_DEVICE void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     uint32_t sz = pred ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
 }
+TTTS_DEVICE void cp_async4(void* smem_dst, const void* gsrc, bool pred) {      // 4 bytes, zero fill when !pred (gsrc must still be a valid address)
+    uint32_t sz = pred ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
 TTTS_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 TTTS_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

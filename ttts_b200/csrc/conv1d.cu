@@ -295,6 +295,163 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_kernel(const ConvParams
     }
 }
 
+// Pipelined form of the implicit GEMM (default; TTTS_CONV_PIPE=0 selects the double-buffered kernel above): the encoder's layers are
+// small (Cout <= 192, 2 304 positions for the 16 WN layers -> 216 CTAs of 4 warps), so each CTA's chunk loop ran at the latency of one
+// L2 round trip per 16-row chunk (~1.7 us per chunk, profiles/r1d_launches_vqenc.csv: 104 us for 0.85 GFLOP).  Here the im2col gather
+// is IG_STAGES - 1 chunks ahead through 4-byte cp.async (zero fill for padding), the (ci, k) decomposition of the row index is advanced
+// incrementally instead of divided out per element, leaky-ReLU moves to the shared-memory read.  Same accumulation order: bit-identical.
+constexpr int IG_STAGES = 4;
+
+template <int CO_T>
+__global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvParams p) {
+    constexpr int NT = CO_T * 4;                 // threads: (CO_T/4) x 16
+    constexpr int LDA = CO_T + 4, LDB = IG_P + 4;
+    constexpr int NB = IG_R * IG_P / NT;         // B-tile elements per thread (4 or 8)
+    constexpr int S = IG_STAGES;
+    constexpr int A_ST = IG_R * LDA, B_ST = IG_R * LDB;                         // floats per stage
+    constexpr int GATE_F = CO_T * (IG_P + 1);                                   // gated epilogue exchange buffer aliases the ring
+    constexpr int SMEM_F = S * (A_ST + B_ST) > GATE_F ? S * (A_ST + B_ST) : GATE_F;
+    __shared__ __align__(16) float ig_smem[SMEM_F];
+    float* const sA = ig_smem;                   // [S][IG_R][LDA]
+    float* const sB = ig_smem + S * A_ST;        // [S][IG_R][LDB]
+    const int gated = (p.post == 1 || p.post == 3);
+    const int Chalf = p.Cout >> 1;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int p0 = blockIdx.x * IG_P;
+    const int co0 = blockIdx.y * (gated ? CO_T / 2 : CO_T);
+    const int R = p.Cin * p.K;
+    const int Ptot = p.B * p.Tout;
+    const int nchunks = (R + IG_R - 1) / IG_R;
+
+    // ---- B loader: this thread always loads column cb (one output position), rows rb0 + (NT/64)*i
+    const int cb = tid & 63, rb0 = tid >> 6;
+    const int posb = p0 + cb;
+    const bool pos_ok = posb < Ptot;
+    const int bb = pos_ok ? posb / p.Tout : 0;
+    const int tb = pos_ok ? posb - bb * p.Tout : 0;
+    const float* xb = p.x + (size_t)bb * p.Cin * p.Tin;
+    const int ti0 = tb * p.stride - p.pad;
+    // ---- A loader: row (output channel) ca, r-columns ra4..ra4+3
+    const int ca = tid >> 2, ra4 = (tid & 3) * 4;
+    int coa; bool coa_ok;
+    if (gated) { const int cl = ca < CO_T / 2 ? ca : ca - CO_T / 2; coa_ok = (co0 + cl) < Chalf; coa = (ca < CO_T / 2 ? 0 : Chalf) + co0 + cl; }
+    else { coa = co0 + ca; coa_ok = coa < p.Cout; }
+    const float* wa = p.w + (size_t)coa * R;
+
+    // (ci, k) of each of this thread's B elements, advanced by IG_R rows per issued chunk (no division in the loop)
+    int bci[NB], bk[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { const int rr = rb0 + (NT / 64) * i; bci[i] = rr / p.K; bk[i] = rr - bci[i] * p.K; }
+    const int c16 = IG_R / p.K, k16 = IG_R - c16 * p.K;
+    // chunks are issued in order: chunk -> stage chunk % S, 4-byte cp.async with zero fill for padding / tails
+    auto issue = [&](int chunk) {
+        const int r0 = chunk * IG_R;
+        float* a = sA + (chunk % S) * A_ST;
+        float* b = sB + (chunk % S) * B_ST;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = r0 + ra4 + i;
+            const bool ok = coa_ok && rr < R;
+            cp_async4(&a[(ra4 + i) * LDA + ca], ok ? wa + rr : p.w, ok);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int rr = r0 + rb0 + (NT / 64) * i;
+            const int ti = ti0 + bk[i] * p.dil;
+            const bool ok = pos_ok && rr < R && ti >= 0 && ti < p.Tin;
+            cp_async4(&b[(rb0 + (NT / 64) * i) * LDB + cb], ok ? xb + (size_t)bci[i] * p.Tin + ti : p.x, ok);
+            bk[i] += k16; bci[i] += c16;
+            if (bk[i] >= p.K) { bk[i] -= p.K; ++bci[i]; }
+        }
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) { if (s < nchunks) issue(s); cp_async_commit(); }
+    const bool lrelu = p.pre_lrelu != 0;
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<S - 2>();                  // chunk c has landed (S - 2 younger groups may still be in flight)
+        __syncthreads();                         // ... for every thread, and everybody is done computing on stage (c - 1) % S
+        if (c + S - 1 < nchunks) issue(c + S - 1);
+        cp_async_commit();
+        const float* a = sA + (c % S) * A_ST;
+        const float* b = sB + (c % S) * B_ST;
+#pragma unroll
+        for (int r = 0; r < IG_R; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&a[r * LDA + ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&b[r * LDB + tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+            if (lrelu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b4[j] = b4[j] > 0.f ? b4[j] : 0.1f * b4[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    if (!gated) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = p0 + tx * 4 + j;
+            if (pos >= Ptot) continue;
+            const int b = pos / p.Tout, t = pos - b * p.Tout;
+            const float mk = p.mask ? p.mask[(size_t)b * p.Tout + t] : 1.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = co0 + ty * 4 + i;
+                if (co >= p.Cout) continue;
+                float v = acc[i][j] + (p.bias ? __ldg(p.bias + co) : 0.f);
+                if (p.post == 2) v = mish_f(v);
+                const size_t o = ((size_t)b * p.Cout + co) * p.Tout + t;
+                if (p.resid) v += p.resid[o];
+                v *= p.out_scale;
+                if (p.mask) v *= mk;
+                p.y[o] = p.accumulate ? p.y[o] + v : v;
+            }
+        }
+    } else {
+        // rows < CO_T/2 of the tile are "a" channels, rows >= CO_T/2 the matching "b" channels -> exchange through shared memory
+        float (*sgate)[IG_P + 1] = reinterpret_cast<float (*)[IG_P + 1]>(ig_smem);
+        __syncthreads();                         // the ring is dead: every thread has left the main loop
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sgate[ty * 4 + i][tx * 4 + j] = acc[i][j];
+        __syncthreads();
+        for (int i = tid; i < (CO_T / 2) * IG_P; i += NT) {
+            const int cl = i / IG_P, pl = i - cl * IG_P;
+            const int c = co0 + cl, pos = p0 + pl;
+            if (c >= Chalf || pos >= Ptot) continue;
+            const int b = pos / p.Tout, t = pos - b * p.Tout;
+            float a = sgate[cl][pl] + (p.bias ? __ldg(p.bias + c) : 0.f);
+            float g = sgate[cl + CO_T / 2][pl] + (p.bias ? __ldg(p.bias + Chalf + c) : 0.f);
+            float v;
+            if (p.post == 1) {
+                v = a * (1.f / (1.f + expf(-g)));                                         // GLU
+            } else {
+                if (p.cond) { a += p.cond[(size_t)b * p.cond_ld + c]; g += p.cond[(size_t)b * p.cond_ld + Chalf + c]; }
+                v = tanhf(a) * (1.f / (1.f + expf(-g)));                                  // WN gate
+            }
+            const size_t o = ((size_t)b * Chalf + c) * p.Tout + t;
+            if (p.resid) v += p.resid[o];
+            v *= p.out_scale;
+            if (p.mask) v *= p.mask[(size_t)b * p.Tout + t];
+            p.y[o] = p.accumulate ? p.y[o] + v : v;
+        }
+    }
+}
+
 // weight norm: w[co, :] = g[co] * v[co, :] / ||v[co, :]||      (torch.nn.utils.weight_norm, dim=0)
 __global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int Cout, int n) {
     const int co = blockIdx.x;
@@ -384,12 +541,16 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
         // 32-channel tiles when the layer has few output channels (or few CTAs): no half-empty tiles, more CTAs in flight
         const long long ctas64 = ((Ptot + IG_P - 1) / IG_P) * ((ceff + (gated ? 31 : 63)) / (gated ? 32 : 64));
         const bool small = (gated ? ceff <= 16 : ceff <= 32) || ctas64 < 2 * num_sms();
+        static int pipe = -1;
+        if (pipe < 0) { const char* e = getenv("TTTS_CONV_PIPE"); pipe = (e && e[0] == '0') ? 0 : 1; }
         if (small) {
             dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 15 : 31)) / (gated ? 16 : 32));
-            conv1d_igemm_kernel<32><<<grid, 128, 0, st>>>(p);
+            if (pipe) conv1d_igemm_pipe_kernel<32><<<grid, 128, 0, st>>>(p);
+            else conv1d_igemm_kernel<32><<<grid, 128, 0, st>>>(p);
         } else {
             dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 31 : 63)) / (gated ? 32 : 64));
-            conv1d_igemm_kernel<64><<<grid, 256, 0, st>>>(p);
+            if (pipe) conv1d_igemm_pipe_kernel<64><<<grid, 256, 0, st>>>(p);
+            else conv1d_igemm_kernel<64><<<grid, 256, 0, st>>>(p);
         }
         TTTS_LAUNCH_CHECK("conv1d_igemm");
         return TTTS_OK;

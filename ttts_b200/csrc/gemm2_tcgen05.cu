@@ -377,7 +377,7 @@ static int gemm2_impl(const ttts_gemm_args& a, cudaStream_t stream) {
     p.a3d = p.b3d = 0;
     p.quad = 0;
     static int l2pf = -1;
-    if (l2pf < 0) { const char* e = getenv("TTTS_GEMM_L2PF"); l2pf = (e && e[0] == '0') ? 0 : 1; }
+    if (l2pf < 0) { const char* e = getenv("TTTS_GEMM_L2PF"); l2pf = (e && e[0] == '1') ? 1 : 0; }
     p.l2pf = l2pf;
     int items = p.num_m_blocks * p.num_n_blocks * p.split_k;
     int grid = C::kCtas * (items < clusters ? items : clusters);

@@ -19,7 +19,7 @@ struct GemmParams {
     void* aux_out; int ldaux_out;
     uint32_t drop_thresh16; float drop_scale; uint64_t drop_seed;
     int a3d, b3d;               // MN-major operand fetched with ONE 3-D TMA box per stage (extent % 64 == 0)
-    int l2pf;                   // TMA epilogue: L2-prefetch the next tile's residual / pre-activation slab (TTTS_GEMM_L2PF=0: off)
+    int l2pf;                   // TMA epilogue: L2-prefetch the next tile's residual / pre-activation slab (TTTS_GEMM_L2PF=1; measured slower: default off)
     int quad;                   // CTA-pair kernel in clusters of 4: two pairs on neighbouring n-blocks share the A tile by TMA multicast
 };
 

@@ -78,8 +78,10 @@ TTTS_DEVICE bool epi_has_load(const GemmParams& p) {
     return epi == TTTS_EPI_RESID || epi == TTTS_EPI_DGELU;
 }
 
-// L2 prefetch of the aux input this warp will need for a whole tile (32 rows x 128 columns): one bulk prefetch per lane = per row.
-// Issued one tile ahead, so the chunk-by-chunk TMA loads below hit L2 instead of waiting for HBM inside the epilogue's critical path.
+// L2 prefetch of the aux input this warp will need for a whole tile (32 rows x 128 columns), one row per lane, issued one tile ahead
+// so that the chunk-by-chunk TMA loads below hit L2 instead of waiting for HBM inside the epilogue's critical path.  Plain
+// prefetch.global.L2 (LSU path): the bulk form goes through the TMA unit's queue, where 256 extra requests per tile delayed the main
+// loop's operand loads (measured: every aux-loading GEMM got 4 - 11 % slower with cp.async.bulk.prefetch.L2).
 template <int EPI>
 TTTS_DEVICE void epi_l2_prefetch(const GemmParams& p, const int row0, const int colw, const int lane) {
     const int epi = EPI >= 0 ? EPI : p.epi;
@@ -87,7 +89,9 @@ TTTS_DEVICE void epi_l2_prefetch(const GemmParams& p, const int row0, const int 
     if (!p.l2pf || row0 + lane >= p.M || colw + 128 > p.N) return;
     const int eb = epi == TTTS_EPI_RESID ? 4 : 2;
     const uint8_t* g = reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)(row0 + lane) * p.ldaux + colw) * eb;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(128 * eb) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i * 128 < 128 * eb) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + i * 128) : "memory");
 }
 
 // Issue the aux-input load of chunk (row0, col0) into the staging units.  Warp-collective (all lanes call; lane 0 issues).  For DGELU

@@ -46,6 +46,9 @@ class FusedStep:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.comm_stream = torch.cuda.Stream(device=self.eng.device) if self.world > 1 else None
         L = model.layers
+        # TTTS_COMM_CHUNKS overrides the number of overlapped all-reduce chunks; 0 = ONE all-reduce of the whole buffer after backward
+        comm_chunks = int(os.environ.get("TTTS_COMM_CHUNKS", comm_chunks))
+        self.overlap = comm_chunks > 0
         n = max(1, min(comm_chunks, L))
         # stage 0 = heads/final norms, stages 1..L = layers L-1..0, stage L+1 = embeddings
         bounds = [0, 1] + [1 + (L * (i + 1)) // n for i in range(n)]
@@ -78,7 +81,10 @@ class FusedStep:
             eng.grads.zero_()
         last = (self._micro == self.accumulate - 1)
         wt, wm = self.text_weight / self.accumulate, self.mel_weight / self.accumulate
-        if self.world > 1 and last:
+        if self.world > 1 and last and not self.overlap:
+            eng.backward(weight_text=wt, weight_mel=wm)
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        elif self.world > 1 and last:
             main = torch.cuda.current_stream()
             for (s0, s1) in self.chunks:
                 eng.backward(weight_text=wt, weight_mel=wm, stage_begin=s0, stage_end=s1)
