@@ -30,10 +30,15 @@ def t(fn):
     return e0.elapsed_time(e1) / iters
 
 
-for p in (0.0, 0.1):
+for p in ([float(os.environ['ONLY_P'])] if 'ONLY_P' in os.environ else [0.0, 0.1]):
     f = lambda: L.check(lib.ttts_attn_fwd(L.ptr(qkv), L.ptr(out), L.ptr(lse), B, T, H, ctypes.c_float(p), ctypes.c_uint64(7), L.stream_ptr()))
     b = lambda: L.check(lib.ttts_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(scratch), L.ptr(dqkv), B, T, H, ctypes.c_float(p),
                                           ctypes.c_uint64(7), L.stream_ptr()))
     mf, mb = t(f), t(b)
     print("legacy=%s p=%.1f  fwd %.3f ms (%.0f TFLOP/s)   bwd %.3f ms (%.0f TFLOP/s, 2.5x fwd flops)" % (
         os.environ.get("TTTS_ATTN_LEGACY", "0"), p, mf, flops_fwd / mf / 1e9, mb, 2.5 * flops_fwd / mb / 1e9), flush=True)
+    # digests of the results: runs with different TTTS_ATTN_VER must print identical lines (the versions differ in schedule only)
+    import hashlib
+    torch.cuda.synchronize()
+    dig = [hashlib.sha1(x.detach().cpu().view(torch.uint8).numpy().tobytes()).hexdigest()[:12] for x in (out, lse, dqkv)]
+    print("digest p=%.1f out %s lse %s dqkv %s" % (p, *dig), flush=True)

@@ -1054,6 +1054,14 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 // per-CTA prologue / epilogue that cost ~1 000 (forward) - 2 600 (backward) cycles per 128x128 block pair at T = 1 156 (5.5 block pairs
 // per CTA on average, profiles/r1_notes.md) is overlapped instead of exposed.
 // ------------------------------------------------------------------------------------------------------------
+// Exact n / d for n * d < 2^32 by one multiply-high (m = ceil(2^32 / d); d == 1 handled apart).  The persistent kernels decompose an item
+// index three times per item in each of the 18 warps; the generic integer division (I2F + MUFU.RCP + ~20 instructions) queued behind the
+// softmax warps' MUFU.EX2 stream (profiles/r1h_attn_bwd4_ncu_full.txt: 3.7 % of all stall samples on one I2F).
+struct FastDiv { uint32_t d, m; };
+TTTS_DEVICE FastDiv fastdiv_make(uint32_t d) { FastDiv f; f.d = d; f.m = (uint32_t)((0x100000000ULL + d - 1) / d); return f; }
+TTTS_DEVICE uint32_t fastdiv(uint32_t n, const FastDiv f) { return f.d == 1 ? n : __umulhi(n, f.m); }
+TTTS_DEVICE uint32_t fastmod(uint32_t n, const FastDiv f) { return n - fastdiv(n, f) * f.d; }
+
 struct Fwd4Smem {
     static constexpr int kKvStages = 3;
     static constexpr int oQ = 0;                                        // [2]
@@ -1064,6 +1072,14 @@ struct Fwd4Smem {
     static constexpr int kBytes = oXch + (2 * 4 * 128 + 4 * 128) * 4 + 1024;
 };
 
+// kMode 0: the r1e kernel as measured in profiles/r1h_attn_fwd4_ncu_full.txt (dropout decided at run time, after all exponentials, one
+// 512-thread barrier per key block).  kMode 1 (dropout) / 2 (none) = version 5: the r1h profile showed the 16 softmax warps spending 27 % of
+// their time in a MUFU-bound exponential phase (32 MUFU.EX2 per warp, 4 warps per sub-partition in lock step) followed by 26 % in a pure
+// integer phase (the dropout hash, behind a uniform branch the scheduler cannot move code across).  With the dropout decision a template
+// parameter and the hash of each 4-key group written next to that group's exponentials, both sit in one basic block and the IMAD / LOP3
+// work issues in the shadow of the MUFU pipe.  The row-max exchange only concerns the four warps that share a lane quadrant (same rows,
+// different columns), so it uses one 128-thread named barrier per quadrant instead of one for all 16 warps.  Same arithmetic, same bits.
+template <int kMode>
 __global__ void __maxnreg__(96)
 attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, int BH, float scale,
                     DropCfg drop) {
@@ -1090,9 +1106,10 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     // gridDim.x: in round n this CTA takes position (blockIdx.x + n) mod gridDim.x.  CTAs running at the same time therefore work on
     // ~gridDim.x / nq neighbouring heads (their K/V stay in L2), and the rotation walks every CTA through all block weights.
     const int rounds = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)((blockIdx.x + n) % gridDim.x); return idx < total ? idx : -1; };
-    auto item_qb = [&](int idx) { return nq - 1 - idx % nq; };
-    auto item_bh = [&](int idx) { return idx / nq; };
+    const FastDiv fd_grid = fastdiv_make(gridDim.x), fd_nq = fastdiv_make((uint32_t)nq), fd_H = fastdiv_make((uint32_t)H);
+    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)fastmod(blockIdx.x + n, fd_grid); return idx < total ? idx : -1; };
+    auto item_qb = [&](int idx) { return nq - 1 - (int)fastmod((uint32_t)idx, fd_nq); };
+    auto item_bh = [&](int idx) { return (int)fastdiv((uint32_t)idx, fd_nq); };
     auto item_nkv = [&](int qb) { return min(qb + 1, (T + AT_BN - 1) / AT_BN); };
 
     if (threadIdx.x == 0) {
@@ -1118,7 +1135,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         // ---------------- TMA: Q per item (double-buffered), K/V ring across items ----------------
         uint32_t kvc = 0;
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
-            const int qb = item_qb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int qb = item_qb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, nkv = item_nkv(qb);
             mbar_wait(&q_empty[n & 1], ((n >> 1) & 1) ^ 1);
             if (elect_one()) {
@@ -1199,7 +1216,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         const uint32_t t32 = drop.thresh16 << 16;
         uint32_t g = 0;
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
-            const int qb = item_qb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int qb = item_qb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, nkv = item_nkv(qb);
             const int qi = qb * AT_BM + r;
             float m_used = -INFINITY, l_run = 0.f;
@@ -1228,7 +1245,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
                 xmax[((g & 1) * 4 + qtr) * 128 + r] = fmaxf(mx0, mx1);
-                named_bar_sync(2, 512);
+                if (kMode == 0) named_bar_sync(2, 512); else named_bar_sync(2 + quad, 128);
                 const float* xm = xmax + (g & 1) * 4 * 128 + r;
                 const float m_new = fmaxf(fmaxf(fmaxf(xm[0], xm[128]), fmaxf(xm[256], xm[384])), m_used);
                 if (j == 0) {
@@ -1253,37 +1270,103 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
                 }
                 const float msc = m_used * sl2;
                 float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc));
-                    const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
-                    const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -msc));
-                    const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -msc));
-                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                    v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
-                }
-                l_run += (rs0 + rs1) + (rs2 + rs3);
-                if (drop.thresh16) {
+                if (kMode == 1) {
+                    // Two schedules, chosen per warp: odd column quarters hash BEFORE their exponentials, even ones after.  The four warps
+                    // of a sub-partition enter every key block together (row-max barrier), so with a single schedule they would all sit in
+                    // the MUFU-bound phase and then all in the integer phase; split 2 + 2, one pair's IMAD / LOP3 stream issues while the
+                    // other pair occupies the MUFU pipe.  The branches are warp-uniform; the empty volatile asms keep the front end from
+                    // merging or sinking the two copies of the hash (ptxas does not move code across the branches).
+                    const bool hash_first = (qtr & 1) != 0;
                     const uint32_t g0 = (uint32_t)kc0 >> 2;
+                    uint32_t w[16];
+                    float mscv = msc;
+                    if (hash_first) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) attn_drop_words(rk, g0 + i4, w[2 * i4], w[2 * i4 + 1]);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) asm volatile("" : "+r"(w[e]));
+                        // ptxas hoists the (speculation-safe) exponentials above this block unless they depend on it: OR in a word that is
+                        // zero at run time (thresh16 < 2^16) but not provably so
+                        mscv = __uint_as_float(__float_as_uint(msc) | (w[15] & (drop.thresh16 >> 16)));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) asm volatile("" : "=r"(w[e]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));        // the exponentials start after the first hash block
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -mscv));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -mscv));
+                        const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -mscv));
+                        const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -mscv));
+                        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                        v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
+                    }
+                    l_run += (rs0 + rs1) + (rs2 + rs3);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+                    if (!hash_first) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) attn_drop_words(rk, g0 + i4, w[2 * i4], w[2 * i4 + 1]);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) asm volatile("" : "+r"(w[e]));
+                    }
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        uint32_t w0, w1;
-                        attn_drop_words(rk, g0 + i4, w0, w1);
+                        const uint32_t w0 = w[2 * i4], w1 = w[2 * i4 + 1];
                         v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
                         v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
                         v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
                         v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
                     }
-                }
-                mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
-                const uint32_t sP = smem_u32(smem + S::oP + (g & 1) * 2 * AT_TILE);
+                } else {
 #pragma unroll
-                for (int gg = 0; gg < 4; ++gg)
-                    st_tile_chunk(sP, r, qtr * 4 + gg,
-                                  make_uint4(pack_bf16(__uint_as_float(v[8 * gg]), __uint_as_float(v[8 * gg + 1])),
-                                             pack_bf16(__uint_as_float(v[8 * gg + 2]), __uint_as_float(v[8 * gg + 3])),
-                                             pack_bf16(__uint_as_float(v[8 * gg + 4]), __uint_as_float(v[8 * gg + 5])),
-                                             pack_bf16(__uint_as_float(v[8 * gg + 6]), __uint_as_float(v[8 * gg + 7]))));
+                    for (int i = 0; i < 32; i += 4) {
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
+                        const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -msc));
+                        const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -msc));
+                        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                        v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
+                    }
+                    l_run += (rs0 + rs1) + (rs2 + rs3);
+                    if (kMode == 0 && drop.thresh16) {
+                        const uint32_t g0 = (uint32_t)kc0 >> 2;
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            uint32_t w0, w1;
+                            attn_drop_words(rk, g0 + i4, w0, w1);
+                            v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
+                            v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
+                            v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
+                            v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
+                        }
+                    }
+                }
+                const uint32_t sP = smem_u32(smem + S::oP + (g & 1) * 2 * AT_TILE);
+                if (kMode == 0) {
+                    mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg)
+                        st_tile_chunk(sP, r, qtr * 4 + gg,
+                                      make_uint4(pack_bf16(__uint_as_float(v[8 * gg]), __uint_as_float(v[8 * gg + 1])),
+                                                 pack_bf16(__uint_as_float(v[8 * gg + 2]), __uint_as_float(v[8 * gg + 3])),
+                                                 pack_bf16(__uint_as_float(v[8 * gg + 4]), __uint_as_float(v[8 * gg + 5])),
+                                                 pack_bf16(__uint_as_float(v[8 * gg + 6]), __uint_as_float(v[8 * gg + 7]))));
+                } else {
+                    // packed BEFORE the wait and pinned there: otherwise the front end sinks the hash / select / pack chain below the
+                    // wait loop (a block boundary), which is exactly the serial MUFU-phase-then-integer-phase schedule this version removes
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        pk[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                        asm volatile("" : "+r"(pk[e]));
+                    }
+                    mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) st_tile_chunk(sP, r, qtr * 4 + gg, make_uint4(pk[4 * gg], pk[4 * gg + 1], pk[4 * gg + 2], pk[4 * gg + 3]));
+                }
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
@@ -1299,7 +1382,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             tmem_ld_wait();
             tc_fence_before();
             xsum[qtr * 128 + r] = l_run;
-            named_bar_sync(2, 512);
+            if (kMode == 0) named_bar_sync(2, 512); else named_bar_sync(2 + quad, 128);
             const float l_tot = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
             if (qi < T) {
                 const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;
@@ -1332,6 +1415,9 @@ struct Bwd4Smem {
     static constexpr int kBytes = oBar + 256 + 1024;
 };
 
+// kMode as in the forward kernel: 0 = r1e code (run-time dropout branch after the exponentials of each 16-column chunk), 1 / 2 = dropout
+// on / off fixed at compile time with each 4-key group's hash next to its exponentials.
+template <int kMode>
 __global__ void __maxnreg__(96)
 attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
                     const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, int BH, float scale,
@@ -1360,9 +1446,10 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     // head-major items dealt out in rotating rounds (see the forward kernel): concurrent CTAs share a few heads, so Q / dO / K / V and the
     // fp32 dQ accumulator rows they red.add into stay in L2 (with key-block-major items the accumulator traffic went to HBM)
     const int rounds = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)((blockIdx.x + n) % gridDim.x); return idx < total ? idx : -1; };
-    auto item_jb = [&](int idx) { return idx % nq; };
-    auto item_bh = [&](int idx) { return idx / nq; };
+    const FastDiv fd_grid = fastdiv_make(gridDim.x), fd_nq = fastdiv_make((uint32_t)nq), fd_H = fastdiv_make((uint32_t)H);
+    auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)fastmod(blockIdx.x + n, fd_grid); return idx < total ? idx : -1; };
+    auto item_jb = [&](int idx) { return (int)fastmod((uint32_t)idx, fd_nq); };
+    auto item_bh = [&](int idx) { return (int)fastdiv((uint32_t)idx, fd_nq); };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -1387,7 +1474,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     if (warp == 0) {
         uint32_t c = 0;
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
-            const int jb = item_jb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int jb = item_jb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, k0 = jb * AT_BN, nit = nq - jb;
             mbar_wait(&kv_empty[n & 1], ((n >> 1) & 1) ^ 1);
             uint8_t* sk = smem + S::oKV + (n & 1) * 2 * AT_TILE;
@@ -1510,7 +1597,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         { const int idx0 = item_at(0); if (idx0 >= 0) fetch_row_stats(item_bh(idx0), item_jb(idx0)); }
         uint32_t c = 0;
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
-            const int jb = item_jb(idx), bh = item_bh(idx), b = bh / H, h = bh - b * H;
+            const int jb = item_jb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, k0 = jb * AT_BN, nit = nq - jb;
             const int kc0 = k0 + qtr * 32;
             const int idx_nx = item_at(n + 1);
@@ -1521,8 +1608,12 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 const uint32_t ph = c & 1;
                 const int qi = i * AT_BM + r;
                 const bool q_ok = qi < T;
-                const float lse2 = lse_nx * kLog2eF;
-                const float dlt = dlt_nx;
+                // pinned: without it the compiler rotates this multiply into the previous iteration, right behind the load it was meant to
+                // be a whole block away from (r1h profile: 4.5 % of the stall samples on that FMUL)
+                float lse_cur = lse_nx, dlt_cur = dlt_nx;
+                asm volatile("" : "+f"(lse_cur), "+f"(dlt_cur));
+                const float lse2 = lse_cur * kLog2eF;
+                const float dlt = dlt_cur;
                 if (it + 1 < nit) fetch_row_stats(bh, i + 1);
                 else if (idx_nx >= 0) fetch_row_stats(bh_nx, jb_nx);
                 const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
@@ -1544,34 +1635,69 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                         if (lane == 0) mbar_arrive(sdp_empty);
                     }
                     float p[16];
-                    if (need_mask) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int kj = kc0 + cc * 16 + e;
-                            p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
-                    }
                     float ds[16];
-                    if (drop.thresh16) {
+                    if (kMode == 1) {
+                        // per 4-key group: hash, exponentials, gradient -- one basic block per mask variant, integer work under the MUFU latency
                         const uint32_t g0 = (uint32_t)(kc0 + cc * 16) >> 2;
+                        if (need_mask) {
 #pragma unroll
-                        for (int e4 = 0; e4 < 4; ++e4) {
-                            uint32_t w0, w1;
-                            attn_drop_words(rk, g0 + e4, w0, w1);
-                            const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
+                            for (int e4 = 0; e4 < 4; ++e4) {
+                                uint32_t w0, w1;
+                                attn_drop_words(rk, g0 + e4, w0, w1);
+                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                                ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
-                                p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
+                                for (int e = 0; e < 4; ++e) {
+                                    const int kj = kc0 + cc * 16 + e4 * 4 + e;
+                                    const float pe = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e4 * 4 + e]), sl2, -lse2)) : 0.f;
+                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
+                                    ds[e4 * 4 + e] = pe * (k4[e] ? u : -dlt);
+                                    p[e4 * 4 + e] = k4[e] ? pe : 0.f;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4) {
+                                uint32_t w0, w1;
+                                attn_drop_words(rk, g0 + e4, w0, w1);
+                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float pe = ex2_fast(fmaf(__uint_as_float(sv[e4 * 4 + e]), sl2, -lse2));
+                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
+                                    ds[e4 * 4 + e] = pe * (k4[e] ? u : -dlt);
+                                    p[e4 * 4 + e] = k4[e] ? pe : 0.f;
+                                }
                             }
                         }
                     } else {
+                        if (need_mask) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
+                            for (int e = 0; e < 16; ++e) {
+                                const int kj = kc0 + cc * 16 + e;
+                                p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
+                        }
+                        if (kMode == 0 && drop.thresh16) {
+                            const uint32_t g0 = (uint32_t)(kc0 + cc * 16) >> 2;
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4) {
+                                uint32_t w0, w1;
+                                attn_drop_words(rk, g0 + e4, w0, w1);
+                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
+                                    ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
+                                    p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
+                        }
                     }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { pp[cc * 8 + e] = pack_bf16(p[2 * e], p[2 * e + 1]); dd[cc * 8 + e] = pack_bf16(ds[2 * e], ds[2 * e + 1]); }
@@ -1643,10 +1769,11 @@ bool attn_use_tc() {
     return !legacy;
 }
 
-// TTTS_ATTN_VER=2|3 selects the earlier kernels (2: 8 softmax warps; 3: 16 warps, one CTA per item) for A/B measurements; default 4 (persistent)
+// TTTS_ATTN_VER=2|3|4 selects the earlier kernels (2: 8 softmax warps; 3: 16 warps, one CTA per item; 4: persistent, run-time dropout
+// branch) for A/B measurements; default 5 (persistent, dropout fixed at compile time, hash interleaved with the exponentials)
 static int attn_tc_version() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 4; }
+    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : 5; }
     return v;
 }
 
@@ -1664,9 +1791,18 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
     dim3 grid((T + AT_BM - 1) / AT_BM, B * H);
     if (attn_tc_version() >= 4) {
         static bool attr4 = false;
-        if (!attr4) { TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes)); attr4 = true; }
+        if (!attr4) {
+            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+            attr4 = true;
+        }
         const int items = (int)grid.x * B * H;
-        attn_fwd_tc4_kernel<<<items < num_sms() ? items : num_sms(), AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
+        const int nblk = items < num_sms() ? items : num_sms();
+        TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
+        if (attn_tc_version() == 4) attn_fwd_tc4_kernel<0><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
+        else if (drop.thresh16) attn_fwd_tc4_kernel<1><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
+        else attn_fwd_tc4_kernel<2><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
     } else if (attn_tc_version() >= 3) attn_fwd_tc3_kernel<<<grid, AT3_THREADS, Fwd3Smem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     else attn_fwd_tc_kernel<<<grid, AT_THREADS, FwdSmem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
@@ -1697,10 +1833,18 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
     dim3 grid((T + AT_BN - 1) / AT_BN, B * H);
     if (attn_tc_version() >= 4) {
         static bool attr4 = false;
-        if (!attr4) { TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes)); attr4 = true; }
+        if (!attr4) {
+            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+            attr4 = true;
+        }
         const int items = (int)grid.x * B * H;
-        attn_bwd_tc4_kernel<<<items < num_sms() ? items : num_sms(), AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f,
-                                                                                                      drop);
+        const int nblk = items < num_sms() ? items : num_sms();
+        TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
+        if (attn_tc_version() == 4) attn_bwd_tc4_kernel<0><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
+        else if (drop.thresh16) attn_bwd_tc4_kernel<1><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
+        else attn_bwd_tc4_kernel<2><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
     } else if (attn_tc_version() >= 3) attn_bwd_tc3_kernel<<<grid, AT3_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     else attn_bwd_tc_kernel<<<grid, AT_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_bwd_tc");

@@ -112,6 +112,189 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mel_kernel(const float* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Register-resident mixed-radix form for the two transform sizes the reference uses (n_fft 2048 -> 1024 complex points = 16 x 16 x 4,
+// n_fft 1024 -> 512 = 16 x 16 x 2); default for those sizes, TTTS_STFT_V1=1 selects the radix-2 kernel above.
+// The radix-2 kernel makes 10 passes over shared memory with a barrier each and one butterfly per thread per pass: 41 M frames/s =
+// 126 GB/s, 2 % of the HBM roof (r1g bench).  Here a frame is transformed by N2/16 threads holding 16 complex points each in registers:
+//   pass 1: 16-point DFTs over n1 (stride N2/16), twiddle W_N2^(n2 k1)           -> smem [k1][n2]
+//   pass 2: 16-point DFTs over n2a,               twiddle W_M^(n2b k2a), M = N2/16 -> smem [n2b][k2a 16 + k1]
+//   pass 3: R3-point DFTs over n2b (R3 = N2/256)                                 -> smem, natural order k = k1 + 16 k2a + 256 k2b
+// i.e. three exchanges instead of ten, all shared-memory accesses conflict-free by the row pitches chosen below; the 15 twiddles of a
+// thread are built from 4 table entries (w, w^2, w^4, w^8).  After the transform: real-FFT unpack, magnitudes, spectrogram / sparse mel
+// as in the kernel above.  What bounds it: 1024-point FFT = 51 kFLOP of mostly non-fused adds per frame against 7.2 KB of HBM traffic
+// -> the fp32 pipe, not HBM.
+// ------------------------------------------------------------------------------------------------------------
+TTTS_DEVICE float2 cmulf(const float2 a, const float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+TTTS_DEVICE void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {       // forward: W4 = -i
+    const float2 s02 = make_float2(x0.x + x2.x, x0.y + x2.y), d02 = make_float2(x0.x - x2.x, x0.y - x2.y);
+    const float2 s13 = make_float2(x1.x + x3.x, x1.y + x3.y), d13 = make_float2(x1.x - x3.x, x1.y - x3.y);
+    x0 = make_float2(s02.x + s13.x, s02.y + s13.y);
+    x2 = make_float2(s02.x - s13.x, s02.y - s13.y);
+    x1 = make_float2(d02.x + d13.y, d02.y - d13.x);
+    x3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+}
+// in place, natural order in and out: A[k] = sum_n a[n] W16^(n k)
+TTTS_DEVICE void dft16(float2 (&a)[16]) {
+    constexpr float C = 0.92387953251128674f, S = 0.38268343236508977f, H = 0.70710678118654752f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4(a[b], a[4 + b], a[8 + b], a[12 + b]);        // t[b][c] in a[4 c + b]
+    // t[b][c] *= W16^(b c)
+    a[4 * 1 + 1] = cmulf(a[4 * 1 + 1], make_float2(C, -S));
+    a[4 * 2 + 1] = cmulf(a[4 * 2 + 1], make_float2(H, -H));
+    a[4 * 3 + 1] = cmulf(a[4 * 3 + 1], make_float2(S, -C));
+    a[4 * 1 + 2] = cmulf(a[4 * 1 + 2], make_float2(H, -H));
+    a[4 * 2 + 2] = make_float2(a[4 * 2 + 2].y, -a[4 * 2 + 2].x);
+    a[4 * 3 + 2] = cmulf(a[4 * 3 + 2], make_float2(-H, -H));
+    a[4 * 1 + 3] = cmulf(a[4 * 1 + 3], make_float2(S, -C));
+    a[4 * 2 + 3] = cmulf(a[4 * 2 + 3], make_float2(-H, -H));
+    a[4 * 3 + 3] = cmulf(a[4 * 3 + 3], make_float2(-C, S));
+    // A[c + 4 d] = DFT4 over b of t[b][c]; t[b][c] sits in a[4 c + b], the results go to a[4 c + d] -> one transposition at the end
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int d = c + 1; d < 4; ++d) { const float2 t = a[4 * c + d]; a[4 * c + d] = a[4 * d + c]; a[4 * d + c] = t; }
+}
+// a[k] *= w^k, k = 1 .. 15, from w, w^2, w^4, w^8
+TTTS_DEVICE void twiddle16(float2 (&a)[16], const float2 w1, const float2 w2, const float2 w4, const float2 w8) {
+    const float2 w3 = cmulf(w1, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
+    a[1] = cmulf(a[1], w1); a[2] = cmulf(a[2], w2); a[3] = cmulf(a[3], w3); a[4] = cmulf(a[4], w4);
+    a[5] = cmulf(a[5], w5); a[6] = cmulf(a[6], w6); a[7] = cmulf(a[7], w7); a[8] = cmulf(a[8], w8);
+    a[9] = cmulf(a[9], cmulf(w8, w1)); a[10] = cmulf(a[10], cmulf(w8, w2)); a[11] = cmulf(a[11], cmulf(w8, w3));
+    a[12] = cmulf(a[12], cmulf(w8, w4)); a[13] = cmulf(a[13], cmulf(w8, w5)); a[14] = cmulf(a[14], cmulf(w8, w6));
+    a[15] = cmulf(a[15], cmulf(w8, w7));
+}
+
+template <int LOG2N2>
+struct StftR16 {
+    static constexpr int N2 = 1 << LOG2N2, R3 = N2 / 256, M = N2 / 16, FPB = STFT_THREADS / M;
+    static constexpr int PA = M + R3;                 // pass-1 layout [k1][n2]: pass-2 thread (k1, n2b) reads bank (k1 PA + n2b) mod 32, all distinct
+    static constexpr int PB = 256 + 32 / R3;          // pass-2 layout [n2b][k2a 16 + k1]: writes of a warp hit banks (n2b PB + k1) mod 32, all distinct
+    static constexpr int BUF0 = 16 * PA > N2 ? 16 * PA : N2;          // floats per component
+    static constexpr int BUF1 = R3 * PB > N2 + 4 ? R3 * PB : N2 + 4;  // also holds the N2 + 1 magnitudes
+    static constexpr int FR = 2 * BUF0 + 2 * BUF1;    // floats per frame
+    static constexpr size_t kSmem = (size_t)FPB * FR * sizeof(float);
+};
+
+template <int LOG2N2>
+__global__ void __launch_bounds__(STFT_THREADS) stft_mel_r16_kernel(const float* __restrict__ wav, int L, int hop, int pad, const float* __restrict__ window,
+                                                                    const float2* __restrict__ tw, float eps_inside, int F, float* __restrict__ spec_out,
+                                                                    int n_mels, const int* __restrict__ band_lo, const int* __restrict__ band_off,
+                                                                    const float* __restrict__ band_w, float log_floor, float* __restrict__ mel_out) {
+    using C = StftR16<LOG2N2>;
+    constexpr int N2 = C::N2, R3 = C::R3, M = C::M, FPB = C::FPB, PA = C::PA, PB = C::PB;
+    constexpr int bins = N2 + 1;
+    extern __shared__ float st16_smem[];
+    const int tid = threadIdx.x;
+    const int fr = tid / M, t = tid - fr * M;
+    float* re0 = st16_smem + fr * C::FR;
+    float* im0 = re0 + C::BUF0;
+    float* re1 = im0 + C::BUF0;
+    float* im1 = re1 + C::BUF1;
+    const int b = blockIdx.y;
+    const int f0 = blockIdx.x * FPB;
+    const int f = f0 + fr;
+    const float* w = wav + (size_t)b * L;
+    float2 a[16];
+
+    // ---- pass 1: thread n2 = t takes z[n1 M + n2], n1 = 0 .. 15 (z[m] = windowed samples 2m, 2m + 1) ----
+    {
+        const int s0 = f * hop - pad;
+        const bool live = f < F;
+        const bool inside = live && s0 >= 0 && s0 + 2 * N2 <= L;
+        const bool vec = inside && ((((size_t)b * L + s0) & 1) == 0) && ((reinterpret_cast<uintptr_t>(wav) & 7) == 0);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int m = n1 * M + t;
+            float2 v = make_float2(0.f, 0.f);
+            if (vec) v = *reinterpret_cast<const float2*>(w + s0 + 2 * m);
+            else if (inside) { v.x = w[s0 + 2 * m]; v.y = w[s0 + 2 * m + 1]; }
+            else if (live) { v.x = w[reflect_index(s0 + 2 * m, L)]; v.y = w[reflect_index(s0 + 2 * m + 1, L)]; }
+            const float2 wn = __ldg(reinterpret_cast<const float2*>(window) + m);
+            a[n1] = make_float2(v.x * wn.x, v.y * wn.y);
+        }
+        dft16(a);
+        twiddle16(a, __ldg(tw + 2 * t), __ldg(tw + 4 * t), __ldg(tw + 8 * t), __ldg(tw + 16 * t));        // W_N2^(n2 k1) = tw[2 n2 k1]
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) { re0[k1 * PA + t] = a[k1].x; im0[k1 * PA + t] = a[k1].y; }
+    }
+    __syncthreads();
+    // ---- pass 2: thread (k1, n2b) = (t / R3, t % R3) takes y[k1][n2a R3 + n2b], n2a = 0 .. 15 ----
+    {
+        const int k1 = t / R3, n2b = t - k1 * R3;
+#pragma unroll
+        for (int n2a = 0; n2a < 16; ++n2a) a[n2a] = make_float2(re0[k1 * PA + n2a * R3 + n2b], im0[k1 * PA + n2a * R3 + n2b]);
+        dft16(a);
+        twiddle16(a, __ldg(tw + 32 * n2b), __ldg(tw + 64 * n2b), __ldg(tw + 128 * n2b), __ldg(tw + 256 * n2b));   // W_M^(n2b k2a) = tw[32 n2b k2a]
+#pragma unroll
+        for (int k2a = 0; k2a < 16; ++k2a) { re1[n2b * PB + k2a * 16 + k1] = a[k2a].x; im1[n2b * PB + k2a * 16 + k1] = a[k2a].y; }
+    }
+    __syncthreads();
+    // ---- pass 3: R3-point DFTs over n2b for j = k2a 16 + k1 = t + M i ; Z[j + 256 k2b] -> buffer 0, natural order ----
+#pragma unroll
+    for (int i = 0; i < 16 / R3; ++i) {
+        const int j = t + M * i;
+        if (R3 == 4) {
+            float2 x0 = make_float2(re1[j], im1[j]), x1 = make_float2(re1[PB + j], im1[PB + j]);
+            float2 x2 = make_float2(re1[2 * PB + j], im1[2 * PB + j]), x3 = make_float2(re1[3 * PB + j], im1[3 * PB + j]);
+            dft4(x0, x1, x2, x3);
+            a[4 * i] = x0; a[4 * i + 1] = x1; a[4 * i + 2] = x2; a[4 * i + 3] = x3;
+        } else {
+            const float2 x0 = make_float2(re1[j], im1[j]), x1 = make_float2(re1[PB + j], im1[PB + j]);
+            a[2 * i] = make_float2(x0.x + x1.x, x0.y + x1.y);
+            a[2 * i + 1] = make_float2(x0.x - x1.x, x0.y - x1.y);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16 / R3; ++i)
+#pragma unroll
+        for (int k2b = 0; k2b < R3; ++k2b) { re0[t + M * i + 256 * k2b] = a[R3 * i + k2b].x; im0[t + M * i + 256 * k2b] = a[R3 * i + k2b].y; }
+    __syncthreads();
+    // ---- unpack to the real-FFT bins, magnitudes -> re1[0 .. N2] ----
+    for (int k = t; k < bins; k += M) {
+        const int kz = k & (N2 - 1), kc = (N2 - k) & (N2 - 1);
+        const float zkx = re0[kz], zky = im0[kz], zcx = re0[kc], zcy = im0[kc];
+        const float er = 0.5f * (zkx + zcx), ei = 0.5f * (zky - zcy);
+        const float orr = 0.5f * (zkx - zcx), oi = 0.5f * (zky + zcy);
+        const float2 tk = __ldg(tw + k);
+        const float re = er + (tk.x * oi + tk.y * orr);
+        const float im = ei - (tk.x * orr - tk.y * oi);
+        re1[k] = sqrtf(re * re + im * im + eps_inside);
+    }
+    __syncthreads();
+    const float* mag0 = st16_smem + 2 * C::BUF0;       // frame fr2: mag0 + fr2 * FR
+    // ---- spectrogram out: [B, bins, F], FPB consecutive frames per bin ----
+    if (spec_out) {
+        float* so = spec_out + (size_t)b * bins * F;
+        const bool vec4 = ((F & 3) == 0) && (f0 + FPB <= F);
+        for (int k = tid; k < bins; k += STFT_THREADS) {
+            if (vec4) {
+#pragma unroll
+                for (int q = 0; q < FPB / 4; ++q)
+                    *reinterpret_cast<float4*>(so + (size_t)k * F + f0 + 4 * q) =
+                        make_float4(mag0[(4 * q) * C::FR + k], mag0[(4 * q + 1) * C::FR + k], mag0[(4 * q + 2) * C::FR + k], mag0[(4 * q + 3) * C::FR + k]);
+            } else {
+                for (int q = 0; q < FPB; ++q) if (f0 + q < F) so[(size_t)k * F + f0 + q] = mag0[q * C::FR + k];
+            }
+        }
+    }
+    // ---- sparse mel + log ----
+    if (mel_out) {
+        float* mo = mel_out + (size_t)b * n_mels * F;
+        for (int i = tid; i < FPB * n_mels; i += STFT_THREADS) {
+            const int m = i / FPB, q = i - m * FPB;          // frames fastest: neighbouring threads write neighbouring addresses
+            if (f0 + q >= F) continue;
+            const int lo = band_lo[m], o0 = band_off[m], o1 = band_off[m + 1];
+            const float* mg = mag0 + q * C::FR + lo;
+            float s = 0.f;
+            for (int o = o0; o < o1; ++o) s = fmaf(__ldg(band_w + o), mg[o - o0], s);
+            mo[(size_t)m * F + f0 + q] = logf(fmaxf(s, log_floor));
+        }
+    }
+}
+
 // spec_to_mel_torch on an existing spectrogram [B, bins, F]
 __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ spec, int bins, int F, int n_mels, const int* __restrict__ band_lo,
                                                      const int* __restrict__ band_off, const float* __restrict__ band_w, float log_floor,
@@ -150,6 +333,28 @@ int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t
     if (smem > attr_smem) {
         TTTS_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
+    }
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("TTTS_STFT_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (!v1 && (n_fft == 2048 || n_fft == 1024) && (reinterpret_cast<uintptr_t>(window) & 7) == 0) {
+        static bool attr16 = false;
+        if (!attr16) {
+            TTTS_CUDA(cudaFuncSetAttribute(stft_mel_r16_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftR16<10>::kSmem));
+            TTTS_CUDA(cudaFuncSetAttribute(stft_mel_r16_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftR16<9>::kSmem));
+            attr16 = true;
+        }
+        const float2* tw2 = reinterpret_cast<const float2*>(twiddle);
+        if (n_fft == 2048) {
+            dim3 grid16((F + StftR16<10>::FPB - 1) / StftR16<10>::FPB, B);
+            stft_mel_r16_kernel<10><<<grid16, STFT_THREADS, StftR16<10>::kSmem, st>>>(wav, L, hop, pad, window, tw2, eps_inside, F, spec_out, n_mels, band_lo,
+                                                                                        band_off, band_w, log_floor, mel_out);
+        } else {
+            dim3 grid16((F + StftR16<9>::FPB - 1) / StftR16<9>::FPB, B);
+            stft_mel_r16_kernel<9><<<grid16, STFT_THREADS, StftR16<9>::kSmem, st>>>(wav, L, hop, pad, window, tw2, eps_inside, F, spec_out, n_mels, band_lo,
+                                                                                      band_off, band_w, log_floor, mel_out);
+        }
+        TTTS_LAUNCH_CHECK("stft_mel_r16");
+        return TTTS_OK;
     }
     dim3 grid((F + STFT_FPB - 1) / STFT_FPB, B);
     stft_mel_kernel<<<grid, STFT_THREADS, smem, st>>>(wav, L, n_fft, log2_half, hop, pad, window, reinterpret_cast<const float2*>(twiddle), eps_inside, F,

@@ -169,6 +169,167 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
     }
 }
 
+// Pipelined form (default when D % 16 == 0 and E is 16-byte aligned; TTTS_VQ_V1=1 selects the kernel above).  The kernel above reads every
+// codebook chunk with a synchronous, transposing gather (8 scalar L2 loads per thread -> st.shared -> barrier -> 512 FMAs): the FMA pipe idles
+// for an L2 round trip per chunk unless another CTA covers it (measured 19.6 TFLOP/s = 27 % of the fp32 peak at N = 2^20, r1g bench).
+// Here the chunk [128 codes x 16 dims] is copied as it lies in E (64 contiguous bytes per code) with two 16-byte cp.async per thread into a
+// double buffer, one chunk ahead of the FMAs; the tile is stored code-major with a 20-float row pitch, thread tx owns codes tx, tx + 16, ...
+// so that its float4 reads along the dims are bank-conflict free.  Accumulation order over d is unchanged: distances and indices are
+// bit-identical to the kernel above.
+constexpr int VQ_EP = VQ_DC + 4;      // row pitch (floats) of the code-major chunk
+
+__global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
+                                                                    const float* __restrict__ ee, int K, int64_t* __restrict__ idx_out,
+                                                                    float* __restrict__ q_out, int straight_through,
+                                                                    float* __restrict__ commit_partial, float* __restrict__ hist,
+                                                                    float* __restrict__ embed_sum) {
+    extern __shared__ __align__(16) float vq_smem[];
+    float* Xs = vq_smem;                         // [D][VQ_TM]
+    float* Es = Xs + (size_t)D * VQ_TM;          // [2][VQ_TN][VQ_EP]
+    float* xx = Es + 2 * VQ_TN * VQ_EP;          // [VQ_TM]
+    int* sidx = reinterpret_cast<int*>(xx + VQ_TM);   // [VQ_TM]
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int v0 = blockIdx.x * VQ_TM;
+    const int nchunks = D / VQ_DC;
+    const int ntiles = (K + VQ_TN - 1) / VQ_TN;
+    const int total = ntiles * nchunks;
+
+    // chunk q = (code tile q / nchunks, dims (q % nchunks) * 16 ...): thread copies 16 bytes of codes c and c + 64
+    auto issue = [&](int q, int ct, int d0) {
+        float* es = Es + (q & 1) * VQ_TN * VQ_EP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = (tid >> 2) + h * 64, part = (tid & 3) * 4;
+            const bool ok = ct + c < K;
+            cp_async16(es + c * VQ_EP + part, ok ? E + (size_t)(ct + c) * D + d0 + part : E, ok);
+        }
+    };
+    issue(0, 0, 0);
+    cp_async_commit();
+
+    // ---- x tile -> smem (transposed to [d][v]) ----
+    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
+        int d, vl;
+        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
+        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
+        const int v = v0 + vl;
+        float val = 0.f;
+        if (v < N) {
+            const int b = v / lay.Nn, n = v - b * lay.Nn;
+            val = x[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)];
+        }
+        Xs[d * VQ_TM + vl] = val;
+    }
+    __syncthreads();
+    if (tid < VQ_TM) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) { float t = Xs[d * VQ_TM + tid]; s += t * t; }
+        xx[tid] = s;
+    }
+
+    float best[4]; int besti[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = -INFINITY; besti[i] = 0; }
+    float acc[4][8];
+    int ch = 0, ct = 0;                          // chunk q = dims ch * 16 ... of code tile ct (no division in the loop)
+    for (int q = 0; q < total; ++q) {
+        if (ch == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        }
+        cp_async_wait<0>();                      // chunk q has landed (this thread's part)
+        __syncthreads();                         // ... everybody's part; and all threads are done with chunk q - 1 (the buffer refilled next)
+        if (q + 1 < total) { const bool wrap = ch + 1 == nchunks; issue(q + 1, wrap ? ct + VQ_TN : ct, wrap ? 0 : (ch + 1) * VQ_DC); }
+        cp_async_commit();
+        const float* es = Es + (q & 1) * VQ_TN * VQ_EP;
+#pragma unroll
+        for (int d4 = 0; d4 < VQ_DC; d4 += 4) {
+            float4 ev[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ev[j] = *reinterpret_cast<const float4*>(es + (j * 16 + tx) * VQ_EP + d4);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                const float4 xv = *reinterpret_cast<const float4*>(Xs + (ch * VQ_DC + d4 + dd) * VQ_TM + ty * 4);
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float e = dd == 0 ? ev[j].x : dd == 1 ? ev[j].y : dd == 2 ? ev[j].z : ev[j].w;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(xa[i], e, acc[i][j]);
+                }
+            }
+        }
+        if (ch == nchunks - 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {        // ascending k within the thread: strict > keeps the lowest index among equals
+                const int k = ct + j * 16 + tx;
+                if (k < K) {
+                    const float e2 = __ldg(ee + k);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float dist = -((xx[ty * 4 + i] - 2.0f * acc[i][j]) + e2);
+                        if (dist > best[i]) { best[i] = dist; besti[i] = k; }
+                    }
+                }
+            }
+            ch = 0; ct += VQ_TN;
+        } else {
+            ++ch;
+        }
+    }
+    // reduce across the 16 lanes (tx) that share the same 4 vectors
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+            if (ob > best[i] || (ob == best[i] && oi < besti[i])) { best[i] = ob; besti[i] = oi; }
+        }
+        if (tx == 0) sidx[ty * 4 + i] = besti[i];
+    }
+    __syncthreads();
+
+    // ---- epilogue: indices, dequantised rows, commit-loss partial, EMA statistics (as in the kernel above) ----
+    if (tid < VQ_TM && v0 + tid < N) {
+        idx_out[v0 + tid] = (int64_t)sidx[tid];
+        if (hist) atomicAdd(hist + sidx[tid], 1.0f);
+    }
+    float csum = 0.f;
+    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
+        int d, vl;
+        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
+        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
+        const int v = v0 + vl;
+        if (v < N) {
+            const int k = sidx[vl];
+            const float q = __ldg(E + (size_t)k * D + d);
+            const float xv = Xs[d * VQ_TM + vl];
+            const float diff = q - xv;
+            csum += diff * diff;
+            if (q_out) {
+                const int b = v / lay.Nn, n = v - b * lay.Nn;
+                q_out[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)] = straight_through ? (xv + diff) : q;
+            }
+            if (embed_sum) atomicAdd(embed_sum + (size_t)k * D + d, xv);
+        }
+    }
+    if (commit_partial) {
+        __shared__ float red[VQ_THREADS / 32];
+        csum = warp_sum(csum);
+        if ((tid & 31) == 0) red[tid >> 5] = csum;
+        __syncthreads();
+        if (tid < 32) {
+            float s = tid < VQ_THREADS / 32 ? red[tid] : 0.f;
+            s = warp_sum(s);
+            if (tid == 0) commit_partial[blockIdx.x] = s;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) vq_commit_final_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
     __shared__ float sm[32];
     float s = 0.f;
@@ -260,15 +421,27 @@ int ttts_vq_forward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t la
     const int blocks = (N + VQ_TM - 1) / VQ_TM;
     vq_code_norms_kernel<<<(K + 7) / 8, 256, 0, st>>>(embed, K, D, ee);
     TTTS_LAUNCH_CHECK("vq_code_norms");
-    const size_t smem = ((size_t)D * VQ_TM + 2 * VQ_DC * VQ_TN + VQ_TM) * sizeof(float) + VQ_TM * sizeof(int);
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("TTTS_VQ_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    const bool pipe = !v1 && D % VQ_DC == 0 && (reinterpret_cast<uintptr_t>(embed) & 15) == 0;
+    const size_t smem = ((size_t)D * VQ_TM + (pipe ? 2 * VQ_TN * VQ_EP : 2 * VQ_DC * VQ_TN) + VQ_TM) * sizeof(float) + VQ_TM * sizeof(int);
     TTTS_CHECK_ARG(smem <= 200 * 1024, "vq: D too large for the shared-memory x tile");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        TTTS_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+    static size_t attr_smem = 0, attr_smem_pipe = 0;
+    if (pipe) {
+        if (smem > attr_smem_pipe) {
+            TTTS_CUDA(cudaFuncSetAttribute(vq_argmin_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem_pipe = smem;
+        }
+        vq_argmin_pipe_kernel<<<blocks, VQ_THREADS, smem, st>>>(x, lay, N, D, embed, ee, K, codes, quantized, straight_through,
+                                                                commit_out ? partial : nullptr, hist, embed_sum);
+    } else {
+        if (smem > attr_smem) {
+            TTTS_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        vq_argmin_kernel<<<blocks, VQ_THREADS, smem, st>>>(x, lay, N, D, embed, ee, K, codes, quantized, straight_through, commit_out ? partial : nullptr,
+                                                           hist, embed_sum);
     }
-    vq_argmin_kernel<<<blocks, VQ_THREADS, smem, st>>>(x, lay, N, D, embed, ee, K, codes, quantized, straight_through, commit_out ? partial : nullptr,
-                                                       hist, embed_sum);
     TTTS_LAUNCH_CHECK("vq_argmin");
     if (commit_out) {
         vq_commit_final_kernel<<<1, 1024, 0, st>>>(partial, blocks, 1.0f / ((float)N * (float)D), commit_out);
