@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
 // so that its float4 reads along the dims are bank-conflict free.  Accumulation order over d is unchanged: distances and indices are
 // bit-identical to the kernel above.
 constexpr int VQ_EP = VQ_DC + 4;      // row pitch (floats) of the code-major chunk
+// x tile [d][64 vectors] with the 16 four-vector groups of row d permuted by d mod 16: a warp that writes (or reads back) 32 consecutive
+// dims of one vector -- the coalesced order for row-major [N, D] input -- then touches 16 different bank groups instead of one (the r1n
+// profile had the shared-memory pipe at 76 % with a third of its wavefronts from these 32-way conflicts); the main loop's float4 reads
+// (one row, groups ty) only see a different group number.
+TTTS_DEVICE int vq_xs_index(int d, int vl) { return d * VQ_TM + ((((vl >> 2) ^ d) & 15) << 2) + (vl & 3); }
 
 __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
                                                                     const float* __restrict__ ee, int K, int64_t* __restrict__ idx_out,
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
                                                                     float* __restrict__ commit_partial, float* __restrict__ hist,
                                                                     float* __restrict__ embed_sum) {
     extern __shared__ __align__(16) float vq_smem[];
-    float* Xs = vq_smem;                         // [D][VQ_TM]
+    float* Xs = vq_smem;                         // [D][VQ_TM], 16-byte groups of a row XOR-swizzled by d (vq_xs_index)
     float* Es = Xs + (size_t)D * VQ_TM;          // [2][VQ_TN][VQ_EP]
     float* xx = Es + 2 * VQ_TN * VQ_EP;          // [VQ_TM]
     int* sidx = reinterpret_cast<int*>(xx + VQ_TM);   // [VQ_TM]
@@ -219,12 +224,12 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
             const int b = v / lay.Nn, n = v - b * lay.Nn;
             val = x[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)];
         }
-        Xs[d * VQ_TM + vl] = val;
+        Xs[vq_xs_index(d, vl)] = val;
     }
     __syncthreads();
     if (tid < VQ_TM) {
         float s = 0.f;
-        for (int d = 0; d < D; ++d) { float t = Xs[d * VQ_TM + tid]; s += t * t; }
+        for (int d = 0; d < D; ++d) { float t = Xs[vq_xs_index(d, tid)]; s += t * t; }
         xx[tid] = s;
     }
 
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
             for (int j = 0; j < 8; ++j) ev[j] = *reinterpret_cast<const float4*>(es + (j * 16 + tx) * VQ_EP + d4);
 #pragma unroll
             for (int dd = 0; dd < 4; ++dd) {
-                const float4 xv = *reinterpret_cast<const float4*>(Xs + (ch * VQ_DC + d4 + dd) * VQ_TM + ty * 4);
+                const float4 xv = *reinterpret_cast<const float4*>(Xs + (ch * VQ_DC + d4 + dd) * VQ_TM + ((ty ^ (d4 + dd)) << 2));
                 const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
         if (v < N) {
             const int k = sidx[vl];
             const float q = __ldg(E + (size_t)k * D + d);
-            const float xv = Xs[d * VQ_TM + vl];
+            const float xv = Xs[vq_xs_index(d, vl)];
             const float diff = q - xv;
             csum += diff * diff;
             if (q_out) {
