@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                                          int B, int T, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
     // 8 lanes per (token, head): one 16-byte load of O and of dO each (8 dims), 3 shuffle steps; 2 pairs per thread for loads in flight
     const size_t total = (size_t)B * T * H;
     const size_t pair0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 3;
@@ -532,7 +534,7 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
 
 int attn_delta(const bf16* o, const bf16* dout, float* delta, int B, int T, int H, cudaStream_t st) {
     const size_t half = ((size_t)B * T * H + 1) / 2;                       // each thread group of 8 lanes handles pairs p and p + half
-    attn_delta_kernel<<<(unsigned)((half * 8 + 255) / 256), 256, 0, st>>>(o, dout, delta, B, T, H);
+    TTTS_CUDA(launch_pdl(attn_delta_kernel, dim3((unsigned)((half * 8 + 255) / 256)), dim3(256), 0, st, o, dout, delta, B, T, H));
     TTTS_LAUNCH_CHECK("attn_delta");
     return TTTS_OK;
 }

@@ -1130,6 +1130,8 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t tS = tmem_base;              // [2] x 128 cols
     const uint32_t tO = tmem_base + 256;        // 64 cols
+    pdl_launch_dependents();                    // PDL (common.cuh): the prologue above overlapped the previous kernel's tail
+    pdl_wait();
 
     if (warp == 0) {
         // ---------------- TMA: Q per item (double-buffered), K/V ring across items ----------------
@@ -1470,6 +1472,8 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         uint32_t c = 0;
@@ -1588,6 +1592,43 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
         // lse / delta of this thread's query row are fetched ONE query block ahead (across item boundaries too): loaded right before use
         // they cost an L2 round trip per block pair (r1h profile: 4.5 % of all stall samples on the first use of lse)
+        // dK (x softmax scale), dV (x dropout scale) of item idx_: TMEM -> registers (then the accumulators are free) -> bf16 rows of dqkv
+        auto dkv_out = [&](int idx_) {
+            const int jb_ = item_jb(idx_), bh_ = item_bh(idx_), b_ = (int)fastdiv((uint32_t)bh_, fd_H), h_ = bh_ - b_ * H;
+            const int kj = jb_ * AT_BN + r;
+            bf16* dkp = dqkv + (size_t)(b_ * T + min(kj, T - 1)) * ld3 + d + h_ * 64 + qtr * 16;
+            bf16* dvp = dkp + d;
+            uint32_t a[16], v[16];
+            __syncwarp();
+            tmem_ld_32x16(tDK + lane_off + qtr * 16, a);
+            tmem_ld_32x16(tDV + lane_off + qtr * 16, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_empty);
+            if (kj < T) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    reinterpret_cast<uint4*>(dkp)[g] =
+                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * scale, __uint_as_float(a[8 * g + 1]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * scale, __uint_as_float(a[8 * g + 3]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * scale, __uint_as_float(a[8 * g + 5]) * scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * scale, __uint_as_float(a[8 * g + 7]) * scale));
+                    reinterpret_cast<uint4*>(dvp)[g] =
+                        make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * drop.scale, __uint_as_float(v[8 * g + 1]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 2]) * drop.scale, __uint_as_float(v[8 * g + 3]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 4]) * drop.scale, __uint_as_float(v[8 * g + 5]) * drop.scale),
+                                   pack_bf16(__uint_as_float(v[8 * g + 6]) * drop.scale, __uint_as_float(v[8 * g + 7]) * drop.scale));
+                }
+            }
+        };
+        // Version 5 defers an item's tail -- the dQ tile of its last query block and the dK / dV read-out, both of which need the item's
+        // last gradient MMAs to have completed -- to after the FIRST block of the next item has been handed to the MMA warp: the wait
+        // that was exposed once per item (r1h / r1n profiles: 6.6 % of all stall samples on that one try_wait) now overlaps a whole
+        // block of softmax-gradient math.  The MMA warp's dkv_empty wait before the next item's first gradient MMA is unchanged.
+        constexpr bool kDefer = kMode != 0;
+        float* prev_dst = nullptr;
+        int idx_prev = -1;
         float lse_nx = 0.f, dlt_nx = 0.f;
         auto fetch_row_stats = [&](int bh_, int i_) {
             const int qi_ = i_ * AT_BM + r;
@@ -1602,7 +1643,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const int kc0 = k0 + qtr * 32;
             const int idx_nx = item_at(n + 1);
             const int bh_nx = idx_nx >= 0 ? item_bh(idx_nx) : 0, jb_nx = idx_nx >= 0 ? item_jb(idx_nx) : 0;
-            float* prev_dst = nullptr;
+            if (!kDefer) prev_dst = nullptr;
             for (int it = 0; it < nit; ++it, ++c) {
                 const int i = jb + it;
                 const uint32_t ph = c & 1;
@@ -1713,37 +1754,16 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pds_full);
                 if (it > 0) dq_out(c - 1, prev_dst);
+                else if (kDefer && n > 0) { dq_out(c - 1, prev_dst); dkv_out(idx_prev); }      // the previous item's tail, under this block's MMAs
                 prev_dst = cur_dst;
             }
-            dq_out(c - 1, prev_dst);                                   // last query block of the item; all gradient MMAs are complete after this
-            // dK (x softmax scale), dV (x dropout scale) of this key block
-            const int kj = k0 + r;
-            bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64 + qtr * 16;
-            bf16* dvp = dkp + d;
-            uint32_t a[16], v[16];
-            __syncwarp();
-            tmem_ld_32x16(tDK + lane_off + qtr * 16, a);
-            tmem_ld_32x16(tDV + lane_off + qtr * 16, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dkv_empty);
-            if (kj < T) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    reinterpret_cast<uint4*>(dkp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * scale, __uint_as_float(a[8 * g + 1]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * scale, __uint_as_float(a[8 * g + 3]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * scale, __uint_as_float(a[8 * g + 5]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * scale, __uint_as_float(a[8 * g + 7]) * scale));
-                    reinterpret_cast<uint4*>(dvp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * drop.scale, __uint_as_float(v[8 * g + 1]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 2]) * drop.scale, __uint_as_float(v[8 * g + 3]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 4]) * drop.scale, __uint_as_float(v[8 * g + 5]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 6]) * drop.scale, __uint_as_float(v[8 * g + 7]) * drop.scale));
-                }
+            if (!kDefer) {
+                dq_out(c - 1, prev_dst);                               // last query block of the item; all gradient MMAs are complete after this
+                dkv_out(idx);
             }
+            idx_prev = idx;
         }
+        if (kDefer && c > 0) { dq_out(c - 1, prev_dst); dkv_out(idx_prev); }
     }
     tc_fence_before();
     __syncthreads();
@@ -1753,6 +1773,8 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
 // fp32 dQ accumulation buffer [B*T, d] -> bf16 dqkv[:, 0:d]
 __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, size_t rows, int d, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t n4 = rows * (size_t)d / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 4;
@@ -1800,9 +1822,9 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
         const int items = (int)grid.x * B * H;
         const int nblk = items < num_sms() ? items : num_sms();
         TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
-        if (attn_tc_version() == 4) attn_fwd_tc4_kernel<0><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
-        else if (drop.thresh16) attn_fwd_tc4_kernel<1><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
-        else attn_fwd_tc4_kernel<2><<<nblk, AT3_THREADS, Fwd4Smem::kBytes, st>>>(tm, o, lse, T, H, B * H, 0.125f, drop);
+        if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+        else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+        else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
     } else if (attn_tc_version() >= 3) attn_fwd_tc3_kernel<<<grid, AT3_THREADS, Fwd3Smem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     else attn_fwd_tc_kernel<<<grid, AT_THREADS, FwdSmem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
@@ -1842,16 +1864,16 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
         const int items = (int)grid.x * B * H;
         const int nblk = items < num_sms() ? items : num_sms();
         TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
-        if (attn_tc_version() == 4) attn_bwd_tc4_kernel<0><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
-        else if (drop.thresh16) attn_bwd_tc4_kernel<1><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
-        else attn_bwd_tc4_kernel<2><<<nblk, AT3_THREADS, Bwd4Smem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop);
+        if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+        else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+        else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
     } else if (attn_tc_version() >= 3) attn_bwd_tc3_kernel<<<grid, AT3_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     else attn_bwd_tc_kernel<<<grid, AT_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
     TTTS_LAUNCH_CHECK("attn_bwd_tc");
     const size_t n4 = (size_t)B * T * d / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>(dq_acc, dqkv, (size_t)B * T, d, 0.125f);     // dQ = scale * dS K
+    TTTS_CUDA(launch_pdl(attn_dq_convert_kernel, dim3(blocks), dim3(256), 0, st, dq_acc, dqkv, (size_t)B * T, d, 0.125f));     // dQ = scale * dS K
     TTTS_LAUNCH_CHECK("attn_dq_convert");
     return TTTS_OK;
 }

@@ -368,6 +368,13 @@ TTTS_DEVICE void cp_async4(void* smem_dst, const void* gsrc, bool pred) {      /
     uint32_t sz = pred ? 4u : 0u;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while
+// its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are visible, so
+// everything before it (barrier init, TMEM allocation, tensor-map prefetch -- nothing that touches global memory the predecessor writes
+// or reads) overlaps the predecessor's tail.  pdl_launch_dependents() lets the successor be scheduled as soon as every CTA of THIS grid
+// has executed it or exited.  Both are no-ops for kernels launched without the attribute.
+TTTS_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TTTS_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 TTTS_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 TTTS_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

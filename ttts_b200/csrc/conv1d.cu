@@ -377,6 +377,17 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvP
     const bool lrelu = p.pre_lrelu != 0;
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<S - 2>();                  // chunk c has landed (S - 2 younger groups may still be in flight)
+        if (lrelu) {
+            // leaky ReLU once per element, by the thread that copied it (its own cp.async data is visible to it after the wait): in the
+            // FMA loop it cost 12 instructions per 16 FMAs (r1n profile: FSETP + FMUL = 15 % of all instructions, FFMA 28 %)
+            float* bw = sB + (c % S) * B_ST;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                float* e = &bw[(rb0 + (NT / 64) * i) * LDB + cb];
+                const float v = *e;
+                *e = v > 0.f ? v : 0.1f * v;
+            }
+        }
         __syncthreads();                         // ... for every thread, and everybody is done computing on stage (c - 1) % S
         if (c + S - 1 < nchunks) issue(c + S - 1);
         cp_async_commit();
@@ -387,11 +398,7 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvP
             const float4 av = *reinterpret_cast<const float4*>(&a[r * LDA + ty * 4]);
             const float4 bv = *reinterpret_cast<const float4*>(&b[r * LDB + tx * 4]);
             const float a4[4] = {av.x, av.y, av.z, av.w};
-            float b4[4] = {bv.x, bv.y, bv.z, bv.w};
-            if (lrelu) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b4[j] = b4[j] > 0.f ? b4[j] : 0.1f * b4[j];
-            }
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll

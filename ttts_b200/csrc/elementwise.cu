@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ w2, const float* __restrict__ b2, void* __restrict__ y,
                                                      float* __restrict__ stats, int M, RowMap map) {
     constexpr int d = NCH * 128;
+    pdl_launch_dependents();                     // PDL (common.cuh)
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
     if (row >= M) return;
@@ -231,10 +233,10 @@ template <int NCH>
 static int ln_fwd_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, void* y, float* stats, int M,
                          bool dbl, bool out_bf16, RowMap map, cudaStream_t st) {
     dim3 grid((M + 7) / 8);
-    if (dbl && out_bf16) ln_fwd_kernel<NCH, true, true><<<grid, 256, 0, st>>>(x, w1, b1, w2, b2, y, stats, M, map);
-    else if (dbl) ln_fwd_kernel<NCH, true, false><<<grid, 256, 0, st>>>(x, w1, b1, w2, b2, y, stats, M, map);
-    else if (out_bf16) ln_fwd_kernel<NCH, false, true><<<grid, 256, 0, st>>>(x, w1, b1, w2, b2, y, stats, M, map);
-    else ln_fwd_kernel<NCH, false, false><<<grid, 256, 0, st>>>(x, w1, b1, w2, b2, y, stats, M, map);
+    if (dbl && out_bf16) TTTS_CUDA(launch_pdl(ln_fwd_kernel<NCH, true, true>, dim3(grid), dim3(256), 0, st, x, w1, b1, w2, b2, y, stats, M, map));
+    else if (dbl) TTTS_CUDA(launch_pdl(ln_fwd_kernel<NCH, true, false>, dim3(grid), dim3(256), 0, st, x, w1, b1, w2, b2, y, stats, M, map));
+    else if (out_bf16) TTTS_CUDA(launch_pdl(ln_fwd_kernel<NCH, false, true>, dim3(grid), dim3(256), 0, st, x, w1, b1, w2, b2, y, stats, M, map));
+    else TTTS_CUDA(launch_pdl(ln_fwd_kernel<NCH, false, false>, dim3(grid), dim3(256), 0, st, x, w1, b1, w2, b2, y, stats, M, map));
     TTTS_LAUNCH_CHECK("ln_fwd");
     return TTTS_OK;
 }
@@ -325,6 +327,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     for (int a = 0; a < NARR; ++a)
         for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(s_row[a] + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
+    pdl_launch_dependents();                     // PDL (common.cuh): the shared-memory clearing above overlapped the previous kernel's tail
+    pdl_wait();
     for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
         {
             float xv[NCH * 4], dy[NCH * 4];
@@ -426,11 +430,11 @@ static int ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const fl
     if (dbl) {
         static bool attr = false;
         if (!attr) { TTTS_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 8 * d * 4)); attr = true; }
-        ln_bwd_kernel<NCH, true><<<blocks, 256, smem, st>>>(dy, dy_is_f32, x, stats, w1, b1, w2, g_in, g_out, g16_out, dw1, db1, dw2, db2, dbias_next, M, drop, map);
+        TTTS_CUDA(launch_pdl(ln_bwd_kernel<NCH, true>, dim3(blocks), dim3(256), smem, st, dy, dy_is_f32, x, stats, w1, b1, w2, g_in, g_out, g16_out, dw1, db1, dw2, db2, dbias_next, M, drop, map));
     } else {
         static bool attr = false;
         if (!attr) { TTTS_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * d * 4)); attr = true; }
-        ln_bwd_kernel<NCH, false><<<blocks, 256, smem, st>>>(dy, dy_is_f32, x, stats, w1, b1, w2, g_in, g_out, g16_out, dw1, db1, dw2, db2, dbias_next, M, drop, map);
+        TTTS_CUDA(launch_pdl(ln_bwd_kernel<NCH, false>, dim3(blocks), dim3(256), smem, st, dy, dy_is_f32, x, stats, w1, b1, w2, g_in, g_out, g16_out, dw1, db1, dw2, db2, dbias_next, M, drop, map));
     }
     TTTS_LAUNCH_CHECK("ln_bwd");
     return TTTS_OK;
@@ -526,6 +530,8 @@ int ce_bwd(const bf16* logits, int ld, int V, const int32_t* tgt, int rows, cons
 // column sums of a bf16 matrix [M, ld] (N columns) -> out[N] += sum_rows   (bias gradients)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ a, int ld, int M, int N, float* __restrict__ out) {
+    pdl_launch_dependents();                     // PDL (common.cuh)
+    pdl_wait();
     // block = 32 column groups of 8 (one 16-byte load each) x 8 row lanes ; grid.x over column tiles of 256, grid.y over row chunks.
     // Four independent 16-byte loads per thread in flight (the first version moved 4 bytes per load with one load in flight).
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -571,7 +577,7 @@ int colsum_bf16(const bf16* a, int ld, int M, int N, float* out, cudaStream_t st
     int gy = (num_sms() * 8 + gx - 1) / gx;
     if (gy > (M + 63) / 64) gy = (M + 63) / 64;
     if (gy < 1) gy = 1;
-    colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(a, ld, M, N, out);
+    TTTS_CUDA(launch_pdl(colsum_bf16_kernel, dim3(gx, gy), dim3(256), 0, st, a, ld, M, N, out));
     TTTS_LAUNCH_CHECK("colsum_bf16");
     return TTTS_OK;
 }

@@ -105,6 +105,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // PDL: everything above ran while the previous kernel of the stream was finishing; from here on its outputs are read
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs): the whole warp runs the loop, one elected lane issues =================
@@ -314,10 +317,12 @@ static int launch_gemm2(const ttts_gemm_args& a, const GemmParams& p_in, int gri
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? (p.quad ? 4 : 2) : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     prof_gemm_begin(stream, 2.0 * (double)a.M * (double)a.N * (double)a.K);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, tmAuxOut, p);
     prof_gemm_end(stream);

@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
@@ -42,6 +43,12 @@ void prof_gemm_end(cudaStream_t st) {
     if (!g_prof) return;
     cudaEventRecord(g_prof_recs[g_prof_used].e1, st);
     ++g_prof_used;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
 }
 
 int num_sms() {

@@ -41,6 +41,20 @@ void prof_gemm_end(cudaStream_t st);
         ::ttts::count_launch();                                   \
     } while (0)
 
+// TTTS_PDL=0 disables programmatic dependent launch (common.cuh: pdl_wait) for A/B measurements
+bool pdl_enabled();
+// <<<grid, block, smem, st>>> with the PDL attribute; only for kernels that call pdl_wait() before their first global-memory access
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 2-D bf16/fp32 tiled tensor map; swizzle: 0 = none, 1 (true) = 128B, 2 = 64B.
 //   inner/outer: tensor extents in elements (inner = contiguous dim); ld_elems: row stride in elements
 //   box_inner/box_outer: box extents in elements

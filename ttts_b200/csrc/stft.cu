@@ -174,7 +174,9 @@ struct StftR16 {
     static constexpr int PB = 256 + 32 / R3;          // pass-2 layout [n2b][k2a 16 + k1]: writes of a warp hit banks (n2b PB + k1) mod 32, all distinct
     static constexpr int BUF0 = 16 * PA > N2 ? 16 * PA : N2;          // floats per component
     static constexpr int BUF1 = R3 * PB > N2 + 4 ? R3 * PB : N2 + 4;  // also holds the N2 + 1 magnitudes
-    static constexpr int FR = 2 * BUF0 + 2 * BUF1;    // floats per frame
+    static constexpr int BUF = BUF0 > BUF1 ? BUF0 : BUF1;
+    static constexpr int FR = 2 * BUF;                // floats per frame: ONE re / im buffer pair, every pass reads it into registers,
+                                                      // barrier, writes it back in the next layout (34 KB per CTA -> 4 CTAs per SM, register-bound)
     static constexpr size_t kSmem = (size_t)FPB * FR * sizeof(float);
 };
 
@@ -190,9 +192,9 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mel_r16_kernel(const float*
     const int tid = threadIdx.x;
     const int fr = tid / M, t = tid - fr * M;
     float* re0 = st16_smem + fr * C::FR;
-    float* im0 = re0 + C::BUF0;
-    float* re1 = im0 + C::BUF0;
-    float* im1 = re1 + C::BUF1;
+    float* im0 = re0 + C::BUF;
+    float* re1 = re0;                                 // same storage, next layout
+    float* im1 = im0;
     const int b = blockIdx.y;
     const int f0 = blockIdx.x * FPB;
     const int f = f0 + fr;
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mel_r16_kernel(const float*
         const int k1 = t / R3, n2b = t - k1 * R3;
 #pragma unroll
         for (int n2a = 0; n2a < 16; ++n2a) a[n2a] = make_float2(re0[k1 * PA + n2a * R3 + n2b], im0[k1 * PA + n2a * R3 + n2b]);
+        __syncthreads();                              // every thread has its 16 points: the buffer may be overwritten
         dft16(a);
         twiddle16(a, __ldg(tw + 32 * n2b), __ldg(tw + 64 * n2b), __ldg(tw + 128 * n2b), __ldg(tw + 256 * n2b));   // W_M^(n2b k2a) = tw[32 n2b k2a]
 #pragma unroll
@@ -257,24 +260,34 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mel_r16_kernel(const float*
             a[2 * i + 1] = make_float2(x0.x - x1.x, x0.y - x1.y);
         }
     }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16 / R3; ++i)
 #pragma unroll
         for (int k2b = 0; k2b < R3; ++k2b) { re0[t + M * i + 256 * k2b] = a[R3 * i + k2b].x; im0[t + M * i + 256 * k2b] = a[R3 * i + k2b].y; }
     __syncthreads();
-    // ---- unpack to the real-FFT bins, magnitudes -> re1[0 .. N2] ----
-    for (int k = t; k < bins; k += M) {
-        const int kz = k & (N2 - 1), kc = (N2 - k) & (N2 - 1);
-        const float zkx = re0[kz], zky = im0[kz], zcx = re0[kc], zcy = im0[kc];
-        const float er = 0.5f * (zkx + zcx), ei = 0.5f * (zky - zcy);
-        const float orr = 0.5f * (zkx - zcx), oi = 0.5f * (zky + zcy);
-        const float2 tk = __ldg(tw + k);
-        const float re = er + (tk.x * oi + tk.y * orr);
-        const float im = ei - (tk.x * orr - tk.y * oi);
-        re1[k] = sqrtf(re * re + im * im + eps_inside);
+    // ---- unpack to the real-FFT bins, magnitudes (bins t + M i in registers, then back into re[0 .. N2]) ----
+    float mg[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const int k = t + M * i;
+        mg[i] = 0.f;
+        if (k < bins) {
+            const int kz = k & (N2 - 1), kc = (N2 - k) & (N2 - 1);
+            const float zkx = re0[kz], zky = im0[kz], zcx = re0[kc], zcy = im0[kc];
+            const float er = 0.5f * (zkx + zcx), ei = 0.5f * (zky - zcy);
+            const float orr = 0.5f * (zkx - zcx), oi = 0.5f * (zky + zcy);
+            const float2 tk = __ldg(tw + k);
+            const float re = er + (tk.x * oi + tk.y * orr);
+            const float im = ei - (tk.x * orr - tk.y * oi);
+            mg[i] = sqrtf(re * re + im * im + eps_inside);
+        }
     }
     __syncthreads();
-    const float* mag0 = st16_smem + 2 * C::BUF0;       // frame fr2: mag0 + fr2 * FR
+#pragma unroll
+    for (int i = 0; i < 17; ++i) { const int k = t + M * i; if (k < bins) re1[k] = mg[i]; }
+    __syncthreads();
+    const float* mag0 = st16_smem;                     // frame fr2: mag0 + fr2 * FR
     // ---- spectrogram out: [B, bins, F], FPB consecutive frames per bin ----
     if (spec_out) {
         float* so = spec_out + (size_t)b * bins * F;
