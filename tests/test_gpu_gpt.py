@@ -209,3 +209,46 @@ def test_cfg3_full_size_properties():
         flat.copy_(base)
     fd = (lp - lmn) / (2 * eps)
     assert abs(fd - an) <= 0.1 * abs(an), (fd, an, lp, lmn)
+
+
+def test_inference_speech_greedy_matches_oracle():
+    """ttts/gpt/model.py:533-562 (kv_cache=False): every greedily chosen code is, under teacher forcing in the fp32 oracle, the arg-max of the
+    oracle's logits up to the stated bf16 logit tolerance; shapes / stop handling follow HF generate."""
+    cfg = O.default_config(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=60)
+    m, params = build(cfg)
+    m.post_init_gpt2_config(kv_cache=False)
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, 255, (2, 9), generator=g)
+    cond = torch.randint(0, 1024, (2, 6), generator=g)
+    gen = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12)
+    assert gen.dtype == torch.int64 and gen.shape[0] == 2 and 1 <= gen.shape[1] <= 12
+    for b in range(2):
+        full = torch.cat([cond[b], gen[b].cpu()])
+        n = full.shape[0]
+        _, _, logits = O.forward(params, cfg, text[b:b + 1], torch.tensor([9]), full[None].clone(), torch.tensor([(n + 1) * 1024]))
+        logits = torch.as_tensor(logits)[0]                              # [1026, n + 2]
+        done = False
+        for i in range(6, n):
+            if done:
+                assert full[i] == cfg["stop_mel_token"]                  # pad_token_id after eos
+                continue
+            col = logits[:, i]
+            assert col.max() - col[full[i]] <= 0.02 * col.abs().max() + 1e-3, (b, i)
+            done = bool(full[i] == cfg["stop_mel_token"])
+    # greedy is deterministic; num_return_sequences expands neighbours-together like HF
+    gen3 = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12, num_return_sequences=3)
+    assert gen3.shape[0] == 6 and torch.equal(gen3[0], gen3[2]) and torch.equal(gen3[3], gen3[5]) and torch.equal(gen3[0, :gen.shape[1]], gen[0])
+    # sampling: seeded, top_k = 1 degenerates to greedy, a large repetition penalty forbids immediate repeats of a positive-score token
+    kw = dict(do_sample=True, top_p=0.8, temperature=0.8, repetition_penalty=2.0, max_generate_length=12)
+    a = m.inference_speech(text.cuda(), cond.cuda(), generator=torch.Generator(device="cuda").manual_seed(3), **kw)
+    b_ = m.inference_speech(text.cuda(), cond.cuda(), generator=torch.Generator(device="cuda").manual_seed(3), **kw)
+    assert torch.equal(a, b_) and a.max() <= 1025 and a.min() >= 0
+    k1 = m.inference_speech(text.cuda(), cond.cuda(), do_sample=True, top_k=1, max_generate_length=12)
+    assert torch.equal(k1, gen)
+    # eos: a head that always prefers the stop code ends every sequence after one token
+    with torch.no_grad():
+        m.mel_head.bias[cfg["stop_mel_token"]] += 100.0
+    stop = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12)
+    assert stop.shape == (2, 1) and bool((stop == cfg["stop_mel_token"]).all())
+    with pytest.raises(NotImplementedError):
+        m.inference_speech(text.cuda(), cond.cuda(), num_beams=4)

@@ -135,6 +135,29 @@ def test_mel_features_24k_vs_reference_golden(mel):
     assert one.shape == (100, 94)
 
 
+def test_batched_mel_extractor_equals_per_clip(mel, tmp_path):
+    """`<wav>.mel.pth` files of the batched extractor (prepare/extract_mel.py) == the front end run one clip at a time, reference format."""
+    from ttts_b200.prepare.extract_mel import extract_mel
+    from ttts_b200.vqvae.mel import MelSpectrogramFeatures
+    g = torch.Generator().manual_seed(3)
+    clips = {"a.wav": torch.tensor(mel["wav"][0]).unsqueeze(0), "b.wav": torch.tensor(mel["wav"][1]), "c.wav": 0.1 * torch.randn(2, 31111, generator=g),
+             "d.wav": 0.1 * torch.randn(1, 24000, generator=g), "odd.wav": 0.1 * torch.randn(1, 5000, generator=g), "tiny.wav": torch.zeros(1, 400)}
+    paths = [str(tmp_path / k) for k in clips]
+    done = extract_mel(paths, load_fn=lambda p: clips[os.path.basename(p)], batch_size=4)
+    assert set(done) == set(paths[:5]) and not os.path.exists(paths[5] + ".mel.pth")
+    fe = MelSpectrogramFeatures()
+    for p in paths[:5]:
+        w = clips[os.path.basename(p)]
+        w = w.mean(0) if w.dim() == 2 and w.shape[0] > 1 else w.reshape(-1)
+        got = torch.load(p + ".mel.pth")
+        assert got.shape == (1, 100, 1 + w.shape[0] // 256) and got.dtype == torch.float32 and got.device.type == "cpu"
+        assert torch.equal(got[0], fe(w.cuda()).cpu())
+    ref = torch.tensor(mel["feats24"][0])
+    got = torch.load(paths[0] + ".mel.pth")[0]
+    ok = ref > -4.0
+    assert (got - ref)[ok].abs().max() < 2e-4
+
+
 def test_stft_linearity_and_batch_independence():
     from ttts_b200.vqvae.mel import spectrogram_torch
     g = torch.Generator(device="cuda").manual_seed(0)

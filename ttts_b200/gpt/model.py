@@ -271,5 +271,80 @@ class UnifiedVoice(nn.Module):
         loss_text, loss_mel, mel_logits = _GPTStepFn.apply(self, text_inputs, mel_codes, wav_lengths, TL, CL, drop_p, seed, need_grad, *params)
         return loss_text, loss_mel, mel_logits.permute(0, 2, 1)
 
-    def inference_speech(self, *a, **k):
-        raise NotImplementedError("autoregressive sampling (ttts/gpt/model.py:533-562) is out of scope of the training hot path")
+    def post_init_gpt2_config(self, use_deepspeed=False, kv_cache=False, half=False):
+        """ttts/gpt/model.py:357-394 builds a HF GPT2InferenceModel around the trained modules; here generation runs on the same engine
+        as training, so there is nothing to build.  `kv_cache=True` is refused: the reference's cached path feeds a position index that
+        is off by one against its own uncached path (model.py:144-147 vs :134-142) and ttts/api_zh.py:51 uses kv_cache=False."""
+        if use_deepspeed or half:
+            raise NotImplementedError("deepspeed / fp16 inference wrappers are not part of this path (the engine computes in bf16 already)")
+        if kv_cache:
+            raise NotImplementedError("kv_cache=True (position index differs from the uncached reference path); use kv_cache=False")
+        self.eval()
+
+    @torch.no_grad()
+    def inference_speech(self, text_inputs, mel_codes, input_tokens=None, num_return_sequences=1, max_generate_length=None,
+                         typical_sampling=False, typical_mass=.9, generator=None, **hf_generate_kwargs):
+        """Autoregressive code generation, ttts/gpt/model.py:533-562 with kv_cache=False (the configuration ttts/api_zh.py:51 uses).
+
+        Prompt = [start, text..., stop] followed by [start_mel, conditioning codes...]; every step runs the SAME forward as training
+        (`ttts_gpt_forward`, no activations saved) over the sequence so far and reads the mel logits at the last token -- exactly what the
+        reference's uncached `GPT2InferenceModel.forward` recomputes per step (model.py:132-142, 159-171).  Token selection follows HF
+        `generate` (ttts_b200/gpt/sampling.py).  Returns the generated ids [B * num_return_sequences, n] after the prompt, padded with
+        stop_mel_token once a sequence has emitted it (pad_token_id = eos_token_id = stop_mel_token, model.py:555-556)."""
+        from . import sampling as S
+        kw = dict(hf_generate_kwargs)
+        do_sample = bool(kw.pop("do_sample", False))
+        top_p, top_k = kw.pop("top_p", None), kw.pop("top_k", None)
+        temperature = kw.pop("temperature", 1.0)
+        repetition_penalty = kw.pop("repetition_penalty", 1.0)
+        kw.pop("length_penalty", None)                               # beam search only
+        if kw.pop("num_beams", 1) != 1:
+            raise NotImplementedError("beam search is not used by the reference's call (ttts/api_zh.py:78-86) and is not implemented")
+        if kw:
+            raise TypeError("unsupported generate() arguments: %s" % sorted(kw))
+        L.require_cuda(text_inputs, mel_codes)
+        dev = text_inputs.device
+        text = text_inputs.long()
+        cond = mel_codes.long()
+        if input_tokens is not None:
+            # model.py:546-550 repeats the prompt itself AND passes num_return_sequences on to generate(), which expands once more
+            assert num_return_sequences % input_tokens.shape[0] == 0, "The number of return sequences must be divisible by the number of input sequences"
+            text = text.repeat(num_return_sequences, 1)
+            cond = cond.repeat(num_return_sequences, 1)
+            cond = torch.cat([cond, input_tokens.long().repeat(num_return_sequences // input_tokens.shape[0], 1)], dim=1)
+        if num_return_sequences > 1:
+            text = text.repeat_interleave(num_return_sequences, 0)   # HF expands each prompt num_return_sequences times, neighbours together
+            cond = cond.repeat_interleave(num_return_sequences, 0)
+        B, TL, m = text.shape[0], text.shape[1], cond.shape[1]
+        trunc_index = (TL + 2) + (mel_codes.shape[1] + 1)            # fake text ids + [start_mel, conditioning codes]
+        max_length = trunc_index + (self.max_mel_tokens - 1 if max_generate_length is None else max_generate_length)
+        n_max = max_length - (TL + 2) - 1                            # codes after start_mel the sequence may hold
+        n_max = min(n_max, self.max_mel_tokens + 1)                  # the position table ends there (the reference would raise an index error)
+        if TL + 2 > self.max_text_tokens + 2 or m > self.max_mel_tokens:
+            raise IndexError("prompt longer than the position tables (max_text_tokens=%d, max_mel_tokens=%d)" % (self.max_text_tokens, self.max_mel_tokens))
+        codes = torch.full((B, max(n_max, m) + 1), self.stop_mel_token, dtype=torch.int64, device=dev)
+        codes[:, :m] = cond
+        # what HF's processors see as input_ids: `1` for every text position (model.py:541), then start_mel + codes so far
+        ids = torch.cat([torch.ones(B, TL + 2, dtype=torch.int64, device=dev),
+                         torch.full((B, 1), self.start_mel_token, dtype=torch.int64, device=dev), codes], dim=1)
+        text = text.contiguous()
+        eng = self._engine()
+        eng.refresh_shadow(force=not eng.trust_version)
+        ld = L.lib().ttts_gpt_logits_ld(self.number_mel_codes)
+        unfinished = torch.ones(B, dtype=torch.bool, device=dev)
+        n = m
+        while n < n_max:
+            wav = torch.full((B,), (n + 1) * self.mel_length_compression, dtype=torch.int64, device=dev)      # nothing is stop-padded
+            eng.forward(text, codes, wav, TL, n, save=False)
+            logits = eng.ws_view(E.WS_MEL_LOGITS, B, TL, n, False, torch.bfloat16, (B, n + 2, ld))
+            scores = logits[:, n, :self.number_mel_codes].float()    # position of the last real token (mel_in[n])
+            scores = S.process_logits(scores, ids[:, :TL + 3 + n], do_sample, temperature, top_k, top_p, repetition_penalty, typical_sampling, typical_mass)
+            nxt = S.select_tokens(scores, do_sample, generator)
+            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, self.stop_mel_token))
+            codes[:, n] = nxt
+            ids[:, TL + 3 + n] = nxt
+            unfinished = unfinished & (nxt != self.stop_mel_token)
+            n += 1
+            if not bool(unfinished.any()):                           # the same host sync HF's stopping criteria make every step
+                break
+        return codes[:, mel_codes.shape[1]:n].clone()                # gen[:, trunc_index:] (input_tokens, if any, included -- as in the reference)
