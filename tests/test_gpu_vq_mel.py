@@ -78,6 +78,29 @@ def test_vq_large_random_vs_oracle_with_tie_margin():
     assert np.array_equal(q.cpu().numpy(), E[got])
 
 
+@pytest.mark.parametrize("K,D,N,bdn", [(1000, 64, 777, False), (130, 16, 65, False), (1024, 192, 18 * 7, True), (300, 24, 100, False)])
+def test_vq_ragged_shapes_vs_oracle(K, D, N, bdn):
+    """codebook sizes that are not a multiple of the 128-code tile, short x tiles, both input layouts; D = 24 takes the non-pipelined kernel"""
+    from ttts_b200.vqvae.quantize import vq_lookup
+    rs = np.random.RandomState(K + D)
+    E = rs.standard_normal((K, D)).astype(np.float32)
+    if bdn:
+        xb = rs.standard_normal((7, D, N // 7)).astype(np.float32)
+        x = np.ascontiguousarray(xb.transpose(0, 2, 1)).reshape(-1, D)
+        codes, q, _ = vq_lookup(torch.tensor(xb).cuda(), torch.tensor(E).cuda(), True)
+        qn = np.ascontiguousarray(q.cpu().numpy().transpose(0, 2, 1)).reshape(-1, D)
+    else:
+        x = rs.standard_normal((N, D)).astype(np.float32)
+        codes, q, _ = vq_lookup(torch.tensor(x).cuda(), torch.tensor(E).cuda(), False)
+        qn = q.cpu().numpy()
+    got = codes.cpu().numpy()
+    want = V.vq_quantize(x, E)
+    flips = got != want
+    assert got.min() >= 0 and got.max() < K
+    assert not np.any(flips & (V.vq_margin(x, E, want) > 1e-6)) and flips.sum() <= 1
+    assert np.array_equal(qn, E[got])
+
+
 def test_vq_full_size_properties():
     """N = 2^20 vectors (dataset-extraction regime): codebook rows map to themselves; encode(decode(c)) == c."""
     from ttts_b200.vqvae.quantize import vq_lookup
@@ -156,6 +179,21 @@ def test_batched_mel_extractor_equals_per_clip(mel, tmp_path):
     got = torch.load(paths[0] + ".mel.pth")[0]
     ok = ref > -4.0
     assert (got - ref)[ok].abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("L,B", [(23041, 3), (4099, 2), (2048 + 5 * 640 + 7, 1)])
+def test_spectrogram_odd_lengths_vs_oracle(L, B):
+    """odd clip lengths: clips 1, 2, ... start at odd sample offsets (the kernel's scalar-load path), frame counts not a multiple of 4
+    (the scalar spectrogram write-out), every frame of a short clip touches the reflect padding"""
+    from ttts_b200.vqvae.mel import spectrogram_torch, mel_spectrogram_torch
+    rs = np.random.RandomState(L)
+    wav = np.clip(0.1 * rs.standard_normal((B, L)), -1, 1).astype(np.float32)
+    s = spectrogram_torch(torch.tensor(wav).cuda(), 2048, 640, 2048).cpu().numpy()
+    ref = V.spectrogram(wav)
+    assert s.shape == ref.shape == (B, 1025, 1 + (L + 1408 - 2048) // 640)
+    assert np.abs(s - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+    m = mel_spectrogram_torch(torch.tensor(wav).cuda(), 2048, 128, 32000, 640, 2048, 0, None).cpu().numpy()
+    assert np.abs(m - V.mel_spectrogram(wav)).max() < 1e-3
 
 
 def test_stft_linearity_and_batch_independence():
