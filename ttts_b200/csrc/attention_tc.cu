@@ -16,9 +16,10 @@
 //             dK += dS^T Q      A=dS (MN-maj) B=Q  (MN-maj) 128x64x128
 //             dQ  = dS K        A=dS (K-maj)  B=K  (MN-maj) 128x64x128 -> TMEM -> red.global.add.f32 into an fp32 dQ buffer
 //
-// Warp roles (320 threads): warp 0 = TMA loader, warp 1 = MMA issuer + TMEM alloc, warps 2-9 = softmax / gradient math: two warps
-// per TMEM lane quadrant, each owning half of the tile's columns (64 keys, 32 of the 64 output dims), so every SM sub-partition has
-// two math warps to hide latency (the first version with one warp per sub-partition issued 0.19 instr/cycle, profiles/r1_notes.md).
+// Warp roles (576 threads): warp 0 = TMA loader, warp 1 = MMA issuer + TMEM alloc, warps 2-17 = softmax / gradient math: four warps
+// per TMEM lane quadrant, each owning a quarter of the tile's columns (32 keys, 16 of the 64 output dims).  Earlier versions (one,
+// then two math warps per sub-partition, one CTA per (block, head) item) are described in profiles/r1_notes.md; what is kept here is
+// the persistent kernel pair in two flavours: kMode 0 = "version 4" as profiled in r1h, kMode 1 / 2 = "version 5" (default).
 #include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
@@ -29,7 +30,6 @@ namespace ttts {
 constexpr int AT_BM = 128;            // queries per tile
 constexpr int AT_BN = 128;            // keys per tile
 constexpr int AT_TILE = 128 * 128;    // bytes of a [128 x 64] bf16 tile
-constexpr int AT_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9: two warps per TMEM lane quadrant (each takes half of the columns)
 constexpr float kLog2eF = 1.4426950408889634f;
 
 TTTS_DEVICE void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -46,1006 +46,7 @@ TTTS_DEVICE void st_tile_chunk(uint32_t base, int r, int c16, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------------------
-struct FwdSmem {
-    static constexpr int kKvStages = 3;
-    static constexpr int oQ = 0;
-    static constexpr int oKV = AT_TILE;                                 // [stages][K | V]
-    static constexpr int oP = oKV + kKvStages * 2 * AT_TILE;            // [2][2 atoms]
-    static constexpr int oBar = oP + 2 * 2 * AT_TILE;
-    static constexpr int oXch = oBar + 256;                             // row-max / row-sum exchange between the two column halves: [2][2][128] floats
-    static constexpr int kBytes = oXch + 3 * 2 * 128 * 4 + 1024;       // 2 max buffers + 1 sum buffer
-};
-
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, float scale,
-                   DropCfg drop) {
-    using S = FwdSmem;
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
-    uint64_t* q_full = bars;                       // 1
-    uint64_t* kv_full = bars + 1;                  // [3]
-    uint64_t* kv_empty = bars + 4;                 // [3]
-    uint64_t* s_full = bars + 7;                   // [2]
-    uint64_t* s_empty = bars + 9;                  // [2]
-    uint64_t* p_full = bars + 11;                  // [2]
-    uint64_t* p_empty = bars + 13;                 // [2]
-    uint64_t* o_full = bars + 15;                  // [2]
-    uint64_t* o_empty = bars + 17;                 // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 19);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = gridDim.x - 1 - blockIdx.x;            // heavy (late) query blocks first
-    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int d = H * 64;
-    const int q0 = qb * AT_BM;
-    const int nkv = min(qb + 1, (T + AT_BN - 1) / AT_BN);
-    const int row_base = b * T;                            // row of token 0 of this sequence in the [B*T, .] matrices
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < S::kKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 256);
-            mbar_init(&p_full[s], 256); mbar_init(&p_empty[s], 1);
-            mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 256);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tS = tmem_base;              // [2] x 128 cols
-    const uint32_t tO = tmem_base + 256;        // [2] x 64 cols
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA loader ----------------
-            mbar_arrive_expect_tx(q_full, AT_TILE);
-            tma_load_2d(smem + S::oQ, &tmQKV, q_full, h * 64, row_base + q0);
-            int st = 0; uint32_t ph = 0;
-            for (int j = 0; j < nkv; ++j) {
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                uint8_t* sk = smem + S::oKV + st * 2 * AT_TILE;
-                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
-                tma_load_2d(sk, &tmQKV, &kv_full[st], d + h * 64, row_base + j * AT_BN);
-                tma_load_2d(sk + AT_TILE, &tmQKV, &kv_full[st], 2 * d + h * 64, row_base + j * AT_BN);
-                if (++st == S::kKvStages) { st = 0; ph ^= 1; }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-            const uint32_t sQ = smem_u32(smem + S::oQ);
-            auto issue_s = [&](int j, int st) {
-                const uint32_t sK = smem_u32(smem + S::oKV + st * 2 * AT_TILE);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS + (j & 1) * 128, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(&s_full[j & 1]);
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);                                    // s_empty[0] is trivially free for j = 0
-            int st = 0; uint32_t ph = 0;                      // stage / phase of block j
-            for (int j = 0; j < nkv; ++j) {
-                int st1 = st + 1; uint32_t ph1 = ph;
-                if (st1 == S::kKvStages) { st1 = 0; ph1 ^= 1; }
-                if (j + 1 < nkv) {
-                    mbar_wait(&kv_full[st1], ph1);
-                    mbar_wait(&s_empty[(j + 1) & 1], (((j + 1) >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    issue_s(j + 1, st1);
-                }
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-                mbar_wait(&o_empty[j & 1], ((j >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t sP = smem_u32(smem + S::oP + (j & 1) * 2 * AT_TILE);
-                const uint32_t sV = smem_u32(smem + S::oKV + st * 2 * AT_TILE + AT_TILE);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tO + (j & 1) * 64, desc_kmajor(sP, k), desc_mnmajor(sV, k), idesc_o, k > 0 ? 1u : 0u);
-                umma_commit(&o_full[j & 1]);
-                umma_commit(&p_empty[j & 1]);
-                umma_commit(&kv_empty[st]);
-                st = st1; ph = ph1;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ---------------- softmax warps: thread = (query row = TMEM lane, column half) ----------------
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;                    // 0: keys 0-63 / out dims 0-31 ; 1: keys 64-127 / out dims 32-63
-        const int r = quad * 32 + lane;
-        const int qi = q0 + r;                               // query index within the sequence
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const float sl2 = scale * kLog2eF;
-        float* xch = reinterpret_cast<float*>(smem + S::oXch);               // [buf][half][row]
-        float m_run = -INFINITY, l_run = 0.f;                // l_run: partial row sum over THIS thread's keys
-        const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
-        const uint32_t t32 = drop.thresh16 << 16;
-        float o[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-
-        for (int j = 0; j < nkv; ++j) {
-            const int k0 = j * AT_BN;
-            const bool need_mask = (j == qb) || (k0 + AT_BN > T);
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t ts = tS + (j & 1) * 128 + lane_off + half * 64;
-            const int kc0 = k0 + half * 64;
-            // pass 1: row max over this thread's 64 keys
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(ts + c * 32, v);
-                tmem_ld_wait();
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int kj = kc0 + c * 32 + i;
-                        if (kj <= qi && kj < T) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
-            }
-            xch[((j & 1) * 2 + half) * 128 + r] = mx;
-            named_bar_sync(2, 256);
-            mx = fmaxf(fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]), m_run);
-            const float msc = (mx == -INFINITY) ? 0.f : mx * sl2;
-            const float corr = ex2_fast(m_run * sl2 - msc);       // 0 when m_run = -inf
-            // pass 2: probabilities -> bf16 P tile in smem
-            mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
-            const uint32_t sP = smem_u32(smem + S::oP + (j & 1) * 2 * AT_TILE);
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(ts + c * 32, v);
-                tmem_ld_wait();
-                float pv[32];
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int kj = kc0 + c * 32 + i;
-                        pv[i] = (kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
-                        rs += pv[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc)); rs += pv[i]; }
-                }
-                if (drop.thresh16) {
-                    // keep decisions of 4 consecutive keys per multiply-fold hash (common.cuh); the 1/(1-p) scale is applied once, to O
-                    const uint32_t g0 = (uint32_t)(kc0 + c * 32) >> 2;
-#pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        uint32_t w0, w1;
-                        attn_drop_words(rk, g0 + i4, w0, w1);
-                        pv[i4 * 4 + 0] = (w0 >= t32) ? pv[i4 * 4 + 0] : 0.f;
-                        pv[i4 * 4 + 1] = ((w0 << 16) >= t32) ? pv[i4 * 4 + 1] : 0.f;
-                        pv[i4 * 4 + 2] = (w1 >= t32) ? pv[i4 * 4 + 2] : 0.f;
-                        pv[i4 * 4 + 3] = ((w1 << 16) >= t32) ? pv[i4 * 4 + 3] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    st_tile_chunk(sP, r, (half * 2 + c) * 4 + g,
-                                  make_uint4(pack_bf16(pv[8 * g], pv[8 * g + 1]), pack_bf16(pv[8 * g + 2], pv[8 * g + 3]),
-                                             pack_bf16(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16(pv[8 * g + 6], pv[8 * g + 7])));
-            }
-            tc_fence_before();
-            mbar_arrive(&s_empty[j & 1]);
-            fence_proxy_async();
-            mbar_arrive(&p_full[j & 1]);
-            l_run = l_run * corr + rs;
-            m_run = mx;
-            if (j >= 1) {        // fold in P_{j-1} V_{j-1}, which the tensor core finished while we did the softmax of block j
-                mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-                tc_fence_after();
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(tO + ((j - 1) & 1) * 64 + lane_off + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
-                tc_fence_before();
-                mbar_arrive(&o_empty[(j - 1) & 1]);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] *= corr;
-        }
-        {
-            const int jl = nkv - 1;
-            mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
-            tc_fence_after();
-            uint32_t v[32];
-            __syncwarp();
-            tmem_ld_32x32(tO + (jl & 1) * 64 + lane_off + half * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
-            tc_fence_before();
-            mbar_arrive(&o_empty[jl & 1]);
-        }
-        // total row sum = the two halves' partial sums
-        xch[(4 + half) * 128 + r] = l_run;
-        named_bar_sync(2, 256);
-        const float l_tot = l_run + xch[(4 + (half ^ 1)) * 128 + r];
-        if (qi < T) {
-            const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;      // dropout's 1/(1-p) folded in here (scale = 1 when off)
-            if (half == 0) lse_out[(size_t)bh * T + qi] = m_run * scale + logf(l_tot);
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + half * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                dst[g] = make_uint4(pack_bf16(o[8 * g] * inv, o[8 * g + 1] * inv), pack_bf16(o[8 * g + 2] * inv, o[8 * g + 3] * inv),
-                                    pack_bf16(o[8 * g + 4] * inv, o[8 * g + 5] * inv), pack_bf16(o[8 * g + 6] * inv, o[8 * g + 7] * inv));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// forward, version 3: 16 softmax warps (4 per SM sub-partition, each thread = one query row x 32 of the tile's 128 keys), S read
-// from TMEM exactly once (into registers), O accumulated IN TMEM by the tensor core across key blocks and rescaled lazily: the
-// running max used for the exponentials only moves when the true max grew by more than 2^8 (then a warp multiplies its 16 O columns
-// in TMEM by the correction factor) -- exact, because the softmax normaliser is accumulated in the same stale scale.
-// Why: ncu of version 2 (profiles/r1_notes.md) showed 2 warps per sub-partition issuing 0.48 instr/cycle with S read twice and the
-// O tile read back every block.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int AT3_THREADS = 576;
-struct Fwd3Smem {
-    static constexpr int kKvStages = 3;
-    static constexpr int oQ = 0;
-    static constexpr int oKV = AT_TILE;                                 // [stages][K | V]
-    static constexpr int oP = oKV + kKvStages * 2 * AT_TILE;            // [2][2 atoms]
-    static constexpr int oBar = oP + 2 * 2 * AT_TILE;
-    static constexpr int oXch = oBar + 256;                             // row max [2][4][128] + row sum [4][128] floats
-    static constexpr int kBytes = oXch + (2 * 4 * 128 + 4 * 128) * 4 + 1024;
-};
-
-__global__ void __maxnreg__(96)      // 18 warps: two sub-partitions host 5 warps -> 16384 / (5*32) = 102 registers at most
-attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, float scale,
-                    DropCfg drop) {
-    using S = Fwd3Smem;
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
-    uint64_t* q_full = bars;                       // 1
-    uint64_t* kv_full = bars + 1;                  // [3]
-    uint64_t* kv_empty = bars + 4;                 // [3]
-    uint64_t* s_full = bars + 7;                   // [2]
-    uint64_t* s_empty = bars + 9;                  // [2]  16 (one arrival per softmax warp)
-    uint64_t* p_full = bars + 11;                  // [2]  16
-    uint64_t* p_empty = bars + 13;                 // [2]
-    uint64_t* o_full = bars + 15;                  // 1: completes once per key block (P_j V_j accumulated)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = gridDim.x - 1 - blockIdx.x;            // heavy (late) query blocks first
-    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int d = H * 64;
-    const int q0 = qb * AT_BM;
-    const int nkv = min(qb + 1, (T + AT_BN - 1) / AT_BN);
-    const int row_base = b * T;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < S::kKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 16);
-            mbar_init(&p_full[s], 16); mbar_init(&p_empty[s], 1);
-        }
-        mbar_init(o_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tS = tmem_base;              // [2] x 128 cols
-    const uint32_t tO = tmem_base + 256;        // 64 cols, accumulated over all key blocks
-
-    // Role warps run their loops with all 32 lanes (uniform control flow); only the TMA / tcgen05 instructions themselves are issued
-    // by one elected lane, so their operands stay on the uniform datapath (common.cuh elect_one).
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, AT_TILE);
-            tma_load_2d(smem + S::oQ, &tmQKV, q_full, h * 64, row_base + q0);
-        }
-        __syncwarp();
-        int st = 0; uint32_t ph = 0;
-        for (int j = 0; j < nkv; ++j) {
-            mbar_wait(&kv_empty[st], ph ^ 1);
-            uint8_t* sk = smem + S::oKV + st * 2 * AT_TILE;
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
-                tma_load_2d(sk, &tmQKV, &kv_full[st], d + h * 64, row_base + j * AT_BN);
-                tma_load_2d(sk + AT_TILE, &tmQKV, &kv_full[st], 2 * d + h * 64, row_base + j * AT_BN);
-            }
-            __syncwarp();
-            if (++st == S::kKvStages) { st = 0; ph ^= 1; }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
-        constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-        const uint32_t smem_base = smem_u32(smem);
-        const uint64_t dQ = desc_kmajor(smem_base + S::oQ, 0);
-        auto issue_s = [&](int j, int st) {
-            const uint64_t dK = desc_kmajor(smem_base + S::oKV + st * 2 * AT_TILE, 0);
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS + (j & 1) * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(&s_full[j & 1]);
-            }
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        issue_s(0, 0);
-        int st = 0; uint32_t ph = 0;
-        for (int j = 0; j < nkv; ++j) {
-            int st1 = st + 1; uint32_t ph1 = ph;
-            if (st1 == S::kKvStages) { st1 = 0; ph1 ^= 1; }
-            if (j + 1 < nkv) {
-                mbar_wait(&kv_full[st1], ph1);
-                mbar_wait(&s_empty[(j + 1) & 1], (((j + 1) >> 1) & 1) ^ 1);
-                tc_fence_after();
-                issue_s(j + 1, st1);
-            }
-            mbar_wait(&p_full[j & 1], (j >> 1) & 1);       // P_j in smem AND any rescale of O finished
-            tc_fence_after();
-            // P: K-major, two 64-key atoms AT_TILE apart, 16 keys (32 B) per k-step; V: MN-major, 16 key rows (2048 B) per k-step
-            const uint64_t dP = desc_kmajor(smem_base + S::oP + (j & 1) * 2 * AT_TILE, 0);
-            const uint64_t dV = desc_mnmajor(smem_base + S::oKV + st * 2 * AT_TILE + AT_TILE, 0);
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tO, dP + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), dV + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                umma_commit(o_full);
-                umma_commit(&p_empty[j & 1]);
-                umma_commit(&kv_empty[st]);
-            }
-            __syncwarp();
-            st = st1; ph = ph1;
-        }
-    } else {
-        const int quad = warp & 3;                           // TMEM lane quadrant this warp may touch
-        const int qtr = (warp - 2) >> 2;                     // which 32 keys of the tile / which 16 output dims
-        const int r = quad * 32 + lane;
-        const int qi = q0 + r;
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const float sl2 = scale * kLog2eF;
-        float* xmax = reinterpret_cast<float*>(smem + S::oXch);               // [buf][qtr][row]
-        float* xsum = xmax + 2 * 4 * 128;                                     // [qtr][row]
-        float m_used = -INFINITY, l_run = 0.f;               // l_run: partial row sum over THIS thread's keys, in the scale of m_used
-        const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
-        const uint32_t t32 = drop.thresh16 << 16;
-
-        for (int j = 0; j < nkv; ++j) {
-            const int k0 = j * AT_BN;
-            const bool need_mask = (j == qb) || (k0 + AT_BN > T);
-            const int kc0 = k0 + qtr * 32;
-            uint32_t v[32];
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            __syncwarp();
-            tmem_ld_32x32(tS + (j & 1) * 128 + lane_off + qtr * 32, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[j & 1]);     // S_j is in registers
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-            if (need_mask) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int kj = kc0 + i;
-                    if (!(kj <= qi && kj < T)) v[i] = 0xff800000u;         // -inf -> probability 0
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
-            xmax[((j & 1) * 4 + qtr) * 128 + r] = fmaxf(mx0, mx1);
-            named_bar_sync(2, 512);
-            const float* xm = xmax + (j & 1) * 4 * 128 + r;
-            const float m_new = fmaxf(fmaxf(fmaxf(xm[0], xm[128]), fmaxf(xm[256], xm[384])), m_used);
-            if (j == 0) {
-                m_used = m_new;
-            } else {
-                const bool grow = (m_new - m_used) * sl2 > 8.f;
-                if (__any_sync(0xffffffffu, grow)) {
-                    // rescale this warp's 32 rows x 16 output columns of O in TMEM (rows that did not grow: factor 1)
-                    const float f = grow ? ex2_fast((m_used - m_new) * sl2) : 1.f;
-                    mbar_wait(o_full, (uint32_t)((j - 1) & 1));          // P_{j-1} V_{j-1} has landed
-                    tc_fence_after();
-                    uint32_t o[16];
-                    __syncwarp();
-                    tmem_ld_32x16(tO + lane_off + qtr * 16, o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                    tmem_st_32x16(tO + lane_off + qtr * 16, o);
-                    tmem_st_wait();
-                    l_run *= f;
-                    if (grow) m_used = m_new;
-                }
-            }
-            const float msc = m_used * sl2;
-            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc));
-                const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
-                const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -msc));
-                const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -msc));
-                rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
-            }
-            l_run += (rs0 + rs1) + (rs2 + rs3);
-            if (drop.thresh16) {
-                // keep decisions of 4 consecutive keys per multiply-fold hash (common.cuh); the 1/(1-p) scale is applied once, to O
-                const uint32_t g0 = (uint32_t)kc0 >> 2;
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    uint32_t w0, w1;
-                    attn_drop_words(rk, g0 + i4, w0, w1);
-                    v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
-                    v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
-                    v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
-                    v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
-                }
-            }
-            mbar_wait(&p_empty[j & 1], ((j >> 1) & 1) ^ 1);
-            const uint32_t sP = smem_u32(smem + S::oP + (j & 1) * 2 * AT_TILE);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                st_tile_chunk(sP, r, qtr * 4 + g,
-                              make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                                         pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                                         pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                                         pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]))));
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[j & 1]);
-        }
-        // epilogue: O / l  (dropout's 1/(1-p) folded in), lse
-        mbar_wait(o_full, (uint32_t)((nkv - 1) & 1));
-        tc_fence_after();
-        uint32_t o[16];
-        __syncwarp();
-        tmem_ld_32x16(tO + lane_off + qtr * 16, o);
-        tmem_ld_wait();
-        xsum[qtr * 128 + r] = l_run;
-        named_bar_sync(2, 512);
-        const float l_tot = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
-        if (qi < T) {
-            const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;
-            if (qtr == 0) lse_out[(size_t)bh * T + qi] = m_used * scale + logf(l_tot);
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + qtr * 16);
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-                dst[g] = make_uint4(pack_bf16(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
-                                    pack_bf16(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
-                                    pack_bf16(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
-                                    pack_bf16(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// backward: CTA owns key block jb, loops over query blocks i >= jb
-// ------------------------------------------------------------------------------------------------------------
-struct BwdSmem {
-    static constexpr int oK = 0;
-    static constexpr int oV = AT_TILE;
-    static constexpr int oQdO = 2 * AT_TILE;                  // [2 stages][Q | dO]
-    static constexpr int oP = oQdO + 2 * 2 * AT_TILE;         // 2 atoms
-    static constexpr int oDS = oP + 2 * AT_TILE;              // 2 atoms
-    static constexpr int oBar = oDS + 2 * AT_TILE;
-    static constexpr int kBytes = oBar + 256 + 1024;
-};
-
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
-                   const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, float scale, DropCfg drop) {
-    using S = BwdSmem;
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
-    uint64_t* kv_full = bars;                 // 1
-    uint64_t* qdo_full = bars + 1;            // [2]
-    uint64_t* qdo_empty = bars + 3;           // [2]
-    uint64_t* sdp_full = bars + 5;            // S and dP in TMEM (commit)
-    uint64_t* sdp_empty = bars + 6;           // 128: S, dP read out of TMEM
-    uint64_t* pds_full = bars + 7;            // 128: P, dS written to smem
-    uint64_t* pds_empty = bars + 8;           // commit: the three gradient MMAs finished reading P / dS
-    uint64_t* dq_full = bars + 9;             // commit
-    uint64_t* dq_empty = bars + 10;           // 128
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jb = blockIdx.x;                               // key block (early blocks are the heavy ones)
-    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int d = H * 64, ld3 = 3 * d;
-    const int k0 = jb * AT_BN;
-    const int nq = (T + AT_BM - 1) / AT_BM;
-    const int row_base = b * T;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmQKV);
-        tma_prefetch_desc(&tmDO);
-        mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 256);
-        mbar_init(pds_full, 256); mbar_init(pds_empty, 1);
-        mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
-            tma_load_2d(smem + S::oK, &tmQKV, kv_full, d + h * 64, row_base + k0);
-            tma_load_2d(smem + S::oV, &tmQKV, kv_full, 2 * d + h * 64, row_base + k0);
-            int it = 0;
-            for (int i = jb; i < nq; ++i, ++it) {
-                const int st = it & 1;
-                mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
-                uint8_t* sq = smem + S::oQdO + st * 2 * AT_TILE;
-                mbar_arrive_expect_tx(&qdo_full[st], 2 * AT_TILE);
-                tma_load_2d(sq, &tmQKV, &qdo_full[st], h * 64, row_base + i * AT_BM);
-                tma_load_2d(sq + AT_TILE, &tmDO, &qdo_full[st], h * 64, row_base + i * AT_BM);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);    // S, dP
-            constexpr uint32_t idesc_g = make_idesc_bf16(128, 64, true, true);       // dV, dK
-            constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);      // dQ
-            const uint32_t sK = smem_u32(smem + S::oK), sV = smem_u32(smem + S::oV);
-            const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
-            mbar_wait(kv_full, 0);
-            int it = 0;
-            for (int i = jb; i < nq; ++i, ++it) {
-                const int st = it & 1;
-                const uint32_t ph = it & 1 ? 1u : 0u;        // barriers that complete once per iteration: parity = it & 1
-                const uint32_t sQ = smem_u32(smem + S::oQdO + st * 2 * AT_TILE), sDO = sQ + AT_TILE;
-                mbar_wait(&qdo_full[st], (it >> 1) & 1);
-                mbar_wait(sdp_empty, ph ^ 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tDP, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(sdp_full);
-                mbar_wait(pds_full, ph);
-                mbar_wait(dq_empty, ph ^ 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tDV, desc_mnmajor(sP, k), desc_mnmajor(sDO, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tDK, desc_mnmajor(sDS, k), desc_mnmajor(sQ, k), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tDQ, desc_kmajor(sDS, k), desc_mnmajor(sK, k), idesc_q, k > 0 ? 1u : 0u);
-                umma_commit(dq_full);
-                umma_commit(pds_empty);
-                umma_commit(&qdo_empty[st]);
-            }
-        }
-        __syncwarp();
-    } else {
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;                    // column half: keys 0-63 / 64-127 of the tile, 32 of the 64 head dims
-        const int r = quad * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const float sl2 = scale * kLog2eF;
-        const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
-        const uint32_t t32 = drop.thresh16 << 16;
-        int it = 0;
-        for (int i = jb; i < nq; ++i, ++it) {
-            const uint32_t ph = it & 1 ? 1u : 0u;
-            const int qi = i * AT_BM + r;                      // this thread's query
-            const bool q_ok = qi < T;
-            const float lse2 = q_ok ? lse[(size_t)bh * T + qi] * kLog2eF : 0.f;
-            const float dlt = q_ok ? delta[(size_t)bh * T + qi] : 0.f;
-            const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
-            const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
-            const int kc0 = k0 + half * 64;
-            mbar_wait(sdp_full, ph);
-            tc_fence_after();
-            mbar_wait(pds_empty, ph ^ 1);
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t sv[32], gv[32];
-                __syncwarp();
-                tmem_ld_32x32(tS + lane_off + half * 64 + c * 32, sv);
-                tmem_ld_32x32(tDP + lane_off + half * 64 + c * 32, gv);
-                tmem_ld_wait();
-                float p[32], ds[32];
-                if (need_mask) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int kj = kc0 + c * 32 + e;
-                        p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
-                }
-                // The softmax scale (a power of two) and the dropout scale are applied to the OUTPUTS (dQ, dK resp. dV), not per element:
-                //   ds = P (mask * dP / (1-p) - delta)      pd = mask * P
-                if (drop.thresh16) {
-                    const uint32_t g0 = (uint32_t)(kc0 + c * 32) >> 2;
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        uint32_t w0, w1;
-                        attn_drop_words(rk, g0 + e4, w0, w1);
-                        const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
-                            p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    st_tile_chunk(sP, r, (half * 2 + c) * 4 + g,
-                                  make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
-                                             pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7])));
-                    st_tile_chunk(sDS, r, (half * 2 + c) * 4 + g,
-                                  make_uint4(pack_bf16(ds[8 * g], ds[8 * g + 1]), pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
-                                             pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16(ds[8 * g + 6], ds[8 * g + 7])));
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(sdp_empty);
-            fence_proxy_async();
-            mbar_arrive(pds_full);
-            // dQ tile of this (query block, key block) pair -> fp32 accumulation buffer (this thread: 32 of the 64 dims)
-            mbar_wait(dq_full, ph);
-            tc_fence_after();
-            float* dst = dq_acc + (size_t)(row_base + qi) * d + h * 64 + half * 32;
-            {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(tDQ + lane_off + half * 32, v);
-                tmem_ld_wait();
-                if (q_ok) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(v[4 * g])),
-                                     "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3])) : "memory");
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(dq_empty);
-        }
-        // dK, dV of this key block (complete once the last iteration's commit has fired: dq_full of that iteration)
-        const int kj = k0 + r;
-        bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64 + half * 32;
-        bf16* dvp = dkp + d;
-        {
-            uint32_t a[32], v[32];
-            __syncwarp();                                   // .aligned TMEM loads: whole warp, unconditionally
-            tmem_ld_32x32(tDK + lane_off + half * 32, a);
-            tmem_ld_32x32(tDV + lane_off + half * 32, v);
-            tmem_ld_wait();
-            if (kj < T) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) { a[e] = __float_as_uint(__uint_as_float(a[e]) * scale); v[e] = __float_as_uint(__uint_as_float(v[e]) * drop.scale); }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    reinterpret_cast<uint4*>(dkp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]), __uint_as_float(a[8 * g + 1])), pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3])),
-                                   pack_bf16(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5])), pack_bf16(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7])));
-                    reinterpret_cast<uint4*>(dvp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                                   pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// backward, version 3: 16 math warps (thread = query row x 32 keys), and the tensor core never waits for the math:
-//   * S/dP of query block it+1 are issued as soon as block it's S/dP have been pulled into registers (sdp_empty), BEFORE the
-//     three gradient GEMMs of block it -> they run while the math warps are still busy with block it;
-//   * the gradient GEMMs of block it then run while the math warps already work on block it+1;
-//   * the dQ tile of block it is read out of TMEM at the END of iteration it+1 (registers are free there) and red.add'ed to the
-//     fp32 accumulator.
-// Version 2 (one S/dP -> math -> gradients -> dQ chain per iteration, 8 math warps) took ~10 000 cycles per 128x128 block pair.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __maxnreg__(96)
-attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
-                    const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, float scale, DropCfg drop) {
-    using S = BwdSmem;
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::oBar);
-    uint64_t* kv_full = bars;                 // 1
-    uint64_t* qdo_full = bars + 1;            // [2]
-    uint64_t* qdo_empty = bars + 3;           // [2]
-    uint64_t* sdp_full = bars + 5;            // commit: S and dP in TMEM
-    uint64_t* sdp_empty = bars + 6;           // 16: S, dP are in registers
-    uint64_t* pds_full = bars + 7;            // 16: P, dS written to smem
-    uint64_t* pds_empty = bars + 8;           // commit: the three gradient MMAs finished reading P / dS
-    uint64_t* dq_full = bars + 9;             // commit
-    uint64_t* dq_empty = bars + 10;           // 16
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jb = blockIdx.x;                               // key block (early blocks are the heavy ones)
-    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int d = H * 64, ld3 = 3 * d;
-    const int k0 = jb * AT_BN;
-    const int nq = (T + AT_BM - 1) / AT_BM;
-    const int nit = nq - jb;
-    const int row_base = b * T;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmQKV);
-        tma_prefetch_desc(&tmDO);
-        mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 16);
-        mbar_init(pds_full, 16); mbar_init(pds_empty, 1);
-        mbar_init(dq_full, 1); mbar_init(dq_empty, 16);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
-            tma_load_2d(smem + S::oK, &tmQKV, kv_full, d + h * 64, row_base + k0);
-            tma_load_2d(smem + S::oV, &tmQKV, kv_full, 2 * d + h * 64, row_base + k0);
-        }
-        __syncwarp();
-        for (int it = 0; it < nit; ++it) {
-            const int st = it & 1, i = jb + it;
-            mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
-            uint8_t* sq = smem + S::oQdO + st * 2 * AT_TILE;
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&qdo_full[st], 2 * AT_TILE);
-                tma_load_2d(sq, &tmQKV, &qdo_full[st], h * 64, row_base + i * AT_BM);
-                tma_load_2d(sq + AT_TILE, &tmDO, &qdo_full[st], h * 64, row_base + i * AT_BM);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);    // S, dP
-        constexpr uint32_t idesc_g = make_idesc_bf16(128, 64, true, true);       // dV, dK
-        constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);      // dQ
-        const uint32_t smem_base = smem_u32(smem);
-        const uint64_t dK_k = desc_kmajor(smem_base + S::oK, 0), dV_k = desc_kmajor(smem_base + S::oV, 0);
-        const uint64_t dK_mn = desc_mnmajor(smem_base + S::oK, 0);
-        const uint64_t dP_mn = desc_mnmajor(smem_base + S::oP, 0), dDS_mn = desc_mnmajor(smem_base + S::oDS, 0);
-        const uint64_t dDS_k = desc_kmajor(smem_base + S::oDS, 0);
-        auto issue_sdp = [&](int it) {
-            const uint32_t sQ = smem_base + S::oQdO + (it & 1) * 2 * AT_TILE;
-            const uint64_t dQ_k = desc_kmajor(sQ, 0), dDO_k = desc_kmajor(sQ + AT_TILE, 0);
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS, dQ_k + 2 * k, dK_k + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tDP, dDO_k + 2 * k, dV_k + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(sdp_full);
-            }
-            __syncwarp();
-        };
-        mbar_wait(kv_full, 0);
-        mbar_wait(&qdo_full[0], 0);
-        tc_fence_after();
-        issue_sdp(0);
-        for (int it = 0; it < nit; ++it) {
-            const uint32_t ph = (uint32_t)(it & 1);
-            if (it + 1 < nit) {
-                mbar_wait(&qdo_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
-                mbar_wait(sdp_empty, ph);                       // block it's S / dP are in registers
-                tc_fence_after();
-                issue_sdp(it + 1);
-            }
-            mbar_wait(pds_full, ph);
-            mbar_wait(dq_empty, ph ^ 1);                        // dQ of block it-1 has been read out
-            tc_fence_after();
-            const uint32_t sQ = smem_base + S::oQdO + (it & 1) * 2 * AT_TILE;
-            const uint64_t dQ_mn = desc_mnmajor(sQ, 0), dDO_mn = desc_mnmajor(sQ + AT_TILE, 0);
-            if (elect_one()) {
-                // MN-major operands: 16 K-rows (2048 B) per k-step; the K-major dS: 32 B per k-step, second 64-key atom AT_TILE further
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tDV, dP_mn + (uint64_t)(k * 128), dDO_mn + (uint64_t)(k * 128), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) umma_bf16(tDK, dDS_mn + (uint64_t)(k * 128), dQ_mn + (uint64_t)(k * 128), idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tDQ, dDS_k + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), dK_mn + (uint64_t)(k * 128), idesc_q, k > 0 ? 1u : 0u);
-                umma_commit(dq_full);
-                umma_commit(pds_empty);
-                umma_commit(&qdo_empty[it & 1]);
-            }
-            __syncwarp();
-        }
-    } else {
-        const int quad = warp & 3;
-        const int qtr = (warp - 2) >> 2;                     // 32 keys of the tile / 16 of the 64 head dims
-        const int r = quad * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const float sl2 = scale * kLog2eF;
-        const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
-        const uint32_t t32 = drop.thresh16 << 16;
-        const int kc0 = k0 + qtr * 32;
-
-        // dQ tile of query block `blk` (finished by the gradient MMAs of that iteration) -> fp32 accumulator, scaled at conversion time
-        auto dq_out = [&](int it_done) {
-            const int qrow = (jb + it_done) * AT_BM + r;
-            mbar_wait(dq_full, (uint32_t)(it_done & 1));
-            tc_fence_after();
-            uint32_t v[16];
-            __syncwarp();
-            tmem_ld_32x16(tDQ + lane_off + qtr * 16, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
-            if (qrow < T) {
-                float* dst = dq_acc + (size_t)(row_base + qrow) * d + h * 64 + qtr * 16;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(v[4 * g])),
-                                 "f"(__uint_as_float(v[4 * g + 1])), "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3])) : "memory");
-            }
-        };
-
-        for (int it = 0; it < nit; ++it) {
-            const int i = jb + it;
-            const uint32_t ph = (uint32_t)(it & 1);
-            const int qi = i * AT_BM + r;                      // this thread's query
-            const bool q_ok = qi < T;
-            const float lse2 = q_ok ? lse[(size_t)bh * T + qi] * kLog2eF : 0.f;
-            const float dlt = q_ok ? delta[(size_t)bh * T + qi] : 0.f;
-            const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
-            const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
-            uint32_t pp[16], dd[16];                          // packed bf16 pairs: P (dropped) and dS for this thread's 32 keys
-            mbar_wait(sdp_full, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t sv[16], gv[16];
-                __syncwarp();
-                tmem_ld_32x16(tS + lane_off + qtr * 32 + c * 16, sv);
-                tmem_ld_32x16(tDP + lane_off + qtr * 32 + c * 16, gv);
-                tmem_ld_wait();
-                if (c == 1) {                                  // everything this warp needs from S / dP is in registers
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sdp_empty);
-                }
-                float p[16];
-                if (need_mask) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int kj = kc0 + c * 16 + e;
-                        p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
-                }
-                // softmax scale and dropout scale are applied to the OUTPUTS (dQ, dK resp. dV):  ds = P (mask dP/(1-p) - delta), pd = mask P
-                float ds[16];
-                if (drop.thresh16) {
-                    const uint32_t g0 = (uint32_t)(kc0 + c * 16) >> 2;
-#pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        uint32_t w0, w1;
-                        attn_drop_words(rk, g0 + e4, w0, w1);
-                        const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                            ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
-                            p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { pp[c * 8 + e] = pack_bf16(p[2 * e], p[2 * e + 1]); dd[c * 8 + e] = pack_bf16(ds[2 * e], ds[2 * e + 1]); }
-            }
-            mbar_wait(pds_empty, ph ^ 1);                      // gradient MMAs of block it-1 no longer read the P / dS buffers
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                st_tile_chunk(sP, r, qtr * 4 + g, make_uint4(pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]));
-                st_tile_chunk(sDS, r, qtr * 4 + g, make_uint4(dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]));
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
-            if (it > 0) dq_out(it - 1);
-        }
-        dq_out(nit - 1);                                       // also: all gradient MMAs (dK, dV) are complete after this wait
-        // dK (x softmax scale), dV (x dropout scale) of this key block
-        const int kj = k0 + r;
-        bf16* dkp = dqkv + (size_t)(row_base + min(kj, T - 1)) * ld3 + d + h * 64 + qtr * 16;
-        bf16* dvp = dkp + d;
-        {
-            uint32_t a[16], v[16];
-            __syncwarp();
-            tmem_ld_32x16(tDK + lane_off + qtr * 16, a);
-            tmem_ld_32x16(tDV + lane_off + qtr * 16, v);
-            tmem_ld_wait();
-            if (kj < T) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    reinterpret_cast<uint4*>(dkp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * scale, __uint_as_float(a[8 * g + 1]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * scale, __uint_as_float(a[8 * g + 3]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * scale, __uint_as_float(a[8 * g + 5]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * scale, __uint_as_float(a[8 * g + 7]) * scale));
-                    reinterpret_cast<uint4*>(dvp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * drop.scale, __uint_as_float(v[8 * g + 1]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 2]) * drop.scale, __uint_as_float(v[8 * g + 3]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 4]) * drop.scale, __uint_as_float(v[8 * g + 5]) * drop.scale),
-                                   pack_bf16(__uint_as_float(v[8 * g + 6]) * drop.scale, __uint_as_float(v[8 * g + 7]) * drop.scale));
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
-}
+constexpr int AT3_THREADS = 576;      // warp 0 TMA, warp 1 MMA, 16 math warps (four per TMEM lane quadrant, 32 columns each)
 
 // ------------------------------------------------------------------------------------------------------------
 // Version 4 = version 3 made PERSISTENT: one CTA per SM walks a list of (query block, head) items, heavy items first.  TMEM is
@@ -1791,11 +792,11 @@ bool attn_use_tc() {
     return !legacy;
 }
 
-// TTTS_ATTN_VER=2|3|4 selects the earlier kernels (2: 8 softmax warps; 3: 16 warps, one CTA per item; 4: persistent, run-time dropout
-// branch) for A/B measurements; default 5 (persistent, dropout fixed at compile time, hash interleaved with the exponentials)
+// TTTS_ATTN_VER=4 selects the r1e/r1h flavour of the persistent kernels (run-time dropout branch, 512-thread row-max barrier, exposed item
+// tails) for A/B measurements; default 5
 static int attn_tc_version() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : 5; }
+    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] == '4') ? 4 : 5; }
     return v;
 }
 
@@ -1804,29 +805,20 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
     CUtensorMap tm;
     int rc = make_tmap_2d(&tm, qkv, 2, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, 128, true);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kBytes));
-        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd3Smem::kBytes));
-        attr = true;
+    static bool attr4 = false;
+    if (!attr4) {
+        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
+        attr4 = true;
     }
-    dim3 grid((T + AT_BM - 1) / AT_BM, B * H);
-    if (attn_tc_version() >= 4) {
-        static bool attr4 = false;
-        if (!attr4) {
-            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
-            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
-            TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
-            attr4 = true;
-        }
-        const int items = (int)grid.x * B * H;
-        const int nblk = items < num_sms() ? items : num_sms();
-        TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
-        if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
-        else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
-        else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
-    } else if (attn_tc_version() >= 3) attn_fwd_tc3_kernel<<<grid, AT3_THREADS, Fwd3Smem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
-    else attn_fwd_tc_kernel<<<grid, AT_THREADS, FwdSmem::kBytes, st>>>(tm, o, lse, T, H, 0.125f, drop);
+    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int items = nq * B * H;
+    const int nblk = items < num_sms() ? items : num_sms();
+    TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nq <= 4096, "attention: too many (block, head) items");
+    if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+    else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+    else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
     return TTTS_OK;
 }
@@ -1846,29 +838,20 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
     if (rc) return rc;
     rc = make_tmap_2d(&tmDO, dout, 2, (uint64_t)d, (uint64_t)B * T, (uint64_t)d, 64, 128, true);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kBytes));
-        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kBytes));
-        attr = true;
+    static bool attr4 = false;
+    if (!attr4) {
+        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
+        attr4 = true;
     }
-    dim3 grid((T + AT_BN - 1) / AT_BN, B * H);
-    if (attn_tc_version() >= 4) {
-        static bool attr4 = false;
-        if (!attr4) {
-            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
-            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
-            TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
-            attr4 = true;
-        }
-        const int items = (int)grid.x * B * H;
-        const int nblk = items < num_sms() ? items : num_sms();
-        TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && grid.x <= 4096, "attention: too many (block, head) items");
-        if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
-        else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
-        else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
-    } else if (attn_tc_version() >= 3) attn_bwd_tc3_kernel<<<grid, AT3_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
-    else attn_bwd_tc_kernel<<<grid, AT_THREADS, BwdSmem::kBytes, st>>>(tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, 0.125f, drop);
+    const int nkb = (T + AT_BN - 1) / AT_BN;
+    const int items = nkb * B * H;
+    const int nblk = items < num_sms() ? items : num_sms();
+    TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nkb <= 4096, "attention: too many (block, head) items");
+    if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+    else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+    else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_bwd_tc");
     const size_t n4 = (size_t)B * T * d / 4;
     int blocks = (int)((n4 + 255) / 256);

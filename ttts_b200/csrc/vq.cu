@@ -35,6 +35,91 @@ __global__ void vq_code_norms_kernel(const float* __restrict__ E, int K, int D, 
 
 struct VqLayout { long long sB, sD, sN; int Nn; };   // element (b, d, n) of x at b*sB + d*sD + n*sN ; vector v = b*Nn + n
 
+// x tile [d][64 vectors].  SWZ: the 16 four-vector groups of row d are permuted by d mod 16, so a warp that writes (or reads back) 32
+// consecutive dims of one vector -- the coalesced order for row-major [N, D] input -- touches 16 different bank groups instead of one;
+// the main loop's float4 reads (one row, group ty) only see a different group number.
+template <bool SWZ>
+TTTS_DEVICE int vq_xs_index(int d, int vl) { return SWZ ? d * VQ_TM + ((((vl >> 2) ^ d) & 15) << 2) + (vl & 3) : d * VQ_TM + vl; }
+
+// x tile -> shared memory (transposed to [d][v]) and |x|^2 per vector.  Ends with the tile visible to the whole CTA.
+template <bool SWZ>
+TTTS_DEVICE void vq_load_x_tile(const float* __restrict__ x, const VqLayout& lay, int N, int D, int v0, float* Xs, float* xx, int tid) {
+    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
+        int d, vl;
+        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }        // row-major [N, D]: consecutive threads along d
+        else { d = i / VQ_TM; vl = i - d * VQ_TM; }             // [B, D, Nn]: consecutive threads along n
+        const int v = v0 + vl;
+        float val = 0.f;
+        if (v < N) {
+            const int b = v / lay.Nn, n = v - b * lay.Nn;
+            val = x[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)];
+        }
+        Xs[vq_xs_index<SWZ>(d, vl)] = val;
+    }
+    __syncthreads();
+    if (tid < VQ_TM) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) { float t = Xs[vq_xs_index<SWZ>(d, tid)]; s += t * t; }
+        xx[tid] = s;
+    }
+}
+
+// Per-thread (best, index) of 4 vectors -> CTA-wide argmax (lowest index among equals), then the fused epilogue: indices, dequantised
+// rows, straight-through values, commit-loss partial, code histogram and embedding sums for the EMA update.
+template <bool SWZ>
+TTTS_DEVICE void vq_finish_tile(float (&best)[4], int (&besti)[4], const VqLayout& lay, int N, int D,
+                                const float* __restrict__ E, int v0, const float* Xs, int* sidx, int64_t* __restrict__ idx_out,
+                                float* __restrict__ q_out, int straight_through, float* __restrict__ commit_partial, float* __restrict__ hist,
+                                float* __restrict__ embed_sum, int tid) {
+    const int tx = tid & 15, ty = tid >> 4;
+    // reduce across the 16 lanes (tx) that share the same 4 vectors
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+            if (ob > best[i] || (ob == best[i] && oi < besti[i])) { best[i] = ob; besti[i] = oi; }
+        }
+        if (tx == 0) sidx[ty * 4 + i] = besti[i];
+    }
+    __syncthreads();
+    if (tid < VQ_TM && v0 + tid < N) {
+        idx_out[v0 + tid] = (int64_t)sidx[tid];
+        if (hist) atomicAdd(hist + sidx[tid], 1.0f);
+    }
+    float csum = 0.f;
+    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
+        int d, vl;
+        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
+        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
+        const int v = v0 + vl;
+        if (v < N) {
+            const int k = sidx[vl];
+            const float q = __ldg(E + (size_t)k * D + d);
+            const float xv = Xs[vq_xs_index<SWZ>(d, vl)];
+            const float diff = q - xv;
+            csum += diff * diff;
+            if (q_out) {
+                const int b = v / lay.Nn, n = v - b * lay.Nn;
+                q_out[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)] = straight_through ? (xv + diff) : q;
+            }
+            if (embed_sum) atomicAdd(embed_sum + (size_t)k * D + d, xv);
+        }
+    }
+    if (commit_partial) {
+        __shared__ float red[VQ_THREADS / 32];
+        csum = warp_sum(csum);
+        if ((tid & 31) == 0) red[tid >> 5] = csum;
+        __syncthreads();
+        if (tid < 32) {
+            float s = tid < VQ_THREADS / 32 ? red[tid] : 0.f;
+            s = warp_sum(s);
+            if (tid == 0) commit_partial[blockIdx.x] = s;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
                                                                const float* __restrict__ ee, int K, int64_t* __restrict__ idx_out,
                                                                float* __restrict__ q_out, int straight_through, float* __restrict__ commit_partial,
@@ -48,25 +133,7 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
     const int tx = tid & 15, ty = tid >> 4;
     const int v0 = blockIdx.x * VQ_TM;
 
-    // ---- x tile -> smem (transposed to [d][v]) ----
-    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
-        int d, vl;
-        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }        // row-major [N, D]: consecutive threads along d
-        else { d = i / VQ_TM; vl = i - d * VQ_TM; }             // [B, D, Nn]: consecutive threads along n
-        const int v = v0 + vl;
-        float val = 0.f;
-        if (v < N) {
-            const int b = v / lay.Nn, n = v - b * lay.Nn;
-            val = x[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)];
-        }
-        Xs[d * VQ_TM + vl] = val;
-    }
-    __syncthreads();
-    if (tid < VQ_TM) {
-        float s = 0.f;
-        for (int d = 0; d < D; ++d) { float t = Xs[d * VQ_TM + tid]; s += t * t; }
-        xx[tid] = s;
-    }
+    vq_load_x_tile<false>(x, lay, N, D, v0, Xs, xx, tid);
 
     float best[4]; int besti[4];
 #pragma unroll
@@ -119,54 +186,7 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
             }
         }
     }
-    // reduce across the 16 lanes (tx) that share the same 4 vectors
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
-            const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
-            if (ob > best[i] || (ob == best[i] && oi < besti[i])) { best[i] = ob; besti[i] = oi; }
-        }
-        if (tx == 0) sidx[ty * 4 + i] = besti[i];
-    }
-    __syncthreads();
-
-    // ---- epilogue: indices, dequantised rows, commit-loss partial, EMA statistics ----
-    if (tid < VQ_TM && v0 + tid < N) {
-        idx_out[v0 + tid] = (int64_t)sidx[tid];
-        if (hist) atomicAdd(hist + sidx[tid], 1.0f);
-    }
-    float csum = 0.f;
-    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
-        int d, vl;
-        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
-        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
-        const int v = v0 + vl;
-        if (v < N) {
-            const int k = sidx[vl];
-            const float q = __ldg(E + (size_t)k * D + d);
-            const float xv = Xs[d * VQ_TM + vl];
-            const float diff = q - xv;
-            csum += diff * diff;
-            if (q_out) {
-                const int b = v / lay.Nn, n = v - b * lay.Nn;
-                q_out[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)] = straight_through ? (xv + diff) : q;
-            }
-            if (embed_sum) atomicAdd(embed_sum + (size_t)k * D + d, xv);
-        }
-    }
-    if (commit_partial) {
-        __shared__ float red[VQ_THREADS / 32];
-        csum = warp_sum(csum);
-        if ((tid & 31) == 0) red[tid >> 5] = csum;
-        __syncthreads();
-        if (tid < 32) {
-            float s = tid < VQ_THREADS / 32 ? red[tid] : 0.f;
-            s = warp_sum(s);
-            if (tid == 0) commit_partial[blockIdx.x] = s;
-        }
-    }
+    vq_finish_tile<false>(best, besti, lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
 }
 
 // Pipelined form (default when D % 16 == 0 and E is 16-byte aligned; TTTS_VQ_V1=1 selects the kernel above).  The kernel above reads every
@@ -177,11 +197,6 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
 // so that its float4 reads along the dims are bank-conflict free.  Accumulation order over d is unchanged: distances and indices are
 // bit-identical to the kernel above.
 constexpr int VQ_EP = VQ_DC + 4;      // row pitch (floats) of the code-major chunk
-// x tile [d][64 vectors] with the 16 four-vector groups of row d permuted by d mod 16: a warp that writes (or reads back) 32 consecutive
-// dims of one vector -- the coalesced order for row-major [N, D] input -- then touches 16 different bank groups instead of one (the r1n
-// profile had the shared-memory pipe at 76 % with a third of its wavefronts from these 32-way conflicts); the main loop's float4 reads
-// (one row, groups ty) only see a different group number.
-TTTS_DEVICE int vq_xs_index(int d, int vl) { return d * VQ_TM + ((((vl >> 2) ^ d) & 15) << 2) + (vl & 3); }
 
 __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
                                                                     const float* __restrict__ ee, int K, int64_t* __restrict__ idx_out,
@@ -213,25 +228,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
     issue(0, 0, 0);
     cp_async_commit();
 
-    // ---- x tile -> smem (transposed to [d][v]) ----
-    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
-        int d, vl;
-        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
-        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
-        const int v = v0 + vl;
-        float val = 0.f;
-        if (v < N) {
-            const int b = v / lay.Nn, n = v - b * lay.Nn;
-            val = x[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)];
-        }
-        Xs[vq_xs_index(d, vl)] = val;
-    }
-    __syncthreads();
-    if (tid < VQ_TM) {
-        float s = 0.f;
-        for (int d = 0; d < D; ++d) { float t = Xs[vq_xs_index(d, tid)]; s += t * t; }
-        xx[tid] = s;
-    }
+    vq_load_x_tile<true>(x, lay, N, D, v0, Xs, xx, tid);
 
     float best[4]; int besti[4];
 #pragma unroll
@@ -285,54 +282,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
             ++ch;
         }
     }
-    // reduce across the 16 lanes (tx) that share the same 4 vectors
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
-            const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
-            if (ob > best[i] || (ob == best[i] && oi < besti[i])) { best[i] = ob; besti[i] = oi; }
-        }
-        if (tx == 0) sidx[ty * 4 + i] = besti[i];
-    }
-    __syncthreads();
-
-    // ---- epilogue: indices, dequantised rows, commit-loss partial, EMA statistics (as in the kernel above) ----
-    if (tid < VQ_TM && v0 + tid < N) {
-        idx_out[v0 + tid] = (int64_t)sidx[tid];
-        if (hist) atomicAdd(hist + sidx[tid], 1.0f);
-    }
-    float csum = 0.f;
-    for (int i = tid; i < D * VQ_TM; i += VQ_THREADS) {
-        int d, vl;
-        if (lay.sD == 1) { vl = i / D; d = i - vl * D; }
-        else { d = i / VQ_TM; vl = i - d * VQ_TM; }
-        const int v = v0 + vl;
-        if (v < N) {
-            const int k = sidx[vl];
-            const float q = __ldg(E + (size_t)k * D + d);
-            const float xv = Xs[vq_xs_index(d, vl)];
-            const float diff = q - xv;
-            csum += diff * diff;
-            if (q_out) {
-                const int b = v / lay.Nn, n = v - b * lay.Nn;
-                q_out[(size_t)(b * lay.sB + d * lay.sD + n * lay.sN)] = straight_through ? (xv + diff) : q;
-            }
-            if (embed_sum) atomicAdd(embed_sum + (size_t)k * D + d, xv);
-        }
-    }
-    if (commit_partial) {
-        __shared__ float red[VQ_THREADS / 32];
-        csum = warp_sum(csum);
-        if ((tid & 31) == 0) red[tid >> 5] = csum;
-        __syncthreads();
-        if (tid < 32) {
-            float s = tid < VQ_THREADS / 32 ? red[tid] : 0.f;
-            s = warp_sum(s);
-            if (tid == 0) commit_partial[blockIdx.x] = s;
-        }
-    }
+    vq_finish_tile<true>(best, besti, lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
 }
 
 __global__ void __launch_bounds__(1024) vq_commit_final_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
