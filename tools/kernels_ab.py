@@ -72,3 +72,18 @@ if os.path.exists(prev):
             print("%s | max |%s - previous run| = %.3e (max |value| %.3f)" % (tag, k, float(np.abs(v - old[k]).max()), float(np.abs(v).max())), flush=True)
 else:
     np.savez(prev, **keep)
+if only == "enc":
+    # whole encode (64 clips): time + digests of z and codes.  TTTS_CONV_DIRECT=0 / TTTS_CONV_PIPE=0 select the older conv kernels,
+    # which accumulate in the same order: the digests must not change.
+    from ttts_b200.vqvae.encoder import VQEncoder
+    torch.manual_seed(0)
+    wav = torch.clamp(0.1 * torch.randn(64, 23040, device=dev, generator=g), -1, 1)
+    enc = VQEncoder().to(dev).eval()
+    cb = enc.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(torch.randn(1024, 192, device=dev, generator=g)); cb.inited.fill_(1)
+    ms = t(lambda: enc(wav), n=10)
+    out = enc(wav)
+    dz = hashlib.sha1(out["z"].cpu().numpy().tobytes()).hexdigest()[:12]
+    dc = hashlib.sha1(out["codes"].cpu().numpy().tobytes()).hexdigest()[:12]
+    print("conv_direct=%s conv_pipe=%s | encode 64 clips: %.3f ms  %.1f Msamples/s  z digest %s codes digest %s" % (
+        os.environ.get("TTTS_CONV_DIRECT", "1"), os.environ.get("TTTS_CONV_PIPE", "1"), ms, wav.numel() / ms / 1e3, dz, dc), flush=True)

@@ -459,6 +459,151 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvP
     }
 }
 
+// Direct form for the ResBlock1 convolutions of the waveform branch (stride 1, kernel 3 / 7 / 11, dilation 1 / 3 / 5, "same" padding,
+// 32 - 192 channels; vq2.py:723-729 -> modules.py:224-318): 90 of the ~150 convolutions of an encode and its critical path.  The
+// implicit-GEMM kernels above rebuild the im2col tile element by element -- (ci, k) bookkeeping, bounds tests and a 4-byte cp.async per
+// element, every element fetched K times -- so on these layers FFMA was 28 % of the instruction stream (profiles/r1n_conv_pipe_ncu_full.txt).
+// Here a CTA stages, per 16 input channels, the input WINDOW [16][32 J + (K-1) DIL] once (each sample fetched once, leaky ReLU applied as
+// it lands) and the weight slab [32 channels][16 K]; a thread owns 8 output channels x J positions (t = tx + 32 j: conflict-free scalar
+// reads of the window, broadcast reads of the weights) and runs the fully unrolled (k) loop: 8 + J shared-memory loads per 8 J FFMAs.  Stages are double-buffered with cp.async.  The accumulation order r = ci * K + k is the implicit GEMM's: bit-identical output.
+constexpr int DC_CI = 16;
+template <int K, int DIL, int J>
+struct DirectConv {
+    static constexpr int TP = 32 * J;                     // positions per CTA
+    static constexpr int W = TP + (K - 1) * DIL;          // input window per channel
+    static constexpr int WP = (W + 3) & ~3;               // row pitch
+    static constexpr int RK = DC_CI * K;                  // weight columns (ci, k) per stage
+    static constexpr int WPITCH = RK + 1;                 // weight slab [32 co][RK] (+1: the 8 rows a thread reads sit in different banks)
+    static constexpr int XS = DC_CI * WP, WS = (32 * WPITCH + 3) & ~3;
+    static constexpr size_t kSmem = 2 * (size_t)(XS + WS) * sizeof(float);
+};
+
+template <int K, int DIL, int J>
+__global__ void __launch_bounds__(128) conv1d_direct_kernel(const ConvParams p) {
+    using C = DirectConv<K, DIL, J>;
+    extern __shared__ __align__(16) float dc_smem[];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int b = blockIdx.z, t0 = blockIdx.x * C::TP, co0 = blockIdx.y * 32;
+    const float* xb = p.x + (size_t)b * p.Cin * p.Tin;
+    const int in0 = t0 - p.pad;
+    const int nst = (p.Cin + DC_CI - 1) / DC_CI;
+    const bool lrelu = p.pre_lrelu != 0;
+
+    auto issue = [&](int s) {
+        float* xs = dc_smem + (s & 1) * (C::XS + C::WS);
+        float* ws = xs + C::XS;
+        const int c0 = s * DC_CI;
+        for (int i = tid; i < DC_CI * C::W; i += 128) {
+            const int ci = i / C::W, u = i - ci * C::W;
+            const int c = c0 + ci, ti = in0 + u;
+            const bool ok = c < p.Cin && ti >= 0 && ti < p.Tin;
+            cp_async4(xs + ci * C::WP + u, ok ? xb + (size_t)c * p.Tin + ti : p.x, ok);
+        }
+        // weights: lanes run along (ci, k), which is contiguous in w[co][ci][k] -> one cache line per warp copy (with lanes along co every
+        // copy touched 32 lines and the L1 tag stage, not the FMA pipe, set the pace: r1u, 188 us for a layer the FMAs need 60 us for)
+        for (int i = tid; i < 32 * C::RK; i += 128) {
+            const int co = i / C::RK, rk = i - co * C::RK;
+            const bool ok = c0 * K + rk < p.Cin * K && co0 + co < p.Cout;
+            cp_async4(ws + co * C::WPITCH + rk, ok ? p.w + ((size_t)(co0 + co) * p.Cin + c0) * K + rk : p.w, ok);
+        }
+    };
+
+    float acc[8][J];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[i][j] = 0.f;
+
+    issue(0);
+    cp_async_commit();
+    for (int s = 0; s < nst; ++s) {
+        cp_async_wait<0>();                                  // stage s has landed (this thread's copies)
+        float* xs = dc_smem + (s & 1) * (C::XS + C::WS);
+        if (lrelu) {                                         // once per sample, by the thread that copied it
+            for (int i = tid; i < DC_CI * C::W; i += 128) {
+                const int ci = i / C::W, u = i - ci * C::W;
+                float* e = xs + ci * C::WP + u;
+                const float v = *e;
+                *e = v > 0.f ? v : 0.1f * v;
+            }
+        }
+        __syncthreads();                                     // everybody's copies are visible; everybody is done with stage s - 1
+        if (s + 1 < nst) issue(s + 1);                       // into the buffer stage s - 1 used
+        cp_async_commit();
+        const float* ws = xs + C::XS;
+        const int cimax = min(DC_CI, p.Cin - s * DC_CI);
+        for (int ci = 0; ci < cimax; ++ci) {
+            const float* xr = xs + ci * C::WP + tx;
+            const float* wr = ws + (ty * 8) * C::WPITCH + ci * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float wa[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) wa[i] = wr[i * C::WPITCH + k];          // warp-uniform addresses: broadcast reads
+                float xv[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) xv[j] = xr[32 * j + k * DIL];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) acc[i][j] = fmaf(wa[i], xv[j], acc[i][j]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + ty * 8 + i;
+        if (co >= p.Cout) continue;
+        const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int t = t0 + tx + 32 * j;
+            if (t >= p.Tout) continue;
+            float v = acc[i][j] + bv;
+            const size_t o = ((size_t)b * p.Cout + co) * p.Tout + t;
+            if (p.resid) v += p.resid[o];
+            v *= p.out_scale;
+            p.y[o] = p.accumulate ? p.y[o] + v : v;
+        }
+    }
+}
+
+template <int K, int DIL, int J>
+static int conv1d_direct_launch(const ConvParams& p, cudaStream_t st) {
+    using C = DirectConv<K, DIL, J>;
+    static bool attr = false;
+    if (!attr) { TTTS_CUDA(cudaFuncSetAttribute(conv1d_direct_kernel<K, DIL, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem)); attr = true; }
+    dim3 grid((p.Tout + C::TP - 1) / C::TP, (p.Cout + 31) / 32, p.B);
+    conv1d_direct_kernel<K, DIL, J><<<grid, 128, C::kSmem, st>>>(p);
+    TTTS_LAUNCH_CHECK("conv1d_direct");
+    return TTTS_OK;
+}
+
+template <int J>
+static int conv1d_direct_dispatch(const ConvParams& p, cudaStream_t st) {
+#define TTTS_DC(KK, DD) if (p.K == KK && p.dil == DD) return conv1d_direct_launch<KK, DD, J>(p, st)
+    TTTS_DC(3, 1); TTTS_DC(3, 3); TTTS_DC(3, 5);
+    TTTS_DC(7, 1); TTTS_DC(7, 3); TTTS_DC(7, 5);
+    TTTS_DC(11, 1); TTTS_DC(11, 3); TTTS_DC(11, 5);
+#undef TTTS_DC
+    return -1;
+}
+
+// returns -1 when the layer is not one the direct kernel covers (the caller falls through to the implicit GEMM)
+static int conv1d_direct_try(const ConvParams& p, cudaStream_t st) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_CONV_DIRECT"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (!on || p.stride != 1 || p.post != 0 || p.mask != nullptr || p.Tout != p.Tin || p.B > 65535 || p.Tout < 256) return -1;
+    if (!(p.K == 3 || p.K == 7 || p.K == 11) || !(p.dil == 1 || p.dil == 3 || p.dil == 5)) return -1;
+    // J = 3 (96 positions per CTA) or 4 (128): the smaller tail waste wins; the layer must still fill the machine twice over
+    const int waste3 = (p.Tout + 95) / 96 * 96 - p.Tout, waste4 = (p.Tout + 127) / 128 * 128 - p.Tout;
+    const bool j3 = waste3 * 128 < waste4 * 96;
+    const long long ctas = (long long)((p.Tout + (j3 ? 95 : 127)) / (j3 ? 96 : 128)) * ((p.Cout + 31) / 32) * p.B;
+    if (ctas < 2 * num_sms()) return -1;
+    return j3 ? conv1d_direct_dispatch<3>(p, st) : conv1d_direct_dispatch<4>(p, st);
+}
+
 // weight norm: w[co, :] = g[co] * v[co, :] / ||v[co, :]||      (torch.nn.utils.weight_norm, dim=0)
 __global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int Cout, int n) {
     const int co = blockIdx.x;
@@ -542,6 +687,8 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
     static int use_v1 = -1;
     if (use_v1 < 0) { const char* e = getenv("TTTS_CONV_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     if (!use_v1) {
+        const int rc_direct = conv1d_direct_try(p, st);
+        if (rc_direct >= 0) return rc_direct;
         const long long Ptot = (long long)B * Tout;
         TTTS_CHECK_ARG(Ptot < (1ll << 31) && (long long)Cin * K < (1ll << 31), "conv1d: problem too large");
         const int ceff = gated ? Cout / 2 : Cout;                  // channels a CTA row tile is cut from
