@@ -463,12 +463,14 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvP
 // 32 - 192 channels; vq2.py:723-729 -> modules.py:224-318): 90 of the ~150 convolutions of an encode and its critical path.  The
 // implicit-GEMM kernels above rebuild the im2col tile element by element -- (ci, k) bookkeeping, bounds tests and a 4-byte cp.async per
 // element, every element fetched K times -- so on these layers FFMA was 28 % of the instruction stream (profiles/r1n_conv_pipe_ncu_full.txt).
-// Here a CTA stages, per 16 input channels, the input WINDOW [16][32 J + (K-1) DIL] once (each sample fetched once, leaky ReLU applied as
+// Here a CTA stages, per 16 (K = 11: 8) input channels, the input WINDOW [16][32 J + (K-1) DIL] once (each sample fetched once, leaky ReLU applied as
 // it lands) and the weight slab [32 channels][16 K]; a thread owns 8 output channels x J positions (t = tx + 32 j: conflict-free scalar
 // reads of the window, broadcast reads of the weights) and runs the fully unrolled (k) loop: 8 + J shared-memory loads per 8 J FFMAs.  Stages are double-buffered with cp.async.  The accumulation order r = ci * K + k is the implicit GEMM's: bit-identical output.
-constexpr int DC_CI = 16;
+// input channels per stage: 16, or 8 for the K = 11 layers (68 KB of staging at 16 allowed only 3 CTAs per SM)
+template <int K> struct DcStage { static constexpr int CI = K >= 11 ? 8 : 16; };
 template <int K, int DIL, int J>
 struct DirectConv {
+    static constexpr int DC_CI = DcStage<K>::CI;
     static constexpr int TP = 32 * J;                     // positions per CTA
     static constexpr int W = TP + (K - 1) * DIL;          // input window per channel
     static constexpr int WP = (W + 3) & ~3;               // row pitch
@@ -486,14 +488,14 @@ __global__ void __launch_bounds__(128) conv1d_direct_kernel(const ConvParams p) 
     const int b = blockIdx.z, t0 = blockIdx.x * C::TP, co0 = blockIdx.y * 32;
     const float* xb = p.x + (size_t)b * p.Cin * p.Tin;
     const int in0 = t0 - p.pad;
-    const int nst = (p.Cin + DC_CI - 1) / DC_CI;
+    const int nst = (p.Cin + C::DC_CI - 1) / C::DC_CI;
     const bool lrelu = p.pre_lrelu != 0;
 
     auto issue = [&](int s) {
         float* xs = dc_smem + (s & 1) * (C::XS + C::WS);
         float* ws = xs + C::XS;
-        const int c0 = s * DC_CI;
-        for (int i = tid; i < DC_CI * C::W; i += 128) {
+        const int c0 = s * C::DC_CI;
+        for (int i = tid; i < C::DC_CI * C::W; i += 128) {
             const int ci = i / C::W, u = i - ci * C::W;
             const int c = c0 + ci, ti = in0 + u;
             const bool ok = c < p.Cin && ti >= 0 && ti < p.Tin;
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(128) conv1d_direct_kernel(const ConvParams p) 
         cp_async_wait<0>();                                  // stage s has landed (this thread's copies)
         float* xs = dc_smem + (s & 1) * (C::XS + C::WS);
         if (lrelu) {                                         // once per sample, by the thread that copied it
-            for (int i = tid; i < DC_CI * C::W; i += 128) {
+            for (int i = tid; i < C::DC_CI * C::W; i += 128) {
                 const int ci = i / C::W, u = i - ci * C::W;
                 float* e = xs + ci * C::WP + u;
                 const float v = *e;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(128) conv1d_direct_kernel(const ConvParams p) 
         if (s + 1 < nst) issue(s + 1);                       // into the buffer stage s - 1 used
         cp_async_commit();
         const float* ws = xs + C::XS;
-        const int cimax = min(DC_CI, p.Cin - s * DC_CI);
+        const int cimax = min(C::DC_CI, p.Cin - s * C::DC_CI);
         for (int ci = 0; ci < cimax; ++ci) {
             const float* xr = xs + ci * C::WP + tx;
             const float* wr = ws + (ty * 8) * C::WPITCH + ci * K;
