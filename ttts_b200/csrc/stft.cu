@@ -348,6 +348,7 @@ int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t
     const int F = 1 + (L + 2 * pad - n_fft) / hop;
     TTTS_CHECK_ARG(F >= 1 && F == n_frames, "stft: frame count mismatch (expected %d, got %d)", F, n_frames);
     TTTS_CHECK_ARG(!mel_out || (band_lo && band_off && band_w && n_mels > 0), "stft: mel requested without a filterbank");
+    TTTS_CHECK_ARG(B >= 1 && B <= 65535, "stft: batch %d outside [1, 65535] (one grid row per clip)", B);
     int log2_half = 0;
     while ((1 << log2_half) < (n_fft >> 1)) ++log2_half;
     const int N2 = n_fft >> 1;
