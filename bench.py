@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg3": dict(layers=24, model_dim=1024, heads=16, B=32, TL=128, CL=1024),
     "cfg2": dict(layers=12, model_dim=512, heads=8, B=8, TL=128, CL=512),
+    "tiny": dict(layers=2, model_dim=128, heads=2, B=2, TL=16, CL=32),        # tests/test_bench_contract_cpu.py only: not a bench configuration
 }
 GPT_KW = dict(max_text_tokens=800, max_mel_tokens=1600, number_text_tokens=256, start_text_token=255, number_mel_codes=1026,
               start_mel_token=1024, stop_mel_token=1025)
