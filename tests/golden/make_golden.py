@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, vq.npz, mel.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -79,6 +79,32 @@ def gpt_case(gm, name, cfg_over, B, TL, CL, text_lengths=None, wav_lengths=None,
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "loss_text %.6f loss_mel %.6f" % (float(loss_text), float(loss_mel)), "->", path, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+def generate_case(gm):
+    """Greedy `inference_speech` of the REAL reference (ttts/gpt/model.py:533-562, kv_cache=False as in ttts/api_zh.py:51).  transformers 5
+    no longer mixes GenerationMixin into PreTrainedModel, so it is appended to the bases of the reference's GPT2InferenceModel here (a shim
+    in the sense of SURVEY.md Appendix D: nothing under /root/reference is modified).  Also stores the last-position logits of the prompt."""
+    from transformers import GenerationMixin
+    from oracle import gpt_oracle as O
+    if not hasattr(gm.GPT2InferenceModel, "generate"):
+        gm.GPT2InferenceModel.__bases__ = gm.GPT2InferenceModel.__bases__ + (GenerationMixin,)
+    cfg = O.default_config(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=60)
+    params = O.init_params(cfg, seed=0)
+    kw = {k: cfg[k] for k in ("layers", "model_dim", "heads", "max_text_tokens", "max_mel_tokens", "number_text_tokens", "start_text_token",
+                              "number_mel_codes", "start_mel_token", "stop_mel_token")}
+    model = gm.UnifiedVoice(**kw, use_mel_codes_as_input=True, train_solo_embeddings=False).eval()
+    model.load_state_dict({k: v.clone() for k, v in params.items()})
+    model.post_init_gpt2_config(use_deepspeed=False, kv_cache=False, half=False)
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, 255, (2, 9), generator=g)
+    cond = torch.randint(0, 1024, (2, 6), generator=g)
+    with torch.no_grad():
+        greedy = model.inference_speech(text, cond, max_generate_length=12, do_sample=False)
+        rep = model.inference_speech(text, cond, max_generate_length=12, do_sample=False, repetition_penalty=2.0)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "gpt_generate.npz"), cfg_json=np.array(repr(cfg)), seed=0, text=text.numpy(),
+                        cond=cond.numpy(), greedy=greedy.numpy(), greedy_rep2=rep.numpy())
+    print("gpt_generate: greedy", greedy.tolist(), "rep2", rep.tolist())
 
 
 def vq_case():
@@ -210,6 +236,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "generate":
+        generate_case(gm)
+        sys.exit(0)
     tiny = dict(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
     gpt_case(gm, "gpt_tiny", tiny, B=2, TL=12, CL=24)
     # ragged: clipping + set_mel_padding paths (wav_lengths//1024+1 < CL for some rows)
@@ -217,6 +246,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_case()
         sys.exit(0)
+    generate_case(gm)
     vq_case()
     mel_case()
     encoder_case()

@@ -211,6 +211,29 @@ def test_cfg3_full_size_properties():
     assert abs(fd - an) <= 0.1 * abs(an), (fd, an, lp, lmn)
 
 
+def assert_generated_like_reference(gen, want, cond, text, params, cfg, tol_rel=0.02, repetition_penalty=1.0):
+    """gen / want: [B, n] generated codes (ours / the REAL reference's, tests/golden/gpt_generate.npz).  Rows must agree token for token up to
+    the first position where the fp32 oracle, teacher-forced on OUR row, rates both candidates within the stated bf16 logit tolerance (a
+    near-tie; after it the two greedy continuations legitimately differ)."""
+    gen, want = gen.cpu(), torch.as_tensor(want)
+    m = cond.shape[1]
+    for b in range(gen.shape[0]):
+        n = min(gen.shape[1], want.shape[1])
+        diff = (gen[b, :n] != want[b, :n]).nonzero()
+        if diff.numel() == 0:
+            continue
+        j = int(diff[0])
+        full = torch.cat([cond[b], gen[b]])
+        _, _, logits = O.forward(params, cfg, text[b:b + 1], torch.tensor([text.shape[1]]), full[None].clone(), torch.tensor([(full.shape[0] + 1) * 1024]))
+        col = torch.as_tensor(logits)[0][:, m + j].float()
+        scale = float(col.abs().max())
+        if repetition_penalty != 1.0:                 # compare what the arg-max saw: HF's input_ids = 1 per text slot, start_mel, codes so far
+            from ttts_b200.gpt import sampling as S
+            ids = torch.cat([torch.ones(text.shape[1] + 2, dtype=torch.int64), torch.tensor([cfg["start_mel_token"]]), full[:m + j]])
+            col = S.repetition_penalty_(col[None].clone(), ids[None], repetition_penalty)[0]
+        assert abs(float(col[gen[b, j]] - col[want[b, j]])) <= tol_rel * scale + 1e-3, (b, j, int(gen[b, j]), int(want[b, j]))
+
+
 def test_inference_speech_greedy_matches_oracle():
     """ttts/gpt/model.py:533-562 (kv_cache=False): every greedily chosen code is, under teacher forcing in the fp32 oracle, the arg-max of the
     oracle's logits up to the stated bf16 logit tolerance; shapes / stop handling follow HF generate."""
@@ -222,6 +245,12 @@ def test_inference_speech_greedy_matches_oracle():
     cond = torch.randint(0, 1024, (2, 6), generator=g)
     gen = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12)
     assert gen.dtype == torch.int64 and gen.shape[0] == 2 and 1 <= gen.shape[1] <= 12
+    # against tokens generated by the REAL reference's inference_speech for the same prompt (tests/golden/make_golden.py generate)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt_generate.npz"))
+    assert np.array_equal(z["text"], text.numpy()) and np.array_equal(z["cond"], cond.numpy())
+    assert_generated_like_reference(gen, z["greedy"], cond, text, params, cfg)
+    rep = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12, repetition_penalty=2.0)
+    assert_generated_like_reference(rep, z["greedy_rep2"], cond, text, params, cfg, repetition_penalty=2.0)
     for b in range(2):
         full = torch.cat([cond[b], gen[b].cpu()])
         n = full.shape[0]
@@ -235,9 +264,12 @@ def test_inference_speech_greedy_matches_oracle():
             col = logits[:, i]
             assert col.max() - col[full[i]] <= 0.02 * col.abs().max() + 1e-3, (b, i)
             done = bool(full[i] == cfg["stop_mel_token"])
-    # greedy is deterministic; num_return_sequences expands neighbours-together like HF
-    gen3 = m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12, num_return_sequences=3)
-    assert gen3.shape[0] == 6 and torch.equal(gen3[0], gen3[2]) and torch.equal(gen3[3], gen3[5]) and torch.equal(gen3[0, :gen.shape[1]], gen[0])
+    # num_return_sequences: refused for greedy search exactly as HF does, expands the batch when sampling
+    with pytest.raises(ValueError):
+        m.inference_speech(text.cuda(), cond.cuda(), max_generate_length=12, num_return_sequences=3)
+    gen3 = m.inference_speech(text.cuda(), cond.cuda(), do_sample=True, top_p=0.8, max_generate_length=5, num_return_sequences=3,
+                              generator=torch.Generator(device="cuda").manual_seed(11))
+    assert gen3.shape[0] == 6 and 1 <= gen3.shape[1] <= 5
     # sampling: seeded, top_k = 1 degenerates to greedy, a large repetition penalty forbids immediate repeats of a positive-score token
     kw = dict(do_sample=True, top_p=0.8, temperature=0.8, repetition_penalty=2.0, max_generate_length=12)
     a = m.inference_speech(text.cuda(), cond.cuda(), generator=torch.Generator(device="cuda").manual_seed(3), **kw)

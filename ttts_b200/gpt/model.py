@@ -300,6 +300,9 @@ class UnifiedVoice(nn.Module):
         kw.pop("length_penalty", None)                               # beam search only
         if kw.pop("num_beams", 1) != 1:
             raise NotImplementedError("beam search is not used by the reference's call (ttts/api_zh.py:78-86) and is not implemented")
+        if not do_sample and num_return_sequences != 1:              # HF GenerationConfig.validate
+            raise ValueError("Greedy methods (do_sample != True) without beam search do not support `num_return_sequences` different than 1 "
+                             "(got %d)." % num_return_sequences)
         if kw:
             raise TypeError("unsupported generate() arguments: %s" % sorted(kw))
         L.require_cuda(text_inputs, mel_codes)
@@ -324,27 +327,17 @@ class UnifiedVoice(nn.Module):
             raise IndexError("prompt longer than the position tables (max_text_tokens=%d, max_mel_tokens=%d)" % (self.max_text_tokens, self.max_mel_tokens))
         codes = torch.full((B, max(n_max, m) + 1), self.stop_mel_token, dtype=torch.int64, device=dev)
         codes[:, :m] = cond
-        # what HF's processors see as input_ids: `1` for every text position (model.py:541), then start_mel + codes so far
-        ids = torch.cat([torch.ones(B, TL + 2, dtype=torch.int64, device=dev),
-                         torch.full((B, 1), self.start_mel_token, dtype=torch.int64, device=dev), codes], dim=1)
         text = text.contiguous()
         eng = self._engine()
         eng.refresh_shadow(force=not eng.trust_version)
         ld = L.lib().ttts_gpt_logits_ld(self.number_mel_codes)
-        unfinished = torch.ones(B, dtype=torch.bool, device=dev)
-        n = m
-        while n < n_max:
+
+        def step_logits(n):
             wav = torch.full((B,), (n + 1) * self.mel_length_compression, dtype=torch.int64, device=dev)      # nothing is stop-padded
             eng.forward(text, codes, wav, TL, n, save=False)
             logits = eng.ws_view(E.WS_MEL_LOGITS, B, TL, n, False, torch.bfloat16, (B, n + 2, ld))
-            scores = logits[:, n, :self.number_mel_codes].float()    # position of the last real token (mel_in[n])
-            scores = S.process_logits(scores, ids[:, :TL + 3 + n], do_sample, temperature, top_k, top_p, repetition_penalty, typical_sampling, typical_mass)
-            nxt = S.select_tokens(scores, do_sample, generator)
-            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, self.stop_mel_token))
-            codes[:, n] = nxt
-            ids[:, TL + 3 + n] = nxt
-            unfinished = unfinished & (nxt != self.stop_mel_token)
-            n += 1
-            if not bool(unfinished.any()):                           # the same host sync HF's stopping criteria make every step
-                break
+            return logits[:, n, :self.number_mel_codes].float()      # position of the last real token (mel_in[n])
+
+        n = S.generate_codes(step_logits, codes, m, n_max, TL + 2, self.start_mel_token, self.stop_mel_token, do_sample, temperature, top_k, top_p,
+                             repetition_penalty, typical_sampling, typical_mass, generator)
         return codes[:, mel_codes.shape[1]:n].clone()                # gen[:, trunc_index:] (input_tokens, if any, included -- as in the reference)

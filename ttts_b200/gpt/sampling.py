@@ -80,3 +80,31 @@ def select_tokens(scores, do_sample, generator=None):
         return torch.argmax(scores, dim=-1)
     probs = torch.softmax(scores, dim=-1)
     return torch.multinomial(probs, num_samples=1, generator=generator).squeeze(1)
+
+
+def generate_codes(step_logits, codes, n_prompt, n_max, text_positions, start_mel_token, stop_mel_token, do_sample=False, temperature=1.0,
+                   top_k=None, top_p=None, repetition_penalty=1.0, typical_sampling=False, typical_mass=0.9, generator=None):
+    """The token loop of `GPT2InferenceModel.generate` as the reference drives it (ttts/gpt/model.py:533-562), independent of how logits
+    are produced: `step_logits(n) -> [B, V] float32` returns the mel logits at the last of the n codes currently in `codes[:, :n]`
+    (`codes` [B, >= n_max + 1] int64 is updated in place, pre-filled with the conditioning codes in its first `n_prompt` columns).
+    What HF's processors see as `input_ids` is rebuilt here: the id 1 for each of the `text_positions` text slots (model.py:541), then
+    start_mel_token, then the codes so far.  Finished rows keep emitting stop_mel_token (pad_token_id = eos_token_id, model.py:555-556).
+    Returns the number of code columns filled."""
+    B, dev = codes.shape[0], codes.device
+    ids = torch.cat([torch.ones(B, text_positions, dtype=torch.int64, device=dev),
+                     torch.full((B, 1), start_mel_token, dtype=torch.int64, device=dev), codes], dim=1)
+    unfinished = torch.ones(B, dtype=torch.bool, device=dev)
+    n = n_prompt
+    while n < n_max:
+        scores = step_logits(n)
+        scores = process_logits(scores, ids[:, :text_positions + 1 + n], do_sample, temperature, top_k, top_p, repetition_penalty,
+                                typical_sampling, typical_mass)
+        nxt = select_tokens(scores, do_sample, generator)
+        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, stop_mel_token))
+        codes[:, n] = nxt
+        ids[:, text_positions + 1 + n] = nxt
+        unfinished = unfinished & (nxt != stop_mel_token)
+        n += 1
+        if not bool(unfinished.any()):                               # the same host sync HF's stopping criteria make every step
+            break
+    return n
