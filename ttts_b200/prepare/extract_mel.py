@@ -14,9 +14,10 @@ Only clips of the same length share a batch: the front end pads each clip by ref
 depend on where it ends.  Equal-length batching keeps every file bit-identical to a batch-of-one run.
 """
 import os
-from collections import defaultdict
 
 import torch
+
+from .extract_vq import plan_batches          # equal-length clips together, at most batch_size per batch, longest first
 
 
 def condition_wav(wav):
@@ -27,15 +28,6 @@ def condition_wav(wav):
     if wav.shape[-1] <= 512:          # reflect padding of n_fft / 2 = 512 samples needs a longer clip (torch raises for these too)
         return None
     return wav
-
-
-def plan_batches(lengths, batch_size=64):
-    """Equal-length clips together, at most `batch_size` per batch, longest first.  lengths[i] is None for skipped clips."""
-    groups = defaultdict(list)
-    for i, n in enumerate(lengths):
-        if n is not None:
-            groups[int(n)].append(i)
-    return [idx[s:s + batch_size] for n in sorted(groups, reverse=True) for idx in [groups[n]] for s in range(0, len(idx), batch_size)]
 
 
 def save_mel(path, mel):
