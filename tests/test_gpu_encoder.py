@@ -85,6 +85,22 @@ def test_encoder_vs_reference_golden(model, enc):
     assert np.array_equal(codes.reshape(-1), want)
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_CONV_TC") != "1", reason="experimental tensor-core convolution (conv1d_tc.cu): opt-in, round-2 work in progress")
+@pytest.mark.parametrize("C,K,dil,T", [(32, 3, 1, 2304), (32, 11, 5, 2304), (64, 7, 3, 288), (64, 11, 1, 300)])
+def test_conv1d_tc_vs_torch(C, K, dil, T):
+    """split-bf16 tcgen05 convolution vs torch fp32: relative error ~1e-5 (tools/split_bf16_conv_study.py), bias / residual / scale fused"""
+    from ttts_b200.vqvae.encoder import conv1d
+    g = torch.Generator(device="cuda").manual_seed(C + K + dil)
+    x = torch.randn(3, C, T, device="cuda", generator=g)
+    w = 0.1 * torch.randn(C, C, K, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    res = torch.randn(3, C, T, device="cuda", generator=g)
+    pad = dil * (K - 1) // 2
+    got = conv1d(x, w, b, dil=dil, pad=pad, pre_lrelu=True, resid=res, out_scale=0.5)
+    want = (torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x, 0.1), w, b, dilation=dil, padding=pad) + res) * 0.5
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-4
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

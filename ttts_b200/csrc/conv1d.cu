@@ -16,6 +16,10 @@
 
 namespace ttts {
 
+// conv1d_tc.cu (experimental, off unless TTTS_CONV_TC=1): returns -1 when it does not take the layer
+int conv1d_tc_try(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int stride, int dil, int pad,
+                  int pre_lrelu, const float* resid, float out_scale, int accumulate, const float* mask, int post, cudaStream_t st);
+
 constexpr int CV_CO = 64, CV_T = 64, CV_CI = 16, CV_THREADS = 256;
 
 struct ConvParams {
@@ -689,6 +693,8 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
     static int use_v1 = -1;
     if (use_v1 < 0) { const char* e = getenv("TTTS_CONV_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     if (!use_v1) {
+        const int rc_tc = conv1d_tc_try(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, st);
+        if (rc_tc >= 0) return rc_tc;                              // experimental tensor-core path, only with TTTS_CONV_TC=1 (conv1d_tc.cu)
         const int rc_direct = conv1d_direct_try(p, st);
         if (rc_direct >= 0) return rc_direct;
         const long long Ptot = (long long)B * Tout;
