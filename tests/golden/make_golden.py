@@ -220,6 +220,31 @@ def encoder_case():
         a = net.enc_p.down_pre(wav.unsqueeze(1))
         a1 = net.enc_p.downs[0](a)
         r0 = net.enc_p.resblocks[0](a1)
+    # gradients of the encode half (the oracle for the next scope row, the encoder's backward): L = <z, R> + 0.5 mean(x^2) with a seeded R;
+    # per parameter tensor the L2 norm of its gradient and its projection on a seeded direction, plus a few small tensors in full
+    gR = torch.Generator().manual_seed(123)
+    R = torch.randn(3, 192, 36, generator=gR)
+    for prm in net.parameters():
+        prm.grad = None
+    ge_g = net.ref_enc(spec * y_mask, y_mask)
+    _, m_g, logs_g = net.enc_p(spec, wav.unsqueeze(1), y_mask, g=ge_g)
+    z_g = (m_g + eps * torch.exp(logs_g)) * y_mask
+    x_g = net.proj(z_g)
+    loss = (z_g * R).sum() + 0.5 * (x_g ** 2).mean()
+    loss.backward()
+    gnames, gnorm, gproj = [], [], []
+    full = {}
+    for k, prm in net.named_parameters():
+        if k.startswith("quantizer."):
+            continue
+        gk = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(gnames)))
+        gnames.append(k); gnorm.append(float(gk.norm())); gproj.append(float((gk * d).sum()))
+        if gk.numel() <= 4096 and len(full) < 12:
+            full["gradfull/" + k] = gk.numpy().copy()
+    path = os.path.join(ROOT, "tests", "golden", "encoder_grads.npz")
+    np.savez_compressed(path, names=np.array(gnames), norm=np.array(gnorm), proj=np.array(gproj), loss=float(loss), **full)
+    print("encoder grads ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), len(gnames), "tensors, loss %.6f" % float(loss))
     path = os.path.join(ROOT, "tests", "golden", "encoder.npz")
     np.savez_compressed(path, wav=wav.numpy(), lengths=lengths.numpy(), eps=eps.numpy(), E=E, ge=ge.numpy(), m=m.numpy(), logs=logs.numpy(),
                         z=z.numpy(), x=x.numpy(), codes=codes.numpy(), quantized=quantized.numpy(),

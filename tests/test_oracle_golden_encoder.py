@@ -43,3 +43,37 @@ def test_encoder_oracle_matches_reference(enc):
 def test_masked_frames_are_zero(enc):
     z = enc["z"]
     assert np.all(z[1, :, 30:] == 0) and np.all(z[2, :, 17:] == 0)
+
+
+def test_encoder_oracle_gradients_match_reference(enc, golden_dir):
+    """The oracle for the NEXT scope row (the encoder's backward): autograd through the functional encoder oracle reproduces
+    the gradients of the REAL reference modules (tests/golden/encoder_grads.npz: per parameter tensor the L2 norm of the gradient and its
+    projection on a seeded direction, a dozen small tensors in full) for L = <z, R> + 0.5 mean(x^2)."""
+    g = np.load(os.path.join(golden_dir, "encoder_grads.npz"))
+    P = {k: v.clone().requires_grad_(True) for k, v in EO.init_params(seed=5).items()}
+    wav = torch.tensor(enc["wav"])
+    spec = torch.tensor(V.spectrogram(enc["wav"]))
+    o = EO.encode(P, spec, wav, lengths=torch.tensor(enc["lengths"]), eps=torch.tensor(enc["eps"]))
+    R = torch.randn(3, 192, 36, generator=torch.Generator().manual_seed(123))
+    loss = (o["z"] * R).sum() + 0.5 * (o["x"] ** 2).mean()
+    assert abs(float(loss) - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
+    loss.backward()
+    names = [str(n) for n in g["names"]]
+    assert set(names) == set(P.keys())
+    num = den = 0.0
+    floor = 1e-6 * float(np.sqrt((g["norm"] ** 2).sum()))        # gradients that are zero in exact arithmetic (e.g. the attention key bias) are fp32 noise
+    for i, k in enumerate(names):
+        gk = P[k].grad if P[k].grad is not None else torch.zeros_like(P[k])
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(g["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(g["proj"][i])) <= 1e-2 * scale + floor, k
+        num += (float(gk.norm()) - float(g["norm"][i])) ** 2
+        den += float(g["norm"][i]) ** 2
+    assert (num / den) ** 0.5 < 1e-3
+    for key in g.files:
+        if key.startswith("gradfull/"):
+            k = key[len("gradfull/"):]
+            ref = g[key]
+            got = P[k].grad.numpy()
+            assert np.linalg.norm(got - ref) <= 2e-3 * np.linalg.norm(ref) + floor, k
