@@ -107,6 +107,36 @@ def generate_case(gm):
     print("gpt_generate: greedy", greedy.tolist(), "rep2", rep.tolist())
 
 
+def decoder_case():
+    """The REAL reference Generator (ttts/vqvae/vq2.py:341-416, hyper-parameters of vqvae/config.json) on CPU: waveform for a seeded latent,
+    and per parameter tensor the gradient norm / projection of L = <y, R>.  Oracle for the next scope row (decoder of the VQ-VAE-GAN step)."""
+    from oracle import decoder_oracle as DO
+    from ttts.vqvae.vq2 import Generator
+    net = Generator(192, "1", [3, 7, 11], [[1, 3, 5]] * 3, [10, 8, 2, 2, 2], 512, [16, 16, 8, 2, 2], gin_channels=512).eval()
+    P = DO.init_params(seed=9)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(P.keys()), sorted(set(sd.keys()) ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P)
+    g0 = torch.Generator().manual_seed(31)
+    z = torch.randn(2, 192, 6, generator=g0)
+    gcond = torch.randn(2, 512, 1, generator=g0)
+    y = net(z, g=gcond)
+    R = torch.randn(y.shape, generator=torch.Generator().manual_seed(32))
+    loss = (y * R).sum()
+    loss.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net.named_parameters():
+        gk = prm.grad
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    path = os.path.join(ROOT, "tests", "golden", "decoder.npz")
+    np.savez_compressed(path, z=z.numpy(), g=gcond.numpy(), y=y.detach().numpy(), loss=float(loss), names=np.array(names), norm=np.array(norm),
+                        proj=np.array(proj))
+    print("decoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), tuple(y.shape), "loss %.5f" % float(loss))
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -261,6 +291,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "decoder":
+        decoder_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
@@ -272,6 +305,7 @@ if __name__ == "__main__":
         encoder_case()
         sys.exit(0)
     generate_case(gm)
+    decoder_case()
     vq_case()
     mel_case()
     encoder_case()
