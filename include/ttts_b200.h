@@ -150,6 +150,35 @@ int ttts_gpt_forward(const ttts_gpt_io* io, void* stream);
 int ttts_gpt_backward(const ttts_gpt_io* io, int32_t stage_begin, int32_t stage_end, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * KV-cache decode: autoregressive code generation, one new code per sequence per call -- the cached branch of
+ * GPT2InferenceModel.forward (ttts/gpt/model.py:106-171 with past_key_values, :144-147 single-token embedding) as
+ * UnifiedVoice.inference_speech drives it (:533-562).  The cache holds, per layer, K and V of every position so far:
+ * bf16 [layers][2 (k|v)][B][heads][T_max][64].  Fill it from a prompt with ttts_gpt_forward(save_acts = 1) followed by
+ * ttts_gpt_kv_prefill, then call ttts_gpt_decode_step once per generated code.
+ * ------------------------------------------------------------------------------------------ */
+int64_t ttts_gpt_kv_bytes(const ttts_gpt_config* cfg, int32_t B, int32_t T_max);
+int64_t ttts_gpt_decode_workspace_bytes(const ttts_gpt_config* cfg, int32_t B);
+/* copy K / V of sequence positions [0, n_pos) of every layer out of the workspace of a ttts_gpt_forward(save_acts = 1) pass */
+int ttts_gpt_kv_prefill(const ttts_gpt_io* io, void* kv, int64_t kv_bytes, int32_t T_max, int32_t n_pos, void* stream);
+
+typedef struct {
+    ttts_gpt_config cfg;
+    int32_t B, T_max;                  /* sequences ; cache capacity in positions                                          */
+    int32_t text_positions;            /* TL + 2: cache slots taken by [start, text..., stop]                              */
+    int32_t pos_shift;                 /* 0: mel position index = the uncached path's (model.py:134-142) ;
+                                          1: the index the reference's cached branch computes (model.py:144-147), one later */
+    const int64_t* codes; int32_t ld_codes;   /* [B, >= n] codes so far; the token fed is codes[b, slot - text_positions - 1]   */
+    int32_t* slot;                     /* device scalar: cache slot of the token being fed (= positions cached so far);
+                                          read by every kernel of the step and advanced by one at its end, so a captured
+                                          step (CUDA graph) replays for the next position unchanged                        */
+    const float* params; const void* params16;
+    void* kv; int64_t kv_bytes;
+    void* workspace; int64_t workspace_bytes;
+    float* logits;                     /* out: fp32 [B, n_mel_vocab] mel-head logits of the fed token (bf16-rounded values) */
+} ttts_gpt_decode;
+int ttts_gpt_decode_step(const ttts_gpt_decode* args, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * step tail: get_grad_norm + clip_grad_norm_(1.0) + AdamW (ttts/gpt/train.py:22-31,114-118)
  * ------------------------------------------------------------------------------------------ */
 int ttts_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);

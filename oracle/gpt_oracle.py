@@ -146,6 +146,8 @@ def gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16=False, collect=None):
         q = q.view(B, T, H, hd).transpose(1, 2)
         k = k.view(B, T, H, hd).transpose(1, 2)
         v = v.view(B, T, H, hd).transpose(1, 2)
+        if collect is not None:
+            collect["k%d" % i], collect["v%d" % i] = k, v
         att = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
         att = att.masked_fill(~causal, float("-inf"))
         att = torch.softmax(att, dim=-1)
@@ -186,6 +188,60 @@ def forward(params, cfg, text_inputs, text_lengths, mel_codes, wav_lengths, clip
     loss_text = F.cross_entropy(text_logits, text_tgt.long())
     loss_mel = F.cross_entropy(mel_logits, mel_tgt.long())
     return loss_text.mean(), loss_mel.mean(), mel_logits
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# KV-cache decode: the cached branch of GPT2InferenceModel.forward (ttts/gpt/model.py:106-171) as a plain incremental
+# restatement.  The cache has the layout the CUDA path uses, [layers, 2 (k|v), B, heads, T_max, head_dim].
+# ---------------------------------------------------------------------------------------------------------------------
+def kv_prefill(params, cfg, text_in, mel_in, T_max, emulate_bf16=False):
+    """Full forward over the prompt [text_in ; mel_in] (both already start/stop padded, mel_in = [start_mel, codes...]).
+    Returns (cache, slot, logits of the last position [B, V_mel]); slot = number of cached positions."""
+    col = {}
+    enc = gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16, col)
+    B, T = enc.shape[0], enc.shape[1]
+    H = cfg["heads"]
+    hd = cfg["model_dim"] // H
+    assert T <= T_max
+    cache = torch.zeros(cfg["layers"], 2, B, H, T_max, hd, dtype=enc.dtype)
+    for i in range(cfg["layers"]):
+        cache[i, 0, :, :, :T] = col["k%d" % i]
+        cache[i, 1, :, :, :T] = col["v%d" % i]
+    r = (lambda t: t.to(torch.bfloat16).float()) if emulate_bf16 else (lambda t: t)
+    logits = r(_mm(enc[:, -1], params["mel_head.weight"].t(), emulate_bf16) + params["mel_head.bias"])
+    return cache, T, logits
+
+
+def kv_decode_step(params, cfg, cache, slot, tokens, text_positions, pos_shift=0, emulate_bf16=False):
+    """One cached step: `tokens` [B] int64 are the codes being fed, stored at cache slot `slot`.  Position embedding index of the token:
+    its index inside the mel segment (`slot - text_positions`, what the uncached path uses, model.py:134-142) + pos_shift; the reference's
+    cached branch uses `attention_mask.shape[1] - mel_len` = that index + 1 (model.py:144-147), i.e. pos_shift = 1.
+    Returns logits [B, V_mel]; the cache is updated in place (caller advances slot)."""
+    d, H = cfg["model_dim"], cfg["heads"]
+    hd = d // H
+    B = tokens.shape[0]
+    r = (lambda t: t.to(torch.bfloat16).float()) if emulate_bf16 else (lambda t: t)
+    pos = slot - text_positions + pos_shift
+    x = params["mel_embedding.weight"][tokens] + params["mel_pos_embedding.emb.weight"][pos]
+    for i in range(cfg["layers"]):
+        p = "gpt.h.%d." % i
+        h = layer_norm(x, params[p + "ln_1.weight"], params[p + "ln_1.bias"])
+        qkv = r(_mm(h, params[p + "attn.c_attn.weight"], emulate_bf16) + params[p + "attn.c_attn.bias"])
+        q, k, v = qkv.split(d, dim=1)
+        cache[i, 0, :, :, slot] = k.view(B, H, hd)
+        cache[i, 1, :, :, slot] = v.view(B, H, hd)
+        K, V = cache[i, 0, :, :, :slot + 1], cache[i, 1, :, :, :slot + 1]                # [B, H, n, hd]
+        att = torch.einsum("bhd,bhnd->bhn", q.view(B, H, hd), K) * (hd ** -0.5)
+        att = torch.softmax(att, dim=-1)
+        a = r(torch.einsum("bhn,bhnd->bhd", r(att), V)).reshape(B, d)
+        x = x + r(_mm(a, params[p + "attn.c_proj.weight"], emulate_bf16) + params[p + "attn.c_proj.bias"])
+        h = layer_norm(x, params[p + "ln_2.weight"], params[p + "ln_2.bias"])
+        f = r(_mm(h, params[p + "mlp.c_fc.weight"], emulate_bf16) + params[p + "mlp.c_fc.bias"])
+        g = r(gelu_new(f))
+        x = x + r(_mm(g, params[p + "mlp.c_proj.weight"], emulate_bf16) + params[p + "mlp.c_proj.bias"])
+    x = layer_norm(x, params["gpt.ln_f.weight"], params["gpt.ln_f.bias"])
+    x = layer_norm(x, params["final_norm.weight"], params["final_norm.bias"])
+    return r(_mm(x, params["mel_head.weight"].t(), emulate_bf16) + params["mel_head.bias"])
 
 
 def loss_and_grads(params, cfg, text_inputs, text_lengths, mel_codes, wav_lengths, text_weight=0.01, mel_weight=1.0,

@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -105,6 +105,52 @@ def generate_case(gm):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "gpt_generate.npz"), cfg_json=np.array(repr(cfg)), seed=0, text=text.numpy(),
                         cond=cond.numpy(), greedy=greedy.numpy(), greedy_rep2=rep.numpy())
     print("gpt_generate: greedy", greedy.tolist(), "rep2", rep.tolist())
+
+
+def kv_case(gm):
+    """Cached decoding of the REAL reference, stepped by hand: `GPT2InferenceModel.forward` (ttts/gpt/model.py:106-171) on the full prompt with
+    use_cache, then one id at a time with the returned `past_key_values` and an attention mask of the total length -- the call sequence HF 4.x
+    `generate` makes when `kv_cache=True` (under transformers 5.5 `generate` hands the reference's `prepare_inputs_for_generation` a non-empty
+    cache object on the first call, so the prompt is dropped; the model's own forward is unaffected, hence the manual stepping).  Pins the
+    position rule of the cached branch (:144-147: index = tokens in the mel segment INCLUDING the one being fed, one more than the uncached
+    branch gives the same token)."""
+    import torch.nn.functional as F
+    from oracle import gpt_oracle as O
+    cfg = O.default_config(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=60)
+    params = O.init_params(cfg, seed=0)
+    kw = {k: cfg[k] for k in ("layers", "model_dim", "heads", "max_text_tokens", "max_mel_tokens", "number_text_tokens", "start_text_token",
+                              "number_mel_codes", "start_mel_token", "stop_mel_token")}
+    model = gm.UnifiedVoice(**kw, use_mel_codes_as_input=True, train_solo_embeddings=False).eval()
+    model.load_state_dict({k: v.clone() for k, v in params.items()})
+    model.post_init_gpt2_config(use_deepspeed=False, kv_cache=True, half=False)
+    im = model.inference_model
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, 255, (2, 9), generator=g)
+    cond = torch.randint(0, 1024, (2, 6), generator=g)
+    steps = 6
+    with torch.no_grad():
+        ti = F.pad(text, (0, 1), value=model.stop_text_token)
+        ti, _ = model.build_aligned_inputs_and_targets(ti, model.start_text_token, model.stop_text_token)
+        emb = model.text_embedding(ti) + model.text_pos_embedding(ti)
+        im.store_mel_emb(emb)
+        mi, _ = model.build_aligned_inputs_and_targets(cond, model.start_mel_token, model.stop_mel_token)
+        fake = torch.ones(2, emb.shape[1] + mi.shape[1], dtype=torch.long)
+        fake[:, -mi.shape[1]:] = mi
+        out = im(input_ids=fake, past_key_values=None, use_cache=True, attention_mask=torch.ones_like(fake), return_dict=True)
+        pkv, lg, n = out.past_key_values, out.logits[:, -1], fake.shape[1]
+        logits, tokens = [lg.numpy()], []
+        for s in range(steps):
+            tok = lg.argmax(-1)
+            if s == 2:
+                tok = torch.tensor([7, 1000])          # rows diverge (greedy keeps them identical on this seed)
+            tokens.append(tok.numpy())
+            n += 1
+            out = im(input_ids=tok[:, None], past_key_values=pkv, use_cache=True, attention_mask=torch.ones(2, n, dtype=torch.long), return_dict=True)
+            pkv, lg = out.past_key_values, out.logits[:, -1]
+            logits.append(lg.numpy())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "gpt_kvstep.npz"), cfg_json=np.array(repr(cfg)), seed=0, text=text.numpy(),
+                        cond=cond.numpy(), tokens=np.stack(tokens), logits=np.stack(logits))
+    print("gpt_kvstep: tokens", np.stack(tokens).T.tolist())
 
 
 def decoder_case():
@@ -297,6 +343,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "kv":
+        kv_case(gm)
+        sys.exit(0)
     tiny = dict(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
     gpt_case(gm, "gpt_tiny", tiny, B=2, TL=12, CL=24)
     # ragged: clipping + set_mel_padding paths (wav_lengths//1024+1 < CL for some rows)
@@ -305,6 +354,7 @@ if __name__ == "__main__":
         encoder_case()
         sys.exit(0)
     generate_case(gm)
+    kv_case(gm)
     decoder_case()
     vq_case()
     mel_case()

@@ -140,12 +140,6 @@ static inline DropCfg site_drop(float p, uint64_t seed, int site, int layer) {
 }
 enum { SITE_EMBD = 0, SITE_ATTN_P = 1, SITE_ATTN_O = 2, SITE_MLP_O = 3 };
 
-#define TTTS_RUN(expr)              \
-    do {                            \
-        int _rc = (expr);           \
-        if (_rc != TTTS_OK) return _rc; \
-    } while (0)
-
 static int gemm(int M, int N, int K, const void* A, int lda, bool a_mn, const void* B, int ldb, bool b_mn, int epi, void* out, int ldo,
                 const float* bias, const void* aux, int ldaux, void* aux_out, int ldaux_out, int split_k, DropCfg drop, cudaStream_t st) {
     ttts_gemm_args g;
@@ -369,6 +363,33 @@ int gpt_backward(const ttts_gpt_io* io, int stage_begin, int stage_end, cudaStre
     return TTTS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// KV-cache decode support (kernels in gpt_decode.cu): parameter offsets and the cache fill from a saved forward
+// ---------------------------------------------------------------------------------------------------------
+int64_t gpt_param_off(const ttts_gpt_config& c, int tensor, int layer) {
+    if (tensor < 0 || tensor >= TTTS_P_COUNT || check_cfg(c) != TTTS_OK) return -1;
+    if (is_layer_tensor(tensor) && (layer < 0 || layer >= c.layers)) return -1;
+    return poff(make_layout(c), tensor, layer);
+}
+
+int gpt_kv_prefill(const ttts_gpt_io* io, void* kv, int64_t kv_bytes, int T_max, int n_pos, cudaStream_t st) {
+    Workspace w; ParamLayout P;
+    TTTS_RUN(validate_io(io, w, P));
+    TTTS_CHECK_ARG(io->save_acts, "kv prefill needs a forward run with save_acts=1 (every layer's c_attn output is kept)");
+    TTTS_CHECK_ARG(kv != nullptr && ((uintptr_t)kv & 15) == 0, "kv prefill: null / unaligned cache");
+    TTTS_CHECK_ARG(T_max >= n_pos && n_pos >= 1 && n_pos <= w.T, "kv prefill: %d positions (sequence %d, cache capacity %d)", n_pos, w.T, T_max);
+    TTTS_CHECK_ARG(kv_bytes >= gpt_kv_bytes(w.L, w.B, w.H, T_max), "kv prefill: cache too small (%lld < %lld)", (long long)kv_bytes,
+                   (long long)gpt_kv_bytes(w.L, w.B, w.H, T_max));
+    const uint8_t* ws = reinterpret_cast<const uint8_t*>(io->workspace);
+    bf16* cache = reinterpret_cast<bf16*>(kv);
+    const size_t half = (size_t)w.B * w.H * T_max * 64;
+    for (int l = 0; l < w.L; ++l) {
+        const bf16* qkv = reinterpret_cast<const bf16*>(ws + w.qkv + w.s_qkv * l);
+        TTTS_RUN(gpt_kv_fill_layer(qkv, w.B, w.T, w.d, w.H, n_pos, cache + (size_t)l * 2 * half, cache + (size_t)l * 2 * half + half, T_max, st));
+    }
+    return TTTS_OK;
+}
+
 }  // namespace ttts
 
 using namespace ttts;
@@ -422,6 +443,19 @@ int ttts_gpt_forward(const ttts_gpt_io* io, void* stream) { return gpt_forward(i
 int ttts_gpt_backward(const ttts_gpt_io* io, int32_t stage_begin, int32_t stage_end, void* stream) {
     return gpt_backward(io, stage_begin, stage_end, (cudaStream_t)stream);
 }
+
+int64_t ttts_gpt_kv_bytes(const ttts_gpt_config* cfg, int32_t B, int32_t T_max) {
+    if (!cfg || check_cfg(*cfg) != TTTS_OK || B < 1 || T_max < 1) return -1;
+    return gpt_kv_bytes(cfg->layers, B, cfg->heads, T_max);
+}
+int64_t ttts_gpt_decode_workspace_bytes(const ttts_gpt_config* cfg, int32_t B) {
+    if (!cfg || check_cfg(*cfg) != TTTS_OK || B < 1) return -1;
+    return gpt_decode_workspace_bytes(B, cfg->model_dim);
+}
+int ttts_gpt_kv_prefill(const ttts_gpt_io* io, void* kv, int64_t kv_bytes, int32_t T_max, int32_t n_pos, void* stream) {
+    return gpt_kv_prefill(io, kv, kv_bytes, T_max, n_pos, (cudaStream_t)stream);
+}
+int ttts_gpt_decode_step(const ttts_gpt_decode* args, void* stream) { return gpt_decode_step(args, (cudaStream_t)stream); }
 
 int ttts_cast_bf16(const float* src, void* dst, int64_t n, void* stream) { return cast_bf16(src, (bf16*)dst, (size_t)n, (cudaStream_t)stream); }
 int ttts_grad_norm(const float* grads, int64_t n, float* scratch, float* norm_out, void* stream) {

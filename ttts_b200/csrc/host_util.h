@@ -41,6 +41,12 @@ void prof_gemm_end(cudaStream_t st);
         ::ttts::count_launch();                                   \
     } while (0)
 
+#define TTTS_RUN(expr)                  \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != TTTS_OK) return _rc; \
+    } while (0)
+
 // TTTS_PDL=0 disables programmatic dependent launch (common.cuh: pdl_wait) for A/B measurements
 bool pdl_enabled();
 // <<<grid, block, smem, st>>> with the PDL attribute; only for kernels that call pdl_wait() before their first global-memory access

@@ -34,6 +34,20 @@ class GptIO(ctypes.Structure):
     ]
 
 
+class GptDecode(ctypes.Structure):
+    """ttts_gpt_decode (include/ttts_b200.h): one KV-cache decode step"""
+    _fields_ = [
+        ("cfg", GptConfig),
+        ("B", ctypes.c_int32), ("T_max", ctypes.c_int32), ("text_positions", ctypes.c_int32), ("pos_shift", ctypes.c_int32),
+        ("codes", ctypes.c_void_p), ("ld_codes", ctypes.c_int32),
+        ("slot", ctypes.c_void_p),
+        ("params", ctypes.c_void_p), ("params16", ctypes.c_void_p),
+        ("kv", ctypes.c_void_p), ("kv_bytes", ctypes.c_int64),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+        ("logits", ctypes.c_void_p),
+    ]
+
+
 # tensor ids (ttts_gpt_tensor)
 (P_TEXT_EMB, P_MEL_EMB, P_TEXT_POS, P_MEL_POS, P_LN1_W, P_LN1_B, P_ATTN_W, P_ATTN_B, P_PROJ_W, P_PROJ_B, P_LN2_W, P_LN2_B,
  P_FC_W, P_FC_B, P_PR_W, P_PR_B, P_LNF_W, P_LNF_B, P_FN_W, P_FN_B, P_TEXT_HEAD_W, P_TEXT_HEAD_B, P_MEL_HEAD_W, P_MEL_HEAD_B) = range(24)
@@ -59,6 +73,12 @@ def _setup_prototypes(lib):
     lib.ttts_gpt_logits_ld.argtypes = [ctypes.c_int32]
     lib.ttts_gpt_forward.argtypes = [ctypes.POINTER(GptIO), ctypes.c_void_p]
     lib.ttts_gpt_backward.argtypes = [ctypes.POINTER(GptIO), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    lib.ttts_gpt_kv_bytes.restype = ctypes.c_int64
+    lib.ttts_gpt_kv_bytes.argtypes = [ctypes.POINTER(GptConfig), ctypes.c_int32, ctypes.c_int32]
+    lib.ttts_gpt_decode_workspace_bytes.restype = ctypes.c_int64
+    lib.ttts_gpt_decode_workspace_bytes.argtypes = [ctypes.POINTER(GptConfig), ctypes.c_int32]
+    lib.ttts_gpt_kv_prefill.argtypes = [ctypes.POINTER(GptIO), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    lib.ttts_gpt_decode_step.argtypes = [ctypes.POINTER(GptDecode), ctypes.c_void_p]
     lib.ttts_cast_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.ttts_grad_norm.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.ttts_adamw_step.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 7 + [ctypes.c_int32, ctypes.c_void_p]
@@ -206,6 +226,63 @@ class Engine:
         if stage_end is None:
             stage_end = self.cfg.layers + 2
         L.check(L.lib().ttts_gpt_backward(ctypes.byref(io), stage_begin, stage_end, L.stream_ptr().value), "ttts_gpt_backward")
+
+    # ---- KV-cache decode (inference_speech with kv_cache=True) ----
+    def decode_setup(self, B, T_max):
+        """Allocate (or reuse) the cache [layers, 2, B, heads, T_max, 64] bf16, the decode workspace, the device slot counter and the logits."""
+        lib = L.lib()
+        st = getattr(self, "_dec", None)
+        if st is not None and st["B"] == B and st["T_max"] >= T_max:
+            return st
+        T_max = (T_max + 63) // 64 * 64
+        kv_bytes = lib.ttts_gpt_kv_bytes(ctypes.byref(self.cfg), B, T_max)
+        ws_bytes = lib.ttts_gpt_decode_workspace_bytes(ctypes.byref(self.cfg), B)
+        if kv_bytes <= 0 or ws_bytes <= 0:
+            raise L.TTTSError("decode size query failed: " + lib.ttts_last_error().decode())
+        self._dec = None
+        st = dict(B=B, T_max=T_max,
+                  kv=torch.empty(kv_bytes, dtype=torch.uint8, device=self.device),
+                  ws=torch.empty(ws_bytes, dtype=torch.uint8, device=self.device),
+                  slot=torch.zeros(1, dtype=torch.int32, device=self.device),
+                  logits=torch.zeros(B, self.cfg.n_mel_vocab, dtype=torch.float32, device=self.device),
+                  graph=None, graph_key=None)
+        self._dec = st
+        return st
+
+    def kv_prefill(self, io, n_pos):
+        """Copy K / V of positions [0, n_pos) of every layer out of the workspace of the forward(save=True) that produced `io`."""
+        st = self._dec
+        L.check(L.lib().ttts_gpt_kv_prefill(ctypes.byref(io), st["kv"].data_ptr(), st["kv"].numel(), st["T_max"], int(n_pos), L.stream_ptr().value),
+                "ttts_gpt_kv_prefill")
+        st["slot"].fill_(int(n_pos))
+
+    def decode_step(self, codes, text_positions, pos_shift=0, graph=False):
+        """Feed codes[:, slot - text_positions - 1] (slot lives on the device and is advanced by the step); returns the fp32 logits buffer [B, V]."""
+        st = self._dec
+        assert codes.dtype == torch.int64 and codes.stride(1) == 1 and codes.shape[0] == st["B"]
+        a = GptDecode()
+        a.cfg = self.cfg
+        a.B, a.T_max, a.text_positions, a.pos_shift = st["B"], st["T_max"], int(text_positions), int(pos_shift)
+        a.codes, a.ld_codes = codes.data_ptr(), codes.stride(0)
+        a.slot = st["slot"].data_ptr()
+        a.params, a.params16 = self.flat.data_ptr(), self.flat16.data_ptr()
+        a.kv, a.kv_bytes = st["kv"].data_ptr(), st["kv"].numel()
+        a.workspace, a.workspace_bytes = st["ws"].data_ptr(), st["ws"].numel()
+        a.logits = st["logits"].data_ptr()
+        if not graph:
+            L.check(L.lib().ttts_gpt_decode_step(ctypes.byref(a), L.stream_ptr().value), "ttts_gpt_decode_step")
+            return st["logits"]
+        # every kernel of the step reads the slot from device memory, so ONE captured step replays for every position
+        key = (codes.data_ptr(), codes.stride(0), int(text_positions), int(pos_shift))
+        if st["graph"] is None or st["graph_key"] != key:
+            g = torch.cuda.CUDAGraph()
+            slot0 = st["slot"].clone()
+            with torch.cuda.graph(g):
+                L.check(L.lib().ttts_gpt_decode_step(ctypes.byref(a), L.stream_ptr().value), "ttts_gpt_decode_step (capture)")
+            st["slot"].copy_(slot0)                  # capture does not execute; keep the counter where it was
+            st["graph"], st["graph_key"] = g, key
+        st["graph"].replay()
+        return st["logits"]
 
     # ---- step tail ----
     def grad_norm(self):

@@ -10,6 +10,7 @@ No CPU fallback: calling forward on a non-CUDA / non-sm_100 device raises.  Infe
 the training hot path (`text_first=False`, `raw_mels`, `return_attentions`, `inference_speech`) raise NotImplementedError.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -271,14 +272,20 @@ class UnifiedVoice(nn.Module):
         loss_text, loss_mel, mel_logits = _GPTStepFn.apply(self, text_inputs, mel_codes, wav_lengths, TL, CL, drop_p, seed, need_grad, *params)
         return loss_text, loss_mel, mel_logits.permute(0, 2, 1)
 
-    def post_init_gpt2_config(self, use_deepspeed=False, kv_cache=False, half=False):
+    def post_init_gpt2_config(self, use_deepspeed=False, kv_cache=False, half=False, kv_positions=None):
         """ttts/gpt/model.py:357-394 builds a HF GPT2InferenceModel around the trained modules; here generation runs on the same engine
-        as training, so there is nothing to build.  `kv_cache=True` is refused: the reference's cached path feeds a position index that
-        is off by one against its own uncached path (model.py:144-147 vs :134-142) and ttts/api_zh.py:51 uses kv_cache=False."""
+        as training, so there is nothing to build.  `kv_cache=False` (what ttts/api_zh.py:51 uses): every step re-runs the training forward
+        over the sequence so far.  `kv_cache=True`: one-token decode steps against cached keys / values (`ttts_gpt_decode_step`).  The
+        reference's cached branch indexes the position table one row later than its uncached branch does for the same token
+        (model.py:144-147 vs :134-142; pinned by tests/golden/gpt_kvstep.npz), so the two settings generate different codes THERE;
+        `kv_positions="reference"` (default with kv_cache=True) keeps that rule, `kv_positions="uncached"` runs the cached kernels with the
+        uncached branch's positions, i.e. the kv_cache=False results at a fraction of the cost."""
         if use_deepspeed or half:
             raise NotImplementedError("deepspeed / fp16 inference wrappers are not part of this path (the engine computes in bf16 already)")
-        if kv_cache:
-            raise NotImplementedError("kv_cache=True (position index differs from the uncached reference path); use kv_cache=False")
+        if kv_positions not in (None, "reference", "uncached"):
+            raise ValueError("kv_positions must be 'reference' or 'uncached'")
+        self._kv_cache = bool(kv_cache)
+        self._kv_pos_shift = 1 if (kv_cache and kv_positions in (None, "reference")) else 0
         self.eval()
 
     @torch.no_grad()
@@ -337,6 +344,22 @@ class UnifiedVoice(nn.Module):
             eng.forward(text, codes, wav, TL, n, save=False)
             logits = eng.ws_view(E.WS_MEL_LOGITS, B, TL, n, False, torch.bfloat16, (B, n + 2, ld))
             return logits[:, n, :self.number_mel_codes].float()      # position of the last real token (mel_in[n])
+
+        if getattr(self, "_kv_cache", False):
+            # cached decoding: the prompt [start, text, stop | start_mel, conditioning codes] goes through the training forward once (its
+            # per-layer c_attn outputs fill the cache), every later code is ONE decode step.  Cache slot of code j = TL + 3 + j.
+            use_graph = os.environ.get("TTTS_DECODE_GRAPH", "0") == "1"
+            eng.decode_setup(B, TL + 3 + max(n_max, m) + 1)
+            shift = self._kv_pos_shift
+
+            def step_logits(n):                                      # noqa: F811  (replaces the uncached closure above)
+                if n == m:
+                    wav = torch.full((B,), (m + 1) * self.mel_length_compression, dtype=torch.int64, device=dev)
+                    io = eng.forward(text, codes, wav, TL, m, save=True)
+                    eng.kv_prefill(io, TL + 3 + m)                   # text slots + start_mel + m codes
+                    logits = eng.ws_view(E.WS_MEL_LOGITS, B, TL, m, True, torch.bfloat16, (B, m + 2, ld))
+                    return logits[:, m, :self.number_mel_codes].float()
+                return eng.decode_step(codes, TL + 2, shift, graph=use_graph).clone()      # feeds codes[:, n - 1]
 
         n = S.generate_codes(step_logits, codes, m, n_max, TL + 2, self.start_mel_token, self.stop_mel_token, do_sample, temperature, top_k, top_p,
                              repetition_penalty, typical_sampling, typical_mass, generator)
