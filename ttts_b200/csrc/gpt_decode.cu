@@ -11,7 +11,7 @@
 // epilogues round (c_attn out, both c_proj outs before the residual add, c_fc pre-activation) ; gelu_new in packed bf16x2 ; attention
 // probabilities rounded to bf16 before P.V with an fp32 normaliser ; heads: bf16(acc + bias).
 //
-// Kernels per layer (7 launches; all small, all with programmatic dependent launch so the launch latencies overlap):
+// Kernels per layer (8 launches; all small, all with programmatic dependent launch so the launch latencies overlap):
 //   dec_rowop   (finalise the previous projection into the residual stream, or embed; LayerNorm -> bf16)      grid B
 //   dec_gemv    c_attn   partial sums over a K slice: part[s][b][n]                                           grid (N/256, S, B/BT)
 //   dec_attn    sum partials + bias -> q,k,v ; append k,v to the cache ; softmax(q K^T / 8) V                 grid (H, B)
@@ -21,10 +21,19 @@
 //   dec_gemv    mlp c_proj
 // then dec_rowop (residual add + ln_f + final_norm), dec_head (mel head), dec_advance (slot += 1).
 // Every kernel reads the current cache slot from DEVICE memory, so one recorded step (a CUDA graph) replays for every position.
+//
+// This file is also compiled for the HOST by tests/emu (g++ -DTTTS_HOST_EMU: one OS thread per CUDA thread, blocks one after another),
+// which runs these very kernels and the launch sequence below on CPU against the oracle -- hence no <<<>>> and the TTTS_DYN_SMEM macro.
 #include <string.h>
+#ifdef TTTS_HOST_EMU
+#include "cuda_emu.h"
+#else
 #include "common.cuh"
 #include "host_util.h"
 #include "kernels.h"
+#define TTTS_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+#include "gpt_layout.h"
 
 namespace ttts {
 
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(256) dec_rowop_kernel(const RowopArgs a) {
 template <int BT>
 __global__ void __launch_bounds__(256) dec_gemv_kernel(const bf16* __restrict__ x16, const bf16* __restrict__ W, float* __restrict__ part, int K, int N,
                                                        int B, int ks) {
-    extern __shared__ float dec_smem[];
+    TTTS_DYN_SMEM(float, dec_smem);
     float* xs = dec_smem;                       // [BT][ks]
     float* red = dec_smem + BT * ks;            // [8][BT][256]
     pdl_launch_dependents();
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(256) dec_gemv_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(128) dec_attn_kernel(const float* __restrict__ part, const float* __restrict__ bias, int S, int B, int d, int H,
                                                        bf16* __restrict__ kcache, bf16* __restrict__ vcache, int T_max,
                                                        const int32_t* __restrict__ slot_p, bf16* __restrict__ att16) {
-    extern __shared__ float dec_smem[];
+    TTTS_DYN_SMEM(float, dec_smem);
     float* sc = dec_smem;                       // [T_max] scores -> probabilities
     __shared__ float qs[64];
     __shared__ float red[4];
@@ -379,7 +388,7 @@ static int dec_gemv(const bf16* x16, const bf16* W, float* part, int K, int N, i
 
 int gpt_kv_fill_layer(const bf16* qkv, int B, int T, int d, int H, int n_pos, bf16* kcache, bf16* vcache, int T_max, cudaStream_t st) {
     TTTS_CHECK_ARG(n_pos >= 1 && n_pos <= T && n_pos <= T_max, "decode: prefill of %d positions (sequence %d, cache %d)", n_pos, T, T_max);
-    dec_kv_fill_kernel<<<dim3(n_pos, B), 128, 0, st>>>(qkv, T, d, H, B, kcache, vcache, T_max);
+    TTTS_CUDA(launch_plain(dec_kv_fill_kernel, dim3(n_pos, B), dim3(128), 0, st, qkv, T, d, H, B, kcache, vcache, T_max));
     TTTS_LAUNCH_CHECK("dec_kv_fill");
     return TTTS_OK;
 }

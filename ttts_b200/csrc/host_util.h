@@ -61,6 +61,14 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// plain <<<grid, block, smem, st>>> launch as a function call (sources that are also compiled by the CPU emulation, tests/emu, use it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 2-D bf16/fp32 tiled tensor map; swizzle: 0 = none, 1 (true) = 128B, 2 = 64B.
 //   inner/outer: tensor extents in elements (inner = contiguous dim); ld_elems: row stride in elements
 //   box_inner/box_outer: box extents in elements

@@ -56,8 +56,7 @@ int attn_dropout_mask(uint8_t* mask, int BH, int T, DropCfg drop, cudaStream_t s
 int attn_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv, int B, int T, int H, DropCfg drop,
              cudaStream_t st);
 
-// gpt_decode.cu : KV-cache decode step (inference_speech); gpt_engine.cu owns the parameter layout and the prefill
-int64_t gpt_param_off(const ttts_gpt_config& c, int tensor, int layer);       // -1 on a bad config
+// gpt_decode.cu : KV-cache decode step (inference_speech); gpt_layout.h owns the parameter layout, gpt_engine.cu the prefill
 int64_t gpt_kv_bytes(int layers, int B, int H, int T_max);
 int64_t gpt_decode_workspace_bytes(int B, int d);
 int gpt_kv_fill_layer(const bf16* qkv, int B, int T, int d, int H, int n_pos, bf16* kcache, bf16* vcache, int T_max, cudaStream_t st);
