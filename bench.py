@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vq-encode", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the headline): the workload's batch PER GPU; strong: that batch split over the GPUs (SURVEY.md 8d secondary line)")
     ap.add_argument("--profile-run", action="store_true", help="for ncu runs only: honour --warmup < 3 (numbers printed are not bench values)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -213,6 +215,9 @@ def main():
                           "text_weight": 0.01, "mel_weight": 1, "accumulate_num": 1},
                 "gpt": dict(GPT_KW, layers=wl["layers"], model_dim=wl["model_dim"], heads=wl["heads"])}
     B, TL, CL = wl["B"], wl["TL"], wl["CL"]
+    if args.scaling == "strong":
+        assert B % world == 0, "strong scaling: global batch %d is not divisible by %d GPUs" % (B, world)
+        B //= world
     torch.manual_seed(0)
 
     # host batches (pinned) -- a few distinct ones, rank-dependent
@@ -317,7 +322,7 @@ def main():
     }
     out = {
         "metric": "gpt_step_audio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms_step, "step_ms_rank0": {"p10": pct(0.1), "median": pct(0.5), "p90": pct(0.9)}, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "ms_per_step": ms_step, "step_ms_rank0": {"p10": pct(0.1), "median": pct(0.5), "p90": pct(0.9)}, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d/H%d" % (wl["layers"], wl["model_dim"], wl["heads"]), "per_gpu_batch": B,
                    "global_batch": B * world, "text_len": TL, "code_len": CL, "seq_len": TL + CL + 4, "parallelism": "dp%d" % world,
                    "dropout": args.dropout, "l2": "working set (~33 GB activations + 5 GB optimizer state per step) far exceeds the 126 MB L2; no flush needed",
