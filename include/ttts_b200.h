@@ -253,6 +253,11 @@ int ttts_logmel(const float* spec, int32_t B, int32_t bins, int32_t F, int32_t n
 int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                     int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
                     const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream);
+/* the same convolution on the split-reduction kernel (groups = 2 or 4 warp groups share a tile's reduction; conv1d_split.cu), whatever
+ * the layer: per-kernel parity tests.  ttts_conv1d_f32 itself picks it for latency-bound layers when TTTS_CONV_SPLIT=1. */
+int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                          int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                          const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream);
 /* torch weight_norm (dim 0): w[co,:] = g[co] * v[co,:] / ||v[co,:]|| */
 int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream);
 /* Activation1d(SnakeBeta(alpha_logscale)) : 2x kaiser-sinc upsample, x + sin^2(e^a x)/e^b, 2x low-pass downsample

@@ -45,6 +45,8 @@ inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return
 inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 typedef void* cudaStream_t;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> inline int cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 typedef int cudaError_t;
 constexpr int cudaSuccess = 0;
 
@@ -147,6 +149,16 @@ inline float emu_gelu_bf16(float x) {
     return bf16_round(fmaf(hx, t, hx));
 }
 inline uint32_t gelu_new_bf2(uint32_t x) { return pack_bf16(emu_gelu_bf16(bf16_lo(x)), emu_gelu_bf16(bf16_hi(x))); }
+// cp.async as a synchronous copy (zero fill when !pred); commit / wait are no-ops.  The emulation therefore cannot see a MISSING wait;
+// it does see wrong addresses, wrong stage indices and misplaced barriers.
+inline void cp_async4(void* smem_dst, const void* gsrc, bool pred) {
+    if (pred) memcpy(smem_dst, gsrc, 4); else memset(smem_dst, 0, 4);
+}
+inline void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    if (pred) memcpy(smem_dst, gsrc, 16); else memset(smem_dst, 0, 16);
+}
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
 inline void pdl_wait() {}
 inline void pdl_launch_dependents() {}
 

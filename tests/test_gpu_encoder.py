@@ -101,6 +101,44 @@ def test_conv1d_tc_vs_torch(C, K, dil, T):
     assert float((got - want).abs().max() / want.abs().max()) < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_SPLIT_TEST") != "1", reason="split-reduction convolution (conv1d_split.cu): validated on the CPU emulation only so far; set TTTS_SPLIT_TEST=1")
+@pytest.mark.parametrize("groups", [2, 4])
+@pytest.mark.parametrize("shape", [(64, 192, 36, 384, 5, 1, 1, 2, 3), (64, 192, 36, 384, 1, 1, 1, 0, 0), (64, 128, 72, 128, 11, 1, 5, 25, 0),
+                                   (64, 96, 144, 96, 7, 1, 3, 9, 0), (3, 20, 61, 24, 7, 2, 1, 3, 2), (2, 3, 70, 16, 3, 1, 1, 1, 1)])
+def test_conv1d_split_vs_torch(shape, groups):
+    """ttts_conv1d_f32_split (G warp groups share a tile's reduction) vs torch fp32 on the encoder's latency-bound layer shapes (WN in_layer /
+    res_skip at 64 clips, level-2 / level-3 ResBlock convolutions) and ragged ones; also against the single-group kernel (tolerance: the sum
+    over r is associated differently, nothing else changes)."""
+    from ttts_b200.vqvae.encoder import conv1d
+    B, Cin, T, Cout, K, stride, dil, pad, post = shape
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn(B, Cin, T, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, K, device="cuda", generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
+    Ceff = Cout // 2 if post in (1, 3) else Cout
+    res = torch.randn(B, Ceff, Tout, device="cuda", generator=g)
+    mask = (torch.rand(B, Tout, device="cuda", generator=g) > 0.3).float()
+    cond = torch.randn(B, Cout, device="cuda", generator=g) if post == 3 else None
+    kw = dict(stride=stride, dil=dil, pad=pad, pre_lrelu=(post == 0), resid=res, out_scale=0.5, mask=mask, post=post, cond=cond)
+    got = conv1d(x, w, b, split=groups, **kw)
+    base = conv1d(x, w, b, **kw)
+    xin = torch.nn.functional.leaky_relu(x, 0.1) if post == 0 else x
+    y = torch.nn.functional.conv1d(xin, w, b, stride=stride, dilation=dil, padding=pad)
+    if post in (1, 3):
+        a, gt = y.chunk(2, 1)
+        if cond is not None:
+            ca, cg = cond.chunk(2, 1)
+            a, gt = a + ca[:, :, None], gt + cg[:, :, None]
+        y = (torch.tanh(a) if post == 3 else a) * torch.sigmoid(gt)
+    elif post == 2:
+        y = torch.nn.functional.mish(y)
+    want = (y + res) * 0.5 * mask[:, None, :]
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * max(1.0, scale)
+    assert float((got - base).abs().max()) <= 1e-5 * max(1.0, scale)
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

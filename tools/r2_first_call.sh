@@ -8,7 +8,11 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 TTTS_KV_TEST=1 timeout 600 python -m pytest tests/test_gpu_gpt.py -m gpu -q -k "kv" > gpurun_out/r2a_pytest_kv.log 2>&1; tail -15 gpurun_out/r2a_pytest_kv.log
 timeout 600 python tools/decode_bench.py 1 32 256 > gpurun_out/r2a_decode_b1.json 2> gpurun_out/r2a_decode_b1.err; cat gpurun_out/r2a_decode_b1.json; tail -2 gpurun_out/r2a_decode_b1.err
 timeout 600 python tools/decode_bench.py 8 32 256 > gpurun_out/r2a_decode_b8.json 2> gpurun_out/r2a_decode_b8.err; cat gpurun_out/r2a_decode_b8.json; tail -2 gpurun_out/r2a_decode_b8.err
-# 3. split-bf16 tcgen05 convolution (conv1d_tc.cu; desk-checked + index emulation only).  Own timeout: a hang must not take the box.
+# 3. split-reduction convolution (conv1d_split.cu; CPU emulation only): kernel parity, whole-encoder parity with it on, A/B of the encode
+TTTS_SPLIT_TEST=1 timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "conv1d_split" > gpurun_out/r2a_pytest_split.log 2>&1; tail -8 gpurun_out/r2a_pytest_split.log
+TTTS_CONV_SPLIT=1 timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu -q > gpurun_out/r2a_pytest_enc_split.log 2>&1; tail -8 gpurun_out/r2a_pytest_enc_split.log
+(ONLY=enc timeout 200 python tools/kernels_ab.py; ONLY=enc TTTS_CONV_SPLIT=1 timeout 200 python tools/kernels_ab.py) 2>&1 | grep -v "^$" | tee gpurun_out/r2a_conv_split_ab.txt
+# 4. split-bf16 tcgen05 convolution (conv1d_tc.cu; desk-checked + index emulation only).  Own timeout: a hang must not take the box.
 TTTS_CONV_TC=1 timeout 300 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "conv1d_tc" > gpurun_out/r2a_pytest_convtc.log 2>&1; tail -15 gpurun_out/r2a_pytest_convtc.log
 (ONLY=enc timeout 200 python tools/kernels_ab.py; ONLY=enc TTTS_CONV_TC=1 timeout 200 python tools/kernels_ab.py) 2>&1 | grep -v "^$" | tee gpurun_out/r2a_conv_tc_ab.txt
 TTTS_CONV_TC=1 timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu -q > gpurun_out/r2a_pytest_enc_tc.log 2>&1; tail -8 gpurun_out/r2a_pytest_enc_tc.log

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "kernels.h"
+#include "conv_params.h"
 
 namespace ttts {
 
@@ -20,25 +21,10 @@ namespace ttts {
 int conv1d_tc_try(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int stride, int dil, int pad,
                   int pre_lrelu, const float* resid, float out_scale, int accumulate, const float* mask, int post, cudaStream_t st);
 
+// conv1d_split.cu (off unless TTTS_CONV_SPLIT=1 or forced by ttts_conv1d_f32_split): split-reduction form of the <32> pipelined kernel
+int conv1d_split_try(const ConvParams& p, dim3 grid, int force_groups, cudaStream_t st);
+
 constexpr int CV_CO = 64, CV_T = 64, CV_CI = 16, CV_THREADS = 256;
-
-struct ConvParams {
-    const float* x; const float* w; const float* bias; float* y;
-    int B, Cin, Tin, Cout, Tout, K, stride, dil, pad;
-    int pre_lrelu;            // leaky_relu(0.1) on the input
-    const float* resid;       // [B, Cout_eff, Tout] added to the result (may alias y)
-    float out_scale;          // y = (conv + resid) * out_scale
-    int accumulate;           // y += ... instead of y = ...
-    const float* mask;        // [B, Tout] multiplied in (or null)
-    int post;                 // 0 none, 1 GLU (Cout = 2*C: y[C] = a * sigmoid(b) (+resid)), 2 Mish, 3 WN gate (Cout = 2*C with cond)
-    const float* cond;        // post==3: [B, 2*C] per-batch conditioning added before tanh/sigmoid (or null)
-    int cond_ld;
-};
-
-TTTS_DEVICE float mish_f(float x) {
-    const float sp = x > 20.f ? x : log1pf(expf(x));
-    return x * tanhf(sp);
-}
 
 // For the gated posts (GLU / WN) a CTA computes BOTH halves of 32 gate channels: output-channel tile of 64 = 32 "a" + 32 "b".
 __global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvParams p) {
@@ -161,7 +147,6 @@ __global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvParams
 // Why: the encoder launch list (profiles/r1c_launches_vqenc_summary.txt) showed the window kernel at ~5.6 TFLOP/s: 64x64 tiles half
 // empty for Cout = 32 or T = 36, tiny grids, runtime-K inner loops.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int IG_P = 64, IG_R = 16;
 
 template <int CO_T>
 __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_kernel(const ConvParams p) {
@@ -304,7 +289,6 @@ __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_kernel(const ConvParams
 // L2 round trip per 16-row chunk (~1.7 us per chunk, profiles/r1d_launches_vqenc.csv: 104 us for 0.85 GFLOP).  Here the im2col gather
 // is IG_STAGES - 1 chunks ahead through 4-byte cp.async (zero fill for padding), the (ci, k) decomposition of the row index is advanced
 // incrementally instead of divided out per element, leaky-ReLU moves to the shared-memory read.  Same accumulation order: bit-identical.
-constexpr int IG_STAGES = 4;
 
 template <int CO_T>
 __global__ void __launch_bounds__(CO_T * 4) conv1d_igemm_pipe_kernel(const ConvParams p) {
@@ -676,10 +660,9 @@ using namespace ttts;
 
 extern "C" {
 
-int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
-                    int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
-                    const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int conv1d_run(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                      int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                      const float* mask, int32_t post, const float* cond, int32_t cond_ld, int force_split, cudaStream_t st) {
     TTTS_CHECK_ARG(x && w && y, "conv1d: null pointer");
     TTTS_CHECK_ARG(B > 0 && Cin > 0 && Tin > 0 && Cout > 0 && K > 0 && stride > 0 && dil > 0 && pad >= 0, "conv1d: bad shape");
     const int Tout = (Tin + 2 * pad - dil * (K - 1) - 1) / stride + 1;
@@ -692,6 +675,14 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
     p.post = post; p.cond = cond; p.cond_ld = cond_ld;
     static int use_v1 = -1;
     if (use_v1 < 0) { const char* e = getenv("TTTS_CONV_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (force_split) {                                             // ttts_conv1d_f32_split: the split-reduction kernel on the <32> tiling, whatever the layer
+        const long long Ptot = (long long)B * Tout;
+        TTTS_CHECK_ARG(force_split == 2 || force_split == 4, "conv1d split: groups must be 2 or 4");
+        TTTS_CHECK_ARG(Ptot < (1ll << 31) && (long long)Cin * K < (1ll << 31), "conv1d: problem too large");
+        const int ceff = gated ? Cout / 2 : Cout;
+        dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 15 : 31)) / (gated ? 16 : 32));
+        return conv1d_split_try(p, grid, force_split, st);
+    }
     if (!use_v1) {
         const int rc_tc = conv1d_tc_try(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, st);
         if (rc_tc >= 0) return rc_tc;                              // experimental tensor-core path, only with TTTS_CONV_TC=1 (conv1d_tc.cu)
@@ -707,6 +698,10 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
         if (pipe < 0) { const char* e = getenv("TTTS_CONV_PIPE"); pipe = (e && e[0] == '0') ? 0 : 1; }
         if (small) {
             dim3 grid((unsigned)((Ptot + IG_P - 1) / IG_P), (ceff + (gated ? 15 : 31)) / (gated ? 16 : 32));
+            if (pipe) {
+                const int rc_split = conv1d_split_try(p, grid, 0, st);        // latency-bound layers, only with TTTS_CONV_SPLIT=1
+                if (rc_split >= 0) return rc_split;
+            }
             if (pipe) conv1d_igemm_pipe_kernel<32><<<grid, 128, 0, st>>>(p);
             else conv1d_igemm_kernel<32><<<grid, 128, 0, st>>>(p);
         } else {
@@ -731,6 +726,19 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
     conv1d_f32_kernel<<<grid, CV_THREADS, smem, st>>>(p);
     TTTS_LAUNCH_CHECK("conv1d_f32");
     return TTTS_OK;
+}
+
+int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                    int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                    const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream) {
+    return conv1d_run(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld, 0,
+                      (cudaStream_t)stream);
+}
+int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                          int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
+                          const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream) {
+    return conv1d_run(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld,
+                      groups, (cudaStream_t)stream);
 }
 
 int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream) {

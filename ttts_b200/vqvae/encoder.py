@@ -28,6 +28,7 @@ def _protos(lib):
         return
     vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
     lib.ttts_conv1d_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, vp]
+    lib.ttts_conv1d_f32_split.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32, vp]
     lib.ttts_weight_norm.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.ttts_snake_aa.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.ttts_mha_small.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
@@ -41,8 +42,9 @@ def _p(t):
 
 
 def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None, out_scale=1.0, out=None, accumulate=False, mask=None,
-           post=0, cond=None):
-    """Raw call of ttts_conv1d_f32.  x [B,Cin,T] fp32 contiguous, w [Cout,Cin,K]."""
+           post=0, cond=None, split=0):
+    """Raw call of ttts_conv1d_f32.  x [B,Cin,T] fp32 contiguous, w [Cout,Cin,K].  split = 2 / 4: force the split-reduction kernel
+    (ttts_conv1d_f32_split; per-kernel tests)."""
     lib = L.lib(); _protos(lib)
     L.require_cuda(x, w)
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
@@ -54,6 +56,11 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
     if out is None:
         out = torch.empty(B, Ceff, Tout, dtype=torch.float32, device=x.device)
     cond_ld = cond.stride(0) if cond is not None else 0
+    if split:
+        L.check(lib.ttts_conv1d_f32_split(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid),
+                                          float(out_scale), int(accumulate), _p(mask), post, _p(cond), cond_ld, int(split), L.stream_ptr().value),
+                "ttts_conv1d_f32_split")
+        return out
     L.check(lib.ttts_conv1d_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid), float(out_scale),
                                 int(accumulate), _p(mask), post, _p(cond), cond_ld, L.stream_ptr().value), "ttts_conv1d_f32")
     return out
