@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -183,6 +183,55 @@ def decoder_case():
     print("decoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), tuple(y.shape), "loss %.5f" % float(loss))
 
 
+def disc_case():
+    """The REAL reference MultiPeriodDiscriminator (ttts/vqvae/vq2.py:418-551) and GAN losses (ttts/vqvae/losses.py) on CPU, as the trainer
+    uses them (ttts/vqvae/train.py:349-388): discriminator step on (y, y_hat.detach()), generator step = generator_loss + feature_loss.
+    Stored: logits of every discriminator, per-feature-map means, the three losses, and per parameter tensor the gradient norm / projection
+    of the discriminator loss; the gradient of the generator-side loss with respect to y_hat.  Oracle for the next scope row."""
+    from oracle import disc_oracle as DO
+    from ttts.vqvae.vq2 import MultiPeriodDiscriminator
+    from ttts.vqvae import losses as RL
+    net = MultiPeriodDiscriminator(False).eval()
+    P = DO.init_params(seed=4)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(P.keys()), sorted(set(sd.keys()) ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P)
+    g0 = torch.Generator().manual_seed(41)
+    T = 2309                                         # not a multiple of 2, 3, 5, 7 or 11: every period discriminator reflect-pads
+    y = torch.tanh(torch.randn(2, 1, T, generator=g0))
+    y_hat = torch.tanh(y + 0.3 * torch.randn(2, 1, T, generator=g0)).requires_grad_(True)
+    # discriminator step
+    y_d_r, y_d_g, _, _ = net(y, y_hat.detach())
+    loss_d, _, _ = RL.discriminator_loss(y_d_r, y_d_g)
+    loss_d.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net.named_parameters():
+        gk = prm.grad
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    # generator step (discriminator weights are not stepped here; only dL/dy_hat matters downstream)
+    y_d_r2, y_d_g2, fmap_r, fmap_g = net(y, y_hat)
+    loss_fm = RL.feature_loss(fmap_r, fmap_g)
+    loss_gen, _ = RL.generator_loss(y_d_g2)
+    (loss_gen + loss_fm).backward()
+    out = dict(y=y.numpy(), y_hat=y_hat.detach().numpy(), loss_d=float(loss_d), loss_fm=float(loss_fm), loss_gen=float(loss_gen),
+               names=np.array(names), norm=np.array(norm), proj=np.array(proj), dy_hat=y_hat.grad.numpy(),
+               fmap_mean=np.array([[float(f.mean()) for f in fm] + [0.0] * (7 - len(fm)) for fm in fmap_g]),
+               fmap_abs=np.array([[float(f.abs().mean()) for f in fm] + [0.0] * (7 - len(fm)) for fm in fmap_g]))
+    for i, (r, gg) in enumerate(zip(y_d_r, y_d_g)):
+        out["d%d_real" % i] = r.detach().numpy(); out["d%d_gen" % i] = gg.detach().numpy()
+    g1 = torch.Generator().manual_seed(42)
+    z_p, logs_q, m_p, logs_p = [torch.randn(2, 192, 9, generator=g1) for _ in range(4)]
+    z_mask = (torch.rand(2, 1, 9, generator=g1) > 0.2).float()
+    out.update(kl_in=np.stack([t.numpy() for t in (z_p, logs_q, m_p, logs_p)]), kl_mask=z_mask.numpy(),
+               kl=float(RL.kl_loss(z_p, logs_q, m_p, logs_p, z_mask)))
+    path = os.path.join(ROOT, "tests", "golden", "disc.npz")
+    np.savez_compressed(path, **out)
+    print("disc ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "loss_d %.5f loss_gen %.5f loss_fm %.5f" % (float(loss_d), float(loss_gen), float(loss_fm)))
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -343,6 +392,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "disc":
+        disc_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "kv":
         kv_case(gm)
         sys.exit(0)
@@ -356,6 +408,7 @@ if __name__ == "__main__":
     generate_case(gm)
     kv_case(gm)
     decoder_case()
+    disc_case()
     vq_case()
     mel_case()
     encoder_case()
