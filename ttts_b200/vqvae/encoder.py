@@ -14,6 +14,7 @@ row of SURVEY.md section 8(f).  No CPU fallback.
 """
 import ctypes
 import math
+import os
 
 import torch
 from torch import nn
@@ -358,6 +359,11 @@ class PosteriorAudioEncoder(nn.Module):
         cat = torch.empty(B, 2 * self.hidden_channels, T, dtype=torch.float32, device=x.device)
         with torch.cuda.stream(side[2]):
             side[2].wait_event(fork)
+            if callable(g):                                  # TTTS_ENC_OVERLAP=1: the style encoder runs here, beside the waveform branch
+                g = g()
+                self.last_g = g
+                if not torch.cuda.is_current_stream_capturing():
+                    g.record_stream(main)
             h = conv1d(x.contiguous(), self.pre.weight, self.pre.bias, mask=mask2)
             hb = self.enc(h, x_mask, g=g)
             if not torch.cuda.is_current_stream_capturing():
@@ -422,8 +428,15 @@ class VQEncoder(nn.Module):
             mask = torch.ones(B, 1, T, dtype=torch.float32, device=wav.device)
         else:
             mask = (torch.arange(T, device=wav.device)[None, :] < lengths[:, None]).float().unsqueeze(1)      # commons.sequence_mask
-        ge = self.ref_enc(spec * mask, mask)
-        z, m, logs = self.enc_p(spec, wav.unsqueeze(1), mask, g=ge, eps=eps)
+        if os.environ.get("TTTS_ENC_OVERLAP", "0") == "1":
+            # opt-in (not yet run on hardware): only the WN branch needs the style vector, so MelStyleEncoder (~15 small launches, two of them
+            # 1025-row reductions) moves onto the WN branch's stream and overlaps the waveform branch instead of preceding both.  Same kernels,
+            # same inputs: bit-identical results.
+            z, m, logs = self.enc_p(spec, wav.unsqueeze(1), mask, g=lambda: self.ref_enc(spec * mask, mask), eps=eps)
+            ge = self.enc_p.last_g                           # joined: enc_p waited for the side stream before returning
+        else:
+            ge = self.ref_enc(spec * mask, mask)
+            z, m, logs = self.enc_p(spec, wav.unsqueeze(1), mask, g=ge, eps=eps)
         x = conv1d(z, self.proj.weight, self.proj.bias, stride=2)
         self.quantizer.eval()
         quantized, codes, commit, _ = self.quantizer(x, layers=[0])
