@@ -258,6 +258,14 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
 int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
                           const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream);
+/* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- written without hardware, validated on the CPU
+ * emulation of the source only).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
+ *   bwd_input : dx[B,Cin,Tin] (+)= lrelu'(x) * conv_transpose(dy, w)      x only read when pre_lrelu (the forward's input)
+ *   bwd_weight: dw[Cout,Cin,K] += dy (*) lrelu(x) ; db[Cout] += sum dy (db may be NULL).  Gradients ACCUMULATE: zero them first. */
+int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                          int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, int32_t accumulate, void* stream);
+int ttts_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, void* stream);
 /* torch weight_norm (dim 0): w[co,:] = g[co] * v[co,:] / ||v[co,:]|| */
 int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream);
 /* Activation1d(SnakeBeta(alpha_logscale)) : 2x kaiser-sinc upsample, x + sin^2(e^a x)/e^b, 2x low-pass downsample

@@ -11,6 +11,7 @@
 // What it cannot show: memory-model races between blocks, coalescing, occupancy, anything about performance.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdarg>
@@ -30,6 +31,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 #define TTTS_DEVICE inline
 #define TTTS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::ttts_emu::tl.dyn_smem)
 
@@ -110,6 +112,7 @@ inline float __shfl_xor_sync(unsigned, float v, int o) {
     return r;
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 inline float __expf(float x) { return expf(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }

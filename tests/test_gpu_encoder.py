@@ -139,6 +139,30 @@ def test_conv1d_split_vs_torch(shape, groups):
     assert float((got - base).abs().max()) <= 1e-5 * max(1.0, scale)
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="Conv1d backward kernels (conv1d_bwd.cu, next scope row): validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+@pytest.mark.parametrize("shape", [(64, 192, 36, 384, 5, 1, 1, 2, False), (8, 32, 2304, 32, 11, 1, 5, 25, True), (8, 16, 2304, 32, 16, 8, 1, 7, False),
+                                   (2, 20, 61, 24, 7, 2, 1, 3, True), (1, 3, 70, 5, 3, 1, 1, 1, False)])
+def test_conv1d_backward_vs_autograd(shape):
+    """ttts_conv1d_bwd_input / ttts_conv1d_bwd_weight vs torch.autograd of F.conv1d(leaky_relu(x)) in fp32 (atomics: order-dependent at 1e-6)"""
+    from ttts_b200.vqvae.encoder import conv1d_backward
+    B, Cin, T, Cout, K, stride, dil, pad, lrelu = shape
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn(B, Cin, T, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(Cout, Cin, K, device="cuda", generator=g) / (Cin * K) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, device="cuda", generator=g, requires_grad=True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x, 0.1) if lrelu else x, w, b, stride=stride, dilation=dil, padding=pad)
+        dy = torch.randn(y.shape, device="cuda", generator=g)
+        y.backward(dy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    dx, dw, db = conv1d_backward(dy.contiguous(), x.detach(), w.detach(), stride=stride, dil=dil, pad=pad, pre_lrelu=lrelu)
+    for got, want in ((dx, x.grad), (dw, w.grad), (db, b.grad)):
+        assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

@@ -1,0 +1,304 @@
+// NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent; validated on the CPU emulation of this source, tests/emu,
+// against torch.autograd).  First kernels of the next scope row (the VQ-VAE-GAN train step): the backward of the fp32
+// Conv1d that ttts_conv1d_f32 computes -- input gradient, weight gradient, bias gradient -- for any stride / dilation / padding, i.e. the
+// autograd of nn.Conv1d in PosteriorAudioEncoder / WN / ResBlock1 / the downsampling stack (ttts/vqvae/vq2.py:667-745, modules.py:136-318).
+// Exact fp32 on CUDA cores like the forward; correctness first: double-buffered register staging, no cp.async pipeline yet.
+//
+//   dgrad:  dx[b, ci, ti] (+)= lrelu'(x[b, ci, ti]) * sum_{co, k} w[co, ci, k] * dy[b, co, (ti + pad - k dil) / stride]   (when divisible, in range)
+//           implicit GEMM: rows = 32 input channels, columns = 64 input positions (batch x time flattened), reduction r = co * K + k
+//   wgrad:  dw[co, ci, k] += sum_{b, to} dy[b, co, to] * lrelu(x)[b, ci, to stride + k dil - pad]
+//           implicit GEMM: rows = 32 output channels, columns = 64 of the (ci, k) pairs (= dw's memory order), reduction over the B * Tout
+//           positions, cut into slices across grid.z; slices combine with fp32 atomic adds (gradients ACCUMULATE, as in the GPT engine)
+//   bgrad:  db[co] += sum_{b, to} dy[b, co, to]                                                    one CTA per channel, fixed order
+#include <stdlib.h>
+#ifdef TTTS_HOST_EMU
+#include "cuda_emu.h"
+#else
+#include "common.cuh"
+#include "host_util.h"
+#include "kernels.h"
+#endif
+#include "conv_params.h"
+
+namespace ttts {
+
+struct ConvBwdParams {
+    const float* dy;          // [B, Cout, Tout]
+    const float* w;           // [Cout, Cin, K]
+    const float* x;           // [B, Cin, Tin] forward input (wgrad: always; dgrad: only with pre_lrelu)
+    float* dx;                // [B, Cin, Tin]
+    float* dw;                // [Cout, Cin, K]
+    int B, Cin, Tin, Cout, Tout, K, stride, dil, pad;
+    int pre_lrelu;            // the forward applied leaky_relu(0.1) to x before the convolution
+    int accumulate;           // dgrad: dx += instead of dx =
+    int slice;                // wgrad: positions per grid.z slice (a multiple of IG_R)
+};
+
+constexpr int BW_T = 32, BW_NT = BW_T * 4, BW_LDA = BW_T + 4, BW_LDB = IG_P + 4, BW_NB = IG_R * IG_P / BW_NT;
+
+// ------------------------------------------------------------------------------------------------------------
+// input gradient
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BW_NT) conv1d_dgrad_kernel(const ConvBwdParams p) {
+    __shared__ __align__(16) float sA[2][IG_R][BW_LDA];
+    __shared__ __align__(16) float sB[2][IG_R][BW_LDB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int p0 = blockIdx.x * IG_P, ci0 = blockIdx.y * BW_T;
+    const int R = p.Cout * p.K, Ptot = p.B * p.Tin;
+    const int nchunks = (R + IG_R - 1) / IG_R;
+    // B loader: column cb = one input position, rows rb0 + 2 i
+    const int cb = tid & 63, rb0 = tid >> 6;
+    const int posb = p0 + cb;
+    const bool pos_ok = posb < Ptot;
+    const int bb = pos_ok ? posb / p.Tin : 0;
+    const int tin = pos_ok ? posb - bb * p.Tin : 0;
+    const float* dyb = p.dy + (size_t)bb * p.Cout * p.Tout;
+    // A loader: column ca = input channel, rows ra4 .. ra4 + 3
+    const int ca = tid >> 2, ra4 = (tid & 3) * 4;
+    const bool cia_ok = ci0 + ca < p.Cin;
+
+    float ra[4], rb[BW_NB];
+    auto gload = [&](int chunk) {
+        const int r0 = chunk * IG_R;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = r0 + ra4 + i;
+            const int co = rr / p.K, k = rr - co * p.K;
+            ra[i] = (cia_ok && rr < R) ? __ldg(p.w + ((size_t)co * p.Cin + ci0 + ca) * p.K + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < BW_NB; ++i) {
+            const int rr = r0 + rb0 + (BW_NT / 64) * i;
+            const int co = rr / p.K, k = rr - co * p.K;
+            const int num = tin + p.pad - k * p.dil;
+            float v = 0.f;
+            if (pos_ok && rr < R && num >= 0) {
+                const int to = num / p.stride;
+                if (to * p.stride == num && to < p.Tout) v = __ldg(dyb + (size_t)co * p.Tout + to);
+            }
+            rb[i] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sA[buf][ra4 + i][ca] = ra[i];
+#pragma unroll
+        for (int i = 0; i < BW_NB; ++i) sB[buf][rb0 + (BW_NT / 64) * i][cb] = rb[i];
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) gload(c + 1);
+#pragma unroll
+        for (int r = 0; r < IG_R; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&sA[buf][r][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[buf][r][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        if (c + 1 < nchunks) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pos = p0 + tx * 4 + j;
+        if (pos >= Ptot) continue;
+        const int b = pos / p.Tin, t = pos - b * p.Tin;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ci = ci0 + ty * 4 + i;
+            if (ci >= p.Cin) continue;
+            const size_t o = ((size_t)b * p.Cin + ci) * p.Tin + t;
+            float v = acc[i][j];
+            if (p.pre_lrelu) v *= p.x[o] > 0.f ? 1.f : 0.1f;
+            p.dx[o] = p.accumulate ? p.dx[o] + v : v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BW_NT) conv1d_wgrad_kernel(const ConvBwdParams p) {
+    __shared__ __align__(16) float sA[2][IG_R][BW_LDA];
+    __shared__ __align__(16) float sB[2][IG_R][BW_LDB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * IG_P, co0 = blockIdx.y * BW_T;
+    const int N = p.Cin * p.K, Ptot = p.B * p.Tout;
+    const int q_begin = blockIdx.z * p.slice, q_end = min(Ptot, q_begin + p.slice);
+    const int nchunks = (max(0, q_end - q_begin) + IG_R - 1) / IG_R;
+    if (nchunks == 0) return;
+    // B loader: column cb = one (ci, k) pair, rows (positions) rb0 + 2 i
+    const int cb = tid & 63, rb0 = tid >> 6;
+    const int nb = n0 + cb;
+    const bool n_ok = nb < N;
+    const int cib = n_ok ? nb / p.K : 0;
+    const int kb = n_ok ? nb - cib * p.K : 0;
+    const int toff = kb * p.dil - p.pad;
+    // A loader: column ca = output channel, rows ra4 .. ra4 + 3
+    const int ca = tid >> 2, ra4 = (tid & 3) * 4;
+    const bool coa_ok = co0 + ca < p.Cout;
+
+    float ra[4], rb[BW_NB];
+    auto gload = [&](int chunk) {
+        const int q0 = q_begin + chunk * IG_R;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + ra4 + i;
+            float v = 0.f;
+            if (coa_ok && q < q_end) { const int b = q / p.Tout, to = q - b * p.Tout; v = __ldg(p.dy + ((size_t)b * p.Cout + co0 + ca) * p.Tout + to); }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < BW_NB; ++i) {
+            const int q = q0 + rb0 + (BW_NT / 64) * i;
+            float v = 0.f;
+            if (n_ok && q < q_end) {
+                const int b = q / p.Tout, to = q - b * p.Tout;
+                const int ti = to * p.stride + toff;
+                if (ti >= 0 && ti < p.Tin) {
+                    v = __ldg(p.x + ((size_t)b * p.Cin + cib) * p.Tin + ti);
+                    if (p.pre_lrelu) v = v > 0.f ? v : 0.1f * v;
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sA[buf][ra4 + i][ca] = ra[i];
+#pragma unroll
+        for (int i = 0; i < BW_NB; ++i) sB[buf][rb0 + (BW_NT / 64) * i][cb] = rb[i];
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) gload(c + 1);
+#pragma unroll
+        for (int r = 0; r < IG_R; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&sA[buf][r][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[buf][r][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        if (c + 1 < nchunks) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) atomicAdd(p.dw + (size_t)co * N + n, acc[i][j]);
+        }
+    }
+}
+
+// db[co] += sum over (b, to) of dy ; one CTA per output channel, fixed summation order
+__global__ void __launch_bounds__(256) conv1d_bgrad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int Cout, int Tout) {
+    __shared__ float red[8];
+    const int co = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < B * Tout; i += 256) {
+        const int b = i / Tout, t = i - b * Tout;
+        s += dy[((size_t)b * Cout + co) * Tout + t];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        db[co] += t;
+    }
+}
+
+static int bwd_params(ConvBwdParams& p, int B, int Cin, int Tin, int Cout, int K, int stride, int dil, int pad) {
+    TTTS_CHECK_ARG(B > 0 && Cin > 0 && Tin > 0 && Cout > 0 && K > 0 && stride > 0 && dil > 0 && pad >= 0, "conv1d backward: bad shape");
+    const int Tout = (Tin + 2 * pad - dil * (K - 1) - 1) / stride + 1;
+    TTTS_CHECK_ARG(Tout > 0, "conv1d backward: empty output");
+    TTTS_CHECK_ARG((long long)B * Tin < (1ll << 31) && (long long)Cin * K < (1ll << 31) && (long long)Cout * K < (1ll << 31),
+                   "conv1d backward: problem too large");
+    p.B = B; p.Cin = Cin; p.Tin = Tin; p.Cout = Cout; p.Tout = Tout; p.K = K; p.stride = stride; p.dil = dil; p.pad = pad;
+    return TTTS_OK;
+}
+
+int conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx, int B, int Cin, int Tin, int Cout, int K, int stride, int dil,
+                     int pad, int pre_lrelu, int accumulate, cudaStream_t st) {
+    ConvBwdParams p = {};
+    TTTS_RUN(bwd_params(p, B, Cin, Tin, Cout, K, stride, dil, pad));
+    TTTS_CHECK_ARG(dy && w && dx && (!pre_lrelu || x), "conv1d dgrad: null pointer");
+    p.dy = dy; p.w = w; p.x = x; p.dx = dx; p.pre_lrelu = pre_lrelu; p.accumulate = accumulate;
+    const dim3 grid((unsigned)(((long long)B * Tin + IG_P - 1) / IG_P), (Cin + BW_T - 1) / BW_T);
+    TTTS_CUDA(launch_plain(conv1d_dgrad_kernel, grid, dim3(BW_NT), 0, st, p));
+    TTTS_LAUNCH_CHECK("conv1d_dgrad");
+    return TTTS_OK;
+}
+
+int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int B, int Cin, int Tin, int Cout, int K, int stride, int dil, int pad,
+                      int pre_lrelu, cudaStream_t st) {
+    ConvBwdParams p = {};
+    TTTS_RUN(bwd_params(p, B, Cin, Tin, Cout, K, stride, dil, pad));
+    TTTS_CHECK_ARG(dy && x && dw, "conv1d wgrad: null pointer");
+    p.dy = dy; p.x = x; p.dw = dw; p.pre_lrelu = pre_lrelu;
+    const int gx = (Cin * K + IG_P - 1) / IG_P, gy = (Cout + BW_T - 1) / BW_T;
+    const long long Ptot = (long long)B * p.Tout;
+    // slices of the position axis: about two CTAs per SM in total, at least 4 chunks each
+    long long S = (2ll * num_sms() + (long long)gx * gy - 1) / ((long long)gx * gy);
+    const long long s_max = (Ptot + 4 * IG_R - 1) / (4 * IG_R);
+    if (S > s_max) S = s_max;
+    if (S < 1) S = 1;
+    if (S > 65535) S = 65535;
+    long long slice = (Ptot + S - 1) / S;
+    slice = (slice + IG_R - 1) / IG_R * IG_R;
+    p.slice = (int)slice;
+    const dim3 grid(gx, gy, (unsigned)((Ptot + slice - 1) / slice));
+    TTTS_CUDA(launch_plain(conv1d_wgrad_kernel, grid, dim3(BW_NT), 0, st, p));
+    TTTS_LAUNCH_CHECK("conv1d_wgrad");
+    if (db) {
+        TTTS_CUDA(launch_plain(conv1d_bgrad_kernel, dim3(Cout), dim3(256), 0, st, dy, db, B, Cout, p.Tout));
+        TTTS_LAUNCH_CHECK("conv1d_bgrad");
+    }
+    return TTTS_OK;
+}
+
+}  // namespace ttts
+
+#ifndef TTTS_HOST_EMU
+extern "C" {
+int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                          int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, int32_t accumulate, void* stream) {
+    return ttts::conv1d_bwd_input(dy, w, x, dx, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, accumulate, (cudaStream_t)stream);
+}
+int ttts_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, void* stream) {
+    return ttts::conv1d_bwd_weight(dy, x, dw, db, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, (cudaStream_t)stream);
+}
+}
+#endif

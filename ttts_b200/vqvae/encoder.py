@@ -30,6 +30,8 @@ def _protos(lib):
     vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
     lib.ttts_conv1d_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, vp]
     lib.ttts_conv1d_f32_split.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32, vp]
+    lib.ttts_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
+    lib.ttts_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.ttts_weight_norm.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.ttts_snake_aa.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.ttts_mha_small.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
@@ -65,6 +67,23 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
     L.check(lib.ttts_conv1d_f32(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid), float(out_scale),
                                 int(accumulate), _p(mask), post, _p(cond), cond_ld, L.stream_ptr().value), "ttts_conv1d_f32")
     return out
+
+
+def conv1d_backward(dy, x, w, stride=1, dil=1, pad=0, pre_lrelu=False, need_bias=True):
+    """Autograd of `conv1d(x, w, b, stride, dil, pad, pre_lrelu)` for a given dy [B,Cout,Tout]: returns (dx, dw, db).  Raw calls of
+    ttts_conv1d_bwd_input / ttts_conv1d_bwd_weight (csrc/conv1d_bwd.cu; next scope row, not yet wired into a training module)."""
+    lib = L.lib(); _protos(lib)
+    L.require_cuda(dy, x, w)
+    assert dy.is_contiguous() and x.is_contiguous() and w.is_contiguous()
+    B, Cin, Tin = x.shape
+    Cout, _, K = w.shape
+    dx = torch.empty_like(x)
+    dw = torch.zeros_like(w)
+    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if need_bias else None
+    st = L.stream_ptr().value
+    L.check(lib.ttts_conv1d_bwd_input(_p(dy), _p(w), _p(x), _p(dx), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), 0, st), "ttts_conv1d_bwd_input")
+    L.check(lib.ttts_conv1d_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), st), "ttts_conv1d_bwd_weight")
+    return dx, dw, db
 
 
 _wn_cache = {}
