@@ -52,6 +52,18 @@ def run(hbm_gbs=6570.3, with_cpu=False):
         out["encode_graphed_error"] = repr(e)[:200]
     out["batch"] = B
     out["samples_per_clip"] = Lw
+    # end to end with HOST buffers, as an extraction script calls it: pinned waveforms -> device, encode, codes -> host, every batch
+    try:
+        hw = wav.cpu().pin_memory()
+
+        def e2e():
+            return enc(hw.to(dev, non_blocking=True))["codes"].cpu()
+        assert torch.equal(e2e(), enc(wav)["codes"].cpu())
+        mse = _time(e2e, iters=10)
+        out["encode_e2e"] = {"ms_per_batch": mse, "msamples_per_s": B * Lw / mse / 1e3, "h2d_bytes_per_batch": hw.numel() * 4,
+                             "d2h_bytes_per_batch": int(enc(wav)["codes"].numel()) * 8}
+    except Exception as e:
+        out["encode_e2e_error"] = repr(e)[:200]
     # STFT + mel (v2 front end): per frame 640*4 B in, (1025 + 128)*4 B out
     F = 36
     ms_spec = _time(lambda: spectrogram_torch(wav, 2048, 640, 2048), iters=50)
