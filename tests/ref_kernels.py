@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE: the per-op contract of the encoder's training kernels (ttts_b200/vqvae/train_encoder.py: `K`) restated in plain torch on
+CPU.  Forward functions follow oracle/encoder_oracle.py (pinned to the REAL reference); every backward is the local torch.autograd of that
+forward, so this file is the specification the CUDA kernels are checked against op by op (CPU emulation and GPU), and running the training
+graph over it pins the graph's wiring against the reference's gradients (tests/test_train_encoder_cpu.py).  Never imported by the product."""
+import torch
+import torch.nn.functional as F
+
+
+def _vjp(fn, inputs, dy):
+    xs = [t.detach().clone().requires_grad_(True) for t in inputs]
+    y = fn(*xs)
+    return torch.autograd.grad(y, xs, dy, allow_unused=True)
+
+
+class TorchRefKernels:
+    # ---- convolution: y = conv1d(leaky_relu(x, 0.1) if pre_lrelu else x, w, b)            ttts_conv1d_f32 (post = 0) / ttts_conv1d_bwd_* ----
+    @staticmethod
+    def _conv(x, w, b, stride, dil, pad, pre_lrelu):
+        return F.conv1d(F.leaky_relu(x, 0.1) if pre_lrelu else x, w, b, stride=stride, dilation=dil, padding=pad)
+
+    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
+        return self._conv(x, w, b, stride, dil, pad, pre_lrelu)
+
+    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
+        dx, dw = _vjp(lambda a, c: self._conv(a, c, None, stride, dil, pad, pre_lrelu), [x, w], dy)
+        return (dx if need_dx else None), dw, (dy.sum(dim=(0, 2)) if need_db else None)
+
+    # ---- weight norm over dim 0: w = g * v / ||v||                                           ttts_weight_norm / ttts_weight_norm_bwd ----
+    @staticmethod
+    def _wn(v, g):
+        return g.view(-1, 1, 1) * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+
+    def wn_fwd(self, v, g):
+        return self._wn(v, g)
+
+    def wn_bwd(self, dw, v, g):
+        dv, dg = _vjp(self._wn, [v, g], dw)
+        return dv, dg
+
+    # ---- elementwise ----
+    def add(self, a, b):
+        return a + b
+
+    def scale(self, a, s):
+        return a * s
+
+    def mul_mask(self, a, mask):                                      # a [B,C,T], mask [B,T]
+        return a * mask[:, None, :]
+
+    @staticmethod
+    def _glu(raw):
+        a, g = raw.chunk(2, 1)
+        return a * torch.sigmoid(g)
+
+    def glu_fwd(self, raw):
+        return self._glu(raw)
+
+    def glu_bwd(self, dy, raw):
+        return _vjp(self._glu, [raw], dy)[0]
+
+    @staticmethod
+    def _mish(x):
+        return x * torch.tanh(F.softplus(x))
+
+    def mish_fwd(self, x):
+        return self._mish(x)
+
+    def mish_bwd(self, dy, x):
+        return _vjp(self._mish, [x], dy)[0]
+
+    # ---- WN gate: tanh(a + cond_a) * sigmoid(b + cond_b), raw [B,2H,T], cond [B,2H] or None  (modules.py:195-201 fused_add_tanh_sigmoid_multiply) ----
+    @staticmethod
+    def _gate(raw, cond):
+        a = raw if cond is None else raw + cond[:, :, None]
+        h = a.shape[1] // 2
+        return torch.tanh(a[:, :h]) * torch.sigmoid(a[:, h:])
+
+    def gate_fwd(self, raw, cond):
+        return self._gate(raw, cond)
+
+    def gate_bwd(self, dy, raw, cond):
+        if cond is None:
+            return _vjp(lambda r: self._gate(r, None), [raw], dy)[0], None
+        return _vjp(self._gate, [raw, cond], dy)
+
+    # ---- Activation1d(SnakeBeta, log-scale alpha / beta)                                      alias_free_torch/act.py:8-28, activations.py:62-119 ----
+    @staticmethod
+    def _snake(x, la, lb, filt):
+        C = x.shape[1]
+        f = filt.view(1, 1, -1)
+        xp = F.pad(x, (5, 5), mode="replicate")
+        up = 2 * F.conv_transpose1d(xp, f.expand(C, -1, -1), stride=2, groups=C)[..., 15:-15]
+        alpha, beta = torch.exp(la).view(1, -1, 1), torch.exp(lb).view(1, -1, 1)
+        up = up + (1.0 / (beta + 1e-9)) * torch.sin(up * alpha) ** 2
+        return F.conv1d(F.pad(up, (5, 6), mode="replicate"), f.expand(C, -1, -1), stride=2, groups=C)
+
+    def snake_fwd(self, x, la, lb, filt):
+        return self._snake(x, la, lb, filt)
+
+    def snake_bwd(self, dy, x, la, lb, filt):
+        return _vjp(lambda a, b, c: self._snake(a, b, c, filt), [x, la, lb], dy)
+
+    # ---- small masked multi-head attention, channel-major [B,C,T]; keys >= lens[b] masked    modules.py:640-683 (MultiHeadAttention of MelStyleEncoder) ----
+    @staticmethod
+    def _mha(q, k, v, lens, heads, temperature):
+        B, C, T = q.shape
+        dk = C // heads
+        qh, kh, vh = [t.view(B, heads, dk, T) for t in (q, k, v)]
+        att = torch.einsum("bhdt,bhds->bhts", qh, kh) / temperature
+        pad = torch.arange(T)[None, :] >= lens[:, None]                     # [B, T] True at padding
+        att = att.masked_fill(pad[:, None, None, :], float("-inf"))
+        return torch.einsum("bhts,bhds->bhdt", torch.softmax(att, dim=-1), vh).reshape(B, C, T)
+
+    def mha_fwd(self, q, k, v, lens, heads, temperature):
+        return self._mha(q, k, v, lens, heads, temperature)
+
+    def mha_bwd(self, do, q, k, v, lens, heads, temperature):
+        return _vjp(lambda a, b, c: self._mha(a, b, c, lens, heads, temperature), [q, k, v], do)
+
+    # ---- masked temporal mean: y[b,c] = sum_{t < lens[b]} x[b,c,t] / lens[b]                  modules.py:757-763 ----
+    def masked_mean_fwd(self, x, lens):
+        T = x.shape[-1]
+        m = (torch.arange(T)[None, :] < lens[:, None]).float()
+        return (x * m[:, None, :]).sum(-1) / lens[:, None].float()
+
+    def masked_mean_bwd(self, dy, lens, T):
+        m = (torch.arange(T)[None, :] < lens[:, None]).float()
+        return (dy / lens[:, None].float())[:, :, None] * m[:, None, :]
+
+    # ---- posterior sample: z = (m + eps * exp(logs)) * mask, stats = [m | logs]               vq2.py:742-744 ----
+    @staticmethod
+    def _posterior(stats, eps, mask):
+        m, logs = stats.chunk(2, 1)
+        e = eps if eps is not None else torch.zeros_like(m)
+        return (m + e * torch.exp(logs)) * mask[:, None, :]
+
+    def posterior_fwd(self, stats, eps, mask):
+        return self._posterior(stats, eps, mask)
+
+    def posterior_bwd(self, dz, stats, eps, mask):
+        return _vjp(lambda s: self._posterior(s, eps, mask), [stats], dz)[0]

@@ -1,0 +1,316 @@
+"""Training-mode encode half of the VQ-VAE (next scope row, SURVEY.md 8f-1: the encoder's backward inside the VQ-VAE-GAN train step,
+ttts/vqvae/train.py:330-406 -> vq2.py:843-852): MelStyleEncoder, PosteriorAudioEncoder (downsampling stack, 15 ResBlock1, anti-aliased
+SnakeBeta, 16-layer WN), posterior sample, proj -- forward with the activations kept, and the gradient of every parameter.
+
+DRAFT, NOT YET RUN ON HARDWARE.  Structure:
+  * a small tape (`Tape`, `Var`, `Ops`): every op is ONE forward kernel call and records ONE closure that calls its backward kernel, so the
+    backward pass is the tape in reverse -- no tracing compiler, no torch.autograd on the compute path;
+  * the kernels come from a backend object `K`.  The product backend is `CudaKernels` (ctypes into libttts_b200.so: ttts_conv1d_f32,
+    ttts_conv1d_bwd_input / _weight, ttts_weight_norm(_bwd), ttts_snake_aa(_bwd), ... ) and raises off-GPU: there is no CPU fallback.
+    tests/ref_kernels.py holds a torch restatement of the same per-op contract; tests/test_train_encoder_cpu.py runs THIS graph over it and
+    checks all 414 parameter gradients against the REAL reference's (tests/golden/encoder_grads.npz), which pins the wiring of the graph;
+    the CUDA kernels are checked op by op against the same contract on the CPU emulation (tests/test_emu_*) and on the GPU.
+  * slicing / concatenation / reshapes are memory plumbing and use torch tensor views.
+"""
+import math
+
+import torch
+
+HID, GIN = 192, 512
+RATES, KSZ = [10, 8, 2, 2, 2], [16, 16, 8, 2, 2]
+
+
+class Var:
+    """a tensor on the tape and the slot its gradient accumulates into"""
+    __slots__ = ("v", "g")
+
+    def __init__(self, v):
+        self.v, self.g = v, None
+
+
+class Tape:
+    def __init__(self):
+        self.steps = []
+
+    def record(self, fn):
+        self.steps.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.steps):
+            fn()
+        self.steps = []
+
+
+class Ops:
+    """The op set of the encoder: forward = one kernel call on `K`, backward = one recorded closure."""
+
+    def __init__(self, K, tape):
+        self.K, self.tape = K, tape
+
+    def _acc(self, var, g):
+        if g is None:
+            return
+        var.g = g if var.g is None else self.K.add(var.g, g)
+
+    def conv(self, x, w, b=None, stride=1, dil=1, pad=0, pre_lrelu=False, need_dx=True):
+        y = Var(self.K.conv_fwd(x.v, w.v, b.v if b is not None else None, stride, dil, pad, pre_lrelu))
+
+        def bwd():
+            if y.g is None:
+                return
+            dx, dw, db = self.K.conv_bwd(y.g, x.v, w.v, stride, dil, pad, pre_lrelu, need_dx, b is not None)
+            if need_dx:
+                self._acc(x, dx)
+            self._acc(w, dw)
+            if b is not None:
+                self._acc(b, db)
+        self.tape.record(bwd)
+        return y
+
+    def wn(self, v, g):
+        w = Var(self.K.wn_fwd(v.v, g.v))
+
+        def bwd():
+            if w.g is None:
+                return
+            dv, dg = self.K.wn_bwd(w.g, v.v, g.v)
+            self._acc(v, dv); self._acc(g, dg)
+        self.tape.record(bwd)
+        return w
+
+    def add(self, a, b):
+        c = Var(self.K.add(a.v, b.v))
+
+        def bwd():
+            self._acc(a, c.g); self._acc(b, c.g)
+        self.tape.record(bwd)
+        return c
+
+    def scale(self, a, s):
+        c = Var(self.K.scale(a.v, s))
+
+        def bwd():
+            if c.g is not None:
+                self._acc(a, self.K.scale(c.g, s))
+        self.tape.record(bwd)
+        return c
+
+    def mul_mask(self, a, mask):
+        c = Var(self.K.mul_mask(a.v, mask))
+
+        def bwd():
+            if c.g is not None:
+                self._acc(a, self.K.mul_mask(c.g, mask))
+        self.tape.record(bwd)
+        return c
+
+    def _unary(self, name, x, *consts):
+        y = Var(getattr(self.K, name + "_fwd")(x.v, *consts))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, getattr(self.K, name + "_bwd")(y.g, x.v, *consts))
+        self.tape.record(bwd)
+        return y
+
+    def glu(self, raw):
+        return self._unary("glu", raw)
+
+    def mish(self, x):
+        return self._unary("mish", x)
+
+    def gate(self, raw, cond):
+        y = Var(self.K.gate_fwd(raw.v, cond.v if cond is not None else None))
+
+        def bwd():
+            if y.g is None:
+                return
+            draw, dcond = self.K.gate_bwd(y.g, raw.v, cond.v if cond is not None else None)
+            self._acc(raw, draw)
+            if cond is not None:
+                self._acc(cond, dcond)
+        self.tape.record(bwd)
+        return y
+
+    def snake(self, x, log_alpha, log_beta, filt):
+        y = Var(self.K.snake_fwd(x.v, log_alpha.v, log_beta.v, filt))
+
+        def bwd():
+            if y.g is None:
+                return
+            dx, dla, dlb = self.K.snake_bwd(y.g, x.v, log_alpha.v, log_beta.v, filt)
+            self._acc(x, dx); self._acc(log_alpha, dla); self._acc(log_beta, dlb)
+        self.tape.record(bwd)
+        return y
+
+    def mha(self, q, k, v, lens, heads, temperature):
+        o = Var(self.K.mha_fwd(q.v, k.v, v.v, lens, heads, temperature))
+
+        def bwd():
+            if o.g is None:
+                return
+            dq, dk, dv = self.K.mha_bwd(o.g, q.v, k.v, v.v, lens, heads, temperature)
+            self._acc(q, dq); self._acc(k, dk); self._acc(v, dv)
+        self.tape.record(bwd)
+        return o
+
+    def masked_mean(self, x, lens):
+        T = x.v.shape[-1]
+        y = Var(self.K.masked_mean_fwd(x.v, lens))                  # [B, C]
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, self.K.masked_mean_bwd(y.g, lens, T))
+        self.tape.record(bwd)
+        return y
+
+    def posterior(self, stats, eps, mask):
+        z = Var(self.K.posterior_fwd(stats.v, eps, mask))
+
+        def bwd():
+            if z.g is not None:
+                self._acc(stats, self.K.posterior_bwd(z.g, stats.v, eps, mask))
+        self.tape.record(bwd)
+        return z
+
+    # ---- memory plumbing (views / copies, no arithmetic) ----
+    def slice_c(self, x, c0, c1):
+        y = Var(x.v[:, c0:c1].contiguous())
+
+        def bwd():
+            if y.g is None:
+                return
+            g = torch.zeros_like(x.v)
+            g[:, c0:c1] = y.g
+            self._acc(x, g)
+        self.tape.record(bwd)
+        return y
+
+    def cat_c(self, a, b):
+        ca = a.v.shape[1]
+        y = Var(torch.cat([a.v, b.v], dim=1))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(a, y.g[:, :ca].contiguous()); self._acc(b, y.g[:, ca:].contiguous())
+        self.tape.record(bwd)
+        return y
+
+    def reshape(self, x, shape):
+        y = Var(x.v.reshape(shape))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, y.g.reshape(x.v.shape))
+        self.tape.record(bwd)
+        return y
+
+
+def kaiser_sinc_filter12(device):
+    """alias_free_torch/filter.py: kaiser_sinc_filter1d(cutoff 0.25, half_width 0.3, kernel 12) -- a constant buffer of the reference"""
+    cutoff, half_width, ks = 0.25, 0.3, 12
+    half = ks // 2
+    A = 2.285 * (half - 1) * math.pi * (4 * half_width) + 7.95
+    beta = 0.1102 * (A - 8.7)
+    window = torch.kaiser_window(ks, beta=beta, periodic=False)
+    time = torch.arange(-half, half) + 0.5
+    f = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    return (f / f.sum()).to(device=device, dtype=torch.float32).contiguous()
+
+
+class EncoderGraph:
+    """The training graph over the reference's parameter names (the state_dict of ref_enc.*, enc_p.*, proj.*)."""
+
+    def __init__(self, K, params):
+        self.K = K
+        self.tape = Tape()
+        self.ops = Ops(K, self.tape)
+        # leaves; 2-D Linear weights enter as [out, in, 1] convolution weights
+        self.P = {k: Var(v.detach().unsqueeze(-1).contiguous() if v.dim() == 2 else v.detach().contiguous()) for k, v in params.items()}
+        self.shapes = {k: tuple(v.shape) for k, v in params.items()}
+
+    def _wn(self, prefix, old=True):
+        if old:
+            return self.ops.wn(self.P[prefix + "weight_v"], self.P[prefix + "weight_g"])
+        return self.ops.wn(self.P[prefix + "parametrizations.weight.original1"], self.P[prefix + "parametrizations.weight.original0"])
+
+    def mel_style_encoder(self, x, mask2, lens):
+        """modules.py:686-764.  x [B,1025,T] already masked (a constant: no gradient flows to the spectrogram)."""
+        o, P, pre = self.ops, self.P, "ref_enc."
+        h = o.mish(o.conv(x, P[pre + "spectral.0.fc.weight"], P[pre + "spectral.0.fc.bias"], need_dx=False))
+        h = o.mish(o.conv(h, P[pre + "spectral.3.fc.weight"], P[pre + "spectral.3.fc.bias"]))
+        for i in range(2):
+            c = o.conv(h, P[pre + "temporal.%d.conv1.conv.weight" % i], P[pre + "temporal.%d.conv1.conv.bias" % i], pad=2)
+            h = o.add(h, o.glu(c))
+        h = o.mul_mask(h, mask2)
+        q = o.conv(h, P[pre + "slf_attn.w_qs.weight"], P[pre + "slf_attn.w_qs.bias"])
+        k = o.conv(h, P[pre + "slf_attn.w_ks.weight"], P[pre + "slf_attn.w_ks.bias"])
+        v = o.conv(h, P[pre + "slf_attn.w_vs.weight"], P[pre + "slf_attn.w_vs.bias"])
+        att = o.mha(q, k, v, lens, 2, math.sqrt(128.0))
+        h = o.add(o.conv(att, P[pre + "slf_attn.fc.weight"], P[pre + "slf_attn.fc.bias"]), h)
+        h = o.conv(h, P[pre + "fc.fc.weight"], P[pre + "fc.fc.bias"])
+        return o.reshape(o.masked_mean(h, lens), (h.v.shape[0], GIN, 1))
+
+    def resblock1(self, prefix, x, k):
+        o, P = self.ops, self.P
+        for t, d in enumerate((1, 3, 5)):
+            xt = o.conv(x, self._wn(prefix + "convs1.%d." % t, old=False), P[prefix + "convs1.%d.bias" % t], dil=d, pad=(k * d - d) // 2, pre_lrelu=True)
+            xt = o.conv(xt, self._wn(prefix + "convs2.%d." % t, old=False), P[prefix + "convs2.%d.bias" % t], pad=(k - 1) // 2, pre_lrelu=True)
+            x = o.add(xt, x)
+        return x
+
+    def wn_stack(self, x, mask2, g):
+        o, P, pre = self.ops, self.P, "enc_p.enc."
+        out = None
+        gc = o.reshape(o.conv(g, self._wn(pre + "cond_layer."), P[pre + "cond_layer.bias"]), (g.v.shape[0], 2 * HID * 16))
+        for i in range(16):
+            raw = o.conv(x, self._wn(pre + "in_layers.%d." % i), P[pre + "in_layers.%d.bias" % i], pad=2)
+            acts = o.gate(raw, o.slice_c(gc, i * 2 * HID, (i + 1) * 2 * HID))
+            rs = o.conv(acts, self._wn(pre + "res_skip_layers.%d." % i), P[pre + "res_skip_layers.%d.bias" % i])
+            if i < 15:
+                x = o.mul_mask(o.add(x, o.slice_c(rs, 0, HID)), mask2)
+                skip = o.slice_c(rs, HID, 2 * HID)
+            else:
+                skip = rs
+            out = skip if out is None else o.add(out, skip)
+        return o.mul_mask(out, mask2)
+
+    def posterior_audio_encoder(self, spec, wav, mask2, g, eps):
+        o, P = self.ops, self.P
+        a = o.conv(wav, P["enc_p.down_pre.weight"], P["enc_p.down_pre.bias"], pad=3, need_dx=False)
+        for i in range(5):
+            a = o.conv(a, self._wn("enc_p.downs.%d." % i), P["enc_p.downs.%d.bias" % i], stride=RATES[i], pad=(KSZ[i] - 1) // 2)
+            xs = None
+            for j, k in enumerate((3, 7, 11)):
+                r = self.resblock1("enc_p.resblocks.%d." % (i * 3 + j), a, k)
+                xs = r if xs is None else o.add(xs, r)
+            a = o.scale(xs, 1.0 / 3.0)
+        a = o.snake(a, P["enc_p.activation_post.act.alpha"], P["enc_p.activation_post.act.beta"], kaiser_sinc_filter12(wav.v.device))
+        a = o.mul_mask(o.conv(a, P["enc_p.conv_post.weight"], P["enc_p.conv_post.bias"], pad=3), mask2)
+        x = o.mul_mask(o.conv(spec, P["enc_p.pre.weight"], P["enc_p.pre.bias"], need_dx=False), mask2)
+        x = self.wn_stack(x, mask2, g)
+        stats = o.mul_mask(o.conv(o.cat_c(x, a), P["enc_p.proj.weight"], P["enc_p.proj.bias"]), mask2)
+        return o.posterior(stats, eps, mask2), stats
+
+    def forward(self, spec, wav, lengths=None, eps=None):
+        """spec [B,1025,T] (constant), wav [B,L].  Returns Vars z [B,192,T] and x [B,192,T/2] (the input of the quantizer)."""
+        B, _, T = spec.shape
+        dev = spec.device
+        if lengths is None:
+            lengths = torch.full((B,), T, dtype=torch.int64, device=dev)
+        mask2 = (torch.arange(T, device=dev)[None, :] < lengths[:, None]).float().contiguous()
+        specm = Var(self.K.mul_mask(spec.contiguous(), mask2))
+        ge = self.mel_style_encoder(specm, mask2, lengths)
+        z, stats = self.posterior_audio_encoder(Var(spec.contiguous()), Var(wav.unsqueeze(1).contiguous()), mask2, ge, eps)
+        x = self.ops.conv(z, self.P["proj.weight"], self.P["proj.bias"], stride=2)
+        self.out = dict(ge=ge, z=z, stats=stats, x=x)
+        return z, x
+
+    def backward(self, dz=None, dx=None):
+        """Seed the gradients of z and / or x and run the tape.  Returns name -> gradient with the parameter's own shape."""
+        if dz is not None:
+            self.out["z"].g = dz.contiguous()
+        if dx is not None:
+            self.out["x"].g = dx.contiguous()
+        self.tape.backward()
+        return {k: (v.g.reshape(self.shapes[k]) if v.g is not None else torch.zeros(self.shapes[k], device=v.v.device)) for k, v in self.P.items()}
