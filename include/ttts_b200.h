@@ -279,6 +279,34 @@ int ttts_masked_mean(const float* x, const int64_t* lens, float* y, int32_t B, i
 /* z = (m + eps * exp(logs)) * mask with stats = [B, 2C, T] (m | logs)  (vq2.py:742-744; eps NULL = 0) */
 int ttts_posterior_sample(const float* stats, const float* eps, const float* mask, float* z, int32_t B, int32_t C, int32_t T, void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Training kernels of the VQ-VAE encode half (next scope row; csrc/encoder_bwd.cu -- written without hardware,
+ * validated on the CPU emulation of the source against tests/ref_kernels.py).  fp32, [B, C, T] channel-major.
+ * ------------------------------------------------------------------------------------------ */
+int ttts_ew_add(const float* a, const float* b, float* o, int64_t n, void* stream);
+int ttts_ew_scale(const float* a, float s, float* o, int64_t n, void* stream);
+int ttts_ew_mul_mask(const float* a, const float* mask, float* o, int32_t B, int32_t C, int32_t T, void* stream);            /* mask [B, T] */
+/* Conv1dGLU gate (modules.py:560-566): raw [B,2C,T] = [a | g] ; backward = 0: out [B,C,T] = a sigmoid(g) ; 1: out = d raw from dy [B,C,T] */
+int ttts_glu(const float* raw, const float* dy, float* out, int32_t B, int32_t C, int32_t T, int32_t backward, void* stream);
+/* Mish: backward = 0: out = x tanh(softplus(x)) ; 1: out = dy * d/dx */
+int ttts_mish(const float* x, const float* dy, float* out, int64_t n, int32_t backward, void* stream);
+/* WN gate (modules.py:195-201): raw [B,2H,T], cond [B,2H] or NULL ; backward = 0: out [B,H,T] ; 1: out = d raw, dcond [B,2H] (or NULL) */
+int ttts_wn_gate(const float* raw, const float* cond, const float* dy, float* out, float* dcond, int32_t B, int32_t H, int32_t T,
+                 int32_t backward, void* stream);
+/* backward of ttts_weight_norm: dv [Cout, n], dg [Cout] from dw */
+int ttts_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg, int32_t Cout, int32_t n_per_out, void* stream);
+/* backward of ttts_snake_aa: dx [B,C,T] ; dla / dlb [C] ACCUMULATE (zero them first) */
+int ttts_snake_aa_bwd(const float* dy, const float* x, const float* log_alpha, const float* log_beta, const float* filt12, float* dx,
+                      float* dla, float* dlb, int32_t B, int32_t C, int32_t T, void* stream);
+/* backward of ttts_mha_small (T <= 64) */
+int ttts_mha_small_bwd(const float* dout, const float* q, const float* k, const float* v, const int64_t* lens, float* dq, float* dk, float* dv,
+                       int32_t B, int32_t C, int32_t T, int32_t heads, float temperature, void* stream);
+/* backward of ttts_masked_mean: dy [B, C] -> dx [B, C, T] */
+int ttts_masked_mean_bwd(const float* dy, const int64_t* lens, float* dx, int32_t B, int32_t C, int32_t T, void* stream);
+/* backward of ttts_posterior_sample: dz [B,C,T] -> dstats [B,2C,T] */
+int ttts_posterior_sample_bwd(const float* dz, const float* stats, const float* eps, const float* mask, float* dstats, int32_t B, int32_t C,
+                              int32_t T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,6 +163,34 @@ def test_conv1d_backward_vs_autograd(shape):
         assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the encode half (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_training_graph_gradients_vs_reference_golden(enc, golden_dir):
+    """train_encoder.EncoderGraph over the CUDA kernels: forward values and all 414 parameter gradients against the REAL reference's
+    (tests/golden/encoder_grads.npz) -- the same assertions tests/test_train_encoder_cpu.py makes over the torch restatement of the op contract."""
+    from oracle import encoder_oracle as EO
+    from ttts_b200.vqvae.mel import spectrogram_torch
+    from ttts_b200.vqvae.train_encoder import CudaKernels, EncoderGraph
+    g = np.load(os.path.join(golden_dir, "encoder_grads.npz"))
+    P = {k: v.cuda() for k, v in EO.init_params(seed=5).items()}
+    wav = torch.tensor(enc["wav"]).cuda()
+    spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
+    graph = EncoderGraph(CudaKernels(), P)
+    z, x = graph.forward(spec, wav, lengths=torch.tensor(enc["lengths"]).cuda(), eps=torch.tensor(enc["eps"]).cuda())
+    assert np.abs(z.v.cpu().numpy() - enc["z"]).max() <= 5e-4 * np.abs(enc["z"]).max()
+    assert np.abs(x.v.cpu().numpy() - enc["x"]).max() <= 5e-4 * np.abs(enc["x"]).max()
+    R = torch.randn(3, 192, 36, generator=torch.Generator().manual_seed(123)).cuda()
+    grads = graph.backward(dz=R, dx=x.v / x.v.numel())
+    names = [str(n) for n in g["names"]]
+    assert set(names) == set(grads.keys())
+    floor = 1e-6 * float(np.sqrt((g["norm"] ** 2).sum()))
+    for i, k in enumerate(names):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(g["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(g["proj"][i])) <= 1e-2 * scale + floor, k
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

@@ -314,3 +314,198 @@ class EncoderGraph:
             self.out["x"].g = dx.contiguous()
         self.tape.backward()
         return {k: (v.g.reshape(self.shapes[k]) if v.g is not None else torch.zeros(self.shapes[k], device=v.v.device)) for k, v in self.P.items()}
+
+
+class CudaKernels:
+    """The product backend: every method is one call (conv_bwd: two) into libttts_b200.so on the current stream.  Device tensors only."""
+
+    def __init__(self):
+        import ctypes
+        from .. import _lib as L
+        from . import encoder as E
+        self.L, self.E, self.lib = L, E, L.lib()
+        lib = self.lib
+        E._protos(lib)
+        if not getattr(lib, "_train_protos", False):
+            vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+            lib.ttts_ew_add.argtypes = [vp, vp, vp, i64, vp]
+            lib.ttts_ew_scale.argtypes = [vp, f32, vp, i64, vp]
+            lib.ttts_ew_mul_mask.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+            lib.ttts_glu.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+            lib.ttts_mish.argtypes = [vp, vp, vp, i64, i32, vp]
+            lib.ttts_wn_gate.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+            lib.ttts_weight_norm_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+            lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
+            lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
+            lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+            lib.ttts_posterior_sample_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+            lib._train_protos = True
+
+    def _st(self):
+        return self.L.stream_ptr().value
+
+    def _chk(self, rc, what):
+        self.L.check(rc, what)
+
+    @staticmethod
+    def _p(t):
+        return t.data_ptr() if t is not None else None
+
+    def _req(self, *ts):
+        self.L.require_cuda(*[t for t in ts if t is not None])
+        for t in ts:
+            assert t is None or (t.is_contiguous() and t.dtype in (torch.float32, torch.int64)), "contiguous fp32 / int64 tensors only"
+
+    # ---- convolution / weight norm ----
+    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
+        return self.E.conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=pre_lrelu)
+
+    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
+        self._req(dy, x, w)
+        B, Cin, Tin = x.shape
+        Cout, _, K = w.shape
+        p, lib, st = self._p, self.lib, self._st()
+        dx = None
+        if need_dx:
+            dx = torch.empty_like(x)
+            self._chk(lib.ttts_conv1d_bwd_input(p(dy), p(w), p(x), p(dx), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), 0, st), "ttts_conv1d_bwd_input")
+        dw = torch.zeros_like(w)
+        db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if need_db else None
+        self._chk(lib.ttts_conv1d_bwd_weight(p(dy), p(x), p(dw), p(db), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), st), "ttts_conv1d_bwd_weight")
+        return dx, dw, db
+
+    def wn_fwd(self, v, g):
+        self._req(v, g)
+        w = torch.empty_like(v)
+        self._chk(self.lib.ttts_weight_norm(self._p(v), self._p(g), self._p(w), v.shape[0], v[0].numel(), self._st()), "ttts_weight_norm")
+        return w
+
+    def wn_bwd(self, dw, v, g):
+        self._req(dw, v, g)
+        dv, dg = torch.empty_like(v), torch.empty_like(g)
+        self._chk(self.lib.ttts_weight_norm_bwd(self._p(dw), self._p(v), self._p(g), self._p(dv), self._p(dg), v.shape[0], v[0].numel(), self._st()),
+                  "ttts_weight_norm_bwd")
+        return dv, dg
+
+    # ---- element-wise ----
+    def add(self, a, b):
+        self._req(a, b)
+        o = torch.empty_like(a)
+        self._chk(self.lib.ttts_ew_add(self._p(a), self._p(b), self._p(o), a.numel(), self._st()), "ttts_ew_add")
+        return o
+
+    def scale(self, a, s):
+        self._req(a)
+        o = torch.empty_like(a)
+        self._chk(self.lib.ttts_ew_scale(self._p(a), float(s), self._p(o), a.numel(), self._st()), "ttts_ew_scale")
+        return o
+
+    def mul_mask(self, a, mask):
+        self._req(a, mask)
+        B, C, T = a.shape
+        o = torch.empty_like(a)
+        self._chk(self.lib.ttts_ew_mul_mask(self._p(a), self._p(mask), self._p(o), B, C, T, self._st()), "ttts_ew_mul_mask")
+        return o
+
+    def glu_fwd(self, raw):
+        self._req(raw)
+        B, C2, T = raw.shape
+        y = torch.empty(B, C2 // 2, T, dtype=torch.float32, device=raw.device)
+        self._chk(self.lib.ttts_glu(self._p(raw), None, self._p(y), B, C2 // 2, T, 0, self._st()), "ttts_glu")
+        return y
+
+    def glu_bwd(self, dy, raw):
+        self._req(dy, raw)
+        B, C2, T = raw.shape
+        d = torch.empty_like(raw)
+        self._chk(self.lib.ttts_glu(self._p(raw), self._p(dy), self._p(d), B, C2 // 2, T, 1, self._st()), "ttts_glu (backward)")
+        return d
+
+    def mish_fwd(self, x):
+        self._req(x)
+        y = torch.empty_like(x)
+        self._chk(self.lib.ttts_mish(self._p(x), None, self._p(y), x.numel(), 0, self._st()), "ttts_mish")
+        return y
+
+    def mish_bwd(self, dy, x):
+        self._req(dy, x)
+        d = torch.empty_like(x)
+        self._chk(self.lib.ttts_mish(self._p(x), self._p(dy), self._p(d), x.numel(), 1, self._st()), "ttts_mish (backward)")
+        return d
+
+    def gate_fwd(self, raw, cond):
+        self._req(raw, cond)
+        B, H2, T = raw.shape
+        y = torch.empty(B, H2 // 2, T, dtype=torch.float32, device=raw.device)
+        self._chk(self.lib.ttts_wn_gate(self._p(raw), self._p(cond), None, self._p(y), None, B, H2 // 2, T, 0, self._st()), "ttts_wn_gate")
+        return y
+
+    def gate_bwd(self, dy, raw, cond):
+        self._req(dy, raw, cond)
+        B, H2, T = raw.shape
+        d = torch.empty_like(raw)
+        dc = torch.empty_like(cond) if cond is not None else None
+        self._chk(self.lib.ttts_wn_gate(self._p(raw), self._p(cond), self._p(dy), self._p(d), self._p(dc), B, H2 // 2, T, 1, self._st()), "ttts_wn_gate (backward)")
+        return d, dc
+
+    # ---- SnakeBeta, attention, mean, posterior ----
+    def snake_fwd(self, x, la, lb, filt):
+        self._req(x, la, lb, filt)
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        self._chk(self.lib.ttts_snake_aa(self._p(x), self._p(la), self._p(lb), self._p(filt), self._p(y), B, C, T, self._st()), "ttts_snake_aa")
+        return y
+
+    def snake_bwd(self, dy, x, la, lb, filt):
+        self._req(dy, x, la, lb, filt)
+        B, C, T = x.shape
+        dx, dla, dlb = torch.empty_like(x), torch.zeros_like(la), torch.zeros_like(lb)
+        self._chk(self.lib.ttts_snake_aa_bwd(self._p(dy), self._p(x), self._p(la), self._p(lb), self._p(filt), self._p(dx), self._p(dla), self._p(dlb),
+                                             B, C, T, self._st()), "ttts_snake_aa_bwd")
+        return dx, dla, dlb
+
+    def mha_fwd(self, q, k, v, lens, heads, temperature):
+        self._req(q, k, v, lens)
+        B, C, T = q.shape
+        o = torch.empty_like(q)
+        self._chk(self.lib.ttts_mha_small(self._p(q), self._p(k), self._p(v), self._p(lens), self._p(o), B, C, T, heads, float(temperature), self._st()),
+                  "ttts_mha_small")
+        return o
+
+    def mha_bwd(self, do, q, k, v, lens, heads, temperature):
+        self._req(do, q, k, v, lens)
+        B, C, T = q.shape
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        self._chk(self.lib.ttts_mha_small_bwd(self._p(do), self._p(q), self._p(k), self._p(v), self._p(lens), self._p(dq), self._p(dk), self._p(dv),
+                                              B, C, T, heads, float(temperature), self._st()), "ttts_mha_small_bwd")
+        return dq, dk, dv
+
+    def masked_mean_fwd(self, x, lens):
+        self._req(x, lens)
+        B, C, T = x.shape
+        y = torch.empty(B, C, dtype=torch.float32, device=x.device)
+        self._chk(self.lib.ttts_masked_mean(self._p(x), self._p(lens), self._p(y), B, C, T, self._st()), "ttts_masked_mean")
+        return y
+
+    def masked_mean_bwd(self, dy, lens, T):
+        dy = dy.contiguous()
+        self._req(dy, lens)
+        B, C = dy.shape
+        dx = torch.empty(B, C, T, dtype=torch.float32, device=dy.device)
+        self._chk(self.lib.ttts_masked_mean_bwd(self._p(dy), self._p(lens), self._p(dx), B, C, T, self._st()), "ttts_masked_mean_bwd")
+        return dx
+
+    def posterior_fwd(self, stats, eps, mask):
+        self._req(stats, eps, mask)
+        B, C2, T = stats.shape
+        z = torch.empty(B, C2 // 2, T, dtype=torch.float32, device=stats.device)
+        self._chk(self.lib.ttts_posterior_sample(self._p(stats), self._p(eps), self._p(mask), self._p(z), B, C2 // 2, T, self._st()), "ttts_posterior_sample")
+        return z
+
+    def posterior_bwd(self, dz, stats, eps, mask):
+        self._req(dz, stats, eps, mask)
+        B, C2, T = stats.shape
+        d = torch.empty_like(stats)
+        self._chk(self.lib.ttts_posterior_sample_bwd(self._p(dz), self._p(stats), self._p(eps), self._p(mask), self._p(d), B, C2 // 2, T, self._st()),
+                  "ttts_posterior_sample_bwd")
+        return d
