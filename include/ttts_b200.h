@@ -266,6 +266,9 @@ int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, int32_t accumulate, void* stream);
 int ttts_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                            int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, void* stream);
+/* db[C] += sum over (b, t) of dy[B,C,T].  ConvTranspose1d (the Generator's up-sampling, vq2.py:369-378) is served by these three entry points
+ * with the roles swapped: forward = ttts_conv1d_bwd_input(x, w), dx = ttts_conv1d_f32(dy, w), dw = ttts_conv1d_bwd_weight(dy := x, x := dy). */
+int ttts_bias_grad(const float* dy, float* db, int32_t B, int32_t C, int32_t T, void* stream);
 /* torch weight_norm (dim 0): w[co,:] = g[co] * v[co,:] / ||v[co,:]|| */
 int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream);
 /* Activation1d(SnakeBeta(alpha_logscale)) : 2x kaiser-sinc upsample, x + sin^2(e^a x)/e^b, 2x low-pass downsample
@@ -293,6 +296,12 @@ int ttts_mish(const float* x, const float* dy, float* out, int64_t n, int32_t ba
 /* WN gate (modules.py:195-201): raw [B,2H,T], cond [B,2H] or NULL ; backward = 0: out [B,H,T] ; 1: out = d raw, dcond [B,2H] (or NULL) */
 int ttts_wn_gate(const float* raw, const float* cond, const float* dy, float* out, float* dcond, int32_t B, int32_t H, int32_t T,
                  int32_t backward, void* stream);
+/* leaky ReLU with an explicit slope / tanh: backward = 0: out = f(x) ; 1: out = dy f'(x) */
+int ttts_lrelu(const float* x, const float* dy, float* out, int64_t n, float slope, int32_t backward, void* stream);
+int ttts_tanh(const float* x, const float* dy, float* out, int64_t n, int32_t backward, void* stream);
+/* out[b,c,t] = a[b,c,t] + v[c] (per_batch = 0) or v[b,c] (per_batch = 1) ; ttts_sum_t: out[row] = sum_t a[row, t] */
+int ttts_add_bcast(const float* a, const float* v, float* out, int32_t B, int32_t C, int32_t T, int32_t per_batch, void* stream);
+int ttts_sum_t(const float* a, float* out, int32_t rows, int32_t T, void* stream);
 /* backward of ttts_weight_norm: dv [Cout, n], dg [Cout] from dw */
 int ttts_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg, int32_t Cout, int32_t n_per_out, void* stream);
 /* backward of ttts_snake_aa: dx [B,C,T] ; dla / dlb [C] ACCUMULATE (zero them first) */

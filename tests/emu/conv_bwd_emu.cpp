@@ -11,5 +11,8 @@ int emu_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db,
                           int pre_lrelu) {
     return ttts::conv1d_bwd_weight(dy, x, dw, db, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, nullptr);
 }
+int emu_bias_grad(const float* dy, float* db, int B, int C, int T) {
+    return ttts::launch_plain(ttts::conv1d_bgrad_kernel, dim3(C), dim3(256), 0, nullptr, dy, db, B, C, T);
+}
 const char* emu_last_error() { return ttts::g_err; }
 }

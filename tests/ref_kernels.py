@@ -25,6 +25,14 @@ class TorchRefKernels:
         dx, dw = _vjp(lambda a, c: self._conv(a, c, None, stride, dil, pad, pre_lrelu), [x, w], dy)
         return (dx if need_dx else None), dw, (dy.sum(dim=(0, 2)) if need_db else None)
 
+    # ---- transposed convolution: y = conv_transpose1d(x, w[Cin, Cout, K], b, stride, padding)   (Generator.ups, vq2.py:369-378) ----
+    def convT_fwd(self, x, w, b, stride, pad):
+        return F.conv_transpose1d(x, w, b, stride=stride, padding=pad)
+
+    def convT_bwd(self, dy, x, w, stride, pad, need_db):
+        dx, dw = _vjp(lambda a, c: F.conv_transpose1d(a, c, None, stride=stride, padding=pad), [x, w], dy)
+        return dx, dw, (dy.sum(dim=(0, 2)) if need_db else None)
+
     # ---- weight norm over dim 0: w = g * v / ||v||                                           ttts_weight_norm / ttts_weight_norm_bwd ----
     @staticmethod
     def _wn(v, g):
@@ -46,6 +54,24 @@ class TorchRefKernels:
 
     def mul_mask(self, a, mask):                                      # a [B,C,T], mask [B,T]
         return a * mask[:, None, :]
+
+    def lrelu_fwd(self, x, slope):
+        return F.leaky_relu(x, slope)
+
+    def lrelu_bwd(self, dy, x, slope):
+        return dy * torch.where(x > 0, torch.ones_like(x), torch.full_like(x, slope))
+
+    def tanh_fwd(self, x):
+        return torch.tanh(x)
+
+    def tanh_bwd(self, dy, x):
+        return dy * (1 - torch.tanh(x) ** 2)
+
+    def add_bcast_fwd(self, x, c):                                    # x [B,C,T] + c [B,C,1]
+        return x + c
+
+    def add_bcast_bwd(self, dy):                                      # gradient of c
+        return dy.sum(-1, keepdim=True)
 
     @staticmethod
     def _glu(raw):

@@ -27,6 +27,7 @@ def emu(tmp_path_factory):
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     lib.emu_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10
     lib.emu_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9
+    lib.emu_bias_grad.argtypes = [vp, vp, i32, i32, i32]
     lib.emu_last_error.restype = ctypes.c_char_p
     return lib
 
@@ -73,6 +74,35 @@ def test_conv1d_backward_on_the_cpu_emulation(emu, case):
     dw2 = torch.zeros_like(wd)
     assert emu.emu_conv1d_bwd_weight(p(dy), p(xd), p(dw2), None, B, Cin, T, Cout, K, stride, dil, pad, int(lrelu)) == 0
     assert float((dw2 - w.grad).abs().max()) <= 5e-5 * wscale
+
+
+@pytest.mark.parametrize("Cin,Cout,K,stride,pad,T", [(12, 6, 16, 10, 3, 7), (8, 4, 16, 8, 4, 9), (6, 3, 8, 2, 3, 20), (5, 40, 2, 2, 0, 33)])
+def test_transposed_convolution_from_the_same_kernels(emu, Cin, Cout, K, stride, pad, T):
+    """ConvTranspose1d (the Generator's up-sampling layers, vq2.py:369-378: kernel / stride pairs (16,10) (16,8) (8,2) (2,2)) needs no kernel
+    of its own: forward = the dgrad kernel, weight gradient = the wgrad kernel with input and output-gradient swapped (dx = the forward
+    convolution, GPU-validated already).  Checked against torch's conv_transpose1d and its autograd."""
+    B = 2
+    g = torch.Generator().manual_seed(Cin * 131 + K)
+    x = torch.randn(B, Cin, T, generator=g, requires_grad=True)
+    w = (torch.randn(Cin, Cout, K, generator=g) / (Cin * K) ** 0.5).requires_grad_(True)
+    y = F.conv_transpose1d(x, w, None, stride=stride, padding=pad)
+    Tout = (T - 1) * stride - 2 * pad + K
+    assert y.shape[-1] == Tout
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    p = lambda t: t.data_ptr() if t is not None else None
+    xd, wd = x.detach().contiguous(), w.detach().contiguous()
+    got = torch.full((B, Cout, Tout), 9.0)
+    assert emu.emu_conv1d_bwd_input(p(xd), p(wd), None, p(got), B, Cout, Tout, Cin, K, stride, 1, pad, 0, 0) == 0, emu.emu_last_error()
+    assert float((got - y.detach()).abs().max()) <= 2e-5 * max(1.0, float(y.detach().abs().max()))
+    dw = torch.zeros_like(wd)
+    assert emu.emu_conv1d_bwd_weight(p(xd), p(dy), p(dw), None, B, Cout, Tout, Cin, K, stride, 1, pad, 0) == 0, emu.emu_last_error()
+    assert float((dw - w.grad).abs().max()) <= 5e-5 * max(1.0, float(w.grad.abs().max()))
+    db = torch.full((Cout,), 1.5)
+    assert emu.emu_bias_grad(p(dy), p(db), B, Cout, Tout) == 0
+    assert float((db - 1.5 - dy.sum(dim=(0, 2))).abs().max()) <= 5e-5 * max(1.0, float(dy.sum(dim=(0, 2)).abs().max()))
+    # dx of the transposed convolution is the plain forward convolution of dy with the same weight
+    assert float((F.conv1d(dy, wd, None, stride=stride, padding=pad) - x.grad).abs().max()) <= 2e-5 * max(1.0, float(x.grad.abs().max()))
 
 
 def test_bad_arguments_are_reported(emu):

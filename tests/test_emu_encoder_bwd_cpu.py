@@ -37,6 +37,10 @@ def emu(tmp_path_factory):
     lib.ttts_mish.argtypes = [vp, vp, vp, i64, i32, vp]
     lib.ttts_wn_gate.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.ttts_weight_norm_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.ttts_lrelu.argtypes = [vp, vp, vp, i64, f32, i32, vp]
+    lib.ttts_tanh.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.ttts_add_bcast.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.ttts_sum_t.argtypes = [vp, vp, i32, i32, vp]
     lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
     lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
     lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -97,6 +101,28 @@ def test_glu_mish_gate(emu):
         close(draw, wr)
         if cond is not None:
             close(dcond, wc)
+
+
+def test_lrelu_tanh_broadcast_add_and_row_sum(emu):
+    x, dy = rnd(3, 4, 21), rnd(3, 4, 21, seed=1)
+    o = torch.empty_like(x)
+    for slope in (0.1, 0.01):
+        assert emu.ttts_lrelu(P(x), None, P(o), x.numel(), slope, 0, None) == 0
+        close(o, R.lrelu_fwd(x, slope), 1e-7)
+        assert emu.ttts_lrelu(P(x), P(dy), P(o), x.numel(), slope, 1, None) == 0
+        close(o, R.lrelu_bwd(dy, x, slope), 1e-7)
+    assert emu.ttts_tanh(P(x), None, P(o), x.numel(), 0, None) == 0
+    close(o, R.tanh_fwd(x))
+    assert emu.ttts_tanh(P(x), P(dy), P(o), x.numel(), 1, None) == 0
+    close(o, R.tanh_bwd(dy, x))
+    c, bias = rnd(3, 4, 1, seed=2), rnd(4, seed=3)
+    assert emu.ttts_add_bcast(P(x), P(c), P(o), 3, 4, 21, 1, None) == 0
+    close(o, R.add_bcast_fwd(x, c), 0)
+    assert emu.ttts_add_bcast(P(x), P(bias), P(o), 3, 4, 21, 0, None) == 0
+    close(o, x + bias.view(1, -1, 1), 0)
+    s = torch.empty(3, 4, 1)
+    assert emu.ttts_sum_t(P(dy), P(s), 12, 21, None) == 0
+    close(s, R.add_bcast_bwd(dy))
 
 
 def test_weight_norm_backward(emu):

@@ -191,6 +191,27 @@ def test_training_graph_gradients_vs_reference_golden(enc, golden_dir):
         assert abs(float((gk * d).sum()) - float(g["proj"][i])) <= 1e-2 * scale + floor, k
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the decoder (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_decoder_training_graph_vs_reference_golden(golden_dir):
+    """train_decoder.DecoderGraph over the CUDA kernels: waveform and parameter gradients of the REAL reference Generator (decoder.npz)"""
+    from oracle import decoder_oracle as DO
+    from ttts_b200.vqvae.train_decoder import DecoderGraph
+    from ttts_b200.vqvae.train_encoder import CudaKernels
+    dec = np.load(os.path.join(golden_dir, "decoder.npz"))
+    graph = DecoderGraph(CudaKernels(), {k: v.cuda() for k, v in DO.init_params(seed=9).items()})
+    y = graph.forward(torch.tensor(dec["z"]).cuda(), torch.tensor(dec["g"]).cuda())
+    assert np.linalg.norm(y.v.cpu().numpy() - dec["y"]) <= 5e-5 * np.linalg.norm(dec["y"])
+    R = torch.randn(y.v.shape, generator=torch.Generator().manual_seed(32))
+    grads = graph.backward(R.cuda())
+    floor = 1e-6 * float(np.sqrt((dec["norm"] ** 2).sum()))
+    for i, k in enumerate([str(n) for n in dec["names"]]):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(dec["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(dec["proj"][i])) <= 1e-2 * scale + floor, k
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

@@ -296,6 +296,12 @@ int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, int32_t accumulate, void* stream) {
     return ttts::conv1d_bwd_input(dy, w, x, dx, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, accumulate, (cudaStream_t)stream);
 }
+int ttts_bias_grad(const float* dy, float* db, int32_t B, int32_t C, int32_t T, void* stream) {
+    TTTS_CHECK_ARG(dy && db && B > 0 && C > 0 && T > 0, "bias_grad: bad args");
+    TTTS_CUDA(ttts::launch_plain(ttts::conv1d_bgrad_kernel, dim3(C), dim3(256), 0, (cudaStream_t)stream, dy, db, B, C, T));
+    TTTS_LAUNCH_CHECK("bias_grad");
+    return TTTS_OK;
+}
 int ttts_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                            int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, void* stream) {
     return ttts::conv1d_bwd_weight(dy, x, dw, db, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, (cudaStream_t)stream);

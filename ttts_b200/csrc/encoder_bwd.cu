@@ -54,6 +54,34 @@ __global__ void mish_kernel(const float* __restrict__ x, const float* __restrict
         o[i] = dir == 0 ? v * th : dy[i] * (th + v * (1.f - th * th) * sigmoid_f(v));
     }
 }
+// leaky ReLU with an explicit slope (the Generator uses 0.1 between stages and torch's default 0.01 before conv_post, vq2.py:392,404)
+__global__ void lrelu_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ o, size_t n, float slope, int dir) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        o[i] = dir == 0 ? (v > 0.f ? v : slope * v) : dy[i] * (v > 0.f ? 1.f : slope);
+    }
+}
+__global__ void tanh_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ o, size_t n, int dir) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = tanhf(x[i]);
+        o[i] = dir == 0 ? t : dy[i] * (1.f - t * t);
+    }
+}
+// o[b, c, t] = a[b, c, t] + v[c] (per_batch = 0: a bias) or + v[b, c] (per_batch = 1: a conditioning vector)
+__global__ void add_bcast_kernel(const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ o, int C, int T, size_t n, int per_batch) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bc = i / T;
+        o[i] = a[i] + v[per_batch ? bc : bc % C];
+    }
+}
+// o[b, c] = sum_t a[b, c, t] : one warp per row, fixed order
+__global__ void __launch_bounds__(32) sum_t_kernel(const float* __restrict__ a, float* __restrict__ o, int T) {
+    const size_t row = blockIdx.x;
+    float s = 0.f;
+    for (int t = threadIdx.x; t < T; t += 32) s += a[row * T + t];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) o[row] = s;
+}
 // posterior sample backward: z = (m + eps e^logs) mask  ->  dm = dz mask ; dlogs = dz mask eps e^logs          (vq2.py:742-744)
 __global__ void posterior_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ eps,
                                      const float* __restrict__ mask, float* __restrict__ dstats, int C, int T, size_t n) {
@@ -314,6 +342,31 @@ TTTS_API int ttts_wn_gate(const float* raw, const float* cond, const float* dy, 
     TTTS_CHECK_ARG(raw && out && (!backward || dy) && B > 0 && B <= 65535 && H > 0 && T > 0, "wn_gate: bad args");
     TTTS_CUDA(launch_plain(gate_kernel, dim3(H, B), dim3(32), 0, (cudaStream_t)stream, raw, cond, dy, out, dcond, H, T, backward));
     TTTS_LAUNCH_CHECK("wn_gate");
+    return TTTS_OK;
+}
+TTTS_API int ttts_lrelu(const float* x, const float* dy, float* out, int64_t n, float slope, int32_t backward, void* stream) {
+    TTTS_CHECK_ARG(x && out && (!backward || dy) && n > 0, "lrelu: bad args");
+    TTTS_CUDA(launch_plain(lrelu_kernel, dim3(ew_blocks((size_t)n)), dim3(256), 0, (cudaStream_t)stream, x, dy, out, (size_t)n, slope, backward));
+    TTTS_LAUNCH_CHECK("lrelu");
+    return TTTS_OK;
+}
+TTTS_API int ttts_tanh(const float* x, const float* dy, float* out, int64_t n, int32_t backward, void* stream) {
+    TTTS_CHECK_ARG(x && out && (!backward || dy) && n > 0, "tanh: bad args");
+    TTTS_CUDA(launch_plain(tanh_kernel, dim3(ew_blocks((size_t)n)), dim3(256), 0, (cudaStream_t)stream, x, dy, out, (size_t)n, backward));
+    TTTS_LAUNCH_CHECK("tanh");
+    return TTTS_OK;
+}
+TTTS_API int ttts_add_bcast(const float* a, const float* v, float* out, int32_t B, int32_t C, int32_t T, int32_t per_batch, void* stream) {
+    TTTS_CHECK_ARG(a && v && out && B > 0 && C > 0 && T > 0, "add_bcast: bad args");
+    const size_t n = (size_t)B * C * T;
+    TTTS_CUDA(launch_plain(add_bcast_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, v, out, C, T, n, per_batch));
+    TTTS_LAUNCH_CHECK("add_bcast");
+    return TTTS_OK;
+}
+TTTS_API int ttts_sum_t(const float* a, float* out, int32_t rows, int32_t T, void* stream) {
+    TTTS_CHECK_ARG(a && out && rows > 0 && T > 0, "sum_t: bad args");
+    TTTS_CUDA(launch_plain(sum_t_kernel, dim3(rows), dim3(32), 0, (cudaStream_t)stream, a, out, T));
+    TTTS_LAUNCH_CHECK("sum_t");
     return TTTS_OK;
 }
 TTTS_API int ttts_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg, int32_t Cout, int32_t n_per_out, void* stream) {

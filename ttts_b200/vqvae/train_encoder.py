@@ -116,6 +116,36 @@ class Ops:
     def glu(self, raw):
         return self._unary("glu", raw)
 
+    def lrelu(self, x, slope):
+        return self._unary("lrelu", x, slope)
+
+    def tanh(self, x):
+        return self._unary("tanh", x)
+
+    def add_bcast(self, x, c):
+        """x [B,C,T] + c [B,C,1]"""
+        y = Var(self.K.add_bcast_fwd(x.v, c.v))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, y.g); self._acc(c, self.K.add_bcast_bwd(y.g))
+        self.tape.record(bwd)
+        return y
+
+    def convT(self, x, w, b, stride, pad):
+        """ConvTranspose1d with weight [Cin, Cout, K] (Generator.ups, vq2.py:369-378)"""
+        y = Var(self.K.convT_fwd(x.v, w.v, b.v if b is not None else None, stride, pad))
+
+        def bwd():
+            if y.g is None:
+                return
+            dx, dw, db = self.K.convT_bwd(y.g, x.v, w.v, stride, pad, b is not None)
+            self._acc(x, dx); self._acc(w, dw)
+            if b is not None:
+                self._acc(b, db)
+        self.tape.record(bwd)
+        return y
+
     def mish(self, x):
         return self._unary("mish", x)
 
@@ -335,6 +365,11 @@ class CudaKernels:
             lib.ttts_mish.argtypes = [vp, vp, vp, i64, i32, vp]
             lib.ttts_wn_gate.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
             lib.ttts_weight_norm_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+            lib.ttts_lrelu.argtypes = [vp, vp, vp, i64, f32, i32, vp]
+            lib.ttts_tanh.argtypes = [vp, vp, vp, i64, i32, vp]
+            lib.ttts_add_bcast.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+            lib.ttts_sum_t.argtypes = [vp, vp, i32, i32, vp]
+            lib.ttts_bias_grad.argtypes = [vp, vp, i32, i32, i32, vp]
             lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
             lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
             lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -373,6 +408,74 @@ class CudaKernels:
         db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if need_db else None
         self._chk(lib.ttts_conv1d_bwd_weight(p(dy), p(x), p(dw), p(db), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), st), "ttts_conv1d_bwd_weight")
         return dx, dw, db
+
+    def convT_fwd(self, x, w, b, stride, pad):
+        """conv_transpose1d = the input gradient of a convolution whose weight is w read as [Cout' = Cin, Cin' = Cout, K]"""
+        self._req(x, w, b)
+        B, Cin, T = x.shape
+        _, Cout, K = w.shape
+        Tout = (T - 1) * stride - 2 * pad + K
+        y = torch.empty(B, Cout, Tout, dtype=torch.float32, device=x.device)
+        p, lib, st = self._p, self.lib, self._st()
+        self._chk(lib.ttts_conv1d_bwd_input(p(x), p(w), None, p(y), B, Cout, Tout, Cin, K, stride, 1, pad, 0, 0, st), "ttts_conv1d_bwd_input (convT forward)")
+        if b is not None:
+            self._chk(lib.ttts_add_bcast(p(y), p(b), p(y), B, Cout, Tout, 0, st), "ttts_add_bcast (bias)")
+        return y
+
+    def convT_bwd(self, dy, x, w, stride, pad, need_db):
+        self._req(dy, x, w)
+        B, Cin, T = x.shape
+        _, Cout, K = w.shape
+        Tout = dy.shape[-1]
+        p, lib, st = self._p, self.lib, self._st()
+        dx = self.E.conv1d(dy, w, None, stride=stride, dil=1, pad=pad)                      # [B, Cin, T]
+        assert dx.shape == x.shape
+        dw = torch.zeros_like(w)
+        self._chk(lib.ttts_conv1d_bwd_weight(p(x), p(dy), p(dw), None, B, Cout, Tout, Cin, K, stride, 1, pad, 0, st), "ttts_conv1d_bwd_weight (convT)")
+        db = None
+        if need_db:
+            db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            self._chk(lib.ttts_bias_grad(p(dy), p(db), B, Cout, Tout, st), "ttts_bias_grad")
+        return dx, dw, db
+
+    def lrelu_fwd(self, x, slope):
+        self._req(x)
+        y = torch.empty_like(x)
+        self._chk(self.lib.ttts_lrelu(self._p(x), None, self._p(y), x.numel(), float(slope), 0, self._st()), "ttts_lrelu")
+        return y
+
+    def lrelu_bwd(self, dy, x, slope):
+        self._req(dy, x)
+        d = torch.empty_like(x)
+        self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dy), self._p(d), x.numel(), float(slope), 1, self._st()), "ttts_lrelu (backward)")
+        return d
+
+    def tanh_fwd(self, x):
+        self._req(x)
+        y = torch.empty_like(x)
+        self._chk(self.lib.ttts_tanh(self._p(x), None, self._p(y), x.numel(), 0, self._st()), "ttts_tanh")
+        return y
+
+    def tanh_bwd(self, dy, x):
+        self._req(dy, x)
+        d = torch.empty_like(x)
+        self._chk(self.lib.ttts_tanh(self._p(x), self._p(dy), self._p(d), x.numel(), 1, self._st()), "ttts_tanh (backward)")
+        return d
+
+    def add_bcast_fwd(self, x, c):
+        c = c.contiguous()
+        self._req(x, c)
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        self._chk(self.lib.ttts_add_bcast(self._p(x), self._p(c), self._p(y), B, C, T, 1, self._st()), "ttts_add_bcast")
+        return y
+
+    def add_bcast_bwd(self, dy):
+        self._req(dy)
+        B, C, T = dy.shape
+        o = torch.empty(B, C, 1, dtype=torch.float32, device=dy.device)
+        self._chk(self.lib.ttts_sum_t(self._p(dy), self._p(o), B * C, T, self._st()), "ttts_sum_t")
+        return o
 
     def wn_fwd(self, v, g):
         self._req(v, g)
