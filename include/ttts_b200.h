@@ -316,6 +316,13 @@ int ttts_masked_mean_bwd(const float* dy, const int64_t* lens, float* dx, int32_
 int ttts_posterior_sample_bwd(const float* dz, const float* stats, const float* eps, const float* mask, float* dstats, int32_t B, int32_t C,
                               int32_t T, void* stream);
 
+/* adversarial losses of the VQ-VAE-GAN step (ttts/vqvae/losses.py:7-44; csrc/gan_losses.cu, same validation status).  Deterministic
+ * two-stage reductions; scratch = 256 floats; out / dL are device scalars. */
+int ttts_lsgan_loss(const float* x, float c, int64_t n, float* scratch, float* out, void* stream);                 /* mean((c - x)^2)            */
+int ttts_lsgan_loss_bwd(const float* x, float c, const float* dL, int64_t n, float* dx, void* stream);
+int ttts_l1_mean(const float* a, const float* b, int64_t n, float* scratch, float* out, void* stream);               /* mean(|a - b|), a detached  */
+int ttts_l1_mean_bwd(const float* a, const float* b, const float* dL, int64_t n, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

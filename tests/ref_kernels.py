@@ -15,15 +15,28 @@ def _vjp(fn, inputs, dy):
 class TorchRefKernels:
     # ---- convolution: y = conv1d(leaky_relu(x, 0.1) if pre_lrelu else x, w, b)            ttts_conv1d_f32 (post = 0) / ttts_conv1d_bwd_* ----
     @staticmethod
-    def _conv(x, w, b, stride, dil, pad, pre_lrelu):
-        return F.conv1d(F.leaky_relu(x, 0.1) if pre_lrelu else x, w, b, stride=stride, dilation=dil, padding=pad)
+    def _conv(x, w, b, stride, dil, pad, pre_lrelu, groups=1):
+        return F.conv1d(F.leaky_relu(x, 0.1) if pre_lrelu else x, w, b, stride=stride, dilation=dil, padding=pad, groups=groups)
 
-    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
-        return self._conv(x, w, b, stride, dil, pad, pre_lrelu)
+    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, groups=1):
+        return self._conv(x, w, b, stride, dil, pad, pre_lrelu, groups)
 
-    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
-        dx, dw = _vjp(lambda a, c: self._conv(a, c, None, stride, dil, pad, pre_lrelu), [x, w], dy)
+    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
+        dx, dw = _vjp(lambda a, c: self._conv(a, c, None, stride, dil, pad, pre_lrelu, groups), [x, w], dy)
         return (dx if need_dx else None), dw, (dy.sum(dim=(0, 2)) if need_db else None)
+
+    # ---- adversarial losses (losses.py:7-44): scalars as [1] tensors                         ttts_lsgan_loss / ttts_l1_mean ----
+    def lsgan_fwd(self, x, c):
+        return ((c - x) ** 2).mean().reshape(1)
+
+    def lsgan_bwd(self, dL, x, c):
+        return dL * 2 * (x - c) / x.numel()
+
+    def l1_fwd(self, a, b):
+        return (a - b).abs().mean().reshape(1)
+
+    def l1_bwd(self, dL, a, b):                                       # gradient of b; a is the detached (real) side
+        return dL * torch.sign(b - a) / b.numel()
 
     # ---- transposed convolution: y = conv_transpose1d(x, w[Cin, Cout, K], b, stride, padding)   (Generator.ups, vq2.py:369-378) ----
     def convT_fwd(self, x, w, b, stride, pad):

@@ -1,0 +1,52 @@
+"""CPU emulation of the adversarial-loss reductions (tests/emu builds ttts_b200/csrc/gan_losses.cu for the host) against the op contract
+tests/ref_kernels.py (losses.py:7-44 of the reference)."""
+import ctypes
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ref_kernels import TorchRefKernels  # noqa: E402
+
+R = TorchRefKernels()
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = str(tmp_path_factory.mktemp("emu") / "libgan_losses_emu.so")
+    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
+           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "gan_losses_emu.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(so)
+    vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
+    lib.ttts_lsgan_loss.argtypes = [vp, f32, i64, vp, vp, vp]
+    lib.ttts_lsgan_loss_bwd.argtypes = [vp, f32, vp, i64, vp, vp]
+    lib.ttts_l1_mean.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.ttts_l1_mean_bwd.argtypes = [vp, vp, vp, i64, vp, vp]
+    return lib
+
+
+@pytest.mark.parametrize("n", [1, 255, 70001])
+def test_loss_reductions_and_their_gradients(emu, n):
+    g = torch.Generator().manual_seed(n)
+    x, a = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    scratch, out, dL = torch.zeros(256), torch.zeros(1), torch.tensor([0.7])
+    for c in (0.0, 1.0):
+        assert emu.ttts_lsgan_loss(x.data_ptr(), c, n, scratch.data_ptr(), out.data_ptr(), None) == 0
+        assert abs(float(out) - float(R.lsgan_fwd(x, c))) <= 2e-6 * max(1.0, float(R.lsgan_fwd(x, c)))
+        dx = torch.empty(n)
+        assert emu.ttts_lsgan_loss_bwd(x.data_ptr(), c, dL.data_ptr(), n, dx.data_ptr(), None) == 0
+        assert float((dx - R.lsgan_bwd(dL, x, c)).abs().max()) <= 1e-6
+    assert emu.ttts_l1_mean(a.data_ptr(), x.data_ptr(), n, scratch.data_ptr(), out.data_ptr(), None) == 0
+    assert abs(float(out) - float(R.l1_fwd(a, x))) <= 2e-6 * max(1.0, float(R.l1_fwd(a, x)))
+    db = torch.empty(n)
+    assert emu.ttts_l1_mean_bwd(a.data_ptr(), x.data_ptr(), dL.data_ptr(), n, db.data_ptr(), None) == 0
+    assert float((db - R.l1_bwd(dL, a, x)).abs().max()) <= 1e-7

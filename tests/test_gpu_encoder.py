@@ -212,6 +212,40 @@ def test_decoder_training_graph_vs_reference_golden(golden_dir):
         assert abs(float((gk * d).sum()) - float(dec["proj"][i])) <= 1e-2 * scale + floor, k
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the discriminators (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_discriminator_training_graph_vs_reference_golden(golden_dir):
+    """train_disc.DiscriminatorGraph over the CUDA kernels: the three adversarial losses, the discriminator step's parameter gradients and
+    dL/dy_hat of the generator step against the REAL reference MultiPeriodDiscriminator (disc.npz)"""
+    from oracle import disc_oracle as DO
+    from ttts_b200.vqvae.train_disc import DiscriminatorGraph
+    from ttts_b200.vqvae.train_encoder import CudaKernels, Var
+    z = np.load(os.path.join(golden_dir, "disc.npz"))
+    P = {k: v.cuda() for k, v in DO.init_params(seed=4).items()}
+    y, y_hat = torch.tensor(z["y"]).cuda(), torch.tensor(z["y_hat"]).cuda()
+    graph = DiscriminatorGraph(CudaKernels(), P)
+    real, _ = graph.forward(y)
+    gen, _ = graph.forward(y_hat)
+    loss = graph.discriminator_loss(real, gen)
+    assert abs(float(loss.v) - float(z["loss_d"])) <= 1e-4 * float(z["loss_d"])
+    grads = graph.backward(loss)
+    floor = 1e-6 * float(np.sqrt((z["norm"] ** 2).sum()))
+    for i, k in enumerate([str(n) for n in z["names"]]):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(z["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(z["proj"][i])) <= 1e-2 * scale + floor, k
+    graph = DiscriminatorGraph(CudaKernels(), P)
+    yh = Var(y_hat)
+    _, fmap_r = graph.forward(y)
+    gen, fmap_g = graph.forward(yh)
+    loss_gen, loss_fm = graph.generator_losses(gen, fmap_r, fmap_g)
+    assert abs(float(loss_gen.v) - float(z["loss_gen"])) <= 1e-4 * float(z["loss_gen"])
+    assert abs(float(loss_fm.v) - float(z["loss_fm"])) <= 1e-4 * float(z["loss_fm"])
+    graph.backward(graph.ops.add(loss_gen, loss_fm))
+    assert np.linalg.norm(yh.g.cpu().numpy() - z["dy_hat"]) <= 1e-3 * np.linalg.norm(z["dy_hat"])
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

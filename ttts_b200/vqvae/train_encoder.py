@@ -52,13 +52,14 @@ class Ops:
             return
         var.g = g if var.g is None else self.K.add(var.g, g)
 
-    def conv(self, x, w, b=None, stride=1, dil=1, pad=0, pre_lrelu=False, need_dx=True):
-        y = Var(self.K.conv_fwd(x.v, w.v, b.v if b is not None else None, stride, dil, pad, pre_lrelu))
+    def conv(self, x, w, b=None, stride=1, dil=1, pad=0, pre_lrelu=False, need_dx=True, groups=1):
+        kw = {} if groups == 1 else {"groups": groups}
+        y = Var(self.K.conv_fwd(x.v, w.v, b.v if b is not None else None, stride, dil, pad, pre_lrelu, **kw))
 
         def bwd():
             if y.g is None:
                 return
-            dx, dw, db = self.K.conv_bwd(y.g, x.v, w.v, stride, dil, pad, pre_lrelu, need_dx, b is not None)
+            dx, dw, db = self.K.conv_bwd(y.g, x.v, w.v, stride, dil, pad, pre_lrelu, need_dx, b is not None, **kw)
             if need_dx:
                 self._acc(x, dx)
             self._acc(w, dw)
@@ -121,6 +122,26 @@ class Ops:
 
     def tanh(self, x):
         return self._unary("tanh", x)
+
+    def lsgan(self, x, c):
+        """mean((c - x)^2) as a [1] tensor (losses.py:18-44)"""
+        y = Var(self.K.lsgan_fwd(x.v, c))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, self.K.lsgan_bwd(y.g, x.v, c))
+        self.tape.record(bwd)
+        return y
+
+    def l1_mean(self, a_const, b):
+        """mean(|a - b|) with a detached (losses.py:7-15)"""
+        y = Var(self.K.l1_fwd(a_const, b.v))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(b, self.K.l1_bwd(y.g, a_const, b.v))
+        self.tape.record(bwd)
+        return y
 
     def add_bcast(self, x, c):
         """x [B,C,T] + c [B,C,1]"""
@@ -370,6 +391,10 @@ class CudaKernels:
             lib.ttts_add_bcast.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
             lib.ttts_sum_t.argtypes = [vp, vp, i32, i32, vp]
             lib.ttts_bias_grad.argtypes = [vp, vp, i32, i32, i32, vp]
+            lib.ttts_lsgan_loss.argtypes = [vp, f32, i64, vp, vp, vp]
+            lib.ttts_lsgan_loss_bwd.argtypes = [vp, f32, vp, i64, vp, vp]
+            lib.ttts_l1_mean.argtypes = [vp, vp, i64, vp, vp, vp]
+            lib.ttts_l1_mean_bwd.argtypes = [vp, vp, vp, i64, vp, vp]
             lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
             lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
             lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -392,10 +417,23 @@ class CudaKernels:
             assert t is None or (t.is_contiguous() and t.dtype in (torch.float32, torch.int64)), "contiguous fp32 / int64 tensors only"
 
     # ---- convolution / weight norm ----
-    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
+    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, groups=1):
+        if groups > 1:
+            # grouped convolution (DiscriminatorS, vq2.py:498-507) as one launch per group on channel slices: correct, not fast -- a grouped
+            # variant of the kernels is the follow-up once this row is measured
+            ci, co = x.shape[1] // groups, w.shape[0] // groups
+            return torch.cat([self.conv_fwd(x[:, g * ci:(g + 1) * ci].contiguous(), w[g * co:(g + 1) * co].contiguous(),
+                                            b[g * co:(g + 1) * co].contiguous() if b is not None else None, stride, dil, pad, pre_lrelu)
+                              for g in range(groups)], dim=1)
         return self.E.conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=pre_lrelu)
 
-    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
+    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
+        if groups > 1:
+            ci, co = x.shape[1] // groups, w.shape[0] // groups
+            parts = [self.conv_bwd(dy[:, g * co:(g + 1) * co].contiguous(), x[:, g * ci:(g + 1) * ci].contiguous(), w[g * co:(g + 1) * co].contiguous(),
+                                   stride, dil, pad, pre_lrelu, need_dx, need_db) for g in range(groups)]
+            return (torch.cat([p[0] for p in parts], dim=1) if need_dx else None, torch.cat([p[1] for p in parts], dim=0),
+                    torch.cat([p[2] for p in parts], dim=0) if need_db else None)
         self._req(dy, x, w)
         B, Cin, Tin = x.shape
         Cout, _, K = w.shape
@@ -437,6 +475,36 @@ class CudaKernels:
             db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
             self._chk(lib.ttts_bias_grad(p(dy), p(db), B, Cout, Tout, st), "ttts_bias_grad")
         return dx, dw, db
+
+    def _scratch(self, dev):
+        s = getattr(self, "_red", None)
+        if s is None or s.device != dev:
+            s = self._red = torch.empty(256, dtype=torch.float32, device=dev)
+        return s
+
+    def lsgan_fwd(self, x, c):
+        self._req(x)
+        o = torch.empty(1, dtype=torch.float32, device=x.device)
+        self._chk(self.lib.ttts_lsgan_loss(self._p(x), float(c), x.numel(), self._p(self._scratch(x.device)), self._p(o), self._st()), "ttts_lsgan_loss")
+        return o
+
+    def lsgan_bwd(self, dL, x, c):
+        self._req(dL, x)
+        d = torch.empty_like(x)
+        self._chk(self.lib.ttts_lsgan_loss_bwd(self._p(x), float(c), self._p(dL), x.numel(), self._p(d), self._st()), "ttts_lsgan_loss_bwd")
+        return d
+
+    def l1_fwd(self, a, b):
+        self._req(a, b)
+        o = torch.empty(1, dtype=torch.float32, device=b.device)
+        self._chk(self.lib.ttts_l1_mean(self._p(a), self._p(b), b.numel(), self._p(self._scratch(b.device)), self._p(o), self._st()), "ttts_l1_mean")
+        return o
+
+    def l1_bwd(self, dL, a, b):
+        self._req(dL, a, b)
+        d = torch.empty_like(b)
+        self._chk(self.lib.ttts_l1_mean_bwd(self._p(a), self._p(b), self._p(dL), b.numel(), self._p(d), self._st()), "ttts_l1_mean_bwd")
+        return d
 
     def lrelu_fwd(self, x, slope):
         self._req(x)
