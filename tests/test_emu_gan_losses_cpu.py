@@ -34,7 +34,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-@pytest.mark.parametrize("n", [1, 255, 70001])
+@pytest.mark.parametrize("n", [255, 70001])
 def test_loss_reductions_and_their_gradients(emu, n):
     g = torch.Generator().manual_seed(n)
     x, a = torch.randn(n, generator=g), torch.randn(n, generator=g)
