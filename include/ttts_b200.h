@@ -322,6 +322,12 @@ int ttts_lsgan_loss(const float* x, float c, int64_t n, float* scratch, float* o
 int ttts_lsgan_loss_bwd(const float* x, float c, const float* dL, int64_t n, float* dx, void* stream);
 int ttts_l1_mean(const float* a, const float* b, int64_t n, float* scratch, float* out, void* stream);               /* mean(|a - b|), a detached  */
 int ttts_l1_mean_bwd(const float* a, const float* b, const float* dL, int64_t n, float* db, void* stream);
+/* kl_loss (losses.py:47-61): out2[0] = sum((logs_p - logs_q - 0.5 + 0.5 (z_p - m_p)^2 exp(-2 logs_p)) mask) / sum(mask), out2[1] = sum(mask);
+ * tensors [B,C,T], mask [B,T]; scratch = 512 floats.  Backward: any of the four gradient outputs may be NULL. */
+int ttts_kl_loss(const float* z_p, const float* logs_q, const float* m_p, const float* logs_p, const float* mask, int32_t B, int32_t C,
+                 int32_t T, float* scratch, float* out2, void* stream);
+int ttts_kl_loss_bwd(const float* z_p, const float* m_p, const float* logs_p, const float* mask, const float* dL, const float* fwd_out2,
+                     int32_t B, int32_t C, int32_t T, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p, void* stream);
 
 #ifdef __cplusplus
 }

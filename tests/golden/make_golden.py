@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -232,6 +232,37 @@ def disc_case():
     print("disc ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "loss_d %.5f loss_gen %.5f loss_fm %.5f" % (float(loss_d), float(loss_gen), float(loss_fm)))
 
 
+def flow_case():
+    """The REAL reference flow, ResidualCouplingBlock(192, 192, 5, 1, 4, gin_channels=512) (ttts/vqvae/vq2.py:209-246), forward direction as in
+    SynthesizerTrn.forward (:858), followed by the KL term of the trainer (losses.py:47-61): z_p, the loss and per parameter tensor the
+    gradient norm / projection, plus the gradients of z and g.  `post` is given non-zero weights (its zero init makes the flow the identity)."""
+    from oracle import flow_oracle as FO
+    from ttts.vqvae.vq2 import ResidualCouplingBlock
+    from ttts.vqvae import losses as RL
+    net = ResidualCouplingBlock(192, 192, 5, 1, 4, gin_channels=512).eval()
+    P = FO.init_params(seed=6)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(P.keys()), sorted(set(sd.keys()) ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P)
+    z, ge, mask, logs_q, m_p, logs_p = FO.golden_inputs()
+    z.requires_grad_(True); ge.requires_grad_(True)
+    z_p = net(z, mask, g=ge)
+    loss = RL.kl_loss(z_p, logs_q, m_p, logs_p, mask)
+    loss.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net.named_parameters():
+        gk = prm.grad
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    path = os.path.join(ROOT, "tests", "golden", "flow.npz")
+    # inputs are NOT stored: the test regenerates them from the same seeded generator calls (FO.golden_inputs)
+    np.savez_compressed(path, z_sum=float(z.sum()), z_p=z_p.detach().numpy(), loss=float(loss), names=np.array(names), norm=np.array(norm),
+                        proj=np.array(proj), dz=z.grad.numpy(), dg=ge.grad.numpy())
+    print("flow ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "kl %.6f" % float(loss))
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -392,6 +423,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "flow":
+        flow_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "disc":
         disc_case()
         sys.exit(0)
@@ -409,6 +443,7 @@ if __name__ == "__main__":
     kv_case(gm)
     decoder_case()
     disc_case()
+    flow_case()
     vq_case()
     mel_case()
     encoder_case()

@@ -32,6 +32,18 @@ class TorchRefKernels:
     def lsgan_bwd(self, dL, x, c):
         return dL * 2 * (x - c) / x.numel()
 
+    @staticmethod
+    def _kl(z_p, logs_q, m_p, logs_p, mask):                          # mask [B, T]
+        m3 = mask[:, None, :]
+        kl = logs_p - logs_q - 0.5 + 0.5 * ((z_p - m_p) ** 2) * torch.exp(-2.0 * logs_p)
+        return (torch.sum(kl * m3) / torch.sum(m3)).reshape(1)
+
+    def kl_fwd(self, z_p, logs_q, m_p, logs_p, mask):
+        return self._kl(z_p, logs_q, m_p, logs_p, mask)
+
+    def kl_bwd(self, dL, z_p, logs_q, m_p, logs_p, mask):
+        return _vjp(lambda a, b, c, d: self._kl(a, b, c, d, mask), [z_p, logs_q, m_p, logs_p], dL)
+
     def l1_fwd(self, a, b):
         return (a - b).abs().mean().reshape(1)
 

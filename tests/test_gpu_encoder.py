@@ -246,6 +246,31 @@ def test_discriminator_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(yh.g.cpu().numpy() - z["dy_hat"]) <= 1e-3 * np.linalg.norm(z["dy_hat"])
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the flow (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_flow_training_graph_vs_reference_golden(golden_dir):
+    """train_flow.FlowGraph + the KL term over the CUDA kernels against the REAL reference ResidualCouplingBlock / kl_loss (flow.npz)"""
+    from oracle import flow_oracle as FO
+    from ttts_b200.vqvae.train_encoder import CudaKernels, Var
+    from ttts_b200.vqvae.train_flow import FlowGraph
+    z = np.load(os.path.join(golden_dir, "flow.npz"))
+    zz, ge, mask, logs_q, m_p, logs_p = [t.cuda() for t in FO.golden_inputs()]
+    graph = FlowGraph(CudaKernels(), {k: v.cuda() for k, v in FO.init_params(seed=6).items()})
+    zv, gv, mask2 = Var(zz), Var(ge), mask[:, 0].contiguous()
+    z_p = graph.forward(zv, mask2, gv)
+    assert np.abs(z_p.v.cpu().numpy() - z["z_p"]).max() <= 1e-4 * np.abs(z["z_p"]).max()
+    loss = graph.ops.kl(z_p, Var(logs_q), Var(m_p), Var(logs_p), mask2)
+    assert abs(float(loss.v) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    grads = graph.backward(loss)
+    floor = 1e-6 * float(np.sqrt((z["norm"] ** 2).sum()))
+    for i, k in enumerate([str(n) for n in z["names"]]):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(z["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(z["proj"][i])) <= 1e-2 * scale + floor, k
+    assert np.linalg.norm(zv.g.cpu().numpy() - z["dz"]) <= 1e-3 * np.linalg.norm(z["dz"])
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

@@ -133,6 +133,19 @@ class Ops:
         self.tape.record(bwd)
         return y
 
+    def kl(self, z_p, logs_q, m_p, logs_p, mask):
+        """kl_loss of the trainer (losses.py:47-61) as a [1] tensor; all four inputs are Vars, mask [B, T]"""
+        y = Var(self.K.kl_fwd(z_p.v, logs_q.v, m_p.v, logs_p.v, mask))
+
+        def bwd():
+            if y.g is None:
+                return
+            gs = self.K.kl_bwd(y.g, z_p.v, logs_q.v, m_p.v, logs_p.v, mask)
+            for var, g in zip((z_p, logs_q, m_p, logs_p), gs):
+                self._acc(var, g)
+        self.tape.record(bwd)
+        return y
+
     def l1_mean(self, a_const, b):
         """mean(|a - b|) with a detached (losses.py:7-15)"""
         y = Var(self.K.l1_fwd(a_const, b.v))
@@ -247,6 +260,15 @@ class Ops:
         self.tape.record(bwd)
         return y
 
+    def flip_c(self, x):
+        y = Var(torch.flip(x.v, [1]).contiguous())
+
+        def bwd():
+            if y.g is not None:
+                self._acc(x, torch.flip(y.g, [1]).contiguous())
+        self.tape.record(bwd)
+        return y
+
     def reshape(self, x, shape):
         y = Var(x.v.reshape(shape))
 
@@ -267,6 +289,25 @@ def kaiser_sinc_filter12(device):
     time = torch.arange(-half, half) + 0.5
     f = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
     return (f / f.sum()).to(device=device, dtype=torch.float32).contiguous()
+
+
+def wn_stack(o, P, pre, x, mask2, g, hid, n_layers, kernel_size=5):
+    """WN (modules.py:136-221; dilation_rate 1): gated convolutions conditioned on g, residual and skip paths.  Used by the posterior
+    encoders (16 layers) and by the flow's coupling layers (4 layers)."""
+    wn = lambda prefix: o.wn(P[prefix + "weight_v"], P[prefix + "weight_g"])
+    out = None
+    gc = o.reshape(o.conv(g, wn(pre + "cond_layer."), P[pre + "cond_layer.bias"]), (g.v.shape[0], 2 * hid * n_layers))
+    for i in range(n_layers):
+        raw = o.conv(x, wn(pre + "in_layers.%d." % i), P[pre + "in_layers.%d.bias" % i], pad=(kernel_size - 1) // 2)
+        acts = o.gate(raw, o.slice_c(gc, i * 2 * hid, (i + 1) * 2 * hid))
+        rs = o.conv(acts, wn(pre + "res_skip_layers.%d." % i), P[pre + "res_skip_layers.%d.bias" % i])
+        if i < n_layers - 1:
+            x = o.mul_mask(o.add(x, o.slice_c(rs, 0, hid)), mask2)
+            skip = o.slice_c(rs, hid, 2 * hid)
+        else:
+            skip = rs
+        out = skip if out is None else o.add(out, skip)
+    return o.mul_mask(out, mask2)
 
 
 class EncoderGraph:
@@ -311,20 +352,7 @@ class EncoderGraph:
         return x
 
     def wn_stack(self, x, mask2, g):
-        o, P, pre = self.ops, self.P, "enc_p.enc."
-        out = None
-        gc = o.reshape(o.conv(g, self._wn(pre + "cond_layer."), P[pre + "cond_layer.bias"]), (g.v.shape[0], 2 * HID * 16))
-        for i in range(16):
-            raw = o.conv(x, self._wn(pre + "in_layers.%d." % i), P[pre + "in_layers.%d.bias" % i], pad=2)
-            acts = o.gate(raw, o.slice_c(gc, i * 2 * HID, (i + 1) * 2 * HID))
-            rs = o.conv(acts, self._wn(pre + "res_skip_layers.%d." % i), P[pre + "res_skip_layers.%d.bias" % i])
-            if i < 15:
-                x = o.mul_mask(o.add(x, o.slice_c(rs, 0, HID)), mask2)
-                skip = o.slice_c(rs, HID, 2 * HID)
-            else:
-                skip = rs
-            out = skip if out is None else o.add(out, skip)
-        return o.mul_mask(out, mask2)
+        return wn_stack(self.ops, self.P, "enc_p.enc.", x, mask2, g, HID, 16)
 
     def posterior_audio_encoder(self, spec, wav, mask2, g, eps):
         o, P = self.ops, self.P
@@ -395,6 +423,8 @@ class CudaKernels:
             lib.ttts_lsgan_loss_bwd.argtypes = [vp, f32, vp, i64, vp, vp]
             lib.ttts_l1_mean.argtypes = [vp, vp, i64, vp, vp, vp]
             lib.ttts_l1_mean_bwd.argtypes = [vp, vp, vp, i64, vp, vp]
+            lib.ttts_kl_loss.argtypes = [vp] * 5 + [i32, i32, i32, vp, vp, vp]
+            lib.ttts_kl_loss_bwd.argtypes = [vp] * 6 + [i32, i32, i32, vp, vp, vp, vp, vp]
             lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
             lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
             lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -493,6 +523,26 @@ class CudaKernels:
         d = torch.empty_like(x)
         self._chk(self.lib.ttts_lsgan_loss_bwd(self._p(x), float(c), self._p(dL), x.numel(), self._p(d), self._st()), "ttts_lsgan_loss_bwd")
         return d
+
+    def kl_fwd(self, z_p, logs_q, m_p, logs_p, mask):
+        self._req(z_p, logs_q, m_p, logs_p, mask)
+        B, C, T = z_p.shape
+        dev = z_p.device
+        if getattr(self, "_red2", None) is None or self._red2.device != dev:
+            self._red2 = torch.empty(512, dtype=torch.float32, device=dev)
+        self._kl_out = torch.empty(2, dtype=torch.float32, device=dev)
+        self._chk(self.lib.ttts_kl_loss(self._p(z_p), self._p(logs_q), self._p(m_p), self._p(logs_p), self._p(mask), B, C, T, self._p(self._red2),
+                                        self._p(self._kl_out), self._st()), "ttts_kl_loss")
+        return self._kl_out[:1]
+
+    def kl_bwd(self, dL, z_p, logs_q, m_p, logs_p, mask):
+        self._req(z_p, logs_q, m_p, logs_p, mask)
+        B, C, T = z_p.shape
+        gs = [torch.empty_like(z_p) for _ in range(4)]
+        dL = dL.contiguous()
+        self._chk(self.lib.ttts_kl_loss_bwd(self._p(z_p), self._p(m_p), self._p(logs_p), self._p(mask), self._p(dL), self._p(self._kl_out), B, C, T,
+                                            self._p(gs[0]), self._p(gs[1]), self._p(gs[2]), self._p(gs[3]), self._st()), "ttts_kl_loss_bwd")
+        return gs
 
     def l1_fwd(self, a, b):
         self._req(a, b)
