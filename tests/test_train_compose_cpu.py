@@ -1,0 +1,63 @@
+"""CPU: the training graphs COMPOSED on one tape (next scope row): latent z -> flow -> KL, and z -> Generator -> MultiPeriodDiscriminator ->
+generator_loss + feature_loss, with z and the style vector g shared between the branches -- the dependency structure of the generator step
+(ttts/vqvae/vq2.py:855-862, train.py:386-395) minus the parts not built yet.  Over the torch restatement of the kernel contract, against
+torch.autograd through the pinned oracles (decoder / disc / flow oracles each equal the REAL reference)."""
+import os
+import sys
+
+import torch
+
+from oracle import decoder_oracle as DEC
+from oracle import disc_oracle as DIS
+from oracle import flow_oracle as FO
+from ttts_b200.vqvae.train_decoder import DecoderGraph
+from ttts_b200.vqvae.train_disc import DiscriminatorGraph
+from ttts_b200.vqvae.train_encoder import Ops, Tape, Var
+from ttts_b200.vqvae.train_flow import FlowGraph
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ref_kernels import TorchRefKernels  # noqa: E402
+
+
+def test_graphs_compose_on_one_tape():
+    K = TorchRefKernels()
+    g0 = torch.Generator().manual_seed(3)
+    B, T = 2, 6
+    z0, ge0 = torch.randn(B, 192, T, generator=g0), torch.randn(B, 512, 1, generator=g0)
+    mask = torch.ones(B, 1, T)
+    logs_q, m_p, logs_p = [0.3 * torch.randn(B, 192, T, generator=g0) for _ in range(3)]
+    y_real = torch.tanh(torch.randn(B, 1, T * 640, generator=g0))
+    Pf, Pd, Pm = FO.init_params(seed=6), DEC.init_params(seed=9), DIS.init_params(seed=4)
+    params = {**{"flow." + k: v for k, v in Pf.items()}, **{"dec." + k: v for k, v in Pd.items()}, **{"net_d." + k: v for k, v in Pm.items()}}
+
+    # ---- ours: one tape, three graphs, shared leaves z and g ----
+    tape = Tape()
+    flow, dec, disc = FlowGraph(K, params, tape, "flow."), DecoderGraph(K, params, tape, "dec."), DiscriminatorGraph(K, params, tape, "net_d.")
+    ops = Ops(K, tape)
+    z, ge = Var(z0), Var(ge0)
+    mask2 = mask[:, 0].contiguous()
+    loss_kl = ops.kl(flow.forward(z, mask2, ge), Var(logs_q), Var(m_p), Var(logs_p), mask2)
+    y_hat = dec.forward(z, ge)
+    _, fmap_r = disc.forward(y_real)
+    gen, fmap_g = disc.forward(y_hat)
+    loss_gen, loss_fm = disc.generator_losses(gen, fmap_r, fmap_g)
+    total = ops.add(ops.add(loss_gen, loss_fm), loss_kl)
+    total.g = torch.ones(1)
+    tape.backward()
+
+    # ---- torch.autograd through the oracles ----
+    zt, gt = z0.clone().requires_grad_(True), ge0.clone().requires_grad_(True)
+    Pf_t = {k: v.clone().requires_grad_(True) for k, v in Pf.items()}
+    Pd_t = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+    want_kl = DIS.kl_loss(FO.flow(Pf_t, zt, mask, gt), logs_q, m_p, logs_p, mask)
+    yh = DEC.generator(Pd_t, zt, gt)
+    _, y_d_g, fr, fg = DIS.mpd(Pm, y_real, yh)
+    want = DIS.generator_loss(y_d_g) + DIS.feature_loss(fr, fg) + want_kl
+    want.backward()
+    assert abs(float(total.v) - float(want.detach())) <= 1e-5 * abs(float(want.detach()))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    assert rel(z.g, zt.grad) <= 1e-4 and rel(ge.g, gt.grad) <= 1e-4                        # both branches accumulate into the shared leaves
+    for k, v in Pf_t.items():
+        assert rel(flow.P[k].g, v.grad) <= 1e-3 + 1e-6 / (float(v.grad.norm()) + 1e-30), k
+    for k, v in Pd_t.items():
+        assert rel(dec.P[k].g.reshape(v.shape), v.grad) <= 1e-3, k

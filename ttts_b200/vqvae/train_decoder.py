@@ -16,9 +16,12 @@ RATES, KSZ, RES_K = [10, 8, 2, 2, 2], [16, 16, 8, 2, 2], (3, 7, 11)
 class DecoderGraph:
     """Parameter names = the reference's `dec.*` state_dict entries without the prefix."""
 
-    def __init__(self, K, params):
+    def __init__(self, K, params, tape=None, prefix=""):
+        """`tape`: share one tape between graphs to differentiate through their composition (the full step); `prefix`: the sub-module's
+        prefix inside `params` (e.g. "dec."), stripped from the names the graph uses"""
+        params = {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
         self.K = K
-        self.tape = Tape()
+        self.tape = tape if tape is not None else Tape()
         self.ops = Ops(K, self.tape)
         self.P = {k: Var(v.detach().contiguous()) for k, v in params.items()}
         self.shapes = {k: tuple(v.shape) for k, v in params.items()}

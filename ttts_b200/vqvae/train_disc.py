@@ -20,9 +20,12 @@ P_CONVS = [(1, 32, 3), (32, 128, 3), (128, 512, 3), (512, 1024, 3), (1024, 1024,
 
 
 class DiscriminatorGraph:
-    def __init__(self, K, params):
+    def __init__(self, K, params, tape=None, prefix=""):
+        """`tape`: share one tape between graphs to differentiate through their composition (the full step); `prefix`: the sub-module's
+        prefix inside `params` (e.g. "dec."), stripped from the names the graph uses"""
+        params = {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
         self.K = K
-        self.tape = Tape()
+        self.tape = tape if tape is not None else Tape()
         self.ops = Ops(K, self.tape)
         # (k,1) Conv2d weights [Cout, Cin, k, 1] enter as Conv1d weights [Cout, Cin, k]; weight_g [Cout,1,1,1] as [Cout,1,1]
         self.P = {k: Var(v.detach().squeeze(-1).contiguous() if v.dim() == 4 else v.detach().contiguous()) for k, v in params.items()}

@@ -313,9 +313,12 @@ def wn_stack(o, P, pre, x, mask2, g, hid, n_layers, kernel_size=5):
 class EncoderGraph:
     """The training graph over the reference's parameter names (the state_dict of ref_enc.*, enc_p.*, proj.*)."""
 
-    def __init__(self, K, params):
+    def __init__(self, K, params, tape=None, prefix=""):
+        """`tape`: share one tape between graphs to differentiate through their composition (the full step); `prefix`: the sub-module's
+        prefix inside `params` (e.g. "dec."), stripped from the names the graph uses"""
+        params = {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
         self.K = K
-        self.tape = Tape()
+        self.tape = tape if tape is not None else Tape()
         self.ops = Ops(K, self.tape)
         # leaves; 2-D Linear weights enter as [out, in, 1] convolution weights
         self.P = {k: Var(v.detach().unsqueeze(-1).contiguous() if v.dim() == 2 else v.detach().contiguous()) for k, v in params.items()}
@@ -351,24 +354,25 @@ class EncoderGraph:
             x = o.add(xt, x)
         return x
 
-    def wn_stack(self, x, mask2, g):
-        return wn_stack(self.ops, self.P, "enc_p.enc.", x, mask2, g, HID, 16)
+    def wn_stack(self, x, mask2, g, pre="enc_p."):
+        return wn_stack(self.ops, self.P, pre + "enc.", x, mask2, g, HID, 16)
 
-    def posterior_audio_encoder(self, spec, wav, mask2, g, eps):
+    def posterior_audio_encoder(self, spec, wav, mask2, g, eps, pre="enc_p."):
+        """PosteriorAudioEncoder (vq2.py:667-745); `pre` = "enc_p." or "enc_q." (the same class, vq2.py:814-828)"""
         o, P = self.ops, self.P
-        a = o.conv(wav, P["enc_p.down_pre.weight"], P["enc_p.down_pre.bias"], pad=3, need_dx=False)
+        a = o.conv(wav, P[pre + "down_pre.weight"], P[pre + "down_pre.bias"], pad=3, need_dx=False)
         for i in range(5):
-            a = o.conv(a, self._wn("enc_p.downs.%d." % i), P["enc_p.downs.%d.bias" % i], stride=RATES[i], pad=(KSZ[i] - 1) // 2)
+            a = o.conv(a, self._wn(pre + "downs.%d." % i), P[pre + "downs.%d.bias" % i], stride=RATES[i], pad=(KSZ[i] - 1) // 2)
             xs = None
             for j, k in enumerate((3, 7, 11)):
-                r = self.resblock1("enc_p.resblocks.%d." % (i * 3 + j), a, k)
+                r = self.resblock1(pre + "resblocks.%d." % (i * 3 + j), a, k)
                 xs = r if xs is None else o.add(xs, r)
             a = o.scale(xs, 1.0 / 3.0)
-        a = o.snake(a, P["enc_p.activation_post.act.alpha"], P["enc_p.activation_post.act.beta"], kaiser_sinc_filter12(wav.v.device))
-        a = o.mul_mask(o.conv(a, P["enc_p.conv_post.weight"], P["enc_p.conv_post.bias"], pad=3), mask2)
-        x = o.mul_mask(o.conv(spec, P["enc_p.pre.weight"], P["enc_p.pre.bias"], need_dx=False), mask2)
-        x = self.wn_stack(x, mask2, g)
-        stats = o.mul_mask(o.conv(o.cat_c(x, a), P["enc_p.proj.weight"], P["enc_p.proj.bias"]), mask2)
+        a = o.snake(a, P[pre + "activation_post.act.alpha"], P[pre + "activation_post.act.beta"], kaiser_sinc_filter12(wav.v.device))
+        a = o.mul_mask(o.conv(a, P[pre + "conv_post.weight"], P[pre + "conv_post.bias"], pad=3), mask2)
+        x = o.mul_mask(o.conv(spec, P[pre + "pre.weight"], P[pre + "pre.bias"], need_dx=False), mask2)
+        x = self.wn_stack(x, mask2, g, pre)
+        stats = o.mul_mask(o.conv(o.cat_c(x, a), P[pre + "proj.weight"], P[pre + "proj.bias"]), mask2)
         return o.posterior(stats, eps, mask2), stats
 
     def forward(self, spec, wav, lengths=None, eps=None):

@@ -13,7 +13,8 @@ CH, HID, NL, NF = 192, 192, 4, 4
 class FlowGraph:
     """Parameter names = the reference's `flow.*` state_dict entries without the prefix."""
 
-    def __init__(self, K, params, tape=None):
+    def __init__(self, K, params, tape=None, prefix=""):
+        params = {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
         self.K = K
         self.tape = tape if tape is not None else Tape()
         self.ops = Ops(K, self.tape)
