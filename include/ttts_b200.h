@@ -243,6 +243,12 @@ int ttts_vq_backward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t l
 int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t pad, const float* window,
                   const float* twiddle, float eps_inside, float* spec_out, int32_t n_mels, const int32_t* band_lo,
                   const int32_t* band_off, const float* band_w, float log_floor, float* mel_out, int32_t n_frames, void* stream);
+/* backward of ttts_stft_mel's mel_out with respect to the waveform (the mel-reconstruction loss of the VQ-VAE-GAN step differentiates through
+ * mel_spectrogram_torch(y_hat), ttts/vqvae/train.py:357-366,389; csrc/stft_bwd.cu -- written without hardware, CPU-emulation-validated).
+ * dwav [B, L] ACCUMULATES (zero it first); dlogmel [B, n_mels, n_frames]. */
+int ttts_stft_mel_bwd(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t pad, const float* window, float eps_inside,
+                      int32_t n_mels, const int32_t* band_lo, const int32_t* band_off, const float* band_w, float log_floor,
+                      const float* dlogmel, int32_t n_frames, float* dwav, void* stream);
 int ttts_logmel(const float* spec, int32_t B, int32_t bins, int32_t F, int32_t n_mels, const int32_t* band_lo, const int32_t* band_off,
                 const float* band_w, float log_floor, float* mel_out, void* stream);
 

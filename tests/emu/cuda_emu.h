@@ -114,6 +114,7 @@ inline float __shfl_xor_sync(unsigned, float v, int o) {
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 inline float __expf(float x) { return expf(x); }
+inline void sincospif(float x, float* s, float* c) { *s = (float)sin(3.14159265358979323846 * (double)x); *c = (float)cos(3.14159265358979323846 * (double)x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

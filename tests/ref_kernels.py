@@ -25,6 +25,22 @@ class TorchRefKernels:
         dx, dw = _vjp(lambda a, c: self._conv(a, c, None, stride, dil, pad, pre_lrelu, groups), [x, w], dy)
         return (dx if need_dx else None), dw, (dy.sum(dim=(0, 2)) if need_db else None)
 
+    # ---- log-mel spectrogram of the v2 front end: mel_spectrogram_torch(y, 2048, 128, 32000, 640, 2048, 0, None)   (data_utils.py:106-156) ----
+    @staticmethod
+    def _logmel(wav):
+        from oracle import vq_mel_oracle as V
+        basis = torch.tensor(V.mel_basis_slaney(32000, 2048, 128, 0.0, None).astype("float32"))
+        xp = F.pad(wav.unsqueeze(1), (704, 704), mode="reflect").squeeze(1)
+        spec = torch.stft(xp, 2048, hop_length=640, win_length=2048, window=torch.hann_window(2048), center=False, onesided=True, return_complex=True)
+        mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2 + 1e-6)
+        return torch.log(torch.clamp(basis @ mag, min=1e-5))
+
+    def logmel_fwd(self, wav):                                       # wav [B, L] -> [B, 128, L / 640]
+        return self._logmel(wav)
+
+    def logmel_bwd(self, dmel, wav):
+        return _vjp(self._logmel, [wav], dmel)[0]
+
     # ---- adversarial losses (losses.py:7-44): scalars as [1] tensors                         ttts_lsgan_loss / ttts_l1_mean ----
     def lsgan_fwd(self, x, c):
         return ((c - x) ** 2).mean().reshape(1)

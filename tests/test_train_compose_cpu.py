@@ -61,3 +61,31 @@ def test_graphs_compose_on_one_tape():
         assert rel(flow.P[k].g, v.grad) <= 1e-3 + 1e-6 / (float(v.grad.norm()) + 1e-30), k
     for k, v in Pd_t.items():
         assert rel(dec.P[k].g.reshape(v.shape), v.grad) <= 1e-3, k
+
+
+def test_mel_reconstruction_loss_through_the_generator():
+    """loss_mel = l1(y_mel, mel_spectrogram_torch(y_hat)) * c_mel (train.py:357-366,389) with y_hat = Generator(z): tape vs torch.autograd"""
+    K = TorchRefKernels()
+    g0 = torch.Generator().manual_seed(8)
+    B, T = 2, 5
+    z0 = torch.randn(B, 192, T, generator=g0)
+    y_real = torch.tanh(torch.randn(B, T * 640, generator=g0))
+    Pd = DEC.init_params(seed=9)
+    tape = Tape()
+    dec, ops = DecoderGraph(K, Pd, tape), Ops(K, tape)
+    z = Var(z0)
+    y_hat = dec.forward(z, None)
+    mel_hat = ops.logmel(ops.reshape(y_hat, (B, T * 640)))
+    y_mel = K.logmel_fwd(y_real)
+    loss = ops.scale(ops.l1_mean(y_mel, mel_hat), 45.0)
+    loss.g = torch.ones(1)
+    tape.backward()
+    zt = z0.clone().requires_grad_(True)
+    Pt = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+    want = torch.nn.functional.l1_loss(y_mel, K._logmel(DEC.generator(Pt, zt, None).squeeze(1))) * 45.0
+    want.backward()
+    assert abs(float(loss.v) - float(want.detach())) <= 1e-5 * abs(float(want.detach()))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    assert rel(z.g, zt.grad) <= 1e-4
+    for k in ("conv_post.weight", "ups.0.weight_v", "resblocks.14.convs2.2.bias", "conv_pre.bias"):
+        assert rel(dec.P[k].g.reshape(Pt[k].shape), Pt[k].grad) <= 1e-3, k

@@ -133,6 +133,17 @@ class Ops:
         self.tape.record(bwd)
         return y
 
+    def logmel(self, wav):
+        """mel_spectrogram_torch of the v2 front end (data_utils.py:106-156) of a waveform Var [B, L]: the mel-reconstruction loss
+        differentiates through it (train.py:357-366,389)"""
+        y = Var(self.K.logmel_fwd(wav.v))
+
+        def bwd():
+            if y.g is not None:
+                self._acc(wav, self.K.logmel_bwd(y.g, wav.v))
+        self.tape.record(bwd)
+        return y
+
     def kl(self, z_p, logs_q, m_p, logs_p, mask):
         """kl_loss of the trainer (losses.py:47-61) as a [1] tensor; all four inputs are Vars, mask [B, T]"""
         y = Var(self.K.kl_fwd(z_p.v, logs_q.v, m_p.v, logs_p.v, mask))
@@ -527,6 +538,26 @@ class CudaKernels:
         d = torch.empty_like(x)
         self._chk(self.lib.ttts_lsgan_loss_bwd(self._p(x), float(c), self._p(dL), x.numel(), self._p(d), self._st()), "ttts_lsgan_loss_bwd")
         return d
+
+    def logmel_fwd(self, wav):
+        from . import mel as M
+        self._req(wav)
+        return M.mel_spectrogram_torch(wav, 2048, 128, 32000, 640, 2048, 0, None)
+
+    def logmel_bwd(self, dmel, wav):
+        import ctypes
+        from . import mel as M
+        dmel = dmel.contiguous()
+        self._req(dmel, wav)
+        B, Lw = wav.shape
+        window, _ = M._stft_consts(2048, 2048, wav.device)
+        lo, off, w = M._mel_consts("slaney", 32000, 2048, 128, 0, None, wav.device)
+        vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+        self.lib.ttts_stft_mel_bwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, f32, vp, i32, vp, vp]
+        dwav = torch.zeros_like(wav)
+        self._chk(self.lib.ttts_stft_mel_bwd(self._p(wav), B, Lw, 2048, 640, 704, self._p(window), 1e-6, 128, lo.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                             1e-5, self._p(dmel), dmel.shape[-1], self._p(dwav), self._st()), "ttts_stft_mel_bwd")
+        return dwav
 
     def kl_fwd(self, z_p, logs_q, m_p, logs_p, mask):
         self._req(z_p, logs_q, m_p, logs_p, mask)
