@@ -41,6 +41,30 @@ class TorchRefKernels:
     def logmel_bwd(self, dmel, wav):
         return _vjp(self._logmel, [wav], dmel)[0]
 
+    # ---- VQ lookup with straight-through output and commitment loss (core_vq.py:174-182, 303-322): x [B,D,N], embed [K,D] ----
+    @staticmethod
+    def _vq_codes(x, embed):
+        B, D, N = x.shape
+        flat = x.permute(0, 2, 1).reshape(B * N, D)
+        dist = -(flat.pow(2).sum(1, keepdim=True) - 2 * flat @ embed.t() + embed.pow(2).sum(1)[None])
+        return dist.max(dim=-1).indices
+
+    def vq_fwd(self, x, embed):
+        B, D, N = x.shape
+        codes = self._vq_codes(x, embed)
+        q = embed[codes].view(B, N, D).permute(0, 2, 1)
+        return x + (q - x), ((q - x) ** 2).mean().reshape(1), codes
+
+    def vq_bwd(self, dq, dcommit, x, embed, codes):
+        B, D, N = x.shape
+        q = embed[codes].view(B, N, D).permute(0, 2, 1)
+        dx = torch.zeros_like(x)
+        if dq is not None:
+            dx = dx + dq                                             # straight-through
+        if dcommit is not None:
+            dx = dx + dcommit * 2 * (x - q) / x.numel()              # mse(q.detach(), x)
+        return dx
+
     # ---- adversarial losses (losses.py:7-44): scalars as [1] tensors                         ttts_lsgan_loss / ttts_l1_mean ----
     def lsgan_fwd(self, x, c):
         return ((c - x) ** 2).mean().reshape(1)

@@ -89,3 +89,47 @@ def test_mel_reconstruction_loss_through_the_generator():
     assert rel(z.g, zt.grad) <= 1e-4
     for k in ("conv_post.weight", "ups.0.weight_v", "resblocks.14.convs2.2.bias", "conv_pre.bias"):
         assert rel(dec.P[k].g.reshape(Pt[k].shape), Pt[k].grad) <= 1e-3, k
+
+
+def test_encoder_quantizer_chain(golden_dir):
+    """wav -> MelStyleEncoder / PosteriorAudioEncoder -> proj -> VQ (straight-through + commitment loss) -> nearest x2 up-sampling -> a
+    random time window per clip (vq2.py:846-862): the head of SynthesizerTrn.forward on one tape, against torch.autograd through the encoder
+    oracle (pinned to the REAL reference) and the quantizer formulas (core_vq.py:303-322)."""
+    import numpy as np
+    from oracle import encoder_oracle as EO
+    from oracle import vq_mel_oracle as V
+    from ttts_b200.vqvae.train_encoder import EncoderGraph
+    K = TorchRefKernels()
+    enc = np.load(os.path.join(golden_dir, "encoder.npz"))
+    P = EO.init_params(seed=5)
+    wav, lengths, eps = torch.tensor(enc["wav"]), torch.tensor(enc["lengths"]), torch.tensor(enc["eps"])
+    spec = torch.tensor(V.spectrogram(enc["wav"]))
+    E = torch.tensor(enc["E"])
+    g0 = torch.Generator().manual_seed(21)
+    R = torch.randn(3, 192, 8, generator=g0)
+    starts = [3, 20, 0]
+    graph = EncoderGraph(K, P)
+    z, x = graph.forward(spec, wav, lengths=lengths, eps=eps)
+    q, commit, codes = graph.ops.vq(x, E)
+    assert np.array_equal(codes.view(3, -1).numpy(), enc["codes"][0])                     # the reference's own codes for these clips
+    seg = graph.ops.slice_t(graph.ops.upsample2(q), starts, 8)
+    o = graph.ops
+    loss = o.add(o.scale(commit, 1.0), o.lsgan(seg, 0.0))                                 # commit + mean(seg^2) ...
+    loss.g = torch.ones(1)
+    seg.g = R.clone()                                                                     # ... + <seg, R>, seeded directly on the window
+    graph.tape.backward()
+    Pt = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ot = EO.encode(Pt, spec, wav, lengths=lengths, eps=eps)
+    xt = ot["x"]
+    qt_codes = K._vq_codes(xt.detach(), E)
+    qq = E[qt_codes].view(3, -1, 192).permute(0, 2, 1)
+    q_st = xt + (qq - xt).detach()
+    commit_t = ((qq.detach() - xt) ** 2).mean()
+    up = q_st.repeat_interleave(2, dim=-1)
+    seg_t = torch.stack([up[b, :, s:s + 8] for b, s in enumerate(starts)])
+    (commit_t + (seg_t ** 2).mean() + (seg_t * R).sum()).backward()
+    floor = 1e-6 * float(torch.sqrt(sum((v.grad ** 2).sum() for v in Pt.values() if v.grad is not None)))
+    for k, v in Pt.items():
+        want = v.grad if v.grad is not None else torch.zeros_like(v)
+        got = graph.P[k].g.reshape(v.shape) if graph.P[k].g is not None else torch.zeros_like(v)
+        assert float((got - want).norm()) <= 2e-3 * float(want.norm()) + floor, k

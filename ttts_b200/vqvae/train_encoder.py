@@ -133,6 +133,44 @@ class Ops:
         self.tape.record(bwd)
         return y
 
+    def vq(self, x, embed):
+        """EuclideanCodebook lookup in training mode (core_vq.py:174-182, 303-322): returns (straight-through quantized Var, commit loss Var
+        [1], codes).  The codebook itself has no gradient (EMA-updated buffers); its update is the caller's (ttts_vq_ema_update)."""
+        qv, cv, codes = self.K.vq_fwd(x.v, embed)
+        q, c = Var(qv), Var(cv)
+
+        def bwd():
+            if q.g is None and c.g is None:
+                return
+            self._acc(x, self.K.vq_bwd(q.g, c.g, x.v, embed, codes))
+        self.tape.record(bwd)
+        return q, c, codes
+
+    def upsample2(self, x):
+        """F.interpolate(x, size = 2 T, mode="nearest") (vq2.py:853-855): memory plumbing; the backward sums the pairs"""
+        y = Var(x.v.repeat_interleave(2, dim=-1).contiguous())
+
+        def bwd():
+            if y.g is not None:
+                B, C, T2 = y.g.shape
+                self._acc(x, self.K.add(y.g[..., 0::2].contiguous(), y.g[..., 1::2].contiguous()))
+        self.tape.record(bwd)
+        return y
+
+    def slice_t(self, x, starts, size):
+        """commons.slice_segments (vq2.py:860-862): per-sequence windows [start, start + size) along time; backward scatters"""
+        B = x.v.shape[0]
+        y = Var(torch.stack([x.v[b, :, int(starts[b]):int(starts[b]) + size] for b in range(B)]).contiguous())
+
+        def bwd():
+            if y.g is not None:
+                g = torch.zeros_like(x.v)
+                for b in range(B):
+                    g[b, :, int(starts[b]):int(starts[b]) + size] = y.g[b]
+                self._acc(x, g)
+        self.tape.record(bwd)
+        return y
+
     def logmel(self, wav):
         """mel_spectrogram_torch of the v2 front end (data_utils.py:106-156) of a waveform Var [B, L]: the mel-reconstruction loss
         differentiates through it (train.py:357-366,389)"""
@@ -538,6 +576,24 @@ class CudaKernels:
         d = torch.empty_like(x)
         self._chk(self.lib.ttts_lsgan_loss_bwd(self._p(x), float(c), self._p(dL), x.numel(), self._p(d), self._st()), "ttts_lsgan_loss_bwd")
         return d
+
+    def vq_fwd(self, x, embed):
+        from . import quantize as Q
+        self._req(x, embed)
+        codes, q, commit = Q.vq_lookup(x, embed, True, True, straight_through=True, want_commit=True)
+        return q, commit.reshape(1), codes
+
+    def vq_bwd(self, dq, dcommit, x, embed, codes):
+        from . import quantize as Q
+        lib = self.lib
+        Q._protos(lib)
+        B, D, Nn = x.shape
+        dx = torch.empty_like(x)
+        dq = dq.contiguous() if dq is not None else None
+        dc = dcommit.contiguous() if dcommit is not None else None
+        self._chk(lib.ttts_vq_backward(self._p(x), B, D, Nn, 1, self._p(embed), self._p(codes), self._p(dq), self._p(dc), self._p(dx), self._st()),
+                  "ttts_vq_backward")
+        return dx
 
     def logmel_fwd(self, wav):
         from . import mel as M
