@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -263,6 +263,36 @@ def flow_case():
     print("flow ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "kl %.6f" % float(loss))
 
 
+def text_encoder_case():
+    """The REAL reference `enc_p_2` = TextEncoder(192, 192, 768, 2, 6, 3, 0.1) (ttts/vqvae/vq2.py:101-164, built at :817-825) in eval mode:
+    outputs (y, m_p, logs_p) and, for L = <m, R1> + <logs, R2>, per parameter tensor the gradient norm / projection, plus dL/dy and dL/dge."""
+    from oracle import text_encoder_oracle as TO
+    from ttts.vqvae.vq2 import TextEncoder
+    net = TextEncoder(192, 192, 768, 2, 6, 3, 0.1).eval()
+    P = TO.init_params(seed=8)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(P.keys()), sorted(set(sd.keys()) ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P)
+    y, y_lengths, text, text_lengths, ge = TO.golden_inputs()
+    y.requires_grad_(True); ge.requires_grad_(True)
+    yo, m, logs = net(y, y_lengths, text.clone(), text_lengths, ge)
+    gR = torch.Generator().manual_seed(62)
+    R1, R2 = torch.randn(m.shape, generator=gR), torch.randn(m.shape, generator=gR)
+    loss = (m * R1).sum() + (logs * R2).sum()
+    loss.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net.named_parameters():
+        gk = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    path = os.path.join(ROOT, "tests", "golden", "text_encoder.npz")
+    np.savez_compressed(path, y_sum=float(y.sum()), yo=yo.detach().numpy(), m=m.detach().numpy(), logs=logs.detach().numpy(), loss=float(loss),
+                        names=np.array(names), norm=np.array(norm), proj=np.array(proj), dy=y.grad.numpy(), dge=ge.grad.numpy())
+    print("text_encoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "loss %.5f" % float(loss))
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -423,6 +453,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "text_encoder":
+        text_encoder_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "flow":
         flow_case()
         sys.exit(0)
@@ -444,6 +477,7 @@ if __name__ == "__main__":
     decoder_case()
     disc_case()
     flow_case()
+    text_encoder_case()
     vq_case()
     mel_case()
     encoder_case()
