@@ -41,6 +41,53 @@ class TorchRefKernels:
     def logmel_bwd(self, dmel, wav):
         return _vjp(self._logmel, [wav], dmel)[0]
 
+    # ---- multi-head attention with an optional relative-position window (attentions.py:231-363, vc_utils.py:568-640) ----
+    # q [B,C,Tq], k / v [B,C,Tk] channel-major, heads split the channels; q_len / k_len [B] mask queries x keys (scores -1e4 where masked);
+    # emb_k / emb_v [1, 2w+1, dk] or None (then plain cross / self attention)
+    @staticmethod
+    def _attn(q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        import math
+        B, C, Tq = q.shape
+        Tk = k.shape[2]
+        dk = C // heads
+        qh = q.view(B, heads, dk, Tq).transpose(2, 3) / math.sqrt(dk)
+        kh = k.view(B, heads, dk, Tk).transpose(2, 3)
+        vh = v.view(B, heads, dk, Tk).transpose(2, 3)
+        scores = qh @ kh.transpose(-2, -1)
+        if emb_k is not None:
+            w = (emb_k.shape[1] - 1) // 2
+            idx = torch.arange(Tk)[None, :] - torch.arange(Tq)[:, None]
+            ok = (idx.abs() <= w)[:, :, None]
+            rk = emb_k[0][(idx + w).clamp(0, 2 * w)] * ok
+            rv = emb_v[0][(idx + w).clamp(0, 2 * w)] * ok
+            scores = scores + torch.einsum("bhid,ijd->bhij", qh, rk)
+        mask = (torch.arange(Tq)[None, :, None] < q_len[:, None, None]) & (torch.arange(Tk)[None, None, :] < k_len[:, None, None])
+        p = torch.softmax(scores.masked_fill(~mask[:, None], -1e4), dim=-1)
+        out = p @ vh
+        if emb_k is not None:
+            out = out + torch.einsum("bhij,ijd->bhid", p, rv)
+        return out.transpose(2, 3).reshape(B, C, Tq)
+
+    def attn_fwd(self, q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        return self._attn(q, k, v, emb_k, emb_v, q_len, k_len, heads)
+
+    def attn_bwd(self, do, q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        if emb_k is None:
+            dq, dk, dv = _vjp(lambda a, b, c: self._attn(a, b, c, None, None, q_len, k_len, heads), [q, k, v], do)
+            return dq, dk, dv, None, None
+        return _vjp(lambda a, b, c, d, e: self._attn(a, b, c, d, e, q_len, k_len, heads), [q, k, v, emb_k, emb_v], do)
+
+    # ---- LayerNorm over the channel axis of [B, C, T] (modules.py:20-32), eps 1e-5 ----
+    @staticmethod
+    def _lnc(x, gamma, beta):
+        return F.layer_norm(x.transpose(1, -1), (x.shape[1],), gamma, beta, 1e-5).transpose(1, -1)
+
+    def lnc_fwd(self, x, gamma, beta):
+        return self._lnc(x, gamma, beta)
+
+    def lnc_bwd(self, dy, x, gamma, beta):
+        return _vjp(self._lnc, [x, gamma, beta], dy)
+
     # ---- VQ lookup with straight-through output and commitment loss (core_vq.py:174-182, 303-322): x [B,D,N], embed [K,D] ----
     @staticmethod
     def _vq_codes(x, embed):

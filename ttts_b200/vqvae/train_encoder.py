@@ -133,6 +133,45 @@ class Ops:
         self.tape.record(bwd)
         return y
 
+    def attn(self, q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        """multi-head attention, channel-major, with an optional relative-position window (emb_k / emb_v Vars or None)"""
+        ek, ev = (emb_k.v, emb_v.v) if emb_k is not None else (None, None)
+        o = Var(self.K.attn_fwd(q.v, k.v, v.v, ek, ev, q_len, k_len, heads))
+
+        def bwd():
+            if o.g is None:
+                return
+            dq, dk, dv, dek, dev = self.K.attn_bwd(o.g, q.v, k.v, v.v, ek, ev, q_len, k_len, heads)
+            self._acc(q, dq); self._acc(k, dk); self._acc(v, dv)
+            if emb_k is not None:
+                self._acc(emb_k, dek); self._acc(emb_v, dev)
+        self.tape.record(bwd)
+        return o
+
+    def lnc(self, x, gamma, beta):
+        """LayerNorm over the channel axis of [B, C, T]"""
+        y = Var(self.K.lnc_fwd(x.v, gamma.v, beta.v))
+
+        def bwd():
+            if y.g is None:
+                return
+            dx, dg, db = self.K.lnc_bwd(y.g, x.v, gamma.v, beta.v)
+            self._acc(x, dx); self._acc(gamma, dg); self._acc(beta, db)
+        self.tape.record(bwd)
+        return y
+
+    def embedding(self, table, idx):
+        """table [V, C] Var, idx [B, T] int64 -> [B, C, T]; memory gather, the backward scatter-adds rows"""
+        y = Var(table.v[idx].transpose(1, 2).contiguous())
+
+        def bwd():
+            if y.g is not None:
+                g = torch.zeros_like(table.v)
+                g.index_add_(0, idx.reshape(-1), y.g.transpose(1, 2).reshape(-1, table.v.shape[1]))
+                self._acc(table, g)
+        self.tape.record(bwd)
+        return y
+
     def vq(self, x, embed):
         """EuclideanCodebook lookup in training mode (core_vq.py:174-182, 303-322): returns (straight-through quantized Var, commit loss Var
         [1], codes).  The codebook itself has no gradient (EMA-updated buffers); its update is the caller's (ttts_vq_ema_update)."""
