@@ -335,6 +335,19 @@ int ttts_kl_loss(const float* z_p, const float* logs_q, const float* m_p, const 
 int ttts_kl_loss_bwd(const float* z_p, const float* m_p, const float* logs_p, const float* mask, const float* dL, const float* fwd_out2,
                      int32_t B, int32_t C, int32_t T, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p, void* stream);
 
+/* prior encoder enc_p_2 (TextEncoder + MRTE, vq2.py:17-164; csrc/text_encoder_kernels.cu, same validation status): multi-head attention over
+ * short sequences, channel-major, with an optional windowed relative-position term (attentions.py:231-363 in closed form; emb_k / emb_v
+ * [2 win + 1, C / heads] or NULL), query / key lengths and the reference's -1e4 masking; LayerNorm over the channel axis (modules.py:20-32). */
+int ttts_attn_small(const float* q, const float* k, const float* v, const float* emb_k, const float* emb_v, const int64_t* q_len,
+                    const int64_t* k_len, float* out, int32_t B, int32_t C, int32_t Tq, int32_t Tk, int32_t heads, int32_t win, void* stream);
+int ttts_attn_small_bwd(const float* dout, const float* q, const float* k, const float* v, const float* emb_k, const float* emb_v,
+                        const int64_t* q_len, const int64_t* k_len, float* dq, float* dk, float* dv, float* demb_k, float* demb_v,
+                        int32_t B, int32_t C, int32_t Tq, int32_t Tk, int32_t heads, int32_t win, void* stream);   /* demb_* ACCUMULATE */
+int ttts_layernorm_c(const float* x, const float* gamma, const float* beta, float* y, float* stats, int32_t B, int32_t C, int32_t T,
+                     void* stream);                                                                                  /* stats: B*T*2 floats */
+int ttts_layernorm_c_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                         float* scratch, int32_t B, int32_t C, int32_t T, void* stream);                             /* scratch: B*T*2 floats */
+
 #ifdef __cplusplus
 }
 #endif

@@ -271,6 +271,33 @@ def test_flow_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(zv.g.cpu().numpy() - z["dz"]) <= 1e-3 * np.linalg.norm(z["dz"])
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the prior encoder (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_text_encoder_training_graph_vs_reference_golden(golden_dir):
+    """train_text_encoder.TextEncoderGraph over the CUDA kernels against the REAL reference TextEncoder (text_encoder.npz)"""
+    from oracle import text_encoder_oracle as TO
+    from ttts_b200.vqvae.train_encoder import CudaKernels, Var
+    from ttts_b200.vqvae.train_text_encoder import TextEncoderGraph
+    z = np.load(os.path.join(golden_dir, "text_encoder.npz"))
+    y, y_lengths, text, text_lengths, ge = [t.cuda() for t in TO.golden_inputs()]
+    graph = TextEncoderGraph(CudaKernels(), {k: v.cuda() for k, v in TO.init_params(seed=8).items()})
+    yv, gv = Var(y), Var(ge)
+    yo, stats = graph.forward(yv, y_lengths, text, text_lengths, gv)
+    assert np.abs(stats.v[:, :192].cpu().numpy() - z["m"]).max() <= 2e-4 * max(1.0, np.abs(z["m"]).max())
+    gR = torch.Generator().manual_seed(62)
+    R1, R2 = torch.randn(z["m"].shape, generator=gR), torch.randn(z["m"].shape, generator=gR)
+    stats.g = torch.cat([R1, R2], dim=1).cuda()
+    graph.tape.backward()
+    grads = graph.grads()
+    floor = 1e-6 * float(np.sqrt((z["norm"] ** 2).sum()))
+    for i, k in enumerate([str(n) for n in z["names"]]):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(z["norm"][i])
+        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
+        assert abs(float((gk * d).sum()) - float(z["proj"][i])) <= 1e-2 * scale + floor, k
+    assert np.linalg.norm(yv.g.cpu().numpy() - z["dy"]) <= 1e-3 * np.linalg.norm(z["dy"])
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

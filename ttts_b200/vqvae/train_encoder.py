@@ -515,6 +515,10 @@ class CudaKernels:
             lib.ttts_lsgan_loss_bwd.argtypes = [vp, f32, vp, i64, vp, vp]
             lib.ttts_l1_mean.argtypes = [vp, vp, i64, vp, vp, vp]
             lib.ttts_l1_mean_bwd.argtypes = [vp, vp, vp, i64, vp, vp]
+            lib.ttts_attn_small.argtypes = [vp] * 8 + [i32] * 6 + [vp]
+            lib.ttts_attn_small_bwd.argtypes = [vp] * 13 + [i32] * 6 + [vp]
+            lib.ttts_layernorm_c.argtypes = [vp] * 5 + [i32] * 3 + [vp]
+            lib.ttts_layernorm_c_bwd.argtypes = [vp] * 8 + [i32] * 3 + [vp]
             lib.ttts_kl_loss.argtypes = [vp] * 5 + [i32, i32, i32, vp, vp, vp]
             lib.ttts_kl_loss_bwd.argtypes = [vp] * 6 + [i32, i32, i32, vp, vp, vp, vp, vp]
             lib.ttts_snake_aa_bwd.argtypes = [vp] * 8 + [i32, i32, i32, vp]
@@ -615,6 +619,50 @@ class CudaKernels:
         d = torch.empty_like(x)
         self._chk(self.lib.ttts_lsgan_loss_bwd(self._p(x), float(c), self._p(dL), x.numel(), self._p(d), self._st()), "ttts_lsgan_loss_bwd")
         return d
+
+    def attn_fwd(self, q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        self._req(q, k, v, emb_k, emb_v, q_len, k_len)
+        B, C, Tq = q.shape
+        win = (emb_k.shape[1] - 1) // 2 if emb_k is not None else 0
+        o = torch.empty_like(q)
+        self._chk(self.lib.ttts_attn_small(self._p(q), self._p(k), self._p(v), self._p(emb_k), self._p(emb_v), self._p(q_len), self._p(k_len), self._p(o),
+                                           B, C, Tq, k.shape[2], heads, win, self._st()), "ttts_attn_small")
+        return o
+
+    def attn_bwd(self, do, q, k, v, emb_k, emb_v, q_len, k_len, heads):
+        do = do.contiguous()
+        self._req(do, q, k, v, emb_k, emb_v, q_len, k_len)
+        B, C, Tq = q.shape
+        win = (emb_k.shape[1] - 1) // 2 if emb_k is not None else 0
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dek = torch.zeros_like(emb_k) if emb_k is not None else None
+        dev = torch.zeros_like(emb_v) if emb_v is not None else None
+        self._chk(self.lib.ttts_attn_small_bwd(self._p(do), self._p(q), self._p(k), self._p(v), self._p(emb_k), self._p(emb_v), self._p(q_len), self._p(k_len),
+                                               self._p(dq), self._p(dk), self._p(dv), self._p(dek), self._p(dev), B, C, Tq, k.shape[2], heads, win,
+                                               self._st()), "ttts_attn_small_bwd")
+        return dq, dk, dv, dek, dev
+
+    def lnc_fwd(self, x, gamma, beta):
+        self._req(x, gamma, beta)
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(B * T * 2, dtype=torch.float32, device=x.device)
+        self._chk(self.lib.ttts_layernorm_c(self._p(x), self._p(gamma), self._p(beta), self._p(y), self._p(stats), B, C, T, self._st()), "ttts_layernorm_c")
+        return y
+
+    def lnc_bwd(self, dy, x, gamma, beta):
+        dy = dy.contiguous()
+        self._req(dy, x, gamma, beta)
+        B, C, T = x.shape
+        # the statistics are recomputed (2 small launches) rather than kept per call site
+        stats = torch.empty(B * T * 2, dtype=torch.float32, device=x.device)
+        tmp = torch.empty_like(x)
+        self._chk(self.lib.ttts_layernorm_c(self._p(x), self._p(gamma), self._p(beta), self._p(tmp), self._p(stats), B, C, T, self._st()), "ttts_layernorm_c")
+        dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(beta)
+        scratch = torch.empty(B * T * 2, dtype=torch.float32, device=x.device)
+        self._chk(self.lib.ttts_layernorm_c_bwd(self._p(dy), self._p(x), self._p(stats), self._p(gamma), self._p(dx), self._p(dg), self._p(db),
+                                                self._p(scratch), B, C, T, self._st()), "ttts_layernorm_c_bwd")
+        return dx, dg, db
 
     def vq_fwd(self, x, embed):
         from . import quantize as Q

@@ -3,9 +3,9 @@ TextEncoder(192, 192, 768, heads 2, layers 6, kernel 3) (ttts/vqvae/vq2.py:101-1
 quantized latents (3 layers) and the embedded text (6 layers), MRTE cross-attention with the style vector added (vq2.py:17-50), 3 more layers,
 projection to (m_p, logs_p).  Eval-mode semantics (the reference's p = 0.1 dropouts are not drawn here yet).
 
-DRAFT: the graph over the torch restatement of the op contract reproduces the REAL module's outputs and all gradients
-(tests/test_train_text_encoder_cpu.py vs tests/golden/text_encoder.npz); the two ops it adds -- `attn` (windowed relative-position /
-cross attention) and `lnc` (channel LayerNorm) -- have no CUDA kernels yet, so `CudaKernels` raises for them."""
+DRAFT, NOT YET RUN ON HARDWARE: the graph over the torch restatement of the op contract reproduces the REAL module's outputs and all
+gradients (tests/test_train_text_encoder_cpu.py vs tests/golden/text_encoder.npz); the two ops it adds -- `attn` (windowed relative-position /
+cross attention) and `lnc` (channel LayerNorm) -- are csrc/text_encoder_kernels.cu, checked on the CPU emulation (tests/test_emu_text_encoder_cpu.py)."""
 import torch
 
 from .train_encoder import Ops, Tape, Var
