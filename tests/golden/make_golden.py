@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -293,6 +293,76 @@ def text_encoder_case():
     print("text_encoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "loss %.5f" % float(loss))
 
 
+def step_params():
+    """name -> tensor for the whole generator (net_g) and the discriminators (net_d), assembled from the per-module oracle initialisers"""
+    from oracle import decoder_oracle as DEC, disc_oracle as DIS, encoder_oracle as EO, flow_oracle as FO, text_encoder_oracle as TO
+    G = dict(EO.init_params(seed=5))                                                   # enc_p.*, ref_enc.*, proj.*
+    G.update({"enc_q." + k[len("enc_p."):]: v for k, v in EO.init_params(seed=7).items() if k.startswith("enc_p.")})
+    G.update({"dec." + k: v for k, v in DEC.init_params(seed=9).items()})
+    G.update({"flow." + k: v for k, v in FO.init_params(seed=6).items()})
+    G.update({"enc_p_2." + k: v for k, v in TO.init_params(seed=8).items()})
+    return G, DIS.init_params(seed=4)
+
+
+def step_inputs():
+    enc = np.load(os.path.join(ROOT, "tests", "golden", "encoder.npz"))
+    g0 = torch.Generator().manual_seed(71)
+    text = torch.randint(0, 256, (3, 15), generator=g0)
+    return torch.tensor(enc["wav"]), torch.tensor(enc["lengths"]), text, torch.tensor([15, 9, 4]), torch.tensor(enc["E"])
+
+
+def vqvae_step_case():
+    """The generator half of ONE train step of the REAL reference (ttts/vqvae/train.py:336-395 over SynthesizerTrn.forward, vq2.py:843-871, and
+    MultiPeriodDiscriminator): the five losses and, per net_g parameter tensor, the gradient norm / projection of
+    loss_gen_all = loss_gen + loss_fm + loss_mel + kl_ssl + loss_kl.  Modules in eval mode (the TextEncoder's dropouts off) except the
+    quantizer (training: straight-through + commitment loss); posterior noises and the segment starts come from torch.manual_seed(0) and are
+    regenerated by the test in the same order; segment = 8 frames; wav_aug = wav (no augmentation)."""
+    from ttts.vqvae.vq2 import SynthesizerTrn, MultiPeriodDiscriminator
+    from ttts.vqvae import losses as RL
+    from ttts.utils import commons
+    from ttts.utils.data_utils import spectrogram_torch, spec_to_mel_torch, mel_spectrogram_torch
+    import json
+    cfg = json.load(open("/root/reference/ttts/vqvae/config.json"))
+    SEG = 8
+    net_g = SynthesizerTrn(1025, SEG, **cfg["vqvae"]).eval()
+    net_d = MultiPeriodDiscriminator(False).eval()
+    G, D = step_params()
+    sd = net_g.state_dict()
+    learn = {k for k in sd if not k.startswith("quantizer.") and not k.endswith(".filter")}
+    assert learn == set(G.keys()), sorted(learn ^ set(G.keys()))[:10]
+    net_g.load_state_dict(G, strict=False)
+    net_d.load_state_dict(D)
+    wav, lengths, text, text_lengths, E = step_inputs()
+    cb = net_g.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(E); cb.embed_avg.copy_(E); cb.cluster_size.fill_(10); cb.inited.fill_(1)
+    net_g.quantizer.train()
+    spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
+    torch.manual_seed(0)
+    y_hat, kl_ssl, ids_slice, z_mask, (z, z_p, m_p, logs_p, m_q, logs_q), _ = net_g(wav, wav, lengths * 640, spec, spec, lengths, text.clone(), text_lengths)
+    mel = spec_to_mel_torch(spec, 2048, 128, 32000, 0.0, None)
+    y_mel = commons.slice_segments(mel, ids_slice, SEG)
+    y_hat_mel = mel_spectrogram_torch(y_hat.squeeze(1), 2048, 128, 32000, 640, 2048, 0.0, None)
+    y = commons.slice_segments(wav.unsqueeze(1), ids_slice * 640, SEG * 640)
+    y_d_hat_r, y_d_hat_g, fmap_r, fmap_g = net_d(y, y_hat)
+    loss_mel = torch.nn.functional.l1_loss(y_mel, y_hat_mel) * 45
+    loss_kl = RL.kl_loss(z_p, logs_q, m_p, logs_p, z_mask) * 1.0
+    loss_fm = RL.feature_loss(fmap_r, fmap_g)
+    loss_gen, _ = RL.generator_loss(y_d_hat_g)
+    total = loss_gen + loss_fm + loss_mel + kl_ssl * 1 + loss_kl
+    total.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net_g.named_parameters():
+        gk = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    path = os.path.join(ROOT, "tests", "golden", "vqvae_step.npz")
+    np.savez_compressed(path, ids_slice=ids_slice.numpy(), loss_gen=float(loss_gen), loss_fm=float(loss_fm), loss_mel=float(loss_mel),
+                        kl_ssl=float(kl_ssl), loss_kl=float(loss_kl), total=float(total), y_hat_sum=float(y_hat.sum()), z_sum=float(z.sum()),
+                        names=np.array(names), norm=np.array(norm), proj=np.array(proj))
+    print("vqvae_step ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), len(names), "tensors; gen %.4f fm %.4f mel %.4f commit %.5f kl %.4f" %
+          (float(loss_gen), float(loss_fm), float(loss_mel), float(kl_ssl), float(loss_kl)), "ids", ids_slice.tolist())
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -453,6 +523,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "step":
+        vqvae_step_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "text_encoder":
         text_encoder_case()
         sys.exit(0)
@@ -478,6 +551,7 @@ if __name__ == "__main__":
     disc_case()
     flow_case()
     text_encoder_case()
+    vqvae_step_case()
     vq_case()
     mel_case()
     encoder_case()
