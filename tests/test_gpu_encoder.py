@@ -298,6 +298,41 @@ def test_text_encoder_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(yv.g.cpu().numpy() - z["dy"]) <= 1e-3 * np.linalg.norm(z["dy"])
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="generator half of the VQ-VAE-GAN step (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
+def test_generator_step_vs_reference_golden(golden_dir):
+    """train_step.GeneratorStep over the CUDA kernels: the five losses and the gradients of all 1455 net_g tensors of the REAL reference step
+    (vqvae_step.npz) -- the assertions of tests/test_train_step_cpu.py with the product backend"""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden as MG
+    from ttts_b200.vqvae.mel import spectrogram_torch
+    from ttts_b200.vqvae.train_encoder import CudaKernels
+    from ttts_b200.vqvae.train_step import GeneratorStep
+    z = np.load(os.path.join(golden_dir, "vqvae_step.npz"))
+    G, D = MG.step_params()
+    wav, lengths, text, text_lengths, E = MG.step_inputs()
+    torch.manual_seed(0)
+    eps_p, eps_q = torch.randn(3, 192, 36), torch.randn(3, 192, 36)
+    ids = (torch.rand([3]) * (lengths - 8 + 1)).to(torch.long).tolist()
+    assert ids == z["ids_slice"].tolist()
+    c = lambda t: t.cuda()
+    step = GeneratorStep(CudaKernels(), {k: c(v) for k, v in G.items()}, {k: c(v) for k, v in D.items()})
+    spec = spectrogram_torch(c(wav), 2048, 640, 2048, center=False)
+    out = step.forward(c(wav), spec, c(lengths), c(text), c(text_lengths), c(E), c(eps_p), c(eps_q), ids, 8)
+    for key in ("loss_gen", "loss_fm", "loss_mel", "kl_ssl", "loss_kl", "total"):
+        assert abs(float(out[key].v) - float(z[key])) <= 1e-3 * max(1.0, abs(float(z[key]))), (key, float(out[key].v), float(z[key]))
+    grads = step.backward()
+    floor = 1e-6 * float(np.sqrt((z["norm"] ** 2).sum()))
+    bad = []
+    for i, k in enumerate([str(n) for n in z["names"]]):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(z["norm"][i])
+        if not (abs(float(gk.norm()) - scale) <= 5e-3 * scale + floor and abs(float((gk * d).sum()) - float(z["proj"][i])) <= 2e-2 * scale + floor):
+            bad.append((k, float(gk.norm()), scale))
+    assert not bad, bad[:10]
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)
