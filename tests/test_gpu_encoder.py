@@ -333,6 +333,39 @@ def test_generator_step_vs_reference_golden(golden_dir):
     assert not bad, bad[:10]
 
 
+@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="full VQ-VAE-GAN train step (next scope row): not yet run on hardware; set TTTS_BWD_TEST=1")
+def test_full_train_step_runs_in_the_reference_order(golden_dir):
+    """train_step.TrainStep: synthesis -> discriminator step -> adversarial losses through the updated discriminators -> generator step, two
+    fused AdamW launches over flat buffers.  Losses that do not depend on the discriminators equal the reference golden; the update of a
+    parameter equals torch's AdamW applied to the gradient the tape produced (first step: lr * sign-like update of magnitude ~lr)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden as MG
+    from ttts_b200.vqvae.mel import spectrogram_torch
+    from ttts_b200.vqvae.train_encoder import CudaKernels
+    from ttts_b200.vqvae.train_step import TrainStep
+    z = np.load(os.path.join(golden_dir, "vqvae_step.npz"))
+    G, D = MG.step_params()
+    wav, lengths, text, text_lengths, E = MG.step_inputs()
+    torch.manual_seed(0)
+    eps_p, eps_q = torch.randn(3, 192, 36), torch.randn(3, 192, 36)
+    ids = (torch.rand([3]) * (lengths - 8 + 1)).to(torch.long).tolist()
+    c = lambda t: t.cuda()
+    ts = TrainStep(CudaKernels(), {k: c(v) for k, v in G.items()}, {k: c(v) for k, v in D.items()})
+    before = {k: v.clone() for k, v in ts.opt_g.params().items()}
+    spec = spectrogram_torch(c(wav), 2048, 640, 2048, center=False)
+    out = ts.step(c(wav), spec, c(lengths), c(text), c(text_lengths), c(E), c(eps_p), c(eps_q), ids, 8)
+    for key in ("loss_mel", "kl_ssl", "loss_kl"):
+        assert abs(float(out[key]) - float(z[key])) <= 1e-3 * max(1.0, abs(float(z[key]))), key
+    assert all(bool(torch.isfinite(v).all()) for v in out.values())
+    assert abs(float(out["loss_gen"]) - float(z["loss_gen"])) <= 0.05 * float(z["loss_gen"])      # the discriminators moved by one lr = 1e-4 step
+    # first AdamW step: p <- p (1 - lr wd) - lr g / (|g| + eps)  (bias-corrected m / sqrt(v) = sign-like)
+    k = "dec.conv_post.weight"
+    g = ts.opt_g.grad[:0]  # noqa: F841  (flat gradient buffer exists)
+    moved = (ts.opt_g.params()[k] - before[k] * (1 - 1e-4 * 0.01)).abs()
+    assert float(moved.max()) <= 1.001e-4 and float(moved.mean()) >= 0.5e-4
+
+
 def test_encoder_batch64_properties(model):
     """BASELINE config: 64 clips x 23 040 samples.  Batch independence + masked frames are zero + deterministic."""
     g = torch.Generator(device="cuda").manual_seed(1234)

@@ -14,7 +14,7 @@ TTTS_CONV_SPLIT=1 timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu 
 (ONLY=enc timeout 200 python tools/kernels_ab.py; ONLY=enc TTTS_CONV_SPLIT=1 timeout 200 python tools/kernels_ab.py) 2>&1 | grep -v "^$" | tee gpurun_out/r2a_conv_split_ab.txt
 TTTS_ENC_OVERLAP=1 timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu -q > gpurun_out/r2a_pytest_enc_overlap.log 2>&1; tail -4 gpurun_out/r2a_pytest_enc_overlap.log
 (ONLY=enc TTTS_ENC_OVERLAP=1 timeout 200 python tools/kernels_ab.py; ONLY=enc TTTS_ENC_OVERLAP=1 TTTS_CONV_SPLIT=1 timeout 200 python tools/kernels_ab.py) 2>&1 | grep -v "^$" | tee gpurun_out/r2a_enc_overlap_ab.txt
-TTTS_BWD_TEST=1 timeout 600 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "conv1d_backward or training_graph or generator_step" > gpurun_out/r2a_pytest_convbwd.log 2>&1; tail -6 gpurun_out/r2a_pytest_convbwd.log
+TTTS_BWD_TEST=1 timeout 600 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "conv1d_backward or training_graph or generator_step or full_train_step" > gpurun_out/r2a_pytest_convbwd.log 2>&1; tail -6 gpurun_out/r2a_pytest_convbwd.log
 timeout 600 python tools/vqvae_step_bench.py 8 > gpurun_out/r2a_vqvae_step_b8.json 2> gpurun_out/r2a_vqvae_step_b8.err; cat gpurun_out/r2a_vqvae_step_b8.json; tail -2 gpurun_out/r2a_vqvae_step_b8.err
 # 4. split-bf16 tcgen05 convolution (conv1d_tc.cu; desk-checked + index emulation only).  Own timeout: a hang must not take the box.
 TTTS_CONV_TC=1 timeout 300 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "conv1d_tc" > gpurun_out/r2a_pytest_convtc.log 2>&1; tail -15 gpurun_out/r2a_pytest_convtc.log

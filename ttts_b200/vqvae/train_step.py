@@ -29,9 +29,10 @@ class GeneratorStep:
         self.dec = DecoderGraph(K, params_g, self.tape, "dec.")
         self.disc = DiscriminatorGraph(K, params_d, self.tape)
 
-    def forward(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
-        """wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav); wav_aug = wav), lengths [B] frames, text [B,Tt] int64, codebook [1024,192],
-        eps_p / eps_q [B,192,T] posterior noises, ids_slice [B] segment starts (frames).  Returns the dict of loss Vars."""
+    def synthesize(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+        """SynthesizerTrn.forward (vq2.py:843-871) and the losses that do not involve the discriminators.
+        wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav); wav_aug = wav), lengths [B] frames, text [B,Tt] int64, codebook [1024,192],
+        eps_p / eps_q [B,192,T] posterior noises, ids_slice [B] segment starts (frames)."""
         o, enc = self.ops, self.enc
         B, _, T = spec.shape
         dev = spec.device
@@ -48,18 +49,30 @@ class GeneratorStep:
         logs_q = o.slice_c(stats_q, 192, 384)
         z_p = self.flow.forward(z, mask2, ge)                                                                 # :859
         y_hat = self.dec.forward(o.slice_t(z, ids_slice, segment_frames), ge)                                 # :861-864
-        # ---- losses (train.py:357-395) ----
+        # ---- mel / commitment / KL losses (train.py:357-366, 389-390) ----
         L = segment_frames * HOP
         y_mel = torch.stack([self.K.logmel_fwd(wav)[b, :, int(s):int(s) + segment_frames] for b, s in enumerate(ids_slice)]).contiguous()
         loss_mel = o.scale(o.l1_mean(y_mel, o.logmel(o.reshape(y_hat, (B, L)))), C_MEL)
-        y_seg = torch.stack([wav[b, int(s) * HOP:int(s) * HOP + L] for b, s in enumerate(ids_slice)]).unsqueeze(1).contiguous()
-        _, fmap_r = self.disc.forward(y_seg)
-        gen, fmap_g = self.disc.forward(y_hat)
-        loss_gen, loss_fm = self.disc.generator_losses(gen, fmap_r, fmap_g)
         loss_kl = o.scale(o.kl(z_p, logs_q, m_p, logs_p, mask2), C_KL)
-        total = o.add(o.add(o.add(loss_gen, loss_fm), o.add(loss_mel, commit)), loss_kl)
-        self.out = dict(loss_gen=loss_gen, loss_fm=loss_fm, loss_mel=loss_mel, kl_ssl=commit, loss_kl=loss_kl, total=total, y_hat=y_hat, z=z, codes=codes)
+        y_seg = torch.stack([wav[b, int(s) * HOP:int(s) * HOP + L] for b, s in enumerate(ids_slice)]).unsqueeze(1).contiguous()
+        self.out = dict(loss_mel=loss_mel, kl_ssl=commit, loss_kl=loss_kl, y_hat=y_hat, y_seg=y_seg, z=z, codes=codes)
         return self.out
+
+    def adversarial(self):
+        """generator_loss + feature_loss through the discriminators as they are NOW (the trainer steps optim_d between the synthesis and this
+        call, train.py:372-388), then the total"""
+        o, out = self.ops, self.out
+        _, fmap_r = self.disc.forward(out["y_seg"])
+        gen, fmap_g = self.disc.forward(out["y_hat"])
+        loss_gen, loss_fm = self.disc.generator_losses(gen, fmap_r, fmap_g)
+        total = o.add(o.add(o.add(loss_gen, loss_fm), o.add(out["loss_mel"], out["kl_ssl"])), out["loss_kl"])
+        out.update(loss_gen=loss_gen, loss_fm=loss_fm, total=total)
+        return out
+
+    def forward(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+        """synthesize + adversarial with the discriminators unchanged in between.  Returns the dict of loss Vars."""
+        self.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames)
+        return self.adversarial()
 
     def backward(self):
         """d loss_gen_all / d every net_g parameter, by the reference's state_dict names"""
@@ -71,3 +84,65 @@ class GeneratorStep:
                 shape = graph.shapes[k]
                 grads[prefix + k] = v.g.reshape(shape) if v.g is not None else torch.zeros(shape, device=v.v.device)
         return grads
+
+
+class FlatAdamW:
+    """torch.optim.AdamW(params, lr, betas, eps) of the trainer (train.py:292-303: lr 1e-4, betas (0.8, 0.99), eps 1e-9, weight decay 0.01) over
+    ONE flat fp32 buffer: the named tensors become views of it, the gradients are gathered into a second flat buffer and ONE launch of the
+    fused ttts_adamw_step (the GPT trainer's kernel) updates everything.  `clip_grad_value_(params, None)` of the reference only measures."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.8, 0.99), eps=1e-9, weight_decay=0.01):
+        from .. import _lib as L
+        from ..gpt import engine as E
+        self.L = L
+        E._setup_prototypes(L.lib())
+        self.names = list(params.keys())
+        sizes = [params[k].numel() for k in self.names]
+        dev = params[self.names[0]].device
+        L.require_cuda(params[self.names[0]])
+        self.flat = torch.cat([params[k].detach().reshape(-1).float() for k in self.names]).contiguous()
+        self.grad = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.views, o = {}, 0
+        for k, n in zip(self.names, sizes):
+            self.views[k] = self.flat[o:o + n].view(params[k].shape)
+            o += n
+        self.lr, self.betas, self.eps, self.wd, self.t = lr, betas, eps, weight_decay, 0
+        self.device = dev
+
+    def params(self):
+        """name -> view of the flat buffer (pass these to the graphs: the update is then visible to the next step without copies)"""
+        return self.views
+
+    def step(self, grads):
+        self.t += 1
+        torch.cat([grads[k].reshape(-1) for k in self.names], out=self.grad)
+        L = self.L
+        L.check(L.lib().ttts_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), None, self.flat.numel(),
+                                        None, 0.0, 1.0, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+                                        int(self.t), L.stream_ptr().value), "ttts_adamw_step")
+
+
+class TrainStep:
+    """One optimisation step of ttts/vqvae/train.py:330-406 in the reference's order: synthesis -> discriminator loss on (y, y_hat.detach())
+    -> optim_d.step() -> adversarial + feature losses through the UPDATED discriminators -> optim_g.step().  The quantizer's EMA update
+    (core_vq.py:217-228) is the caller's (ResidualVectorQuantizer / ttts_vq_ema_update); posterior noises and segment starts are inputs."""
+
+    def __init__(self, K, params_g, params_d, lr=1e-4):
+        self.K = K
+        self.opt_g, self.opt_d = FlatAdamW(params_g, lr), FlatAdamW(params_d, lr)
+
+    def step(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+        Pg, Pd = self.opt_g.params(), self.opt_d.params()
+        gen = GeneratorStep(self.K, Pg, Pd)
+        out = gen.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames)
+        dgraph = DiscriminatorGraph(self.K, Pd)
+        real, _ = dgraph.forward(out["y_seg"])
+        fake, _ = dgraph.forward(out["y_hat"].v)                      # .detach(): a constant for the discriminator step
+        loss_d = dgraph.discriminator_loss(real, fake)
+        self.opt_d.step(dgraph.backward(loss_d))
+        # the generator graph read the discriminator weights as views of the flat buffer: rebuild its discriminator leaves after the update
+        gen.disc = DiscriminatorGraph(self.K, Pd, gen.tape)
+        out = gen.adversarial()
+        self.opt_g.step(gen.backward())
+        return dict(loss_disc=loss_d.v, **{k: out[k].v for k in ("loss_gen", "loss_fm", "loss_mel", "kl_ssl", "loss_kl", "total")})
