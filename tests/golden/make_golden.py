@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vqvae_full_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -363,6 +363,61 @@ def vqvae_step_case():
           (float(loss_gen), float(loss_fm), float(loss_mel), float(kl_ssl), float(loss_kl)), "ids", ids_slice.tolist())
 
 
+def vqvae_full_step_case():
+    """ONE full optimisation step of the REAL reference in its own order (ttts/vqvae/train.py:372-395): discriminator loss on
+    (y, y_hat.detach()) -> optim_d.step() -> generator + feature losses through the UPDATED discriminators -> optim_g.step(), both
+    torch.optim.AdamW(lr 1e-4, betas (0.8, 0.99), eps 1e-9) (train.py:193-205).  Stored: the losses and, per parameter tensor of net_g and
+    net_d, the norm of the update and its projection on a seeded direction.  Same inputs / modes / seed as vqvae_step_case."""
+    from ttts.vqvae.vq2 import SynthesizerTrn, MultiPeriodDiscriminator
+    from ttts.vqvae import losses as RL
+    from ttts.utils import commons
+    from ttts.utils.data_utils import spectrogram_torch, spec_to_mel_torch, mel_spectrogram_torch
+    import json
+    cfg = json.load(open("/root/reference/ttts/vqvae/config.json"))
+    SEG = 8
+    net_g = SynthesizerTrn(1025, SEG, **cfg["vqvae"]).eval()
+    net_d = MultiPeriodDiscriminator(False).eval()
+    G, D = step_params()
+    net_g.load_state_dict(G, strict=False)
+    net_d.load_state_dict(D)
+    wav, lengths, text, text_lengths, E = step_inputs()
+    cb = net_g.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(E); cb.embed_avg.copy_(E); cb.cluster_size.fill_(10); cb.inited.fill_(1)
+    net_g.quantizer.train()
+    optim_g = torch.optim.AdamW(net_g.parameters(), 1e-4, betas=(0.8, 0.99), eps=1e-9)
+    optim_d = torch.optim.AdamW(net_d.parameters(), 1e-4, betas=(0.8, 0.99), eps=1e-9)
+    g_before = {k: v.detach().clone() for k, v in net_g.named_parameters()}
+    d_before = {k: v.detach().clone() for k, v in net_d.named_parameters()}
+    spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
+    torch.manual_seed(0)
+    y_hat, kl_ssl, ids_slice, z_mask, (z, z_p, m_p, logs_p, m_q, logs_q), _ = net_g(wav, wav, lengths * 640, spec, spec, lengths, text.clone(), text_lengths)
+    mel = spec_to_mel_torch(spec, 2048, 128, 32000, 0.0, None)
+    y_mel = commons.slice_segments(mel, ids_slice, SEG)
+    y_hat_mel = mel_spectrogram_torch(y_hat.squeeze(1), 2048, 128, 32000, 640, 2048, 0.0, None)
+    y = commons.slice_segments(wav.unsqueeze(1), ids_slice * 640, SEG * 640)
+    y_d_hat_r, y_d_hat_g, _, _ = net_d(y, y_hat.detach())
+    loss_disc, _, _ = RL.discriminator_loss(y_d_hat_r, y_d_hat_g)
+    optim_d.zero_grad(); loss_disc.backward(); optim_d.step()
+    y_d_hat_r, y_d_hat_g, fmap_r, fmap_g = net_d(y, y_hat)
+    loss_mel = torch.nn.functional.l1_loss(y_mel, y_hat_mel) * 45
+    loss_kl = RL.kl_loss(z_p, logs_q, m_p, logs_p, z_mask) * 1.0
+    loss_fm = RL.feature_loss(fmap_r, fmap_g)
+    loss_gen, _ = RL.generator_loss(y_d_hat_g)
+    total = loss_gen + loss_fm + loss_mel + kl_ssl * 1 + loss_kl
+    optim_g.zero_grad(); total.backward(); optim_g.step()
+    out = dict(loss_disc=float(loss_disc), loss_gen=float(loss_gen), loss_fm=float(loss_fm), total=float(total))
+    for tag, net, before in (("g", net_g, g_before), ("d", net_d, d_before)):
+        names, norm, proj = [], [], []
+        for k, prm in net.named_parameters():
+            dlt = prm.detach() - before[k]
+            d = torch.randn(dlt.shape, generator=torch.Generator().manual_seed(len(names)))
+            names.append(k); norm.append(float(dlt.norm())); proj.append(float((dlt * d).sum()))
+        out[tag + "_names"], out[tag + "_norm"], out[tag + "_proj"] = np.array(names), np.array(norm), np.array(proj)
+    path = os.path.join(ROOT, "tests", "golden", "vqvae_full_step.npz")
+    np.savez_compressed(path, **out)
+    print("vqvae_full_step ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "disc %.4f gen %.4f fm %.4f" % (float(loss_disc), float(loss_gen), float(loss_fm)))
+
+
 def vq_case():
     """EuclideanCodebook / ResidualVectorQuantizer (ttts/vqvae/core_vq.py:96-382, quantize.py:28-118)."""
     from ttts.vqvae.quantize import ResidualVectorQuantizer
@@ -523,6 +578,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "full_step":
+        vqvae_full_step_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "step":
         vqvae_step_case()
         sys.exit(0)
@@ -552,6 +610,7 @@ if __name__ == "__main__":
     flow_case()
     text_encoder_case()
     vqvae_step_case()
+    vqvae_full_step_case()
     vq_case()
     mel_case()
     encoder_case()

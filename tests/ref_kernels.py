@@ -277,3 +277,20 @@ class TorchRefKernels:
 
     def posterior_bwd(self, dz, stats, eps, mask):
         return _vjp(lambda s: self._posterior(s, eps, mask), [stats], dz)[0]
+
+
+class TorchAdamW:
+    """the optimizer contract of train_step.TrainStep with torch.optim.AdamW(lr, betas (0.8, 0.99), eps 1e-9) -- the trainer's own
+    (ttts/vqvae/train.py:193-205) -- so that the ORDER of the step can be checked against the reference on CPU"""
+
+    def __init__(self, params, lr=1e-4):
+        self.p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        self.opt = torch.optim.AdamW(list(self.p.values()), lr, betas=(0.8, 0.99), eps=1e-9)
+
+    def params(self):
+        return {k: v.detach() for k, v in self.p.items()}              # same storage: the in-place update is visible to the graphs
+
+    def step(self, grads):
+        for k, v in self.p.items():
+            v.grad = grads[k].reshape(v.shape).clone()
+        self.opt.step()

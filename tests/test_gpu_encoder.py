@@ -361,7 +361,6 @@ def test_full_train_step_runs_in_the_reference_order(golden_dir):
     assert abs(float(out["loss_gen"]) - float(z["loss_gen"])) <= 0.05 * float(z["loss_gen"])      # the discriminators moved by one lr = 1e-4 step
     # first AdamW step: p <- p (1 - lr wd) - lr g / (|g| + eps)  (bias-corrected m / sqrt(v) = sign-like)
     k = "dec.conv_post.weight"
-    g = ts.opt_g.grad[:0]  # noqa: F841  (flat gradient buffer exists)
     moved = (ts.opt_g.params()[k] - before[k] * (1 - 1e-4 * 0.01)).abs()
     assert float(moved.max()) <= 1.001e-4 and float(moved.mean()) >= 0.5e-4
 

@@ -128,9 +128,12 @@ class TrainStep:
     -> optim_d.step() -> adversarial + feature losses through the UPDATED discriminators -> optim_g.step().  The quantizer's EMA update
     (core_vq.py:217-228) is the caller's (ResidualVectorQuantizer / ttts_vq_ema_update); posterior noises and segment starts are inputs."""
 
-    def __init__(self, K, params_g, params_d, lr=1e-4):
+    def __init__(self, K, params_g, params_d, lr=1e-4, optimizer=None):
+        """`optimizer`: class with (params, lr) -> .params() / .step(grads); the product default is FlatAdamW (CUDA).  Tests pass a torch one
+        to check the ORDER of the step against the reference on CPU."""
         self.K = K
-        self.opt_g, self.opt_d = FlatAdamW(params_g, lr), FlatAdamW(params_d, lr)
+        opt = optimizer if optimizer is not None else FlatAdamW
+        self.opt_g, self.opt_d = opt(params_g, lr), opt(params_d, lr)
 
     def step(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
         Pg, Pd = self.opt_g.params(), self.opt_d.params()
