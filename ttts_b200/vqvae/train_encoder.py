@@ -665,13 +665,30 @@ class CudaKernels:
         return dx, dg, db
 
     def vq_fwd(self, x, embed):
+        """`embed`: the codebook tensor [K, D], or the reference-shaped EuclideanCodebook module of ttts_b200.vqvae.quantize -- then the step is
+        the module's training forward (core_vq.py:205-230): lookup -> expire_codes_ -> EMA update of cluster_size / embed_avg / embed"""
         from . import quantize as Q
+        cb = None
+        if not torch.is_tensor(embed):
+            cb, embed = embed, embed.embed
         self._req(x, embed)
-        codes, q, commit = Q.vq_lookup(x, embed, True, True, straight_through=True, want_commit=True)
+        hist = embed_sum = None
+        if cb is not None:
+            hist = torch.zeros(cb.codebook_size, dtype=torch.float32, device=x.device)
+            embed_sum = torch.zeros_like(cb.embed)
+            embed = embed.clone()                                     # the backward gathers from the PRE-update codebook
+        codes, q, commit = Q.vq_lookup(x, embed, True, True, straight_through=True, want_commit=True, hist=hist, embed_sum=embed_sum)
+        if cb is not None:
+            B, D, Nn = x.shape
+            cb.expire_codes_(x.detach().permute(0, 2, 1).reshape(B * Nn, D))
+            cb._ema_update(hist, embed_sum)
+            self._vq_embed = embed
         return q, commit.reshape(1), codes
 
     def vq_bwd(self, dq, dcommit, x, embed, codes):
         from . import quantize as Q
+        if not torch.is_tensor(embed):
+            embed = self._vq_embed
         lib = self.lib
         Q._protos(lib)
         B, D, Nn = x.shape

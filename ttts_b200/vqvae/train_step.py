@@ -31,7 +31,8 @@ class GeneratorStep:
 
     def synthesize(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
         """SynthesizerTrn.forward (vq2.py:843-871) and the losses that do not involve the discriminators.
-        wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav); wav_aug = wav), lengths [B] frames, text [B,Tt] int64, codebook [1024,192],
+        wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav); wav_aug = wav), lengths [B] frames, text [B,Tt] int64, codebook [1024,192]
+        (or, with the CUDA backend, the EuclideanCodebook module: its EMA buffers are then updated like in the reference's training forward),
         eps_p / eps_q [B,192,T] posterior noises, ids_slice [B] segment starts (frames)."""
         o, enc = self.ops, self.enc
         B, _, T = spec.shape
@@ -125,8 +126,8 @@ class FlatAdamW:
 
 class TrainStep:
     """One optimisation step of ttts/vqvae/train.py:330-406 in the reference's order: synthesis -> discriminator loss on (y, y_hat.detach())
-    -> optim_d.step() -> adversarial + feature losses through the UPDATED discriminators -> optim_g.step().  The quantizer's EMA update
-    (core_vq.py:217-228) is the caller's (ResidualVectorQuantizer / ttts_vq_ema_update); posterior noises and segment starts are inputs."""
+    -> optim_d.step() -> adversarial + feature losses through the UPDATED discriminators -> optim_g.step().  Pass the EuclideanCodebook module as
+    `codebook` to have the quantizer's EMA update (core_vq.py:217-228) inside the step; posterior noises and segment starts are inputs."""
 
     def __init__(self, K, params_g, params_d, lr=1e-4, optimizer=None):
         """`optimizer`: class with (params, lr) -> .params() / .step(grads); the product default is FlatAdamW (CUDA).  Tests pass a torch one
