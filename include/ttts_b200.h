@@ -335,6 +335,12 @@ int ttts_kl_loss(const float* z_p, const float* logs_q, const float* m_p, const 
 int ttts_kl_loss_bwd(const float* z_p, const float* m_p, const float* logs_p, const float* mask, const float* dL, const float* fwd_out2,
                      int32_t B, int32_t C, int32_t T, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p, void* stream);
 
+/* grouped Conv1d (DiscriminatorS, vq2.py:498-507: kernel 41, stride 4, four input channels per group; csrc/conv1d_grouped.cu, same validation
+ * status): x [B,Cin,Tin], w [Cout, Cin/groups, K], dilation 1.  Backward: dx written, dw ACCUMULATES; either may be NULL. */
+int ttts_gconv1d(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
+                 int32_t stride, int32_t pad, int32_t groups, void* stream);
+int ttts_gconv1d_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout,
+                     int32_t K, int32_t stride, int32_t pad, int32_t groups, void* stream);
 /* prior encoder enc_p_2 (TextEncoder + MRTE, vq2.py:17-164; csrc/text_encoder_kernels.cu, same validation status): multi-head attention over
  * short sequences, channel-major, with an optional windowed relative-position term (attentions.py:231-363 in closed form; emb_k / emb_v
  * [2 win + 1, C / heads] or NULL), query / key lengths and the reference's -1e4 masking; LayerNorm over the channel axis (modules.py:20-32). */

@@ -515,6 +515,8 @@ class CudaKernels:
             lib.ttts_lsgan_loss_bwd.argtypes = [vp, f32, vp, i64, vp, vp]
             lib.ttts_l1_mean.argtypes = [vp, vp, i64, vp, vp, vp]
             lib.ttts_l1_mean_bwd.argtypes = [vp, vp, vp, i64, vp, vp]
+            lib.ttts_gconv1d.argtypes = [vp] * 4 + [i32] * 8 + [vp]
+            lib.ttts_gconv1d_bwd.argtypes = [vp] * 5 + [i32] * 8 + [vp]
             lib.ttts_attn_small.argtypes = [vp] * 8 + [i32] * 6 + [vp]
             lib.ttts_attn_small_bwd.argtypes = [vp] * 13 + [i32] * 6 + [vp]
             lib.ttts_layernorm_c.argtypes = [vp] * 5 + [i32] * 3 + [vp]
@@ -544,22 +546,31 @@ class CudaKernels:
 
     # ---- convolution / weight norm ----
     def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, groups=1):
-        if groups > 1:
-            # grouped convolution (DiscriminatorS, vq2.py:498-507) as one launch per group on channel slices: correct, not fast -- a grouped
-            # variant of the kernels is the follow-up once this row is measured
-            ci, co = x.shape[1] // groups, w.shape[0] // groups
-            return torch.cat([self.conv_fwd(x[:, g * ci:(g + 1) * ci].contiguous(), w[g * co:(g + 1) * co].contiguous(),
-                                            b[g * co:(g + 1) * co].contiguous() if b is not None else None, stride, dil, pad, pre_lrelu)
-                              for g in range(groups)], dim=1)
+        if groups > 1:                                                 # DiscriminatorS (vq2.py:498-507): csrc/conv1d_grouped.cu
+            assert dil == 1 and not pre_lrelu
+            self._req(x, w, b)
+            B, Cin, Tin = x.shape
+            Cout, _, K = w.shape
+            y = torch.empty(B, Cout, (Tin + 2 * pad - K) // stride + 1, dtype=torch.float32, device=x.device)
+            self._chk(self.lib.ttts_gconv1d(self._p(x), self._p(w), self._p(b), self._p(y), B, Cin, Tin, Cout, K, stride, pad, groups, self._st()), "ttts_gconv1d")
+            return y
         return self.E.conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=pre_lrelu)
 
     def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
         if groups > 1:
-            ci, co = x.shape[1] // groups, w.shape[0] // groups
-            parts = [self.conv_bwd(dy[:, g * co:(g + 1) * co].contiguous(), x[:, g * ci:(g + 1) * ci].contiguous(), w[g * co:(g + 1) * co].contiguous(),
-                                   stride, dil, pad, pre_lrelu, need_dx, need_db) for g in range(groups)]
-            return (torch.cat([p[0] for p in parts], dim=1) if need_dx else None, torch.cat([p[1] for p in parts], dim=0),
-                    torch.cat([p[2] for p in parts], dim=0) if need_db else None)
+            assert dil == 1 and not pre_lrelu
+            self._req(dy, x, w)
+            B, Cin, Tin = x.shape
+            Cout, _, K = w.shape
+            dx = torch.empty_like(x) if need_dx else None
+            dw = torch.zeros_like(w)
+            self._chk(self.lib.ttts_gconv1d_bwd(self._p(dy), self._p(x), self._p(w), self._p(dx), self._p(dw), B, Cin, Tin, Cout, K, stride, pad, groups,
+                                                self._st()), "ttts_gconv1d_bwd")
+            db = None
+            if need_db:
+                db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
+                self._chk(self.lib.ttts_bias_grad(self._p(dy), self._p(db), B, Cout, dy.shape[-1], self._st()), "ttts_bias_grad")
+            return dx, dw, db
         self._req(dy, x, w)
         B, Cin, Tin = x.shape
         Cout, _, K = w.shape
