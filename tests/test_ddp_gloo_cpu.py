@@ -82,3 +82,33 @@ def test_codebook_statistics_sync_modes():
     port = 31000 + (os.getpid() % 2000)
     mp.spawn(_vq_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _vqvae_worker(rank, world, port, out):
+    """the VQ-VAE step's data parallelism (train_step.gather_and_reduce): the per-rank gradient dict is gathered into one flat buffer in the
+    optimizer's name order, summed with ONE all-reduce, and the returned factor turns the sum into DDP's mean"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ttts_b200.vqvae.train_step import gather_and_reduce
+    shapes = {"dec.conv_pre.weight": (8, 4, 7), "flow.flows.0.pre.bias": (5,), "enc_q.proj.weight": (6, 3, 1), "enc_p_2.text_embedding.weight": (9, 4)}
+    names = list(shapes.keys())
+
+    def grads_for(r):
+        g = torch.Generator().manual_seed(500 + r)
+        return {k: torch.randn(*shapes[k], generator=g) for k in names}
+    flat = torch.zeros(sum(int(torch.tensor(s).prod()) for s in shapes.values()))
+    scale = gather_and_reduce(grads_for(rank), names, flat)
+    want = sum(torch.cat([grads_for(r)[k].reshape(-1) for k in names]) for r in range(world)) / world
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    out[rank] = bool(scale == 1.0 / world and torch.allclose(flat * scale, want, atol=1e-6) and all(torch.equal(gathered[0], t) for t in gathered))
+    dist.destroy_process_group()
+
+
+def test_vqvae_step_gradients_are_averaged_with_one_allreduce():
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_vqvae_worker, args=(world, 29611, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))

@@ -87,6 +87,18 @@ class GeneratorStep:
         return grads
 
 
+def gather_and_reduce(grads, names, flat):
+    """Gather the named gradients into `flat` (the order of `names`) and, under torch.distributed, SUM them over the ranks with one
+    all-reduce (the reference wraps net_g / net_d in DDP, train.py:206-208: mean over ranks).  Returns the factor that turns the sum into the
+    mean (1 / world size), which the fused AdamW kernel applies while it reads the gradient."""
+    import torch.distributed as dist
+    torch.cat([grads[k].reshape(-1) for k in names], out=flat)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
 class FlatAdamW:
     """torch.optim.AdamW(params, lr, betas, eps) of the trainer (train.py:292-303: lr 1e-4, betas (0.8, 0.99), eps 1e-9, weight decay 0.01) over
     ONE flat fp32 buffer: the named tensors become views of it, the gradients are gathered into a second flat buffer and ONE launch of the
@@ -117,11 +129,11 @@ class FlatAdamW:
 
     def step(self, grads):
         self.t += 1
-        torch.cat([grads[k].reshape(-1) for k in self.names], out=self.grad)
+        scale = gather_and_reduce(grads, self.names, self.grad)       # data parallel: ONE all-reduce of the flat gradient buffer per optimizer
         L = self.L
         L.check(L.lib().ttts_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), None, self.flat.numel(),
-                                        None, 0.0, 1.0, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
-                                        int(self.t), L.stream_ptr().value), "ttts_adamw_step")
+                                        None, 0.0, float(scale), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                        float(self.wd), int(self.t), L.stream_ptr().value), "ttts_adamw_step")
 
 
 class TrainStep:
