@@ -290,7 +290,6 @@ int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int
 
 }  // namespace ttts
 
-#ifndef TTTS_HOST_EMU
 extern "C" {
 int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, int32_t accumulate, void* stream) {
@@ -307,4 +306,3 @@ int ttts_conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db
     return ttts::conv1d_bwd_weight(dy, x, dw, db, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, (cudaStream_t)stream);
 }
 }
-#endif

@@ -490,15 +490,26 @@ class EncoderGraph:
 class CudaKernels:
     """The product backend: every method is one call (conv_bwd: two) into libttts_b200.so on the current stream.  Device tensors only."""
 
-    def __init__(self):
-        import ctypes
+    def __init__(self, lib=None):
+        """`lib`: None = libttts_b200.so (the product).  tests/emu_kernels.py passes the host builds of the same sources instead, to run THIS
+        class's argument marshalling on the CPU emulation."""
         from .. import _lib as L
         from . import encoder as E
-        self.L, self.E, self.lib = L, E, L.lib()
-        lib = self.lib
-        E._protos(lib)
+        self.L, self.E = L, E
+        if lib is None:
+            lib = L.lib()
+            E._protos(lib)
+        self.lib = lib
+        self._train_protos(lib)
+
+    @staticmethod
+    def _train_protos(lib):
+        import ctypes
         if not getattr(lib, "_train_protos", False):
             vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+            lib.ttts_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
+            lib.ttts_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
+            lib.ttts_stft_mel_bwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, f32, vp, i32, vp, vp]
             lib.ttts_ew_add.argtypes = [vp, vp, vp, i64, vp]
             lib.ttts_ew_scale.argtypes = [vp, f32, vp, i64, vp]
             lib.ttts_ew_mul_mask.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -539,8 +550,11 @@ class CudaKernels:
     def _p(t):
         return t.data_ptr() if t is not None else None
 
+    def _device_check(self, ts):
+        self.L.require_cuda(*ts)
+
     def _req(self, *ts):
-        self.L.require_cuda(*[t for t in ts if t is not None])
+        self._device_check([t for t in ts if t is not None])
         for t in ts:
             assert t is None or (t.is_contiguous() and t.dtype in (torch.float32, torch.int64)), "contiguous fp32 / int64 tensors only"
 
@@ -603,7 +617,7 @@ class CudaKernels:
         _, Cout, K = w.shape
         Tout = dy.shape[-1]
         p, lib, st = self._p, self.lib, self._st()
-        dx = self.E.conv1d(dy, w, None, stride=stride, dil=1, pad=pad)                      # [B, Cin, T]
+        dx = self.conv_fwd(dy, w, None, stride, 1, pad, False)                              # [B, Cin, T]
         assert dx.shape == x.shape
         dw = torch.zeros_like(w)
         self._chk(lib.ttts_conv1d_bwd_weight(p(x), p(dy), p(dw), None, B, Cout, Tout, Cin, K, stride, 1, pad, 0, st), "ttts_conv1d_bwd_weight (convT)")
@@ -716,15 +730,12 @@ class CudaKernels:
         return M.mel_spectrogram_torch(wav, 2048, 128, 32000, 640, 2048, 0, None)
 
     def logmel_bwd(self, dmel, wav):
-        import ctypes
         from . import mel as M
         dmel = dmel.contiguous()
         self._req(dmel, wav)
         B, Lw = wav.shape
         window, _ = M._stft_consts(2048, 2048, wav.device)
         lo, off, w = M._mel_consts("slaney", 32000, 2048, 128, 0, None, wav.device)
-        vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
-        self.lib.ttts_stft_mel_bwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, f32, vp, i32, vp, vp]
         dwav = torch.zeros_like(wav)
         self._chk(self.lib.ttts_stft_mel_bwd(self._p(wav), B, Lw, 2048, 640, 704, self._p(window), 1e-6, 128, lo.data_ptr(), off.data_ptr(), w.data_ptr(),
                                              1e-5, self._p(dmel), dmel.shape[-1], self._p(dwav), self._st()), "ttts_stft_mel_bwd")
