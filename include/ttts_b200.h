@@ -208,6 +208,11 @@ int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 /* keep mask [BH, T, T] (1 = kept) of the attention-probability dropout for (drop_p, seed): with it torch can reproduce
  * ttts_attn_fwd/bwd under dropout exactly (HF:modeling_gpt2.py:216 attn_dropout; the hash is ours) */
 int ttts_attn_dropout_mask(uint8_t* mask, int32_t BH, int32_t T, float drop_p, uint64_t seed, void* stream);
+/* keep mask one dropout site of ttts_gpt_forward(io) draws for (io->drop_p, io->seed): site 0 = embedding (HF drop, modeling_gpt2.py
+ * GPT2Model.forward), 1 = attention probabilities (attn_dropout; mask [rows = B*H, cols = T, T]), 2 = attention output / 3 = MLP output
+ * (resid_dropout; mask [rows = B*T, cols = d]); `layer` is ignored for site 0.  Kept elements are scaled by 65536 / (65536 - round(p * 65536)).
+ * With the four masks a plain-torch restatement reproduces the TRAINING-mode step exactly (tests/test_gpu_gpt.py). */
+int ttts_gpt_dropout_mask(uint8_t* mask, int32_t site, int32_t layer, int32_t rows, int32_t cols, float drop_p, uint64_t seed, void* stream);
 /* mean cross-entropy over rows of bf16 logits [rows, ld] (ttts/gpt/model.py:508-509) */
 int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, float* row_loss, float* row_lse,
                 float* loss_out, void* stream);
@@ -264,6 +269,11 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
 int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
                           const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream);
+/* the stride-1 "same" convolution of a ResBlock1 layer (C -> C channels, C in {32, 64}, K in {3, 7, 11}, dil in {1, 3, 5}, T >= 128) on the
+ * tcgen05 tensor cores with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; conv1d_tc.cu), whatever TTTS_CONV_TC
+ * says: per-kernel parity tests.  ttts_conv1d_f32 itself routes those layers here when TTTS_CONV_TC=1. */
+int ttts_conv1d_tc(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t C, int32_t T, int32_t K, int32_t dil,
+                   int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, void* stream);
 /* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- written without hardware, validated on the CPU
  * emulation of the source only).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
  *   bwd_input : dx[B,Cin,Tin] (+)= lrelu'(x) * conv_transpose(dy, w)      x only read when pre_lrelu (the forward's input)

@@ -124,14 +124,20 @@ def preprocess(cfg, text_inputs, text_lengths, mel_codes, wav_lengths, clip_inpu
     return text_in, text_tgt, mel_in, mel_tgt
 
 
-def gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16=False, collect=None):
-    """Embeddings -> L GPT-2 blocks -> ln_f -> final_norm.  Returns enc (B,T,d) fp32."""
+def gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16=False, collect=None, masks=None, drop_scale=1.0):
+    """Embeddings -> L GPT-2 blocks -> ln_f -> final_norm.  Returns enc (B,T,d) fp32.
+    masks (training mode, HF GPT2Config defaults embd_pdrop = attn_pdrop = resid_pdrop = 0.1): dict of 0/1 keep masks "embd" [B,T,d],
+    "attn_p%d" [B,H,T,T], "attn_o%d" / "mlp_o%d" [B,T,d]; kept elements are scaled by drop_scale = 1/(1-p), as torch's dropout does
+    (HF:modeling_gpt2.py GPT2Model.drop, GPT2Attention.attn_dropout / resid_dropout, GPT2MLP.dropout).  The mask VALUES are an input: the
+    CUDA path draws them from its own counter-based generator and exports them (ttts_gpt_dropout_mask)."""
+    dm = (lambda t, key: t * masks[key].to(t.dtype) * drop_scale) if masks is not None else (lambda t, key: t)
     d, H = cfg["model_dim"], cfg["heads"]
     hd = d // H
     Tt, Tm = text_in.shape[1], mel_in.shape[1]
     text_emb = params["text_embedding.weight"][text_in] + params["text_pos_embedding.emb.weight"][:Tt]
     mel_emb = params["mel_embedding.weight"][mel_in] + params["mel_pos_embedding.emb.weight"][:Tm]
     x = torch.cat([text_emb, mel_emb], dim=1)          # fp32 residual stream (Appendix A)
+    x = dm(x, "embd")
     B, T, _ = x.shape
     causal = torch.ones(T, T, dtype=torch.bool, device=x.device).tril()
     r = (lambda t: t.to(torch.bfloat16).float()) if emulate_bf16 else (lambda t: t)
@@ -151,18 +157,19 @@ def gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16=False, collect=None):
         att = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
         att = att.masked_fill(~causal, float("-inf"))
         att = torch.softmax(att, dim=-1)
+        att = dm(att, "attn_p%d" % i)
         a = r(r(att) @ v) if emulate_bf16 else att @ v
         a = a.transpose(1, 2).reshape(B, T, d)
         o = _mm(a, params[p + "attn.c_proj.weight"], emulate_bf16)
         o = r(o + params[p + "attn.c_proj.bias"]) if emulate_bf16 else o + params[p + "attn.c_proj.bias"]
-        x = x + o
+        x = x + dm(o, "attn_o%d" % i)
         h = layer_norm(x, params[p + "ln_2.weight"], params[p + "ln_2.bias"])
         f = _mm(h, params[p + "mlp.c_fc.weight"], emulate_bf16)
         f = r(f + params[p + "mlp.c_fc.bias"]) if emulate_bf16 else f + params[p + "mlp.c_fc.bias"]
         g = r(gelu_new(f)) if emulate_bf16 else gelu_new(f)
         o = _mm(g, params[p + "mlp.c_proj.weight"], emulate_bf16)
         o = r(o + params[p + "mlp.c_proj.bias"]) if emulate_bf16 else o + params[p + "mlp.c_proj.bias"]
-        x = x + o
+        x = x + dm(o, "mlp_o%d" % i)
         if collect is not None:
             collect["x%d" % (i + 1)] = x
     x = layer_norm(x, params["gpt.ln_f.weight"], params["gpt.ln_f.bias"])
@@ -171,10 +178,10 @@ def gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16=False, collect=None):
 
 
 def forward(params, cfg, text_inputs, text_lengths, mel_codes, wav_lengths, clip_inputs=True, return_latent=False,
-            emulate_bf16=False, collect=None):
-    """UnifiedVoice.forward (ttts/gpt/model.py:453-510), text_first=True, eval mode (dropout off)."""
+            emulate_bf16=False, collect=None, masks=None, drop_scale=1.0):
+    """UnifiedVoice.forward (ttts/gpt/model.py:453-510), text_first=True; eval mode (dropout off) unless `masks` is given (gpt_hidden)."""
     text_in, text_tgt, mel_in, mel_tgt = preprocess(cfg, text_inputs, text_lengths, mel_codes, wav_lengths, clip_inputs)
-    enc = gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16, collect)
+    enc = gpt_hidden(params, cfg, text_in, mel_in, emulate_bf16, collect, masks, drop_scale)
     Tt, Tm = text_in.shape[1], mel_in.shape[1]
     if return_latent:
         return enc[:, -Tm:][:, :-2]
@@ -245,10 +252,11 @@ def kv_decode_step(params, cfg, cache, slot, tokens, text_positions, pos_shift=0
 
 
 def loss_and_grads(params, cfg, text_inputs, text_lengths, mel_codes, wav_lengths, text_weight=0.01, mel_weight=1.0,
-                   emulate_bf16=False):
+                   emulate_bf16=False, masks=None, drop_scale=1.0):
     """fwd + bwd of loss = text_weight*loss_text + mel_weight*loss_mel (ttts/gpt/train.py:109-112)."""
     ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    lt, lm, logits = forward(ps, cfg, text_inputs, text_lengths, mel_codes.clone(), wav_lengths, emulate_bf16=emulate_bf16)
+    lt, lm, logits = forward(ps, cfg, text_inputs, text_lengths, mel_codes.clone(), wav_lengths, emulate_bf16=emulate_bf16, masks=masks,
+                             drop_scale=drop_scale)
     loss = lt * text_weight + lm * mel_weight
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}

@@ -67,25 +67,26 @@ def test_conv1d_kernel_vs_torch():
 def test_encoder_vs_reference_golden(model, enc):
     wav = torch.tensor(enc["wav"]).cuda()
     out = model(wav, lengths=torch.tensor(enc["lengths"]).cuda(), eps=torch.tensor(enc["eps"]).cuda())
-    assert rel(out["ge"].cpu(), enc["ge"]) < 2e-4
-    assert rel(out["m"].cpu(), enc["m"]) < 5e-4
-    assert rel(out["logs"].cpu(), enc["logs"]) < 5e-4
-    assert rel(out["z"].cpu(), enc["z"]) < 5e-4
-    assert rel(out["x"].cpu(), enc["x"]) < 5e-4
+    # exact-fp32 kernels against the reference's fp32 CPU modules: what differs is summation order only (measured on B200: 2e-6, 0 flips),
+    # so the gate is 1e-5 -- a reduced-precision convolution path (plain bf16 operands: 1e-2; TF32: 1e-3) cannot hide behind it
+    assert rel(out["ge"].cpu(), enc["ge"]) < 1e-5
+    assert rel(out["m"].cpu(), enc["m"]) < 1e-5
+    assert rel(out["logs"].cpu(), enc["logs"]) < 1e-5
+    assert rel(out["z"].cpu(), enc["z"]) < 1e-5
+    assert rel(out["x"].cpu(), enc["x"]) < 1e-5
     codes = out["codes"].cpu().numpy()
     assert codes.shape == enc["codes"].shape
     xn = np.ascontiguousarray(enc["x"].transpose(0, 2, 1)).reshape(-1, 192)
     margin = V.vq_margin(xn, enc["E"], enc["codes"].reshape(-1))
     flips = codes.reshape(-1) != enc["codes"].reshape(-1)
-    assert not np.any(flips & (margin > 2e-3)), "code mismatch away from a near-tie of the reference's own encoder output"
-    assert flips.sum() <= 2
+    assert not np.any(flips & (margin > 1e-5)), "code mismatch away from a near-tie of the reference's own encoder output"
+    assert flips.sum() == 0 or margin[flips].max() <= 1e-5
     # given the encoder output, the lookup itself is bit-exact vs the oracle
     xg = out["x"].cpu().numpy()
     want = V.vq_quantize(np.ascontiguousarray(xg.transpose(0, 2, 1)).reshape(-1, 192), enc["E"])
     assert np.array_equal(codes.reshape(-1), want)
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_CONV_TC") != "1", reason="experimental tensor-core convolution (conv1d_tc.cu): opt-in, round-2 work in progress")
 @pytest.mark.parametrize("C,K,dil,T", [(32, 3, 1, 2304), (32, 11, 5, 2304), (64, 7, 3, 288), (64, 11, 1, 300)])
 def test_conv1d_tc_vs_torch(C, K, dil, T):
     """split-bf16 tcgen05 convolution vs torch fp32: relative error ~1e-5 (tools/split_bf16_conv_study.py), bias / residual / scale fused"""
@@ -96,12 +97,11 @@ def test_conv1d_tc_vs_torch(C, K, dil, T):
     b = torch.randn(C, device="cuda", generator=g)
     res = torch.randn(3, C, T, device="cuda", generator=g)
     pad = dil * (K - 1) // 2
-    got = conv1d(x, w, b, dil=dil, pad=pad, pre_lrelu=True, resid=res, out_scale=0.5)
-    want = (torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x, 0.1), w, b, dilation=dil, padding=pad) + res) * 0.5
+    got = conv1d(x, w, b, dil=dil, pad=pad, pre_lrelu=True, resid=res, out_scale=0.5, tc=True)
+    want = (torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x.double(), 0.1), w.double(), b.double(), dilation=dil, padding=pad) + res.double()) * 0.5
     assert float((got - want).abs().max() / want.abs().max()) < 1e-4
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_SPLIT_TEST") != "1", reason="split-reduction convolution (conv1d_split.cu): validated on the CPU emulation only so far; set TTTS_SPLIT_TEST=1")
 @pytest.mark.parametrize("groups", [2, 4])
 @pytest.mark.parametrize("shape", [(64, 192, 36, 384, 5, 1, 1, 2, 3), (64, 192, 36, 384, 1, 1, 1, 0, 0), (64, 128, 72, 128, 11, 1, 5, 25, 0),
                                    (64, 96, 144, 96, 7, 1, 3, 9, 0), (3, 20, 61, 24, 7, 2, 1, 3, 2), (2, 3, 70, 16, 3, 1, 1, 1, 1)])
@@ -139,7 +139,6 @@ def test_conv1d_split_vs_torch(shape, groups):
     assert float((got - base).abs().max()) <= 1e-5 * max(1.0, scale)
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="Conv1d backward kernels (conv1d_bwd.cu, next scope row): validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 @pytest.mark.parametrize("shape", [(64, 192, 36, 384, 5, 1, 1, 2, False), (8, 32, 2304, 32, 11, 1, 5, 25, True), (8, 16, 2304, 32, 16, 8, 1, 7, False),
                                    (2, 20, 61, 24, 7, 2, 1, 3, True), (1, 3, 70, 5, 3, 1, 1, 1, False)])
 def test_conv1d_backward_vs_autograd(shape):
@@ -163,7 +162,6 @@ def test_conv1d_backward_vs_autograd(shape):
         assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the encode half (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_training_graph_gradients_vs_reference_golden(enc, golden_dir):
     """train_encoder.EncoderGraph over the CUDA kernels: forward values and all 414 parameter gradients against the REAL reference's
     (tests/golden/encoder_grads.npz) -- the same assertions tests/test_train_encoder_cpu.py makes over the torch restatement of the op contract."""
@@ -191,7 +189,6 @@ def test_training_graph_gradients_vs_reference_golden(enc, golden_dir):
         assert abs(float((gk * d).sum()) - float(g["proj"][i])) <= 1e-2 * scale + floor, k
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the decoder (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_decoder_training_graph_vs_reference_golden(golden_dir):
     """train_decoder.DecoderGraph over the CUDA kernels: waveform and parameter gradients of the REAL reference Generator (decoder.npz)"""
     from oracle import decoder_oracle as DO
@@ -212,7 +209,6 @@ def test_decoder_training_graph_vs_reference_golden(golden_dir):
         assert abs(float((gk * d).sum()) - float(dec["proj"][i])) <= 1e-2 * scale + floor, k
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the discriminators (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_discriminator_training_graph_vs_reference_golden(golden_dir):
     """train_disc.DiscriminatorGraph over the CUDA kernels: the three adversarial losses, the discriminator step's parameter gradients and
     dL/dy_hat of the generator step against the REAL reference MultiPeriodDiscriminator (disc.npz)"""
@@ -246,7 +242,6 @@ def test_discriminator_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(yh.g.cpu().numpy() - z["dy_hat"]) <= 1e-3 * np.linalg.norm(z["dy_hat"])
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the flow (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_flow_training_graph_vs_reference_golden(golden_dir):
     """train_flow.FlowGraph + the KL term over the CUDA kernels against the REAL reference ResidualCouplingBlock / kl_loss (flow.npz)"""
     from oracle import flow_oracle as FO
@@ -271,7 +266,6 @@ def test_flow_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(zv.g.cpu().numpy() - z["dz"]) <= 1e-3 * np.linalg.norm(z["dz"])
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="training graph of the prior encoder (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_text_encoder_training_graph_vs_reference_golden(golden_dir):
     """train_text_encoder.TextEncoderGraph over the CUDA kernels against the REAL reference TextEncoder (text_encoder.npz)"""
     from oracle import text_encoder_oracle as TO
@@ -298,7 +292,6 @@ def test_text_encoder_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(yv.g.cpu().numpy() - z["dy"]) <= 1e-3 * np.linalg.norm(z["dy"])
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="generator half of the VQ-VAE-GAN step (next scope row): kernels validated on the CPU emulation only so far; set TTTS_BWD_TEST=1")
 def test_generator_step_vs_reference_golden(golden_dir):
     """train_step.GeneratorStep over the CUDA kernels: the five losses and the gradients of all 1455 net_g tensors of the REAL reference step
     (vqvae_step.npz) -- the assertions of tests/test_train_step_cpu.py with the product backend"""
@@ -333,7 +326,6 @@ def test_generator_step_vs_reference_golden(golden_dir):
     assert not bad, bad[:10]
 
 
-@pytest.mark.skipif(os.environ.get("TTTS_BWD_TEST") != "1", reason="full VQ-VAE-GAN train step (next scope row): not yet run on hardware; set TTTS_BWD_TEST=1")
 def test_full_train_step_runs_in_the_reference_order(golden_dir):
     """train_step.TrainStep: synthesis -> discriminator step -> adversarial losses through the updated discriminators -> generator step, two
     fused AdamW launches over flat buffers.  Losses that do not depend on the discriminators equal the reference golden; the update of a
@@ -363,6 +355,48 @@ def test_full_train_step_runs_in_the_reference_order(golden_dir):
     k = "dec.conv_post.weight"
     moved = (ts.opt_g.params()[k] - before[k] * (1 - 1e-4 * 0.01)).abs()
     assert float(moved.max()) <= 1.001e-4 and float(moved.mean()) >= 0.5e-4
+
+
+def test_weight_norm_cache_is_per_parameter_object():
+    """The cached normalised weight belongs to the (v, g) parameter OBJECTS: a second pair that the caching allocator places at the freed
+    addresses of the first (same shape, version 0) must not hit the first pair's entry, and in-place edits invalidate it."""
+    import gc
+    from ttts_b200.vqvae import encoder as EN
+    want = lambda v, g: g * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+    v1 = torch.nn.Parameter(torch.randn(64, 32, 7, device="cuda")); g1 = torch.nn.Parameter(torch.rand(64, 1, 1, device="cuda") + 0.5)
+    w1 = EN.weight_norm_apply(v1, g1)
+    assert EN.weight_norm_apply(v1, g1) is w1                                   # cached
+    assert float((w1 - want(v1, g1)).abs().max()) < 1e-6
+    a1 = (v1.data_ptr(), g1.data_ptr())
+    n0 = len(EN._wn_cache)
+    del v1, g1, w1
+    gc.collect()
+    assert len(EN._wn_cache) == n0 - 1                                          # the entry died with its parameters
+    v2 = torch.nn.Parameter(torch.randn(64, 32, 7, device="cuda")); g2 = torch.nn.Parameter(torch.rand(64, 1, 1, device="cuda") + 0.5)
+    w2 = EN.weight_norm_apply(v2, g2)
+    assert float((w2 - want(v2, g2)).abs().max()) < 1e-6, "stale weight-norm cache entry (address reuse: %s)" % ((v2.data_ptr(), g2.data_ptr()) == a1)
+    with torch.no_grad():
+        v2.mul_(2.0); g2.add_(1.0)
+    assert float((EN.weight_norm_apply(v2, g2) - want(v2, g2)).abs().max()) < 1e-6
+
+
+def test_tape_codebook_kmeans_initialises_on_first_training_batch():
+    """core_vq.py:209: a fresh quantizer (kmeans_init=True -> all-zero codebook, inited = 0) is k-means-initialised from the first training
+    batch, also on the training tape's codebook op (train_encoder.CudaKernels.vq_fwd), so codes do not collapse to 0."""
+    from ttts_b200.vqvae.quantize import ResidualVectorQuantizer
+    from ttts_b200.vqvae.train_encoder import CudaKernels
+    q = ResidualVectorQuantizer(dimension=192, n_q=1, bins=1024).cuda().train()
+    cb = q.vq.layers[0]._codebook
+    assert float(cb.inited.item()) == 0.0 and float(cb.embed.abs().max()) == 0.0
+    x = torch.randn(32, 192, 18, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    quant, commit, codes = CudaKernels().vq_fwd(x, cb)
+    assert float(cb.inited.item()) == 1.0 and float(cb.embed.abs().max()) > 0
+    assert codes.unique().numel() > 100 and torch.isfinite(quant).all() and torch.isfinite(cb.embed).all()
+    # second batch: no re-initialisation, EMA moves the codebook a little
+    e0 = cb.embed.clone()
+    CudaKernels().vq_fwd(torch.randn(32, 192, 18, device="cuda"), cb)
+    d = float((cb.embed - e0).norm() / e0.norm())
+    assert 0 < d < 0.2
 
 
 def test_encoder_batch64_properties(model):

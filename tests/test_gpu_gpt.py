@@ -139,6 +139,78 @@ def test_fused_step_matches_oracle_adamw():
     assert fused.eng.norm.item() > 0
 
 
+@pytest.mark.parametrize("layers,d,heads,B,TL,CL", [(24, 1024, 16, 1, 128, 1024), (24, 1024, 16, 2, 128, 1024), (12, 512, 8, 2, 128, 512)])
+def test_baseline_configs_full_depth_vs_oracle(layers, d, heads, B, TL, CL):
+    """BASELINE configs 3 (24L / d1024 / H16, text 128, codes 1024) and 2 (12L / d512 / H8, text 128, codes 512) at FULL depth and sequence
+    length, batch 1 - 2 (the fp32 CPU oracle needs seconds per sample): losses, logits and every gradient tensor at the stated bf16
+    tolerances -- bf16 error accumulated through all 24 residual layers is what the 2 - 3 layer cases above cannot show."""
+    cfg = O.default_config(layers=layers, model_dim=d, heads=heads)
+    m, params = build(cfg)
+    batch = O.synthetic_batch(B, TL, CL)
+    lt, lm, logits, grads = O.loss_and_grads(params, cfg, *batch)
+    check_against(m, lt, lm, logits, grads, batch)
+
+
+def test_training_mode_step_matches_oracle_with_exported_masks():
+    """TRAINING mode (dropout 0.1 at the four GPT-2 sites -- what the bench times): the CUDA path exports the keep masks it drew
+    (ttts_gpt_dropout_mask: embedding, attention probabilities, attention output, MLP output of every layer) and the fp32 oracle with
+    exactly those masks applied must give the same losses, logits and gradients at the stated bf16 tolerances."""
+    cfg = O.default_config(layers=3, model_dim=256, heads=4, max_text_tokens=40, max_mel_tokens=200)
+    m, params = build(cfg)
+    m.train()
+    batch = O.synthetic_batch(3, 20, 150)
+    text, tl, codes, wl = [t.cuda() for t in batch]
+    glt, glm, glogits = m(text, tl, codes, wl)
+    (0.01 * glt + glm).backward()
+    eng = m._engine()
+    masks = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.dropout_masks().items()}
+    scale = masks.pop("scale")
+    keep = np.mean([float(v.float().mean()) for v in masks.values()])
+    assert abs(keep - 0.9) < 5e-3 and abs(scale - 1 / 0.9) < 1e-4
+    # the causal part of the attention masks only: entries above the diagonal are never used
+    lt, lm, logits, grads = O.loss_and_grads(params, cfg, *batch, masks=masks, drop_scale=scale)
+    with torch.no_grad():
+        m.eval()
+        _, lm_eval, _ = m(text, tl, codes.clone(), wl)
+    assert abs(float(lm) - lm_eval.item()) > 1e-3             # the masks matter: the masked oracle differs from eval ...
+    assert abs(glt.item() - float(lt)) <= 2e-3 and abs(glm.item() - float(lm)) <= 2e-3     # ... and the CUDA step follows the masked one
+    assert rel(glogits, logits) <= 2e-2
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        g = grads[k]
+        assert rel(p.grad, g) <= 3e-2, (k, rel(p.grad, g))
+        num += (p.grad.float().cpu() - g).norm().item() ** 2
+        den += g.norm().item() ** 2
+    assert (num / den) ** 0.5 <= 2e-2
+
+
+def test_checkpoint_load_after_fused_step_refreshes_the_bf16_shadow(tmp_path):
+    """Parameters are views of one flat buffer re-pointed with `p.data = view`, so writes through a parameter do not move the flat buffer's
+    version counter: after a FusedStep (which trusts version counters), load_state_dict / an in-place edit must still re-cast the bf16
+    shadow the kernels read."""
+    from ttts_b200.gpt.train import FusedStep
+    cfg = O.default_config(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
+    m, params = build(cfg)
+    b = [t.cuda() for t in O.synthetic_batch(2, 12, 24)]
+    with torch.no_grad():
+        _, lm0, lg0 = m(b[0], b[1], b[2].clone(), b[3])
+    fused = FusedStep(m, lr=1e-2)
+    fused.sched_step = 600
+    for _ in range(3):
+        fused(b[0], b[1], b[2].clone(), b[3], clip_inputs=False)
+    with torch.no_grad():
+        _, lm1, _ = m(b[0], b[1], b[2].clone(), b[3])
+    assert abs(lm1.item() - lm0.item()) > 1e-2                      # training moved the model
+    m.load_state_dict(params)                                       # back to the initial checkpoint
+    with torch.no_grad():
+        _, lm2, lg2 = m(b[0], b[1], b[2].clone(), b[3])
+    assert lm2.item() == lm0.item() and torch.equal(lg2, lg0)
+    with torch.no_grad():
+        m.mel_head.bias[5] += 3.0                                   # in-place edit through a parameter
+        _, _, lg3 = m(b[0], b[1], b[2].clone(), b[3])
+    assert abs(float(lg3[0, 5, 0].float() - lg0[0, 5, 0].float()) - 3.0) < 0.05
+
+
 def test_cfg3_full_size_properties():
     """BASELINE config 3 (24 layers, d 1024, 16 heads, batch 32, text 128, codes 1024 -> 36 992 rows): the CPU oracle needs minutes per
     sample at this size, so parity is checked through size-independent properties of the step:
@@ -287,12 +359,9 @@ def test_inference_speech_greedy_matches_oracle():
         m.inference_speech(text.cuda(), cond.cuda(), num_beams=4)
 
 
-# ---- KV-cache decode (csrc/gpt_decode.cu).  Written in a session whose GPU budget was spent: NOT yet run on hardware, so the tests are
-# ---- opt-in (TTTS_KV_TEST=1) until a B200 run has confirmed them; the same functions are pinned on CPU in tests/test_oracle_kv_decode.py.
-kv_optin = pytest.mark.skipif(os.environ.get("TTTS_KV_TEST") != "1", reason="KV-cache decode kernels: not yet validated on hardware; set TTTS_KV_TEST=1")
+# ---- KV-cache decode (csrc/gpt_decode.cu); the same functions are pinned on CPU in tests/test_oracle_kv_decode.py.
 
 
-@kv_optin
 @pytest.mark.parametrize("pos_shift", [0, 1])
 @pytest.mark.parametrize("dims", [(2, 128, 2), (3, 256, 4), (2, 1024, 16)])
 def test_kv_decode_step_matches_oracle(golden_dir, pos_shift, dims):
@@ -337,7 +406,6 @@ def test_kv_decode_step_matches_oracle(golden_dir, pos_shift, dims):
     assert rel(kv, cache[:, :, :, :, :slot]) <= 2e-2
 
 
-@kv_optin
 def test_inference_speech_kv_cache(golden_dir):
     """kv_positions='uncached': cached decoding reproduces the uncached path (and through it the REAL reference's kv_cache=False tokens) up to
     bf16 near-ties; the CUDA-graph replay of the step is token-identical to eager launches; kv_positions='reference' follows gpt_kvstep.npz."""

@@ -256,3 +256,35 @@ def test_cross_entropy_fwd_bwd(L, V, ld):
     L.check(lib.ttts_ce_bwd(L.ptr(logits), ld, V, L.ptr(tgt), rows, L.ptr(row_lse), L.ptr(gs), ctypes.c_float(2.0), L.ptr(dl), L.stream_ptr()))
     assert rel(dl[:, :V], lr.grad) < 5e-3
     assert bool((dl[:, V:] == 0).all())
+
+
+@pytest.mark.parametrize("world,max_norm", [(1, 1.0), (8, 1.0), (1, 1e9)])
+def test_adamw_kernel_exact(L, world, max_norm):
+    """ttts_grad_norm + ttts_adamw_step vs clip_grad_norm_ + torch.optim.AdamW(betas (0.9, 0.96), wd 0.01) on IDENTICAL fp32 gradients
+    (ttts/gpt/train.py:22-31,56,114-118), three steps: fp32 AdamW is exact arithmetic, so parameters, both moments and the norm agree to
+    rounding (FMA contraction / lerp association: ~1 ulp per step), incl. grad_scale = 1/world on a SUMMED gradient buffer, the clip, the
+    bias corrections, weight decay on every tensor, and the bf16 shadow == p.bfloat16()."""
+    lib = L.lib()
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(7 + world)
+    p = torch.randn(n, device="cuda", generator=g) * 0.05
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    norm = torch.zeros(1, device="cuda"); scratch = torch.zeros(2048, device="cuda")
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-4, betas=(0.9, 0.96), eps=1e-8, weight_decay=0.01)
+    for step in range(1, 4):
+        gsum = torch.randn(n, device="cuda", generator=g) * (0.01 * step) * world        # what the all-reduce (SUM) leaves in the buffer
+        ref.grad = gsum / world
+        want_norm = torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        opt.step()
+        L.check(lib.ttts_grad_norm(gsum.data_ptr(), n, scratch.data_ptr(), norm.data_ptr(), L.stream_ptr().value))
+        L.check(lib.ttts_adamw_step(p.data_ptr(), gsum.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), n, norm.data_ptr(), max_norm,
+                                    1.0 / world, 3e-4, 0.9, 0.96, 1e-8, 0.01, step, L.stream_ptr().value))
+        assert abs(norm.item() / world - want_norm.item()) <= 2e-6 * want_norm.item()
+        st = opt.state[ref]
+        assert float((m - st["exp_avg"]).abs().max()) <= 2e-6 * float(st["exp_avg"].abs().max())
+        assert float((v - st["exp_avg_sq"]).abs().max()) <= 2e-6 * float(st["exp_avg_sq"].abs().max())
+        assert float((p - ref.data).abs().max()) <= 1e-6 * float(ref.data.abs().max())
+        assert torch.equal(p16, p.bfloat16())
+    assert rel(p, ref.data) < 1e-7

@@ -584,4 +584,20 @@ int attn_dropout_mask(uint8_t* mask, int BH, int T, DropCfg drop, cudaStream_t s
     return TTTS_OK;
 }
 
+// keep mask of an element-wise dropout site (embedding, attention-output, MLP-output), [rows, cols] bytes: the decision of element
+// (row, c) is field c & 3 of dropout_bits4(seed, (row * cols + c) >> 2) -- the indexing every kernel of those sites uses
+__global__ void elem_dropout_mask_kernel(uint8_t* __restrict__ mask, int cols, DropCfg drop) {
+    const size_t row = blockIdx.x;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const uint64_t bits = dropout_bits4(drop.seed, (row * (uint64_t)cols + (uint64_t)c) >> 2);
+        mask[row * cols + c] = (!drop.thresh16 || dropout_keep(bits, c & 3, drop.thresh16)) ? 1 : 0;
+    }
+}
+int elem_dropout_mask(uint8_t* mask, int rows, int cols, DropCfg drop, cudaStream_t st) {
+    TTTS_CHECK_ARG(mask != nullptr && rows > 0 && cols > 0 && cols % 4 == 0, "elem_dropout_mask: bad arguments");
+    elem_dropout_mask_kernel<<<rows, 256, 0, st>>>(mask, cols, drop);
+    TTTS_LAUNCH_CHECK("elem_dropout_mask");
+    return TTTS_OK;
+}
+
 }  // namespace ttts

@@ -218,10 +218,10 @@ static int conv1d_tc_dispatch(const ConvTcParams& p, int K, int dil, cudaStream_
 
 // -1: not a layer this kernel covers (or TTTS_CONV_TC != 1): the caller goes on to the fp32 kernels
 int conv1d_tc_try(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int stride, int dil, int pad,
-                  int pre_lrelu, const float* resid, float out_scale, int accumulate, const float* mask, int post, cudaStream_t st) {
+                  int pre_lrelu, const float* resid, float out_scale, int accumulate, const float* mask, int post, int force, cudaStream_t st) {
     static int on = -1;
     if (on < 0) { const char* e = getenv("TTTS_CONV_TC"); on = (e && e[0] == '1') ? 1 : 0; }
-    if (!on || stride != 1 || post != 0 || mask != nullptr || Cin != Cout || !(Cin == 32 || Cin == 64) || T < 128 || B > 65535) return -1;
+    if (!(on || force) || stride != 1 || post != 0 || mask != nullptr || Cin != Cout || !(Cin == 32 || Cin == 64) || T < 128 || B > 65535) return -1;
     if (pad * 2 != dil * (K - 1)) return -1;
     ConvTcParams p;
     p.x = x; p.w = w; p.bias = bias; p.y = y; p.B = B; p.T = T; p.pad = pad; p.pre_lrelu = pre_lrelu; p.resid = resid; p.out_scale = out_scale;

@@ -444,6 +444,12 @@ int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 int ttts_attn_dropout_mask(uint8_t* mask, int32_t BH, int32_t T, float drop_p, uint64_t seed, void* stream) {
     return attn_dropout_mask(mask, BH, T, user_drop(drop_p, seed), (cudaStream_t)stream);
 }
+int ttts_gpt_dropout_mask(uint8_t* mask, int32_t site, int32_t layer, int32_t rows, int32_t cols, float drop_p, uint64_t seed, void* stream) {
+    TTTS_CHECK_ARG(site >= SITE_EMBD && site <= SITE_MLP_O && layer >= 0, "gpt_dropout_mask: bad site / layer");
+    const DropCfg dc = site_drop(drop_p, seed, site, layer);
+    if (site == SITE_ATTN_P) return attn_dropout_mask(mask, rows, cols, dc, (cudaStream_t)stream);
+    return elem_dropout_mask(mask, rows, cols, dc, (cudaStream_t)stream);
+}
 int ttts_ce_fwd(const void* logits, int32_t ld, int32_t V, const int32_t* targets, int32_t rows, float* row_loss, float* row_lse, float* loss_out,
                 void* stream) {
     return ce_fwd((const bf16*)logits, ld, V, targets, rows, row_loss, row_lse, loss_out, (cudaStream_t)stream);

@@ -53,6 +53,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, bf16* p16, size_t n
 // attention.cu : qkv is [B*T, 3*d] bf16 (q | k | v, heads = contiguous 64-wide slices); o/do are [B*T, d] bf16.
 int attn_fwd(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropCfg drop, cudaStream_t st);
 int attn_dropout_mask(uint8_t* mask, int BH, int T, DropCfg drop, cudaStream_t st);
+int elem_dropout_mask(uint8_t* mask, int rows, int cols, DropCfg drop, cudaStream_t st);
 int attn_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv, int B, int T, int H, DropCfg drop,
              cudaStream_t st);
 

@@ -80,6 +80,7 @@ def _setup_prototypes(lib):
     lib.ttts_gpt_kv_prefill.argtypes = [ctypes.POINTER(GptIO), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.ttts_gpt_decode_step.argtypes = [ctypes.POINTER(GptDecode), ctypes.c_void_p]
     lib.ttts_cast_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.ttts_gpt_dropout_mask.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_void_p]
     lib.ttts_grad_norm.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.ttts_adamw_step.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_void_p] + [ctypes.c_float] * 7 + [ctypes.c_int32, ctypes.c_void_p]
     lib._gpt_protos = True
@@ -154,7 +155,11 @@ class Engine:
         self.losses = torch.zeros(2, dtype=torch.float32, device=dev)
         self.ws = None
         self._shadow_version = -1
-        self.trust_version = False   # True: only re-cast the bf16 shadow when flat._version moved (fused trainer)
+        # version key of the fp32 master: the flat buffer's counter PLUS every parameter's own counter -- `p.data = view` (UnifiedVoice._apply)
+        # gives each Parameter its own version counter, so load_state_dict / in-place edits through a parameter do not move flat._version.
+        # The owner (UnifiedVoice) installs `version_fn`; stand-alone engines see only the flat buffer.
+        self.version_fn = None
+        self.trust_version = False   # True: only re-cast the bf16 shadow when the version key moved (fused trainer)
         self._last = None      # (B, TL, CL, save, drop_p, seed, text, codes, wav) of the last forward with save_acts
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(2048, dtype=torch.float32, device=dev)
@@ -162,8 +167,15 @@ class Engine:
         self.exp_avg_sq = None
 
     # ---- bf16 shadow ----
+    def _version(self):
+        return self.flat._version if self.version_fn is None else self.flat._version + self.version_fn()
+
+    def invalidate_shadow(self):
+        """the fp32 master changed behind the engine's back (checkpoint load, external optimizer): re-cast at the next use"""
+        self._shadow_version = -1
+
     def refresh_shadow(self, force=False):
-        v = self.flat._version
+        v = self._version()
         if force or v != self._shadow_version:
             L.check(L.lib().ttts_cast_bf16(self.flat.data_ptr(), self.flat16.data_ptr(), self.layout.total, L.stream_ptr().value), "ttts_cast_bf16")
             self._shadow_version = v
@@ -284,6 +296,28 @@ class Engine:
         st["graph"].replay()
         return st["logits"]
 
+    def dropout_masks(self, drop_p=None, seed=None, B=None, T=None):
+        """The keep masks the last forward(save=True) drew (or those of an explicit (drop_p, seed, B, T)), from ttts_gpt_dropout_mask:
+        {"embd", "attn_p<l>", "attn_o<l>", "mlp_o<l>"} as uint8 tensors, plus "scale" = 65536 / (65536 - round(p * 65536))."""
+        if drop_p is None:
+            B, TL, CL, drop_p, seed = self._last[:5]
+            T = TL + CL + 4
+        lib = L.lib()
+        d, H, nl = self.cfg.model_dim, self.cfg.heads, self.cfg.layers
+        out = {"scale": 1.0 / (1.0 - int(drop_p * 65536.0 + 0.5) / 65536.0)}
+
+        def one(site, layer, rows, cols, shape):
+            m = torch.empty(shape, dtype=torch.uint8, device=self.device)
+            L.check(lib.ttts_gpt_dropout_mask(m.data_ptr(), site, layer, rows, cols, float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, L.stream_ptr().value),
+                    "ttts_gpt_dropout_mask")
+            return m
+        out["embd"] = one(0, 0, B * T, d, (B, T, d))
+        for l in range(nl):
+            out["attn_p%d" % l] = one(1, l, B * H, T, (B, H, T, T))
+            out["attn_o%d" % l] = one(2, l, B * T, d, (B, T, d))
+            out["mlp_o%d" % l] = one(3, l, B * T, d, (B, T, d))
+        return out
+
     # ---- step tail ----
     def grad_norm(self):
         L.check(L.lib().ttts_grad_norm(self.grads.data_ptr(), self.layout.total, self._scratch.data_ptr(), self.norm.data_ptr(),
@@ -299,4 +333,4 @@ class Engine:
                                         self.flat16.data_ptr(), self.layout.total, norm_ptr, float(max_norm), float(grad_scale), float(lr),
                                         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), L.stream_ptr().value),
                 "ttts_adamw_step")
-        self._shadow_version = self.flat._version   # kernel wrote the bf16 shadow itself
+        self._shadow_version = self._version()   # kernel wrote the bf16 shadow itself

@@ -206,6 +206,8 @@ class UnifiedVoice(nn.Module):
                 raise L.TTTSError("UnifiedVoice runs on sm_100a only: move the module to a CUDA device (no CPU fallback)")
             with torch.cuda.device(self._flat.device):
                 self._eng = E.Engine(self._cfg, self._flat)
+            plist = list(self._params_by_name.values())
+            self._eng.version_fn = lambda: sum(p._version for p in plist)
         return self._eng
 
     def _grad_views(self):
@@ -220,7 +222,10 @@ class UnifiedVoice(nn.Module):
     def load_state_dict(self, state_dict, strict=True, assign=False):
         # older HF versions stored causal-mask buffers in the checkpoint; they carry no information
         sd = {k: v for k, v in state_dict.items() if not (k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"))}
-        return super().load_state_dict(sd, strict=strict)
+        out = super().load_state_dict(sd, strict=strict)
+        if self._eng is not None:
+            self._eng.invalidate_shadow()       # the bf16 shadow the kernels read is re-cast from the loaded fp32 master at the next call
+        return out
 
     # ------------------------------------------------------------------ reference helpers kept for API parity
     def build_aligned_inputs_and_targets(self, input, start_token, stop_token):

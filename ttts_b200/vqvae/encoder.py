@@ -14,6 +14,7 @@ row of SURVEY.md section 8(f).  No CPU fallback.
 """
 import ctypes
 import math
+import weakref
 import os
 
 import torch
@@ -30,6 +31,7 @@ def _protos(lib):
     vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
     lib.ttts_conv1d_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, vp]
     lib.ttts_conv1d_f32_split.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32, vp]
+    lib.ttts_conv1d_tc.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp]
     lib.ttts_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
     lib.ttts_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.ttts_weight_norm.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -45,9 +47,9 @@ def _p(t):
 
 
 def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None, out_scale=1.0, out=None, accumulate=False, mask=None,
-           post=0, cond=None, split=0):
+           post=0, cond=None, split=0, tc=False):
     """Raw call of ttts_conv1d_f32.  x [B,Cin,T] fp32 contiguous, w [Cout,Cin,K].  split = 2 / 4: force the split-reduction kernel
-    (ttts_conv1d_f32_split; per-kernel tests)."""
+    (ttts_conv1d_f32_split; per-kernel tests); tc: force the split-bf16 tcgen05 kernel (ttts_conv1d_tc)."""
     lib = L.lib(); _protos(lib)
     L.require_cuda(x, w)
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
@@ -59,6 +61,11 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
     if out is None:
         out = torch.empty(B, Ceff, Tout, dtype=torch.float32, device=x.device)
     cond_ld = cond.stride(0) if cond is not None else 0
+    if tc:
+        assert stride == 1 and Cin == Cout and 2 * pad == dil * (K - 1) and mask is None and post == 0
+        L.check(lib.ttts_conv1d_tc(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, K, dil, int(pre_lrelu), _p(resid), float(out_scale), int(accumulate),
+                                   L.stream_ptr().value), "ttts_conv1d_tc")
+        return out
     if split:
         L.check(lib.ttts_conv1d_f32_split(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid),
                                           float(out_scale), int(accumulate), _p(mask), post, _p(cond), cond_ld, int(split), L.stream_ptr().value),
@@ -86,22 +93,25 @@ def conv1d_backward(dy, x, w, stride=1, dil=1, pad=0, pre_lrelu=False, need_bias
     return dx, dw, db
 
 
-_wn_cache = {}
+_wn_cache = weakref.WeakKeyDictionary()       # v (the Parameter OBJECT) -> (weakref(g), state, w): dies with the module, no address reuse
 
 
 def weight_norm_apply(v, g):
-    """g * v / ||v|| (per output channel).  Cached per (v, g) storage + version: in eval / extraction the weights are
-    constants, so the ~170 normalisations of the encoder stack run once instead of once per call."""
-    key = (v.data_ptr(), g.data_ptr())
-    ver = (v._version, g._version, tuple(v.shape))
-    hit = _wn_cache.get(key)
-    if hit is not None and hit[0] == ver and not torch.cuda.is_current_stream_capturing():
-        return hit[1]
+    """g * v / ||v|| (per output channel).  Cached per (v, g) parameter OBJECT, validated by storage address + version counter + shape
+    (so `.cuda()`, `load_state_dict`, an optimizer step or any in-place edit invalidate it): in eval / extraction the weights are
+    constants, so the ~170 normalisations of the encoder stack run once instead of once per call.  Keying on the objects (weakly) rather
+    than on data_ptr() means a second model that the caching allocator places at a freed model's addresses can never hit a stale entry,
+    and entries are dropped when their module is."""
+    state = (v.data_ptr(), g.data_ptr(), v._version, g._version, tuple(v.shape))
+    capturing = torch.cuda.is_current_stream_capturing()
+    hit = _wn_cache.get(v)
+    if hit is not None and hit[0]() is g and hit[1] == state and not capturing:
+        return hit[2]
     lib = L.lib(); _protos(lib)
     w = torch.empty_like(v)
     L.check(lib.ttts_weight_norm(_p(v), _p(g), _p(w), v.shape[0], v[0].numel(), L.stream_ptr().value), "ttts_weight_norm")
-    if not torch.cuda.is_current_stream_capturing():
-        _wn_cache[key] = (ver, w)
+    if not capturing:
+        _wn_cache[v] = (weakref.ref(g), state, w)
     return w
 
 

@@ -128,11 +128,19 @@ class EuclideanCodebook(nn.Module):
         self.register_buffer("embed", embed)
         self.register_buffer("embed_avg", embed.clone())
         self._scratch = None
+        self._inited_host = False        # host copy of `inited` once it has been seen set: no device read per training forward
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._inited_host = False        # a checkpoint may carry inited = 0 or 1: look again
+        return super()._load_from_state_dict(*args, **kwargs)
 
     # ---- rare host-side maintenance (same algorithm / RNG consumption pattern as the reference) ----
     @torch.no_grad()
     def init_embed_(self, data):
+        if self._inited_host:
+            return
         if bool(self.inited.item()):
+            self._inited_host = True
             return
         samples = data[:500, :]
         means = _sample_vectors(samples, self.codebook_size)
@@ -148,13 +156,18 @@ class EuclideanCodebook(nn.Module):
         self.embed_avg.data.copy_(means)
         self.cluster_size.data.copy_(bins.float())
         self.inited.data.fill_(1.0)
+        self._inited_host = True
 
     @torch.no_grad()
     def expire_codes_(self, batch_samples):
+        """core_vq.py:153-161.  The reference returns early (and draws no random numbers) when no code is dead, which costs a device -> host
+        read per training forward; on the GPU the replacement is applied unconditionally instead -- `where(expired, sample, embed)` with an
+        all-false mask is the identity -- so the training step has no host synchronisation and can be captured in a CUDA graph.  The values
+        are the reference's whenever nothing expired; when something did, the replacement rows are random batch vectors in both."""
         if self.threshold_ema_dead_code == 0:
             return
         expired = self.cluster_size < self.threshold_ema_dead_code
-        if not bool(torch.any(expired)):
+        if not batch_samples.is_cuda and not bool(torch.any(expired)):
             return
         flat = batch_samples.reshape(-1, batch_samples.shape[-1])
         self.embed.data.copy_(torch.where(expired[:, None], _sample_vectors(flat, self.codebook_size), self.embed))

@@ -699,6 +699,11 @@ class CudaKernels:
         self._req(x, embed)
         hist = embed_sum = None
         if cb is not None:
+            B, D, Nn = x.shape
+            # first training batch only: k-means initialisation (core_vq.py:209; kmeans_init=True is the quantizer's default, so a fresh
+            # module has an all-zero codebook until this runs -- without it every vector would map to code 0 and the EMA would collapse)
+            cb.init_embed_(x.detach().permute(0, 2, 1).reshape(B * Nn, D))
+            embed = cb.embed
             hist = torch.zeros(cb.codebook_size, dtype=torch.float32, device=x.device)
             embed_sum = torch.zeros_like(cb.embed)
             embed = embed.clone()                                     # the backward gathers from the PRE-update codebook
