@@ -148,26 +148,125 @@ def cpu_oracle_step_time(wl, B, steps, warm, threads):
     return sum(times) / len(times)
 
 
+def host_info():
+    import torch
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        import transformers
+        tv = transformers.__version__
+    except Exception:
+        tv = None
+    return {"os_cpu_count": os.cpu_count(), "cpu_model": model, "torch": torch.__version__, "transformers": tv}
+
+
+def reference_step_times(gm, wl, Bs, steps, warm, threads, checkpointing, autocast_bf16):
+    """The reference's own train step on the host cores: the REAL ttts.gpt.model.UnifiedVoice driven by the loop body of
+    ttts/gpt/train.py:99-121 restated line by line (accelerate is not installed: `accelerator.autocast()` = torch.autocast('cpu', bf16) or
+    nothing, `accelerator.backward` = loss.backward(), `accelerator.clip_grad_norm_` = torch's) -- forward, 0.01 * loss_text + loss_mel,
+    .item(), backward, get_grad_norm (the per-tensor .item() loop, train.py:22-31), clip 1.0, AdamW(lr 1e-4, betas (0.9, 0.96), wd 0.01),
+    zero_grad, LambdaLR warm-up.  Training mode: the four GPT-2 dropouts are on and gradient checkpointing (the constructor default,
+    model.py:256,297) recomputes every block."""
+    import torch
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    kw = dict(GPT_KW, layers=wl["layers"], model_dim=wl["model_dim"], heads=wl["heads"])
+    model = gm.UnifiedVoice(**kw, checkpointing=checkpointing).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.96), weight_decay=0.01)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda st: float(st / 500) if st < 500 else 1)
+    from ttts_b200.gpt import synth
+    text, tl, codes, wlens = synth.synthetic_batch(Bs, wl["TL"], wl["CL"], seed=1234)
+    times = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        if autocast_bf16:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                loss_text, loss_mel, _ = model(text, tl, codes.clone(), wlens)
+                loss = 0.01 * loss_text + 1.0 * loss_mel
+        else:
+            loss_text, loss_mel, _ = model(text, tl, codes.clone(), wlens)
+            loss = 0.01 * loss_text + 1.0 * loss_mel
+        total = loss.item()
+        loss.backward()
+        total_norm = 0.0
+        for p_ in model.parameters():                       # get_grad_norm, train.py:22-31
+            if p_.grad is not None:
+                total_norm += p_.grad.data.norm(2).item() ** 2
+        total_norm = total_norm ** 0.5
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step(); opt.zero_grad(); sched.step()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    assert total == total and total_norm > 0
+    return sum(times) / len(times), total
+
+
 def run_reference(args, wl):
+    """bench.py --impl reference: the reference's CPU implementation of the path on the box's host cores.  The REAL reference modules when a
+    reference tree is on the box (baseline/_ref, installed by baseline/install_ref.py, or /root/reference): kind "reference"; otherwise the
+    oracle port (unit-tested identical to it): kind "port".  BASELINE.md section 3: fp32 with gradient checkpointing (the reference's default
+    configuration), fp32 without, bf16 autocast with and without, on a bounded sample (batch 2 of the workload's shape; frames/s does not depend on the
+    batch to first order, so the cfg3 batch of 32 is this x16: flagged `extrapolated`).  `value` = the FASTEST variant, so the ratio the driver
+    forms against it is the conservative one."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    gm = None
+    why_port = None
+    try:
+        import ref_loader
+        gm = ref_loader.import_reference()
+        if gm is None:
+            why_port = "no reference tree on this box (baseline/_ref, /root/reference)"
+    except Exception as e:                                   # the port always exists
+        why_port = "reference import failed: " + repr(e)[:200]
     threads = pick_cpu_threads(wl)
-    Bs = 1
-    # bounded: each step is the full-shape step at batch 1; cap the number of timed steps so the arm ends within minutes
-    t1 = cpu_oracle_step_time(wl, Bs, 1, 0, threads)
-    steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
-    t = cpu_oracle_step_time(wl, Bs, steps, 0, threads) if steps > 1 else t1
+    info = host_info()
+    info["threads_used"] = threads
+    info["threads_note"] = "best of {all, 1/2, 1/4} hardware threads on a 2-layer probe (torch's intra-op pool with every thread is slower on many-core hosts)"
+    variants = {}
+    if gm is not None:
+        Bs = 2
+        budget = 150.0
+        plan = [("fp32_gradckpt", True, False), ("fp32", False, False), ("bf16_autocast", False, True), ("bf16_autocast_gradckpt", True, True)]
+        t_probe, _ = reference_step_times(gm, wl, Bs, 1, 0, threads, False, False)
+        steps = max(1, min(args.steps, int(budget / (len(plan) * 1.4 * max(t_probe, 1e-3))) - 1))
+        for name, ckpt, ac in plan:
+            t, loss = reference_step_times(gm, wl, Bs, steps, 1, threads, ckpt, ac)
+            variants[name] = {"s_per_step": t, "frames_per_s": Bs * wl["CL"] / t, "loss": loss}
+        best = max(variants, key=lambda k: variants[k]["frames_per_s"])
+        t = variants[best]["s_per_step"]
+        kind = "reference"
+        sample = ("the REAL ttts.gpt.model.UnifiedVoice (%s) driven by the loop body of ttts/gpt/train.py:99-121, training mode, batch %d of the %s shape, "
+                  "%d timed steps after 1 warm-up per variant; value = fastest variant (%s); the reference's default configuration is fp32_gradckpt"
+                  % (ref_loader.find_reference(), Bs, args.workload, steps, best))
+        dtype = "bf16" if "bf16" in best else "f32"
+    else:
+        Bs = 1
+        t1 = cpu_oracle_step_time(wl, Bs, 1, 0, threads)
+        steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
+        t = cpu_oracle_step_time(wl, Bs, steps, 0, threads) if steps > 1 else t1
+        kind, best, dtype = "port", "fp32_port", "f32"
+        sample = "oracle port (fp32, no grad-ckpt) of the reference step at batch %d of the %s shape, %d timed steps (%s)" % (Bs, args.workload, steps, why_port)
     args.steps = steps
     fps = Bs * wl["CL"] / t
     out = {
         "impl": "reference", "metric": "gpt_step_audio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d" % (wl["layers"], wl["model_dim"]),
-                                       "per_gpu_batch": wl["B"], "text_len": wl["TL"], "code_len": wl["CL"], "sample_batch": Bs},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "oracle port (fp32, no grad-ckpt) of the reference step at batch %d of the %s shape, %d timed steps" % (Bs, args.workload, args.steps)},
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+        "data": "synthetic", "config": {"workload": args.workload, "model": "UnifiedVoice %dL/d%d/H%d" % (wl["layers"], wl["model_dim"], wl["heads"]),
+                                       "per_gpu_batch": wl["B"], "text_len": wl["TL"], "code_len": wl["CL"], "seq_len": wl["TL"] + wl["CL"] + 4,
+                                       "sample_batch": Bs, "extrapolated": Bs != wl["B"], "dropout": 0.1, "step": "fwd+bwd+clip+AdamW"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample, "variant": best, "variants": variants,
+                         "host": info},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

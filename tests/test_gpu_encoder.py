@@ -17,6 +17,33 @@ def rel(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-20)
 
 
+def check_param_grads(grads, names, norms, projs, tol_norm=2e-3, tol_proj=1e-2, kink_layers=2, kink_tol=6e-2):
+    """Every parameter-gradient tensor against the golden (norm and a seeded random projection, both relative to the tensor's norm).
+    These networks are piecewise linear around leaky-ReLU kinks: ONE activation within fp32 rounding of zero takes the other slope
+    (1 vs 0.1) on a different summation order, which moves the gradient row of ONE channel of ONE convolution by ~10 % -- at the golden
+    shapes (a level with ~100 positions) that is ~1 % of that layer's weight / bias tensors.  torch itself shows it: the oracle's autograd
+    on the GPU (true fp32) differs from the CPU golden by 1.2e-2 on one bias while the median tensor agrees to 1e-6, and the CUDA tape is
+    run-to-run bit-identical (tools/bwd_debug.py, profiles/r2b_bwd_debug.txt).  So: all tensors at the tight tolerance, except the tensors of
+    at most `kink_layers` convolutions, which must still be within `kink_tol`."""
+    floor = 1e-6 * float(np.sqrt((np.asarray(norms) ** 2).sum()))
+    loose = set()
+    for i, k in enumerate(names):
+        gk = grads[k].cpu()
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
+        scale = float(norms[i])
+        en, ep = abs(float(gk.norm()) - scale), abs(float((gk * d).sum()) - float(projs[i]))
+        if en <= tol_norm * scale + floor and ep <= tol_proj * scale + floor:
+            continue
+        assert en <= kink_tol * scale + floor and ep <= kink_tol * scale + floor, (k, float(gk.norm()), scale, ep / (scale + 1e-30))
+        layer = k
+        for suf in (".bias", ".parametrizations.weight.original0", ".parametrizations.weight.original1", ".weight_g", ".weight_v", ".weight"):
+            if k.endswith(suf):
+                layer = k[:-len(suf)]
+                break
+        loose.add(layer)
+    assert len(loose) <= kink_layers, sorted(loose)
+
+
 @pytest.fixture(scope="module")
 def enc(golden_dir):
     return np.load(os.path.join(golden_dir, "encoder.npz"))
@@ -200,13 +227,7 @@ def test_decoder_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(y.v.cpu().numpy() - dec["y"]) <= 5e-5 * np.linalg.norm(dec["y"])
     R = torch.randn(y.v.shape, generator=torch.Generator().manual_seed(32))
     grads = graph.backward(R.cuda())
-    floor = 1e-6 * float(np.sqrt((dec["norm"] ** 2).sum()))
-    for i, k in enumerate([str(n) for n in dec["names"]]):
-        gk = grads[k].cpu()
-        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
-        scale = float(dec["norm"][i])
-        assert abs(float(gk.norm()) - scale) <= 2e-3 * scale + floor, (k, float(gk.norm()), scale)
-        assert abs(float((gk * d).sum()) - float(dec["proj"][i])) <= 1e-2 * scale + floor, k
+    check_param_grads(grads, [str(n) for n in dec["names"]], dec["norm"], dec["proj"])
 
 
 def test_discriminator_training_graph_vs_reference_golden(golden_dir):
@@ -315,28 +336,23 @@ def test_generator_step_vs_reference_golden(golden_dir):
     for key in ("loss_gen", "loss_fm", "loss_mel", "kl_ssl", "loss_kl", "total"):
         assert abs(float(out[key].v) - float(z[key])) <= 1e-3 * max(1.0, abs(float(z[key]))), (key, float(out[key].v), float(z[key]))
     grads = step.backward()
-    floor = 1e-6 * float(np.sqrt((z["norm"] ** 2).sum()))
-    bad = []
-    for i, k in enumerate([str(n) for n in z["names"]]):
-        gk = grads[k].cpu()
-        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(i))
-        scale = float(z["norm"][i])
-        if not (abs(float(gk.norm()) - scale) <= 5e-3 * scale + floor and abs(float((gk * d).sum()) - float(z["proj"][i])) <= 2e-2 * scale + floor):
-            bad.append((k, float(gk.norm()), scale))
-    assert not bad, bad[:10]
+    check_param_grads(grads, [str(n) for n in z["names"]], z["norm"], z["proj"], tol_norm=5e-3, tol_proj=2e-2)
 
 
 def test_full_train_step_runs_in_the_reference_order(golden_dir):
-    """train_step.TrainStep: synthesis -> discriminator step -> adversarial losses through the updated discriminators -> generator step, two
-    fused AdamW launches over flat buffers.  Losses that do not depend on the discriminators equal the reference golden; the update of a
-    parameter equals torch's AdamW applied to the gradient the tape produced (first step: lr * sign-like update of magnitude ~lr)."""
+    """train_step.TrainStep: synthesis -> discriminator loss on (y, y_hat.detach()) -> optim_d -> adversarial + feature losses through the
+    UPDATED discriminators -> optim_g (ttts/vqvae/train.py:330-406), the two optimizers as ONE fused ttts_adamw_step launch each over flat
+    buffers.  Against ONE real optimisation step of the reference (tests/golden/vqvae_full_step.npz): the four losses (the generator loss
+    drops from 5.53 to 2.53 because the discriminators are stepped first, so the order is visible) and the update of every one of the
+    1455 + 111 parameter tensors -- the assertions of tests/test_train_step_cpu.py::test_full_step_order_and_update_reproduce_the_real_reference."""
     import sys
     sys.path.insert(0, golden_dir)
     import make_golden as MG
     from ttts_b200.vqvae.mel import spectrogram_torch
     from ttts_b200.vqvae.train_encoder import CudaKernels
     from ttts_b200.vqvae.train_step import TrainStep
-    z = np.load(os.path.join(golden_dir, "vqvae_step.npz"))
+    z = np.load(os.path.join(golden_dir, "vqvae_full_step.npz"))
+    zs = np.load(os.path.join(golden_dir, "vqvae_step.npz"))
     G, D = MG.step_params()
     wav, lengths, text, text_lengths, E = MG.step_inputs()
     torch.manual_seed(0)
@@ -344,17 +360,29 @@ def test_full_train_step_runs_in_the_reference_order(golden_dir):
     ids = (torch.rand([3]) * (lengths - 8 + 1)).to(torch.long).tolist()
     c = lambda t: t.cuda()
     ts = TrainStep(CudaKernels(), {k: c(v) for k, v in G.items()}, {k: c(v) for k, v in D.items()})
-    before = {k: v.clone() for k, v in ts.opt_g.params().items()}
     spec = spectrogram_torch(c(wav), 2048, 640, 2048, center=False)
     out = ts.step(c(wav), spec, c(lengths), c(text), c(text_lengths), c(E), c(eps_p), c(eps_q), ids, 8)
-    for key in ("loss_mel", "kl_ssl", "loss_kl"):
-        assert abs(float(out[key]) - float(z[key])) <= 1e-3 * max(1.0, abs(float(z[key]))), key
     assert all(bool(torch.isfinite(v).all()) for v in out.values())
-    assert abs(float(out["loss_gen"]) - float(z["loss_gen"])) <= 0.05 * float(z["loss_gen"])      # the discriminators moved by one lr = 1e-4 step
-    # first AdamW step: p <- p (1 - lr wd) - lr g / (|g| + eps)  (bias-corrected m / sqrt(v) = sign-like)
-    k = "dec.conv_post.weight"
-    moved = (ts.opt_g.params()[k] - before[k] * (1 - 1e-4 * 0.01)).abs()
-    assert float(moved.max()) <= 1.001e-4 and float(moved.mean()) >= 0.5e-4
+    for key in ("loss_mel", "kl_ssl", "loss_kl"):                        # independent of the discriminators: the generator-step golden
+        assert abs(float(out[key]) - float(zs[key])) <= 1e-3 * max(1.0, abs(float(zs[key]))), key
+    for key in ("loss_disc", "loss_gen", "loss_fm", "total"):
+        assert abs(float(out[key]) - float(z[key])) <= 1e-3 * max(1.0, abs(float(z[key]))), (key, float(out[key]), float(z[key]))
+    for tag, opt, before in (("g", ts.opt_g, G), ("d", ts.opt_d, D)):
+        names = [str(n) for n in z[tag + "_names"]]
+        after = opt.params()
+        assert set(names) == set(after.keys())
+        bad = []
+        for i, k in enumerate(names):
+            dlt = (after[k] - c(before[k])).cpu()
+            scale = float(z[tag + "_norm"][i])
+            if k.endswith("conv_k.bias") or k.endswith("w_ks.bias"):      # analytically zero gradient: the +-lr update is fp32 noise in the reference too
+                assert abs(float(dlt.norm()) - scale) <= 0.5 * scale + 1e-9, k
+                continue
+            d = torch.randn(dlt.shape, generator=torch.Generator().manual_seed(i))
+            # first AdamW step is sign-like: elements whose gradient sits at fp32 noise level flip freely (same tolerances as the CPU test)
+            if not (abs(float(dlt.norm()) - scale) <= 2e-2 * scale + 1e-9 and abs(float((dlt * d).sum()) - float(z[tag + "_proj"][i])) <= 0.15 * scale + 1e-9):
+                bad.append((k, float(dlt.norm()), scale))
+        assert len(bad) <= len(names) // 200, bad[:10]
 
 
 def test_weight_norm_cache_is_per_parameter_object():
@@ -368,10 +396,10 @@ def test_weight_norm_cache_is_per_parameter_object():
     assert EN.weight_norm_apply(v1, g1) is w1                                   # cached
     assert float((w1 - want(v1, g1)).abs().max()) < 1e-6
     a1 = (v1.data_ptr(), g1.data_ptr())
-    n0 = len(EN._wn_cache)
+    wr = __import__("weakref").ref(w1)
     del v1, g1, w1
     gc.collect()
-    assert len(EN._wn_cache) == n0 - 1                                          # the entry died with its parameters
+    assert wr() is None                                                         # the entry died with its parameters
     v2 = torch.nn.Parameter(torch.randn(64, 32, 7, device="cuda")); g2 = torch.nn.Parameter(torch.rand(64, 1, 1, device="cuda") + 0.5)
     w2 = EN.weight_norm_apply(v2, g2)
     assert float((w2 - want(v2, g2)).abs().max()) < 1e-6, "stale weight-norm cache entry (address reuse: %s)" % ((v2.data_ptr(), g2.data_ptr()) == a1)

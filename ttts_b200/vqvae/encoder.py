@@ -93,25 +93,22 @@ def conv1d_backward(dy, x, w, stride=1, dil=1, pad=0, pre_lrelu=False, need_bias
     return dx, dw, db
 
 
-_wn_cache = weakref.WeakKeyDictionary()       # v (the Parameter OBJECT) -> (weakref(g), state, w): dies with the module, no address reuse
-
-
 def weight_norm_apply(v, g):
-    """g * v / ||v|| (per output channel).  Cached per (v, g) parameter OBJECT, validated by storage address + version counter + shape
-    (so `.cuda()`, `load_state_dict`, an optimizer step or any in-place edit invalidate it): in eval / extraction the weights are
-    constants, so the ~170 normalisations of the encoder stack run once instead of once per call.  Keying on the objects (weakly) rather
-    than on data_ptr() means a second model that the caching allocator places at a freed model's addresses can never hit a stale entry,
-    and entries are dropped when their module is."""
+    """g * v / ||v|| (per output channel).  Cached ON the parameter object `v` (attribute `_ttts_wn`), validated by the identity of `g`,
+    storage addresses, version counters and shape (so `.cuda()`, `load_state_dict`, an optimizer step or any in-place edit invalidate it):
+    in eval / extraction the weights are constants, so the ~170 normalisations of the encoder stack run once instead of once per call.
+    Living on the object (not in a table keyed by data_ptr()) the entry dies with its module, and a second model that the caching
+    allocator places at a freed model's addresses can never hit it."""
     state = (v.data_ptr(), g.data_ptr(), v._version, g._version, tuple(v.shape))
     capturing = torch.cuda.is_current_stream_capturing()
-    hit = _wn_cache.get(v)
+    hit = getattr(v, "_ttts_wn", None)
     if hit is not None and hit[0]() is g and hit[1] == state and not capturing:
         return hit[2]
     lib = L.lib(); _protos(lib)
     w = torch.empty_like(v)
     L.check(lib.ttts_weight_norm(_p(v), _p(g), _p(w), v.shape[0], v[0].numel(), L.stream_ptr().value), "ttts_weight_norm")
     if not capturing:
-        _wn_cache[v] = (weakref.ref(g), state, w)
+        v._ttts_wn = (weakref.ref(g), state, w)
     return w
 
 
