@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vq-encode", action="store_true")
+    ap.add_argument("--no-vqvae-step", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): the workload's batch PER GPU; strong: that batch split over the GPUs (SURVEY.md 8d secondary line)")
@@ -466,6 +467,15 @@ def main():
             out["vq_encode"] = vq_encode_bench.run(hbm_gbs=pk["hbm_gbs"], with_cpu=not args.no_cpu_baseline)
         except Exception as e:            # the GPT line must still be printed
             out["vq_encode"] = {"error": repr(e)[:300]}
+    if world == 1 and not args.no_vqvae_step and not args.profile_run and args.workload == "cfg3":
+        # BASELINE config 4: one VQ-VAE-GAN train step (enc + VQ + dec + disc), batch 64 x 23 040 samples, through TrainStep.step
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import vqvae_step_bench
+            torch.cuda.empty_cache()
+            out["vqvae_step"] = vqvae_step_bench.run(B=64, iters=3, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:
+            out["vqvae_step"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

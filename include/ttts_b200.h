@@ -210,7 +210,7 @@ int ttts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 int ttts_attn_dropout_mask(uint8_t* mask, int32_t BH, int32_t T, float drop_p, uint64_t seed, void* stream);
 /* keep mask one dropout site of ttts_gpt_forward(io) draws for (io->drop_p, io->seed): site 0 = embedding (HF drop, modeling_gpt2.py
  * GPT2Model.forward), 1 = attention probabilities (attn_dropout; mask [rows = B*H, cols = T, T]), 2 = attention output / 3 = MLP output
- * (resid_dropout; mask [rows = B*T, cols = d]); `layer` is ignored for site 0.  Kept elements are scaled by 65536 / (65536 - round(p * 65536)).
+ * (resid_dropout; mask [rows = B*T, cols = d]); `layer` is ignored for site 0.  Kept elements are scaled by 32768 / (32768 - round(p * 32768)).
  * With the four masks a plain-torch restatement reproduces the TRAINING-mode step exactly (tests/test_gpu_gpt.py). */
 int ttts_gpt_dropout_mask(uint8_t* mask, int32_t site, int32_t layer, int32_t rows, int32_t cols, float drop_p, uint64_t seed, void* stream);
 /* mean cross-entropy over rows of bf16 logits [rows, ld] (ttts/gpt/model.py:508-509) */
@@ -269,11 +269,16 @@ int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y,
 int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
                           const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream);
-/* the stride-1 "same" convolution of a ResBlock1 layer (C -> C channels, C in {32, 64}, K in {3, 7, 11}, dil in {1, 3, 5}, T >= 128) on the
- * tcgen05 tensor cores with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; conv1d_tc.cu), whatever TTTS_CONV_TC
- * says: per-kernel parity tests.  ttts_conv1d_f32 itself routes those layers here when TTTS_CONV_TC=1. */
-int ttts_conv1d_tc(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t C, int32_t T, int32_t K, int32_t dil,
-                   int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, void* stream);
+/* A stride-1 "same" convolution (pad = dil (K - 1) / 2; Cin % 8 == 0, 16 <= Cin <= 192; Cout in {32, 64, 96, 128, 192, 384}) of the encoder's
+ * ResBlock1 / WN stacks (ttts/vqvae/modules.py:136-318) on the tcgen05 tensor cores with split-bf16 operands -- hi*hi + hi*lo + lo*hi,
+ * fp32 accumulation in TMEM, ~1.5e-5 relative to fp32 -- and no im2col: a tap is a row shift of ONE channel-last window in shared memory
+ * (csrc/conv1d_tcs.cu).  The weights are split once per layer into a caller-owned bf16 buffer of ttts_conv1d_tcs_weight_elems() elements:
+ *   y = ((conv(lrelu?(x), w) + bias) + resid) * out_scale * mask ; accumulate: y += ;  flags bit 0: leave the descriptor base-offset 0 (debug) */
+int64_t ttts_conv1d_tcs_weight_elems(int32_t Cout, int32_t Cin, int32_t K);
+int ttts_conv1d_tcs_prep_weights(const float* w, void* ws_bf16, int32_t Cout, int32_t Cin, int32_t K, void* stream);
+int ttts_conv1d_tcs(const float* x, const void* ws_bf16, const float* bias, float* y, int32_t B, int32_t Cin, int32_t T, int32_t Cout, int32_t K,
+                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t flags,
+                    void* stream);
 /* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- written without hardware, validated on the CPU
  * emulation of the source only).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
  *   bwd_input : dx[B,Cin,Tin] (+)= lrelu'(x) * conv_transpose(dy, w)      x only read when pre_lrelu (the forward's input)

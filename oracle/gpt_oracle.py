@@ -316,7 +316,8 @@ def flops_per_step(cfg, B, TL, CL):
 # quality of the hash (keep rate, correlations, spectrum) is checked on the CPU in tests/test_oracle_golden.py.
 # ---------------------------------------------------------------------------------------------------------------------
 def attn_dropout_thresh16(p):
-    return int(p * 65536.0 + 0.5)
+    """p rounded to a multiple of 2^-15, as a 16-bit threshold (always even): the attention hash decides on 15-bit fields"""
+    return 2 * int(p * 32768.0 + 0.5)
 
 
 def attn_dropout_keep_mask(seed, rows, T, p):
@@ -340,6 +341,8 @@ def attn_dropout_keep_mask(seed, rows, T, p):
         m3 = y * U(0x27D4EB2F)
         w0 = (m3 >> U(32)) ^ (m2 & lo32)
         w1 = (m3 & lo32) ^ (m2 >> U(32))
-        t32 = U(attn_dropout_thresh16(p) << 16)
-        f = np.stack([w0, (w0 << U(16)) & lo32, w1, (w1 << U(16)) & lo32], axis=-1)
-    return (f >= t32).reshape(len(rows), -1)[:, :T]
+        t15 = U(attn_dropout_thresh16(p) >> 1)
+        m15 = U(0x7FFF)
+        # four 15-bit fields per group: key 4g+0 <- w0 bits 0-14, 4g+1 <- w0 bits 16-30, 4g+2 <- w1 bits 0-14, 4g+3 <- w1 bits 16-30
+        f = np.stack([w0 & m15, (w0 >> U(16)) & m15, w1 & m15, (w1 >> U(16)) & m15], axis=-1)
+    return (f >= t15).reshape(len(rows), -1)[:, :T]

@@ -114,19 +114,38 @@ def test_encoder_vs_reference_golden(model, enc):
     assert np.array_equal(codes.reshape(-1), want)
 
 
-@pytest.mark.parametrize("C,K,dil,T", [(32, 3, 1, 2304), (32, 11, 5, 2304), (64, 7, 3, 288), (64, 11, 1, 300)])
-def test_conv1d_tc_vs_torch(C, K, dil, T):
-    """split-bf16 tcgen05 convolution vs torch fp32: relative error ~1e-5 (tools/split_bf16_conv_study.py), bias / residual / scale fused"""
+@pytest.mark.parametrize("B,Cin,Cout,K,dil,T", [(3, 32, 32, 3, 1, 2304), (3, 32, 32, 11, 5, 2304), (3, 64, 64, 7, 3, 288), (2, 64, 64, 11, 1, 300),
+                                                (5, 96, 96, 7, 5, 144), (6, 128, 128, 11, 3, 72), (7, 192, 192, 11, 5, 36), (9, 192, 192, 3, 1, 36),
+                                                (4, 192, 384, 1, 1, 36), (4, 192, 192, 5, 1, 36), (2, 40, 64, 3, 1, 50), (1, 16, 32, 7, 1, 7)])
+def test_conv1d_tcs_vs_torch(B, Cin, Cout, K, dil, T):
+    """ttts_conv1d_tcs (split-bf16 tcgen05, taps as row shifts of one channel-last window, clips packed into 128-row tiles) vs torch in
+    fp64 on every ResBlock1 level of the encoder (32 ... 192 channels, 2304 ... 36 frames), the WN 1x1 / kernel-5 shapes and ragged ones:
+    ~1e-5 relative (three of the four hi / lo products), with bias / leaky-ReLU input / residual / scale / mask / accumulate fused."""
     from ttts_b200.vqvae.encoder import conv1d
-    g = torch.Generator(device="cuda").manual_seed(C + K + dil)
-    x = torch.randn(3, C, T, device="cuda", generator=g)
-    w = 0.1 * torch.randn(C, C, K, device="cuda", generator=g)
-    b = torch.randn(C, device="cuda", generator=g)
-    res = torch.randn(3, C, T, device="cuda", generator=g)
+    g = torch.Generator(device="cuda").manual_seed(B + Cin + K + dil + T)
+    x = torch.randn(B, Cin, T, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, K, device="cuda", generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, T, device="cuda", generator=g)
+    mask = (torch.rand(B, T, device="cuda", generator=g) > 0.2).float()
     pad = dil * (K - 1) // 2
-    got = conv1d(x, w, b, dil=dil, pad=pad, pre_lrelu=True, resid=res, out_scale=0.5, tc=True)
-    want = (torch.nn.functional.conv1d(torch.nn.functional.leaky_relu(x.double(), 0.1), w.double(), b.double(), dilation=dil, padding=pad) + res.double()) * 0.5
-    assert float((got - want).abs().max() / want.abs().max()) < 1e-4
+    y0 = torch.randn(B, Cout, T, device="cuda", generator=g)
+    for lrelu, use_res, scale, use_mask, acc in ((True, True, 0.5, False, False), (False, False, 1.0, True, False), (True, True, 1.0 / 3, False, True)):
+        out = y0.clone()
+        got = conv1d(x, w, b, dil=dil, pad=pad, pre_lrelu=lrelu, resid=res if use_res else None, out_scale=scale, mask=mask if use_mask else None,
+                     out=out, accumulate=acc, tc=True)
+        xin = torch.nn.functional.leaky_relu(x.double(), 0.1) if lrelu else x.double()
+        want = torch.nn.functional.conv1d(xin, w.double(), b.double(), dilation=dil, padding=pad)
+        if use_res:
+            want = want + res.double()
+        want = want * scale
+        if use_mask:
+            want = want * mask[:, None, :].double()
+        if acc:
+            want = want + y0.double()
+        err = float((got.double() - want).norm() / want.norm())
+        assert err < 3e-5, (lrelu, use_res, acc, err)
+        assert float((got.double() - want).abs().max()) < 2e-4 * float(want.abs().max())
 
 
 @pytest.mark.parametrize("groups", [2, 4])
@@ -227,7 +246,8 @@ def test_decoder_training_graph_vs_reference_golden(golden_dir):
     assert np.linalg.norm(y.v.cpu().numpy() - dec["y"]) <= 5e-5 * np.linalg.norm(dec["y"])
     R = torch.randn(y.v.shape, generator=torch.Generator().manual_seed(32))
     grads = graph.backward(R.cuda())
-    check_param_grads(grads, [str(n) for n in dec["names"]], dec["norm"], dec["proj"])
+    # the golden decoder input is 6 frames: its first level has 2 x 48 positions, so one kink flip there is visible in three layers' tensors
+    check_param_grads(grads, [str(n) for n in dec["names"]], dec["norm"], dec["proj"], kink_layers=3)
 
 
 def test_discriminator_training_graph_vs_reference_golden(golden_dir):

@@ -1,7 +1,9 @@
-"""First timing of the generator half of the VQ-VAE-GAN train step (BASELINE.json config 4: enc + VQ + dec + disc) on the
-training tape (ttts_b200/vqvae/train_step.py) with the reference's segment size (20 480 samples = 32 frames) at batch B clips of 23 040
-samples.  Correctness-first kernels (no pipelining, grouped convolutions per group): the number is a starting point, not a claim.
-Prints one JSON object.   python tools/vqvae_step_bench.py [B] [iters]"""
+"""BASELINE.json config 4: one VQ-VAE-GAN train step (enc + VQ + dec + disc; ttts/vqvae/train.py:330-406) at batch B clips of 23 040 samples,
+the reference's segment size (20 480 samples = 32 frames), through `ttts_b200.vqvae.train_step.TrainStep.step` -- synthesis -> discriminator
+loss -> optim_d -> adversarial + feature losses through the updated discriminators -> optim_g, two fused AdamW launches.  CUDA-event timing.
+Imported by bench.py (key "vqvae_step"); stand-alone:   python tools/vqvae_step_bench.py [B] [iters] [--cpu]
+`--cpu` / with_cpu: the REAL reference's step (SynthesizerTrn + MultiPeriodDiscriminator + the trainer's losses and AdamW pair, aug = identity)
+on the host cores at a bounded batch, when a reference tree is on the box (baseline/_ref)."""
 import json
 import os
 import sys
@@ -10,18 +12,21 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+
+SEG = 32            # segment_size 20480 / hop 640 (ttts/vqvae/config.json)
+TEXT = 40
+FLOP_PER_CLIP = 3.87e11     # FlopCounterMode over the reference's full step per sample (aug = identity)
 
 
-def main():
+def run(B=64, iters=3, with_cpu=False, cpu_batch=2):
     import torch
     import make_golden as MG
     from ttts_b200 import _lib as L
     from ttts_b200.vqvae.mel import spectrogram_torch
     from ttts_b200.vqvae.train_encoder import CudaKernels
-    from ttts_b200.vqvae.train_step import GeneratorStep
+    from ttts_b200.vqvae.train_step import TrainStep
 
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     dev = torch.device("cuda")
     G, D = MG.step_params()
     G = {k: v.to(dev) for k, v in G.items()}
@@ -29,32 +34,95 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1234)
     wav = torch.clamp(0.1 * torch.randn(B, 23040, device=dev, generator=g), -1, 1)
     lengths = torch.full((B,), 36, dtype=torch.int64, device=dev)
-    text = torch.randint(0, 256, (B, 40), device=dev, generator=g)
-    text_lengths = torch.full((B,), 40, dtype=torch.int64, device=dev)
+    text = torch.randint(0, 256, (B, TEXT), device=dev, generator=g)
+    text_lengths = torch.full((B,), TEXT, dtype=torch.int64, device=dev)
     E = torch.randn(1024, 192, device=dev, generator=g)
     eps_p, eps_q = torch.randn(B, 192, 36, device=dev, generator=g), torch.randn(B, 192, 36, device=dev, generator=g)
     ids = [int(i) % 5 for i in range(B)]
     lib = L.lib()
     lib.ttts_launch_count.restype = __import__("ctypes").c_ulonglong
-    K = CudaKernels()
-    times, launches = [], 0
-    for it in range(iters + 1):
+    ts = TrainStep(CudaKernels(), G, D)
+
+    def step():
         spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
-        torch.cuda.synchronize()
-        l0, t0 = lib.ttts_launch_count(), time.perf_counter()
-        step = GeneratorStep(K, G, D)
-        out = step.forward(wav, spec, lengths, text, text_lengths, E, eps_p, eps_q, ids, 32)
-        grads = step.backward()
-        torch.cuda.synchronize()
-        if it > 0:
+        return ts.step(wav, spec, lengths, text, text_lengths, E, eps_p, eps_q, ids, SEG)
+    out = step()
+    torch.cuda.synchronize()
+    l0 = lib.ttts_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / iters * 1e3
+    ms = e0.elapsed_time(e1) / iters
+    launches = (lib.ttts_launch_count() - l0) // iters
+    res = {"workload": "VQ-VAE-GAN train step (BASELINE config 4): enc + VQ + dec + disc, generator + discriminator AdamW, segment 20480, aug = identity",
+           "batch": B, "samples_per_clip": 23040, "ms_per_step": ms, "host_ms_per_step": wall, "msamples_per_s": B * 23040 / ms / 1e3,
+           "gpu_launches_per_step": int(launches), "dtype": "f32",
+           "step_tflops": FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
+           "flop_model": "3.87e11 FLOP per clip and step (SURVEY.md section 6, FlopCounterMode over the reference's step)",
+           "losses": {k: float(v) for k, v in out.items()}}
+    if with_cpu:
+        try:
+            res["cpu_baseline"] = cpu_reference_step(cpu_batch)
+        except Exception as e:
+            res["cpu_baseline"] = {"error": repr(e)[:300]}
+    return res
+
+
+def cpu_reference_step(B=2, steps=1):
+    """the REAL reference's optimisation step on the host cores (the body of ttts/vqvae/train.py:330-406 with aug = identity, fp32, as
+    tests/golden/make_golden.py::vqvae_full_step_case runs it), random-init modules, segment 32 frames, one warm-up + `steps` timed"""
+    import torch
+    import ref_loader
+    gm = ref_loader.import_reference()
+    if gm is None:
+        return {"unavailable": "no reference tree on this box (baseline/_ref, /root/reference)"}
+    from ttts.vqvae.vq2 import SynthesizerTrn, MultiPeriodDiscriminator
+    from ttts.vqvae import losses as RL
+    from ttts.utils import commons
+    from ttts.utils.data_utils import spectrogram_torch, spec_to_mel_torch, mel_spectrogram_torch
+    cfg = json.load(open(os.path.join(ref_loader.find_reference(), "ttts", "vqvae", "config.json")))
+    torch.manual_seed(0)
+    net_g = SynthesizerTrn(1025, SEG, **cfg["vqvae"]).train()
+    net_d = MultiPeriodDiscriminator(False).train()
+    cb = net_g.quantizer.vq.layers[0]._codebook
+    cb.embed.copy_(torch.randn(1024, 192)); cb.embed_avg.copy_(cb.embed); cb.cluster_size.fill_(10); cb.inited.fill_(1)
+    optim_g = torch.optim.AdamW(net_g.parameters(), 1e-4, betas=(0.8, 0.99), eps=1e-9)
+    optim_d = torch.optim.AdamW(net_d.parameters(), 1e-4, betas=(0.8, 0.99), eps=1e-9)
+    wav = torch.clamp(0.1 * torch.randn(B, 23040), -1, 1)
+    lengths = torch.full((B,), 36, dtype=torch.int64)
+    text = torch.randint(0, 256, (B, TEXT))
+    text_lengths = torch.full((B,), TEXT, dtype=torch.int64)
+    times = []
+    for i in range(1 + steps):
+        t0 = time.perf_counter()
+        spec = spectrogram_torch(wav, 2048, 640, 2048, center=False)
+        y_hat, kl_ssl, ids_slice, z_mask, (z, z_p, m_p, logs_p, m_q, logs_q), _ = net_g(wav, wav, lengths * 640, spec, spec, lengths, text.clone(), text_lengths)
+        mel = spec_to_mel_torch(spec, 2048, 128, 32000, 0.0, None)
+        y_mel = commons.slice_segments(mel, ids_slice, SEG)
+        y_hat_mel = mel_spectrogram_torch(y_hat.squeeze(1), 2048, 128, 32000, 640, 2048, 0.0, None)
+        y = commons.slice_segments(wav.unsqueeze(1), ids_slice * 640, SEG * 640)
+        y_d_hat_r, y_d_hat_g, _, _ = net_d(y, y_hat.detach())
+        loss_disc, _, _ = RL.discriminator_loss(y_d_hat_r, y_d_hat_g)
+        optim_d.zero_grad(); loss_disc.backward(); optim_d.step()
+        y_d_hat_r, y_d_hat_g, fmap_r, fmap_g = net_d(y, y_hat)
+        loss_mel = torch.nn.functional.l1_loss(y_mel, y_hat_mel) * 45
+        loss_kl = RL.kl_loss(z_p, logs_q, m_p, logs_p, z_mask) * 1.0
+        loss_fm = RL.feature_loss(fmap_r, fmap_g)
+        loss_gen, _ = RL.generator_loss(y_d_hat_g)
+        total = loss_gen + loss_fm + loss_mel + kl_ssl * 1 + loss_kl
+        optim_g.zero_grad(); total.backward(); optim_g.step()
+        if i > 0:
             times.append(time.perf_counter() - t0)
-            launches = lib.ttts_launch_count() - l0
-    ms = 1e3 * sorted(times)[len(times) // 2]
-    print(json.dumps({"workload": "VQ-VAE-GAN generator step (fwd + bwd, no optimizer), segment 20480", "B": B, "ms_per_step": ms,
-                      "samples_per_s": B * 23040 / ms * 1e3, "kernel_launches": int(launches), "n_grad_tensors": len(grads),
-                      "losses": {k: float(out[k].v) for k in ("loss_gen", "loss_fm", "loss_mel", "kl_ssl", "loss_kl")},
-                      "timing": "host wall clock around a synchronised step (hundreds of small launches: launch-bound by construction)"}))
+    t = sum(times) / len(times)
+    return {"value": B * 23040 / t / 1e6, "unit": "Msamples/s", "s_per_step": t, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": "the REAL SynthesizerTrn + MultiPeriodDiscriminator step (fp32, aug = identity) at batch %d, %d timed step(s) after 1 warm-up" % (B, steps)}
 
 
 if __name__ == "__main__":
-    main()
+    a = [x for x in sys.argv[1:] if not x.startswith("--")]
+    print(json.dumps(run(int(a[0]) if a else 8, int(a[1]) if len(a) > 1 else 3, with_cpu="--cpu" in sys.argv)))

@@ -94,7 +94,7 @@ def gemm(A, B, out, *, a_mn=False, b_mn=False, epi=EPI_BF16, bias=None, aux=None
     g.aux_out, g.ldaux_out = (aux_out.data_ptr(), aux_out.stride(0)) if aux_out is not None else (None, 0)
     g.split_k = split_k
     if drop_p > 0:
-        g.drop_thresh16 = int(round(drop_p * 65536))
+        g.drop_thresh16 = 2 * int(drop_p * 32768.0 + 0.5)
         g.drop_scale = 1.0 / (1.0 - g.drop_thresh16 / 65536.0)
         g.drop_seed = drop_seed
     check(lib().ttts_gemm_bf16(ctypes.byref(g), stream_ptr()), "ttts_gemm_bf16")

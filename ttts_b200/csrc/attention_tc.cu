@@ -46,6 +46,13 @@ TTTS_DEVICE void st_tile_chunk(uint32_t base, int r, int c16, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+TTTS_DEVICE uint32_t tile_chunk_addr(uint32_t base, int r, int c16) { return base + (c16 >> 3) * AT_TILE + r * 128 + ((((c16 & 7) ^ r) & 7) << 4); }
+TTTS_DEVICE void sts_v4(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+// shared-space scalar accesses by 32-bit address: through a generic pointer derived from the aligned dynamic-smem base the compiler emits
+// generic LD / ST (r1n profile: the row-max exchange's LD.E was the third-hottest stall site of the forward kernel)
+TTTS_DEVICE void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+TTTS_DEVICE float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+
 constexpr int AT3_THREADS = 576;      // warp 0 TMA, warp 1 MMA, 16 math warps (four per TMEM lane quadrant, 32 columns each)
 
 // ------------------------------------------------------------------------------------------------------------
@@ -81,7 +88,7 @@ struct Fwd4Smem {
 // work issues in the shadow of the MUFU pipe.  The row-max exchange only concerns the four warps that share a lane quadrant (same rows,
 // different columns), so it uses one 128-thread named barrier per quadrant instead of one for all 16 warps.  Same arithmetic, same bits.
 template <int kMode>
-__global__ void __maxnreg__(96)
+__global__ void __maxnreg__(112)
 attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, int BH, float scale,
                     DropCfg drop) {
     using S = Fwd4Smem;
@@ -96,7 +103,6 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     uint64_t* s_empty = bars + 12;                 // [2]  16
     uint64_t* p_full = bars + 14;                  // [2]  16
     uint64_t* p_empty = bars + 16;                 // [2]
-    uint64_t* o_full = bars + 18;                  // completes once per key block, phases counted over the whole item list
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,7 +127,6 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 16);
             mbar_init(&p_full[s], 16); mbar_init(&p_empty[s], 1);
         }
-        mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -140,7 +145,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
             const int qb = item_qb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, nkv = item_nkv(qb);
-            mbar_wait(&q_empty[n & 1], ((n >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&q_empty[n & 1], ((n >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&q_full[n & 1], AT_TILE);
                 tma_load_2d(smem + S::oQ + (n & 1) * AT_TILE, &tmQKV, &q_full[n & 1], h * 64, row_base + qb * AT_BM);
@@ -148,7 +153,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             __syncwarp();
             for (int j = 0; j < nkv; ++j, ++kvc) {
                 const int st = kvc % S::kKvStages; const uint32_t ph = (kvc / S::kKvStages) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_wait_relaxed(&kv_empty[st], ph ^ 1);
                 uint8_t* sk = smem + S::oKV + st * 2 * AT_TILE;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
@@ -201,7 +206,9 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         umma_bf16(tO, dP + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), dV + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(o_full);
+                    // one commit serves both "the P buffer is free" and "O holds key block g": the softmax warps wait on p_empty[g & 1] before
+                    // they rescale or read O (a separate barrier for the second meaning completed a phase per key block that nobody waited
+                    // for in most blocks -- legal, but compute-sanitizer synccheck calls it a missing wait; profiles/r2c_sanitizer_synccheck.log)
                     umma_commit(&p_empty[g & 1]);
                     umma_commit(&kv_empty[st]);
                 }
@@ -214,9 +221,12 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         const int r = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * kLog2eF;
-        float* xmax = reinterpret_cast<float*>(smem + S::oXch);               // [buf][qtr][row]
-        float* xsum = xmax + 2 * 4 * 128;                                     // [qtr][row]
-        const uint32_t t32 = drop.thresh16 << 16;
+        const uint32_t xmax = smem_u32(smem + S::oXch);                       // [buf][qtr][row] floats, shared-space address
+        const uint32_t xsum = xmax + 2 * 4 * 128 * 4;                         // [qtr][row]
+        const uint32_t addc = attn_drop_addc(drop.thresh16);
+        uint32_t p_addr[4];                                                   // this thread's four 16-byte chunks of a P tile (buffer 0)
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) p_addr[gg] = tile_chunk_addr(smem_u32(smem + S::oP), r, qtr * 4 + gg);
         uint32_t g = 0;
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
             const int qb = item_qb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
@@ -239,25 +249,23 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
                 if (lane == 0) mbar_arrive(&s_empty[g & 1]);
                 float mx0 = -INFINITY, mx1 = -INFINITY;
                 if (need_mask) {
+                    const int nv = min(qi, T - 1) - kc0 + 1;         // keys kc0 .. kc0 + nv - 1 exist for this query row (causal + sequence end)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int kj = kc0 + i;
-                        if (!(kj <= qi && kj < T)) v[i] = 0xff800000u;
-                    }
+                    for (int i = 0; i < 32; ++i) v[i] = (i < nv) ? v[i] : 0xff800000u;
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
-                xmax[((g & 1) * 4 + qtr) * 128 + r] = fmaxf(mx0, mx1);
-                if (kMode == 0) named_bar_sync(2, 512); else named_bar_sync(2 + quad, 128);
-                const float* xm = xmax + (g & 1) * 4 * 128 + r;
-                const float m_new = fmaxf(fmaxf(fmaxf(xm[0], xm[128]), fmaxf(xm[256], xm[384])), m_used);
+                sts_f32(xmax + (((g & 1) * 4 + qtr) * 128 + r) * 4, fmaxf(mx0, mx1));
+                named_bar_sync(2 + quad, 128);
+                const uint32_t xm = xmax + ((g & 1) * 4 * 128 + r) * 4;
+                const float m_new = fmaxf(fmaxf(fmaxf(lds_f32(xm), lds_f32(xm + 512)), fmaxf(lds_f32(xm + 1024), lds_f32(xm + 1536))), m_used);
                 if (j == 0) {
                     m_used = m_new;
                 } else {
                     const bool grow = (m_new - m_used) * sl2 > 8.f;
                     if (__any_sync(0xffffffffu, grow)) {
                         const float f = grow ? ex2_fast((m_used - m_new) * sl2) : 1.f;
-                        mbar_wait(o_full, (g - 1) & 1);
+                        mbar_wait(&p_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);      // P V of key block g - 1 has completed (see the MMA warp)
                         tc_fence_after();
                         uint32_t o[16];
                         __syncwarp();
@@ -273,102 +281,49 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
                 }
                 const float msc = m_used * sl2;
                 float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-                if (kMode == 1) {
-                    // Two schedules, chosen per warp: odd column quarters hash BEFORE their exponentials, even ones after.  The four warps
-                    // of a sub-partition enter every key block together (row-max barrier), so with a single schedule they would all sit in
-                    // the MUFU-bound phase and then all in the integer phase; split 2 + 2, one pair's IMAD / LOP3 stream issues while the
-                    // other pair occupies the MUFU pipe.  The branches are warp-uniform; the empty volatile asms keep the front end from
-                    // merging or sinking the two copies of the hash (ptxas does not move code across the branches).
-                    const bool hash_first = (qtr & 1) != 0;
+                uint32_t pk[16];
+                // ONE basic block per key block: exponentials (MUFU + FMA pipe), row sums (FMA pipe), the dropout hash (IMAD.WIDE on the FMA
+                // pipe, LOP3 on the ALU pipe) and the keep masks, applied to the PACKED bf16x2 probabilities (add + PRMT + AND per two keys;
+                // common.cuh attn_drop_mask2).  r1n profile of the previous form (fp32 selects: shift + ISETP + SEL per key, a dead VIADD per
+                // multiply, the P-tile addresses recomputed per block): 17.9 warp instructions per probability, ALU pipe (half rate) busiest.
+                // r2c profile of the single-basic-block form: the instruction count halved (17.9 -> 8.9 per probability) but the kernel only
+                // gained 10 %: ptxas emits the 32 exponentials of a block back to back, the four warps of a scheduler reach that phase together
+                // (row-max barrier), so the MUFU pipe (one warp instruction per 8 cycles and scheduler) runs for ~1 000 cycles with the FMA / ALU
+                // pipes idle, then the integer phase runs with the MUFU pipe idle.  The exponent offset of 4-key group i is therefore made to
+                // DEPEND on the packed probabilities of group i - 2 (OR-ing in a word that is zero at run time, thresh16 < 2^16, but not provably
+                // so): two interleaved dependency chains, so at most 8 exponentials can be adjacent and the hash / row-sum / pack / mask work of
+                // the neighbouring groups has to be scheduled between them -- a software pipeline ptxas cannot undo.
+                {
                     const uint32_t g0 = (uint32_t)kc0 >> 2;
-                    uint32_t w[16];
-                    float mscv = msc;
-                    if (hash_first) {
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) attn_drop_words(rk, g0 + i4, w[2 * i4], w[2 * i4 + 1]);
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) asm volatile("" : "+r"(w[e]));
-                        // ptxas hoists the (speculation-safe) exponentials above this block unless they depend on it: OR in a word that is
-                        // zero at run time (thresh16 < 2^16) but not provably so
-                        mscv = __uint_as_float(__float_as_uint(msc) | (w[15] & (drop.thresh16 >> 16)));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) asm volatile("" : "=r"(w[e]));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));        // the exponentials start after the first hash block
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -mscv));
-                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -mscv));
-                        const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -mscv));
-                        const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -mscv));
-                        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                        v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
-                    }
-                    l_run += (rs0 + rs1) + (rs2 + rs3);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
-                    if (!hash_first) {
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) attn_drop_words(rk, g0 + i4, w[2 * i4], w[2 * i4 + 1]);
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) asm volatile("" : "+r"(w[e]));
-                    }
+                    const uint32_t zero = drop.thresh16 >> 16;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const uint32_t w0 = w[2 * i4], w1 = w[2 * i4 + 1];
-                        v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
-                        v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
-                        v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
-                        v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sl2, -msc));
-                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
-                        const float p2 = ex2_fast(fmaf(__uint_as_float(v[i + 2]), sl2, -msc));
-                        const float p3 = ex2_fast(fmaf(__uint_as_float(v[i + 3]), sl2, -msc));
+                        float mo = msc;
+                        if (i4 >= 2) mo = __uint_as_float(__float_as_uint(msc) | (pk[2 * (i4 - 2)] & zero));
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[4 * i4]), sl2, -mo));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[4 * i4 + 1]), sl2, -mo));
+                        const float p2 = ex2_fast(fmaf(__uint_as_float(v[4 * i4 + 2]), sl2, -mo));
+                        const float p3 = ex2_fast(fmaf(__uint_as_float(v[4 * i4 + 3]), sl2, -mo));
                         rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                        v[i] = __float_as_uint(p0); v[i + 1] = __float_as_uint(p1); v[i + 2] = __float_as_uint(p2); v[i + 3] = __float_as_uint(p3);
-                    }
-                    l_run += (rs0 + rs1) + (rs2 + rs3);
-                    if (kMode == 0 && drop.thresh16) {
-                        const uint32_t g0 = (uint32_t)kc0 >> 2;
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
+                        if (kMode == 1) {
                             uint32_t w0, w1;
                             attn_drop_words(rk, g0 + i4, w0, w1);
-                            v[i4 * 4 + 0] = (w0 >= t32) ? v[i4 * 4 + 0] : 0u;
-                            v[i4 * 4 + 1] = ((w0 << 16) >= t32) ? v[i4 * 4 + 1] : 0u;
-                            v[i4 * 4 + 2] = (w1 >= t32) ? v[i4 * 4 + 2] : 0u;
-                            v[i4 * 4 + 3] = ((w1 << 16) >= t32) ? v[i4 * 4 + 3] : 0u;
+                            pk[2 * i4] = pack_bf16(p0, p1) & attn_drop_mask2(w0, addc);
+                            pk[2 * i4 + 1] = pack_bf16(p2, p3) & attn_drop_mask2(w1, addc);
+                        } else {
+                            pk[2 * i4] = pack_bf16(p0, p1);
+                            pk[2 * i4 + 1] = pack_bf16(p2, p3);
                         }
                     }
                 }
-                const uint32_t sP = smem_u32(smem + S::oP + (g & 1) * 2 * AT_TILE);
-                if (kMode == 0) {
-                    mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                l_run += (rs0 + rs1) + (rs2 + rs3);
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg)
-                        st_tile_chunk(sP, r, qtr * 4 + gg,
-                                      make_uint4(pack_bf16(__uint_as_float(v[8 * gg]), __uint_as_float(v[8 * gg + 1])),
-                                                 pack_bf16(__uint_as_float(v[8 * gg + 2]), __uint_as_float(v[8 * gg + 3])),
-                                                 pack_bf16(__uint_as_float(v[8 * gg + 4]), __uint_as_float(v[8 * gg + 5])),
-                                                 pack_bf16(__uint_as_float(v[8 * gg + 6]), __uint_as_float(v[8 * gg + 7]))));
-                } else {
-                    // packed BEFORE the wait and pinned there: otherwise the front end sinks the hash / select / pack chain below the
-                    // wait loop (a block boundary), which is exactly the serial MUFU-phase-then-integer-phase schedule this version removes
-                    uint32_t pk[16];
+                for (int e = 0; e < 16; ++e) asm volatile("" : "+r"(pk[e]));       // packed BEFORE the wait: the chain must not sink below the wait loop
+                mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                {
+                    const uint32_t pb = (g & 1) * 2 * AT_TILE;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        pk[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                        asm volatile("" : "+r"(pk[e]));
-                    }
-                    mbar_wait(&p_empty[g & 1], ((g >> 1) & 1) ^ 1);
-#pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) st_tile_chunk(sP, r, qtr * 4 + gg, make_uint4(pk[4 * gg], pk[4 * gg + 1], pk[4 * gg + 2], pk[4 * gg + 3]));
+                    for (int gg = 0; gg < 4; ++gg) sts_v4(p_addr[gg] + pb, make_uint4(pk[4 * gg], pk[4 * gg + 1], pk[4 * gg + 2], pk[4 * gg + 3]));
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -377,16 +332,16 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             }
             // item epilogue: O / l (dropout's 1/(1-p) folded in), lse.  The next item's first P V (which overwrites O) cannot be issued
             // before every softmax warp has passed this point and arrived on that block's p_full.
-            mbar_wait(o_full, (g - 1) & 1);
+            mbar_wait(&p_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);                  // the item's last P V has completed
             tc_fence_after();
             uint32_t o[16];
             __syncwarp();
             tmem_ld_32x16(tO + lane_off + qtr * 16, o);
             tmem_ld_wait();
             tc_fence_before();
-            xsum[qtr * 128 + r] = l_run;
-            if (kMode == 0) named_bar_sync(2, 512); else named_bar_sync(2 + quad, 128);
-            const float l_tot = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
+            sts_f32(xsum + (qtr * 128 + r) * 4, l_run);
+            named_bar_sync(2 + quad, 128);
+            const float l_tot = (lds_f32(xsum + r * 4) + lds_f32(xsum + (128 + r) * 4)) + (lds_f32(xsum + (256 + r) * 4) + lds_f32(xsum + (384 + r) * 4));
             if (qi < T) {
                 const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;
                 if (qtr == 0) lse_out[(size_t)bh * T + qi] = m_used * scale + logf(l_tot);
@@ -407,6 +362,44 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
+// Softmax-gradient math of one thread's 32 keys of a [128 x 128] block: P (dropout applied) and dS / c as packed bf16x2 words.
+//     pe = exp2(S * scale * log2e - lse2) ; nd = pe * (-delta / c) ; kept key: dS / c = fma(pe, dP, nd) ; dropped key: nd
+// The keep decision is taken on the PACKED words (common.cuh attn_drop_mask2).  kMasked: diagonal / edge blocks, keys >= n_ok do not exist
+// (a separate instantiation: folded into one body the compiler predicates the per-key compare + select into EVERY block, r2c profile).
+// Software pipeline as in the forward kernel: the exponent offset of group i depends on the packed P of group i - 2 through a word that
+// is zero at run time, so the exponentials cannot be batched and the integer / FMA work of the neighbouring groups fills the MUFU shadow.
+template <int kMode, bool kMasked>
+TTTS_DEVICE void bwd_math(const uint32_t (&sv)[32], const uint32_t (&gv)[32], uint32_t (&pp)[16], uint32_t (&dd)[16], float sl2, float lse2, float ndl,
+                          const AttnDropRow rk, uint32_t g0, uint32_t addc, int n_ok, uint32_t zero) {
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        float lo = lse2;
+        if (i4 >= 2) lo = __uint_as_float(__float_as_uint(lse2) | (pp[2 * (i4 - 2)] & zero));
+        float pe[4], nd[4], dk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            pe[e] = ex2_fast(fmaf(__uint_as_float(sv[i4 * 4 + e]), sl2, -lo));
+            if (kMasked) pe[e] = (i4 * 4 + e < n_ok) ? pe[e] : 0.f;
+            nd[e] = pe[e] * ndl;
+            dk[e] = fmaf(pe[e], __uint_as_float(gv[i4 * 4 + e]), nd[e]);
+        }
+        if (kMode == 1) {
+            uint32_t w0, w1;
+            attn_drop_words(rk, g0 + i4, w0, w1);
+            const uint32_t m0 = attn_drop_mask2(w0, addc), m1 = attn_drop_mask2(w1, addc);
+            pp[2 * i4] = pack_bf16(pe[0], pe[1]) & m0;
+            pp[2 * i4 + 1] = pack_bf16(pe[2], pe[3]) & m1;
+            dd[2 * i4] = (pack_bf16(dk[0], dk[1]) & m0) | (pack_bf16(nd[0], nd[1]) & ~m0);
+            dd[2 * i4 + 1] = (pack_bf16(dk[2], dk[3]) & m1) | (pack_bf16(nd[2], nd[3]) & ~m1);
+        } else {
+            pp[2 * i4] = pack_bf16(pe[0], pe[1]);
+            pp[2 * i4 + 1] = pack_bf16(pe[2], pe[3]);
+            dd[2 * i4] = pack_bf16(dk[0], dk[1]);
+            dd[2 * i4 + 1] = pack_bf16(dk[2], dk[3]);
+        }
+    }
+}
+
 // backward, persistent (see the forward above).  Items = (key block, head), heavy (early) key blocks first; K/V double-buffered so the
 // next item's tiles arrive while the current one finishes; S/dP run one query block ahead of the gradient GEMMs across item boundaries.
 struct Bwd4Smem {
@@ -421,7 +414,7 @@ struct Bwd4Smem {
 // kMode as in the forward kernel: 0 = r1e code (run-time dropout branch after the exponentials of each 16-column chunk), 1 / 2 = dropout
 // on / off fixed at compile time with each 4-key group's hash next to its exponentials.
 template <int kMode>
-__global__ void __maxnreg__(96)
+__global__ void __maxnreg__(112)
 attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
                     const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, int BH, float scale,
                     DropCfg drop) {
@@ -481,7 +474,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         for (int n = 0, idx; (idx = item_at(n)) >= 0; ++n) {
             const int jb = item_jb(idx), bh = item_bh(idx), b = (int)fastdiv((uint32_t)bh, fd_H), h = bh - b * H;
             const int row_base = b * T, k0 = jb * AT_BN, nit = nq - jb;
-            mbar_wait(&kv_empty[n & 1], ((n >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&kv_empty[n & 1], ((n >> 1) & 1) ^ 1);
             uint8_t* sk = smem + S::oKV + (n & 1) * 2 * AT_TILE;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&kv_full[n & 1], 2 * AT_TILE);
@@ -491,7 +484,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             __syncwarp();
             for (int it = 0; it < nit; ++it, ++c) {
                 const int st = c & 1, i = jb + it;
-                mbar_wait(&qdo_empty[st], ((c >> 1) & 1) ^ 1);
+                mbar_wait_relaxed(&qdo_empty[st], ((c >> 1) & 1) ^ 1);
                 uint8_t* sq = smem + S::oQdO + st * 2 * AT_TILE;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&qdo_full[st], 2 * AT_TILE);
@@ -570,7 +563,12 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * kLog2eF;
         const uint32_t sP = smem_u32(smem + S::oP), sDS = smem_u32(smem + S::oDS);
-        const uint32_t t32 = drop.thresh16 << 16;
+        const uint32_t addc = attn_drop_addc(drop.thresh16);
+        const float inv_c = 1.0f / drop.scale;                // drop.scale = 1 without dropout
+        const float out_scale = scale * drop.scale;           // dK (and dQ, in attn_dq_convert) carry the factor c the math warps leave out
+        uint32_t t_off[4];                                    // this thread's four 16-byte chunks inside a [128 x 128] bf16 operand buffer
+#pragma unroll
+        for (int g = 0; g < 4; ++g) t_off[g] = tile_chunk_addr(0u, r, qtr * 4 + g);
 
         // dQ tile of global iteration cc -> fp32 accumulator rows starting at dst (nullptr: row beyond T)
         auto dq_out = [&](uint32_t cc, float* dst) {
@@ -611,10 +609,10 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     reinterpret_cast<uint4*>(dkp)[g] =
-                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * scale, __uint_as_float(a[8 * g + 1]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * scale, __uint_as_float(a[8 * g + 3]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * scale, __uint_as_float(a[8 * g + 5]) * scale),
-                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * scale, __uint_as_float(a[8 * g + 7]) * scale));
+                        make_uint4(pack_bf16(__uint_as_float(a[8 * g]) * out_scale, __uint_as_float(a[8 * g + 1]) * out_scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 2]) * out_scale, __uint_as_float(a[8 * g + 3]) * out_scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 4]) * out_scale, __uint_as_float(a[8 * g + 5]) * out_scale),
+                                   pack_bf16(__uint_as_float(a[8 * g + 6]) * out_scale, __uint_as_float(a[8 * g + 7]) * out_scale));
                     reinterpret_cast<uint4*>(dvp)[g] =
                         make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * drop.scale, __uint_as_float(v[8 * g + 1]) * drop.scale),
                                    pack_bf16(__uint_as_float(v[8 * g + 2]) * drop.scale, __uint_as_float(v[8 * g + 3]) * drop.scale),
@@ -627,7 +625,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         // last gradient MMAs to have completed -- to after the FIRST block of the next item has been handed to the MMA warp: the wait
         // that was exposed once per item (r1h / r1n profiles: 6.6 % of all stall samples on that one try_wait) now overlaps a whole
         // block of softmax-gradient math.  The MMA warp's dkv_empty wait before the next item's first gradient MMA is unchanged.
-        constexpr bool kDefer = kMode != 0;
+        constexpr bool kDefer = true;
         float* prev_dst = nullptr;
         int idx_prev = -1;
         float lse_nx = 0.f, dlt_nx = 0.f;
@@ -664,91 +662,33 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 uint32_t pp[16], dd[16];
                 mbar_wait(sdp_full, ph);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t sv[16], gv[16];
+                // The gradient in the scaling that costs two FMA-pipe operations per element:
+                //     dS / c = P o (mask o dP - delta / c)       (c = dropout scale 1 / (1 - p); the factor c is applied to dK and dQ on the way out)
+                //     nd = pe * (-delta / c) ;  kept key: fma(pe, dP, nd) ;  dropped key: nd
+                // and the keep decision is taken on the PACKED bf16x2 words: P &= mask, dS = select(mask, pack(kept), pack(dropped)) -- two
+                // 16-bit lanes per LOP3 (common.cuh attn_drop_mask2) instead of shift + ISETP + 2 SEL per key on fp32 values.
+                const float ndl = -dlt * inv_c;
+                {
+                    // S and dP of the thread's 32 keys in one go: the accumulators are handed back to the MMA warp (which issues the next
+                    // block's S / dP into them) before the math starts, not half-way through it
+                    uint32_t sv[32], gv[32];
                     __syncwarp();
-                    tmem_ld_32x16(tS + lane_off + qtr * 32 + cc * 16, sv);
-                    tmem_ld_32x16(tDP + lane_off + qtr * 32 + cc * 16, gv);
+                    tmem_ld_32x32(tS + lane_off + qtr * 32, sv);
+                    tmem_ld_32x32(tDP + lane_off + qtr * 32, gv);
                     tmem_ld_wait();
-                    if (cc == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(sdp_empty);
-                    }
-                    float p[16];
-                    float ds[16];
-                    if (kMode == 1) {
-                        // per 4-key group: hash, exponentials, gradient -- one basic block per mask variant, integer work under the MUFU latency
-                        const uint32_t g0 = (uint32_t)(kc0 + cc * 16) >> 2;
-                        if (need_mask) {
-#pragma unroll
-                            for (int e4 = 0; e4 < 4; ++e4) {
-                                uint32_t w0, w1;
-                                attn_drop_words(rk, g0 + e4, w0, w1);
-                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int kj = kc0 + cc * 16 + e4 * 4 + e;
-                                    const float pe = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e4 * 4 + e]), sl2, -lse2)) : 0.f;
-                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                                    ds[e4 * 4 + e] = pe * (k4[e] ? u : -dlt);
-                                    p[e4 * 4 + e] = k4[e] ? pe : 0.f;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int e4 = 0; e4 < 4; ++e4) {
-                                uint32_t w0, w1;
-                                attn_drop_words(rk, g0 + e4, w0, w1);
-                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float pe = ex2_fast(fmaf(__uint_as_float(sv[e4 * 4 + e]), sl2, -lse2));
-                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                                    ds[e4 * 4 + e] = pe * (k4[e] ? u : -dlt);
-                                    p[e4 * 4 + e] = k4[e] ? pe : 0.f;
-                                }
-                            }
-                        }
-                    } else {
-                        if (need_mask) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                const int kj = kc0 + cc * 16 + e;
-                                p[e] = (q_ok && kj <= qi && kj < T) ? ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2)) : 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) p[e] = ex2_fast(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
-                        }
-                        if (kMode == 0 && drop.thresh16) {
-                            const uint32_t g0 = (uint32_t)(kc0 + cc * 16) >> 2;
-#pragma unroll
-                            for (int e4 = 0; e4 < 4; ++e4) {
-                                uint32_t w0, w1;
-                                attn_drop_words(rk, g0 + e4, w0, w1);
-                                const bool k4[4] = {w0 >= t32, (w0 << 16) >= t32, w1 >= t32, (w1 << 16) >= t32};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float u = fmaf(__uint_as_float(gv[e4 * 4 + e]), drop.scale, -dlt);
-                                    ds[e4 * 4 + e] = p[e4 * 4 + e] * (k4[e] ? u : -dlt);
-                                    p[e4 * 4 + e] = k4[e] ? p[e4 * 4 + e] : 0.f;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) ds[e] = p[e] * (__uint_as_float(gv[e]) - dlt);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { pp[cc * 8 + e] = pack_bf16(p[2 * e], p[2 * e + 1]); dd[cc * 8 + e] = pack_bf16(ds[2 * e], ds[2 * e + 1]); }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sdp_empty);
+                    // keys of this block that exist for this query row (causal + sequence end); only consulted on diagonal / edge blocks
+                    const int n_ok = q_ok ? min(qi, T - 1) - kc0 + 1 : 0;
+                    if (need_mask) bwd_math<kMode, true>(sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, n_ok, drop.thresh16 >> 16);
+                    else bwd_math<kMode, false>(sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, 32, drop.thresh16 >> 16);
                 }
                 mbar_wait(pds_empty, ph ^ 1);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    st_tile_chunk(sP, r, qtr * 4 + g, make_uint4(pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]));
-                    st_tile_chunk(sDS, r, qtr * 4 + g, make_uint4(dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]));
+                    sts_v4(sP + t_off[g], make_uint4(pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]));
+                    sts_v4(sDS + t_off[g], make_uint4(dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]));
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -792,14 +732,6 @@ bool attn_use_tc() {
     return !legacy;
 }
 
-// TTTS_ATTN_VER=4 selects the r1e/r1h flavour of the persistent kernels (run-time dropout branch, 512-thread row-max barrier, exposed item
-// tails) for A/B measurements; default 5
-static int attn_tc_version() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("TTTS_ATTN_VER"); v = (e && e[0] == '4') ? 4 : 5; }
-    return v;
-}
-
 int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropCfg drop, cudaStream_t st) {
     const int d = H * 64;
     CUtensorMap tm;
@@ -807,7 +739,6 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
     if (rc) return rc;
     static bool attr4 = false;
     if (!attr4) {
-        TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
         TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
         TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
         attr4 = true;
@@ -816,8 +747,7 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
     const int items = nq * B * H;
     const int nblk = items < num_sms() ? items : num_sms();
     TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nq <= 4096, "attention: too many (block, head) items");
-    if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
-    else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
     else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
     return TTTS_OK;
@@ -840,7 +770,6 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
     if (rc) return rc;
     static bool attr4 = false;
     if (!attr4) {
-        TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
         TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
         TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
         attr4 = true;
@@ -849,14 +778,13 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
     const int items = nkb * B * H;
     const int nblk = items < num_sms() ? items : num_sms();
     TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nkb <= 4096, "attention: too many (block, head) items");
-    if (attn_tc_version() == 4) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<0>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
-    else if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
     else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_bwd_tc");
     const size_t n4 = (size_t)B * T * d / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    TTTS_CUDA(launch_pdl(attn_dq_convert_kernel, dim3(blocks), dim3(256), 0, st, dq_acc, dqkv, (size_t)B * T, d, 0.125f));     // dQ = scale * dS K
+    TTTS_CUDA(launch_pdl(attn_dq_convert_kernel, dim3(blocks), dim3(256), 0, st, dq_acc, dqkv, (size_t)B * T, d, 0.125f * drop.scale));     // dQ = scale * c * (dS / c) K
     TTTS_LAUNCH_CHECK("attn_dq_convert");
     return TTTS_OK;
 }

@@ -113,7 +113,15 @@ TTTS_DEVICE bool dropout_keep(uint64_t bits, int j, uint32_t thresh16) {
 
 // Attention-probability dropout (B*H*T*T decisions per layer: the hash must cost ~2 instructions per element, not ~5 like mix64).
 // Row key = mix64(seed, b*h*T + query) once per row; then per group of 4 consecutive keys three rounds of a 32x32->64 multiply-fold
-// (one IMAD.WIDE + one LOP3 each) give two 32-bit words = four 16-bit uniform fields.  keep <=> field >= thresh16.
+// (one IMAD.WIDE + one LOP3 each) give two 32-bit words = four 15-bit uniform fields (bits 0-14 and 16-30 of each word; bits 15 / 31
+// are cleared by the same LOP3 that folds the last round):
+//     key 4g + 0 -> w0 bits 0-14     key 4g + 1 -> w0 bits 16-30     key 4g + 2 -> w1 bits 0-14     key 4g + 3 -> w1 bits 16-30
+//     keep <=> field >= t15,  t15 = thresh16 >> 1  (the host rounds p to a multiple of 2^-15, thresh16 is even)
+// Round 2 layout (r2c): the 15-bit fields exist so that BOTH decisions of a word come out of one add -- field + (0x8000 - t15) carries
+// into bit 15 / 31 exactly when the key is kept, no carry crosses a field -- and one PRMT with sign replication turns the two flag bits
+// into a 0xFFFF / 0x0000 mask per half-word, which is ANDed onto the packed bf16x2 probabilities: 3 ALU instructions per 2 keys instead
+// of 2 x (shift, ISETP, SEL) on fp32 values.  The r1 profiles had the attention math warps bound by the ALU pipe (half rate on sm_100).
+// mul.wide.u32 in PTX: written as (uint64_t)a * b the compiler adds a dead `+ 0` to every high word (one VIADD per product).
 // Statistical checks (keep rate, key/row/diagonal correlations, 2-D spectrum) are in tests/test_oracle_golden.py::test_attn_dropout_hash.
 struct AttnDropRow { uint32_t k0, k1; };
 TTTS_DEVICE AttnDropRow attn_drop_row(uint64_t seed, uint64_t row) {
@@ -121,20 +129,41 @@ TTTS_DEVICE AttnDropRow attn_drop_row(uint64_t seed, uint64_t row) {
     AttnDropRow k; k.k0 = (uint32_t)z; k.k1 = (uint32_t)(z >> 32);
     return k;
 }
+TTTS_DEVICE void mul_wide_u32(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+#ifdef TTTS_HOST_EMU
+    const uint64_t m = (uint64_t)a * b; lo = (uint32_t)m; hi = (uint32_t)(m >> 32);
+#else
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#endif
+}
 TTTS_DEVICE void attn_drop_words(const AttnDropRow k, uint32_t g, uint32_t& w0, uint32_t& w1) {
     const uint32_t a = g * 0x9E3779B1u + k.k0;
-    const uint64_t m1 = (uint64_t)a * 0x85EBCA6Bu;
-    const uint32_t x = (uint32_t)m1 ^ (uint32_t)(m1 >> 32) ^ k.k1;
-    const uint64_t m2 = (uint64_t)x * 0xC2B2AE35u;
-    const uint32_t y = (uint32_t)m2 ^ (uint32_t)(m2 >> 32);
-    const uint64_t m3 = (uint64_t)y * 0x27D4EB2Fu;
-    w0 = (uint32_t)(m3 >> 32) ^ (uint32_t)m2;
-    w1 = (uint32_t)m3 ^ (uint32_t)(m2 >> 32);
+    uint32_t l1, h1, l2, h2, l3, h3;
+    mul_wide_u32(a, 0x85EBCA6Bu, l1, h1);
+    const uint32_t x = l1 ^ h1 ^ k.k1;
+    mul_wide_u32(x, 0xC2B2AE35u, l2, h2);
+    const uint32_t y = l2 ^ h2;
+    mul_wide_u32(y, 0x27D4EB2Fu, l3, h3);
+    w0 = (h3 ^ l2) & 0x7FFF7FFFu;
+    w1 = (l3 ^ h2) & 0x7FFF7FFFu;
 }
-// keep decisions of keys 4g .. 4g+3 against t32 = thresh16 << 16 (fields: w0 hi, w0 lo, w1 hi, w1 lo)
+// add constant for attn_drop_mask2: both 15-bit fields of a word + (0x8000 - t15) set bit 15 / 31 <=> kept
+TTTS_DEVICE uint32_t attn_drop_addc(uint32_t thresh16) { return (0x8000u - (thresh16 >> 1)) * 0x00010001u; }
+// 0xFFFF in the low / high half-word where the word's low / high key is kept: AND it onto pack_bf16(p[2j], p[2j + 1])
+TTTS_DEVICE uint32_t attn_drop_mask2(uint32_t w, uint32_t addc) {
+#ifdef TTTS_HOST_EMU
+    const uint32_t z = w + addc;
+    return ((z & 0x8000u) ? 0xFFFFu : 0u) | ((z & 0x80000000u) ? 0xFFFF0000u : 0u);
+#else
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(m) : "r"(w + addc), "r"(0u));     // bytes 0,1 <- sign of byte 1 ; bytes 2,3 <- sign of byte 3
+    return m;
+#endif
+}
+// keep decision of key 4g + j (j = 0..3) from the group's words; t32 = thresh16 << 16 (generic form: legacy kernels, mask dump)
 TTTS_DEVICE bool attn_drop_keep(uint32_t w0, uint32_t w1, int j, uint32_t t32) {
     const uint32_t w = (j & 2) ? w1 : w0;
-    return ((j & 1) ? (w << 16) : w) >= t32;
+    return (((j & 1) ? (w >> 16) : w) & 0x7FFFu) >= (t32 >> 17);
 }
 // slow generic form (legacy kernels, mask dump): one element
 TTTS_DEVICE bool attn_drop_keep1(uint64_t seed, uint64_t row, int kj, uint32_t thresh16) {
@@ -176,6 +205,24 @@ TTTS_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {          // try_wait itself suspends the thread for a HW-defined window
+        if ((++spins & 0x3ffu) == 0) {
+            const uint64_t t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) { asm volatile("trap;"); }
+        }
+    }
+}
+
+// the same wait for a warp that is far ahead of its consumers (TMA producers waiting for a free stage): sleeps between polls so that its
+// spin loop does not take issue slots from the math warps of its scheduler (r1n attention profile: 15 % of all stall samples sat on the
+// branches of such loops)
+TTTS_DEVICE void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+#ifndef TTTS_HOST_EMU
+        __nanosleep(100);
+#endif
         if ((++spins & 0x3ffu) == 0) {
             const uint64_t t = global_timer_ns();
             if (t0 == 0) t0 = t;

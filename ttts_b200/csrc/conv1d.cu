@@ -17,10 +17,6 @@
 
 namespace ttts {
 
-// conv1d_tc.cu (experimental, off unless TTTS_CONV_TC=1): returns -1 when it does not take the layer
-int conv1d_tc_try(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int stride, int dil, int pad,
-                  int pre_lrelu, const float* resid, float out_scale, int accumulate, const float* mask, int post, int force, cudaStream_t st);
-
 // conv1d_split.cu (off unless TTTS_CONV_SPLIT=1 or forced by ttts_conv1d_f32_split): split-reduction form of the <32> pipelined kernel
 int conv1d_split_try(const ConvParams& p, dim3 grid, int force_groups, cudaStream_t st);
 
@@ -684,8 +680,6 @@ static int conv1d_run(const float* x, const float* w, const float* bias, float* 
         return conv1d_split_try(p, grid, force_split, st);
     }
     if (!use_v1) {
-        const int rc_tc = conv1d_tc_try(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, 0, st);
-        if (rc_tc >= 0) return rc_tc;                              // experimental tensor-core path, only with TTTS_CONV_TC=1 (conv1d_tc.cu)
         const int rc_direct = conv1d_direct_try(p, st);
         if (rc_direct >= 0) return rc_direct;
         const long long Ptot = (long long)B * Tout;
@@ -739,15 +733,6 @@ int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, flo
                           const float* mask, int32_t post, const float* cond, int32_t cond_ld, int32_t groups, void* stream) {
     return conv1d_run(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld,
                       groups, (cudaStream_t)stream);
-}
-
-int ttts_conv1d_tc(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t C, int32_t T, int32_t K, int32_t dil,
-                   int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, void* stream) {
-    TTTS_CHECK_ARG(x && w && y && B > 0 && T > 0, "conv1d_tc: bad arguments");
-    const int rc = conv1d_tc_try(x, w, bias, y, B, C, T, C, K, 1, dil, dil * (K - 1) / 2, pre_lrelu, resid, out_scale, accumulate, nullptr, 0, 1,
-                                 (cudaStream_t)stream);
-    TTTS_CHECK_ARG(rc >= 0, "conv1d_tc: layer not covered (C in {32, 64}, K in {3, 7, 11}, dil in {1, 3, 5}, T >= 128)");
-    return rc;
 }
 
 int ttts_weight_norm(const float* v, const float* g, float* w, int32_t Cout, int32_t n_per_out, void* stream) {

@@ -1,0 +1,302 @@
+// Stride-1 "same" Conv1d of the VQ-VAE encoder (ResBlock1 / WN layers: 32 ... 192 channels, kernel 1 ... 11, dilation 1 / 3 / 5;
+// ttts/vqvae/modules.py:136-318) on the 5th-gen tensor cores with SPLIT bf16 operands and NO im2col:
+//
+//     x = xh + xl, w = wh + wl   (xh = bf16(x), xl = bf16(x - xh))        y ~= xh wh + xh wl + xl wh     (fp32 accumulation in TMEM)
+//
+// which keeps the whole encoder within ~1.5e-5 of the fp32 reference and all golden codes (tools/split_bf16_conv_study.py).
+//
+// The first tensor-core draft (conv1d_tc.cu, round 1, measured in round 2: 8.9 ms per 64-clip encode against 7.9 ms for the fp32
+// kernels) rebuilt an im2col tile [128 t][64 (tap, ci)] per k-block in shared memory, so every input sample was converted, split and
+// stored K times by 128 threads with one CTA per SM: the transform, not the MMAs, bounded it.  Here a convolution tap is a ROW SHIFT:
+//
+//   * the CTA stages its input window ONCE, channel-last: Xs[row][ci] (hi and lo copies), row = position in a packed row space, 64
+//     channels = 128 bytes per row = one SWIZZLE_128B atom column (Cin > 64: several atoms side by side).  Tap k of the convolution
+//     reads rows [k dil, k dil + 128) of that window: the A operand of tap k is the SAME tile with its start address advanced by
+//     k dil rows (128 B each); the UMMA descriptor carries the swizzle phase of the unaligned start in its base-offset field.
+//   * the weights are pre-split ONCE per layer into [tap][ci atom][hi | lo][co][64 ci] bf16 (conv_tcs_prep_weights) and streamed by
+//     TMA, 128B-swizzled, as K-major B operands [NT co][64 ci] through a ring of stages;
+//   * D[128 rows][NT co] accumulates over taps x ci atoms x 4 k-steps x 3 products in TMEM; epilogue: one row (= one output frame)
+//     per thread, + bias, + residual, * scale, (* mask), coalesced along t.
+//
+// Packed row space: clip b occupies rows [b P, b P + T), P = T + pad; the `pad` rows between clips are zero in the window, so no tap
+// ever reads a neighbouring clip and short clips (T = 36 frames at the deep levels) still fill 128-row MMA tiles.
+#include <stdlib.h>
+#include "common.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace ttts {
+
+constexpr int TCS_ATOM_ROWS = 184;                       // 128 + 2 * 25 (kernel 11, dilation 5) rounded up to 8 rows
+constexpr int TCS_ATOM_BYTES = TCS_ATOM_ROWS * 128;      // one [rows x 64 bf16] atom column
+constexpr int TCS_STAGES = 3;
+constexpr int TCS_THREADS = 192;                         // warps 0-3: transform + epilogue (TMEM lane quadrant = warp), 4: MMA, 5: TMA
+
+struct ConvTcsParams {
+    const float* x; const float* bias; float* y; const float* resid; const float* mask;
+    int B, Cin, Cout, T, K, dil, pad;
+    int P;                 // row pitch of a clip in the packed row space = T + pad
+    int rows;              // B * P
+    int A;                 // ci atoms = ceil(Cin / 64)
+    int NT;                // output channels per CTA
+    int wrows;             // window rows = 128 + 2 * pad
+    int pre_lrelu, accumulate, base_off;
+    float out_scale;
+    uint32_t p_magic;      // ceil(2^32 / P)
+};
+
+TTTS_DEVICE uint64_t tcs_desc(uint32_t saddr, int base_off) {
+    uint64_t d = make_smem_desc_sw128(saddr, 16, 1024);
+    if (base_off) d |= (uint64_t)((saddr >> 7) & 7u) << 49;         // swizzle phase of a start address that is not 1024-byte aligned
+    return d;
+}
+
+struct TcsSmem {
+    static constexpr int oBar = 0;                                    // mbarriers + tmem holder (256 B)
+    static constexpr int oX = 1024;                                   // [hi | lo][A atoms][184 rows][128 B]
+    static size_t x_bytes(int A) { return (size_t)2 * A * TCS_ATOM_BYTES; }
+    static size_t w_stage_bytes(int NT) { return (size_t)2 * NT * 128; }
+    static size_t total(int A, int NT) { return 1024 + x_bytes(A) + TCS_STAGES * w_stage_bytes(NT) + 1024; }
+};
+
+__global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_constant__ CUtensorMap tmW, const ConvTcsParams p) {
+    extern __shared__ uint8_t tcs_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcs_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcsSmem::oBar);
+    uint64_t* w_full = bars;                       // [STAGES] TMA bytes landed
+    uint64_t* w_empty = bars + TCS_STAGES;         // [STAGES] tcgen05.commit: the MMAs that read the stage are done
+    uint64_t* x_full = bars + 2 * TCS_STAGES;      // 4 arrivals: the window is staged
+    uint64_t* acc_full = bars + 2 * TCS_STAGES + 1;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TCS_STAGES + 2);
+    const uint32_t sX = smem_u32(smem + TcsSmem::oX);
+    const uint32_t sXlo = sX + p.A * TCS_ATOM_BYTES;
+    const uint32_t sW = sX + 2 * p.A * TCS_ATOM_BYTES;
+    const uint32_t w_stage = 2 * p.NT * 128;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g0 = blockIdx.x * 128;               // first packed output row of this tile
+    const int n0 = blockIdx.y * p.NT;              // first output channel
+    const int tmem_cols = p.NT <= 32 ? 32 : (p.NT <= 64 ? 64 : 128);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < TCS_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(x_full, 4);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_holder, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const int n_kb = p.K * p.A;                    // weight tiles: (tap, ci atom)
+
+    if (warp == 5) {
+        // ---------------- TMA: weight tiles [NT co][64 ci], hi then lo, one stage per (tap, atom) ----------------
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % TCS_STAGES;
+            mbar_wait(&w_empty[s], ((kb / TCS_STAGES) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&w_full[s], w_stage);
+                uint8_t* dst = smem + TcsSmem::oX + (size_t)2 * p.A * TCS_ATOM_BYTES + (size_t)s * w_stage;
+                tma_load_2d(dst, &tmW, &w_full[s], 0, (kb * 2 + 0) * p.Cout + n0);
+                tma_load_2d(dst + p.NT * 128, &tmW, &w_full[s], 0, (kb * 2 + 1) * p.Cout + n0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = make_idesc_bf16(128, p.NT, false, false);
+        mbar_wait(x_full, 0);
+        tc_fence_after();
+        uint32_t first = 1;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % TCS_STAGES;
+            const int k = kb / p.A, a = kb - k * p.A;
+            mbar_wait(&w_full[s], (kb / TCS_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t row_off = (uint32_t)(k * p.dil) * 128u;          // tap k = the window shifted by k * dil rows
+            const uint32_t aHi = sX + a * TCS_ATOM_BYTES + row_off, aLo = sXlo + a * TCS_ATOM_BYTES + row_off;
+            const uint32_t bHi = sW + s * w_stage, bLo = bHi + p.NT * 128;
+            const int ksteps = min(4, (p.Cin - a * 64 + 15) / 16);
+            if (elect_one()) {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t dAh = tcs_desc(aHi + ks * 32, p.base_off), dAl = tcs_desc(aLo + ks * 32, p.base_off);
+                    const uint64_t dBh = make_smem_desc_sw128(bHi + ks * 32, 16, 1024), dBl = make_smem_desc_sw128(bLo + ks * 32, 16, 1024);
+                    umma_bf16(tmem_base, dAh, dBh, idesc, first ? 0u : 1u);
+                    umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
+                    umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+                    first = 0;
+                }
+                umma_commit(&w_empty[s]);
+                if (kb == n_kb - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- workers: stage the window (channel-last, hi / lo), then the epilogue ----------------
+        const int tid = threadIdx.x;                                         // 0 .. 127
+        const int cgroups = p.A * 8;                                         // 16-byte chunks (8 channels) per row over all atoms
+        for (int jb = 0; jb < p.wrows; jb += 128) {
+            const int j = jb + tid;                                          // window row
+            const int gi = g0 - p.pad + j;                                   // packed input row
+            bool row_ok = (j < p.wrows) && gi >= 0 && gi < p.rows;
+            int b = 0, t = 0;
+            if (row_ok) { b = (int)__umulhi((uint32_t)gi, p.p_magic); if (p.P == 1) b = gi; t = gi - b * p.P; row_ok = t < p.T; }
+            if (j < TCS_ATOM_ROWS) {
+                const float* xp = p.x + ((size_t)b * p.Cin) * p.T + t;
+                // two 8-channel groups per iteration: 16 independent loads in flight per thread (the loads of a group are coalesced across
+                // the warp: consecutive lanes = consecutive frames of one channel)
+                for (int cg = 0; cg < cgroups; cg += 2) {
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int ci = cg * 8 + e;
+                        v[e] = (row_ok && ci < p.Cin) ? __ldg(xp + (size_t)ci * p.T) : 0.f;
+                    }
+                    if (p.pre_lrelu) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
+                    }
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float h0 = bf16_round(v[h2 * 8 + 2 * e]), h1 = bf16_round(v[h2 * 8 + 2 * e + 1]);
+                            hi[e] = pack_bf16(h0, h1);
+                            lo[e] = pack_bf16(v[h2 * 8 + 2 * e] - h0, v[h2 * 8 + 2 * e + 1] - h1);
+                        }
+                        const int c = cg + h2;
+                        const uint32_t off = (uint32_t)(c >> 3) * TCS_ATOM_BYTES + (uint32_t)j * 128u + ((uint32_t)((c ^ j) & 7) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+                    }
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_full);
+
+        // epilogue: thread = packed output row g0 + tid = TMEM lane
+        const int g = g0 + tid;
+        bool ok = g < p.rows;
+        int b = 0, t = 0;
+        if (ok) { b = (int)__umulhi((uint32_t)g, p.p_magic); if (p.P == 1) b = g; t = g - b * p.P; ok = t < p.T; }
+        const float mk = (ok && p.mask) ? p.mask[(size_t)b * p.T + t] : 1.f;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+            uint32_t r[16];
+            __syncwarp();
+            tmem_ld_32x16(tmem_base + lane_off + c0, r);
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int co = n0 + c0 + i;
+                    if (co < p.Cout) {
+                        float v = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co) : 0.f);
+                        const size_t o = ((size_t)b * p.Cout + co) * p.T + t;
+                        if (p.resid) v += p.resid[o];
+                        v *= p.out_scale * mk;
+                        p.y[o] = p.accumulate ? p.y[o] + v : v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// w [Cout][Cin][K] fp32  ->  ws [K][A][hi | lo][Cout][64] bf16 (ci >= Cin: zero)
+__global__ void conv_tcs_prep_weights_kernel(const float* __restrict__ w, bf16* __restrict__ ws, int Cout, int Cin, int K, int A) {
+    const size_t n = (size_t)K * A * Cout * 64;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i & 63);
+        const size_t r = i >> 6;
+        const int co = (int)(r % Cout);
+        const int ka = (int)(r / Cout);
+        const int a = ka % A, k = ka / A;
+        const int ci = a * 64 + cc;
+        const float v = ci < Cin ? w[((size_t)co * Cin + ci) * K + k] : 0.f;
+        const float h = bf16_round(v);
+        ws[(((size_t)ka * 2 + 0) * Cout + co) * 64 + cc] = __float2bfloat16_rn(h);
+        ws[(((size_t)ka * 2 + 1) * Cout + co) * 64 + cc] = __float2bfloat16_rn(v - h);
+    }
+}
+
+int64_t conv_tcs_weight_elems(int Cout, int Cin, int K) { return (int64_t)K * ((Cin + 63) / 64) * 2 * Cout * 64; }
+
+int conv_tcs_prep_weights(const float* w, void* ws, int Cout, int Cin, int K, cudaStream_t st) {
+    TTTS_CHECK_ARG(w && ws && Cout > 0 && Cin > 0 && K > 0, "conv_tcs_prep_weights: bad arguments");
+    const int A = (Cin + 63) / 64;
+    const size_t n = (size_t)K * A * Cout * 64;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    conv_tcs_prep_weights_kernel<<<blocks, 256, 0, st>>>(w, (bf16*)ws, Cout, Cin, K, A);
+    TTTS_LAUNCH_CHECK("conv_tcs_prep_weights");
+    return TTTS_OK;
+}
+
+bool conv_tcs_covers(int Cin, int Cout, int K, int stride, int dil, int pad, int post) {
+    if (stride != 1 || post != 0 || K < 1 || dil < 1) return false;
+    if (pad * 2 != dil * (K - 1) || 128 + 2 * pad > TCS_ATOM_ROWS) return false;
+    if (Cin % 8 != 0 || Cin < 16 || Cin > 192) return false;
+    if (!(Cout == 32 || Cout == 64 || Cout == 96 || Cout == 128 || Cout == 192 || Cout == 384)) return false;
+    return true;
+}
+
+int conv1d_tcs(const float* x, const void* ws, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int dil, int pre_lrelu,
+               const float* resid, float out_scale, int accumulate, const float* mask, int base_off, cudaStream_t st) {
+    const int pad = dil * (K - 1) / 2;
+    TTTS_CHECK_ARG(x && ws && y && B > 0 && T > 0, "conv1d_tcs: bad arguments");
+    TTTS_CHECK_ARG(conv_tcs_covers(Cin, Cout, K, 1, dil, pad, 0), "conv1d_tcs: layer not covered (stride 1, same padding, Cin %% 8 == 0, Cin <= 192, Cout in {32, 64, 96, 128, 192, 384})");
+    ConvTcsParams p = {};
+    p.x = x; p.bias = bias; p.y = y; p.resid = resid; p.mask = mask;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = K; p.dil = dil; p.pad = pad;
+    p.P = T + pad;
+    TTTS_CHECK_ARG((long long)B * p.P < (1ll << 31), "conv1d_tcs: problem too large");
+    p.rows = B * p.P;
+    p.A = (Cin + 63) / 64;
+    p.NT = Cout <= 128 ? Cout : 96;
+    p.wrows = 128 + 2 * pad;
+    p.pre_lrelu = pre_lrelu; p.accumulate = accumulate; p.base_off = base_off; p.out_scale = out_scale;
+    p.p_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.P - 1) / (uint64_t)p.P);
+    CUtensorMap tm;
+    const uint64_t wrows = (uint64_t)K * p.A * 2 * Cout;
+    int rc = make_tmap_2d(&tm, ws, 2, 64, wrows, 64, 64, (uint32_t)p.NT, 1);
+    if (rc) return rc;
+    const size_t smem = TcsSmem::total(p.A, p.NT);
+    static size_t attr = 0;
+    if (smem > attr) {
+        TTTS_CUDA(cudaFuncSetAttribute(conv1d_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        attr = 227 * 1024;
+    }
+    TTTS_CHECK_ARG(smem <= 227 * 1024, "conv1d_tcs: shared memory");
+    dim3 grid((p.rows + 127) / 128, Cout / p.NT);
+    conv1d_tcs_kernel<<<grid, TCS_THREADS, smem, st>>>(tm, p);
+    TTTS_LAUNCH_CHECK("conv1d_tcs");
+    return TTTS_OK;
+}
+
+}  // namespace ttts
+
+extern "C" {
+int64_t ttts_conv1d_tcs_weight_elems(int32_t Cout, int32_t Cin, int32_t K) { return ttts::conv_tcs_weight_elems(Cout, Cin, K); }
+int ttts_conv1d_tcs_prep_weights(const float* w, void* ws_bf16, int32_t Cout, int32_t Cin, int32_t K, void* stream) {
+    return ttts::conv_tcs_prep_weights(w, ws_bf16, Cout, Cin, K, (cudaStream_t)stream);
+}
+int ttts_conv1d_tcs(const float* x, const void* ws_bf16, const float* bias, float* y, int32_t B, int32_t Cin, int32_t T, int32_t Cout, int32_t K,
+                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t flags,
+                    void* stream) {
+    return ttts::conv1d_tcs(x, ws_bf16, bias, y, B, Cin, T, Cout, K, dil, pre_lrelu, resid, out_scale, accumulate, mask, (flags & 1) ? 0 : 1,
+                            (cudaStream_t)stream);
+}
+}

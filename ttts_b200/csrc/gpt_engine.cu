@@ -87,7 +87,7 @@ static Workspace carve(const ttts_gpt_config& c, int B, int TL, int CL, bool sav
 static inline DropCfg site_drop(float p, uint64_t seed, int site, int layer) {
     DropCfg dc = no_drop();
     if (p > 0.f) {
-        dc.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+        dc.thresh16 = 2u * (uint32_t)(p * 32768.0f + 0.5f);         // p as a multiple of 2^-15 (the attention hash decides on 15-bit fields)
         dc.scale = 1.0f / (1.0f - (float)dc.thresh16 / 65536.0f);
         uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site * 1024 + layer + 1);
         z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ULL; z ^= z >> 27; z *= 0x94d049bb133111ebULL; z ^= z >> 31;
@@ -148,10 +148,12 @@ int gpt_forward(const ttts_gpt_io* io, cudaStream_t st) {
                          c.start_text_token, c.stop_text_token, c.start_mel_token, c.stop_mel_token, text_in, text_tgt, mel_in, mel_tgt, st));
 
     auto resid = [&](int l) { return reinterpret_cast<float*>(ws + w.resid + w.s_resid * (w.save ? l : (l & 1))); };
+    NvtxRange nv_fwd("ttts.gpt.forward");
     TTTS_RUN(embed_fwd(text_in, mel_in, p32 + P.off[TTTS_P_TEXT_EMB], p32 + P.off[TTTS_P_MEL_EMB], p32 + P.off[TTTS_P_TEXT_POS],
                        p32 + P.off[TTTS_P_MEL_POS], resid(0), B, w.Tt, w.Tm, d, w.Vt, w.Vm, site_drop(dp, io->seed, SITE_EMBD, 0), st));
 
     for (int l = 0; l < w.L; ++l) {
+        NvtxRange nv_layer("ttts.gpt.fwd.layer", l);
         float* x = resid(l);
         float* xmid = reinterpret_cast<float*>(ws + w.xmid + w.s_xmid * l);
         float* xnext = resid(l + 1);
@@ -239,7 +241,9 @@ int gpt_backward(const ttts_gpt_io* io, int stage_begin, int stage_end, cudaStre
     bf16* dhid = reinterpret_cast<bf16*>(ws + w.dhid);
     float* delta = reinterpret_cast<float*>(ws + w.delta);
 
+    NvtxRange nv_bwd("ttts.gpt.backward");
     for (int stage = stage_begin; stage < stage_end; ++stage) {
+        NvtxRange nv_stage(stage == 0 ? "ttts.gpt.bwd.heads" : (stage <= w.L ? "ttts.gpt.bwd.layer" : "ttts.gpt.bwd.embeddings"), stage <= w.L ? w.L - stage : 0);
         if (stage == 0) {
             // ---------------- heads + CE + final double LayerNorm ----------------
             bf16* enc = reinterpret_cast<bf16*>(ws + w.enc);
@@ -429,7 +433,7 @@ int ttts_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const 
 }
 static DropCfg user_drop(float p, uint64_t seed) {
     DropCfg dc = no_drop();
-    if (p > 0.f) { dc.thresh16 = (uint32_t)(p * 65536.0f + 0.5f); dc.scale = 1.0f / (1.0f - (float)dc.thresh16 / 65536.0f); dc.seed = seed; }
+    if (p > 0.f) { dc.thresh16 = 2u * (uint32_t)(p * 32768.0f + 0.5f); dc.scale = 1.0f / (1.0f - (float)dc.thresh16 / 65536.0f); dc.seed = seed; }
     return dc;
 }
 int64_t ttts_attn_bwd_scratch_floats(int32_t B, int32_t T, int32_t H) { return (int64_t)B * H * T + 64 + (int64_t)B * T * H * 64; }

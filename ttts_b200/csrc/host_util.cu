@@ -7,7 +7,18 @@
 #include <atomic>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace ttts {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::NvtxRange(const char* name, int index) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%s %d", name, index);
+    nvtxRangePushA(buf);
+}
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
 
 static thread_local char g_err[512] = "";
 

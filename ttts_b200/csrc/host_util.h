@@ -47,6 +47,16 @@ void prof_gemm_end(cudaStream_t st);
         if (_rc != TTTS_OK) return _rc; \
     } while (0)
 
+// NVTX range (header-only nvtx3: no link dependency, a no-op unless a profiler injects itself): the kernel groups of the step show up
+// named in Nsight Systems / ncu --nvtx (the reference only has commented-out torch.autograd.profiler stubs)
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    NvtxRange(const char* name, int index);       // "name index"
+    ~NvtxRange();
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // TTTS_PDL=0 disables programmatic dependent launch (common.cuh: pdl_wait) for A/B measurements
 bool pdl_enabled();
 // <<<grid, block, smem, st>>> with the PDL attribute; only for kernels that call pdl_wait() before their first global-memory access

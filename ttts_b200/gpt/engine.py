@@ -298,13 +298,13 @@ class Engine:
 
     def dropout_masks(self, drop_p=None, seed=None, B=None, T=None):
         """The keep masks the last forward(save=True) drew (or those of an explicit (drop_p, seed, B, T)), from ttts_gpt_dropout_mask:
-        {"embd", "attn_p<l>", "attn_o<l>", "mlp_o<l>"} as uint8 tensors, plus "scale" = 65536 / (65536 - round(p * 65536))."""
+        {"embd", "attn_p<l>", "attn_o<l>", "mlp_o<l>"} as uint8 tensors, plus "scale" = 32768 / (32768 - round(p * 32768))."""
         if drop_p is None:
             B, TL, CL, drop_p, seed = self._last[:5]
             T = TL + CL + 4
         lib = L.lib()
         d, H, nl = self.cfg.model_dim, self.cfg.heads, self.cfg.layers
-        out = {"scale": 1.0 / (1.0 - int(drop_p * 65536.0 + 0.5) / 65536.0)}
+        out = {"scale": 1.0 / (1.0 - int(drop_p * 32768.0 + 0.5) / 32768.0)}
 
         def one(site, layer, rows, cols, shape):
             m = torch.empty(shape, dtype=torch.uint8, device=self.device)

@@ -68,6 +68,10 @@ class FusedStep:
 
     def micro_step(self, text, text_lengths, codes, wav_lengths, clip_inputs=True):
         """forward + backward of one micro-batch (device tensors).  Returns the device tensor [loss_text, loss_mel]."""
+        with torch.cuda.nvtx.range("ttts.step.micro"):
+            return self._micro_step(text, text_lengths, codes, wav_lengths, clip_inputs)
+
+    def _micro_step(self, text, text_lengths, codes, wav_lengths, clip_inputs=True):
         m, eng = self.model, self.eng
         TL, CL = text.shape[1], codes.shape[1]
         if clip_inputs:
@@ -92,7 +96,7 @@ class FusedStep:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 self.comm_stream.wait_event(ev)
-                with torch.cuda.stream(self.comm_stream):
+                with torch.cuda.stream(self.comm_stream), torch.cuda.nvtx.range("ttts.step.allreduce_chunk"):
                     dist.all_reduce(eng.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             main.wait_stream(self.comm_stream)
         else:
@@ -103,11 +107,13 @@ class FusedStep:
     def optimizer_step(self):
         """get_grad_norm + clip_grad_norm_(max_norm) + AdamW + scheduler.step (ttts/gpt/train.py:114-120)."""
         eng = self.eng
+        torch.cuda.nvtx.range_push("ttts.step.clip_adamw")
         eng.grad_norm()                      # norm of the SUMMED gradient; the kernel rescales by 1/world
         self.opt_step += 1
         lr = self.lr * warmup(self.sched_step)
         eng.adamw(lr, self.opt_step, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_norm=self.max_norm,
                   grad_scale=1.0 / self.world)
+        torch.cuda.nvtx.range_pop()
         self.sched_step += 1
         return eng.norm
 

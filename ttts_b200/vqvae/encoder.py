@@ -31,7 +31,10 @@ def _protos(lib):
     vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
     lib.ttts_conv1d_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, vp]
     lib.ttts_conv1d_f32_split.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32, vp]
-    lib.ttts_conv1d_tc.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp]
+    lib.ttts_conv1d_tcs_weight_elems.argtypes = [i32, i32, i32]
+    lib.ttts_conv1d_tcs_weight_elems.restype = ctypes.c_int64
+    lib.ttts_conv1d_tcs_prep_weights.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.ttts_conv1d_tcs.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp]
     lib.ttts_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
     lib.ttts_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.ttts_weight_norm.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -46,10 +49,38 @@ def _p(t):
     return t.data_ptr() if t is not None else None
 
 
+# TTTS_CONV_TC=1: route every convolution the tensor-core kernel covers (csrc/conv1d_tcs.cu) to it; 0: the exact-fp32 CUDA-core kernels
+USE_TC = os.environ.get("TTTS_CONV_TC", "0") == "1"
+TC_FLAGS = int(os.environ.get("TTTS_CONV_TC_FLAGS", "0"))
+
+
+def tcs_covers(Cin, Cout, K, stride, dil, pad, post, cond):
+    return (stride == 1 and post == 0 and cond is None and 2 * pad == dil * (K - 1) and 128 + 2 * pad <= 184 and Cin % 8 == 0
+            and 16 <= Cin <= 192 and Cout in (32, 64, 96, 128, 192, 384))
+
+
+def tcs_weights(w):
+    """The split-bf16 form [tap][ci atom][hi | lo][co][64] of a convolution weight for ttts_conv1d_tcs, cached ON the weight tensor object
+    (validated by address + version + shape, as weight_norm_apply does): constant weights are split once, not once per call."""
+    state = (w.data_ptr(), w._version, tuple(w.shape))
+    capturing = torch.cuda.is_current_stream_capturing()
+    hit = getattr(w, "_ttts_tcs", None)
+    if hit is not None and hit[0] == state and not capturing:
+        return hit[1]
+    lib = L.lib(); _protos(lib)
+    Cout, Cin, K = w.shape
+    ws = torch.empty(lib.ttts_conv1d_tcs_weight_elems(Cout, Cin, K), dtype=torch.bfloat16, device=w.device)
+    L.check(lib.ttts_conv1d_tcs_prep_weights(_p(w), _p(ws), Cout, Cin, K, L.stream_ptr().value), "ttts_conv1d_tcs_prep_weights")
+    if not capturing:
+        w._ttts_tcs = (state, ws)
+    return ws
+
+
 def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None, out_scale=1.0, out=None, accumulate=False, mask=None,
-           post=0, cond=None, split=0, tc=False):
+           post=0, cond=None, split=0, tc=None):
     """Raw call of ttts_conv1d_f32.  x [B,Cin,T] fp32 contiguous, w [Cout,Cin,K].  split = 2 / 4: force the split-reduction kernel
-    (ttts_conv1d_f32_split; per-kernel tests); tc: force the split-bf16 tcgen05 kernel (ttts_conv1d_tc)."""
+    (ttts_conv1d_f32_split; per-kernel tests); tc: True = the split-bf16 tcgen05 kernel (ttts_conv1d_tcs), False = the fp32 kernels,
+    None = the tensor-core kernel when TTTS_CONV_TC=1 and it covers the layer."""
     lib = L.lib(); _protos(lib)
     L.require_cuda(x, w)
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
@@ -61,10 +92,12 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
     if out is None:
         out = torch.empty(B, Ceff, Tout, dtype=torch.float32, device=x.device)
     cond_ld = cond.stride(0) if cond is not None else 0
+    if tc is None:
+        tc = USE_TC and not split and tcs_covers(Cin, Cout, K, stride, dil, pad, post, cond)
     if tc:
-        assert stride == 1 and Cin == Cout and 2 * pad == dil * (K - 1) and mask is None and post == 0
-        L.check(lib.ttts_conv1d_tc(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, K, dil, int(pre_lrelu), _p(resid), float(out_scale), int(accumulate),
-                                   L.stream_ptr().value), "ttts_conv1d_tc")
+        assert tcs_covers(Cin, Cout, K, stride, dil, pad, post, cond), "layer not covered by ttts_conv1d_tcs"
+        L.check(lib.ttts_conv1d_tcs(_p(x), _p(tcs_weights(w)), _p(bias), _p(out), B, Cin, Tin, Cout, K, dil, int(pre_lrelu), _p(resid), float(out_scale),
+                                    int(accumulate), _p(mask), TC_FLAGS, L.stream_ptr().value), "ttts_conv1d_tcs")
         return out
     if split:
         L.check(lib.ttts_conv1d_f32_split(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid),
@@ -373,6 +406,7 @@ class PosteriorAudioEncoder(nn.Module):
         torch.randn_like(m) (None = 0, i.e. z = m: the deterministic encode used for extraction / tests)."""
         lib = L.lib(); _protos(lib)
         B, _, T = x.shape
+        torch.cuda.nvtx.range_push("ttts.vqenc.posterior_encoder")
         mask2 = x_mask.reshape(B, T).contiguous()
         # Two independent branches meet at `cat`: the spectrogram branch (pre -> 16 gated WN layers, T = 36 frames: small launches) and
         # the waveform branch (strided convs + 15 ResBlocks).  They run on two streams, and inside the waveform branch the three
@@ -424,6 +458,7 @@ class PosteriorAudioEncoder(nn.Module):
         z = torch.empty(B, self.out_channels, T, dtype=torch.float32, device=x.device)
         L.check(lib.ttts_posterior_sample(_p(stats), _p(eps.contiguous()) if eps is not None else None, _p(mask2), _p(z), B, self.out_channels, T,
                                           L.stream_ptr().value), "ttts_posterior_sample")
+        torch.cuda.nvtx.range_pop()
         return z, m, logs
 
 
