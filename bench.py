@@ -41,22 +41,26 @@ def peaks():
 
 
 def ncu_dram_bytes_per_launch():
-    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r1d_gemm2_pair_ncu_full.txt: the QKV GEMM, M 36 992 x N 3 072 x K 1 024, whose algorithmic
-    operand + output bytes are 309 MB).  Measured under ncu, so it is read from the committed summary, never produced by this run."""
-    path = os.path.join(ROOT, "profiles", "r1d_gemm2_pair_ncu_full.txt")
-    try:
-        rd = wr = None
-        for line in open(path):
-            if line.startswith("dram__bytes_read.sum [Mbyte]"):
-                rd = float(line.split("]")[1].split("|")[0])
-            if line.startswith("dram__bytes_write.sum [Mbyte]"):
-                wr = float(line.split("]")[1].split("|")[0])
-        if rd is None or wr is None:
-            return None, None
-        return (rd + wr) * 1e6, "profiles/r1d_gemm2_pair_ncu_full.txt (QKV GEMM launch: 309 MB algorithmic)"
-    except OSError:
-        return None, None
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the newest committed
+    `ncu --set full` capture of the shipped GEMM kernel (the QKV GEMM, M 36 992 x N 3 072 x K 1 024, whose algorithmic operand + output
+    bytes are 309 MB; `python tools/gemm_prof.py` under ncu).  Measured under ncu, so it is read from the committed summary, never produced
+    by this run."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[2-9]*_gemm_qkv_ncu_full.txt")), reverse=True)
+    cands.append(os.path.join(ROOT, "profiles", "r1d_gemm2_pair_ncu_full.txt"))
+    for path in cands:
+        try:
+            rd = wr = None
+            for line in open(path):
+                if line.startswith("dram__bytes_read.sum [Mbyte]"):
+                    rd = float(line.split("]")[1].split("|")[0])
+                if line.startswith("dram__bytes_write.sum [Mbyte]"):
+                    wr = float(line.split("]")[1].split("|")[0])
+            if rd is not None and wr is not None:
+                return (rd + wr) * 1e6, "profiles/%s (QKV GEMM launch: 309 MB algorithmic)" % os.path.basename(path)
+        except OSError:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -464,7 +468,7 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import vq_encode_bench
-            out["vq_encode"] = vq_encode_bench.run(hbm_gbs=pk["hbm_gbs"], with_cpu=not args.no_cpu_baseline)
+            out["vq_encode"] = vq_encode_bench.run(hbm_gbs=pk["hbm_gbs"], with_cpu=not args.no_cpu_baseline, bf16_tflops=pk["bf16_burst"])
         except Exception as e:            # the GPT line must still be printed
             out["vq_encode"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_vqvae_step and not args.profile_run and args.workload == "cfg3":

@@ -35,7 +35,9 @@ const char* ttts_last_error(void);
 int ttts_device_ok(void);
 /* number of kernels this library has launched since it was loaded (bench.py's gpu_launches) */
 unsigned long long ttts_launch_count(void);
-/* bracket every tcgen05 GEMM launch with CUDA events on its stream (bench.py's live roofline measurement) */
+/* bracket every launch of ONE kernel family with CUDA events on its stream (bench.py's live roofline measurement):
+ * on = 1 tcgen05 GEMMs | 2 conv1d input-gradient | 3 conv1d weight-gradient | 5 conv1d_tcs | 0 off.  The read-out sums ms and
+ * algorithmic FLOPs (2 M N K; convolutions: 2 B Tout Cin Cout K) of the bracketed launches since the enable. */
 void ttts_prof_gemm_enable(int on);
 int ttts_prof_gemm_read(double* ms_total, double* flops_total, long long* launches);
 
@@ -273,12 +275,13 @@ int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, flo
  * ResBlock1 / WN stacks (ttts/vqvae/modules.py:136-318) on the tcgen05 tensor cores with split-bf16 operands -- hi*hi + hi*lo + lo*hi,
  * fp32 accumulation in TMEM, ~1.5e-5 relative to fp32 -- and no im2col: a tap is a row shift of ONE channel-last window in shared memory
  * (csrc/conv1d_tcs.cu).  The weights are split once per layer into a caller-owned bf16 buffer of ttts_conv1d_tcs_weight_elems() elements:
- *   y = ((conv(lrelu?(x), w) + bias) + resid) * out_scale * mask ; accumulate: y += ;  flags bit 0: leave the descriptor base-offset 0 (debug) */
+ *   y = (post(conv(lrelu?(x), w) + bias) + resid) * out_scale * mask ; accumulate: y += ; post: 0 none | 3 WN gate (Cout = 384 -> 192 channels,
+ *   tanh(a + cond_a) * sigmoid(g + cond_g), cond [B, 384] with row stride cond_ld, may be null) ;  flags bit 0: set the descriptor base offset (debug: measured WRONG on B200, the swizzle follows absolute address bits) */
 int64_t ttts_conv1d_tcs_weight_elems(int32_t Cout, int32_t Cin, int32_t K);
 int ttts_conv1d_tcs_prep_weights(const float* w, void* ws_bf16, int32_t Cout, int32_t Cin, int32_t K, void* stream);
 int ttts_conv1d_tcs(const float* x, const void* ws_bf16, const float* bias, float* y, int32_t B, int32_t Cin, int32_t T, int32_t Cout, int32_t K,
-                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t flags,
-                    void* stream);
+                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t post,
+                    const float* cond, int32_t cond_ld, int32_t flags, void* stream);
 /* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- written without hardware, validated on the CPU
  * emulation of the source only).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
  *   bwd_input : dx[B,Cin,Tin] (+)= lrelu'(x) * conv_transpose(dy, w)      x only read when pre_lrelu (the forward's input)

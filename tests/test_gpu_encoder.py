@@ -148,6 +148,26 @@ def test_conv1d_tcs_vs_torch(B, Cin, Cout, K, dil, T):
         assert float((got.double() - want).abs().max()) < 2e-4 * float(want.abs().max())
 
 
+@pytest.mark.parametrize("B,K,dil,T", [(64, 5, 1, 36), (3, 5, 1, 50), (2, 3, 3, 200)])
+def test_conv1d_tcs_wn_gate_vs_torch(B, K, dil, T):
+    """the WN in_layer on the tensor-core kernel: Conv1d(192 -> 384) + bias + conditioning, tanh(a) * sigmoid(g) fused in the epilogue"""
+    from ttts_b200.vqvae.encoder import conv1d
+    g = torch.Generator(device="cuda").manual_seed(B + K + T)
+    x = torch.randn(B, 192, T, device="cuda", generator=g)
+    w = torch.randn(384, 192, K, device="cuda", generator=g) / (192 * K) ** 0.5
+    b = torch.randn(384, device="cuda", generator=g)
+    big = torch.randn(B, 3 * 384, device="cuda", generator=g)
+    cond = big[:, 384:768]                                     # a slice of the cond_layer output: row stride != 384
+    pad = dil * (K - 1) // 2
+    got = conv1d(x, w, b, dil=dil, pad=pad, post=3, cond=cond, tc=True)
+    ref = conv1d(x, w, b, dil=dil, pad=pad, post=3, cond=cond, tc=False)
+    y = torch.nn.functional.conv1d(x.double(), w.double(), b.double(), dilation=dil, padding=pad) + cond.double()[:, :, None]
+    want = torch.tanh(y[:, :192]) * torch.sigmoid(y[:, 192:])
+    assert got.shape == (B, 192, T)
+    assert float((ref.double() - want).norm() / want.norm()) < 2e-6
+    assert float((got.double() - want).norm() / want.norm()) < 3e-5
+
+
 @pytest.mark.parametrize("groups", [2, 4])
 @pytest.mark.parametrize("shape", [(64, 192, 36, 384, 5, 1, 1, 2, 3), (64, 192, 36, 384, 1, 1, 1, 0, 0), (64, 128, 72, 128, 11, 1, 5, 25, 0),
                                    (64, 96, 144, 96, 7, 1, 3, 9, 0), (3, 20, 61, 24, 7, 2, 1, 3, 2), (2, 3, 70, 16, 3, 1, 1, 1, 1)])

@@ -24,7 +24,7 @@ def _time(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def run(hbm_gbs=6570.3, with_cpu=False):
+def run(hbm_gbs=6570.3, with_cpu=False, bf16_tflops=1638.6):
     import numpy as np
     import torch
     from ttts_b200.vqvae.encoder import VQEncoder
@@ -52,6 +52,24 @@ def run(hbm_gbs=6570.3, with_cpu=False):
         out["encode_graphed_error"] = repr(e)[:200]
     out["batch"] = B
     out["samples_per_clip"] = Lw
+    # the convolution stack (90 % of the encode): which kernels run it, and the roofline of the tensor-core convolution
+    from ttts_b200.vqvae import encoder as ENC
+    from ttts_b200 import _lib as L
+    import ctypes
+    out["conv_path"] = "conv1d_tcs (split-bf16 tcgen05, TTTS_CONV_TC=1)" if ENC.USE_TC else "fp32 CUDA-core kernels (TTTS_CONV_TC=0)"
+    if ENC.USE_TC:
+        lib = L.lib()
+        enc(wav); torch.cuda.synchronize()
+        lib.ttts_prof_gemm_enable(5)
+        enc(wav)
+        ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.ttts_prof_gemm_read(ctypes.byref(ms_k), ctypes.byref(fl_k), ctypes.byref(n_k))
+        lib.ttts_prof_gemm_enable(0)
+        if ms_k.value > 0:
+            tf = fl_k.value / (ms_k.value * 1e-3) / 1e12
+            out["conv"] = {"kernel": "conv1d_tcs_kernel", "launches": int(n_k.value), "ms_sum": ms_k.value, "gflop": fl_k.value / 1e9,
+                           "tflops": tf, "frac_tensor": tf / (bf16_tflops / 3.0), "frac_fp32": tf / (148 * 128 * 2 * 1.965e-3),
+                           "tensor_roof": "dense bf16 peak / 3 (three bf16 products per fp32 product)", "note": "sum of the kernels' own durations (CUDA events per launch, streams serialised by the events); share of the fp32-path encode they replace: ~75 % of its FLOPs"}
     # end to end with HOST buffers, as an extraction script calls it: pinned waveforms -> device, encode, codes -> host, every batch
     try:
         hw = wav.cpu().pin_memory()

@@ -65,6 +65,26 @@ def run(B=64, iters=3, with_cpu=False, cpu_batch=2):
            "step_tflops": FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
            "flop_model": "3.87e11 FLOP per clip and step (SURVEY.md section 6, FlopCounterMode over the reference's step)",
            "losses": {k: float(v) for k, v in out.items()}}
+    # roofline of the step's dominant kernels (profiles/r2c_launches_vqvae_b8_summary.txt: conv1d_dgrad 36 %, conv1d_wgrad 26 % of the
+    # serialised step): one more step per family with a CUDA-event pair around each of its launches.  Exact fp32 on the CUDA cores, so the
+    # roof is the fp32 FMA pipe (148 SMs x 128 lanes x 2 FLOP x max SM clock); the bf16 tensor roof / 3 (split operands) is given beside it.
+    import ctypes
+    fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    roof = {}
+    for kind, name in ((2, "conv1d_dgrad_kernel"), (3, "conv1d_wgrad_kernel")):
+        lib.ttts_prof_gemm_enable(kind)
+        step()
+        ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.ttts_prof_gemm_read(ctypes.byref(ms_k), ctypes.byref(fl_k), ctypes.byref(n_k))
+        lib.ttts_prof_gemm_enable(0)
+        if ms_k.value > 0:
+            tf = fl_k.value / (ms_k.value * 1e-3) / 1e12
+            roof[name] = {"launches": int(n_k.value), "ms_per_step": ms_k.value, "share_of_step": ms_k.value / ms, "tflops": tf,
+                          "frac_fp32_fma_peak": tf / fma_peak, "fp32_fma_peak_tflops": fma_peak}
+    if roof:
+        top = max(roof, key=lambda k: roof[k]["ms_per_step"])
+        res["roofline"] = {"bound": "fp32 FMA pipe (exact-fp32 CUDA-core implicit GEMM)", "kernel": top, "achieved": roof[top]["tflops"], "peak": fma_peak,
+                           "unit": "TFLOP/s", "frac": roof[top]["frac_fp32_fma_peak"], "traffic": None, "kernels": roof}
     if with_cpu:
         try:
             res["cpu_baseline"] = cpu_reference_step(cpu_batch)

@@ -88,7 +88,7 @@ struct Fwd4Smem {
 // work issues in the shadow of the MUFU pipe.  The row-max exchange only concerns the four warps that share a lane quadrant (same rows,
 // different columns), so it uses one 128-thread named barrier per quadrant instead of one for all 16 warps.  Same arithmetic, same bits.
 template <int kMode>
-__global__ void __maxnreg__(112)
+__global__ void __maxnreg__(96)
 attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, int BH, float scale,
                     DropCfg drop) {
     using S = Fwd4Smem;
@@ -369,19 +369,21 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 // Software pipeline as in the forward kernel: the exponent offset of group i depends on the packed P of group i - 2 through a word that
 // is zero at run time, so the exponentials cannot be batched and the integer / FMA work of the neighbouring groups fills the MUFU shadow.
 template <int kMode, bool kMasked>
-TTTS_DEVICE void bwd_math(const uint32_t (&sv)[32], const uint32_t (&gv)[32], uint32_t (&pp)[16], uint32_t (&dd)[16], float sl2, float lse2, float ndl,
-                          const AttnDropRow rk, uint32_t g0, uint32_t addc, int n_ok, uint32_t zero) {
+TTTS_DEVICE void bwd_math(const int cc, const uint32_t (&sv)[16], const uint32_t (&gv)[16], uint32_t (&pp)[16], uint32_t (&dd)[16], float sl2, float lse2,
+                          float ndl, const AttnDropRow rk, uint32_t g0, uint32_t addc, int n_ok, uint32_t zero) {
+    // cc = 0 / 1: the thread's first / second 16 keys (groups 0-3 / 4-7 of the block; the dependency chain runs on across the two calls)
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const int i4 = cc * 4 + j4;
         float lo = lse2;
         if (i4 >= 2) lo = __uint_as_float(__float_as_uint(lse2) | (pp[2 * (i4 - 2)] & zero));
         float pe[4], nd[4], dk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            pe[e] = ex2_fast(fmaf(__uint_as_float(sv[i4 * 4 + e]), sl2, -lo));
+            pe[e] = ex2_fast(fmaf(__uint_as_float(sv[j4 * 4 + e]), sl2, -lo));
             if (kMasked) pe[e] = (i4 * 4 + e < n_ok) ? pe[e] : 0.f;
             nd[e] = pe[e] * ndl;
-            dk[e] = fmaf(pe[e], __uint_as_float(gv[i4 * 4 + e]), nd[e]);
+            dk[e] = fmaf(pe[e], __uint_as_float(gv[j4 * 4 + e]), nd[e]);
         }
         if (kMode == 1) {
             uint32_t w0, w1;
@@ -414,7 +416,7 @@ struct Bwd4Smem {
 // kMode as in the forward kernel: 0 = r1e code (run-time dropout branch after the exponentials of each 16-column chunk), 1 / 2 = dropout
 // on / off fixed at compile time with each 4-key group's hash next to its exponentials.
 template <int kMode>
-__global__ void __maxnreg__(112)
+__global__ void __maxnreg__(96)
 attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
                     const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, int BH, float scale,
                     DropCfg drop) {
@@ -669,20 +671,24 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 // 16-bit lanes per LOP3 (common.cuh attn_drop_mask2) instead of shift + ISETP + 2 SEL per key on fp32 values.
                 const float ndl = -dlt * inv_c;
                 {
-                    // S and dP of the thread's 32 keys in one go: the accumulators are handed back to the MMA warp (which issues the next
-                    // block's S / dP into them) before the math starts, not half-way through it
-                    uint32_t sv[32], gv[32];
-                    __syncwarp();
-                    tmem_ld_32x32(tS + lane_off + qtr * 32, sv);
-                    tmem_ld_32x32(tDP + lane_off + qtr * 32, gv);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sdp_empty);
                     // keys of this block that exist for this query row (causal + sequence end); only consulted on diagonal / edge blocks
                     const int n_ok = q_ok ? min(qi, T - 1) - kc0 + 1 : 0;
-                    if (need_mask) bwd_math<kMode, true>(sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, n_ok, drop.thresh16 >> 16);
-                    else bwd_math<kMode, false>(sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, 32, drop.thresh16 >> 16);
+                    const uint32_t zero = drop.thresh16 >> 16;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t sv[16], gv[16];
+                        __syncwarp();
+                        tmem_ld_32x16(tS + lane_off + qtr * 32 + cc * 16, sv);
+                        tmem_ld_32x16(tDP + lane_off + qtr * 32 + cc * 16, gv);
+                        tmem_ld_wait();
+                        if (cc == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sdp_empty);
+                        }
+                        if (need_mask) bwd_math<kMode, true>(cc, sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, n_ok, zero);
+                        else bwd_math<kMode, false>(cc, sv, gv, pp, dd, sl2, lse2, ndl, rk, (uint32_t)kc0 >> 2, addc, 32, zero);
+                    }
                 }
                 mbar_wait(pds_empty, ph ^ 1);
 #pragma unroll

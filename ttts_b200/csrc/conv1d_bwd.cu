@@ -256,7 +256,9 @@ int conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx,
     TTTS_CHECK_ARG(dy && w && dx && (!pre_lrelu || x), "conv1d dgrad: null pointer");
     p.dy = dy; p.w = w; p.x = x; p.dx = dx; p.pre_lrelu = pre_lrelu; p.accumulate = accumulate;
     const dim3 grid((unsigned)(((long long)B * Tin + IG_P - 1) / IG_P), (Cin + BW_T - 1) / BW_T);
+    prof_begin(2, st, 2.0 * B * p.Tout * (double)Cin * Cout * K);
     TTTS_CUDA(launch_plain(conv1d_dgrad_kernel, grid, dim3(BW_NT), 0, st, p));
+    prof_end(2, st);
     TTTS_LAUNCH_CHECK("conv1d_dgrad");
     return TTTS_OK;
 }
@@ -279,7 +281,9 @@ int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int
     slice = (slice + IG_R - 1) / IG_R * IG_R;
     p.slice = (int)slice;
     const dim3 grid(gx, gy, (unsigned)((Ptot + slice - 1) / slice));
+    prof_begin(3, st, 2.0 * B * p.Tout * (double)Cin * Cout * K);
     TTTS_CUDA(launch_plain(conv1d_wgrad_kernel, grid, dim3(BW_NT), 0, st, p));
+    prof_end(3, st);
     TTTS_LAUNCH_CHECK("conv1d_wgrad");
     if (db) {
         TTTS_CUDA(launch_plain(conv1d_bgrad_kernel, dim3(Cout), dim3(256), 0, st, dy, db, B, Cout, p.Tout));

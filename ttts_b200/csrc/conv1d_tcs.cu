@@ -12,7 +12,9 @@
 //   * the CTA stages its input window ONCE, channel-last: Xs[row][ci] (hi and lo copies), row = position in a packed row space, 64
 //     channels = 128 bytes per row = one SWIZZLE_128B atom column (Cin > 64: several atoms side by side).  Tap k of the convolution
 //     reads rows [k dil, k dil + 128) of that window: the A operand of tap k is the SAME tile with its start address advanced by
-//     k dil rows (128 B each); the UMMA descriptor carries the swizzle phase of the unaligned start in its base-offset field.
+//     k dil rows (128 B each).  Measured on B200 (profiles/r2d_pytest_tcs_*.log): the 128-byte swizzle is a function of the ABSOLUTE
+//     shared-memory address bits, so the unaligned start needs NO base offset in the descriptor (with the offset set to
+//     (addr >> 7) & 7, as the wgmma-era documentation suggests for starts off the 1024-byte pattern, every result is wrong).
 //   * the weights are pre-split ONCE per layer into [tap][ci atom][hi | lo][co][64 ci] bf16 (conv_tcs_prep_weights) and streamed by
 //     TMA, 128B-swizzled, as K-major B operands [NT co][64 ci] through a ring of stages;
 //   * D[128 rows][NT co] accumulates over taps x ci atoms x 4 k-steps x 3 products in TMEM; epilogue: one row (= one output frame)
@@ -29,7 +31,7 @@ namespace ttts {
 
 constexpr int TCS_ATOM_ROWS = 184;                       // 128 + 2 * 25 (kernel 11, dilation 5) rounded up to 8 rows
 constexpr int TCS_ATOM_BYTES = TCS_ATOM_ROWS * 128;      // one [rows x 64 bf16] atom column
-constexpr int TCS_STAGES = 3;
+constexpr int TCS_MAX_STAGES = 8;                       // weight-tile ring: as many stages as fit (small tiles are latency-, not bandwidth-bound)
 constexpr int TCS_THREADS = 192;                         // warps 0-3: transform + epilogue (TMEM lane quadrant = warp), 4: MMA, 5: TMA
 
 struct ConvTcsParams {
@@ -41,6 +43,9 @@ struct ConvTcsParams {
     int NT;                // output channels per CTA
     int wrows;             // window rows = 128 + 2 * pad
     int pre_lrelu, accumulate, base_off;
+    int stages;            // weight ring depth, 2 .. TCS_MAX_STAGES
+    int gated;             // WN gate (post = 3): Cout = 2 H, output channel c = tanh(a_c + cond_c) * sigmoid(g_c + cond_{H + c}), a = rows [0, H), g = rows [H, 2H)
+    const float* cond; int cond_ld;      // [B, 2H] conditioning (may be null)
     float out_scale;
     uint32_t p_magic;      // ceil(2^32 / P)
 };
@@ -56,18 +61,19 @@ struct TcsSmem {
     static constexpr int oX = 1024;                                   // [hi | lo][A atoms][184 rows][128 B]
     static size_t x_bytes(int A) { return (size_t)2 * A * TCS_ATOM_BYTES; }
     static size_t w_stage_bytes(int NT) { return (size_t)2 * NT * 128; }
-    static size_t total(int A, int NT) { return 1024 + x_bytes(A) + TCS_STAGES * w_stage_bytes(NT) + 1024; }
+    static size_t total(int A, int NT, int stages) { return 1024 + x_bytes(A) + stages * w_stage_bytes(NT) + 1024; }
 };
 
 __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_constant__ CUtensorMap tmW, const ConvTcsParams p) {
     extern __shared__ uint8_t tcs_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcs_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcsSmem::oBar);
-    uint64_t* w_full = bars;                       // [STAGES] TMA bytes landed
-    uint64_t* w_empty = bars + TCS_STAGES;         // [STAGES] tcgen05.commit: the MMAs that read the stage are done
-    uint64_t* x_full = bars + 2 * TCS_STAGES;      // 4 arrivals: the window is staged
-    uint64_t* acc_full = bars + 2 * TCS_STAGES + 1;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TCS_STAGES + 2);
+    uint64_t* w_full = bars;                       // [stages] TMA bytes landed
+    uint64_t* w_empty = bars + TCS_MAX_STAGES;     // [stages] tcgen05.commit: the MMAs that read the stage are done
+    uint64_t* x_full = bars + 2 * TCS_MAX_STAGES;  // [3] one per ci atom, 4 arrivals each: that atom column of the window is staged
+    uint64_t* acc_full = bars + 2 * TCS_MAX_STAGES + 3;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TCS_MAX_STAGES + 4);
+    const int TCS_STAGES = p.stages;
     const uint32_t sX = smem_u32(smem + TcsSmem::oX);
     const uint32_t sXlo = sX + p.A * TCS_ATOM_BYTES;
     const uint32_t sW = sX + 2 * p.A * TCS_ATOM_BYTES;
@@ -80,8 +86,8 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW);
-        for (int s = 0; s < TCS_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(x_full, 4);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 3; ++a) mbar_init(&x_full[a], 4);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -94,27 +100,37 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
 
     if (warp == 5) {
         // ---------------- TMA: weight tiles [NT co][64 ci], hi then lo, one stage per (tap, atom) ----------------
-        for (int kb = 0; kb < n_kb; ++kb) {
-            const int s = kb % TCS_STAGES;
-            mbar_wait(&w_empty[s], ((kb / TCS_STAGES) & 1) ^ 1);
+        for (int it = 0; it < n_kb; ++it) {
+            const int s = it % TCS_STAGES;
+            const int a = it / p.K, k = it - a * p.K;       // atom-major order: the MMAs of atom 0 run while atoms 1, 2 are still being staged
+            const int kb = k * p.A + a;                     // tile index in the pre-split weight tensor [tap][atom]
+            mbar_wait(&w_empty[s], ((it / TCS_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&w_full[s], w_stage);
                 uint8_t* dst = smem + TcsSmem::oX + (size_t)2 * p.A * TCS_ATOM_BYTES + (size_t)s * w_stage;
-                tma_load_2d(dst, &tmW, &w_full[s], 0, (kb * 2 + 0) * p.Cout + n0);
-                tma_load_2d(dst + p.NT * 128, &tmW, &w_full[s], 0, (kb * 2 + 1) * p.Cout + n0);
+                if (!p.gated) {
+                    tma_load_2d(dst, &tmW, &w_full[s], 0, (kb * 2 + 0) * p.Cout + n0);
+                    tma_load_2d(dst + p.NT * 128, &tmW, &w_full[s], 0, (kb * 2 + 1) * p.Cout + n0);
+                } else {                                  // tile = NT / 2 `a` channels followed by the NT / 2 `g` channels of the same outputs
+                    const int hN = p.NT / 2, c0 = blockIdx.y * hN, H = p.Cout / 2;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tma_load_2d(dst + h * p.NT * 128, &tmW, &w_full[s], 0, (kb * 2 + h) * p.Cout + c0);
+                        tma_load_2d(dst + h * p.NT * 128 + hN * 128, &tmW, &w_full[s], 0, (kb * 2 + h) * p.Cout + H + c0);
+                    }
+                }
             }
             __syncwarp();
         }
     } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = make_idesc_bf16(128, p.NT, false, false);
-        mbar_wait(x_full, 0);
-        tc_fence_after();
         uint32_t first = 1;
-        for (int kb = 0; kb < n_kb; ++kb) {
-            const int s = kb % TCS_STAGES;
-            const int k = kb / p.A, a = kb - k * p.A;
-            mbar_wait(&w_full[s], (kb / TCS_STAGES) & 1);
+        for (int it = 0; it < n_kb; ++it) {
+            const int s = it % TCS_STAGES;
+            const int a = it / p.K, k = it - a * p.K;
+            if (k == 0) mbar_wait(&x_full[a], 0);
+            mbar_wait(&w_full[s], (it / TCS_STAGES) & 1);
             tc_fence_after();
             const uint32_t row_off = (uint32_t)(k * p.dil) * 128u;          // tap k = the window shifted by k * dil rows
             const uint32_t aHi = sX + a * TCS_ATOM_BYTES + row_off, aLo = sXlo + a * TCS_ATOM_BYTES + row_off;
@@ -130,25 +146,34 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
                     first = 0;
                 }
                 umma_commit(&w_empty[s]);
-                if (kb == n_kb - 1) umma_commit(acc_full);
+                if (it == n_kb - 1) umma_commit(acc_full);
             }
             __syncwarp();
         }
     } else {
         // ---------------- workers: stage the window (channel-last, hi / lo), then the epilogue ----------------
         const int tid = threadIdx.x;                                         // 0 .. 127
-        const int cgroups = p.A * 8;                                         // 16-byte chunks (8 channels) per row over all atoms
-        for (int jb = 0; jb < p.wrows; jb += 128) {
-            const int j = jb + tid;                                          // window row
-            const int gi = g0 - p.pad + j;                                   // packed input row
-            bool row_ok = (j < p.wrows) && gi >= 0 && gi < p.rows;
-            int b = 0, t = 0;
-            if (row_ok) { b = (int)__umulhi((uint32_t)gi, p.p_magic); if (p.P == 1) b = gi; t = gi - b * p.P; row_ok = t < p.T; }
-            if (j < TCS_ATOM_ROWS) {
-                const float* xp = p.x + ((size_t)b * p.Cin) * p.T + t;
+        // row bookkeeping of this thread's (up to) two window rows
+        int rb[2], rt[2]; bool rok[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = q * 128 + tid;
+            const int gi = g0 - p.pad + j;
+            bool ok_ = (j < p.wrows) && gi >= 0 && gi < p.rows;
+            int b_ = 0, t_ = 0;
+            if (ok_) { b_ = (int)__umulhi((uint32_t)gi, p.p_magic); if (p.P == 1) b_ = gi; t_ = gi - b_ * p.P; ok_ = t_ < p.T; }
+            rb[q] = b_; rt[q] = t_; rok[q] = ok_;
+        }
+        for (int a = 0; a < p.A; ++a) {                                      // atom by atom: the MMA warp starts on atom 0 while 1, 2 are staged
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = q * 128 + tid;                                 // window row
+                if (j >= TCS_ATOM_ROWS) continue;
+                const bool row_ok = rok[q];
+                const float* xp = p.x + ((size_t)rb[q] * p.Cin) * p.T + rt[q];
                 // two 8-channel groups per iteration: 16 independent loads in flight per thread (the loads of a group are coalesced across
                 // the warp: consecutive lanes = consecutive frames of one channel)
-                for (int cg = 0; cg < cgroups; cg += 2) {
+                for (int cg = a * 8; cg < a * 8 + 8; cg += 2) {
                     float v[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -175,10 +200,10 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
                     }
                 }
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_full[a]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(x_full);
 
         // epilogue: thread = packed output row g0 + tid = TMEM lane
         const int g = g0 + tid;
@@ -189,24 +214,67 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        if (p.gated) {
+            const int hN = p.NT / 2, H = p.Cout / 2, cbase = blockIdx.y * hN;
+            const float* cnd = (ok && p.cond) ? p.cond + (size_t)b * p.cond_ld : nullptr;
+            for (int c0 = 0; c0 < hN; c0 += 16) {
+                uint32_t ra[16], rg[16];
+                __syncwarp();
+                tmem_ld_32x16(tmem_base + lane_off + c0, ra);
+                tmem_ld_32x16(tmem_base + lane_off + hN + c0, rg);
+                if (ok) {
+                    float ba[16], bg[16], res[16], old[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = cbase + c0 + i;
+                        const bool cok = c0 + i < hN;
+                        ba[i] = cok ? ((p.bias ? __ldg(p.bias + c) : 0.f) + (cnd ? __ldg(cnd + c) : 0.f)) : 0.f;
+                        bg[i] = cok ? ((p.bias ? __ldg(p.bias + H + c) : 0.f) + (cnd ? __ldg(cnd + H + c) : 0.f)) : 0.f;
+                        const size_t o = ((size_t)b * H + c) * p.T + t;
+                        res[i] = (p.resid && cok) ? __ldg(p.resid + o) : 0.f;
+                        old[i] = (p.accumulate && cok) ? p.y[o] : 0.f;
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = cbase + c0 + i;
+                        if (c0 + i < hN) {
+                            const float a = __uint_as_float(ra[i]) + ba[i], g = __uint_as_float(rg[i]) + bg[i];
+                            const float v = tanhf(a) * (1.f / (1.f + __expf(-g)));
+                            p.y[((size_t)b * H + c) * p.T + t] = old[i] + (v + res[i]) * (p.out_scale * mk);
+                        }
+                    }
+                } else {
+                    tmem_ld_wait();
+                }
+            }
+        } else {
         for (int c0 = 0; c0 < p.NT; c0 += 16) {
             uint32_t r[16];
             __syncwarp();
             tmem_ld_32x16(tmem_base + lane_off + c0, r);
-            tmem_ld_wait();
             if (ok) {
+                // every load of the chunk is issued before the first store: written load -> store -> load per channel the compiler must keep
+                // that order (y may alias resid for all it knows) and a 32-channel tile becomes a chain of 32 dependent DRAM round trips
+                // (r2e launch list: 80 us for a level-0 layer whose MMAs take 2 us)
+                const size_t o0 = ((size_t)b * p.Cout + n0 + c0) * p.T + t;
+                float res[16], old[16], bs[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int co = n0 + c0 + i;
-                    if (co < p.Cout) {
-                        float v = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-                        const size_t o = ((size_t)b * p.Cout + co) * p.T + t;
-                        if (p.resid) v += p.resid[o];
-                        v *= p.out_scale * mk;
-                        p.y[o] = p.accumulate ? p.y[o] + v : v;
-                    }
+                    const bool cok = n0 + c0 + i < p.Cout;
+                    res[i] = (p.resid && cok) ? __ldg(p.resid + o0 + (size_t)i * p.T) : 0.f;
+                    old[i] = (p.accumulate && cok) ? p.y[o0 + (size_t)i * p.T] : 0.f;
+                    bs[i] = (p.bias && cok) ? __ldg(p.bias + n0 + c0 + i) : 0.f;
                 }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (n0 + c0 + i < p.Cout) p.y[o0 + (size_t)i * p.T] = old[i] + (__uint_as_float(r[i]) + bs[i] + res[i]) * (p.out_scale * mk);
+                }
+            } else {
+                tmem_ld_wait();
             }
+        }
         }
         tc_fence_before();
     }
@@ -246,7 +314,7 @@ int conv_tcs_prep_weights(const float* w, void* ws, int Cout, int Cin, int K, cu
 }
 
 bool conv_tcs_covers(int Cin, int Cout, int K, int stride, int dil, int pad, int post) {
-    if (stride != 1 || post != 0 || K < 1 || dil < 1) return false;
+    if (stride != 1 || !(post == 0 || (post == 3 && Cout == 384)) || K < 1 || dil < 1) return false;
     if (pad * 2 != dil * (K - 1) || 128 + 2 * pad > TCS_ATOM_ROWS) return false;
     if (Cin % 8 != 0 || Cin < 16 || Cin > 192) return false;
     if (!(Cout == 32 || Cout == 64 || Cout == 96 || Cout == 128 || Cout == 192 || Cout == 384)) return false;
@@ -254,10 +322,11 @@ bool conv_tcs_covers(int Cin, int Cout, int K, int stride, int dil, int pad, int
 }
 
 int conv1d_tcs(const float* x, const void* ws, const float* bias, float* y, int B, int Cin, int T, int Cout, int K, int dil, int pre_lrelu,
-               const float* resid, float out_scale, int accumulate, const float* mask, int base_off, cudaStream_t st) {
+               const float* resid, float out_scale, int accumulate, const float* mask, int post, const float* cond, int cond_ld, int base_off,
+               cudaStream_t st) {
     const int pad = dil * (K - 1) / 2;
     TTTS_CHECK_ARG(x && ws && y && B > 0 && T > 0, "conv1d_tcs: bad arguments");
-    TTTS_CHECK_ARG(conv_tcs_covers(Cin, Cout, K, 1, dil, pad, 0), "conv1d_tcs: layer not covered (stride 1, same padding, Cin %% 8 == 0, Cin <= 192, Cout in {32, 64, 96, 128, 192, 384})");
+    TTTS_CHECK_ARG(conv_tcs_covers(Cin, Cout, K, 1, dil, pad, post), "conv1d_tcs: layer not covered (stride 1, same padding, Cin %% 8 == 0, Cin <= 192, Cout in {32, 64, 96, 128, 192, 384})");
     ConvTcsParams p = {};
     p.x = x; p.bias = bias; p.y = y; p.resid = resid; p.mask = mask;
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = K; p.dil = dil; p.pad = pad;
@@ -266,22 +335,30 @@ int conv1d_tcs(const float* x, const void* ws, const float* bias, float* y, int 
     p.rows = B * p.P;
     p.A = (Cin + 63) / 64;
     p.NT = Cout <= 128 ? Cout : 96;
+    p.gated = post == 3; p.cond = cond; p.cond_ld = cond_ld;
     p.wrows = 128 + 2 * pad;
     p.pre_lrelu = pre_lrelu; p.accumulate = accumulate; p.base_off = base_off; p.out_scale = out_scale;
     p.p_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.P - 1) / (uint64_t)p.P);
     CUtensorMap tm;
     const uint64_t wrows = (uint64_t)K * p.A * 2 * Cout;
-    int rc = make_tmap_2d(&tm, ws, 2, 64, wrows, 64, 64, (uint32_t)p.NT, 1);
+    int rc = make_tmap_2d(&tm, ws, 2, 64, wrows, 64, 64, (uint32_t)(p.gated ? p.NT / 2 : p.NT), 1);
     if (rc) return rc;
-    const size_t smem = TcsSmem::total(p.A, p.NT);
+    // ring depth: what fits next to the window, at most one stage per weight tile; shallow for the big tiles so that 2 CTAs share an SM
+    const int n_kb = K * p.A;
+    int stages = TCS_MAX_STAGES;
+    while (stages > 2 && (stages > n_kb || TcsSmem::total(p.A, p.NT, stages) > (p.A == 1 ? 110 : 227) * 1024)) --stages;
+    p.stages = stages;
+    const size_t smem = TcsSmem::total(p.A, p.NT, stages);
     static size_t attr = 0;
     if (smem > attr) {
         TTTS_CUDA(cudaFuncSetAttribute(conv1d_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr = 227 * 1024;
     }
     TTTS_CHECK_ARG(smem <= 227 * 1024, "conv1d_tcs: shared memory");
-    dim3 grid((p.rows + 127) / 128, Cout / p.NT);
+    dim3 grid((p.rows + 127) / 128, Cout / p.NT);            // gated: Cout / NT = H / (NT / 2) tiles of NT / 2 output channels
+    prof_begin(5, st, 2.0 * B * T * (double)Cin * Cout * K);
     conv1d_tcs_kernel<<<grid, TCS_THREADS, smem, st>>>(tm, p);
+    prof_end(5, st);
     TTTS_LAUNCH_CHECK("conv1d_tcs");
     return TTTS_OK;
 }
@@ -294,9 +371,9 @@ int ttts_conv1d_tcs_prep_weights(const float* w, void* ws_bf16, int32_t Cout, in
     return ttts::conv_tcs_prep_weights(w, ws_bf16, Cout, Cin, K, (cudaStream_t)stream);
 }
 int ttts_conv1d_tcs(const float* x, const void* ws_bf16, const float* bias, float* y, int32_t B, int32_t Cin, int32_t T, int32_t Cout, int32_t K,
-                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t flags,
-                    void* stream) {
-    return ttts::conv1d_tcs(x, ws_bf16, bias, y, B, Cin, T, Cout, K, dil, pre_lrelu, resid, out_scale, accumulate, mask, (flags & 1) ? 0 : 1,
-                            (cudaStream_t)stream);
+                    int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t post,
+                    const float* cond, int32_t cond_ld, int32_t flags, void* stream) {
+    return ttts::conv1d_tcs(x, ws_bf16, bias, y, B, Cin, T, Cout, K, dil, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld,
+                            (flags & 1) ? 1 : 0, (cudaStream_t)stream);
 }
 }

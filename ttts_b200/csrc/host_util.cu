@@ -38,23 +38,28 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct ProfRec { cudaEvent_t e0, e1; double flops; };
-static bool g_prof = false;
+static int g_prof = 0;             // 0 off | 1 tcgen05 GEMMs | 2 conv1d dgrad | 3 conv1d wgrad | 4 conv1d forward (fp32 kernels) | 5 conv1d_tcs
 static std::vector<ProfRec> g_prof_recs;
 static size_t g_prof_used = 0;
-bool prof_enabled() { return g_prof; }
-void prof_gemm_begin(cudaStream_t st, double flops) {
-    if (!g_prof) return;
+bool prof_enabled() { return g_prof == 1; }
+static bool g_prof_open = false;
+void prof_begin(int kind, cudaStream_t st, double flops) {
+    if (g_prof != kind) return;
+    g_prof_open = true;
     if (g_prof_used == g_prof_recs.size()) {
         ProfRec r; cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); r.flops = 0; g_prof_recs.push_back(r);
     }
     g_prof_recs[g_prof_used].flops = flops;
     cudaEventRecord(g_prof_recs[g_prof_used].e0, st);
 }
-void prof_gemm_end(cudaStream_t st) {
-    if (!g_prof) return;
+void prof_gemm_begin(cudaStream_t st, double flops) { prof_begin(1, st, flops); }
+void prof_end(int kind, cudaStream_t st) {
+    if (g_prof != kind || !g_prof_open) return;
+    g_prof_open = false;
     cudaEventRecord(g_prof_recs[g_prof_used].e1, st);
     ++g_prof_used;
 }
+void prof_gemm_end(cudaStream_t st) { prof_end(1, st); }
 
 bool pdl_enabled() {
     static int on = -1;
@@ -187,7 +192,7 @@ const char* ttts_last_error(void) { return ttts::g_err; }
 
 unsigned long long ttts_launch_count(void) { return ttts::g_launches.load(); }
 
-void ttts_prof_gemm_enable(int on) { ttts::g_prof = on != 0; if (on) ttts::g_prof_used = 0; }
+void ttts_prof_gemm_enable(int on) { ttts::g_prof = on; if (on) ttts::g_prof_used = 0; }
 /* synchronises the device, sums the bracketed GEMM launches since enable: total ms, total FLOPs, launch count */
 int ttts_prof_gemm_read(double* ms_total, double* flops_total, long long* launches) {
     cudaError_t e = cudaDeviceSynchronize();

@@ -19,6 +19,9 @@ void count_launch();
 bool prof_enabled();
 void prof_gemm_begin(cudaStream_t st, double flops);
 void prof_gemm_end(cudaStream_t st);
+// the same bracket for other kernel families (ttts_prof_gemm_enable(kind): 2 conv1d dgrad, 3 conv1d wgrad, 4 conv1d forward, 5 conv1d_tcs)
+void prof_begin(int kind, cudaStream_t st, double flops);
+void prof_end(int kind, cudaStream_t st);
 
 #define TTTS_CHECK_ARG(cond, ...)                    \
     do {                                             \

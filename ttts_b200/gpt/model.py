@@ -69,7 +69,7 @@ class _GPTStepFn(torch.autograd.Function):
         gt = g_text.contiguous().float() if g_text is not None else torch.zeros((), device=eng.device)
         gm = g_mel.contiguous().float() if g_mel is not None else torch.zeros((), device=eng.device)
         eng.backward(gscale_text=gt, gscale_mel=gm)
-        model._after_backward()
+        model._after_backward(in_place)
         if in_place:
             return (None,) * (9 + ctx.nparams)
         return (None,) * 9 + tuple(gviews)
@@ -216,8 +216,31 @@ class UnifiedVoice(nn.Module):
             self._gviews = [gv[n] for n in self._param_names]
         return self._gviews
 
-    def _after_backward(self):
-        pass   # hook point for the data-parallel wrapper (ttts_b200.gpt.train)
+    def enable_flat_allreduce(self, process_group=None, enabled=True):
+        """Data parallelism WITHOUT a DistributedDataParallel wrapper: at the end of every backward the flat gradient buffer is averaged
+        across the process group with ONE all-reduce (NCCL over NVLink / NVSwitch) -- what SURVEY.md 8b asks for in place of DDP's 25 MB
+        buckets (K10).  Under `accelerator.prepare` / DDP leave it off: the wrapper's reducer already averages the (same) gradient views.
+        Gradient accumulation: like the reference's loop (no `no_sync`), every backward reduces."""
+        import torch.distributed as dist
+        if enabled and not (dist.is_available() and dist.is_initialized()):
+            raise L.TTTSError("enable_flat_allreduce needs an initialised torch.distributed process group")
+        self._flat_allreduce = (process_group if process_group is not None else True) if enabled else None
+
+    def _after_backward(self, accumulated=False):
+        pg = getattr(self, "_flat_allreduce", None)
+        if pg is None:
+            return
+        if accumulated:
+            # .grad already held (reduced) gradients that this backward added to: reducing the buffer again would average them twice
+            raise L.TTTSError("enable_flat_allreduce: gradients were accumulated across backward calls; zero_grad(set_to_none=True) between "
+                              "steps, or use ttts_b200.gpt.train.FusedStep(accumulate=n), which reduces once per optimizer step")
+        import torch.distributed as dist
+        group = None if pg is True else pg
+        world = dist.get_world_size(group)
+        if world > 1:
+            g = self._engine().grads
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            g.mul_(1.0 / world)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         # older HF versions stored causal-mask buffers in the checkpoint; they carry no information

@@ -34,7 +34,7 @@ def _protos(lib):
     lib.ttts_conv1d_tcs_weight_elems.argtypes = [i32, i32, i32]
     lib.ttts_conv1d_tcs_weight_elems.restype = ctypes.c_int64
     lib.ttts_conv1d_tcs_prep_weights.argtypes = [vp, vp, i32, i32, i32, vp]
-    lib.ttts_conv1d_tcs.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp]
+    lib.ttts_conv1d_tcs.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32, vp]
     lib.ttts_conv1d_bwd_input.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
     lib.ttts_conv1d_bwd_weight.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.ttts_weight_norm.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -55,8 +55,11 @@ TC_FLAGS = int(os.environ.get("TTTS_CONV_TC_FLAGS", "0"))
 
 
 def tcs_covers(Cin, Cout, K, stride, dil, pad, post, cond):
-    return (stride == 1 and post == 0 and cond is None and 2 * pad == dil * (K - 1) and 128 + 2 * pad <= 184 and Cin % 8 == 0
-            and 16 <= Cin <= 192 and Cout in (32, 64, 96, 128, 192, 384))
+    if not (stride == 1 and 2 * pad == dil * (K - 1) and 128 + 2 * pad <= 184 and Cin % 8 == 0 and 16 <= Cin <= 192):
+        return False
+    if post == 3:
+        return Cout == 384                                    # the WN gate: 192 tanh channels x 192 sigmoid channels
+    return post == 0 and cond is None and Cout in (32, 64, 96, 128, 192, 384)
 
 
 def tcs_weights(w):
@@ -97,7 +100,7 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
     if tc:
         assert tcs_covers(Cin, Cout, K, stride, dil, pad, post, cond), "layer not covered by ttts_conv1d_tcs"
         L.check(lib.ttts_conv1d_tcs(_p(x), _p(tcs_weights(w)), _p(bias), _p(out), B, Cin, Tin, Cout, K, dil, int(pre_lrelu), _p(resid), float(out_scale),
-                                    int(accumulate), _p(mask), TC_FLAGS, L.stream_ptr().value), "ttts_conv1d_tcs")
+                                    int(accumulate), _p(mask), post, _p(cond), cond_ld, TC_FLAGS, L.stream_ptr().value), "ttts_conv1d_tcs")
         return out
     if split:
         L.check(lib.ttts_conv1d_f32_split(_p(x), _p(w), _p(bias), _p(out), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), _p(resid),
