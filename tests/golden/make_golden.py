@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vqvae_full_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_train_masked.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vqvae_full_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -79,6 +79,71 @@ def gpt_case(gm, name, cfg_over, B, TL, CL, text_lengths=None, wav_lengths=None,
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "loss_text %.6f loss_mel %.6f" % (float(loss_text), float(loss_mel)), "->", path, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+def masked_train_masks(cfg, B, T, seed=77, p=0.1):
+    """Seeded keep masks for the four GPT-2 dropout sites (embedding, attention probabilities, attention output, MLP output), in the
+    naming oracle.gpt_oracle.gpt_hidden uses.  Any fixed masks pin the masked oracle to the reference; the CUDA path's own masks come from
+    ttts_gpt_dropout_mask."""
+    g = torch.Generator().manual_seed(seed)
+    d, H = cfg["model_dim"], cfg["heads"]
+    m = {"embd": (torch.rand(B, T, d, generator=g) >= p)}
+    for l in range(cfg["layers"]):
+        m["attn_p%d" % l] = torch.rand(B, H, T, T, generator=g) >= p
+        m["attn_o%d" % l] = torch.rand(B, T, d, generator=g) >= p
+        m["mlp_o%d" % l] = torch.rand(B, T, d, generator=g) >= p
+    return m
+
+
+def gpt_train_masked_case(gm):
+    """The REAL reference in TRAINING mode with the dropout draws replaced by given masks: torch.nn.functional.dropout is patched (for the
+    duration of the call) to multiply by the next mask of the queue -- the order HF's GPT2Model draws them: embedding `drop`, then per layer
+    attention-probability dropout, attention-output `resid_dropout`, MLP `dropout` (eager attention so that the probability dropout is an
+    nn.Dropout call and not inside SDPA; gradient checkpointing off so that nothing is recomputed).  Stores losses, logits and every gradient."""
+    from oracle import gpt_oracle as O
+    cfg = O.default_config(layers=2, model_dim=128, heads=2, max_text_tokens=40, max_mel_tokens=80)
+    params = O.init_params(cfg, seed=0)
+    kw = {k: cfg[k] for k in ("layers", "model_dim", "heads", "max_text_tokens", "max_mel_tokens", "number_text_tokens", "start_text_token",
+                              "number_mel_codes", "start_mel_token", "stop_mel_token")}
+    model = gm.UnifiedVoice(**kw, use_mel_codes_as_input=True, train_solo_embeddings=False, checkpointing=False).train()
+    model.load_state_dict({k: v.clone() for k, v in params.items()})
+    model.gpt.config._attn_implementation = "eager"
+    B, TL, CL = 2, 12, 24
+    T = TL + CL + 4
+    text, tl, codes, wl = O.synthetic_batch(B, TL, CL, seed=1234)
+    masks = masked_train_masks(cfg, B, T)
+    scale = 1.0 / 0.9
+    queue = [masks["embd"]]
+    for l in range(cfg["layers"]):
+        queue += [masks["attn_p%d" % l], masks["attn_o%d" % l], masks["mlp_o%d" % l]]
+    calls = []
+    real = torch.nn.functional.dropout
+
+    def fake(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        mk = queue[len(calls)]
+        calls.append(tuple(x.shape))
+        assert tuple(mk.shape) == tuple(x.shape), (len(calls), mk.shape, x.shape)
+        return x * mk.to(x.dtype) * scale
+    torch.nn.functional.dropout = fake
+    try:
+        loss_text, loss_mel, mel_logits = model(text, tl, codes.clone(), wl)
+        (0.01 * loss_text + loss_mel).backward()
+    finally:
+        torch.nn.functional.dropout = real
+    assert len(calls) == len(queue), (len(calls), len(queue))
+    out = dict(cfg_json=np.array(repr(cfg)), seed=0, mask_seed=77, B=B, TL=TL, CL=CL, text=text.numpy(), text_lengths=tl.numpy(), codes=codes.numpy(),
+               wav_lengths=wl.numpy(), loss_text=loss_text.detach().numpy(), loss_mel=loss_mel.detach().numpy(), mel_logits=mel_logits.detach().numpy())
+    for k, mk in masks.items():
+        out["mask/" + k] = np.packbits(mk.numpy().reshape(-1))
+        out["mshape/" + k] = np.array(mk.shape)
+    for k, prm in model.named_parameters():
+        out["grad/" + k] = prm.grad.detach().numpy()
+    path = os.path.join(ROOT, "tests", "golden", "gpt_train_masked.npz")
+    np.savez_compressed(path, **out)
+    print("gpt_train_masked loss_text %.6f loss_mel %.6f (%d dropout calls) ->" % (float(loss_text), float(loss_mel), len(calls)), path,
+          "%.1f KB" % (os.path.getsize(path) / 1e3))
 
 
 def generate_case(gm):
@@ -575,6 +640,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decoder":
         decoder_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "train_masked":
+        gpt_train_masked_case(gm)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "generate":
         generate_case(gm)
         sys.exit(0)
@@ -603,6 +671,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_case()
         sys.exit(0)
+    gpt_train_masked_case(gm)
     generate_case(gm)
     kv_case(gm)
     decoder_case()

@@ -38,6 +38,25 @@ def test_oracle_matches_reference_golden(golden_dir, name):
         assert np.linalg.norm(g.numpy() - ref) / denom < 2e-5, k
 
 
+def test_masked_oracle_matches_reference_in_training_mode(golden_dir):
+    """TRAINING mode: the oracle with keep masks at the four GPT-2 dropout sites == the REAL reference in train() with exactly those masks
+    injected in place of its dropout draws (tests/golden/make_golden.py::gpt_train_masked_case: eager attention, no gradient checkpointing).
+    This pins the mask-taking oracle that tests/test_gpu_gpt.py::test_training_mode_step_matches_oracle_with_exported_masks checks the
+    CUDA step against (there with the masks the kernels drew themselves)."""
+    z, cfg = _load(golden_dir, "gpt_train_masked")
+    params = O.init_params(cfg, seed=int(z["seed"]))
+    masks = {k[5:]: torch.tensor(np.unpackbits(z[k])[:int(np.prod(z["mshape/" + k[5:]]))].reshape(z["mshape/" + k[5:]])) for k in z.files if k.startswith("mask/")}
+    args = (torch.tensor(z["text"]), torch.tensor(z["text_lengths"]), torch.tensor(z["codes"]), torch.tensor(z["wav_lengths"]))
+    lt, lm, logits, grads = O.loss_and_grads(params, cfg, *args, masks=masks, drop_scale=1.0 / 0.9)
+    assert abs(float(lt) - float(z["loss_text"])) < 2e-6 and abs(float(lm) - float(z["loss_mel"])) < 2e-6
+    np.testing.assert_allclose(logits.numpy(), z["mel_logits"], rtol=0, atol=2e-5)
+    for k, g in grads.items():
+        ref = z["grad/" + k]
+        assert np.linalg.norm(g.numpy() - ref) / (np.linalg.norm(ref) + 1e-12) < 2e-5, k
+    lt0, lm0, _ = O.forward(params, cfg, *[a.clone() for a in args])
+    assert abs(float(lm0) - float(z["loss_mel"])) > 1e-3                 # the masks matter
+
+
 def test_bf16_emulation_is_close_to_fp32(golden_dir):
     z, cfg = _load(golden_dir, "gpt_tiny")
     params = O.init_params(cfg, seed=int(z["seed"]))

@@ -16,7 +16,7 @@ xn = np.ascontiguousarray(enc["x"].transpose(0, 2, 1)).reshape(-1, 192)
 margin = V.vq_margin(xn, enc["E"], enc["codes"].reshape(-1))
 flips = out["codes"].cpu().numpy().reshape(-1) != enc["codes"].reshape(-1)
 print("TTTS_CONV_TC=%s  rel: ge %.2e m %.2e logs %.2e z %.2e x %.2e | code flips %d (largest margin among flips %.2e; smallest margin overall %.2e)" % (
-    os.environ.get("TTTS_CONV_TC", "0"), rel(out["ge"], enc["ge"]), rel(out["m"], enc["m"]), rel(out["logs"], enc["logs"]), rel(out["z"], enc["z"]),
+    os.environ.get("TTTS_CONV_TC", "1"), rel(out["ge"], enc["ge"]), rel(out["m"], enc["m"]), rel(out["logs"], enc["logs"]), rel(out["z"], enc["z"]),
     rel(out["x"], enc["x"]), int(flips.sum()), float(margin[flips].max()) if flips.any() else 0.0, float(margin.min())), flush=True)
 g = torch.Generator(device="cuda").manual_seed(1234)
 wav = torch.clamp(0.1 * torch.randn(64, 23040, device="cuda", generator=g), -1, 1)

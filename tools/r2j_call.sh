@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+T=r2j
+timeout 90 python -m pytest tests/test_gpu_encoder.py -m gpu -q -x -k "conv1d_tcs" > gpurun_out/${T}_pytest_tcs.log 2>&1; rc=$?; tail -3 gpurun_out/${T}_pytest_tcs.log | cut -c1-400
+if [ $rc -ne 0 ]; then echo "conv1d_tcs unit tests failed (rc=$rc): stopping"; grep -h "Error\|assert" gpurun_out/${T}_pytest_tcs.log | head; exit 1; fi
+(timeout 120 python tools/enc_tc_check.py) 2>&1 | grep -v Warning | tee gpurun_out/${T}_enc_tc_check.txt | cut -c1-400
+ONLY=enc ITERS=2 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${T}_launches_vqenc_tc.csv python tools/kernels_ab.py > gpurun_out/${T}_ncu_enc.log 2>&1
+python tools/summarize_launches.py gpurun_out/${T}_launches_vqenc_tc.csv > gpurun_out/${T}_launches_vqenc_tc_summary.txt 2>&1; head -8 gpurun_out/${T}_launches_vqenc_tc_summary.txt
+timeout 400 python -m pytest tests/test_gpu_encoder.py -m gpu -q -rf > gpurun_out/${T}_pytest_encoder.log 2>&1; echo "== encoder rc=$?"; tail -3 gpurun_out/${T}_pytest_encoder.log | cut -c1-300
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log

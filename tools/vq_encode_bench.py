@@ -56,8 +56,8 @@ def run(hbm_gbs=6570.3, with_cpu=False, bf16_tflops=1638.6):
     from ttts_b200.vqvae import encoder as ENC
     from ttts_b200 import _lib as L
     import ctypes
-    out["conv_path"] = "conv1d_tcs (split-bf16 tcgen05, TTTS_CONV_TC=1)" if ENC.USE_TC else "fp32 CUDA-core kernels (TTTS_CONV_TC=0)"
-    if ENC.USE_TC:
+    out["conv_path"] = "conv1d_tcs (split-bf16 tcgen05; default)" if enc.conv_tc else "fp32 CUDA-core kernels (TTTS_CONV_TC=0)"
+    if enc.conv_tc:
         lib = L.lib()
         enc(wav); torch.cuda.synchronize()
         lib.ttts_prof_gemm_enable(5)

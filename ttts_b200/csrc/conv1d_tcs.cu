@@ -29,10 +29,11 @@
 
 namespace ttts {
 
-constexpr int TCS_ATOM_ROWS = 184;                       // 128 + 2 * 25 (kernel 11, dilation 5) rounded up to 8 rows
-constexpr int TCS_ATOM_BYTES = TCS_ATOM_ROWS * 128;      // one [rows x 64 bf16] atom column
+constexpr int TCS_MAX_ROWS = 184;                        // 128 + 2 * 25 (kernel 11, dilation 5) rounded up to 8 rows
 constexpr int TCS_MAX_STAGES = 8;                       // weight-tile ring: as many stages as fit (small tiles are latency-, not bandwidth-bound)
-constexpr int TCS_THREADS = 192;                         // warps 0-3: transform + epilogue (TMEM lane quadrant = warp), 4: MMA, 5: TMA
+constexpr int TCS_WORKERS = 8;                           // worker warps: stage the window (thread = window row), then the epilogue (TMEM lane
+                                                         // quadrant = warp & 3, the two warps of a quadrant take alternate 16-column chunks)
+constexpr int TCS_THREADS = (TCS_WORKERS + 2) * 32;      // + warp 8: MMA issuer, warp 9: weight TMA
 
 struct ConvTcsParams {
     const float* x; const float* bias; float* y; const float* resid; const float* mask;
@@ -42,6 +43,7 @@ struct ConvTcsParams {
     int A;                 // ci atoms = ceil(Cin / 64)
     int NT;                // output channels per CTA
     int wrows;             // window rows = 128 + 2 * pad
+    int arows;             // rows of an atom column in shared memory: wrows rounded up to 8 (atom stride arows * 128 B is a multiple of 1024)
     int pre_lrelu, accumulate, base_off;
     int stages;            // weight ring depth, 2 .. TCS_MAX_STAGES
     int gated;             // WN gate (post = 3): Cout = 2 H, output channel c = tanh(a_c + cond_c) * sigmoid(g_c + cond_{H + c}), a = rows [0, H), g = rows [H, 2H)
@@ -59,12 +61,12 @@ TTTS_DEVICE uint64_t tcs_desc(uint32_t saddr, int base_off) {
 struct TcsSmem {
     static constexpr int oBar = 0;                                    // mbarriers + tmem holder (256 B)
     static constexpr int oX = 1024;                                   // [hi | lo][A atoms][184 rows][128 B]
-    static size_t x_bytes(int A) { return (size_t)2 * A * TCS_ATOM_BYTES; }
+    static size_t x_bytes(int A, int arows) { return (size_t)2 * A * arows * 128; }
     static size_t w_stage_bytes(int NT) { return (size_t)2 * NT * 128; }
-    static size_t total(int A, int NT, int stages) { return 1024 + x_bytes(A) + stages * w_stage_bytes(NT) + 1024; }
+    static size_t total(int A, int arows, int NT, int stages) { return 1024 + x_bytes(A, arows) + stages * w_stage_bytes(NT) + 1024; }
 };
 
-__global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_constant__ CUtensorMap tmW, const ConvTcsParams p) {
+__global__ void __launch_bounds__(TCS_THREADS, 2) conv1d_tcs_kernel(const __grid_constant__ CUtensorMap tmW, const ConvTcsParams p) {
     extern __shared__ uint8_t tcs_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcs_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcsSmem::oBar);
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
     uint64_t* acc_full = bars + 2 * TCS_MAX_STAGES + 3;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TCS_MAX_STAGES + 4);
     const int TCS_STAGES = p.stages;
+    const uint32_t TCS_ATOM_BYTES = (uint32_t)p.arows * 128u;             // one [rows x 64 bf16] atom column
     const uint32_t sX = smem_u32(smem + TcsSmem::oX);
     const uint32_t sXlo = sX + p.A * TCS_ATOM_BYTES;
     const uint32_t sW = sX + 2 * p.A * TCS_ATOM_BYTES;
@@ -87,18 +90,18 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int a = 0; a < 3; ++a) mbar_init(&x_full[a], 4);
+        for (int a = 0; a < 3; ++a) mbar_init(&x_full[a], TCS_WORKERS);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_holder, tmem_cols);
+    if (warp == TCS_WORKERS) tmem_alloc(tmem_holder, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const int n_kb = p.K * p.A;                    // weight tiles: (tap, ci atom)
 
-    if (warp == 5) {
+    if (warp == TCS_WORKERS + 1) {
         // ---------------- TMA: weight tiles [NT co][64 ci], hi then lo, one stage per (tap, atom) ----------------
         for (int it = 0; it < n_kb; ++it) {
             const int s = it % TCS_STAGES;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
             }
             __syncwarp();
         }
-    } else if (warp == 4) {
+    } else if (warp == TCS_WORKERS) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = make_idesc_bf16(128, p.NT, false, false);
         uint32_t first = 1;
@@ -152,76 +155,70 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
         }
     } else {
         // ---------------- workers: stage the window (channel-last, hi / lo), then the epilogue ----------------
-        const int tid = threadIdx.x;                                         // 0 .. 127
-        // row bookkeeping of this thread's (up to) two window rows
-        int rb[2], rt[2]; bool rok[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int j = q * 128 + tid;
-            const int gi = g0 - p.pad + j;
-            bool ok_ = (j < p.wrows) && gi >= 0 && gi < p.rows;
+        const int tid = threadIdx.x;                                         // 0 .. 255 = window row
+        {
+            const int j = tid;
+            const int gi = g0 - p.pad + j;                                   // packed input row
+            bool row_ok = (j < p.wrows) && gi >= 0 && gi < p.rows;
             int b_ = 0, t_ = 0;
-            if (ok_) { b_ = (int)__umulhi((uint32_t)gi, p.p_magic); if (p.P == 1) b_ = gi; t_ = gi - b_ * p.P; ok_ = t_ < p.T; }
-            rb[q] = b_; rt[q] = t_; rok[q] = ok_;
-        }
-        for (int a = 0; a < p.A; ++a) {                                      // atom by atom: the MMA warp starts on atom 0 while 1, 2 are staged
+            if (row_ok) { b_ = (int)__umulhi((uint32_t)gi, p.p_magic); if (p.P == 1) b_ = gi; t_ = gi - b_ * p.P; row_ok = t_ < p.T; }
+            const float* xp = p.x + ((size_t)b_ * p.Cin) * p.T + t_;
+            for (int a = 0; a < p.A; ++a) {                                  // atom by atom: the MMA warp starts on atom 0 while 1, 2 are staged
+                if (j < p.arows) {
+                    // four 8-channel groups per iteration: 32 independent loads in flight per thread (the loads of a channel are coalesced
+                    // across the warp: consecutive lanes = consecutive frames)
+                    for (int cg = a * 8; cg < a * 8 + 8; cg += 4) {
+                        float v[32];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int j = q * 128 + tid;                                 // window row
-                if (j >= TCS_ATOM_ROWS) continue;
-                const bool row_ok = rok[q];
-                const float* xp = p.x + ((size_t)rb[q] * p.Cin) * p.T + rt[q];
-                // two 8-channel groups per iteration: 16 independent loads in flight per thread (the loads of a group are coalesced across
-                // the warp: consecutive lanes = consecutive frames of one channel)
-                for (int cg = a * 8; cg < a * 8 + 8; cg += 2) {
-                    float v[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int ci = cg * 8 + e;
-                        v[e] = (row_ok && ci < p.Cin) ? __ldg(xp + (size_t)ci * p.T) : 0.f;
-                    }
-                    if (p.pre_lrelu) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
-                    }
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float h0 = bf16_round(v[h2 * 8 + 2 * e]), h1 = bf16_round(v[h2 * 8 + 2 * e + 1]);
-                            hi[e] = pack_bf16(h0, h1);
-                            lo[e] = pack_bf16(v[h2 * 8 + 2 * e] - h0, v[h2 * 8 + 2 * e + 1] - h1);
+                        for (int e = 0; e < 32; ++e) {
+                            const int ci = cg * 8 + e;
+                            v[e] = (row_ok && ci < p.Cin) ? __ldg(xp + (size_t)ci * p.T) : 0.f;
                         }
-                        const int c = cg + h2;
-                        const uint32_t off = (uint32_t)(c >> 3) * TCS_ATOM_BYTES + (uint32_t)j * 128u + ((uint32_t)((c ^ j) & 7) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+                        if (p.pre_lrelu) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
+                        }
+#pragma unroll
+                        for (int h4 = 0; h4 < 4; ++h4) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float h0 = bf16_round(v[h4 * 8 + 2 * e]), h1 = bf16_round(v[h4 * 8 + 2 * e + 1]);
+                                hi[e] = pack_bf16(h0, h1);
+                                lo[e] = pack_bf16(v[h4 * 8 + 2 * e] - h0, v[h4 * 8 + 2 * e + 1] - h1);
+                            }
+                            const int c = cg + h4;
+                            const uint32_t off = (uint32_t)(c >> 3) * TCS_ATOM_BYTES + (uint32_t)j * 128u + ((uint32_t)((c ^ j) & 7) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+                        }
                     }
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_full[a]);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&x_full[a]);
         }
 
         // epilogue: thread = packed output row g0 + tid = TMEM lane
-        const int g = g0 + tid;
+        const int quad = warp & 3, half = warp >> 2;                         // TMEM lane quadrant; which of the alternating 16-column chunks
+        const int g = g0 + quad * 32 + lane;
         bool ok = g < p.rows;
         int b = 0, t = 0;
         if (ok) { b = (int)__umulhi((uint32_t)g, p.p_magic); if (p.P == 1) b = g; t = g - b * p.P; ok = t < p.T; }
         const float mk = (ok && p.mask) ? p.mask[(size_t)b * p.T + t] : 1.f;
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         if (p.gated) {
             const int hN = p.NT / 2, H = p.Cout / 2, cbase = blockIdx.y * hN;
             const float* cnd = (ok && p.cond) ? p.cond + (size_t)b * p.cond_ld : nullptr;
-            for (int c0 = 0; c0 < hN; c0 += 16) {
+            for (int c0 = half * 16; c0 < hN; c0 += 32) {
                 uint32_t ra[16], rg[16];
                 __syncwarp();
                 tmem_ld_32x16(tmem_base + lane_off + c0, ra);
                 tmem_ld_32x16(tmem_base + lane_off + hN + c0, rg);
+                tmem_ld_wait();                   // .sync.aligned: must be executed by the converged warp, never inside the `ok` branch
                 if (ok) {
                     float ba[16], bg[16], res[16], old[16];
 #pragma unroll
@@ -234,7 +231,6 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
                         res[i] = (p.resid && cok) ? __ldg(p.resid + o) : 0.f;
                         old[i] = (p.accumulate && cok) ? p.y[o] : 0.f;
                     }
-                    tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int c = cbase + c0 + i;
@@ -244,15 +240,14 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
                             p.y[((size_t)b * H + c) * p.T + t] = old[i] + (v + res[i]) * (p.out_scale * mk);
                         }
                     }
-                } else {
-                    tmem_ld_wait();
                 }
             }
         } else {
-        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+        for (int c0 = half * 16; c0 < p.NT; c0 += 32) {
             uint32_t r[16];
             __syncwarp();
             tmem_ld_32x16(tmem_base + lane_off + c0, r);
+            tmem_ld_wait();                       // .sync.aligned: converged warp only (r2f: inside the divergent `ok` branch it deadlocked)
             if (ok) {
                 // every load of the chunk is issued before the first store: written load -> store -> load per channel the compiler must keep
                 // that order (y may alias resid for all it knows) and a 32-channel tile becomes a chain of 32 dependent DRAM round trips
@@ -266,13 +261,10 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
                     old[i] = (p.accumulate && cok) ? p.y[o0 + (size_t)i * p.T] : 0.f;
                     bs[i] = (p.bias && cok) ? __ldg(p.bias + n0 + c0 + i) : 0.f;
                 }
-                tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (n0 + c0 + i < p.Cout) p.y[o0 + (size_t)i * p.T] = old[i] + (__uint_as_float(r[i]) + bs[i] + res[i]) * (p.out_scale * mk);
                 }
-            } else {
-                tmem_ld_wait();
             }
         }
         }
@@ -280,7 +272,7 @@ __global__ void __launch_bounds__(TCS_THREADS) conv1d_tcs_kernel(const __grid_co
     }
     __syncthreads();
     tc_fence_after();
-    if (warp == 4) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
+    if (warp == TCS_WORKERS) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // w [Cout][Cin][K] fp32  ->  ws [K][A][hi | lo][Cout][64] bf16 (ci >= Cin: zero)
@@ -315,7 +307,7 @@ int conv_tcs_prep_weights(const float* w, void* ws, int Cout, int Cin, int K, cu
 
 bool conv_tcs_covers(int Cin, int Cout, int K, int stride, int dil, int pad, int post) {
     if (stride != 1 || !(post == 0 || (post == 3 && Cout == 384)) || K < 1 || dil < 1) return false;
-    if (pad * 2 != dil * (K - 1) || 128 + 2 * pad > TCS_ATOM_ROWS) return false;
+    if (pad * 2 != dil * (K - 1) || 128 + 2 * pad > TCS_MAX_ROWS) return false;
     if (Cin % 8 != 0 || Cin < 16 || Cin > 192) return false;
     if (!(Cout == 32 || Cout == 64 || Cout == 96 || Cout == 128 || Cout == 192 || Cout == 384)) return false;
     return true;
@@ -337,6 +329,7 @@ int conv1d_tcs(const float* x, const void* ws, const float* bias, float* y, int 
     p.NT = Cout <= 128 ? Cout : 96;
     p.gated = post == 3; p.cond = cond; p.cond_ld = cond_ld;
     p.wrows = 128 + 2 * pad;
+    p.arows = (p.wrows + 7) & ~7;
     p.pre_lrelu = pre_lrelu; p.accumulate = accumulate; p.base_off = base_off; p.out_scale = out_scale;
     p.p_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.P - 1) / (uint64_t)p.P);
     CUtensorMap tm;
@@ -346,12 +339,17 @@ int conv1d_tcs(const float* x, const void* ws, const float* bias, float* y, int 
     // ring depth: what fits next to the window, at most one stage per weight tile; shallow for the big tiles so that 2 CTAs share an SM
     const int n_kb = K * p.A;
     int stages = TCS_MAX_STAGES;
-    while (stages > 2 && (stages > n_kb || TcsSmem::total(p.A, p.NT, stages) > (p.A == 1 ? 110 : 227) * 1024)) --stages;
+    // single-atom layers (level 0 / 1: thousands of small CTAs, DRAM-latency-bound): 2 CTAs per SM (the register file allows no more at
+    // 320 threads x 96 registers); the others: as deep as fits
+    while (stages > 2 && (stages > n_kb || TcsSmem::total(p.A, p.arows, p.NT, stages) > (p.A == 1 ? 110 : 227) * 1024)) --stages;
     p.stages = stages;
-    const size_t smem = TcsSmem::total(p.A, p.NT, stages);
+    const size_t smem = TcsSmem::total(p.A, p.arows, p.NT, stages);
     static size_t attr = 0;
     if (smem > attr) {
         TTTS_CUDA(cudaFuncSetAttribute(conv1d_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        // r2h capture: 70 KB per CTA and still ONE CTA per SM -- 133 registers x 320 threads (now capped by the launch bounds) and a
+        // shared-memory carve-out sized for one block; ask for the full carve-out so that 2 - 3 of the small CTAs share an SM
+        TTTS_CUDA(cudaFuncSetAttribute(conv1d_tcs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         attr = 227 * 1024;
     }
     TTTS_CHECK_ARG(smem <= 227 * 1024, "conv1d_tcs: shared memory");

@@ -104,6 +104,17 @@ class FusedStep:
         self._micro = (self._micro + 1) % self.accumulate
         return eng.losses
 
+    def skip_micro_step(self):
+        """A micro-step without a batch (the collater dropped every sample): contributes a zero gradient, keeps the micro-step counter and
+        the collective schedule in phase with the other ranks."""
+        eng = self.eng
+        if self._micro == 0:
+            eng.grads.zero_()
+        last = (self._micro == self.accumulate - 1)
+        if self.world > 1 and last:
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        self._micro = (self._micro + 1) % self.accumulate
+
     def optimizer_step(self):
         """get_grad_norm + clip_grad_norm_(max_norm) + AdamW + scheduler.step (ttts/gpt/train.py:114-120)."""
         eng = self.eng
@@ -125,9 +136,15 @@ class FusedStep:
 
 
 def cycle(dl):
+    """the reference's `cycle` (ttts/gpt/train.py:32-35), plus `sampler.set_epoch` so that a DistributedSampler reshuffles every epoch"""
+    epoch = 0
     while True:
+        sampler = getattr(dl, "sampler", None)
+        if hasattr(sampler, "set_epoch"):
+            sampler.set_epoch(epoch)
         for data in dl:
             yield data
+        epoch += 1
 
 
 class Trainer(object):
@@ -186,17 +203,20 @@ class Trainer(object):
         Returns (total_loss: float, loss_text, loss_mel, grad_norm) -- the last three are device tensors."""
         total_loss = 0.0
         losses = norm = None
-        for _ in range(self.gradient_accumulate_every):
+        for i in range(self.gradient_accumulate_every):
+            if i > 0:
+                data = next(self.dataloader)                 # one batch per micro-step, fetched at the top like the reference (train.py:100)
             if data is None:
+                # every sample of the batch was dropped (train.py:101-102 `continue`).  The micro-step still counts: the all-reduce of the
+                # last micro-step must be issued on every rank, or the ranks that did get a batch wait for this one forever.
+                self.fused.skip_micro_step()
                 continue
             inp = [data["padded_text"], data["text_lengths"], data["padded_qmel"], data["wav_lens"]]
             inp = [d.to(self.device, non_blocking=True) for d in inp]
             losses = self.fused.micro_step(*inp)
             lt, lm = losses.tolist()                         # the reference's loss.item() (train.py:111)
             total_loss += (lt * self.text_loss_weight + lm * self.mel_loss_weight) / self.gradient_accumulate_every
-            if self.gradient_accumulate_every > 1:
-                data = next(self.dataloader)
-        if losses is not None:
+        if losses is not None or self.fused.world > 1:
             norm = self.fused.optimizer_step()
         return total_loss, losses, norm
 

@@ -49,8 +49,9 @@ def _p(t):
     return t.data_ptr() if t is not None else None
 
 
-# TTTS_CONV_TC=1: route every convolution the tensor-core kernel covers (csrc/conv1d_tcs.cu) to it; 0: the exact-fp32 CUDA-core kernels
-USE_TC = os.environ.get("TTTS_CONV_TC", "0") == "1"
+# True while a VQEncoder forward with `conv_tc` set runs: every convolution the tensor-core kernel covers (csrc/conv1d_tcs.cu) goes to it.
+# Everything else that calls conv1d() -- the training tape (ttts_b200/vqvae/train_*.py), the per-kernel tests -- keeps the exact-fp32 kernels.
+USE_TC = False
 TC_FLAGS = int(os.environ.get("TTTS_CONV_TC_FLAGS", "0"))
 
 
@@ -68,7 +69,7 @@ def tcs_weights(w):
     state = (w.data_ptr(), w._version, tuple(w.shape))
     capturing = torch.cuda.is_current_stream_capturing()
     hit = getattr(w, "_ttts_tcs", None)
-    if hit is not None and hit[0] == state and not capturing:
+    if hit is not None and hit[0] == state:                # also while a CUDA graph is being captured: the cached tensor predates the capture
         return hit[1]
     lib = L.lib(); _protos(lib)
     Cout, Cin, K = w.shape
@@ -138,7 +139,7 @@ def weight_norm_apply(v, g):
     state = (v.data_ptr(), g.data_ptr(), v._version, g._version, tuple(v.shape))
     capturing = torch.cuda.is_current_stream_capturing()
     hit = getattr(v, "_ttts_wn", None)
-    if hit is not None and hit[0]() is g and hit[1] == state and not capturing:
+    if hit is not None and hit[0]() is g and hit[1] == state:      # also under graph capture (entries are only WRITTEN outside a capture)
         return hit[2]
     lib = L.lib(); _protos(lib)
     w = torch.empty_like(v)
@@ -264,6 +265,19 @@ class ResBlock1(nn.Module):
         return x
 
 
+def _halves(t, H):
+    """(t[:H], t[H:]) as contiguous tensors, cached ON the tensor object `t` (address + version checked): the WN res / skip halves are
+    sliced out of one weight every call, and a fresh slice would defeat the per-tensor caches (split-bf16 weights) downstream."""
+    state = (t.data_ptr(), t._version, tuple(t.shape))
+    hit = getattr(t, "_ttts_halves", None)
+    if hit is not None and hit[0] == state:
+        return hit[1], hit[2]
+    lo, hi = t[:H].detach().contiguous(), t[H:].detach().contiguous()
+    if not torch.cuda.is_current_stream_capturing():
+        t._ttts_halves = (state, lo, hi)
+    return lo, hi
+
+
 class WN(nn.Module):
     """ttts/vqvae/modules.py:136-221 (gated dilated convs with global conditioning)."""
 
@@ -293,8 +307,10 @@ class WN(nn.Module):
             acts = conv1d(x, il.weight(), il.bias, dil=il.dil, pad=il.pad, post=3, cond=cond)
             w = rs.weight()
             if i < self.n_layers - 1:
-                conv1d(acts, w[H:].contiguous(), rs.bias[H:].contiguous(), out=output, accumulate=True)
-                x = conv1d(acts, w[:H].contiguous(), rs.bias[:H].contiguous(), resid=x, mask=mask2)
+                w_res, w_skip = _halves(w, H)                      # cached on the tensor: the halves (and their split-bf16 forms) are made once
+                b_res, b_skip = _halves(rs.bias, H)
+                conv1d(acts, w_skip, b_skip, out=output, accumulate=True)
+                x = conv1d(acts, w_res, b_res, resid=x, mask=mask2)
             else:
                 conv1d(acts, w, rs.bias, out=output, accumulate=True)
         return output * x_mask
@@ -476,8 +492,20 @@ class VQEncoder(nn.Module):
         self.quantizer = ResidualVectorQuantizer(dimension=inter_channels, n_q=1, bins=1024)
         self.proj = _Conv(inter_channels, inter_channels, 2, stride=2)
 
+    # convolutions of the extraction / eval forward on the tcgen05 tensor cores with split-bf16 operands (conv1d_tcs: ~1.3e-5 of the fp32
+    # reference, codes identical on the golden clips, 2.2x faster).  TTTS_CONV_TC=0 (or `encoder.conv_tc = False`) = exact-fp32 kernels.
+    conv_tc = os.environ.get("TTTS_CONV_TC", "1") != "0"
+
     @torch.no_grad()
     def forward(self, wav, lengths=None, eps=None, sample=False):
+        global USE_TC
+        prev, USE_TC = USE_TC, bool(self.conv_tc)
+        try:
+            return self._forward(wav, lengths, eps, sample)
+        finally:
+            USE_TC = prev
+
+    def _forward(self, wav, lengths=None, eps=None, sample=False):
         """wav [B, L] fp32 (L a multiple of hop).  Returns dict(spec, ge, z, m, logs, x, codes [1,B,N], quantized).
         Posterior noise: the reference draws `randn_like(m)` even in eval (vq2.py:744).  Pass `eps` [B,192,T] to fix it (parity tests),
         `sample=True` to draw it here with torch's generator (reference behaviour), or neither for the deterministic z = m encode
@@ -520,7 +548,7 @@ class VQEncoder(nn.Module):
     def encode_graphed(self, wav):
         """Extraction fast path: the whole wav -> codes forward (≈ 350 small launches) captured once per input shape in a
         CUDA graph and replayed (streams + graphs instead of a tracing compiler).  Returns codes [1, B, N] (a static buffer)."""
-        key = tuple(wav.shape)
+        key = tuple(wav.shape) + (bool(self.conv_tc),)
         st = getattr(self, "_graphs", None)
         if st is None:
             st = self._graphs = {}

@@ -29,9 +29,12 @@ class GeneratorStep:
         self.dec = DecoderGraph(K, params_g, self.tape, "dec.")
         self.disc = DiscriminatorGraph(K, params_d, self.tape)
 
-    def synthesize(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+    def synthesize(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames, wav_aug=None, spec_aug=None):
         """SynthesizerTrn.forward (vq2.py:843-871) and the losses that do not involve the discriminators.
-        wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav); wav_aug = wav), lengths [B] frames, text [B,Tt] int64, codebook [1024,192]
+        wav [B,L], spec [B,1025,T] (= spectrogram_torch(wav)); wav_aug / spec_aug: the augmented waveform and its spectrogram that `enc_p`
+        sees when the quantizer is not frozen (train.py:330-345, vq2.py:849; default = wav / spec, the `freeze_quantizer` branch and the
+        benchmark's aug = identity; the Praat augmentation itself is CPU third-party code, SURVEY.md section 2).  The TextEncoder's
+        p = 0.1 dropouts are not drawn (eval semantics).  lengths [B] frames, text [B,Tt] int64, codebook [1024,192]
         (or, with the CUDA backend, the EuclideanCodebook module: its EMA buffers are then updated like in the reference's training forward),
         eps_p / eps_q [B,192,T] posterior noises, ids_slice [B] segment starts (frames)."""
         o, enc = self.ops, self.enc
@@ -39,8 +42,10 @@ class GeneratorStep:
         dev = spec.device
         mask2 = (torch.arange(T, device=dev)[None, :] < lengths[:, None]).float().contiguous()
         specv, wavv = Var(spec.contiguous()), Var(wav.unsqueeze(1).contiguous())
+        spec_p = specv if spec_aug is None else Var(spec_aug.contiguous())
+        wav_p = wavv if wav_aug is None else Var(wav_aug.unsqueeze(1).contiguous())
         ge = enc.mel_style_encoder(Var(self.K.mul_mask(spec.contiguous(), mask2)), mask2, lengths)            # vq2.py:847
-        x, _ = enc.posterior_audio_encoder(specv, wavv, mask2, ge, eps_p, "enc_p.")                           # :849 (the noisy sample feeds proj)
+        x, _ = enc.posterior_audio_encoder(spec_p, wav_p, mask2, ge, eps_p, "enc_p.")                         # :849 (the noisy sample feeds proj)
         x = o.conv(x, enc.P["proj.weight"], enc.P["proj.bias"], stride=2)                                     # :851
         quantized, commit, codes = o.vq(x, codebook)                                                          # :852-853
         q_up = o.upsample2(quantized)                                                                         # :854-856
@@ -70,9 +75,9 @@ class GeneratorStep:
         out.update(loss_gen=loss_gen, loss_fm=loss_fm, total=total)
         return out
 
-    def forward(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+    def forward(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames, wav_aug=None, spec_aug=None):
         """synthesize + adversarial with the discriminators unchanged in between.  Returns the dict of loss Vars."""
-        self.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames)
+        self.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames, wav_aug, spec_aug)
         return self.adversarial()
 
     def backward(self):
@@ -148,10 +153,10 @@ class TrainStep:
         opt = optimizer if optimizer is not None else FlatAdamW
         self.opt_g, self.opt_d = opt(params_g, lr), opt(params_d, lr)
 
-    def step(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames):
+    def step(self, wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames, wav_aug=None, spec_aug=None):
         Pg, Pd = self.opt_g.params(), self.opt_d.params()
         gen = GeneratorStep(self.K, Pg, Pd)
-        out = gen.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames)
+        out = gen.synthesize(wav, spec, lengths, text, text_lengths, codebook, eps_p, eps_q, ids_slice, segment_frames, wav_aug, spec_aug)
         dgraph = DiscriminatorGraph(self.K, Pd)
         real, _ = dgraph.forward(out["y_seg"])
         fake, _ = dgraph.forward(out["y_hat"].v)                      # .detach(): a constant for the discriminator step
