@@ -251,7 +251,7 @@ int ttts_stft_mel(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t
                   const float* twiddle, float eps_inside, float* spec_out, int32_t n_mels, const int32_t* band_lo,
                   const int32_t* band_off, const float* band_w, float log_floor, float* mel_out, int32_t n_frames, void* stream);
 /* backward of ttts_stft_mel's mel_out with respect to the waveform (the mel-reconstruction loss of the VQ-VAE-GAN step differentiates through
- * mel_spectrogram_torch(y_hat), ttts/vqvae/train.py:357-366,389; csrc/stft_bwd.cu -- written without hardware, CPU-emulation-validated).
+ * mel_spectrogram_torch(y_hat), ttts/vqvae/train.py:357-366,389; csrc/stft_bwd.cu; GPU-tested through the generator step since r2a).
  * dwav [B, L] ACCUMULATES (zero it first); dlogmel [B, n_mels, n_frames]. */
 int ttts_stft_mel_bwd(const float* wav, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t pad, const float* window, float eps_inside,
                       int32_t n_mels, const int32_t* band_lo, const int32_t* band_off, const float* band_w, float log_floor,
@@ -282,8 +282,8 @@ int ttts_conv1d_tcs_prep_weights(const float* w, void* ws_bf16, int32_t Cout, in
 int ttts_conv1d_tcs(const float* x, const void* ws_bf16, const float* bias, float* y, int32_t B, int32_t Cin, int32_t T, int32_t Cout, int32_t K,
                     int32_t dil, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate, const float* mask, int32_t post,
                     const float* cond, int32_t cond_ld, int32_t flags, void* stream);
-/* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- written without hardware, validated on the CPU
- * emulation of the source only).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
+/* Backward of that convolution (autograd of nn.Conv1d; next scope row, SURVEY.md 8f-1 -- first developed on the CPU
+ * emulation of the source, GPU-tested against torch.autograd since r2a).  dy [B,Cout,Tout] is the gradient of the raw convolution output (before any fused post / residual).
  *   bwd_input : dx[B,Cin,Tin] (+)= lrelu'(x) * conv_transpose(dy, w)      x only read when pre_lrelu (the forward's input)
  *   bwd_weight: dw[Cout,Cin,K] += dy (*) lrelu(x) ; db[Cout] += sum dy (db may be NULL).  Gradients ACCUMULATE: zero them first. */
 int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float* dx, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
@@ -307,7 +307,7 @@ int ttts_masked_mean(const float* x, const int64_t* lens, float* y, int32_t B, i
 int ttts_posterior_sample(const float* stats, const float* eps, const float* mask, float* z, int32_t B, int32_t C, int32_t T, void* stream);
 
 /* --------------------------------------------------------------------------------------------
- * Training kernels of the VQ-VAE encode half (next scope row; csrc/encoder_bwd.cu -- written without hardware,
+ * Training kernels of the VQ-VAE encode half (next scope row; csrc/encoder_bwd.cu -- developed on the CPU emulation, GPU-tested since r2a,
  * validated on the CPU emulation of the source against tests/ref_kernels.py).  fp32, [B, C, T] channel-major.
  * ------------------------------------------------------------------------------------------ */
 int ttts_ew_add(const float* a, const float* b, float* o, int64_t n, void* stream);

@@ -206,3 +206,32 @@ def test_stft_linearity_and_batch_independence():
     s2 = spectrogram_torch(2 * a, 2048, 640, 2048)
     big = s > 0.05
     assert ((s2[big] / s[big]) - 2).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("N,layout_bdn", [(1 << 17, False), (4096 * 3 + 77, True), (5000, False)])
+def test_vq_tensor_core_path_is_bit_identical_to_fp32(N, layout_bdn, monkeypatch):
+    """Large N: distances from split-bf16 products on tcgen05 (vq_tc_scores_kernel), then an exact fp32 re-check of every candidate within
+    the error bound of the best approximate score (vq_tc_finish_kernel).  Codes, dequantised rows and the commitment loss must be
+    BIT-identical to the fp32 FMA kernel -- also with adversarial near-ties: duplicated codebook rows (lowest index must win), vectors
+    exactly half-way between two codes, vectors equal to a code, and a cluster of codes closer together than the error bound (forces
+    the exact full-scan fallback)."""
+    from ttts_b200.vqvae.quantize import vq_lookup
+    g = torch.Generator(device="cuda").manual_seed(N)
+    E = torch.randn(1024, 192, device="cuda", generator=g)
+    E[700] = E[3]; E[701] = E[3]                                  # exact duplicates
+    E[800:806] = E[9] + 1e-6 * torch.randn(6, 192, device="cuda", generator=g)      # a cluster inside the error bound -> fallback scan
+    x = torch.randn(N, 192, device="cuda", generator=g)
+    x[0] = E[3]; x[1] = 0.5 * (E[5] + E[6]); x[2] = E[9]; x[3] = E[803]; x[4] = 0.0
+    x[5:64] = E[torch.randint(0, 1024, (59,), device="cuda", generator=g)] + 1e-3 * torch.randn(59, 192, device="cuda", generator=g)
+    if layout_bdn:
+        Nn = 4096 * 3 + 77
+        xin = x[:Nn].t().contiguous().view(1, 192, Nn)
+    else:
+        xin = x
+    monkeypatch.setenv("TTTS_VQ_TC", "0")
+    c0, q0, l0 = vq_lookup(xin, E, layout_bdn, want_quantized=True, want_commit=True)
+    monkeypatch.setenv("TTTS_VQ_TC", "1")
+    c1, q1, l1 = vq_lookup(xin, E, layout_bdn, want_quantized=True, want_commit=True)
+    assert torch.equal(c0, c1), int((c0 != c1).sum())
+    assert torch.equal(q0, q1) and float(l0) == float(l1)
+    assert int(c1[0]) == 3 and int(c1[2]) in (9, 800, 801, 802, 803, 804, 805)

@@ -103,8 +103,16 @@ def run(hbm_gbs=6570.3, with_cpu=False, bf16_tflops=1638.6):
     for N in (1152, 1 << 20):
         x = torch.randn(N, 192, device=dev, generator=g)
         msv = _time(lambda: vq_lookup(x, E, False), iters=20 if N < 10000 else 5, warm=2)
-        out["vq_argmin_N%d" % N] = {"ms": msv, "tflops_fp32": N * 393216 / msv / 1e9, "gbs": N * 1544 / msv / 1e6,
-                                    "frac_fp32_fma_peak_72tf": N * 393216 / msv / 1e9 / 72.0}
+        tc_path = N >= 4096 and os.environ.get("TTTS_VQ_TC", "1") != "0"
+        ent = {"ms": msv, "gbs": N * 1544 / msv / 1e6, "frac_hbm": N * 1544 / msv / 1e6 / hbm_gbs,
+               "path": "tcgen05 split-bf16 scores + exact fp32 re-check of the candidates (vq_tc_*)" if tc_path else "exact fp32 FMA sweep (vq_argmin_pipe_kernel)"}
+        if tc_path:
+            ent["tflops_equiv"] = N * 393216 / msv / 1e9           # 2 K D FLOP per vector, as the fp32 kernel would spend them
+            ent["frac_tensor"] = 3 * N * 393216 / msv / 1e9 / bf16_tflops      # three bf16 products per fp32 product
+        else:
+            ent["tflops_fp32"] = N * 393216 / msv / 1e9
+            ent["frac_fp32_fma_peak_72tf"] = N * 393216 / msv / 1e9 / 72.0
+        out["vq_argmin_N%d" % N] = ent
     if with_cpu:
         from oracle import encoder_oracle as EO
         from oracle import vq_mel_oracle as V

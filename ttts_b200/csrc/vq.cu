@@ -64,6 +64,11 @@ TTTS_DEVICE void vq_load_x_tile(const float* __restrict__ x, const VqLayout& lay
     }
 }
 
+template <bool SWZ>
+TTTS_DEVICE void vq_emit_tile(const VqLayout& lay, int N, int D, const float* __restrict__ E, int v0, const float* Xs, int* sidx,
+                              int64_t* __restrict__ idx_out, float* __restrict__ q_out, int straight_through, float* __restrict__ commit_partial,
+                              float* __restrict__ hist, float* __restrict__ embed_sum, int tid);
+
 // Per-thread (best, index) of 4 vectors -> CTA-wide argmax (lowest index among equals), then the fused epilogue: indices, dequantised
 // rows, straight-through values, commit-loss partial, code histogram and embedding sums for the EMA update.
 template <bool SWZ>
@@ -83,6 +88,15 @@ TTTS_DEVICE void vq_finish_tile(float (&best)[4], int (&besti)[4], const VqLayou
         }
         if (tx == 0) sidx[ty * 4 + i] = besti[i];
     }
+    vq_emit_tile<SWZ>(lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
+}
+
+// The fused epilogue given the winning code of every vector of the tile in sidx[]: indices, dequantised rows, straight-through values,
+// commit-loss partial, code histogram and embedding sums for the EMA update.
+template <bool SWZ>
+TTTS_DEVICE void vq_emit_tile(const VqLayout& lay, int N, int D, const float* __restrict__ E, int v0, const float* Xs, int* sidx,
+                              int64_t* __restrict__ idx_out, float* __restrict__ q_out, int straight_through, float* __restrict__ commit_partial,
+                              float* __restrict__ hist, float* __restrict__ embed_sum, int tid) {
     __syncthreads();
     if (tid < VQ_TM && v0 + tid < N) {
         idx_out[v0 + tid] = (int64_t)sidx[tid];
@@ -347,6 +361,275 @@ __global__ void vq_bwd_kernel(const float* __restrict__ x, VqLayout lay, int N, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Tensor-core path (large N: codebook extraction over a dataset, k-means).  SURVEY.md section 7 plan: distances from split-bf16 products
+// on tcgen05, then an EXACT fp32 re-check of the candidates, so the codes stay bit-identical to the kernels above.
+//
+//   pass 1  vq_tc_scores_kernel: CTA = 128 vectors.  The x tile is staged once, channel-last, as bf16 hi / lo in the 128-byte-swizzle
+//           K-major layout (exactly conv1d_tcs's window with no halo); the pre-split codebook streams by TMA as [128 codes][64 dims] hi / lo
+//           tiles; D[128 vectors][128 codes] = hi hi + hi lo + lo hi accumulates in TMEM, double-buffered over the K / 128 code tiles so the
+//           epilogue of tile j overlaps the MMAs of tile j + 1.  Epilogue: score~ = |e|^2 - 2 dot~ per code, top-2 per vector and BUCKET of 64
+//           codes (code tile x the alternate 16-code chunks one of the two warps of a TMEM lane quadrant reads) -> partial[2 K / 128][N].
+//   pass 2  vq_tc_finish_kernel: per vector, the candidates are the partial entries within 2 eps of the best approximate score, eps =
+//           1e-4 |x| max|e| (bounds |score~ - score_fp32|: three of four bf16 products, 2^-17 per operand, plus both accumulations).  Each
+//           candidate's distance is recomputed exactly as vq_argmin_pipe_kernel does (fmaf over d in order, -((|x|^2 - 2 acc) + |e|^2)) and
+//           the largest wins, lowest index among equals.  The fp32 kernel's winner w is always among them: score~_w <= score_w + eps <=
+//           score_b + eps <= score~_b + 2 eps for the approximate best b.  If a bucket's SECOND entry is also within 2 eps a third code of
+//           that bucket could hide behind it: its 64 codes are then scanned exactly (rare, and cheap when it happens).
+//           Then the same fused epilogue (vq_emit_tile).
+// ------------------------------------------------------------------------------------------------------------------------------------
+constexpr int VQT_WORKERS = 8;
+constexpr int VQT_THREADS = (VQT_WORKERS + 2) * 32;
+constexpr int VQT_STAGES = 3;
+constexpr int VQT_ATOM = 128 * 128;                 // bytes of one [128 rows x 64 bf16] atom
+constexpr int VQT_WSTAGE = 2 * 128 * 128;           // hi + lo weight tile
+
+struct VqTcParams {
+    const float* x; VqLayout lay; int N, D, K, A;
+    const float* ee;                                 // [K] code norms
+    float4* partial;                                 // [K / 128 code tiles][2 warp halves][Npad]: top-2 {s1, k1, s2, k2} of a bucket of 64 codes
+    int npad;
+};
+
+__global__ void __launch_bounds__(VQT_THREADS, 1) vq_tc_scores_kernel(const __grid_constant__ CUtensorMap tmW, const VqTcParams p) {
+    extern __shared__ uint8_t vqt_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vqt_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* w_full = bars;                         // [3]
+    uint64_t* w_empty = bars + 3;                    // [3]
+    uint64_t* x_full = bars + 6;                     // [3] per atom, 8 arrivals
+    uint64_t* acc_full = bars + 9;                   // [2] commit
+    uint64_t* acc_empty = bars + 11;                 // [2] 8 arrivals
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+    float* ee_s = reinterpret_cast<float*>(smem + 256);              // [K <= 1024] code norms (4 KB)
+    const uint32_t sX = smem_u32(smem + 5120);                       // [hi | lo][A][128 rows][128 B]   (5120 = 5 x 1024)
+    const uint32_t sXlo = sX + p.A * VQT_ATOM;
+    const uint32_t sW = sX + 2 * p.A * VQT_ATOM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v0 = blockIdx.x * 128;
+    const int ntiles = p.K / 128;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < VQT_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 3; ++a) mbar_init(&x_full[a], VQT_WORKERS);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], VQT_WORKERS); }
+        fence_barrier_init();
+    }
+    if (warp == VQT_WORKERS) tmem_alloc(tmem_holder, 256);
+    for (int i = threadIdx.x; i < p.K; i += VQT_THREADS) ee_s[i] = p.ee[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == VQT_WORKERS + 1) {
+        // ---------------- TMA: codebook tiles, (code tile, dim atom) order ----------------
+        int it = 0;
+        for (int nt = 0; nt < ntiles; ++nt)
+            for (int a = 0; a < p.A; ++a, ++it) {
+                const int s = it % VQT_STAGES;
+                mbar_wait(&w_empty[s], ((it / VQT_STAGES) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&w_full[s], VQT_WSTAGE);
+                    uint8_t* dst = smem + 5120 + (size_t)2 * p.A * VQT_ATOM + (size_t)s * VQT_WSTAGE;
+                    tma_load_2d(dst, &tmW, &w_full[s], 0, (a * 2 + 0) * p.K + nt * 128);
+                    tma_load_2d(dst + VQT_ATOM, &tmW, &w_full[s], 0, (a * 2 + 1) * p.K + nt * 128);
+                }
+                __syncwarp();
+            }
+    } else if (warp == VQT_WORKERS) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+        int it = 0;
+        for (int nt = 0; nt < ntiles; ++nt) {
+            mbar_wait(&acc_empty[nt & 1], ((nt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (nt & 1) * 128;
+            for (int a = 0; a < p.A; ++a, ++it) {
+                const int s = it % VQT_STAGES;
+                if (nt == 0) mbar_wait(&x_full[a], 0);
+                mbar_wait(&w_full[s], (it / VQT_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t aHi = sX + a * VQT_ATOM, aLo = sXlo + a * VQT_ATOM;
+                const uint32_t bHi = sW + s * VQT_WSTAGE, bLo = bHi + VQT_ATOM;
+                const int ksteps = min(4, (p.D - a * 64 + 15) / 16);
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t dAh = make_smem_desc_sw128(aHi + ks * 32, 16, 1024), dAl = make_smem_desc_sw128(aLo + ks * 32, 16, 1024);
+                        const uint64_t dBh = make_smem_desc_sw128(bHi + ks * 32, 16, 1024), dBl = make_smem_desc_sw128(bLo + ks * 32, 16, 1024);
+                        umma_bf16(tacc, dAh, dBh, idesc, (a > 0 || ks > 0) ? 1u : 0u);
+                        umma_bf16(tacc, dAh, dBl, idesc, 1u);
+                        umma_bf16(tacc, dAl, dBh, idesc, 1u);
+                    }
+                    umma_commit(&w_empty[s]);
+                    if (a == p.A - 1) umma_commit(&acc_full[nt & 1]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- workers: stage the x tile (thread = vector t & 127, half of the dim groups), then top-2 per code tile ----------------
+        const int tid = threadIdx.x;
+        {
+            const int r = tid & 127, hsel = tid >> 7;
+            const int v = v0 + r;
+            const bool ok = v < p.N;
+            const int b = ok ? v / p.lay.Nn : 0, n = ok ? v - b * p.lay.Nn : 0;
+            const float* xp = p.x + (size_t)(b * p.lay.sB + n * p.lay.sN);
+            for (int a = 0; a < p.A; ++a) {
+                const int cg0 = a * 8 + hsel * 4;                       // four 8-dim groups = 32 loads in flight
+                float vv[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int d = cg0 * 8 + e;
+                    vv[e] = (ok && d < p.D) ? __ldg(xp + (size_t)d * p.lay.sD) : 0.f;
+                }
+#pragma unroll
+                for (int h4 = 0; h4 < 4; ++h4) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h0 = bf16_round(vv[h4 * 8 + 2 * e]), h1 = bf16_round(vv[h4 * 8 + 2 * e + 1]);
+                        hi[e] = pack_bf16(h0, h1);
+                        lo[e] = pack_bf16(vv[h4 * 8 + 2 * e] - h0, vv[h4 * 8 + 2 * e + 1] - h1);
+                    }
+                    const int c = cg0 + h4;
+                    const uint32_t off = (uint32_t)(c >> 3) * VQT_ATOM + (uint32_t)r * 128u + ((uint32_t)((c ^ r) & 7) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_full[a]);
+            }
+        }
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int vrow = v0 + quad * 32 + lane;
+        for (int nt = 0; nt < ntiles; ++nt) {
+            float s1 = INFINITY, s2 = INFINITY; int k1 = 0, k2 = 0;          // top-2 of this bucket: 64 codes of tile nt (this warp's chunks)
+            mbar_wait(&acc_full[nt & 1], (nt >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = half * 16; c0 < 128; c0 += 32) {
+                uint32_t r[16];
+                __syncwarp();
+                tmem_ld_32x16(tmem_base + lane_off + (nt & 1) * 128 + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = nt * 128 + c0 + i;
+                    const float sc = fmaf(-2.0f, __uint_as_float(r[i]), ee_s[k]);
+                    if (sc < s2) {
+                        if (sc < s1) { s2 = s1; k2 = k1; s1 = sc; k1 = k; }
+                        else { s2 = sc; k2 = k; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[nt & 1]);
+            if (vrow < p.N) p.partial[(size_t)(nt * 2 + half) * p.npad + vrow] = make_float4(s1, __int_as_float(k1), s2, __int_as_float(k2));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == VQT_WORKERS) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+}
+
+__global__ void __launch_bounds__(VQ_THREADS) vq_tc_finish_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
+                                                                  const float* __restrict__ ee, int K, const float4* __restrict__ partial, int npad,
+                                                                  int64_t* __restrict__ idx_out, float* __restrict__ q_out, int straight_through,
+                                                                  float* __restrict__ commit_partial, float* __restrict__ hist,
+                                                                  float* __restrict__ embed_sum, unsigned int* __restrict__ fallbacks) {
+    extern __shared__ __align__(16) float vq_smem[];
+    float* Xs = vq_smem;                         // [D][VQ_TM] swizzled
+    float* xx = Xs + (size_t)D * VQ_TM;          // [VQ_TM]
+    int* sidx = reinterpret_cast<int*>(xx + VQ_TM);
+    __shared__ float s_emax[VQ_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int v0 = blockIdx.x * VQ_TM;
+    vq_load_x_tile<true>(x, lay, N, D, v0, Xs, xx, tid);
+    float em = 0.f;
+    for (int k = tid; k < K; k += VQ_THREADS) em = fmaxf(em, __ldg(ee + k));
+    em = warp_max(em);
+    if ((tid & 31) == 0) s_emax[tid >> 5] = em;
+    __syncthreads();
+    // Four threads per vector (sub = tid / 64 takes the buckets q = sub, sub + 4, ...): the exact re-evaluation of a candidate is a chain of
+    // D dependent FMAs fed from L2, so the more chains in flight per CTA the better (r2l capture of the one-thread-per-vector form: 5.8 ms
+    // at N = 2^20 with 12 barrier-stall cycles per issue -- six of eight warps waited for two).
+    __shared__ float s_bd[4][VQ_TM];
+    __shared__ int s_bk[4][VQ_TM];
+    {
+        const int vl = tid & (VQ_TM - 1), sub = tid / VQ_TM;
+        const int v = v0 + vl;
+        float bd = -INFINITY; int bk = 0x7fffffff;
+        if (v < N) {
+            float emax2 = 0.f;
+            for (int w = 0; w < VQ_THREADS / 32; ++w) emax2 = fmaxf(emax2, s_emax[w]);
+            const int nb = 2 * (K / 128);
+            float bestt = INFINITY;
+            for (int q = 0; q < nb; ++q) bestt = fminf(bestt, partial[(size_t)q * npad + v].x);
+            const float xv2 = xx[vl];
+            const float thr = bestt + 2e-4f * sqrtf(xv2) * sqrtf(emax2);
+            auto consider = [&](int k) {
+                float acc = 0.f;
+                const float4* e4p = reinterpret_cast<const float4*>(E + (size_t)k * D);
+                int d = 0;
+                for (; d + 16 <= D; d += 16) {                 // 16 dims per step: four independent 16-byte loads, then the ordered FMA chain
+                    const float4 e0 = __ldg(e4p + (d >> 2)), e1 = __ldg(e4p + (d >> 2) + 1), e2 = __ldg(e4p + (d >> 2) + 2), e3 = __ldg(e4p + (d >> 2) + 3);
+                    const float ev[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc = fmaf(Xs[vq_xs_index<true>(d + j, vl)], ev[j], acc);
+                }
+                for (; d < D; ++d) acc = fmaf(Xs[vq_xs_index<true>(d, vl)], __ldg(E + (size_t)k * D + d), acc);
+                const float dd = -((xv2 - 2.0f * acc) + __ldg(ee + k));
+                if (dd > bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
+            };
+            for (int q = sub; q < nb; q += 4) {
+                const float4 e4 = partial[(size_t)q * npad + v];
+                if (e4.x > thr) continue;
+                if (e4.z <= thr) {
+                    // a third near-tie could hide behind this bucket's second entry: exact scan of its 64 codes
+                    if (fallbacks) atomicAdd(fallbacks, 1u);
+                    const int kb = (q >> 1) * 128 + (q & 1) * 16;
+                    for (int j = 0; j < 4; ++j)
+                        for (int i = 0; i < 16; ++i) consider(kb + 32 * j + i);
+                } else {
+                    consider(__float_as_int(e4.y));
+                }
+            }
+        }
+        s_bd[sub][vl] = bd; s_bk[sub][vl] = bk;
+    }
+    __syncthreads();
+    if (tid < VQ_TM) {
+        float bd = s_bd[0][tid]; int bk = s_bk[0][tid];
+#pragma unroll
+        for (int sub = 1; sub < 4; ++sub) {
+            const float od = s_bd[sub][tid]; const int ok = s_bk[sub][tid];
+            if (od > bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        }
+        sidx[tid] = (v0 + tid < N) ? bk : 0;
+    }
+    vq_emit_tile<true>(lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
+}
+
+// defined in conv1d_tcs.cu: fp32 [Cout][Cin][K] -> split bf16 [K][atoms][hi | lo][Cout][64]
+int conv_tcs_prep_weights(const float* w, void* ws, int Cout, int Cin, int K, cudaStream_t st);
+
+static bool vq_tc_enabled() {                      // read per call (not latched): the parity tests run both paths in one process
+    const char* e = getenv("TTTS_VQ_TC");
+    return !(e && e[0] == '0');
+}
+constexpr int VQ_TC_MIN_N = 4096;                  // below this the fp32 kernel's single launch wins (the encode metric's N = 1 152 stays there)
+
+static bool vq_tc_covers(int N, int D, int K) {
+    return vq_tc_enabled() && N >= VQ_TC_MIN_N && D % 8 == 0 && D >= 16 && D <= 192 && K % 128 == 0 && K >= 128 && K <= 1024;
+}
+
 static VqLayout make_layout(int B, int D, int Nn, int bdn) {
     VqLayout l;
     if (bdn) { l.sB = (long long)D * Nn; l.sD = Nn; l.sN = 1; l.Nn = Nn; }
@@ -361,7 +644,13 @@ using namespace ttts;
 extern "C" {
 
 // workspace floats needed by ttts_vq_forward: K (code norms) + ceil(N/64) (commit partials) + 1
-int64_t ttts_vq_workspace_floats(int32_t N, int32_t K) { return (int64_t)K + (N + VQ_TM - 1) / VQ_TM + 8; }
+// (+ for the tensor-core path at large N: the split-bf16 codebook, 192 K floats' worth, and the top-2 partials, 8 K / 128 floats per vector)
+int64_t ttts_vq_workspace_floats(int32_t N, int32_t K) {
+    int64_t n = (int64_t)K + (N + VQ_TM - 1) / VQ_TM + 8;
+    n = (n + 63) / 64 * 64;
+    if (N >= ttts::VQ_TC_MIN_N) n += (int64_t)192 * K + 8ll * (K / 128 + 1) * ((N + 127) / 128 * 128) + 64;
+    return n;
+}
 
 int ttts_vq_forward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t layout_bdn, const float* embed, int32_t K, int64_t* codes,
                     float* quantized, int32_t straight_through, float* commit_out, float* hist, float* embed_sum, float* workspace, void* stream) {
@@ -376,6 +665,36 @@ int ttts_vq_forward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t la
     const int blocks = (N + VQ_TM - 1) / VQ_TM;
     vq_code_norms_kernel<<<(K + 7) / 8, 256, 0, st>>>(embed, K, D, ee);
     TTTS_LAUNCH_CHECK("vq_code_norms");
+    if (vq_tc_covers(N, D, K) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+        const int A = (D + 63) / 64;
+        int64_t off = ((int64_t)K + blocks + 8 + 63) / 64 * 64;
+        void* esplit = workspace + off;                                    // bf16 [A][hi | lo][K][64]
+        const int npad = (N + 127) / 128 * 128;
+        float4* part = reinterpret_cast<float4*>(workspace + off + (int64_t)192 * K);
+        unsigned int* fb = reinterpret_cast<unsigned int*>(workspace + off + (int64_t)192 * K + 8ll * (K / 128) * npad);
+        TTTS_RUN(conv_tcs_prep_weights(embed, esplit, K, D, 1, st));
+        TTTS_CUDA(cudaMemsetAsync(fb, 0, sizeof(unsigned int), st));
+        CUtensorMap tm;
+        TTTS_RUN(make_tmap_2d(&tm, esplit, 2, 64, (uint64_t)A * 2 * K, 64, 64, 128, 1));
+        VqTcParams p;
+        p.x = x; p.lay = lay; p.N = N; p.D = D; p.K = K; p.A = A; p.ee = ee; p.partial = part; p.npad = npad;
+        const size_t smem1 = 5120 + (size_t)2 * A * VQT_ATOM + VQT_STAGES * VQT_WSTAGE + 1024;
+        static bool attr1 = false;
+        if (!attr1) { TTTS_CUDA(cudaFuncSetAttribute(vq_tc_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); attr1 = true; }
+        vq_tc_scores_kernel<<<npad / 128, VQT_THREADS, smem1, st>>>(tm, p);
+        TTTS_LAUNCH_CHECK("vq_tc_scores");
+        const size_t smem2 = ((size_t)D * VQ_TM + VQ_TM) * sizeof(float) + VQ_TM * sizeof(int);
+        static size_t attr2 = 0;
+        if (smem2 > attr2) { TTTS_CUDA(cudaFuncSetAttribute(vq_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2 = smem2; }
+        vq_tc_finish_kernel<<<blocks, VQ_THREADS, smem2, st>>>(x, lay, N, D, embed, ee, K, part, npad, codes, quantized, straight_through,
+                                                              commit_out ? partial : nullptr, hist, embed_sum, fb);
+        TTTS_LAUNCH_CHECK("vq_tc_finish");
+        if (commit_out) {
+            vq_commit_final_kernel<<<1, 1024, 0, st>>>(partial, blocks, 1.0f / ((float)N * (float)D), commit_out);
+            TTTS_LAUNCH_CHECK("vq_commit_final");
+        }
+        return TTTS_OK;
+    }
     static int v1 = -1;
     if (v1 < 0) { const char* e = getenv("TTTS_VQ_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
     const bool pipe = !v1 && D % VQ_DC == 0 && (reinterpret_cast<uintptr_t>(embed) & 15) == 0;

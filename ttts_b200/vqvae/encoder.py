@@ -115,7 +115,7 @@ def conv1d(x, w, bias=None, stride=1, dil=1, pad=0, pre_lrelu=False, resid=None,
 
 def conv1d_backward(dy, x, w, stride=1, dil=1, pad=0, pre_lrelu=False, need_bias=True):
     """Autograd of `conv1d(x, w, b, stride, dil, pad, pre_lrelu)` for a given dy [B,Cout,Tout]: returns (dx, dw, db).  Raw calls of
-    ttts_conv1d_bwd_input / ttts_conv1d_bwd_weight (csrc/conv1d_bwd.cu; next scope row, not yet wired into a training module)."""
+    ttts_conv1d_bwd_input / ttts_conv1d_bwd_weight (csrc/conv1d_bwd.cu; used by the training tape, ttts_b200/vqvae/train_encoder.py)."""
     lib = L.lib(); _protos(lib)
     L.require_cuda(dy, x, w)
     assert dy.is_contiguous() and x.is_contiguous() and w.is_contiguous()
@@ -521,7 +521,7 @@ class VQEncoder(nn.Module):
         else:
             mask = (torch.arange(T, device=wav.device)[None, :] < lengths[:, None]).float().unsqueeze(1)      # commons.sequence_mask
         if os.environ.get("TTTS_ENC_OVERLAP", "0") == "1":
-            # opt-in (not yet run on hardware): only the WN branch needs the style vector, so MelStyleEncoder (~15 small launches, two of them
+            # opt-in (TTTS_ENC_OVERLAP=1; measured slower in r2b, 8.9 vs 7.9 ms): only the WN branch needs the style vector, so MelStyleEncoder (~15 small launches, two of them
             # 1025-row reductions) moves onto the WN branch's stream and overlaps the waveform branch instead of preceding both.  Same kernels,
             # same inputs: bit-identical results.
             z, m, logs = self.enc_p(spec, wav.unsqueeze(1), mask, g=lambda: self.ref_enc(spec * mask, mask), eps=eps)
