@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_train_masked.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vqvae_full_step.npz, vq.npz, mel.npz, encoder.npz.  Weights are NOT stored: they are regenerated from
+Writes tests/golden/gpt_tiny.npz, gpt_ragged.npz, gpt_train_masked.npz, gpt_generate.npz, gpt_kvstep.npz, disc.npz, flow.npz, text_encoder.npz, vqvae_step.npz, vqvae_full_step.npz, vq.npz, mel.npz, encoder.npz, diffusion.npz.  Weights are NOT stored: they are regenerated from
 numpy seeds by oracle.gpt_oracle.init_params (torch-version independent), loaded into the reference module through its
 state_dict, and the reference's outputs are stored.  The import shims follow SURVEY.md Appendix D; nothing under
 /root/reference is modified or copied.
@@ -629,6 +629,60 @@ def encoder_case():
     print("encoder ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "codes", codes.shape, codes.flatten()[:8].tolist())
 
 
+def diffusion_case():
+    """The REAL `AA_diffusion` (ttts/diffusion/aa_model.py:182-287) in train() mode under the REAL `SpacedDiffusion.training_losses`
+    (ttts/utils/diffusion.py:930-1014) built exactly as ttts/diffusion/train.py:90-92, one micro-step of train.py:168-180: model output,
+    mse / vb terms, loss, and per parameter tensor the gradient norm / projection.  The model's random decisions are pinned by patching the two
+    draws it makes (torch.rand for the unconditioned samples, random.random for the layer drop) to the values oracle.golden_inputs() names."""
+    import random as pyrandom
+    from oracle import diffusion_oracle as DO
+    kd = types.ModuleType("k_diffusion"); ks = types.ModuleType("k_diffusion.sampling")
+    ks.sample_dpmpp_2m = ks.sample_euler_ancestral = None; kd.sampling = ks
+    sys.modules["k_diffusion"] = kd; sys.modules["k_diffusion.sampling"] = ks
+    import ttts.diffusion.aa_model as A
+    from ttts.utils.diffusion import SpacedDiffusion, space_timesteps, get_named_beta_schedule
+    cfg = DO.default_config(**DO.GOLDEN_CFG)
+    net = A.AA_diffusion(**cfg, dropout=0, layer_drop=0.1).train()
+    P = DO.init_params(cfg, seed=12)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(P.keys()), sorted(set(sd.keys()) ^ set(P.keys()))[:10]
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+    net.load_state_dict(P)
+    diffuser = SpacedDiffusion(use_timesteps=space_timesteps(1000, [1000]), model_mean_type="epsilon", model_var_type="learned_range",
+                               loss_type="mse", betas=get_named_beta_schedule("linear", 1000), conditioning_free=False, conditioning_free_k=2.0)
+    I = DO.golden_inputs()
+    B = I["x_start"].shape[0]
+    n_layers = cfg["num_layers"] + 3
+    draws = iter([0.0 if i in I["dropped"] else 0.5 for i in range(1, n_layers - 1)])
+    real_rand, real_random = torch.rand, pyrandom.random
+    captured = {}
+
+    def fake_rand(*a, **k):
+        return torch.where(I["uncond"], 0.0, 0.5).reshape(B, 1, 1).float()
+    hook = net.out.register_forward_hook(lambda m, i, o: captured.__setitem__("out", o.detach().clone()))
+    torch.rand, pyrandom.random = fake_rand, lambda: next(draws)
+    try:
+        terms = diffuser.training_losses(model=net, x_start=I["x_start"], t=torch.tensor(I["t"]), noise=I["noise"],
+                                         model_kwargs={"latent": I["latent"], "refer": I["refer"]})
+    finally:
+        torch.rand, pyrandom.random = real_rand, real_random
+        hook.remove()
+    assert next(draws, None) is None
+    loss = terms["loss"].mean()
+    loss.backward()
+    names, norm, proj = [], [], []
+    for k, prm in net.named_parameters():
+        gk = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        d = torch.randn(gk.shape, generator=torch.Generator().manual_seed(len(names)))
+        names.append(k); norm.append(float(gk.norm())); proj.append(float((gk * d).sum()))
+    path = os.path.join(ROOT, "tests", "golden", "diffusion.npz")
+    np.savez_compressed(path, model_out=captured["out"].numpy(), mse=terms["mse"].detach().numpy(), vb=terms["vb"].detach().numpy(), loss=float(loss),
+                        names=np.array(names), norm=np.array(norm), proj=np.array(proj))
+    print("diffusion ->", path, "%.1f KB" % (os.path.getsize(path) / 1e3), "loss %.6f" % float(loss), "mse", terms["mse"].detach().numpy(), "vb", terms["vb"].detach().numpy(),
+          "zero-grad tensors", sum(1 for v in norm if v == 0.0), "of", len(norm))
+
+
 if __name__ == "__main__":
     import math
     torch.manual_seed(0)
@@ -636,6 +690,9 @@ if __name__ == "__main__":
     gm = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "diffusion":
+        diffusion_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "decoder":
         decoder_case()
@@ -683,3 +740,4 @@ if __name__ == "__main__":
     vq_case()
     mel_case()
     encoder_case()
+    diffusion_case()
