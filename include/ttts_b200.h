@@ -372,6 +372,45 @@ int ttts_layernorm_c(const float* x, const float* gamma, const float* beta, floa
 int ttts_layernorm_c_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx, float* dgamma, float* dbeta,
                          float* scratch, int32_t B, int32_t C, int32_t T, void* stream);                             /* scratch: B*T*2 floats */
 
+/* --------------------------------------------------------------------------------------------
+ * Diffusion mel-refiner train step (BASELINE config 5; csrc/diffusion_kernels.cu): the ops `AA_diffusion`
+ * (ttts/diffusion/aa_model.py:69-287) and `SpacedDiffusion.training_losses` (ttts/utils/diffusion.py:903-1014) add to the training tape.
+ * fp32, [B, C, T] channel-major.
+ * ------------------------------------------------------------------------------------------ */
+/* GroupNorm32 / `normalization` (ttts/utils/utils.py:119-137) fused with the ResBlock's scale-shift modulation and SiLU (aa_model.py:120-135):
+ * y = act(GroupNorm_G(x; gamma, beta, eps 1e-5) * (1 + scale[b,c]) + shift[b,c]); scale / shift [B,C] or both NULL; act = SiLU if silu else
+ * identity; stats [B,G,2] = (mean, rstd) out, read by the backward.  C / G <= 64. */
+int ttts_groupnorm(const float* x, const float* gamma, const float* beta, const float* scale, const float* shift, float* y, float* stats,
+                   int32_t B, int32_t C, int32_t T, int32_t G, int32_t silu, void* stream);
+/* dx [B,C,T], dgamma / dbeta [C], dscale / dshift [B,C] (NULL without modulation) WRITTEN; scratch: B*C*2 floats */
+int ttts_groupnorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, const float* beta, const float* scale,
+                       const float* shift, float* dx, float* dgamma, float* dbeta, float* dscale, float* dshift, float* scratch,
+                       int32_t B, int32_t C, int32_t T, int32_t G, int32_t silu, void* stream);
+/* nn.SiLU: out = x sigmoid(x) (backward = 0) or dy d/dx (backward = 1) */
+int ttts_silu(const float* x, const float* dy, float* out, int64_t n, int32_t backward, void* stream);
+/* QKVAttentionLegacy + RelativePositionBias (utils.py:148-175, utils/xtransformers.py:146-188) inside AttentionBlock: qkv [B,3C,T] with head h
+ * owning channels [3 ch h, 3 ch (h+1)) = q | k | v (ch = C / H in {8,16,32,64}); scores = q.k / sqrt(ch) + sqrt(ch) table[diag[j-i+T-1], h],
+ * non-causal softmax; out [B,C,T]; lse [B,H,T] out for the backward.  table [32,H]; diag int32 [2T-1] = T5 bucket of each relative position
+ * (32 buckets, max_distance 64, bidirectional).  Flash-style: no [T,T] tensor is materialised. */
+int ttts_attn_bias(const float* qkv, const float* table, const int32_t* diag, float* out, float* lse, int32_t B, int32_t C, int32_t T,
+                   int32_t H, void* stream);
+int64_t ttts_attn_bias_bwd_scratch_floats(int32_t B, int32_t T, int32_t H);
+/* dqkv [B,3C,T] and dtable [32,H] WRITTEN (deterministic: per-CTA bucket sums reduced in fixed order) */
+int ttts_attn_bias_bwd(const float* dout, const float* qkv, const float* out, const float* lse, const float* table, const int32_t* diag,
+                       float* dqkv, float* dtable, float* scratch, int32_t B, int32_t C, int32_t T, int32_t H, void* stream);
+/* GaussianDiffusion.q_sample (utils/diffusion.py:243-260): x_t = coef[b,0] x_start + coef[b,1] noise over [B, per] tensors.
+ * coef [B,8] fp32 per sample = sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+ * posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped, log(beta) at t[b] */
+int ttts_diff_q_sample(const float* x_start, const float* noise, const float* coef, float* x_t, int32_t B, int64_t per, void* stream);
+/* training_losses with epsilon prediction, learned-range variance, MSE loss (utils/diffusion.py:930-1014 with _vb_terms_bpd :903-928,
+ * p_mean_variance :284-386, normal_kl / discretized_gaussian_log_likelihood :17-73): model_out [B, 2 Cn, T] = (eps | variance values),
+ * x_start / x_t / noise [B,Cn,T], t_is0 int32 [B] -> terms [2,B] = (mse, vb), loss [1] = mean_b(mse + vb) (ttts/diffusion/train.py:172-180).
+ * scratch: B * 64 floats.  Backward: d model_out for a gradient dL [1] of the loss (the mean prediction is detached inside vb). */
+int ttts_diff_loss(const float* model_out, const float* x_start, const float* x_t, const float* noise, const float* coef, const int32_t* t_is0,
+                   float* terms, float* loss, float* scratch, int32_t B, int32_t Cn, int32_t T, void* stream);
+int ttts_diff_loss_bwd(const float* dL, const float* model_out, const float* x_start, const float* x_t, const float* noise, const float* coef,
+                       const int32_t* t_is0, float* dout, int32_t B, int32_t Cn, int32_t T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

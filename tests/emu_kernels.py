@@ -13,7 +13,7 @@ from ref_kernels import TorchRefKernels
 from ttts_b200.vqvae.train_encoder import CudaKernels
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SOURCES = ("conv_bwd_emu.cpp", "encoder_bwd_emu.cpp", "gan_losses_emu.cpp", "stft_bwd_emu.cpp", "text_encoder_emu.cpp", "gconv_emu.cpp")
+SOURCES = ("conv_bwd_emu.cpp", "encoder_bwd_emu.cpp", "gan_losses_emu.cpp", "stft_bwd_emu.cpp", "text_encoder_emu.cpp", "gconv_emu.cpp", "diffusion_emu.cpp")
 
 
 def build_all(outdir):
@@ -93,3 +93,12 @@ class EmuKernels(CudaKernels):
 
     def logmel_fwd(self, wav):
         return self.ref.logmel_fwd(wav).contiguous()
+
+
+def emu_diffusion_kernels(libs):
+    """the diffusion backend (ttts_b200/diffusion/kernels.py) over the same host builds"""
+    from ttts_b200.diffusion.kernels import DiffusionKernelsMixin
+
+    class EmuDiffusionKernels(DiffusionKernelsMixin, EmuKernels):
+        pass
+    return EmuDiffusionKernels(libs)

@@ -278,6 +278,92 @@ class TorchRefKernels:
     def posterior_bwd(self, dz, stats, eps, mask):
         return _vjp(lambda s: self._posterior(s, eps, mask), [stats], dz)[0]
 
+    # ================= diffusion mel-refiner (ttts_b200/diffusion/train_graph.py; csrc/diffusion_kernels.cu) =================
+    # ---- act(GroupNorm(x) * (1 + scale) + shift), eps 1e-5 (utils.py:119-137, aa_model.py:126-130); stats [B, G, 2] = (mean, rstd) ----
+    @staticmethod
+    def _gn(x, gamma, beta, groups, scale, shift, silu):
+        y = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+        if scale is not None:
+            y = y * (1 + scale) + shift
+        return F.silu(y) if silu else y
+
+    def gn_fwd(self, x, gamma, beta, groups, scale, shift, silu):
+        B, C, T = x.shape
+        xg = x.reshape(B, groups, -1)
+        mean = xg.mean(-1)
+        rstd = torch.rsqrt(xg.var(-1, unbiased=False) + 1e-5)
+        return self._gn(x, gamma, beta, groups, scale, shift, silu), torch.stack([mean, rstd], dim=-1)
+
+    def gn_bwd(self, dy, x, stats, gamma, beta, groups, scale, shift, silu):
+        if scale is None:
+            dx, dg, db = _vjp(lambda a, g, b: self._gn(a, g, b, groups, None, None, silu), [x, gamma, beta], dy)
+            return dx, dg, db, None, None
+        return _vjp(lambda a, g, b, sc, sh: self._gn(a, g, b, groups, sc, sh, silu), [x, gamma, beta, scale, shift], dy)
+
+    def silu_fwd(self, x):
+        return F.silu(x)
+
+    def silu_bwd(self, dy, x):
+        return _vjp(F.silu, [x], dy)[0]
+
+    # ---- QKVAttentionLegacy + RelativePositionBias (utils.py:148-175, xtransformers.py:178-188): qkv [B, 3C, T] with the heads split BEFORE
+    # q / k / v, table [32, H], diag int32 [2T-1] = bucket of (j - i) + T - 1; returns (out [B,C,T], lse [B,H,T] of the biased scores) ----
+    @staticmethod
+    def _attn_bias(qkv, table, heads, diag, want_lse=False):
+        import math
+        B, W, T = qkv.shape
+        ch = W // (3 * heads)
+        q, k, v = qkv.reshape(B * heads, ch * 3, T).split(ch, dim=1)
+        w = torch.einsum("bct,bcs->bts", q, k) / math.sqrt(ch)
+        idx = (torch.arange(T)[None, :] - torch.arange(T)[:, None] + T - 1)
+        bias = table[diag.long()[idx]]                               # [T, T, H]
+        w = (w.reshape(B, heads, T, T) + bias.permute(2, 0, 1)[None] * math.sqrt(ch)).reshape(B * heads, T, T)
+        out = torch.einsum("bts,bcs->bct", torch.softmax(w, dim=-1), v).reshape(B, -1, T)
+        return (out, torch.logsumexp(w, dim=-1).reshape(B, heads, T)) if want_lse else out
+
+    def attn_bias_fwd(self, qkv, table, heads, diag):
+        return self._attn_bias(qkv, table, heads, diag, True)
+
+    def attn_bias_bwd(self, do, qkv, out, lse, table, heads, diag):
+        return _vjp(lambda a, t: self._attn_bias(a, t, heads, diag), [qkv, table], do)
+
+    # ---- q_sample and the loss (utils/diffusion.py:243-260, 903-1014); coef [B, 8] fp32, see train_graph.coef_table ----
+    def q_sample(self, x_start, noise, coef):
+        return coef[:, 0, None, None] * x_start + coef[:, 1, None, None] * noise
+
+    @staticmethod
+    def _diff_terms(out, x_start, x_t, noise, coef, t_is0):
+        import math
+        Cn = x_start.shape[1]
+        co = lambda i: coef[:, i, None, None]
+        eps, v = out[:, :Cn], out[:, Cn:]
+        mse = ((noise - eps) ** 2).mean(dim=(1, 2))
+        eps_d = eps.detach()
+        true_mean = co(4) * x_start + co(5) * x_t
+        frac = (v + 1) / 2
+        logvar = frac * co(7) + (1 - frac) * co(6)
+        mean = co(4) * (co(2) * x_t - co(3) * eps_d).clamp(-1, 1) + co(5) * x_t
+        kl = 0.5 * (-1.0 + logvar - co(6) + torch.exp(co(6) - logvar) + ((true_mean - mean) ** 2) * torch.exp(-logvar))
+        kl = kl.mean(dim=(1, 2)) / math.log(2.0)
+        cdf = lambda a: 0.5 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (a + 0.044715 * torch.pow(a, 3))))
+        cx = x_start - mean
+        inv_std = torch.exp(-0.5 * logvar)
+        cp, cm = cdf(inv_std * (cx + 1.0 / 255.0)), cdf(inv_std * (cx - 1.0 / 255.0))
+        lp = torch.where(x_start < -0.999, torch.log(cp.clamp(min=1e-12)),
+                         torch.where(x_start > 0.999, torch.log((1.0 - cm).clamp(min=1e-12)), torch.log((cp - cm).clamp(min=1e-12))))
+        nll = -lp.mean(dim=(1, 2)) / math.log(2.0)
+        return mse, torch.where(t_is0 != 0, nll, kl)
+
+    def diff_loss_fwd(self, out, x_start, x_t, noise, coef, t_is0):
+        mse, vb = self._diff_terms(out, x_start, x_t, noise, coef, t_is0)
+        return (mse + vb).mean().reshape(1), (mse, vb)
+
+    def diff_loss_bwd(self, dL, out, x_start, x_t, noise, coef, t_is0):
+        def f(o):
+            mse, vb = self._diff_terms(o, x_start, x_t, noise, coef, t_is0)
+            return (mse + vb).mean().reshape(1)
+        return _vjp(f, [out], dL)[0]
+
 
 class TorchAdamW:
     """the optimizer contract of train_step.TrainStep with torch.optim.AdamW(lr, betas (0.8, 0.99), eps 1e-9) -- the trainer's own
@@ -294,3 +380,25 @@ class TorchAdamW:
         for k, v in self.p.items():
             v.grad = grads[k].reshape(v.shape).clone()
         self.opt.step()
+
+
+class TorchAdamWClip:
+    """the optimizer contract of ttts_b200.diffusion.train_step.DiffusionStep with torch's own pieces -- clip_grad_norm_(1.0) +
+    torch.optim.AdamW(lr, betas (0.9, 0.999), weight decay 0.01) with the learning rate scaled per step (ttts/diffusion/train.py:116-117,190-195)"""
+
+    def __init__(self, params, lr=1e-4):
+        self.p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        self.lr = lr
+        self.opt = torch.optim.AdamW(list(self.p.values()), lr, betas=(0.9, 0.999), weight_decay=0.01)
+
+    def params(self):
+        return {k: v.detach() for k, v in self.p.items()}
+
+    def step(self, grads, lr_scale=1.0):
+        for k, v in self.p.items():
+            v.grad = grads[k].reshape(v.shape).clone()
+        norm = torch.nn.utils.clip_grad_norm_(list(self.p.values()), 1.0)
+        for g in self.opt.param_groups:
+            g["lr"] = self.lr * lr_scale
+        self.opt.step()
+        return norm.reshape(1)

@@ -1,0 +1,92 @@
+"""CPU emulation of the diffusion kernels (tests/emu builds ttts_b200/csrc/diffusion_kernels.cu for the host) through the PRODUCT backend's
+marshalling code (ttts_b200/diffusion/kernels.py) against the op contract tests/ref_kernels.py: GroupNorm (+ modulation, + SiLU) forward /
+backward, SiLU, attention with the bucketed relative-position bias (head widths 8 / 16 / 32, lengths that are not tile multiples, several
+query / key tiles) forward / backward, q_sample, and the loss incl. the t = 0 decoder-NLL branch and its |x| > 0.999 cases."""
+import os
+import shutil
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ref_kernels import TorchRefKernels  # noqa: E402
+
+R = TorchRefKernels()
+
+
+@pytest.fixture(scope="module")
+def K(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import emu_kernels as EK
+    return EK.emu_diffusion_kernels(EK.build_all(str(tmp_path_factory.mktemp("emu"))))
+
+
+def close(got, want, tol=3e-5):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = float((got - want).abs().max())
+    assert err <= tol * max(1.0, float(want.abs().max())), (err, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("B,C,T,G,mod,silu", [(2, 32, 9, 8, False, False), (2, 64, 21, 16, True, True), (1, 128, 5, 32, False, True), (3, 16, 40, 8, True, False)])
+def test_groupnorm_fwd_bwd(K, B, C, T, G, mod, silu):
+    g = torch.Generator().manual_seed(B * 100 + C + T)
+    x = torch.randn(B, C, T, generator=g) * 1.7 + 0.3
+    gamma, beta = torch.rand(C, generator=g) + 0.5, 0.2 * torch.randn(C, generator=g)
+    scale = 0.4 * torch.randn(B, C, 1, generator=g) if mod else None
+    shift = 0.4 * torch.randn(B, C, 1, generator=g) if mod else None
+    dy = torch.randn(B, C, T, generator=g)
+    y, stats = K.gn_fwd(x, gamma, beta, G, scale, shift, silu)
+    yr, sr = R.gn_fwd(x, gamma, beta, G, scale, shift, silu)
+    close(y, yr); close(stats, sr)
+    got = K.gn_bwd(dy, x, stats, gamma, beta, G, scale, shift, silu)
+    want = R.gn_bwd(dy, x, sr, gamma, beta, G, scale, shift, silu)
+    for a, b in zip(got, want):
+        if b is None:
+            assert a is None
+        else:
+            close(a, b, 5e-5)
+
+
+def test_silu(K):
+    x, dy = torch.randn(3, 7, 11) * 3, torch.randn(3, 7, 11)
+    close(K.silu_fwd(x), R.silu_fwd(x))
+    close(K.silu_bwd(dy, x), R.silu_bwd(dy, x))
+
+
+@pytest.mark.parametrize("B,H,ch,T", [(1, 2, 16, 70), (2, 1, 32, 24), (1, 2, 8, 130), (1, 1, 64, 65)])
+def test_attn_bias_fwd_bwd(K, B, H, ch, T):
+    from ttts_b200.diffusion.train_graph import diagonal_buckets
+    g = torch.Generator().manual_seed(7 * T + ch)
+    qkv = torch.randn(B, 3 * H * ch, T, generator=g)
+    table = 0.5 * torch.randn(32, H, generator=g)
+    diag = diagonal_buckets(T)
+    do = torch.randn(B, H * ch, T, generator=g)
+    out, lse = K.attn_bias_fwd(qkv, table, H, diag)
+    outr, lser = R.attn_bias_fwd(qkv, table, H, diag)
+    close(out, outr); close(lse, lser)
+    dqkv, dtab = K.attn_bias_bwd(do, qkv, out, lse, table, H, diag)
+    dqr, dtr = R.attn_bias_bwd(do, qkv, outr, lser, table, H, diag)
+    close(dqkv, dqr, 5e-5); close(dtab, dtr, 5e-5)
+
+
+def test_q_sample_and_loss(K):
+    from ttts_b200.diffusion.train_graph import coef_table
+    g = torch.Generator().manual_seed(3)
+    B, Cn, T = 4, 10, 37
+    t = torch.tensor([0, 3, 500, 999])
+    coef = coef_table(t)
+    x0 = 0.6 * torch.randn(B, Cn, T, generator=g)
+    x0[0, :2, :5] = -1.3; x0[0, 2:4, :5] = 1.2
+    noise = torch.randn(B, Cn, T, generator=g)
+    xt = K.q_sample(x0, noise, coef)
+    close(xt, R.q_sample(x0, noise, coef), 1e-6)
+    out = torch.randn(B, 2 * Cn, T, generator=g)
+    out[0, Cn:] *= 2.0                                                 # variance values outside [-1, 1] too
+    t0 = (t == 0).int()
+    loss, (mse, vb) = K.diff_loss_fwd(out, x0, xt, noise, coef, t0)
+    lr, (mr, vr) = R.diff_loss_fwd(out, x0, xt, noise, coef, t0)
+    close(loss, lr, 1e-5); close(mse, mr, 1e-5); close(vb, vr, 2e-5)
+    dL = torch.tensor([1.7])
+    close(K.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), R.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), 5e-5)

@@ -1,0 +1,180 @@
+"""GPU (-m gpu): the diffusion mel-refiner train step (BASELINE config 5) through the C ABI -- the new kernels op by op
+against the contract (tests/ref_kernels.py, itself the autograd of the pinned restatements), the training graph against the REAL reference's
+micro-step (tests/golden/diffusion.npz), the optimisation step against torch's own loop over the pinned oracle, and size-independent
+properties at the BASELINE size (batch 32 x 1024 frames, 512 channels, 16 heads)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import diffusion_oracle as DO
+from ref_kernels import TorchRefKernels
+
+R = TorchRefKernels()
+
+
+@pytest.fixture(scope="module")
+def K():
+    from ttts_b200.diffusion.kernels import DiffusionCudaKernels
+    return DiffusionCudaKernels()
+
+
+def close(got, want, tol=3e-5):
+    got = got.cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = float((got - want).abs().max())
+    assert err <= tol * max(1.0, float(want.abs().max())), (err, float(want.abs().max()))
+
+
+def cu(*ts):
+    return [t.cuda() if t is not None else None for t in ts]
+
+
+@pytest.mark.parametrize("B,C,T,G,mod,silu", [(2, 32, 9, 8, False, False), (2, 64, 21, 16, True, True), (3, 128, 50, 32, False, True),
+                                              (2, 512, 1024, 32, True, True), (2, 512, 257, 32, False, False)])
+def test_groupnorm_fwd_bwd(K, B, C, T, G, mod, silu):
+    g = torch.Generator().manual_seed(B * 100 + C + T)
+    x = torch.randn(B, C, T, generator=g) * 1.7 + 0.3
+    gamma, beta = torch.rand(C, generator=g) + 0.5, 0.2 * torch.randn(C, generator=g)
+    scale = 0.4 * torch.randn(B, C, 1, generator=g) if mod else None
+    shift = 0.4 * torch.randn(B, C, 1, generator=g) if mod else None
+    dy = torch.randn(B, C, T, generator=g)
+    xc, gc, bc, sc, hc, dyc = cu(x, gamma, beta, scale, shift, dy)
+    y, stats = K.gn_fwd(xc, gc, bc, G, sc, hc, silu)
+    yr, sr = R.gn_fwd(x, gamma, beta, G, scale, shift, silu)
+    close(y, yr); close(stats, sr)
+    got = K.gn_bwd(dyc, xc, stats, gc, bc, G, sc, hc, silu)
+    want = R.gn_bwd(dy, x, sr, gamma, beta, G, scale, shift, silu)
+    for a, b in zip(got, want):
+        if b is None:
+            assert a is None
+        else:
+            close(a, b, 2e-4 if T >= 257 else 5e-5)        # long reductions: fp32 summation order
+
+
+def test_silu(K):
+    x, dy = torch.randn(3, 70, 111) * 3, torch.randn(3, 70, 111)
+    close(K.silu_fwd(x.cuda()), R.silu_fwd(x))
+    close(K.silu_bwd(dy.cuda(), x.cuda()), R.silu_bwd(dy, x))
+
+
+@pytest.mark.parametrize("B,H,ch,T", [(1, 2, 16, 70), (2, 1, 32, 24), (1, 2, 8, 130), (1, 1, 64, 65), (2, 3, 32, 256), (1, 2, 64, 232), (1, 2, 32, 1024)])
+def test_attn_bias_fwd_bwd(K, B, H, ch, T):
+    from ttts_b200.diffusion.train_graph import diagonal_buckets
+    g = torch.Generator().manual_seed(7 * T + ch)
+    qkv = torch.randn(B, 3 * H * ch, T, generator=g)
+    table = 0.5 * torch.randn(32, H, generator=g)
+    diag = diagonal_buckets(T)
+    do = torch.randn(B, H * ch, T, generator=g)
+    out, lse = K.attn_bias_fwd(qkv.cuda(), table.cuda(), H, diag.cuda())
+    outr, lser = R.attn_bias_fwd(qkv, table, H, diag)
+    close(out, outr); close(lse, lser)
+    dqkv, dtab = K.attn_bias_bwd(do.cuda(), qkv.cuda(), out, lse, table.cuda(), H, diag.cuda())
+    dqr, dtr = R.attn_bias_bwd(do, qkv, outr, lser, table, H, diag)
+    close(dqkv, dqr, 1e-4); close(dtab, dtr, 2e-4)
+    # deterministic: a second run gives the same bits
+    dq2, dt2 = K.attn_bias_bwd(do.cuda(), qkv.cuda(), out, lse, table.cuda(), H, diag.cuda())
+    assert torch.equal(dq2, dqkv) and torch.equal(dt2, dtab)
+
+
+def test_q_sample_and_loss(K):
+    from ttts_b200.diffusion.train_graph import coef_table
+    g = torch.Generator().manual_seed(3)
+    B, Cn, T = 4, 100, 137
+    t = torch.tensor([0, 3, 500, 999])
+    coef = coef_table(t)
+    x0 = 0.6 * torch.randn(B, Cn, T, generator=g)
+    x0[0, :20, :50] = -1.3; x0[0, 20:40, :50] = 1.2
+    noise = torch.randn(B, Cn, T, generator=g)
+    xt = K.q_sample(x0.cuda(), noise.cuda(), coef.cuda())
+    xtr = R.q_sample(x0, noise, coef)
+    close(xt, xtr, 1e-6)
+    out = torch.randn(B, 2 * Cn, T, generator=g)
+    out[0, Cn:] *= 2.0
+    t0 = (t == 0).int()
+    loss, (mse, vb) = K.diff_loss_fwd(out.cuda(), x0.cuda(), xt, noise.cuda(), coef.cuda(), t0.cuda())
+    lr, (mr, vr) = R.diff_loss_fwd(out, x0, xtr, noise, coef, t0)
+    close(loss, lr, 2e-5); close(mse, mr, 2e-5); close(vb, vr, 5e-5)
+    dL = torch.tensor([1.7])
+    close(K.diff_loss_bwd(dL.cuda(), out.cuda(), x0.cuda(), xt, noise.cuda(), coef.cuda(), t0.cuda()), R.diff_loss_bwd(dL, out, x0, xtr, noise, coef, t0), 1e-4)
+
+
+def test_training_graph_vs_reference_golden(K, golden_dir):
+    """DiffusionGraph over the CUDA kernels against the REAL reference's micro-step: model output, mse / vb terms, loss, and the gradient of
+    all 232 parameter tensors (exact zeros for the dropped layers)"""
+    from test_train_diffusion_cpu import check_against_golden
+    from ttts_b200.diffusion.train_graph import DiffusionGraph
+    z = np.load(os.path.join(golden_dir, "diffusion.npz"))
+    cfg = DO.default_config(**DO.GOLDEN_CFG)
+    graph = DiffusionGraph(K, {k: v.cuda() for k, v in DO.init_params(cfg, seed=12).items()}, cfg)
+    I = DO.golden_inputs()
+    lossv, terms = graph.loss(I["x_start"].cuda(), torch.tensor(I["t"]), I["noise"].cuda(), I["latent"].cuda(), I["refer"].cuda(), I["uncond"], I["dropped"])
+    grads = graph.backward(lossv)
+    check_against_golden(z, graph, lossv, terms, grads, tol=5e-4, out_tol=3e-5, to_cpu=lambda t: t.detach().cpu())
+
+
+def test_optimisation_steps_vs_torch_loop(K):
+    """DiffusionStep with the fused clip + AdamW kernels against torch's own loop (autograd of the pinned oracle, clip_grad_norm_, AdamW,
+    LambdaLR warm-up) over 3 steps"""
+    from test_train_diffusion_cpu import reference_loop, step_batches
+    from ttts_b200.diffusion.train_step import DiffusionStep
+    cfg = DO.default_config(**DO.GOLDEN_CFG)
+    P0 = DO.init_params(cfg, seed=12)
+    batches = step_batches(3)
+    lr = 2.0
+    want_l, want_n, want_P = reference_loop(P0, cfg, batches, lr, 3)
+    ds = DiffusionStep(K, {k: v.cuda() for k, v in P0.items()}, cfg, lr=lr)
+    for s in range(3):
+        b = {k: (v.cuda() if torch.is_tensor(v) and k != "uncond" else v) for k, v in batches[s].items()}
+        b["t"] = torch.tensor(b["t"])
+        out = ds.step([b])
+        assert abs(float(out["loss"]) - want_l[s]) <= 2e-4 * abs(want_l[s]), (s, float(out["loss"]), want_l[s])
+        assert abs(float(out["grad_norm"]) - want_n[s]) <= 2e-3 * want_n[s], (s, float(out["grad_norm"]), want_n[s])
+    got = ds.opt.params()
+    num = sum(float((got[k].cpu() - want_P[k]).norm() ** 2) for k in want_P)
+    den = sum(float((want_P[k] - P0[k]).norm() ** 2) for k in want_P)
+    assert den > 0 and (num / den) ** 0.5 <= 5e-3, (num / den) ** 0.5
+
+
+def test_full_size_properties(K):
+    """BASELINE config 5 size (batch 4 of the 32 x 1024-frame shape, 512 channels, 16 heads, 6 layers): the loss is finite, per-sample terms do
+    not depend on the other samples of the batch (no cross-batch leakage in GroupNorm / attention), the graph is run-to-run bit-identical,
+    and a finite-difference step along the gradient matches <g, g>"""
+    from ttts_b200.diffusion.train_graph import DiffusionGraph
+    cfg = DO.default_config()
+    P = {k: v.cuda() for k, v in DO.init_params(cfg, seed=3).items()}
+    g = torch.Generator().manual_seed(11)
+    B, T, TL, TR = 4, 1024, 256, 200
+    x0 = (0.5 * torch.randn(B, 100, T, generator=g)).cuda()
+    noise = torch.randn(B, 100, T, generator=g).cuda()
+    latent = torch.randn(B, 512, TL, generator=g).cuda()
+    refer = (0.5 * torch.randn(B, 100, TR, generator=g)).cuda()
+    t = torch.tensor([5, 250, 700, 999])
+
+    def run(sel, params=P):
+        graph = DiffusionGraph(K, params, cfg)
+        lossv, terms = graph.loss(x0[sel].contiguous(), t[sel], noise[sel].contiguous(), latent[sel].contiguous(), refer[sel].contiguous(), None, (2,))
+        return graph, lossv, terms
+    graph, lossv, terms = run(slice(0, 4))
+    assert torch.isfinite(lossv.v).all()
+    per = (terms["mse"] + terms["vb"]).cpu()
+    _, _, terms2 = run(slice(1, 3))
+    per2 = (terms2["mse"] + terms2["vb"]).cpu()
+    assert torch.allclose(per[1:3], per2, rtol=1e-5, atol=1e-7), (per, per2)
+    grads = graph.backward(lossv)
+    graph_b, lossv_b, _ = run(slice(0, 4))
+    grads_b = graph_b.backward(lossv_b)
+    assert torch.equal(lossv.v, lossv_b.v)
+    assert all(torch.equal(grads[k], grads_b[k]) for k in grads)
+    gg = sum(float((v.double() ** 2).sum()) for v in grads.values())
+    assert gg > 0
+    h = 1e-3 / gg ** 0.5
+    lp = float(run(slice(0, 4), {k: P[k] + h * grads[k] / gg ** 0.5 for k in P})[1].v)
+    lm = float(run(slice(0, 4), {k: P[k] - h * grads[k] / gg ** 0.5 for k in P})[1].v)
+    fd = (lp - lm) / (2 * h)
+    assert abs(fd - gg ** 0.5) <= 5e-2 * gg ** 0.5, (fd, gg ** 0.5)
