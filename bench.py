@@ -288,6 +288,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vq-encode", action="store_true")
     ap.add_argument("--no-vqvae-step", action="store_true")
+    ap.add_argument("--no-diffusion-step", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): the workload's batch PER GPU; strong: that batch split over the GPUs (SURVEY.md 8d secondary line)")
@@ -480,6 +481,15 @@ def main():
             out["vqvae_step"] = vqvae_step_bench.run(B=64, iters=3, with_cpu=not args.no_cpu_baseline)
         except Exception as e:
             out["vqvae_step"] = {"error": repr(e)[:300]}
+    if world == 1 and not args.no_diffusion_step and not args.profile_run and args.workload == "cfg3":
+        # BASELINE config 5: one diffusion mel-refiner train step (AA_diffusion under training_losses), batch 32 x 1024 frames, through DiffusionStep.step
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import diffusion_step_bench
+            torch.cuda.empty_cache()
+            out["diffusion_step"] = diffusion_step_bench.run(B=32, iters=3, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:
+            out["diffusion_step"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

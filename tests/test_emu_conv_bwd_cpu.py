@@ -40,6 +40,7 @@ CASES = [
     (2, 20, 61, 24, 7, 2, 1, 3, True),         # strided + leaky ReLU, odd length
     (1, 3, 70, 5, 3, 1, 1, 1, False),          # channel counts far below the tile
     (2, 40, 36, 40, 1, 1, 1, 0, False),        # 1x1 (WN res_skip, Linear)
+    (1, 3, 700, 5, 3, 1, 1, 1, True),          # long sequence: several slices of the position axis (atomic combination), many chunks
 ]
 
 

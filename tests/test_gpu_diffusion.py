@@ -143,7 +143,7 @@ def test_optimisation_steps_vs_torch_loop(K):
 
 def test_full_size_properties(K):
     """BASELINE config 5 size (batch 4 of the 32 x 1024-frame shape, 512 channels, 16 heads, 6 layers): the loss is finite, per-sample terms do
-    not depend on the other samples of the batch (no cross-batch leakage in GroupNorm / attention), the graph is run-to-run bit-identical,
+    not depend on the other samples of the batch (no cross-batch leakage in GroupNorm / attention), the graph is run-to-run reproducible,
     and a finite-difference step along the gradient matches <g, g>"""
     from ttts_b200.diffusion.train_graph import DiffusionGraph
     cfg = DO.default_config()
@@ -169,12 +169,50 @@ def test_full_size_properties(K):
     grads = graph.backward(lossv)
     graph_b, lossv_b, _ = run(slice(0, 4))
     grads_b = graph_b.backward(lossv_b)
-    assert torch.equal(lossv.v, lossv_b.v)
-    assert all(torch.equal(grads[k], grads_b[k]) for k in grads)
-    gg = sum(float((v.double() ** 2).sum()) for v in grads.values())
-    assert gg > 0
-    h = 1e-3 / gg ** 0.5
-    lp = float(run(slice(0, 4), {k: P[k] + h * grads[k] / gg ** 0.5 for k in P})[1].v)
-    lm = float(run(slice(0, 4), {k: P[k] - h * grads[k] / gg ** 0.5 for k in P})[1].v)
-    fd = (lp - lm) / (2 * h)
-    assert abs(fd - gg ** 0.5) <= 5e-2 * gg ** 0.5, (fd, gg ** 0.5)
+    assert torch.equal(lossv.v, lossv_b.v)                          # the forward is bit-reproducible
+    # the weight-gradient kernel combines its position slices with fp32 atomics: run-to-run agreement to rounding, not to the bit
+    for k in grads:
+        assert float((grads[k] - grads_b[k]).abs().max()) <= 1e-5 * max(float(grads[k].abs().max()), 1e-12), k
+    assert sum(float((v.double() ** 2).sum()) for v in grads.values()) > 0
+
+
+def test_full_width_vs_oracle(K):
+    """the BASELINE model (512 channels, 16 heads of 32, 6 + 3 layers, RefEncoder heads of 64) at a size the fp32 CPU oracle finishes in
+    seconds (batch 2 x 256 frames, latent 64, reference 50): loss terms, model output and every gradient tensor.  (A finite-difference
+    check of the loss is NOT a valid test here: the variational-bound term detaches the mean prediction, utils/diffusion.py:980.)"""
+    from ttts_b200.diffusion.train_graph import DiffusionGraph
+    cfg = DO.default_config()
+    P0 = DO.init_params(cfg, seed=3)
+    g = torch.Generator().manual_seed(21)
+    B, T, TL, TR = 2, 256, 64, 50
+    x0 = 0.5 * torch.randn(B, 100, T, generator=g)
+    noise = torch.randn(B, 100, T, generator=g)
+    latent = torch.randn(B, 512, TL, generator=g)
+    refer = 0.5 * torch.randn(B, 100, TR, generator=g)
+    t = [40, 800]
+    uncond, dropped = torch.tensor([False, True]), (3, 7)
+    P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+    x_t = DO.q_sample(x0, t, noise)
+    out_ref = DO.model_forward(P, cfg, x_t, torch.tensor(t), latent, refer, uncond, dropped)
+    mse_ref, vb_ref = DO.loss_terms(out_ref, x0, x_t, noise, t)
+    loss_ref = (mse_ref + vb_ref).mean()
+    loss_ref.backward()
+    graph = DiffusionGraph(K, {k: v.cuda() for k, v in P0.items()}, cfg)
+    lossv, terms = graph.loss(x0.cuda(), torch.tensor(t), noise.cuda(), latent.cuda(), refer.cuda(), uncond, dropped)
+    grads = graph.backward(lossv)
+    o = terms["model_out"].v.cpu()
+    assert float((o - out_ref.detach()).abs().max()) <= 1e-4 * float(out_ref.detach().abs().max())
+    assert torch.allclose(terms["mse"].cpu(), mse_ref.detach(), rtol=1e-4) and torch.allclose(terms["vb"].cpu(), vb_ref.detach(), rtol=1e-3, atol=1e-7)
+    assert abs(float(lossv.v) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    num = den = 0.0
+    for k, p in P.items():
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        gk = grads[k].cpu()
+        n_ref = float(gr.norm())
+        if n_ref == 0.0:
+            assert float(gk.abs().max()) == 0.0, k
+            continue
+        e = float((gk - gr).norm())
+        assert e <= 2e-3 * n_ref + 1e-7, (k, e, n_ref)
+        num += e * e; den += n_ref * n_ref
+    assert (num / den) ** 0.5 <= 5e-4, (num / den) ** 0.5

@@ -15,7 +15,8 @@ def check_against_golden(z, graph, lossv, terms, grads, tol=2e-4, out_tol=2e-5, 
     out = to_cpu(terms["model_out"].v).numpy()
     assert np.abs(out - z["model_out"]).max() <= out_tol * np.abs(z["model_out"]).max(), np.abs(out - z["model_out"]).max()
     assert np.allclose(to_cpu(terms["mse"]).numpy(), z["mse"], rtol=10 * out_tol, atol=0)
-    assert np.allclose(to_cpu(terms["vb"]).numpy(), z["vb"], rtol=10 * out_tol, atol=1e-8)
+    # the t = 999 term is ~1e-6: a sum of O(1) quantities that cancel to fp32 rounding, so it carries an absolute floor
+    assert np.allclose(to_cpu(terms["vb"]).numpy(), z["vb"], rtol=10 * out_tol, atol=1e-7)
     assert abs(float(lossv.v) - float(z["loss"])) <= 10 * out_tol * abs(float(z["loss"]))
     names = [str(n) for n in z["names"]]
     assert set(names) == set(grads.keys())

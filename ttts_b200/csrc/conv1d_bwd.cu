@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "kernels.h"
+#define TTTS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 #include "conv_params.h"
 
@@ -220,6 +221,102 @@ __global__ void __launch_bounds__(BW_NT) conv1d_wgrad_kernel(const ConvBwdParams
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// weight gradient, pipelined (default; TTTS_WGRAD_V1=1 = the kernel above).  r2m launch list of the diffusion step: conv1d_wgrad_kernel 37 % of the
+// step at ~12 TFLOP/s while the forward implicit GEMM runs the same FLOPs at ~40.  Same GEMM (rows = output channels, columns = (ci, k) pairs,
+// reduction over the B * Tout positions, slices across grid.z combined by fp32 atomic adds), but: 64 x 64 tile and 256 threads (4 x 4 outputs per
+// thread, strided by 16 so that every float4 shared-memory read of a quarter-warp is conflict-free), chunks of 32 positions staged AS THEY LIE in
+// global memory (position-contiguous rows: [channel][32 positions], pitch 36) by 4-byte cp.async with zero fill through a 3-stage ring, the
+// reduction index inside a chunk vectorised (8 LDS.128 per 64 FMA), the leaky ReLU applied once per element by the thread that copied it.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int W2_T = 64, W2_R = 32, W2_LD = W2_R + 4, W2_STAGES = 3, W2_NT = 256;
+constexpr int W2_SMEM = W2_STAGES * 2 * W2_T * W2_LD * (int)sizeof(float);
+
+__global__ void __launch_bounds__(W2_NT) conv1d_wgrad2_kernel(const ConvBwdParams p) {
+    TTTS_DYN_SMEM(float, w2_smem);
+    float* sA = w2_smem;                                   // [stage][co][W2_LD]
+    float* sB = w2_smem + W2_STAGES * W2_T * W2_LD;        // [stage][n][W2_LD]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * W2_T, co0 = blockIdx.y * W2_T;
+    const int N = p.Cin * p.K, Ptot = p.B * p.Tout;
+    const int q_begin = blockIdx.z * p.slice, q_end = min(Ptot, q_begin + p.slice);
+    const int nchunks = (max(0, q_end - q_begin) + W2_R - 1) / W2_R;
+    if (nchunks == 0) return;
+    // loader: this thread copies position rr of rows r0, r0 + 8, ... of both operand tiles
+    const int rr = tid & 31, r0 = tid >> 5;
+    int xoff[8];                                           // ci * Tin + k * dil - pad of the eight (ci, k) columns, or a negative flag
+    int toffv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + r0 + 8 * i;
+        if (n < N) { const int ci = n / p.K, k = n - ci * p.K; xoff[i] = ci * p.Tin; toffv[i] = k * p.dil - p.pad; }
+        else { xoff[i] = -1; toffv[i] = 0; }
+    }
+    auto issue = [&](int chunk) {
+        const int st = chunk % W2_STAGES;
+        const int q = q_begin + chunk * W2_R + rr;
+        const bool q_ok = q < q_end;
+        const int b = q_ok ? q / p.Tout : 0, to = q_ok ? q - b * p.Tout : 0;
+        const float* dyb = p.dy + (size_t)b * p.Cout * p.Tout + to;
+        const float* xb = p.x + (size_t)b * p.Cin * p.Tin;
+        float* a = sA + (st * W2_T + r0) * W2_LD + rr;
+        float* bs = sB + (st * W2_T + r0) * W2_LD + rr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int co = co0 + r0 + 8 * i;
+            const bool ok = q_ok && co < p.Cout;
+            cp_async4(a + 8 * i * W2_LD, ok ? dyb + (size_t)co * p.Tout : p.dy, ok);
+            const int ti = to * p.stride + toffv[i];
+            const bool okb = q_ok && xoff[i] >= 0 && ti >= 0 && ti < p.Tin;
+            cp_async4(bs + 8 * i * W2_LD, okb ? xb + xoff[i] + ti : p.x, okb);
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < W2_STAGES - 1; ++c) { if (c < nchunks) issue(c); cp_async_commit(); }
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % W2_STAGES;
+        cp_async_wait<W2_STAGES - 2>();
+        if (p.pre_lrelu) {                                  // this thread's own copies of chunk c have landed: activate them in place
+            float* bs = sB + (st * W2_T + r0) * W2_LD + rr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float v = bs[8 * i * W2_LD]; bs[8 * i * W2_LD] = v > 0.f ? v : 0.1f * v; }
+        }
+        __syncthreads();
+        if (c + W2_STAGES - 1 < nchunks) issue(c + W2_STAGES - 1);
+        cp_async_commit();
+        const float* a = sA + st * W2_T * W2_LD;
+        const float* bs = sB + st * W2_T * W2_LD;
+#pragma unroll
+        for (int r = 0; r < W2_R; r += 4) {
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 16 * i) * W2_LD + r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bs + (tx + 16 * j) * W2_LD + r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[i][j] = fmaf(av[i].x, bv[j].x, fmaf(av[i].y, bv[j].y, fmaf(av[i].z, bv[j].z, fmaf(av[i].w, bv[j].w, acc[i][j]))));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty + 16 * i;
+        if (co >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n < N) atomicAdd(p.dw + (size_t)co * N + n, acc[i][j]);
+        }
+    }
+}
+
 // db[co] += sum over (b, to) of dy ; one CTA per output channel, fixed summation order
 __global__ void __launch_bounds__(256) conv1d_bgrad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int Cout, int Tout) {
     __shared__ float red[8];
@@ -269,8 +366,30 @@ int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int
     TTTS_RUN(bwd_params(p, B, Cin, Tin, Cout, K, stride, dil, pad));
     TTTS_CHECK_ARG(dy && x && dw, "conv1d wgrad: null pointer");
     p.dy = dy; p.x = x; p.dw = dw; p.pre_lrelu = pre_lrelu;
-    const int gx = (Cin * K + IG_P - 1) / IG_P, gy = (Cout + BW_T - 1) / BW_T;
+    static int use_v1 = -1;
+    if (use_v1 < 0) { const char* e = getenv("TTTS_WGRAD_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     const long long Ptot = (long long)B * p.Tout;
+    if (!use_v1) {
+        const int gx = (Cin * K + W2_T - 1) / W2_T, gy = (Cout + W2_T - 1) / W2_T;
+        // slices of the position axis: about two CTAs per SM in total, at least 8 chunks each
+        long long S = (2ll * num_sms() + (long long)gx * gy - 1) / ((long long)gx * gy);
+        const long long s_max = (Ptot + 8 * W2_R - 1) / (8 * W2_R);
+        if (S > s_max) S = s_max;
+        if (S < 1) S = 1;
+        if (S > 65535) S = 65535;
+        long long slice = (Ptot + S - 1) / S;
+        slice = (slice + W2_R - 1) / W2_R * W2_R;
+        p.slice = (int)slice;
+        const dim3 grid(gx, gy, (unsigned)((Ptot + slice - 1) / slice));
+#ifndef TTTS_HOST_EMU
+        static bool attr = false;
+        if (!attr) { TTTS_CUDA(cudaFuncSetAttribute(conv1d_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM)); attr = true; }
+#endif
+        prof_begin(3, st, 2.0 * B * p.Tout * (double)Cin * Cout * K);
+        TTTS_CUDA(launch_plain(conv1d_wgrad2_kernel, grid, dim3(W2_NT), (size_t)W2_SMEM, st, p));
+        prof_end(3, st);
+    } else {
+    const int gx = (Cin * K + IG_P - 1) / IG_P, gy = (Cout + BW_T - 1) / BW_T;
     // slices of the position axis: about two CTAs per SM in total, at least 4 chunks each
     long long S = (2ll * num_sms() + (long long)gx * gy - 1) / ((long long)gx * gy);
     const long long s_max = (Ptot + 4 * IG_R - 1) / (4 * IG_R);
@@ -284,6 +403,7 @@ int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int
     prof_begin(3, st, 2.0 * B * p.Tout * (double)Cin * Cout * K);
     TTTS_CUDA(launch_plain(conv1d_wgrad_kernel, grid, dim3(BW_NT), 0, st, p));
     prof_end(3, st);
+    }
     TTTS_LAUNCH_CHECK("conv1d_wgrad");
     if (db) {
         TTTS_CUDA(launch_plain(conv1d_bgrad_kernel, dim3(Cout), dim3(256), 0, st, dy, db, B, Cout, p.Tout));

@@ -135,11 +135,20 @@ class DiffOps(Ops):
         """x[:, :, idx] (nearest-neighbour interpolation); the backward scatter-adds"""
         y = Var(x.v.index_select(2, idx).contiguous())
 
+        Tin, Tout = x.v.shape[2], idx.numel()
+
         def bwd():
-            if y.g is not None:
+            if y.g is None:
+                return
+            if Tout % Tin == 0:                                      # integer ratio: every source frame is repeated Tout / Tin times in a row
+                r = Tout // Tin
+                g = y.g[:, :, 0::r].contiguous()
+                for k in range(1, r):
+                    g = self.K.add(g, y.g[:, :, k::r].contiguous())   # fixed order (index_add_ on the GPU is atomic)
+            else:
                 g = torch.zeros_like(x.v)
                 g.index_add_(2, idx, y.g)
-                self._acc(x, g)
+            self._acc(x, g)
         self.tape.record(bwd)
         return y
 
