@@ -216,3 +216,35 @@ def test_full_width_vs_oracle(K):
         assert e <= 2e-3 * n_ref + 1e-7, (k, e, n_ref)
         num += e * e; den += n_ref * n_ref
     assert (num / den) ** 0.5 <= 5e-4, (num / den) ** 0.5
+
+
+def test_trainer_surface_save_load(K, tmp_path):
+    """ttts_b200.diffusion.train.Trainer (the surface of ttts/diffusion/train.py:78-256) on batches in DiffusionCollater's layout: the warm-up
+    makes step 0 a no-op (lr 0), later steps move the parameters, a checkpoint {'step', 'model'} round-trips with the reference's keys"""
+    from ttts_b200.diffusion.params import param_shapes
+    from ttts_b200.diffusion.train import Trainer
+    cfg = DO.default_config(**DO.GOLDEN_CFG)
+
+    class FrozenGPT:                                               # stands in for UnifiedVoice(return_latent=True): [B, CL, in_latent_channels]
+        mel_length_compression = 1024
+
+        def __call__(self, text, tl, codes, wl, return_latent=True, clip_inputs=False):
+            g = torch.Generator().manual_seed(int(codes.sum()) % 1000)
+            return torch.randn(codes.shape[0], codes.shape[1], cfg["in_latent_channels"], generator=g).cuda()
+    g = torch.Generator().manual_seed(0)
+    batches = [dict(padded_text=torch.randint(0, 200, (3, 9), generator=g), padded_mel_code=torch.randint(0, 1024, (3, 6), generator=g),
+                    padded_mel=2 * torch.randn(3, 100, 24, generator=g) - 5, padded_mel_refer=2 * torch.randn(3, 100, 10, generator=g) - 5) for _ in range(2)]
+    batches.insert(1, None)                                        # a batch whose samples all failed to load is skipped (train.py:158-159)
+    P0 = {k: v.cuda() for k, v in DO.init_params(cfg, seed=12).items()}
+    tr = Trainer(FrozenGPT(), batches, cfg=cfg, lr=1.0, train_steps=3, params=P0)
+    logs = []
+    tr.train(log=lambda s, out: logs.append((s, float(out["loss"]), float(out["grad_norm"]))))
+    assert [s for s, _, _ in logs] == [1, 2, 3] and all(np.isfinite(l) and np.isfinite(n) for _, l, n in logs)
+    sd = tr.state_dict()
+    assert set(sd.keys()) == set(param_shapes(cfg).keys()) and all(tuple(sd[k].shape) == param_shapes(cfg)[k] for k in sd)
+    assert any(float((sd[k] - P0[k]).abs().max()) > 0 for k in sd)
+    path = str(tmp_path / "model-0.pt")
+    tr.save(path)
+    tr2 = Trainer(FrozenGPT(), batches, cfg=cfg, lr=1.0, train_steps=3, params={k: torch.zeros_like(v) for k, v in P0.items()})
+    tr2.load(path)
+    assert tr2.step == 3 and all(torch.equal(tr2.state_dict()[k], sd[k]) for k in sd)

@@ -57,12 +57,12 @@ __global__ void gconv_dgrad_kernel(const GConvParams p) {
             const int co = g * og + o;
             const float* dr = p.dy + ((size_t)b * p.Cout + co) * p.Tout;
             const float* wr = p.w + ((size_t)co * cg + c) * p.K;
-            for (int k = 0; k < p.K; ++k) {
-                const int num = ti + p.pad - k;
-                if (num < 0) break;                                    // larger k only makes it more negative
-                const int to = num / p.stride;
-                if (to * p.stride == num && to < p.Tout) s = fmaf(wr[k], dr[to], s);
-            }
+            // only the taps k = (ti + pad) mod stride, + stride, ... meet this position: to = (ti + pad - k) / stride falls by one per step
+            // (the first version tested all K taps with a division each: gconv_dgrad_kernel was 14 % of the VQ-VAE-GAN step, r2o launch list)
+            int k = (ti + p.pad) % p.stride;
+            int to = (ti + p.pad - k) / p.stride;
+            for (; k < p.K && to >= 0; k += p.stride, --to)
+                if (to < p.Tout) s = fmaf(wr[k], dr[to], s);
         }
         p.dx[i] = s;
     }

@@ -487,6 +487,31 @@ class EncoderGraph:
         return {k: (v.g.reshape(self.shapes[k]) if v.g is not None else torch.zeros(self.shapes[k], device=v.v.device)) for k, v in self.P.items()}
 
 
+def dgrad_by_phase(conv1d_fn, dy, w, Tin, stride, pad):
+    """Input gradient of a STRIDED convolution (dilation 1) as `stride` independent stride-1 convolutions, one per phase of the input
+    position: ti + pad = stride q + phi only meets the taps k = phi + stride j, so
+        dx[ci, stride q + phi - pad] = sum_co sum_j w[co, ci, phi + stride j] dy[co, q - j]
+    -- a "full" correlation of dy with the phase's sub-kernel (K / stride taps).  conv1d_dgrad_kernel walks ALL K taps for every position and
+    multiplies zeros for (stride - 1) / stride of them (the down-sampling stack has stride 10 / kernel 16: 90 % waste); the phases together
+    do exactly the useful FLOPs, on the pipelined forward kernels.  ConvTranspose1d's forward is the same operation (Generator.ups).
+    conv1d_fn(x, w, pad) = stride-1 cross-correlation; dy [B,Cout,Tout], w [Cout,Cin,K] -> dx [B,Cin,Tin]."""
+    B, Cout, Tout = dy.shape
+    Cin, K = w.shape[1], w.shape[2]
+    dx = torch.zeros(B, Cin, Tin, dtype=dy.dtype, device=dy.device)
+    for phi in range(min(stride, K)):
+        J = (K - phi + stride - 1) // stride                        # taps phi, phi + stride, ... < K
+        wt = w[:, :, phi::stride].flip(2).transpose(0, 1).contiguous()          # [Cin, Cout, J], tap order reversed
+        out = conv1d_fn(dy, wt, J - 1)                                # [B, Cin, Tout + J - 1]: out[q] = sum_j w_phi[j] dy[q - j]
+        q_min = max(0, -((phi - pad) // stride))                     # first q with stride q + phi - pad >= 0
+        t0 = stride * q_min + phi - pad
+        if t0 >= Tin:
+            continue
+        n = min((Tin - 1 - t0) // stride + 1, out.shape[2] - q_min)
+        if n > 0:
+            dx[:, :, t0:t0 + stride * (n - 1) + 1:stride] = out[:, :, q_min:q_min + n]
+    return dx
+
+
 class CudaKernels:
     """The product backend: every method is one call (conv_bwd: two) into libttts_b200.so on the current stream.  Device tensors only."""
 
@@ -602,6 +627,10 @@ class CudaKernels:
             assert dx.shape == x.shape
             if pre_lrelu:
                 self._chk(lib.ttts_lrelu(p(x), p(dx), p(dx), x.numel(), 0.1, 1, st), "ttts_lrelu (dgrad)")
+        elif need_dx and stride > 1 and dil == 1 and self.dgrad_as_forward and hasattr(self.E, "conv1d") and dy.is_cuda:
+            dx = dgrad_by_phase(lambda a, wt, pd: self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False), dy, w, Tin, stride, pad)
+            if pre_lrelu:
+                self._chk(lib.ttts_lrelu(p(x), p(dx), p(dx), x.numel(), 0.1, 1, st), "ttts_lrelu (dgrad)")
         elif need_dx:
             dx = torch.empty_like(x)
             self._chk(lib.ttts_conv1d_bwd_input(p(dy), p(w), p(x), p(dx), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), 0, st), "ttts_conv1d_bwd_input")
@@ -616,9 +645,12 @@ class CudaKernels:
         B, Cin, T = x.shape
         _, Cout, K = w.shape
         Tout = (T - 1) * stride - 2 * pad + K
-        y = torch.empty(B, Cout, Tout, dtype=torch.float32, device=x.device)
         p, lib, st = self._p, self.lib, self._st()
-        self._chk(lib.ttts_conv1d_bwd_input(p(x), p(w), None, p(y), B, Cout, Tout, Cin, K, stride, 1, pad, 0, 0, st), "ttts_conv1d_bwd_input (convT forward)")
+        if self.dgrad_as_forward and hasattr(self.E, "conv1d") and x.is_cuda:
+            y = dgrad_by_phase(lambda a, wt, pd: self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False), x, w, Tout, stride, pad)
+        else:
+            y = torch.empty(B, Cout, Tout, dtype=torch.float32, device=x.device)
+            self._chk(lib.ttts_conv1d_bwd_input(p(x), p(w), None, p(y), B, Cout, Tout, Cin, K, stride, 1, pad, 0, 0, st), "ttts_conv1d_bwd_input (convT forward)")
         if b is not None:
             self._chk(lib.ttts_add_bcast(p(y), p(b), p(y), B, Cout, Tout, 0, st), "ttts_add_bcast (bias)")
         return y
