@@ -90,3 +90,25 @@ def test_q_sample_and_loss(K):
     close(loss, lr, 1e-5); close(mse, mr, 1e-5); close(vb, vr, 2e-5)
     dL = torch.tensor([1.7])
     close(K.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), R.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), 5e-5)
+
+
+@pytest.mark.parametrize("B,C,T", [(2, 40, 37), (1, 64, 64), (3, 7, 5)])
+def test_layout_conversion_kernels(K, B, C, T):
+    """ttts_cl_split / ttts_cl_unpack: [B,C,T] fp32 <-> position-major split-bf16 rows with zero rows between the clips"""
+    g = torch.Generator().manual_seed(B + C + T)
+    x = torch.randn(B, C, T, generator=g) * 3
+    buf = K._cl_split("x", x)
+    assert tuple(buf.shape) == (2 + B * (T + 1), 2 * C)
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    want = torch.zeros_like(buf)
+    for b in range(B):
+        want[1 + b * (T + 1):1 + b * (T + 1) + T, :C] = hi[b].t()
+        want[1 + b * (T + 1):1 + b * (T + 1) + T, C:] = lo[b].t()
+    assert torch.equal(buf, want)
+    # hi + lo reproduces x to ~2^-16 relative
+    rec = (buf[:, :C].float() + buf[:, C:].float())[1:1 + B * (T + 1)].reshape(B, T + 1, C)[:, :T].transpose(1, 2)
+    assert float((rec - x).abs().max()) <= 2 ** -15 * float(x.abs().max())
+    D = torch.randn(B * (T + 1), C + 8, generator=g)
+    y = K._cl_unpack(D, B, C, T)
+    assert torch.equal(y, D[:, :C].reshape(B, T + 1, C)[:, :T].transpose(1, 2).contiguous())

@@ -248,3 +248,32 @@ def test_trainer_surface_save_load(K, tmp_path):
     tr2 = Trainer(FrozenGPT(), batches, cfg=cfg, lr=1.0, train_steps=3, params={k: torch.zeros_like(v) for k, v in P0.items()})
     tr2.load(path)
     assert tr2.step == 3 and all(torch.equal(tr2.state_dict()[k], sd[k]) for k in sd)
+
+
+@pytest.mark.parametrize("B,Cin,T,Cout,Kw", [(4, 512, 600, 512, 3), (2, 1024, 1030, 512, 1), (3, 128, 700, 192, 3), (2, 512, 1024, 1536, 1)])
+def test_tensor_core_convolution_vs_torch(K, B, Cin, T, Cout, Kw):
+    """the split-bf16 tcgen05 path of the wide stride-1 convolutions (forward, input gradient, weight and bias gradient) against torch's fp32
+    convolution: fp32-grade agreement (three bf16 products per fp32 product), and it is actually taken for these shapes"""
+    g = torch.Generator().manual_seed(Cin + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, Kw, generator=g) / (Cin * Kw) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, T, generator=g)
+    pad = (Kw - 1) // 2
+    xc, wc, bc, dyc = cu(x, w, b, dy)
+    assert K._tc_ok(xc, wc, 1, 1, pad, False, 1)
+    xr, wr, br = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yr = torch.nn.functional.conv1d(xr.double(), wr.double(), br.double(), padding=pad)
+        yr.backward(dyc.double())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    y = K.conv_fwd(xc, wc, bc, 1, 1, pad, False)
+    dx, dw, db = K.conv_bwd(dyc, xc, wc, 1, 1, pad, False, True, True)
+    rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm())
+    assert rel(y, yr) <= 2e-5, rel(y, yr)
+    assert rel(dx, xr.grad) <= 2e-5, rel(dx, xr.grad)
+    assert rel(dw, wr.grad) <= 2e-5, rel(dw, wr.grad)
+    assert rel(db, br.grad) <= 1e-5

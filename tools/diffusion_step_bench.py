@@ -76,8 +76,13 @@ def run(B=32, iters=3, with_cpu=False, cpu_batch=2):
            "flop_model": "3 x forward FLOP (2 Cin Cout K T per convolution, 4 T^2 C per attention), no layer dropped: %.3e per sample and step" % (3.0 * flop_model(cfg)),
            "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"])}
     fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-    res["roofline"] = {"bound": "fp32 FMA pipe (exact-fp32 CUDA-core kernels)", "achieved": res["step_tflops"], "peak": fma_peak, "unit": "TFLOP/s",
-                       "frac": res["step_tflops"] / fma_peak, "traffic": None, "note": "whole step against the fp32 FMA peak"}
+    tc = os.environ.get("TTTS_DIFF_TC", "1") != "0"
+    res["dtype"] = "f32 (wide convolutions: split-bf16 tcgen05, 3 bf16 products per fp32 product; attention / norms / loss: fp32 CUDA cores)" if tc else "f32"
+    res["conv_path"] = "ttts_gemm_bf16 (tcgen05) with split-bf16 operands" if tc else "fp32 implicit GEMM on CUDA cores"
+    res["roofline"] = {"bound": "fp32 FMA pipe (attention, the dominant kernels after the convolutions moved to tcgen05)" if tc else "fp32 FMA pipe (exact-fp32 CUDA-core kernels)",
+                       "achieved": res["step_tflops"], "peak": fma_peak, "unit": "TFLOP/s", "frac": res["step_tflops"] / fma_peak, "traffic": None,
+                       "note": "whole step (3 x forward FLOP, attention recompute not counted) against the fp32 FMA peak; with the convolutions on the "
+                               "tensor cores the fraction can exceed what CUDA cores alone could reach"}
     if with_cpu:
         try:
             res["cpu_baseline"] = cpu_reference_step(cpu_batch)

@@ -518,6 +518,52 @@ __global__ void diff_loss_bwd_kernel(const float* __restrict__ dL, const float* 
     }
 }
 
+
+// ---------------------------------------------------------------- layout conversion for the tensor-core convolutions ----------------------------------------------------------------
+// The 512-channel 1x1 / K = 3 convolutions of AA_diffusion are GEMMs; they run on ttts_gemm_bf16 (tcgen05) with split-bf16 operands
+// (x = hi + lo, w = hi + lo, y ~ hi hi + hi lo + lo hi with fp32 accumulation: fp32-grade results, ttts_b200/diffusion/kernels.py).
+// The GEMM wants position-major rows, the tape keeps [B, C, T]: these two kernels convert.
+//   cl_split : x [B, C, T] fp32 -> rows [hi(x[b, :, t]) | lo(x[b, :, t])] (2C bf16) at row 1 + b (T + 1) + t of a [2 + B (T + 1), 2C] buffer whose
+//              other rows (one leading, one after every clip, one trailing) stay ZERO: a tap of a K = 3 convolution is the same buffer read one
+//              row earlier / later, and no tap reads a neighbouring clip.  The zero rows are never written (the buffer is zero-initialised once).
+//   cl_unpack: D [B (T + 1), ld] fp32 (row b (T + 1) + t) -> y [B, C, T]
+// 32 x 32 tiles through shared memory: coalesced along time on the [B, C, T] side, along channels on the other.
+__global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int C, int T) {
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, t = t0 + tx;
+        tile[j][tx] = (c < C && t < T) ? x[((size_t)b * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i, c = c0 + tx;
+        if (t < T && c < C) {
+            const float v = tile[tx][i];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            uint16_t* row = out + ((size_t)1 + (size_t)b * (T + 1) + t) * (2 * (size_t)C);
+            row[c] = *reinterpret_cast<const uint16_t*>(&h);
+            row[C + c] = *reinterpret_cast<const uint16_t*>(&l);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict__ D, float* __restrict__ y, int C, int T, int ld) {
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i, c = c0 + tx;
+        tile[i][tx] = (t < T && c < C) ? D[((size_t)b * (T + 1) + t) * ld + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, t = t0 + tx;
+        if (c < C && t < T) y[((size_t)b * C + c) * T + t] = tile[tx][j];
+    }
+}
+
 static inline unsigned df_blocks(size_t n) {
     size_t b = (n + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -669,5 +715,20 @@ extern "C" int ttts_diff_loss_bwd(const float* dL, const float* model_out, const
     TTTS_CUDA(launch_plain(diff_loss_bwd_kernel, dim3(df_blocks((size_t)B * per)), dim3(256), 0, (cudaStream_t)stream, dL, model_out, x_start, x_t, noise,
                            coef, t_is0, dout, B, per));
     TTTS_LAUNCH_CHECK("diff_loss_bwd");
+    return TTTS_OK;
+}
+
+/* x [B,C,T] fp32 -> split-bf16 position-major rows [hi | lo] of a zero-initialised [2 + B (T + 1), 2C] bf16 buffer (see cl_split_kernel) */
+extern "C" int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, void* stream) {
+    TTTS_CHECK_ARG(x && out_bf16 && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && (C + 31) / 32 <= 65535, "cl_split: bad args");
+    TTTS_CUDA(launch_plain(cl_split_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, x, (uint16_t*)out_bf16, C, T));
+    TTTS_LAUNCH_CHECK("cl_split");
+    return TTTS_OK;
+}
+/* D [B (T + 1), ld] fp32 position-major -> y [B,C,T] */
+extern "C" int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, void* stream) {
+    TTTS_CHECK_ARG(D && y && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && ld >= C && (C + 31) / 32 <= 65535, "cl_unpack: bad args");
+    TTTS_CUDA(launch_plain(cl_unpack_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, D, y, C, T, ld));
+    TTTS_LAUNCH_CHECK("cl_unpack");
     return TTTS_OK;
 }
