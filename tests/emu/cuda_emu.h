@@ -46,6 +46,7 @@ struct float4 { float x, y, z, w; };
 inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+inline float2 make_float2(float a, float b) { return float2{a, b}; }
 typedef void* cudaStream_t;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F> inline int cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }

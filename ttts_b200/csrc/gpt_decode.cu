@@ -39,6 +39,7 @@ namespace ttts {
 
 constexpr float kDecLnEps = 1e-5f;
 constexpr int DEC_SPLIT_MAX = 16;      // K slices of a matrix-vector sweep (partials are summed by the consumer in slice order: deterministic)
+constexpr int DEC_PF = 8;              // weight rows per warp requested ahead of griddepcontrol.wait in the sweep
 constexpr int DEC_BT = 4;              // sequences per CTA of the sweep (weights are re-read from L2 for the next group)
 
 // block-wide sum for 256 threads (8 warps); `red` holds >= 8 floats; safe to call back to back (trailing barrier)
@@ -96,8 +97,14 @@ __global__ void __launch_bounds__(256) dec_rowop_kernel(const RowopArgs a) {
             const int c = tid + 256 * i;
             float acc = 0.f;
             if (c < d) {
-                for (int s = 0; s < a.S; ++s) acc += a.part[((size_t)s * a.B + b) * d + c];
-                acc = a.resid[(size_t)b * d + c] + bf16_round(acc + a.bias[c]);
+                // all slices requested before the first add (a run-time loop made 16 DEPENDENT L2 round trips: dec_rowop was 20 us, r2s)
+                float ps[DEC_SPLIT_MAX];
+#pragma unroll
+                for (int s = 0; s < DEC_SPLIT_MAX; ++s) ps[s] = s < a.S ? a.part[((size_t)s * a.B + b) * d + c] : 0.f;
+                const float rv = a.resid[(size_t)b * d + c], bv = a.bias[c];
+#pragma unroll
+                for (int s = 0; s < DEC_SPLIT_MAX; ++s) acc += ps[s];
+                acc = rv + bf16_round(acc + bv);
             }
             v[i] = acc;
         }
@@ -144,11 +151,21 @@ __global__ void __launch_bounds__(256) dec_gemv_kernel(const bf16* __restrict__ 
     TTTS_DYN_SMEM(float, dec_smem);
     float* xs = dec_smem;                       // [BT][ks]
     float* red = dec_smem + BT * ks;            // [8][BT][256]
-    pdl_launch_dependents();
-    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k0 = blockIdx.y * ks, b0 = blockIdx.z * BT;
     const int n0 = blockIdx.x * 256 + lane * 8;
+    // The weights do not depend on the previous kernel: the first DEC_PF rows of this warp are requested BEFORE griddepcontrol.wait, so the
+    // weight stream -- the only HBM traffic of a decode step that matters -- overlaps the tail of the producer instead of starting after it
+    // (r2s launch list: 8.3 us per sweep for 2 - 8 MB of weights, i.e. latency, not bandwidth).
+    const bf16* wp = W + (size_t)k0 * N + n0;
+    uint4 wpre[DEC_PF];
+#pragma unroll
+    for (int j = 0; j < DEC_PF; ++j) {
+        const int k = warp + 8 * j;
+        wpre[j] = (n0 < N && k < ks) ? __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * N)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = tid; i < BT * ks; i += 256) {
         const int bt = i / ks, k = i - bt * ks;
         xs[i] = (b0 + bt < B) ? __bfloat162float(x16[(size_t)(b0 + bt) * K + k0 + k]) : 0.f;
@@ -160,9 +177,22 @@ __global__ void __launch_bounds__(256) dec_gemv_kernel(const bf16* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[bt][j] = 0.f;
     if (n0 < N) {
-        const bf16* wp = W + (size_t)k0 * N + n0;
+#pragma unroll
+        for (int jp = 0; jp < DEC_PF; ++jp) {
+            const int k = warp + 8 * jp;
+            if (k < ks) {
+                const uint4 w = wpre[jp];
+                const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) {
+                    const float xv = xs[bt * ks + k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[bt][j] = fmaf(xv, wf[j], acc[bt][j]);
+                }
+            }
+        }
 #pragma unroll 4
-        for (int k = warp; k < ks; k += 8) {
+        for (int k = warp + 8 * DEC_PF; k < ks; k += 8) {
             const uint4 w = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * N));
             const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
 #pragma unroll
@@ -215,10 +245,14 @@ __global__ void __launch_bounds__(128) dec_attn_kernel(const float* __restrict__
     if (tid < 64) {
         float q = 0.f, k = 0.f, v = 0.f;
         const size_t col = (size_t)h * 64 + tid;
-        for (int s = 0; s < S; ++s) {
-            const float* p = part + ((size_t)s * B + b) * 3 * d;
-            q += p[col]; k += p[d + col]; v += p[2 * d + col];
+        float pq[DEC_SPLIT_MAX], pk[DEC_SPLIT_MAX], pv[DEC_SPLIT_MAX];
+#pragma unroll
+        for (int s = 0; s < DEC_SPLIT_MAX; ++s) {
+            const float* p = part + ((size_t)(s < S ? s : 0) * B + b) * 3 * d;
+            pq[s] = s < S ? p[col] : 0.f; pk[s] = s < S ? p[d + col] : 0.f; pv[s] = s < S ? p[2 * d + col] : 0.f;
         }
+#pragma unroll
+        for (int s = 0; s < DEC_SPLIT_MAX; ++s) { q += pq[s]; k += pk[s]; v += pv[s]; }
         q = bf16_round(q + bias[col]);
         kc[(size_t)slot * 64 + tid] = __float2bfloat16_rn(k + bias[d + col]);
         vc[(size_t)slot * 64 + tid] = __float2bfloat16_rn(v + bias[2 * d + col]);
@@ -283,10 +317,12 @@ __global__ void __launch_bounds__(256) dec_act_kernel(const float* __restrict__ 
     const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
     if (n >= N) return;
     float a0 = 0.f, a1 = 0.f;
-    for (int s = 0; s < S; ++s) {
-        const float2 p = *reinterpret_cast<const float2*>(part + ((size_t)s * B + b) * N + n);
-        a0 += p.x; a1 += p.y;
-    }
+    float2 ps[DEC_SPLIT_MAX];
+#pragma unroll
+    for (int s = 0; s < DEC_SPLIT_MAX; ++s)
+        ps[s] = s < S ? *reinterpret_cast<const float2*>(part + ((size_t)s * B + b) * N + n) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < DEC_SPLIT_MAX; ++s) { a0 += ps[s].x; a1 += ps[s].y; }
     const uint32_t pre = pack_bf16(a0 + bias[n], a1 + bias[n + 1]);
     *reinterpret_cast<uint32_t*>(act16 + (size_t)b * N + n) = gelu_new_bf2(pre);
 }
@@ -295,17 +331,17 @@ __global__ void __launch_bounds__(256) dec_act_kernel(const float* __restrict__ 
 // one warp per vocabulary row (its d bf16 weights stay in registers for all sequences), 8 rows per CTA.
 __global__ void __launch_bounds__(256) dec_head_kernel(const bf16* __restrict__ enc16, const bf16* __restrict__ Wh, const float* __restrict__ bias,
                                                        int B, int d, int V, float* __restrict__ logits) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (v >= V) return;
     uint4 w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i) {                                   // weights are requested ahead of the dependency wait (see dec_gemv)
         const int c = (i * 32 + lane) * 8;
-        w[i] = c < d ? __ldg(reinterpret_cast<const uint4*>(Wh + (size_t)v * d + c)) : make_uint4(0, 0, 0, 0);
+        w[i] = (v < V && c < d) ? __ldg(reinterpret_cast<const uint4*>(Wh + (size_t)v * d + c)) : make_uint4(0, 0, 0, 0);
     }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (v >= V) return;
     const float bv = bias[v];
     for (int b = 0; b < B; ++b) {
         float s = 0.f;
