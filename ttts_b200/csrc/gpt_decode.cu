@@ -222,6 +222,149 @@ __global__ void __launch_bounds__(256) dec_gemv_kernel(const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
+// dec_gemv_fused: the sweep with its INPUT computed in the prologue of every CTA instead of by a kernel of its own (r2t launch list: after the
+// latency fixes a step is still ~200 launches of ~5 us; dec_rowop and dec_act are 2 + 1 of the 8 launches of a layer and do microseconds of work).
+//   MODE 1: x = bf16(LN(resid + bf16(bias + sum_s part_in[s]))) -- the residual add + LayerNorm of dec_rowop.  Every CTA needs the whole row for
+//           the statistics (64 KB of L2-resident partials); CTA (0, 0, z) also writes the new residual row, into the OTHER residual buffer
+//           (the CTAs of one launch read the old one at different times).
+//   MODE 2: x = gelu_new(bf16(bias + sum_s part_in[s])) of this CTA's K slice -- dec_act.
+// Same arithmetic and rounding points as the separate kernels: bit-identical results.  part_in and part are different buffers.
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct GemvPro {
+    const float* part_in; int S_in;      // [S_in][B][K]
+    const float* bias_in;               // [K]
+    const float* resid_in; float* resid_out; const float *ln_w, *ln_b;      // MODE 1
+};
+
+template <int BT, int MODE>
+__global__ void __launch_bounds__(256) dec_gemv_fused_kernel(const GemvPro g, const bf16* __restrict__ W, float* __restrict__ part, int K, int N, int B, int ks) {
+    TTTS_DYN_SMEM(float, dec_smem);
+    __shared__ float red8[8];
+    float* xs = dec_smem;                       // [BT][ks]
+    float* red = dec_smem + BT * ks;            // [8][BT][256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = blockIdx.y * ks, b0 = blockIdx.z * BT;
+    const int n0 = blockIdx.x * 256 + lane * 8;
+    const bf16* wp = W + (size_t)k0 * N + n0;
+    uint4 wpre[DEC_PF];
+#pragma unroll
+    for (int j = 0; j < DEC_PF; ++j) {
+        const int k = warp + 8 * j;
+        wpre[j] = (n0 < N && k < ks) ? __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * N)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (MODE == 1) {
+        const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
+        for (int bt = 0; bt < BT; ++bt) {
+            const int b = b0 + bt;
+            if (b >= B) {                                             // uniform per CTA
+                for (int k = tid; k < ks; k += 256) xs[bt * ks + k] = 0.f;
+                continue;
+            }
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tid + 256 * i;
+                float acc = 0.f;
+                if (c < K) {
+                    float ps[DEC_SPLIT_MAX];
+#pragma unroll
+                    for (int sl = 0; sl < DEC_SPLIT_MAX; ++sl) ps[sl] = sl < g.S_in ? g.part_in[((size_t)sl * B + b) * K + c] : 0.f;
+                    const float rv = g.resid_in[(size_t)b * K + c], bv = g.bias_in[c];
+#pragma unroll
+                    for (int sl = 0; sl < DEC_SPLIT_MAX; ++sl) acc += ps[sl];
+                    acc = rv + bf16_round(acc + bv);
+                    if (writer) g.resid_out[(size_t)b * K + c] = acc;
+                }
+                v[i] = acc;
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sum += (tid + 256 * i < K) ? v[i] : 0.f;
+            const float mean = block_sum_256(sum, red8) / (float)K;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float t = v[i] - mean; q += (tid + 256 * i < K) ? t * t : 0.f; }
+            const float rstd = rsqrtf(block_sum_256(q, red8) / (float)K + kDecLnEps);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tid + 256 * i;
+                if (c >= k0 && c < k0 + ks) xs[bt * ks + c - k0] = bf16_round((v[i] - mean) * rstd * g.ln_w[c] + g.ln_b[c]);
+            }
+        }
+    } else {
+        const int half = ks >> 1;
+        for (int i = tid; i < BT * half; i += 256) {
+            const int bt = i / half, kp = i - bt * half, b = b0 + bt;
+            float x0 = 0.f, x1 = 0.f;
+            if (b < B) {
+                const int n = k0 + 2 * kp;
+                float2 ps[DEC_SPLIT_MAX];
+#pragma unroll
+                for (int sl = 0; sl < DEC_SPLIT_MAX; ++sl)
+                    ps[sl] = sl < g.S_in ? *reinterpret_cast<const float2*>(g.part_in + ((size_t)sl * B + b) * K + n) : make_float2(0.f, 0.f);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < DEC_SPLIT_MAX; ++sl) { a0 += ps[sl].x; a1 += ps[sl].y; }
+                const uint32_t r = gelu_new_bf2(pack_bf16(a0 + g.bias_in[n], a1 + g.bias_in[n + 1]));
+                x0 = bf16_lo(r); x1 = bf16_hi(r);
+            }
+            xs[bt * ks + 2 * kp] = x0; xs[bt * ks + 2 * kp + 1] = x1;
+        }
+    }
+    __syncthreads();
+    float acc[BT][8];
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[bt][j] = 0.f;
+    if (n0 < N) {
+#pragma unroll
+        for (int jp = 0; jp < DEC_PF; ++jp) {
+            const int k = warp + 8 * jp;
+            if (k < ks) {
+                const uint4 w = wpre[jp];
+                const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) {
+                    const float xv = xs[bt * ks + k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[bt][j] = fmaf(xv, wf[j], acc[bt][j]);
+                }
+            }
+        }
+#pragma unroll 4
+        for (int k = warp + 8 * DEC_PF; k < ks; k += 8) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * N));
+            const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                const float xv = xs[bt * ks + k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[bt][j] = fmaf(xv, wf[j], acc[bt][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(warp * BT + bt) * 256 + lane * 8 + j] = acc[bt][j];
+    __syncthreads();
+    const int n = blockIdx.x * 256 + tid;
+    if (n < N) {
+#pragma unroll
+        for (int bt = 0; bt < BT; ++bt) {
+            if (b0 + bt >= B) break;
+            float sm = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sm += red[(w * BT + bt) * 256 + tid];
+            part[((size_t)blockIdx.y * B + b0 + bt) * N + n] = sm;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
 // dec_attn: one CTA per (head, sequence), 128 threads.                     HF: modeling_gpt2.py:185-220 with layer_past
 //   q,k,v[0..63] = bf16(bias + sum_s part[s][b][{0,d,2d} + 64 h + j]) ; k,v -> cache row `slot` ; scores over rows 0..slot (the causal
 //   mask of a single query is "everything cached"), softmax in fp32, probabilities rounded to bf16 for P.V, fp32 normaliser.
@@ -384,16 +527,18 @@ __global__ void __launch_bounds__(128) dec_kv_fill_kernel(const bf16* __restrict
 // ---------------------------------------------------------------------------------------------------------------------------------
 static inline int64_t up256(int64_t n) { return (n + 255) / 256 * 256; }
 
-struct DecWorkspace { int64_t resid, xn16, att16, act16, part, total; };
+struct DecWorkspace { int64_t resid, resid2, xn16, att16, act16, part, part2, total; };
 static DecWorkspace dec_carve(int B, int d) {
     DecWorkspace w;
     int64_t o = 0;
     auto put = [&](int64_t bytes) { int64_t r = o; o += up256(bytes); return r; };
     w.resid = put((int64_t)B * d * 4);
+    w.resid2 = put((int64_t)B * d * 4);
     w.xn16 = put((int64_t)B * d * 2);
     w.att16 = put((int64_t)B * d * 2);
     w.act16 = put((int64_t)B * 4 * d * 2);
     w.part = put((int64_t)DEC_SPLIT_MAX * B * 4 * d * 4);
+    w.part2 = put((int64_t)DEC_SPLIT_MAX * B * 4 * d * 4);
     w.total = o;
     return w;
 }
@@ -418,6 +563,21 @@ static int dec_gemv(const bf16* x16, const bf16* W, float* part, int K, int N, i
     TTTS_CHECK_ARG(smem <= 48 * 1024, "decode: gemv slice of %d rows needs %zu bytes of shared memory", ks, smem);
     TTTS_CUDA(launch_pdl(dec_gemv_kernel<DEC_BT>, grid, dim3(256), smem, st, x16, W, part, K, N, B, ks));
     TTTS_LAUNCH_CHECK("dec_gemv");
+    *S_out = S;
+    return TTTS_OK;
+}
+
+template <int MODE>
+static int dec_gemv_fused(const GemvPro& g, const bf16* W, float* part, int K, int N, int B, int* S_out, cudaStream_t st) {
+    const int S = dec_pick_split(K, N, B);
+    const int ks = K / S;
+    TTTS_CHECK_ARG(K % S == 0 && N % 8 == 0 && ks % 2 == 0 && (MODE != 1 || K <= 1024), "decode: fused gemv shape K=%d N=%d", K, N);
+    TTTS_CHECK_ARG(g.part_in != part, "decode: fused gemv reads and writes the same partial buffer");
+    const dim3 grid((N + 255) / 256, S, (B + DEC_BT - 1) / DEC_BT);
+    const size_t smem = ((size_t)DEC_BT * ks + 8 * DEC_BT * 256) * sizeof(float);
+    TTTS_CHECK_ARG(smem <= 48 * 1024, "decode: gemv slice of %d rows needs %zu bytes of shared memory", ks, smem);
+    TTTS_CUDA(launch_pdl(dec_gemv_fused_kernel<DEC_BT, MODE>, grid, dim3(256), smem, st, g, W, part, K, N, B, ks));
+    TTTS_LAUNCH_CHECK("dec_gemv_fused");
     *S_out = S;
     return TTTS_OK;
 }
@@ -456,6 +616,15 @@ int gpt_decode_step(const ttts_gpt_decode* a, cudaStream_t st) {
     const size_t kv_half = (size_t)B * H * T_max * 64;
     auto P = [&](int t, int l) { return gpt_param_off(c, t, l); };
 
+    // fused schedule by default for B <= DEC_BT sequences (r2u: 1.08 -> 0.88 ms per code at B = 1; at B = 8 every CTA repeats the LayerNorm of four
+    // sequences and the step is 3 % slower than with the separate row-op); TTTS_DECODE_FUSE=0 / 1 forces either
+    static int fuse_env = -2;
+    if (fuse_env == -2) { const char* e = getenv("TTTS_DECODE_FUSE"); fuse_env = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+    const int fuse = fuse_env >= 0 ? fuse_env : (B <= DEC_BT ? 1 : 0);
+    float* R[2] = {resid, reinterpret_cast<float*>(ws + w.resid2)};
+    float* PB[2] = {part, reinterpret_cast<float*>(ws + w.part2)};
+    int cur = 0;                                                      // R[cur] holds the residual stream
+
     RowopArgs r;
     memset(&r, 0, sizeof(r));
     r.d = d; r.B = B; r.resid = resid; r.xn16 = xn16; r.part = part;
@@ -463,7 +632,38 @@ int gpt_decode_step(const ttts_gpt_decode* a, cudaStream_t st) {
     r.T_max = T_max; r.Vm = Vm; r.n_pos_rows = c.max_mel_tokens + 2;
     r.Em = p32 + P(TTTS_P_MEL_EMB, 0); r.Pm = p32 + P(TTTS_P_MEL_POS, 0);
     int S = 1;
+    float* last_part = part;
     for (int l = 0; l < L; ++l) {
+        bf16* kc = kv + (size_t)l * 2 * kv_half;
+        if (fuse) {
+            // 5 launches per layer: [ln_1 +] c_attn | attention | attn c_proj | [residual + ln_2 +] c_fc | [gelu +] mlp c_proj
+            if (l == 0) {
+                r.mode = 0; r.S = 1; r.bias = nullptr; r.resid = R[cur];
+                r.w1 = p32 + P(TTTS_P_LN1_W, l); r.b1 = p32 + P(TTTS_P_LN1_B, l); r.w2 = nullptr; r.b2 = nullptr;
+                TTTS_CUDA(launch_pdl(dec_rowop_kernel, dim3(B), dim3(256), 0, st, r));
+                TTTS_LAUNCH_CHECK("dec_rowop");
+                TTTS_RUN(dec_gemv(xn16, p16 + P(TTTS_P_ATTN_W, l), PB[0], d, 3 * d, B, &S, st));
+            } else {
+                GemvPro g = {PB[1], S, p32 + P(TTTS_P_PR_B, l - 1), R[cur], R[cur ^ 1], p32 + P(TTTS_P_LN1_W, l), p32 + P(TTTS_P_LN1_B, l)};
+                TTTS_RUN(dec_gemv_fused<1>(g, p16 + P(TTTS_P_ATTN_W, l), PB[0], d, 3 * d, B, &S, st));
+                cur ^= 1;
+            }
+            TTTS_CUDA(launch_pdl(dec_attn_kernel, dim3(H, B), dim3(128), (size_t)T_max * sizeof(float), st, (const float*)PB[0],
+                                 p32 + P(TTTS_P_ATTN_B, l), S, B, d, H, kc, kc + kv_half, T_max, (const int32_t*)a->slot, att16));
+            TTTS_LAUNCH_CHECK("dec_attn");
+            TTTS_RUN(dec_gemv(att16, p16 + P(TTTS_P_PROJ_W, l), PB[1], d, d, B, &S, st));
+            {
+                GemvPro g = {PB[1], S, p32 + P(TTTS_P_PROJ_B, l), R[cur], R[cur ^ 1], p32 + P(TTTS_P_LN2_W, l), p32 + P(TTTS_P_LN2_B, l)};
+                TTTS_RUN(dec_gemv_fused<1>(g, p16 + P(TTTS_P_FC_W, l), PB[0], d, 4 * d, B, &S, st));
+                cur ^= 1;
+            }
+            {
+                GemvPro g = {PB[0], S, p32 + P(TTTS_P_FC_B, l), nullptr, nullptr, nullptr, nullptr};
+                TTTS_RUN(dec_gemv_fused<2>(g, p16 + P(TTTS_P_PR_W, l), PB[1], 4 * d, d, B, &S, st));
+            }
+            last_part = PB[1];
+            continue;
+        }
         // embed (layer 0) or residual add of the previous layer's mlp c_proj ; ln_1
         r.mode = l == 0 ? 0 : 1; r.S = S; r.bias = l == 0 ? nullptr : p32 + P(TTTS_P_PR_B, l - 1);
         r.w1 = p32 + P(TTTS_P_LN1_W, l); r.b1 = p32 + P(TTTS_P_LN1_B, l); r.w2 = nullptr; r.b2 = nullptr;
@@ -471,7 +671,6 @@ int gpt_decode_step(const ttts_gpt_decode* a, cudaStream_t st) {
         TTTS_LAUNCH_CHECK("dec_rowop");
         // c_attn
         TTTS_RUN(dec_gemv(xn16, p16 + P(TTTS_P_ATTN_W, l), part, d, 3 * d, B, &S, st));
-        bf16* kc = kv + (size_t)l * 2 * kv_half;
         TTTS_CUDA(launch_pdl(dec_attn_kernel, dim3(H, B), dim3(128), (size_t)T_max * sizeof(float), st, (const float*)part,
                              p32 + P(TTTS_P_ATTN_B, l), S, B, d, H, kc, kc + kv_half, T_max, (const int32_t*)a->slot, att16));
         TTTS_LAUNCH_CHECK("dec_attn");
@@ -489,7 +688,7 @@ int gpt_decode_step(const ttts_gpt_decode* a, cudaStream_t st) {
         TTTS_RUN(dec_gemv(act16, p16 + P(TTTS_P_PR_W, l), part, 4 * d, d, B, &S, st));
     }
     // last residual add ; ln_f ; final_norm ; mel head
-    r.mode = 1; r.S = S; r.bias = p32 + P(TTTS_P_PR_B, L - 1);
+    r.mode = 1; r.S = S; r.bias = p32 + P(TTTS_P_PR_B, L - 1); r.part = last_part; r.resid = R[cur];
     r.w1 = p32 + P(TTTS_P_LNF_W, 0); r.b1 = p32 + P(TTTS_P_LNF_B, 0); r.w2 = p32 + P(TTTS_P_FN_W, 0); r.b2 = p32 + P(TTTS_P_FN_B, 0);
     TTTS_CUDA(launch_pdl(dec_rowop_kernel, dim3(B), dim3(256), 0, st, r));
     TTTS_LAUNCH_CHECK("dec_rowop");
