@@ -436,11 +436,20 @@ __global__ void __launch_bounds__(128) dec_attn_kernel(const float* __restrict__
     l = (red[0] + red[1]) + (red[2] + red[3]);
     // ---- P.V: lane owns dims 2 lane, 2 lane + 1 ; warp w owns keys w, w + 4, ... ----
     float o0 = 0.f, o1 = 0.f;
-    for (int t = warp; t < n_keys; t += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(vc + (size_t)t * 64 + 2 * lane);
-        const float p = sc[t];
-        o0 = fmaf(p, bf16_lo(w), o0);
-        o1 = fmaf(p, bf16_hi(w), o1);
+    for (int t0 = warp; t0 < n_keys; t0 += 4 * 8) {                  // 8 value rows in flight per warp (one row per trip was one L2 round trip each)
+        uint32_t wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = t0 + 4 * u;
+            wv[u] = t < n_keys ? *reinterpret_cast<const uint32_t*>(vc + (size_t)t * 64 + 2 * lane) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = t0 + 4 * u;
+            const float p = t < n_keys ? sc[t] : 0.f;
+            o0 = fmaf(p, bf16_lo(wv[u]), o0);
+            o1 = fmaf(p, bf16_hi(wv[u]), o1);
+        }
     }
     osum[warp][2 * lane] = o0;
     osum[warp][2 * lane + 1] = o1;
