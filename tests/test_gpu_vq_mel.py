@@ -235,3 +235,26 @@ def test_vq_tensor_core_path_is_bit_identical_to_fp32(N, layout_bdn, monkeypatch
     assert torch.equal(c0, c1), int((c0 != c1).sum())
     assert torch.equal(q0, q1) and float(l0) == float(l1)
     assert int(c1[0]) == 3 and int(c1[2]) in (9, 800, 801, 802, 803, 804, 805)
+
+
+@pytest.mark.parametrize("K,D,N,bdn", [(1024, 192, 1152, True), (1024, 192, 65, False), (1000, 64, 777, False), (1024, 192, 2000, False), (130, 16, 300, False)])
+def test_vq_split_sweep_is_bit_identical(K, D, N, bdn, monkeypatch):
+    """small N (the encode metric's own 64 clips x 18 frames = 1 152 vectors): the code tiles are dealt out over grid.y and a second kernel
+    merges the per-group winners.  Codes, dequantised rows and the commitment loss must be BIT-identical to the single launch, with
+    duplicated codebook rows in different tile groups (lowest index wins), a vector equal to a code and a half-way vector."""
+    from ttts_b200.vqvae.quantize import vq_lookup
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    E = torch.randn(K, D, device="cuda", generator=g)
+    if K >= 1000:
+        E[700] = E[3]; E[129] = E[3]; E[999] = E[520]
+    x = torch.randn(N, D, device="cuda", generator=g)
+    x[0] = E[3]; x[1] = 0.5 * (E[5] + E[K - 1]); x[2] = E[min(520, K - 1)]; x[3] = 0.0
+    xin = x.view(N // 18, 18, D).transpose(1, 2).contiguous() if bdn else x
+    monkeypatch.setenv("TTTS_VQ_SPLIT", "0")
+    c0, q0, l0 = vq_lookup(xin, E, bdn, want_quantized=True, want_commit=True)
+    monkeypatch.setenv("TTTS_VQ_SPLIT", "1")
+    c1, q1, l1 = vq_lookup(xin, E, bdn, want_quantized=True, want_commit=True)
+    assert torch.equal(c0, c1), int((c0 != c1).sum())
+    assert torch.equal(q0, q1) and float(l0) == float(l1)
+    if K >= 1000:
+        assert int(c1.reshape(-1)[0]) == 3 and int(c1.reshape(-1)[2]) == 520

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
                                                                     const float* __restrict__ ee, int K, int64_t* __restrict__ idx_out,
                                                                     float* __restrict__ q_out, int straight_through,
                                                                     float* __restrict__ commit_partial, float* __restrict__ hist,
-                                                                    float* __restrict__ embed_sum) {
+                                                                    float* __restrict__ embed_sum, float2* __restrict__ split_part) {
     extern __shared__ __align__(16) float vq_smem[];
     float* Xs = vq_smem;                         // [D][VQ_TM], 16-byte groups of a row XOR-swizzled by d (vq_xs_index)
     float* Es = Xs + (size_t)D * VQ_TM;          // [2][VQ_TN][VQ_EP]
@@ -226,8 +226,14 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
     const int tx = tid & 15, ty = tid >> 4;
     const int v0 = blockIdx.x * VQ_TM;
     const int nchunks = D / VQ_DC;
-    const int ntiles = (K + VQ_TN - 1) / VQ_TN;
+    // gridDim.y > 1: the code tiles are dealt out over blockIdx.y (small N: 18 CTAs walking the whole codebook left 130 SMs idle, 0.17 ms at the
+    // encode metric's N = 1 152); each CTA then writes its (best distance, index) per vector to split_part and vq_split_merge_kernel finishes
+    const int ntiles_all = (K + VQ_TN - 1) / VQ_TN;
+    const int tiles_per = (ntiles_all + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int tile_begin = (int)blockIdx.y * tiles_per;
+    const int ntiles = max(0, min(tiles_per, ntiles_all - tile_begin));
     const int total = ntiles * nchunks;
+    const int ct0 = tile_begin * VQ_TN;
 
     // chunk q = (code tile q / nchunks, dims (q % nchunks) * 16 ...): thread copies 16 bytes of codes c and c + 64
     auto issue = [&](int q, int ct, int d0) {
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
             cp_async16(es + c * VQ_EP + part, ok ? E + (size_t)(ct + c) * D + d0 + part : E, ok);
         }
     };
-    issue(0, 0, 0);
+    if (total > 0) issue(0, ct0, 0);
     cp_async_commit();
 
     vq_load_x_tile<true>(x, lay, N, D, v0, Xs, xx, tid);
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) { best[i] = -INFINITY; besti[i] = 0; }
     float acc[4][8];
-    int ch = 0, ct = 0;                          // chunk q = dims ch * 16 ... of code tile ct (no division in the loop)
+    int ch = 0, ct = ct0;                        // chunk q = dims ch * 16 ... of code tile ct (no division in the loop)
     for (int q = 0; q < total; ++q) {
         if (ch == 0) {
 #pragma unroll
@@ -296,7 +302,49 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_argmin_pipe_kernel(const flo
             ++ch;
         }
     }
+    if (gridDim.y > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+                if (ob > best[i] || (ob == best[i] && oi < besti[i])) { best[i] = ob; besti[i] = oi; }
+            }
+            const int v = v0 + ty * 4 + i;
+            if (tx == 0 && v < N) split_part[(size_t)blockIdx.y * N + v] = make_float2(best[i], __int_as_float(besti[i]));
+        }
+        return;
+    }
     vq_finish_tile<true>(best, besti, lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
+}
+
+// second half of the split sweep: the winner of every vector among the gridDim.y partial results (ascending tile groups, lowest index among equal
+// distances: the same rule as inside a CTA), then the fused epilogue
+__global__ void __launch_bounds__(VQ_THREADS) vq_split_merge_kernel(const float* __restrict__ x, VqLayout lay, int N, int D, const float* __restrict__ E,
+                                                                    const float2* __restrict__ split_part, int Y, int64_t* __restrict__ idx_out,
+                                                                    float* __restrict__ q_out, int straight_through,
+                                                                    float* __restrict__ commit_partial, float* __restrict__ hist,
+                                                                    float* __restrict__ embed_sum) {
+    extern __shared__ __align__(16) float vq_smem[];
+    float* Xs = vq_smem;
+    float* xx = Xs + (size_t)D * VQ_TM;
+    int* sidx = reinterpret_cast<int*>(xx + VQ_TM);
+    const int tid = threadIdx.x, v0 = blockIdx.x * VQ_TM;
+    vq_load_x_tile<true>(x, lay, N, D, v0, Xs, xx, tid);
+    if (tid < VQ_TM) {
+        const int v = v0 + tid;
+        float bd = -INFINITY; int bk = 0;                            // index 0 when nothing compares greater (NaN input), like the single launch
+        if (v < N) {
+            for (int y = 0; y < Y; ++y) {
+                const float2 c = split_part[(size_t)y * N + v];
+                const int k = __float_as_int(c.y);
+                if (c.x > bd || (c.x == bd && k < bk)) { bd = c.x; bk = k; }
+            }
+        }
+        sidx[tid] = bk;
+    }
+    vq_emit_tile<true>(lay, N, D, E, v0, Xs, sidx, idx_out, q_out, straight_through, commit_partial, hist, embed_sum, tid);
 }
 
 __global__ void __launch_bounds__(1024) vq_commit_final_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
@@ -624,6 +672,7 @@ static bool vq_tc_enabled() {                      // read per call (not latched
     const char* e = getenv("TTTS_VQ_TC");
     return !(e && e[0] == '0');
 }
+constexpr int VQ_SPLIT_MAX = 8;                   // code-tile groups of the split exact-fp32 sweep (small N)
 constexpr int VQ_TC_MIN_N = 4096;                  // below this the fp32 kernel's single launch wins (the encode metric's N = 1 152 stays there)
 
 static bool vq_tc_covers(int N, int D, int K) {
@@ -649,6 +698,7 @@ int64_t ttts_vq_workspace_floats(int32_t N, int32_t K) {
     int64_t n = (int64_t)K + (N + VQ_TM - 1) / VQ_TM + 8;
     n = (n + 63) / 64 * 64;
     if (N >= ttts::VQ_TC_MIN_N) n += (int64_t)192 * K + 8ll * (K / 128 + 1) * ((N + 127) / 128 * 128) + 64;
+    else n += 2ll * ttts::VQ_SPLIT_MAX * N + 8;                      // (distance, index) per vector and code-tile group of the split sweep
     return n;
 }
 
@@ -706,8 +756,27 @@ int ttts_vq_forward(const float* x, int32_t B, int32_t D, int32_t Nn, int32_t la
             TTTS_CUDA(cudaFuncSetAttribute(vq_argmin_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_smem_pipe = smem;
         }
-        vq_argmin_pipe_kernel<<<blocks, VQ_THREADS, smem, st>>>(x, lay, N, D, embed, ee, K, codes, quantized, straight_through,
-                                                                commit_out ? partial : nullptr, hist, embed_sum);
+        // few x tiles: deal the code tiles out over grid.y so that the launch covers the SMs (about one wave), merge in a second kernel
+        const int ntiles_all = (K + VQ_TN - 1) / VQ_TN;
+        int Y = 1;
+        const char* se = getenv("TTTS_VQ_SPLIT");                   // read per call: the parity test runs both forms in one process
+        const bool split_on = !(se && se[0] == '0');
+        if (split_on && blocks * 2 <= num_sms() && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0) {
+            Y = num_sms() / blocks;
+            if (Y > ntiles_all) Y = ntiles_all;
+            if (Y > VQ_SPLIT_MAX) Y = VQ_SPLIT_MAX;
+        }
+        float2* sp = reinterpret_cast<float2*>(workspace + ((int64_t)K + blocks + 8 + 63) / 64 * 64);
+        vq_argmin_pipe_kernel<<<dim3(blocks, Y), VQ_THREADS, smem, st>>>(x, lay, N, D, embed, ee, K, codes, quantized, straight_through,
+                                                                       commit_out ? partial : nullptr, hist, embed_sum, sp);
+        if (Y > 1) {
+            TTTS_LAUNCH_CHECK("vq_argmin (split)");
+            const size_t smem_m = ((size_t)D * VQ_TM + VQ_TM) * sizeof(float) + VQ_TM * sizeof(int);
+            static size_t attr_m = 0;
+            if (smem_m > attr_m) { TTTS_CUDA(cudaFuncSetAttribute(vq_split_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); attr_m = smem_m; }
+            vq_split_merge_kernel<<<blocks, VQ_THREADS, smem_m, st>>>(x, lay, N, D, embed, sp, Y, codes, quantized, straight_through,
+                                                                     commit_out ? partial : nullptr, hist, embed_sum);
+        }
     } else {
         if (smem > attr_smem) {
             TTTS_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
