@@ -411,11 +411,12 @@ int ttts_diff_loss(const float* model_out, const float* x_start, const float* x_
 int ttts_diff_loss_bwd(const float* dL, const float* model_out, const float* x_start, const float* x_t, const float* noise, const float* coef,
                        const int32_t* t_is0, float* dout, int32_t B, int32_t Cn, int32_t T, void* stream);
 
-/* Layout conversion around the tensor-core convolutions of the diffusion step (the 512-channel nn.Conv1d of aa_model.py:97-118,198-233 as
- * split-bf16 GEMMs on ttts_gemm_bf16): x [B,C,T] fp32 -> rows [hi(x[b,:,t]) | lo(x[b,:,t])] (2C bf16) at row 1 + b (T + 1) + t of a
- * ZERO-INITIALISED [2 + B (T + 1), 2C] buffer (the untouched rows are the zero padding between clips); and back: D [B (T + 1), ld] fp32 -> y [B,C,T]. */
-int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, void* stream);
-int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, void* stream);
+/* Layout conversion around the tensor-core convolutions of the training tapes (the wide nn.Conv1d / Conv2d-(k,1) layers of aa_model.py:97-118,
+ * 198-233 and vq2.py:341-416,418-496 as split-bf16 GEMMs on ttts_gemm_bf16): x [B,C,T] fp32 (optionally through leaky_relu 0.1) -> rows
+ * [hi(x[b,:,t]) | lo(x[b,:,t])] (2C bf16) at row row_off + b rows_per_clip + t of a ZERO-INITIALISED buffer (the untouched rows are the zero
+ * padding around and between the clips); and back: D fp32 (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T]. */
+int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu, void* stream);
+int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off, void* stream);
 
 #ifdef __cplusplus
 }

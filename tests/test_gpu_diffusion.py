@@ -250,29 +250,33 @@ def test_trainer_surface_save_load(K, tmp_path):
     assert tr2.step == 3 and all(torch.equal(tr2.state_dict()[k], sd[k]) for k in sd)
 
 
-@pytest.mark.parametrize("B,Cin,T,Cout,Kw", [(4, 512, 600, 512, 3), (2, 1024, 1030, 512, 1), (3, 128, 700, 192, 3), (2, 512, 1024, 1536, 1)])
-def test_tensor_core_convolution_vs_torch(K, B, Cin, T, Cout, Kw):
-    """the split-bf16 tcgen05 path of the wide stride-1 convolutions (forward, input gradient, weight and bias gradient) against torch's fp32
-    convolution: fp32-grade agreement (three bf16 products per fp32 product), and it is actually taken for these shapes"""
+@pytest.mark.parametrize("B,Cin,T,Cout,Kw,stride,dil,pad,lrelu", [
+    (4, 512, 600, 512, 3, 1, 1, 1, False), (2, 1024, 1030, 512, 1, 1, 1, 0, False), (3, 128, 700, 192, 3, 1, 1, 1, False), (2, 512, 1024, 1536, 1, 1, 1, 0, False),
+    (10, 512, 760, 1024, 5, 3, 1, 2, False),      # DiscriminatorP 512 -> 1024, kernel 5, stride 3 (vq2.py:418-460)
+    (16, 1024, 253, 1024, 5, 1, 1, 2, False),     # ... 1024 -> 1024, stride 1
+    (4, 128, 2560, 128, 11, 1, 5, 25, True),      # Generator ResBlock1: kernel 11, dilation 5, leaky ReLU on the input (modules.py:224-318)
+    (6, 256, 700, 128, 7, 2, 3, 9, True),         # stride, dilation and padding together
+    (5, 192, 1000, 512, 7, 1, 1, 3, False)])      # Generator.conv_pre
+def test_tensor_core_convolution_vs_torch(K, monkeypatch, B, Cin, T, Cout, Kw, stride, dil, pad, lrelu):
+    """the split-bf16 tcgen05 GEMM route of the wide convolutions (forward, input gradient, weight and bias gradient; any kernel size, stride,
+    dilation, padding, optional leaky ReLU on the input) against torch's fp64 convolution: fp32-grade agreement (three bf16 products per fp32
+    product), and the route is actually taken for these shapes"""
+    F = torch.nn.functional
     g = torch.Generator().manual_seed(Cin + T)
     x = torch.randn(B, Cin, T, generator=g)
     w = torch.randn(Cout, Cin, Kw, generator=g) / (Cin * Kw) ** 0.5
     b = torch.randn(Cout, generator=g)
-    dy = torch.randn(B, Cout, T, generator=g)
-    pad = (Kw - 1) // 2
-    xc, wc, bc, dyc = cu(x, w, b, dy)
-    assert K._tc_ok(xc, wc, 1, 1, pad, False, 1)
-    xr, wr, br = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        yr = torch.nn.functional.conv1d(xr.double(), wr.double(), br.double(), padding=pad)
-        yr.backward(dyc.double())
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
-    y = K.conv_fwd(xc, wc, bc, 1, 1, pad, False)
-    dx, dw, db = K.conv_bwd(dyc, xc, wc, 1, 1, pad, False, True, True)
+    xc, wc, bc = cu(x, w, b)
+    monkeypatch.setattr(K, "GEMM_MIN_POSITIONS", 1)                   # the product takes this route from 4096 output positions; the test shapes are smaller
+    assert K._gemm_ok(xc, wc, stride, dil, pad, 1)
+    xr, wr, br = x.cuda().double().requires_grad_(True), w.cuda().double().requires_grad_(True), b.cuda().double().requires_grad_(True)
+    yr = F.conv1d(F.leaky_relu(xr, 0.1) if lrelu else xr, wr, br, stride=stride, dilation=dil, padding=pad)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy.cuda().double())
+    y = K.conv_fwd(xc, wc, bc, stride, dil, pad, lrelu)
+    dx, dw, db = K.conv_bwd(dy.cuda(), xc, wc, stride, dil, pad, lrelu, True, True)
     rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm())
+    assert y.shape == yr.shape
     assert rel(y, yr) <= 2e-5, rel(y, yr)
     assert rel(dx, xr.grad) <= 2e-5, rel(dx, xr.grad)
     assert rel(dw, wr.grad) <= 2e-5, rel(dw, wr.grad)

@@ -53,6 +53,13 @@ TTTS_DEVICE void sts_v4(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.b32
 TTTS_DEVICE void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 TTTS_DEVICE float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 
+// attention_tail.cu
+int attn_tail_rows(int T);
+int attn_tail_fwd(const bf16* qkv, bf16* out, float* lse, int B, int T, int H, int Tm, uint32_t thresh16, float drop_scale, uint64_t seed, cudaStream_t st);
+int attn_tail_bwd(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv, float* dq_acc, int B, int T, int H, int Tm,
+                  uint32_t thresh16, float drop_scale, uint64_t seed, cudaStream_t st);
+bool attn_tail_split();
+
 constexpr int AT3_THREADS = 576;      // warp 0 TMA, warp 1 MMA, 16 math warps (four per TMEM lane quadrant, 32 columns each)
 
 // ------------------------------------------------------------------------------------------------------------
@@ -89,8 +96,10 @@ struct Fwd4Smem {
 // different columns), so it uses one 128-thread named barrier per quadrant instead of one for all 16 warps.  Same arithmetic, same bits.
 template <int kMode>
 __global__ void __maxnreg__(96)
-attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int H, int BH, float scale,
-                    DropCfg drop) {
+attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int Tm, int H, int BH,
+                    float scale, DropCfg drop) {
+    // T = positions per sequence (row / lse / dropout-row strides); Tm <= T = the positions this kernel attends over (queries AND keys):
+    // Tm = T, or T - T mod 128 when the ragged tail rows are left to attention_tail.cu
     using S = Fwd4Smem;
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -107,7 +116,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = H * 64;
-    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int nq = (Tm + AT_BM - 1) / AT_BM;
     const int total = nq * BH;
     // Items are numbered head-major (all query blocks of a head are neighbours, late = heavy blocks first) and dealt out in rounds of
     // gridDim.x: in round n this CTA takes position (blockIdx.x + n) mod gridDim.x.  CTAs running at the same time therefore work on
@@ -117,7 +126,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     auto item_at = [&](int n) { if (n >= rounds) return -1; const int idx = n * (int)gridDim.x + (int)fastmod(blockIdx.x + n, fd_grid); return idx < total ? idx : -1; };
     auto item_qb = [&](int idx) { return nq - 1 - (int)fastmod((uint32_t)idx, fd_nq); };
     auto item_bh = [&](int idx) { return (int)fastdiv((uint32_t)idx, fd_nq); };
-    auto item_nkv = [&](int qb) { return min(qb + 1, (T + AT_BN - 1) / AT_BN); };
+    auto item_nkv = [&](int qb) { return min(qb + 1, (Tm + AT_BN - 1) / AT_BN); };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -236,7 +245,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int k0 = j * AT_BN;
-                const bool need_mask = (j == qb) || (k0 + AT_BN > T);
+                const bool need_mask = (j == qb) || (k0 + AT_BN > Tm);
                 const int kc0 = k0 + qtr * 32;
                 uint32_t v[32];
                 mbar_wait(&s_full[g & 1], (g >> 1) & 1);
@@ -249,7 +258,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
                 if (lane == 0) mbar_arrive(&s_empty[g & 1]);
                 float mx0 = -INFINITY, mx1 = -INFINITY;
                 if (need_mask) {
-                    const int nv = min(qi, T - 1) - kc0 + 1;         // keys kc0 .. kc0 + nv - 1 exist for this query row (causal + sequence end)
+                    const int nv = min(qi, Tm - 1) - kc0 + 1;        // keys kc0 .. kc0 + nv - 1 exist for this query row (causal + sequence end)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = (i < nv) ? v[i] : 0xff800000u;
                 }
@@ -342,7 +351,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             sts_f32(xsum + (qtr * 128 + r) * 4, l_run);
             named_bar_sync(2 + quad, 128);
             const float l_tot = (lds_f32(xsum + r * 4) + lds_f32(xsum + (128 + r) * 4)) + (lds_f32(xsum + (256 + r) * 4) + lds_f32(xsum + (384 + r) * 4));
-            if (qi < T) {
+            if (qi < Tm) {
                 const float inv = l_tot > 0.f ? drop.scale / l_tot : 0.f;
                 if (qtr == 0) lse_out[(size_t)bh * T + qi] = m_used * scale + logf(l_tot);
                 uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * d + h * 64 + qtr * 16);
@@ -418,8 +427,9 @@ struct Bwd4Smem {
 template <int kMode>
 __global__ void __maxnreg__(96)
 attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
-                    const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int H, int BH, float scale,
+                    const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int Tm, int H, int BH, float scale,
                     DropCfg drop) {
+    // T / Tm as in the forward kernel: strides from T, queries and keys 0 .. Tm - 1
     using S = Bwd4Smem;
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -439,7 +449,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = H * 64, ld3 = 3 * d;
-    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int nq = (Tm + AT_BM - 1) / AT_BM;
     const int total = nq * BH;
     // head-major items dealt out in rotating rounds (see the forward kernel): concurrent CTAs share a few heads, so Q / dO / K / V and the
     // fp32 dQ accumulator rows they red.add into stay in L2 (with key-block-major items the accumulator traffic went to HBM)
@@ -597,7 +607,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         auto dkv_out = [&](int idx_) {
             const int jb_ = item_jb(idx_), bh_ = item_bh(idx_), b_ = (int)fastdiv((uint32_t)bh_, fd_H), h_ = bh_ - b_ * H;
             const int kj = jb_ * AT_BN + r;
-            bf16* dkp = dqkv + (size_t)(b_ * T + min(kj, T - 1)) * ld3 + d + h_ * 64 + qtr * 16;
+            bf16* dkp = dqkv + (size_t)(b_ * T + min(kj, Tm - 1)) * ld3 + d + h_ * 64 + qtr * 16;
             bf16* dvp = dkp + d;
             uint32_t a[16], v[16];
             __syncwarp();
@@ -607,7 +617,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_empty);
-            if (kj < T) {
+            if (kj < Tm) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     reinterpret_cast<uint4*>(dkp)[g] =
@@ -633,7 +643,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         float lse_nx = 0.f, dlt_nx = 0.f;
         auto fetch_row_stats = [&](int bh_, int i_) {
             const int qi_ = i_ * AT_BM + r;
-            if (qi_ < T) { lse_nx = __ldg(lse + (size_t)bh_ * T + qi_); dlt_nx = __ldg(delta + (size_t)bh_ * T + qi_); }
+            if (qi_ < Tm) { lse_nx = __ldg(lse + (size_t)bh_ * T + qi_); dlt_nx = __ldg(delta + (size_t)bh_ * T + qi_); }
             else { lse_nx = 0.f; dlt_nx = 0.f; }
         };
         { const int idx0 = item_at(0); if (idx0 >= 0) fetch_row_stats(item_bh(idx0), item_jb(idx0)); }
@@ -649,7 +659,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 const int i = jb + it;
                 const uint32_t ph = c & 1;
                 const int qi = i * AT_BM + r;
-                const bool q_ok = qi < T;
+                const bool q_ok = qi < Tm;
                 // pinned: without it the compiler rotates this multiply into the previous iteration, right behind the load it was meant to
                 // be a whole block away from (r1h profile: 4.5 % of the stall samples on that FMUL)
                 float lse_cur = lse_nx, dlt_cur = dlt_nx;
@@ -658,7 +668,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 const float dlt = dlt_cur;
                 if (it + 1 < nit) fetch_row_stats(bh, i + 1);
                 else if (idx_nx >= 0) fetch_row_stats(bh_nx, jb_nx);
-                const bool need_mask = (i == jb) || (k0 + AT_BN > T) || (i * AT_BM + AT_BM > T);
+                const bool need_mask = (i == jb) || (k0 + AT_BN > Tm) || (i * AT_BM + AT_BM > Tm);
                 const AttnDropRow rk = attn_drop_row(drop.seed, (uint64_t)bh * (uint64_t)T + (uint64_t)qi);
                 float* cur_dst = q_ok ? dq_acc + (size_t)(row_base + qi) * d + h * 64 + qtr * 16 : nullptr;
                 uint32_t pp[16], dd[16];
@@ -672,7 +682,7 @@ attn_bwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 const float ndl = -dlt * inv_c;
                 {
                     // keys of this block that exist for this query row (causal + sequence end); only consulted on diagonal / edge blocks
-                    const int n_ok = q_ok ? min(qi, T - 1) - kc0 + 1 : 0;
+                    const int n_ok = q_ok ? min(qi, Tm - 1) - kc0 + 1 : 0;
                     const uint32_t zero = drop.thresh16 >> 16;
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
@@ -732,6 +742,13 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* _
     }
 }
 
+// TTTS_ATTN_TAIL=0: the tile kernels take the ragged last query tile themselves (A/B measurements)
+bool attn_tail_split() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TTTS_ATTN_TAIL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+
 bool attn_use_tc() {
     static int legacy = -1;
     if (legacy < 0) { const char* e = getenv("TTTS_ATTN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
@@ -749,13 +766,17 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
         TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
         attr4 = true;
     }
-    const int nq = (T + AT_BM - 1) / AT_BM;
+    // a ragged tail of <= 16 rows (T = 1156 = 9 x 128 + 4 in training) is left to attention_tail.cu: the tile kernel stops at Tm
+    const int tail = attn_tail_split() ? attn_tail_rows(T) : 0;
+    const int Tm = T - tail;
+    const int nq = (Tm + AT_BM - 1) / AT_BM;
     const int items = nq * B * H;
     const int nblk = items < num_sms() ? items : num_sms();
     TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nq <= 4096, "attention: too many (block, head) items");
-    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
-    else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, H, B * H, 0.125f, drop));
+    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, Tm, H, B * H, 0.125f, drop));
+    else TTTS_CUDA(launch_pdl(attn_fwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Fwd4Smem::kBytes, st, tm, o, lse, T, Tm, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_fwd_tc");
+    if (tail) TTTS_RUN(attn_tail_fwd(qkv, o, lse, B, T, H, Tm, drop.thresh16, drop.scale, drop.seed, st));
     return TTTS_OK;
 }
 
@@ -780,13 +801,17 @@ int attn_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* l
         TTTS_CUDA(cudaFuncSetAttribute(attn_bwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd4Smem::kBytes));
         attr4 = true;
     }
-    const int nkb = (T + AT_BN - 1) / AT_BN;
+    const int tail = attn_tail_split() ? attn_tail_rows(T) : 0;
+    const int Tm = T - tail;
+    const int nkb = (Tm + AT_BN - 1) / AT_BN;
     const int items = nkb * B * H;
     const int nblk = items < num_sms() ? items : num_sms();
     TTTS_CHECK_ARG((uint64_t)(items + nblk) * (uint64_t)(nblk > H ? nblk : H) < (1ull << 32) && nkb <= 4096, "attention: too many (block, head) items");
-    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
-    else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, H, B * H, 0.125f, drop));
+    if (drop.thresh16) TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<1>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, Tm, H, B * H, 0.125f, drop));
+    else TTTS_CUDA(launch_pdl(attn_bwd_tc4_kernel<2>, dim3(nblk), dim3(AT3_THREADS), Bwd4Smem::kBytes, st, tmQ, tmDO, lse, delta, dqkv, dq_acc, T, Tm, H, B * H, 0.125f, drop));
     TTTS_LAUNCH_CHECK("attn_bwd_tc");
+    // the tail rows' dQ (into dq_acc) and their share of every dK / dV row (added to what the tile kernel has just written)
+    if (tail) TTTS_RUN(attn_tail_bwd(qkv, dout, lse, delta, dqkv, dq_acc, B, T, H, Tm, drop.thresh16, drop.scale, drop.seed, st));
     const size_t n4 = (size_t)B * T * d / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;

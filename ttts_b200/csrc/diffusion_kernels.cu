@@ -520,21 +520,25 @@ __global__ void diff_loss_bwd_kernel(const float* __restrict__ dL, const float* 
 
 
 // ---------------------------------------------------------------- layout conversion for the tensor-core convolutions ----------------------------------------------------------------
-// The 512-channel 1x1 / K = 3 convolutions of AA_diffusion are GEMMs; they run on ttts_gemm_bf16 (tcgen05) with split-bf16 operands
-// (x = hi + lo, w = hi + lo, y ~ hi hi + hi lo + lo hi with fp32 accumulation: fp32-grade results, ttts_b200/diffusion/kernels.py).
-// The GEMM wants position-major rows, the tape keeps [B, C, T]: these two kernels convert.
-//   cl_split : x [B, C, T] fp32 -> rows [hi(x[b, :, t]) | lo(x[b, :, t])] (2C bf16) at row 1 + b (T + 1) + t of a [2 + B (T + 1), 2C] buffer whose
-//              other rows (one leading, one after every clip, one trailing) stay ZERO: a tap of a K = 3 convolution is the same buffer read one
-//              row earlier / later, and no tap reads a neighbouring clip.  The zero rows are never written (the buffer is zero-initialised once).
-//   cl_unpack: D [B (T + 1), ld] fp32 (row b (T + 1) + t) -> y [B, C, T]
+// The wide convolutions of the training tapes (AA_diffusion's 512-channel layers, the period discriminators' 512 / 1024-channel layers, the
+// Generator's ResBlocks) are GEMMs; they run on ttts_gemm_bf16 (tcgen05) with split-bf16 operands (x = hi + lo, w = hi + lo,
+// y ~ hi hi + hi lo + lo hi with fp32 accumulation: fp32-grade results, ttts_b200/vqvae/train_encoder.py).  The GEMM wants position-major
+// rows, the tape keeps [B, C, T]: these two kernels convert.
+//   cl_split : x [B, C, T] fp32 -> rows [hi(x[b, :, t]) | lo(x[b, :, t])] (2C bf16) at row row_off + b * rows_per_clip + t of a buffer whose other
+//              rows stay ZERO (never written; the buffer is zero-initialised once): tap k of a convolution with stride s is the same buffer read
+//              at rows s m + k (an A operand with row stride s), and no tap reads a neighbouring clip.  lrelu != 0: leaky_relu(0.1) first.
+//   cl_unpack: D fp32 (row row_off + b * rows_per_clip + t, row pitch ld) -> y [B, C, T]
 // 32 x 32 tiles through shared memory: coalesced along time on the [B, C, T] side, along channels on the other.
-__global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int C, int T) {
+__global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int C, int T, int rows_per_clip,
+                                                       int row_off, int lrelu) {
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int j = ty; j < 32; j += 8) {
         const int c = c0 + j, t = t0 + tx;
-        tile[j][tx] = (c < C && t < T) ? x[((size_t)b * C + c) * T + t] : 0.f;
+        float v = (c < C && t < T) ? x[((size_t)b * C + c) * T + t] : 0.f;
+        if (lrelu) v = v > 0.f ? v : 0.1f * v;
+        tile[j][tx] = v;
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -543,19 +547,20 @@ __global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__
             const float v = tile[tx][i];
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-            uint16_t* row = out + ((size_t)1 + (size_t)b * (T + 1) + t) * (2 * (size_t)C);
+            uint16_t* row = out + ((size_t)row_off + (size_t)b * rows_per_clip + t) * (2 * (size_t)C);
             row[c] = *reinterpret_cast<const uint16_t*>(&h);
             row[C + c] = *reinterpret_cast<const uint16_t*>(&l);
         }
     }
 }
-__global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict__ D, float* __restrict__ y, int C, int T, int ld) {
+__global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict__ D, float* __restrict__ y, int C, int T, int ld, int rows_per_clip,
+                                                        int row_off) {
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
         const int t = t0 + i, c = c0 + tx;
-        tile[i][tx] = (t < T && c < C) ? D[((size_t)b * (T + 1) + t) * ld + c] : 0.f;
+        tile[i][tx] = (t < T && c < C) ? D[((size_t)row_off + (size_t)b * rows_per_clip + t) * ld + c] : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -718,17 +723,22 @@ extern "C" int ttts_diff_loss_bwd(const float* dL, const float* model_out, const
     return TTTS_OK;
 }
 
-/* x [B,C,T] fp32 -> split-bf16 position-major rows [hi | lo] of a zero-initialised [2 + B (T + 1), 2C] bf16 buffer (see cl_split_kernel) */
-extern "C" int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, void* stream) {
-    TTTS_CHECK_ARG(x && out_bf16 && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && (C + 31) / 32 <= 65535, "cl_split: bad args");
-    TTTS_CUDA(launch_plain(cl_split_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, x, (uint16_t*)out_bf16, C, T));
+/* x [B,C,T] fp32 -> split-bf16 position-major rows [hi | lo] of a zero-initialised [rows, 2C] bf16 buffer: row row_off + b rows_per_clip + t */
+extern "C" int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu,
+                             void* stream) {
+    TTTS_CHECK_ARG(x && out_bf16 && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && (C + 31) / 32 <= 65535 && rows_per_clip >= T && row_off >= 0,
+                   "cl_split: bad args");
+    TTTS_CUDA(launch_plain(cl_split_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, x, (uint16_t*)out_bf16, C, T,
+                           rows_per_clip, row_off, lrelu));
     TTTS_LAUNCH_CHECK("cl_split");
     return TTTS_OK;
 }
-/* D [B (T + 1), ld] fp32 position-major -> y [B,C,T] */
-extern "C" int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, void* stream) {
-    TTTS_CHECK_ARG(D && y && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && ld >= C && (C + 31) / 32 <= 65535, "cl_unpack: bad args");
-    TTTS_CUDA(launch_plain(cl_unpack_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, D, y, C, T, ld));
+/* D fp32 position-major (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T] */
+extern "C" int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off, void* stream) {
+    TTTS_CHECK_ARG(D && y && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && ld >= C && (C + 31) / 32 <= 65535 && rows_per_clip >= T && row_off >= 0,
+                   "cl_unpack: bad args");
+    TTTS_CUDA(launch_plain(cl_unpack_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(256), 0, (cudaStream_t)stream, D, y, C, T, ld, rows_per_clip,
+                           row_off));
     TTTS_LAUNCH_CHECK("cl_unpack");
     return TTTS_OK;
 }

@@ -528,6 +528,8 @@ class CudaKernels:
         self._train_protos(lib)
         import os
         self.dgrad_as_forward = os.environ.get("TTTS_DGRAD_FWD", "1") != "0"
+        # wide convolutions (both channel counts multiples of 64 and >= 128, >= 4096 output positions) as split-bf16 GEMMs on the tcgen05 GEMM
+        self.conv_gemm = os.environ.get("TTTS_TRAIN_GEMM", "1") != "0" and os.environ.get("TTTS_DIFF_TC", "1") != "0"
 
     @staticmethod
     def _train_protos(lib):
@@ -565,6 +567,11 @@ class CudaKernels:
             lib.ttts_mha_small_bwd.argtypes = [vp] * 8 + [i32, i32, i32, i32, f32, vp]
             lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
             lib.ttts_posterior_sample_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+            try:
+                lib.ttts_cl_split.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+                lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+            except AttributeError:
+                pass                                                  # an emulation set without csrc/diffusion_kernels.cu
             lib._train_protos = True
 
     def _st(self):
@@ -585,6 +592,117 @@ class CudaKernels:
         for t in ts:
             assert t is None or (t.is_contiguous() and t.dtype in (torch.float32, torch.int64)), "contiguous fp32 / int64 tensors only"
 
+
+    # ---------------------------------------------------------------- wide convolutions on the tcgen05 GEMM ----------------------------------------------------------------
+    # x = hi + lo, w = hi + lo (bf16 each), x w ~ hi hi + lo hi + hi lo with fp32 accumulation in TMEM: fp32-grade results (2e-5 relative against an
+    # fp64 convolution, tests/test_gpu_diffusion.py) at tensor-core speed.  ttts_cl_split writes the activation as position-major [hi | lo] rows,
+    # sample t of clip b at row b Tp + pad + t of a zero buffer (Tp = stride * ceil((T + 2 pad) / stride)), so that output row m = b Tp / stride + to
+    # reads tap k at row stride m + k dil: an A operand with ROW STRIDE `stride`, no im2col, no tap reads a neighbouring clip.  Then
+    #   forward : D[m, co]  = sum_k [xh | xl](s m + k dil) . [wh_k | wh_k]^T  +  xh(s m + k dil) . wl_k^T                 (2 launches per tap)
+    #   dgrad   : Dx[s m + k dil, ci] += [dyh | dyl](m) . [wh_k ; wh_k]  +  dyh(m) . wl_k          (fp32 red.add into a strided view of a zero buffer)
+    #   wgrad   : dW_k      = dyh^T . [xh | xl](s . + k dil)  (two column blocks, summed)  +  dyl^T . xh(s . + k dil)        (split-K, fp32 red.add)
+    # r2o / r2p: the diffusion step 353 -> 196 ms; the period discriminators' 512 -> 1024 (stride 3) and 1024 -> 1024 layers are ~60 % of the
+    # VQ-VAE-GAN step's FLOPs.
+    GEMM_MIN_POSITIONS = 4096
+
+    def _gemm_ok(self, x, w, stride, dil, pad, groups):
+        if not self.conv_gemm or not x.is_cuda or groups != 1 or not hasattr(self.lib, "ttts_cl_split"):
+            return False
+        B, Cin, T = x.shape
+        Cout, _, K = w.shape
+        Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        return (Cin % 64 == 0 and Cout % 64 == 0 and min(Cin, Cout) >= 128 and K <= 16 and stride <= 8 and Tout >= 1
+                and B * Tout >= self.GEMM_MIN_POSITIONS)
+
+    def _buf(self, key, shape, dtype, dev, zero=False):
+        """transient buffers, one per key: every use is ordered on the current stream"""
+        pool = self.__dict__.setdefault("_gemm_pool", {})
+        key = (key, tuple(shape), dtype, dev)
+        if key not in pool:
+            pool[key] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+        return pool[key]
+
+    def _cl_split(self, tag, x, rows_per_clip=None, row_off=1, rows=None, lrelu=False):
+        """x [B,C,T] -> [rows, 2C] bf16 rows [hi | lo]; the rows the kernel never writes are the zero padding (default geometry: one zero row
+        before every clip and one after the last)"""
+        B, C, T = x.shape
+        rows_per_clip = T + 1 if rows_per_clip is None else rows_per_clip
+        rows = 2 + B * rows_per_clip if rows is None else rows
+        buf = self._buf((tag, B, C, T, rows_per_clip, row_off), (rows, 2 * C), torch.bfloat16, x.device, zero=True)
+        self._chk(self.lib.ttts_cl_split(self._p(x), self._p(buf), B, C, T, rows_per_clip, row_off, int(bool(lrelu)), self._st()), "ttts_cl_split")
+        return buf
+
+    def _cl_unpack(self, D, B, C, T, rows_per_clip=None, row_off=0):
+        y = torch.empty(B, C, T, dtype=torch.float32, device=D.device)
+        rows_per_clip = T + 1 if rows_per_clip is None else rows_per_clip
+        self._chk(self.lib.ttts_cl_unpack(self._p(D), self._p(y), B, C, T, D.stride(0), rows_per_clip, row_off, self._st()), "ttts_cl_unpack")
+        return y
+
+    @staticmethod
+    def _split_weights(w):
+        wk = w.permute(2, 0, 1).contiguous()                          # [K, Cout, Cin]
+        wh = wk.bfloat16()
+        wl = (wk - wh.float()).bfloat16()
+        return wh, wl
+
+    @staticmethod
+    def _gemm_geometry(B, T, K, stride, dil, pad):
+        Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        Tout_p = (T + 2 * pad + stride - 1) // stride              # output rows per clip (>= Tout; the extra ones are never read back)
+        Tp = stride * Tout_p                                          # input rows per clip (>= T + 2 pad)
+        return Tout, Tout_p, Tp, B * Tout_p, B * Tp + dil * (K - 1) + 1
+
+    def _gemm_conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
+        L = self.L
+        self._req(x, w, b)
+        B, Cin, T = x.shape
+        Cout, _, K = w.shape
+        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
+        X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
+        wh, wl = self._split_weights(w)
+        D = self._buf("D", (M, Cout), torch.float32, x.device)
+        bias = b.clone() if (b is not None and b.data_ptr() % 16) else b
+        first = True
+        for k in range(K):
+            A = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
+            L.gemm(A, torch.cat([wh[k], wh[k]], dim=1), D, epi=L.EPI_F32 if first else L.EPI_F32_ADD, bias=bias if first else None)
+            L.gemm(A[:, :Cin], wl[k], D, epi=L.EPI_F32_ADD)
+            first = False
+        return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0)
+
+    def _gemm_conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
+        L = self.L
+        dy = dy.contiguous()
+        self._req(dy, x, w)
+        B, Cin, T = x.shape
+        Cout, _, K = w.shape
+        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
+        DY = self._cl_split("dy", dy, Tout_p, 0, M)
+        wh, wl = self._split_weights(w)
+        dx = None
+        if need_dx:
+            Dx = self._buf("Dx", (rows, Cin), torch.float32, x.device)
+            Dx.zero_()
+            for k in range(K):
+                O = Dx[k * dil:k * dil + stride * (M - 1) + 1:stride]
+                L.gemm(DY, torch.cat([wh[k], wh[k]], dim=0), O, b_mn=True, epi=L.EPI_F32_ADD)
+                L.gemm(DY[:, :Cout], wl[k], O, b_mn=True, epi=L.EPI_F32_ADD)
+            dx = self._cl_unpack(Dx, B, Cin, T, Tp, pad)
+            if pre_lrelu:
+                self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dx), self._p(dx), x.numel(), 0.1, 1, self._st()), "ttts_lrelu (dgrad)")
+        X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
+        acc = torch.zeros(K, Cout, 2 * Cin, dtype=torch.float32, device=x.device)
+        for k in range(K):
+            Xk = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
+            L.gemm(DY[:, :Cout], Xk, acc[k], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+            L.gemm(DY[:, Cout:], Xk[:, :Cin], acc[k][:, :Cin], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+        dw = (acc[:, :, :Cin] + acc[:, :, Cin:]).permute(1, 2, 0).contiguous()
+        db = None
+        if need_db:
+            db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            self._chk(self.lib.ttts_bias_grad(self._p(dy), self._p(db), B, Cout, Tout, self._st()), "ttts_bias_grad")
+        return dx, dw, db
+
     # ---- convolution / weight norm ----
     def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, groups=1):
         if groups > 1:                                                 # DiscriminatorS (vq2.py:498-507): csrc/conv1d_grouped.cu
@@ -595,6 +713,8 @@ class CudaKernels:
             y = torch.empty(B, Cout, (Tin + 2 * pad - K) // stride + 1, dtype=torch.float32, device=x.device)
             self._chk(self.lib.ttts_gconv1d(self._p(x), self._p(w), self._p(b), self._p(y), B, Cin, Tin, Cout, K, stride, pad, groups, self._st()), "ttts_gconv1d")
             return y
+        if self._gemm_ok(x, w, stride, dil, pad, groups):
+            return self._gemm_conv_fwd(x, w, b, stride, dil, pad, pre_lrelu)
         return self.E.conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=pre_lrelu)
 
     def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
@@ -612,6 +732,8 @@ class CudaKernels:
                 db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
                 self._chk(self.lib.ttts_bias_grad(self._p(dy), self._p(db), B, Cout, dy.shape[-1], self._st()), "ttts_bias_grad")
             return dx, dw, db
+        if self._gemm_ok(x, w, stride, dil, pad, groups):
+            return self._gemm_conv_bwd(dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db)
         self._req(dy, x, w)
         B, Cin, Tin = x.shape
         Cout, _, K = w.shape
