@@ -256,7 +256,11 @@ def test_trainer_surface_save_load(K, tmp_path):
     (16, 1024, 253, 1024, 5, 1, 1, 2, False),     # ... 1024 -> 1024, stride 1
     (4, 128, 2560, 128, 11, 1, 5, 25, True),      # Generator ResBlock1: kernel 11, dilation 5, leaky ReLU on the input (modules.py:224-318)
     (6, 256, 700, 128, 7, 2, 3, 9, True),         # stride, dilation and padding together
-    (5, 192, 1000, 512, 7, 1, 1, 3, False)])      # Generator.conv_pre
+    (5, 192, 1000, 512, 7, 1, 1, 3, False),       # Generator.conv_pre
+    (3, 64, 1700, 64, 11, 1, 1, 5, True),         # narrow layers (tap-concatenated form only): Generator ResBlocks at 64 ...
+    (3, 32, 2100, 32, 7, 1, 1, 3, True),          # ... and 32 channels
+    (4, 32, 1500, 128, 5, 3, 1, 2, False),        # DiscriminatorP 32 -> 128, stride 3
+    (2, 64, 1203, 32, 3, 1, 1, 1, False)])
 def test_tensor_core_convolution_vs_torch(K, monkeypatch, B, Cin, T, Cout, Kw, stride, dil, pad, lrelu):
     """the split-bf16 tcgen05 GEMM route of the wide convolutions (forward, input gradient, weight and bias gradient; any kernel size, stride,
     dilation, padding, optional leaky ReLU on the input) against torch's fp64 convolution: fp32-grade agreement (three bf16 products per fp32
@@ -267,6 +271,10 @@ def test_tensor_core_convolution_vs_torch(K, monkeypatch, B, Cin, T, Cout, Kw, s
     w = torch.randn(Cout, Cin, Kw, generator=g) / (Cin * Kw) ** 0.5
     b = torch.randn(Cout, generator=g)
     xc, wc, bc = cu(x, w, b)
+    if Cin % 64 or Cout % 64 or min(Cin, Cout) < 128:
+        if not (K.tap_concat and K.wgrad_concat):
+            pytest.skip("narrow layers take the route in the tap-concatenated form only")
+        monkeypatch.setattr(K, "gemm_narrow", True)                   # opt-in in the product (TTTS_GEMM_NARROW=1)
     monkeypatch.setattr(K, "GEMM_MIN_POSITIONS", 1)                   # the product takes this route from 4096 output positions; the test shapes are smaller
     assert K._gemm_ok(xc, wc, stride, dil, pad, 1)
     xr, wr, br = x.cuda().double().requires_grad_(True), w.cuda().double().requires_grad_(True), b.cuda().double().requires_grad_(True)
@@ -277,6 +285,33 @@ def test_tensor_core_convolution_vs_torch(K, monkeypatch, B, Cin, T, Cout, Kw, s
     dx, dw, db = K.conv_bwd(dy.cuda(), xc, wc, stride, dil, pad, lrelu, True, True)
     rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm())
     assert y.shape == yr.shape
+    assert rel(y, yr) <= 2e-5, rel(y, yr)
+    assert rel(dx, xr.grad) <= 2e-5, rel(dx, xr.grad)
+    assert rel(dw, wr.grad) <= 2e-5, rel(dw, wr.grad)
+    assert rel(db, br.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("B,Cin,T,Cout,Kw,stride,pad", [(8, 512, 40, 256, 16, 8, 4), (4, 128, 700, 64, 4, 2, 1), (3, 256, 330, 128, 16, 8, 4)])
+def test_conv_transpose_on_the_gemm_route(K, monkeypatch, B, Cin, T, Cout, Kw, stride, pad):
+    """Generator.ups (ConvTranspose1d, modules.py / vq2.py Generator): forward = the phases of a strided input gradient, each a stride-1
+    convolution with K / stride taps on the split-bf16 GEMM route; backward = a strided convolution (dx) and its weight gradient with the roles
+    of x and dy swapped -- against torch's fp64 conv_transpose1d"""
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(Cin + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, Kw, generator=g) / (Cin * Kw / stride) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    monkeypatch.setattr(K, "GEMM_MIN_POSITIONS", 1)
+    monkeypatch.setattr(K, "gemm_narrow", True)
+    xc, wc, bc = cu(x, w, b)
+    xr, wr, br = x.cuda().double().requires_grad_(True), w.cuda().double().requires_grad_(True), b.cuda().double().requires_grad_(True)
+    yr = F.conv_transpose1d(xr, wr, br, stride=stride, padding=pad)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy.cuda().double())
+    y = K.convT_fwd(xc, wc, bc, stride, pad)
+    dx, dw, db = K.convT_bwd(dy.cuda(), xc, wc, stride, pad, True)
+    rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm())
+    assert y.shape == yr.shape and dx.shape == x.shape and dw.shape == w.shape
     assert rel(y, yr) <= 2e-5, rel(y, yr)
     assert rel(dx, xr.grad) <= 2e-5, rel(dx, xr.grad)
     assert rel(dw, wr.grad) <= 2e-5, rel(dw, wr.grad)

@@ -116,6 +116,19 @@ def test_attention_fwd_bwd(L, B, T, H):
         assert rel(dqkv[:, i * d:(i + 1) * d], dref[:, i * d:(i + 1) * d]) < 8e-3
 
 
+def test_attention_tail_split_opt_in():
+    """TTTS_ATTN_TAIL=1 (csrc/attention_tail.cu: the last T mod 128 <= 16 query rows on CUDA cores, the tile kernels stop at the last full
+    tile): the same parity tests, in a child process (the switch is read once per process).  T = 644, 131, 389 take the split."""
+    import subprocess, sys, os
+    if os.environ.get("TTTS_TEST_CHILD") == "1":
+        pytest.skip("child process of this very test")
+    env = dict(os.environ, TTTS_ATTN_TAIL="1", TTTS_TEST_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k",
+                        "test_attention_fwd_bwd or (test_attention_dropout_exact_with_mask and not 1-389-4-1 and not 2-200-2-1)"],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("legacy", [0, 1])
 @pytest.mark.parametrize("B,T,H", [(2, 200, 2), (1, 389, 4)])
 def test_attention_dropout_exact_with_mask(L, B, T, H, legacy):

@@ -61,17 +61,24 @@ def run(B=64, iters=3, with_cpu=False, cpu_batch=2):
     launches = (lib.ttts_launch_count() - l0) // iters
     res = {"workload": "VQ-VAE-GAN train step (BASELINE config 4): enc + VQ + dec + disc, generator + discriminator AdamW, segment 20480, aug = identity",
            "batch": B, "samples_per_clip": 23040, "ms_per_step": ms, "host_ms_per_step": wall, "msamples_per_s": B * 23040 / ms / 1e3,
-           "gpu_launches_per_step": int(launches), "dtype": "f32",
+           "gpu_launches_per_step": int(launches), "dtype": "f32 (wide convolutions: split-bf16 tcgen05, 3 bf16 products per fp32 product)",
            "step_tflops": FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
            "flop_model": "3.87e11 FLOP per clip and step (SURVEY.md section 6, FlopCounterMode over the reference's step)",
            "losses": {k: float(v) for k, v in out.items()}}
-    # roofline of the step's dominant kernels (profiles/r2c_launches_vqvae_b8_summary.txt: conv1d_dgrad 36 %, conv1d_wgrad 26 % of the
-    # serialised step): one more step per family with a CUDA-event pair around each of its launches.  Exact fp32 on the CUDA cores, so the
-    # roof is the fp32 FMA pipe (148 SMs x 128 lanes x 2 FLOP x max SM clock); the bf16 tensor roof / 3 (split operands) is given beside it.
+    # roofline of the step's kernel families: one more step per family with a CUDA-event pair around each of its launches (host_util.cu:
+    # 1 = the tcgen05 GEMM that the wide convolutions run on with split-bf16 operands, 3 = conv1d_wgrad2, 4 = the fp32 forward kernels, which
+    # also compute the input gradients).  The GEMM family is measured against the measured dense bf16 peak (its FLOP count is the bf16 work:
+    # three bf16 products per fp32 product), the exact-fp32 CUDA-core families against the fp32 FMA pipe (148 SMs x 128 lanes x 2 FLOP x max clock).
     import ctypes
     fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    try:
+        bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+        peak_src = "measured (MEASURED_PEAKS.json, burst)"
+    except (OSError, KeyError):
+        bf16_peak, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
     roof = {}
-    for kind, name in ((2, "conv1d_dgrad_kernel"), (3, "conv1d_wgrad_kernel")):
+    for kind, name, tensor in ((1, "gemm_bf16 / gemm2_bf16_kernel (tcgen05; split-bf16 convolutions)", True), (3, "conv1d_wgrad2_kernel", False),
+                               (4, "conv1d_igemm_pipe_kernel / conv1d_direct_kernel (fp32 forward family, incl. input gradients)", False)):
         lib.ttts_prof_gemm_enable(kind)
         step()
         ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -79,12 +86,14 @@ def run(B=64, iters=3, with_cpu=False, cpu_batch=2):
         lib.ttts_prof_gemm_enable(0)
         if ms_k.value > 0:
             tf = fl_k.value / (ms_k.value * 1e-3) / 1e12
+            pk = bf16_peak if tensor else fma_peak
             roof[name] = {"launches": int(n_k.value), "ms_per_step": ms_k.value, "share_of_step": ms_k.value / ms, "tflops": tf,
-                          "frac_fp32_fma_peak": tf / fma_peak, "fp32_fma_peak_tflops": fma_peak}
+                          "bound": "tensor (dense bf16, %s)" % peak_src if tensor else "fp32 FMA pipe", "peak_tflops": pk, "frac": tf / pk}
     if roof:
         top = max(roof, key=lambda k: roof[k]["ms_per_step"])
-        res["roofline"] = {"bound": "fp32 FMA pipe (exact-fp32 CUDA-core implicit GEMM)", "kernel": top, "achieved": roof[top]["tflops"], "peak": fma_peak,
-                           "unit": "TFLOP/s", "frac": roof[top]["frac_fp32_fma_peak"], "traffic": None, "kernels": roof}
+        res["roofline"] = {"bound": "tensor" if roof[top]["bound"].startswith("tensor") else "fp32 FMA pipe (exact-fp32 CUDA-core implicit GEMM)",
+                           "kernel": top, "achieved": roof[top]["tflops"], "peak": roof[top]["peak_tflops"], "unit": "TFLOP/s", "frac": roof[top]["frac"],
+                           "traffic": None, "kernels": roof}
     if with_cpu:
         try:
             res["cpu_baseline"] = cpu_reference_step(cpu_batch)

@@ -4,8 +4,12 @@
 // text 128 + 2, codes 1024 + 2 = 1156 = 9 x 128 + 4 positions (ttts/gpt/model.py:454-489: start / stop tokens around both segments), so a
 // tenth query tile with FOUR valid rows walked all ten key blocks at full tile cost: 10 of 55 block pairs per head = 18 % of the forward and of
 // the backward (cfg2: T = 644 = 5 x 128 + 4, 6 of 21 pairs).  When 0 < T mod 128 <= 16 the tile kernels now stop at Tm = T - T mod 128 (all
-// their tiles full, no sequence-end masks) and these two kernels do the r = T - Tm tail rows: r x T x 64 multiply-adds per head, a few
-// microseconds for the whole batch.
+// their tiles full, no sequence-end masks) and these two kernels do the r = T - Tm tail rows: r x T x 64 multiply-adds per head.
+//
+// STATUS: opt-in (TTTS_ATTN_TAIL=1), parity-green on a B200 (r2ab, r2ac) but NOT a win: the arithmetic is negligible, the traffic is not --
+// four query rows meet every key, so the forward streams K and V (151 MB at B = 32, H = 16, T = 1156) once more and the backward adds a
+// read-modify-write of every dK / dV row (453 MB, 70 us at the HBM roof): 61 / 200 us measured against 51 / 90 us saved in the tile kernels.
+// Kept as the reference for the in-tile version (tail rows handled while the key / value tiles sit in shared memory), which removes that traffic.
 //
 // Same arithmetic and rounding points as the tile kernels (HF: modeling_gpt2.py:185-226; dropout on the probabilities, :207-222):
 //   forward : s = q . k (bf16 products, fp32 sum) ; m = max s ; p = 2^(s c - m c), c = scale log2 e ; l = sum p (fp32, before dropout) ;
@@ -51,17 +55,74 @@ TTTS_DEVICE bool tail_keep(const AttnDropRow rk, int j, uint32_t thresh16) {
     return attn_drop_keep(w0, w1, j & 3, thresh16 << 16);
 }
 
-// shared memory (floats): q rows [R][64] | (backward: dO rows [R][64]) | row stats [2][R] | score rows [R][T] (backward: two of them) |
-// cross-slice reduction [4][R][64]
+TTTS_DEVICE void tail_unpack8(const uint4 v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// red[warp][i][c] = this warp's share of sum_j w[i][j] m[j][c]   (w: shared [R][T]; m: bf16 rows of 64 dims, row pitch ld elements).
+// lane = (key mod 4, 8-dim chunk): a warp load covers four whole 128-byte rows; warp x takes keys 4 x .. 4 x + 3 of every 32.  The loads of
+// four rounds are requested before the first multiply-add: r2ab measured the one-load-per-iteration form of this loop at ~50 us per CTA
+// (every iteration exposed a full L2 round trip), slower than the tile it was meant to replace.
 template <int R>
-__global__ void __launch_bounds__(AT_TAIL_THREADS)
+TTTS_DEVICE void tail_rows_times_matrix(const float* w, const bf16* mp, int ld, int T, float* red) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kq = lane >> 3, c8 = lane & 7;
+    float acc[R][8];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+    for (int j0 = warp * 4 + kq; j0 < T; j0 += 32 * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 32 * u;
+            raw[u] = j < T ? *reinterpret_cast<const uint4*>(mp + (size_t)j * ld + c8 * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < T) {
+                float mf[8];
+                tail_unpack8(raw[u], mf);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const float wv = w[(size_t)i * T + j];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wv, mf[e], acc[i][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = acc[i][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (kq == 0) red[(warp * R + i) * 64 + c8 * 8 + e] = v;
+        }
+}
+TTTS_DEVICE float tail_red8(const float* red, int R, int i, int c) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < AT_TAIL_THREADS / 32; ++w) v += red[(w * R + i) * 64 + c];
+    return v;
+}
+
+// shared memory (floats): q rows [R][64] | (backward: dO rows [R][64]) | row stats [2][R] | score rows [R][T] (backward: two of them) |
+// cross-warp reduction [8][R][64]
+template <int R>
+__global__ void __launch_bounds__(AT_TAIL_THREADS, R <= 4 ? 4 : (R <= 8 ? 2 : 1))
 attn_tail_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse_out, int T, int Tm, int H, float scale,
                      uint32_t thresh16, float drop_scale, uint64_t seed) {
     TTTS_DYN_SMEM(float, tail_sm);
     float* qs = tail_sm;                      // [R][64]
     float* stat = qs + R * 64;                // [R] row sums
     float* sc = stat + 2 * R;                 // [R][T]
-    float* red = sc + (size_t)R * T;          // [4][R][64]
+    float* red = sc + (size_t)R * T;          // [8][R][64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bh = blockIdx.x, b = bh / H, h = bh - b * H, d = H * 64, ld = 3 * d;
     const int r = T - Tm;
@@ -123,25 +184,12 @@ attn_tail_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
         }
     }
     __syncthreads();
-    // out rows = P V: thread = (output dim, key slice)
-    {
-        const int c = tid & 63, sl = tid >> 6;
-        const bf16* vp = base + 2 * d + c;
-        float acc[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) acc[i] = 0.f;
-        for (int j = sl; j < T; j += 4) {
-            const float v = tail_bf(vp + (size_t)j * ld);
-#pragma unroll
-            for (int i = 0; i < R; ++i) acc[i] = fmaf(sc[(size_t)i * T + j], v, acc[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < R; ++i) red[(sl * R + i) * 64 + c] = acc[i];
-    }
+    // out rows = P V
+    tail_rows_times_matrix<R>(sc, base + 2 * d, ld, T, red);
     __syncthreads();
     for (int e = tid; e < r * 64; e += AT_TAIL_THREADS) {
         const int i = e >> 6, c = e & 63;
-        const float o = (red[(0 * R + i) * 64 + c] + red[(1 * R + i) * 64 + c]) + (red[(2 * R + i) * 64 + c] + red[(3 * R + i) * 64 + c]);
+        const float o = tail_red8(red, R, i, c);
         const float l = stat[i];
         const float inv = l > 0.f ? drop_scale / l : 0.f;
         out[(size_t)(b * T + Tm + i) * d + h * 64 + c] = __float2bfloat16_rn(o * inv);
@@ -149,7 +197,7 @@ attn_tail_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
 }
 
 template <int R>
-__global__ void __launch_bounds__(AT_TAIL_THREADS)
+__global__ void __launch_bounds__(AT_TAIL_THREADS, R <= 4 ? 4 : (R <= 8 ? 2 : 1))
 attn_tail_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse, const float* __restrict__ delta,
                      bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int Tm, int H, float scale, uint32_t thresh16, float drop_scale,
                      uint64_t seed) {
@@ -160,7 +208,7 @@ attn_tail_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
     uint32_t* rkw = reinterpret_cast<uint32_t*>(stat + 2 * R);      // [2][R]: the rows' dropout keys
     float* sp = stat + 4 * R;                 // [R][T]  P~
     float* sd = sp + (size_t)R * T;           // [R][T]  dS~
-    float* red = sd + (size_t)R * T;          // [4][R][64]
+    float* red = sd + (size_t)R * T;          // [8][R][64]
     const int tid = threadIdx.x;
     const int bh = blockIdx.x, b = bh / H, h = bh - b * H, d = H * 64, ld = 3 * d;
     const int r = T - Tm;
@@ -219,64 +267,60 @@ attn_tail_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
         }
     }
     __syncthreads();
-    // dK / dV rows: thread = (key, 8-dim chunk); read - add - write for the keys the tile kernel has written (j < Tm)
+    // dK / dV rows: thread = (key, 8-dim chunk); read - add - write for the keys the tile kernel has written (j < Tm).  Four items per round,
+    // all eight loads requested before the first store (a load may not be moved above a store the compiler cannot tell apart from it)
     {
+        constexpr int U = 4;
         const float ks = scale * drop_scale;
-        for (int it = tid; it < T * 8; it += AT_TAIL_THREADS) {
-            const int j = it >> 3, c8 = it & 7;
-            bf16* dkp = dqkv + (size_t)(b * T + j) * ld + d + h * 64 + c8 * 8;
-            bf16* dvp = dkp + d;
-            float ok[8], ov[8];                                        // requested first: the shared-memory sums below run under the two loads
-            if (j < Tm) {
-                tail_ld8(dkp, ok);
-                tail_ld8(dvp, ov);
-            } else {
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int it0 = tid; it0 < T * 8; it0 += AT_TAIL_THREADS * U) {
+            uint4 rk4[U], rv4[U];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { ok[e] = 0.f; ov[e] = 0.f; }
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + AT_TAIL_THREADS * u, j = it >> 3, c8 = it & 7;
+                const bool rd = it < T * 8 && j < Tm;
+                const bf16* dkp = dqkv + (size_t)(b * T + (rd ? j : 0)) * ld + d + h * 64 + c8 * 8;
+                rk4[u] = rd ? *reinterpret_cast<const uint4*>(dkp) : z4;
+                rv4[u] = rd ? *reinterpret_cast<const uint4*>(dkp + d) : z4;
             }
-            float ak[8], av[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { ak[e] = 0.f; av[e] = 0.f; }
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + AT_TAIL_THREADS * u, j = it >> 3, c8 = it & 7;
+                if (it < T * 8) {
+                    float ak[8], av[8], ok[8], ov[8];
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const float ds = sd[(size_t)i * T + j], p = sp[(size_t)i * T + j];
+                    for (int e = 0; e < 8; ++e) { ak[e] = 0.f; av[e] = 0.f; }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    ak[e] = fmaf(ds, qs[i * 64 + c8 * 8 + e], ak[e]);
-                    av[e] = fmaf(p, dos[i * 64 + c8 * 8 + e], av[e]);
+                    for (int i = 0; i < R; ++i) {
+                        const float ds = sd[(size_t)i * T + j], p = sp[(size_t)i * T + j];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            ak[e] = fmaf(ds, qs[i * 64 + c8 * 8 + e], ak[e]);
+                            av[e] = fmaf(p, dos[i * 64 + c8 * 8 + e], av[e]);
+                        }
+                    }
+                    tail_unpack8(rk4[u], ok);
+                    tail_unpack8(rv4[u], ov);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { ok[e] = fmaf(ak[e], ks, ok[e]); ov[e] = fmaf(av[e], drop_scale, ov[e]); }
+                    bf16* dkp = dqkv + (size_t)(b * T + j) * ld + d + h * 64 + c8 * 8;
+                    *reinterpret_cast<uint4*>(dkp) = make_uint4(pack_bf16(ok[0], ok[1]), pack_bf16(ok[2], ok[3]), pack_bf16(ok[4], ok[5]), pack_bf16(ok[6], ok[7]));
+                    *reinterpret_cast<uint4*>(dkp + d) = make_uint4(pack_bf16(ov[0], ov[1]), pack_bf16(ov[2], ov[3]), pack_bf16(ov[4], ov[5]), pack_bf16(ov[6], ov[7]));
                 }
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { ok[e] = fmaf(ak[e], ks, ok[e]); ov[e] = fmaf(av[e], drop_scale, ov[e]); }
-            *reinterpret_cast<uint4*>(dkp) = make_uint4(pack_bf16(ok[0], ok[1]), pack_bf16(ok[2], ok[3]), pack_bf16(ok[4], ok[5]), pack_bf16(ok[6], ok[7]));
-            *reinterpret_cast<uint4*>(dvp) = make_uint4(pack_bf16(ov[0], ov[1]), pack_bf16(ov[2], ov[3]), pack_bf16(ov[4], ov[5]), pack_bf16(ov[6], ov[7]));
         }
     }
-    // dQ rows (fp32 accumulator, unscaled): thread = (dim, key slice)
-    {
-        const int c = tid & 63, sl = tid >> 6;
-        const bf16* kp = base + d + c;
-        float acc[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) acc[i] = 0.f;
-        for (int j = sl; j < T; j += 4) {
-            const float k = tail_bf(kp + (size_t)j * ld);
-#pragma unroll
-            for (int i = 0; i < R; ++i) acc[i] = fmaf(sd[(size_t)i * T + j], k, acc[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < R; ++i) red[(sl * R + i) * 64 + c] = acc[i];
-    }
+    // dQ rows (fp32 accumulator, unscaled) = dS~ K
+    tail_rows_times_matrix<R>(sd, base + d, ld, T, red);
     __syncthreads();
     for (int e = tid; e < r * 64; e += AT_TAIL_THREADS) {
         const int i = e >> 6, c = e & 63;
-        dq_acc[(size_t)(b * T + Tm + i) * d + h * 64 + c] =
-            (red[(0 * R + i) * 64 + c] + red[(1 * R + i) * 64 + c]) + (red[(2 * R + i) * 64 + c] + red[(3 * R + i) * 64 + c]);
+        dq_acc[(size_t)(b * T + Tm + i) * d + h * 64 + c] = tail_red8(red, R, i, c);
     }
 }
 
 static size_t tail_smem_bytes(int R, int T, bool bwd) {
-    return sizeof(float) * ((size_t)(bwd ? 2 : 1) * R * 64 + (bwd ? 4 : 2) * R + (size_t)(bwd ? 2 : 1) * R * T + 4 * R * 64);
+    return sizeof(float) * ((size_t)(bwd ? 2 : 1) * R * 64 + (bwd ? 4 : 2) * R + (size_t)(bwd ? 2 : 1) * R * T + (AT_TAIL_THREADS / 32) * R * 64);
 }
 static int tail_R(int r) { return r <= 4 ? 4 : (r <= 8 ? 8 : 16); }
 

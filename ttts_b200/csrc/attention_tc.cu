@@ -742,10 +742,15 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* _
     }
 }
 
-// TTTS_ATTN_TAIL=0: the tile kernels take the ragged last query tile themselves (A/B measurements)
+// TTTS_ATTN_TAIL=1: leave a ragged last query tile of <= 16 rows to attention_tail.cu.  OFF by default -- measured (r2ab / r2ac, B = 32,
+// H = 16, T = 1156): the tile kernels do get faster without their tenth, four-row query tile (forward 0.362 -> 0.311 ms, backward
+// 0.62 -> 0.53 ms), but four query rows still meet EVERY key: the tail kernels stream K and V (151 MB) once more in the forward and K, V plus
+// a read-modify-write of all dK / dV rows (453 MB, 70 us at the HBM roof) in the backward, and came out at 61 / 200 us -- a net loss
+// (forward 0.382 vs 0.362 ms, backward 0.814 vs 0.685 ms).  The traffic only disappears if the tail rows are handled while the key / value
+// tiles are resident in shared memory, i.e. inside the tile kernels.
 bool attn_tail_split() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("TTTS_ATTN_TAIL"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on < 0) { const char* e = getenv("TTTS_ATTN_TAIL"); on = (e && e[0] == '1') ? 1 : 0; }
     return on != 0;
 }
 
@@ -766,7 +771,7 @@ int attn_fwd_tc(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, DropC
         TTTS_CUDA(cudaFuncSetAttribute(attn_fwd_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kBytes));
         attr4 = true;
     }
-    // a ragged tail of <= 16 rows (T = 1156 = 9 x 128 + 4 in training) is left to attention_tail.cu: the tile kernel stops at Tm
+    // opt-in (see attn_tail_split): a ragged tail of <= 16 rows (T = 1156 = 9 x 128 + 4 in training) is left to attention_tail.cu, the tile kernel stops at Tm
     const int tail = attn_tail_split() ? attn_tail_rows(T) : 0;
     const int Tm = T - tail;
     const int nq = (Tm + AT_BM - 1) / AT_BM;

@@ -725,8 +725,13 @@ static int conv1d_run(const float* x, const float* w, const float* bias, float* 
 int ttts_conv1d_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                     int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,
                     const float* mask, int32_t post, const float* cond, int32_t cond_ld, void* stream) {
-    return conv1d_run(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld, 0,
-                      (cudaStream_t)stream);
+    // profiling family 4 (host_util.cu): the fp32 forward kernels -- also the input gradients that run on them (flipped weights / phases)
+    const int Tout_ = (Tin + 2 * pad - dil * (K - 1) - 1) / (stride > 0 ? stride : 1) + 1;
+    prof_begin(4, (cudaStream_t)stream, 2.0 * B * (double)(Tout_ > 0 ? Tout_ : 0) * Cin * Cout * K);
+    const int rc = conv1d_run(x, w, bias, y, B, Cin, Tin, Cout, K, stride, dil, pad, pre_lrelu, resid, out_scale, accumulate, mask, post, cond, cond_ld, 0,
+                              (cudaStream_t)stream);
+    prof_end(4, (cudaStream_t)stream);
+    return rc;
 }
 int ttts_conv1d_f32_split(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout, int32_t K,
                           int32_t stride, int32_t dil, int32_t pad, int32_t pre_lrelu, const float* resid, float out_scale, int32_t accumulate,

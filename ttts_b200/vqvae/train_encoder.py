@@ -530,6 +530,13 @@ class CudaKernels:
         self.dgrad_as_forward = os.environ.get("TTTS_DGRAD_FWD", "1") != "0"
         # wide convolutions (both channel counts multiples of 64 and >= 128, >= 4096 output positions) as split-bf16 GEMMs on the tcgen05 GEMM
         self.conv_gemm = os.environ.get("TTTS_TRAIN_GEMM", "1") != "0" and os.environ.get("TTTS_DIFF_TC", "1") != "0"
+        # dil = 1 layers: all taps in one GEMM reduction over an overlapped view of the activation rows (TTTS_GEMM_TAPCAT=0: one GEMM pair per tap)
+        self.tap_concat = os.environ.get("TTTS_GEMM_TAPCAT", "1") != "0"
+        self.wgrad_concat = self.tap_concat and os.environ.get("TTTS_GEMM_WCAT", "1") != "0"        # the same for the weight gradient
+        # 32- / 64-channel dil = 1 layers too: parity-green (tests/test_gpu_diffusion.py) but OFF by default -- r2ae, B = 64: the fp32 families lose
+        # 83 ms, the GEMM family gains 44 ms and the layout conversions around it (cl_split / cl_unpack of [B, C, 10 240] tensors) the rest:
+        # 549 vs 541 ms per step
+        self.gemm_narrow = os.environ.get("TTTS_GEMM_NARROW", "0") == "1"
 
     @staticmethod
     def _train_protos(lib):
@@ -611,8 +618,15 @@ class CudaKernels:
         B, Cin, T = x.shape
         Cout, _, K = w.shape
         Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
-        return (Cin % 64 == 0 and Cout % 64 == 0 and min(Cin, Cout) >= 128 and K <= 16 and stride <= 8 and Tout >= 1
-                and B * Tout >= self.GEMM_MIN_POSITIONS)
+        if not (K <= 16 and stride <= 8 and Tout >= 1 and B * Tout >= self.GEMM_MIN_POSITIONS):
+            return False
+        if Cin % 64 == 0 and Cout % 64 == 0 and min(Cin, Cout) >= 128:
+            return True
+        # narrow layers (the Generator's 64- and 32-channel ResBlock convolutions on 5 120 / 10 240 positions per clip): only in the
+        # tap-concatenated form, where every product reduces over K 2 Cin >= 64 and the accumulator is swept twice instead of 2 K times
+        # (per tap these layers were bound by that traffic and lost to the fp32 kernels)
+        return (self.gemm_narrow and self.tap_concat and self.wgrad_concat and dil == 1 and K > 1 and Cin % 32 == 0 and Cout % 32 == 0
+                and pad <= K - 1 and (stride == 1 or Cout % 64 == 0))
 
     def _buf(self, key, shape, dtype, dev, zero=False):
         """transient buffers, one per key: every use is ordered on the current stream"""
@@ -662,6 +676,18 @@ class CudaKernels:
         wh, wl = self._split_weights(w)
         D = self._buf("D", (M, Cout), torch.float32, x.device)
         bias = b.clone() if (b is not None and b.data_ptr() % 16) else b
+        if dil == 1 and K > 1 and self.tap_concat:
+            # all taps in ONE reduction: row m of the A operand is the K consecutive buffer rows stride m .. stride m + K - 1 seen as one
+            # K 2C-wide row -- an OVERLAPPED view (row pitch stride 2C < row length K 2C; the TMA tensor map takes the pitch as given), so
+            # still no im2col.  D is written once and updated once instead of 2 K read-modify-write sweeps (r2aa launch list: the per-tap
+            # GEMMs of a 128-channel K = 11 layer were bound by that fp32 accumulator traffic, not by the tensor cores).  The hi . lo
+            # product reads the same operand against [wl_k | 0] (the zero half costs MMA time, which is not what bounds these layers).
+            A = X.as_strided((M, K * 2 * Cin), (stride * 2 * Cin, 1))
+            W1 = torch.cat([wh, wh], dim=2).permute(1, 0, 2).reshape(Cout, K * 2 * Cin)
+            W2 = torch.cat([wl, torch.zeros_like(wl)], dim=2).permute(1, 0, 2).reshape(Cout, K * 2 * Cin)
+            L.gemm(A, W1, D, epi=L.EPI_F32, bias=bias)
+            L.gemm(A, W2, D, epi=L.EPI_F32_ADD)
+            return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0)
         first = True
         for k in range(K):
             A = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
@@ -680,6 +706,14 @@ class CudaKernels:
         DY = self._cl_split("dy", dy, Tout_p, 0, M)
         wh, wl = self._split_weights(w)
         dx = None
+        if need_dx and stride == 1 and dil == 1 and K > 1 and pad <= K - 1 and self.tap_concat:
+            # input gradient of a stride-1 convolution = the forward route on dy with the taps flipped and the channel roles swapped
+            # (padding K - 1 - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer
+            dx = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, 1, K - 1 - pad, False)
+            assert dx.shape == x.shape
+            if pre_lrelu:
+                self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dx), self._p(dx), x.numel(), 0.1, 1, self._st()), "ttts_lrelu (dgrad)")
+            need_dx = False
         if need_dx:
             Dx = self._buf("Dx", (rows, Cin), torch.float32, x.device)
             Dx.zero_()
@@ -691,12 +725,22 @@ class CudaKernels:
             if pre_lrelu:
                 self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dx), self._p(dx), x.numel(), 0.1, 1, self._st()), "ttts_lrelu (dgrad)")
         X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
-        acc = torch.zeros(K, Cout, 2 * Cin, dtype=torch.float32, device=x.device)
-        for k in range(K):
-            Xk = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
-            L.gemm(DY[:, :Cout], Xk, acc[k], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
-            L.gemm(DY[:, Cout:], Xk[:, :Cin], acc[k][:, :Cin], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
-        dw = (acc[:, :, :Cin] + acc[:, :, Cin:]).permute(1, 2, 0).contiguous()
+        if dil == 1 and K > 1 and self.wgrad_concat:
+            # all taps as column blocks of ONE product: the overlapped view again, now as the MN-major B operand [positions, K 2 Cin]; dy is read
+            # once per product instead of once per tap.  Both halves of dy meet the whole view, so the lo . lo term comes along for free.
+            Xov = X.as_strided((M, K * 2 * Cin), (stride * 2 * Cin, 1))
+            acc = torch.zeros(Cout, K * 2 * Cin, dtype=torch.float32, device=x.device)
+            L.gemm(DY[:, :Cout], Xov, acc, a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+            L.gemm(DY[:, Cout:], Xov, acc, a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+            acc = acc.view(Cout, K, 2 * Cin)
+            dw = (acc[:, :, :Cin] + acc[:, :, Cin:]).permute(0, 2, 1).contiguous()
+        else:
+            acc = torch.zeros(K, Cout, 2 * Cin, dtype=torch.float32, device=x.device)
+            for k in range(K):
+                Xk = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
+                L.gemm(DY[:, :Cout], Xk, acc[k], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+                L.gemm(DY[:, Cout:], Xk[:, :Cin], acc[k][:, :Cin], a_mn=True, b_mn=True, epi=L.EPI_F32_ADD, split_k=16)
+            dw = (acc[:, :, :Cin] + acc[:, :, Cin:]).permute(1, 2, 0).contiguous()
         db = None
         if need_db:
             db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
@@ -750,7 +794,7 @@ class CudaKernels:
             if pre_lrelu:
                 self._chk(lib.ttts_lrelu(p(x), p(dx), p(dx), x.numel(), 0.1, 1, st), "ttts_lrelu (dgrad)")
         elif need_dx and stride > 1 and dil == 1 and self.dgrad_as_forward and hasattr(self.E, "conv1d") and dy.is_cuda:
-            dx = dgrad_by_phase(lambda a, wt, pd: self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False), dy, w, Tin, stride, pad)
+            dx = dgrad_by_phase(self._phase_conv, dy, w, Tin, stride, pad)
             if pre_lrelu:
                 self._chk(lib.ttts_lrelu(p(x), p(dx), p(dx), x.numel(), 0.1, 1, st), "ttts_lrelu (dgrad)")
         elif need_dx:
@@ -761,6 +805,12 @@ class CudaKernels:
         self._chk(lib.ttts_conv1d_bwd_weight(p(dy), p(x), p(dw), p(db), B, Cin, Tin, Cout, K, stride, dil, pad, int(pre_lrelu), st), "ttts_conv1d_bwd_weight")
         return dx, dw, db
 
+    def _phase_conv(self, a, wt, pd):
+        """stride-1 cross-correlation of one phase (dgrad_by_phase): the GEMM route when the phase's sub-kernel qualifies, else the fp32 kernels"""
+        if self._gemm_ok(a, wt, 1, 1, pd, 1):
+            return self._gemm_conv_fwd(a, wt, None, 1, 1, pd, False)
+        return self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False)
+
     def convT_fwd(self, x, w, b, stride, pad):
         """conv_transpose1d = the input gradient of a convolution whose weight is w read as [Cout' = Cin, Cin' = Cout, K]"""
         self._req(x, w, b)
@@ -769,7 +819,7 @@ class CudaKernels:
         Tout = (T - 1) * stride - 2 * pad + K
         p, lib, st = self._p, self.lib, self._st()
         if self.dgrad_as_forward and hasattr(self.E, "conv1d") and x.is_cuda:
-            y = dgrad_by_phase(lambda a, wt, pd: self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False), x, w, Tout, stride, pad)
+            y = dgrad_by_phase(self._phase_conv, x, w, Tout, stride, pad)
         else:
             y = torch.empty(B, Cout, Tout, dtype=torch.float32, device=x.device)
             self._chk(lib.ttts_conv1d_bwd_input(p(x), p(w), None, p(y), B, Cout, Tout, Cin, K, stride, 1, pad, 0, 0, st), "ttts_conv1d_bwd_input (convT forward)")
@@ -785,8 +835,12 @@ class CudaKernels:
         p, lib, st = self._p, self.lib, self._st()
         dx = self.conv_fwd(dy, w, None, stride, 1, pad, False)                              # [B, Cin, T]
         assert dx.shape == x.shape
-        dw = torch.zeros_like(w)
-        self._chk(lib.ttts_conv1d_bwd_weight(p(x), p(dy), p(dw), None, B, Cout, Tout, Cin, K, stride, 1, pad, 0, st), "ttts_conv1d_bwd_weight (convT)")
+        if self._gemm_ok(dy, w, stride, 1, pad, 1):
+            # the weight gradient of the convolution dy -> x whose input gradient this layer's forward is: roles of x and dy swapped
+            _, dw, _ = self._gemm_conv_bwd(x, dy, w, stride, 1, pad, False, False, False)
+        else:
+            dw = torch.zeros_like(w)
+            self._chk(lib.ttts_conv1d_bwd_weight(p(x), p(dy), p(dw), None, B, Cout, Tout, Cin, K, stride, 1, pad, 0, st), "ttts_conv1d_bwd_weight (convT)")
         db = None
         if need_db:
             db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
