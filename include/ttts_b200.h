@@ -416,7 +416,8 @@ int ttts_diff_loss_bwd(const float* dL, const float* model_out, const float* x_s
  * [hi(x[b,:,t]) | lo(x[b,:,t])] (2C bf16) at row row_off + b rows_per_clip + t of a ZERO-INITIALISED buffer (the untouched rows are the zero
  * padding around and between the clips); and back: D fp32 (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T]. */
 int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu, void* stream);
-int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off, void* stream);
+int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off,
+                   const float* lrelu_x /* NULL, or [B,C,T]: y *= leaky_relu'(lrelu_x), slope 0.1 */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,18 @@ def test_transposed_convolution_from_the_same_kernels(emu, Cin, Cout, K, stride,
     assert float((F.conv1d(dy, wd, None, stride=stride, padding=pad) - x.grad).abs().max()) <= 2e-5 * max(1.0, float(x.grad.abs().max()))
 
 
+@pytest.mark.parametrize("B,C,T", [(3, 5, 2052), (2, 4, 1024), (5, 3, 8), (2, 3, 1030), (1, 2, 7)])
+def test_bias_gradient_kernels(emu, B, C, T):
+    """ttts_bias_grad: the 16-byte-load kernel (T a multiple of 4: items of 1024 positions dealt out over the slices, four loads in flight, the
+    ragged last item of a row) and the scalar kernel (any T); both ADD to db"""
+    g = torch.Generator().manual_seed(B * 100 + T)
+    dy = torch.randn(B, C, T, generator=g)
+    db = torch.full((C,), -2.25)
+    assert emu.emu_bias_grad(dy.data_ptr(), db.data_ptr(), B, C, T) == 0, emu.emu_last_error()
+    want = dy.double().sum(dim=(0, 2))
+    assert float((db.double() + 2.25 - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
 def test_bad_arguments_are_reported(emu):
     t = torch.zeros(8)
     assert emu.emu_conv1d_bwd_input(t.data_ptr(), t.data_ptr(), None, t.data_ptr(), 1, 1, 2, 1, 5, 1, 1, 0, 0, 0) != 0     # empty output

@@ -92,7 +92,7 @@ def test_q_sample_and_loss(K):
     close(K.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), R.diff_loss_bwd(dL, out, x0, xt, noise, coef, t0), 5e-5)
 
 
-@pytest.mark.parametrize("B,C,T", [(2, 40, 37), (1, 64, 64), (3, 7, 5)])
+@pytest.mark.parametrize("B,C,T", [(2, 40, 37), (1, 64, 64), (3, 7, 5), (2, 130, 70), (1, 65, 129)])
 def test_layout_conversion_kernels(K, B, C, T):
     """ttts_cl_split / ttts_cl_unpack: [B,C,T] fp32 <-> position-major split-bf16 rows with zero rows between the clips"""
     g = torch.Generator().manual_seed(B + C + T)
@@ -111,4 +111,18 @@ def test_layout_conversion_kernels(K, B, C, T):
     assert float((rec - x).abs().max()) <= 2 ** -15 * float(x.abs().max())
     D = torch.randn(B * (T + 1), C + 8, generator=g)
     y = K._cl_unpack(D, B, C, T)
-    assert torch.equal(y, D[:, :C].reshape(B, T + 1, C)[:, :T].transpose(1, 2).contiguous())
+    want_y = D[:, :C].reshape(B, T + 1, C)[:, :T].transpose(1, 2).contiguous()
+    assert torch.equal(y, want_y)
+    # with the derivative of a leaky ReLU (slope 0.1) on the layer's input folded in, and the activation itself folded into the split
+    yg = K._cl_unpack(D, B, C, T, lrelu_x=x)
+    assert torch.equal(yg, torch.where(x > 0, want_y, 0.1 * want_y))
+    xa = torch.nn.functional.leaky_relu(x, 0.1)
+    buf2 = K._cl_split("x", x, lrelu=True).clone()
+    assert torch.equal(buf2[:, :C], K._cl_split("x", xa)[:, :C])
+    # other geometries: padding rows before each clip, a longer clip pitch
+    buf3 = K._cl_split("g", x, T + 5, 3, 3 + B * (T + 5) + 2)
+    want3 = torch.zeros_like(buf3)
+    for b in range(B):
+        want3[3 + b * (T + 5):3 + b * (T + 5) + T, :C] = hi[b].t()
+        want3[3 + b * (T + 5):3 + b * (T + 5) + T, C:] = lo[b].t()
+    assert torch.equal(buf3, want3)

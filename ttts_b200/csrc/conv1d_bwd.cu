@@ -339,6 +339,36 @@ __global__ void __launch_bounds__(256) conv1d_bgrad_kernel(const float* __restri
         if (gridDim.y == 1) db[co] += t; else atomicAdd(db + co, t);
     }
 }
+// The same sum with 16-byte loads, four of them in flight per thread, for rows that allow it (Tout a multiple of 4 keeps every (b, co) row
+// 16-byte aligned): an item = 1024 consecutive positions of one (b, co) row, slice y takes items y, y + gridDim.y, ...  r2ah launch list: the
+// scalar kernel above read a 84 MB dy in 92 us (0.9 TB/s: one 4-byte load per thread and iteration, an integer division per element,
+// 384 CTAs) -- as long as one of the GEMMs of the layer it belongs to.
+__global__ void __launch_bounds__(256) conv1d_bgrad4_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int Cout, int Tout) {
+    __shared__ float red[8];
+    const int co = blockIdx.x;
+    const int chunks = (Tout + 1023) / 1024;
+    const int items = B * chunks;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int it0 = blockIdx.y; it0 < items; it0 += 4 * (int)gridDim.y) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * (int)gridDim.y;
+            const int b = it / chunks, t = (it - b * chunks) * 1024 + 4 * (int)threadIdx.x;
+            v[u] = (it < items && t < Tout) ? *reinterpret_cast<const float4*>(dy + ((size_t)b * Cout + co) * Tout + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s0 += v[u].x; s1 += v[u].y; s2 += v[u].z; s3 += v[u].w; }
+    }
+    float s = warp_sum((s0 + s1) + (s2 + s3));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        if (gridDim.y == 1) db[co] += t; else atomicAdd(db + co, t);
+    }
+}
 static inline dim3 bgrad_grid(int B, int Cout, int Tout) {
     const long long P = (long long)B * Tout;
     long long S = (2ll * num_sms() + Cout - 1) / Cout;
@@ -346,6 +376,19 @@ static inline dim3 bgrad_grid(int B, int Cout, int Tout) {
     if (S > s_max) S = s_max;
     if (S < 1) S = 1;
     return dim3(Cout, (unsigned)S);
+}
+// db += column sums of dy [B, Cout, Tout]
+static int bgrad_launch(const float* dy, float* db, int B, int Cout, int Tout, cudaStream_t st) {
+    if ((Tout & 3) == 0 && (((uintptr_t)dy) & 15) == 0) {
+        const long long items = (long long)B * ((Tout + 1023) / 1024);
+        long long S = (8ll * num_sms() + Cout - 1) / Cout;               // ~8 CTAs per SM in all
+        const long long s_max = (items + 3) / 4;                          // at least one full round of four loads per slice
+        if (S > s_max) S = s_max;
+        if (S < 1) S = 1;
+        if (S > 65535) S = 65535;
+        return (int)launch_plain(conv1d_bgrad4_kernel, dim3(Cout, (unsigned)S), dim3(256), 0, st, dy, db, B, Cout, Tout);
+    }
+    return (int)launch_plain(conv1d_bgrad_kernel, bgrad_grid(B, Cout, Tout), dim3(256), 0, st, dy, db, B, Cout, Tout);
 }
 
 static int bwd_params(ConvBwdParams& p, int B, int Cin, int Tin, int Cout, int K, int stride, int dil, int pad) {
@@ -418,7 +461,7 @@ int conv1d_bwd_weight(const float* dy, const float* x, float* dw, float* db, int
     }
     TTTS_LAUNCH_CHECK("conv1d_wgrad");
     if (db) {
-        TTTS_CUDA(launch_plain(conv1d_bgrad_kernel, bgrad_grid(B, Cout, p.Tout), dim3(256), 0, st, dy, db, B, Cout, p.Tout));
+        TTTS_CUDA((cudaError_t)bgrad_launch(dy, db, B, Cout, p.Tout, st));
         TTTS_LAUNCH_CHECK("conv1d_bgrad");
     }
     return TTTS_OK;
@@ -433,7 +476,7 @@ int ttts_conv1d_bwd_input(const float* dy, const float* w, const float* x, float
 }
 int ttts_bias_grad(const float* dy, float* db, int32_t B, int32_t C, int32_t T, void* stream) {
     TTTS_CHECK_ARG(dy && db && B > 0 && C > 0 && T > 0, "bias_grad: bad args");
-    TTTS_CUDA(ttts::launch_plain(ttts::conv1d_bgrad_kernel, ttts::bgrad_grid(B, C, T), dim3(256), 0, (cudaStream_t)stream, dy, db, B, C, T));
+    TTTS_CUDA((cudaError_t)ttts::bgrad_launch(dy, db, B, C, T, (cudaStream_t)stream));
     TTTS_LAUNCH_CHECK("bias_grad");
     return TTTS_OK;
 }

@@ -533,10 +533,10 @@ class CudaKernels:
         # dil = 1 layers: all taps in one GEMM reduction over an overlapped view of the activation rows (TTTS_GEMM_TAPCAT=0: one GEMM pair per tap)
         self.tap_concat = os.environ.get("TTTS_GEMM_TAPCAT", "1") != "0"
         self.wgrad_concat = self.tap_concat and os.environ.get("TTTS_GEMM_WCAT", "1") != "0"        # the same for the weight gradient
-        # 32- / 64-channel dil = 1 layers too: parity-green (tests/test_gpu_diffusion.py) but OFF by default -- r2ae, B = 64: the fp32 families lose
-        # 83 ms, the GEMM family gains 44 ms and the layout conversions around it (cl_split / cl_unpack of [B, C, 10 240] tensors) the rest:
-        # 549 vs 541 ms per step
-        self.gemm_narrow = os.environ.get("TTTS_GEMM_NARROW", "0") == "1"
+        # 32- / 64-channel layers too (TTTS_GEMM_NARROW=0: fp32 kernels).  r2ae, B = 64: the fp32 families lose 83 ms, the GEMM family gains
+        # 44 ms and the layout conversions around such thin GEMMs ate the rest (549 vs 541 ms); with the conversions on 64 x 64 tiles / packed
+        # stores and the 16-byte-load bias gradient (r2ai) the route wins: 501 vs 521 ms per step
+        self.gemm_narrow = os.environ.get("TTTS_GEMM_NARROW", "1") != "0"
 
     @staticmethod
     def _train_protos(lib):
@@ -576,7 +576,7 @@ class CudaKernels:
             lib.ttts_posterior_sample_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
             try:
                 lib.ttts_cl_split.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
-                lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+                lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
             except AttributeError:
                 pass                                                  # an emulation set without csrc/diffusion_kernels.cu
             lib._train_protos = True
@@ -646,10 +646,12 @@ class CudaKernels:
         self._chk(self.lib.ttts_cl_split(self._p(x), self._p(buf), B, C, T, rows_per_clip, row_off, int(bool(lrelu)), self._st()), "ttts_cl_split")
         return buf
 
-    def _cl_unpack(self, D, B, C, T, rows_per_clip=None, row_off=0):
+    def _cl_unpack(self, D, B, C, T, rows_per_clip=None, row_off=0, lrelu_x=None):
+        """D (position-major fp32 rows) -> [B,C,T]; lrelu_x: multiply by leaky_relu'(lrelu_x) on the way (the input gradient of a layer that
+        applies the activation to its input)"""
         y = torch.empty(B, C, T, dtype=torch.float32, device=D.device)
         rows_per_clip = T + 1 if rows_per_clip is None else rows_per_clip
-        self._chk(self.lib.ttts_cl_unpack(self._p(D), self._p(y), B, C, T, D.stride(0), rows_per_clip, row_off, self._st()), "ttts_cl_unpack")
+        self._chk(self.lib.ttts_cl_unpack(self._p(D), self._p(y), B, C, T, D.stride(0), rows_per_clip, row_off, self._p(lrelu_x), self._st()), "ttts_cl_unpack")
         return y
 
     @staticmethod
@@ -659,6 +661,16 @@ class CudaKernels:
         wl = (wk - wh.float()).bfloat16()
         return wh, wl
 
+    def _concat_weights(self, w):
+        """w [Cout, Cin, K] -> the two B operands of the tap-concatenated GEMM pair, [Cout, K 2 Cin] bf16 each: taps side by side, per tap
+        [wh | wh] and [wl | 0]"""
+        Cout, Cin, K = w.shape
+        wk = w.permute(0, 2, 1)                                       # [Cout, K, Cin] (a view)
+        wh = wk.bfloat16()                                            # contiguous [Cout, K, Cin]
+        wl = (wk - wh).bfloat16()                                     # bf16 promotes to fp32 in the subtraction
+        Z = self._buf("wzero", (Cout, K, Cin), torch.bfloat16, w.device, zero=True)
+        return torch.cat([wh, wh], dim=2).view(Cout, K * 2 * Cin), torch.cat([wl, Z], dim=2).view(Cout, K * 2 * Cin)
+
     @staticmethod
     def _gemm_geometry(B, T, K, stride, dil, pad):
         Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
@@ -666,15 +678,21 @@ class CudaKernels:
         Tp = stride * Tout_p                                          # input rows per clip (>= T + 2 pad)
         return Tout, Tout_p, Tp, B * Tout_p, B * Tp + dil * (K - 1) + 1
 
-    def _gemm_conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu):
-        L = self.L
+    def _gemm_conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, lrelu_x=None, split_tag="x"):
+        """lrelu_x: see _cl_unpack (used when this is the input gradient of another layer); returns (y, X) with split_tag given back so that a
+        caller can reuse the split buffer -- plain callers take [0]"""
         self._req(x, w, b)
         B, Cin, T = x.shape
         Cout, _, K = w.shape
         Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
-        X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
-        wh, wl = self._split_weights(w)
-        D = self._buf("D", (M, Cout), torch.float32, x.device)
+        X = self._cl_split(split_tag, x, Tp, pad, rows, pre_lrelu)
+        return self._gemm_conv_core(X, B, Cin, T, w, b, stride, dil, pad, lrelu_x), X
+
+    def _gemm_conv_core(self, X, B, Cin, T, w, b, stride, dil, pad, lrelu_x=None):
+        L = self.L
+        Cout, _, K = w.shape
+        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
+        D = self._buf("D", (M, Cout), torch.float32, X.device)
         bias = b.clone() if (b is not None and b.data_ptr() % 16) else b
         if dil == 1 and K > 1 and self.tap_concat:
             # all taps in ONE reduction: row m of the A operand is the K consecutive buffer rows stride m .. stride m + K - 1 seen as one
@@ -683,18 +701,18 @@ class CudaKernels:
             # GEMMs of a 128-channel K = 11 layer were bound by that fp32 accumulator traffic, not by the tensor cores).  The hi . lo
             # product reads the same operand against [wl_k | 0] (the zero half costs MMA time, which is not what bounds these layers).
             A = X.as_strided((M, K * 2 * Cin), (stride * 2 * Cin, 1))
-            W1 = torch.cat([wh, wh], dim=2).permute(1, 0, 2).reshape(Cout, K * 2 * Cin)
-            W2 = torch.cat([wl, torch.zeros_like(wl)], dim=2).permute(1, 0, 2).reshape(Cout, K * 2 * Cin)
+            W1, W2 = self._concat_weights(w)
             L.gemm(A, W1, D, epi=L.EPI_F32, bias=bias)
             L.gemm(A, W2, D, epi=L.EPI_F32_ADD)
-            return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0)
+            return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0, lrelu_x)
+        wh, wl = self._split_weights(w)
         first = True
         for k in range(K):
             A = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
             L.gemm(A, torch.cat([wh[k], wh[k]], dim=1), D, epi=L.EPI_F32 if first else L.EPI_F32_ADD, bias=bias if first else None)
             L.gemm(A[:, :Cin], wl[k], D, epi=L.EPI_F32_ADD)
             first = False
-        return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0)
+        return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0, lrelu_x)
 
     def _gemm_conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
         L = self.L
@@ -703,27 +721,30 @@ class CudaKernels:
         B, Cin, T = x.shape
         Cout, _, K = w.shape
         Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
-        DY = self._cl_split("dy", dy, Tout_p, 0, M)
-        wh, wl = self._split_weights(w)
-        dx = None
+        dx, DY = None, None
         if need_dx and stride == 1 and dil == 1 and K > 1 and pad <= K - 1 and self.tap_concat:
             # input gradient of a stride-1 convolution = the forward route on dy with the taps flipped and the channel roles swapped
-            # (padding K - 1 - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer
-            dx = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, 1, K - 1 - pad, False)
+            # (padding K - 1 - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer; the derivative of a
+            # leaky ReLU on the layer's input is applied by the conversion back to [B, C, T]
+            dx, DYp = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, 1, K - 1 - pad, False,
+                                          lrelu_x=x if pre_lrelu else None, split_tag="dyp")
             assert dx.shape == x.shape
-            if pre_lrelu:
-                self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dx), self._p(dx), x.numel(), 0.1, 1, self._st()), "ttts_lrelu (dgrad)")
+            if 2 * pad == K - 1:
+                # a "same" convolution: the padded rows of dy just written have the clip pitch the weight gradient needs (T + K - 1), shifted
+                # by the padding -- one split of dy serves both gradients
+                DY = DYp[K - 1 - pad:K - 1 - pad + M]
             need_dx = False
+        if DY is None:
+            DY = self._cl_split("dy", dy, Tout_p, 0, M)
         if need_dx:
+            wh, wl = self._split_weights(w)
             Dx = self._buf("Dx", (rows, Cin), torch.float32, x.device)
             Dx.zero_()
             for k in range(K):
                 O = Dx[k * dil:k * dil + stride * (M - 1) + 1:stride]
                 L.gemm(DY, torch.cat([wh[k], wh[k]], dim=0), O, b_mn=True, epi=L.EPI_F32_ADD)
                 L.gemm(DY[:, :Cout], wl[k], O, b_mn=True, epi=L.EPI_F32_ADD)
-            dx = self._cl_unpack(Dx, B, Cin, T, Tp, pad)
-            if pre_lrelu:
-                self._chk(self.lib.ttts_lrelu(self._p(x), self._p(dx), self._p(dx), x.numel(), 0.1, 1, self._st()), "ttts_lrelu (dgrad)")
+            dx = self._cl_unpack(Dx, B, Cin, T, Tp, pad, x if pre_lrelu else None)
         X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
         if dil == 1 and K > 1 and self.wgrad_concat:
             # all taps as column blocks of ONE product: the overlapped view again, now as the MN-major B operand [positions, K 2 Cin]; dy is read
@@ -758,7 +779,7 @@ class CudaKernels:
             self._chk(self.lib.ttts_gconv1d(self._p(x), self._p(w), self._p(b), self._p(y), B, Cin, Tin, Cout, K, stride, pad, groups, self._st()), "ttts_gconv1d")
             return y
         if self._gemm_ok(x, w, stride, dil, pad, groups):
-            return self._gemm_conv_fwd(x, w, b, stride, dil, pad, pre_lrelu)
+            return self._gemm_conv_fwd(x, w, b, stride, dil, pad, pre_lrelu)[0]
         return self.E.conv1d(x, w, b, stride=stride, dil=dil, pad=pad, pre_lrelu=pre_lrelu)
 
     def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
@@ -808,7 +829,7 @@ class CudaKernels:
     def _phase_conv(self, a, wt, pd):
         """stride-1 cross-correlation of one phase (dgrad_by_phase): the GEMM route when the phase's sub-kernel qualifies, else the fp32 kernels"""
         if self._gemm_ok(a, wt, 1, 1, pd, 1):
-            return self._gemm_conv_fwd(a, wt, None, 1, 1, pd, False)
+            return self._gemm_conv_fwd(a, wt, None, 1, 1, pd, False)[0]
         return self.E.conv1d(a, wt, None, stride=1, dil=1, pad=pd, tc=False)
 
     def convT_fwd(self, x, w, b, stride, pad):
