@@ -414,10 +414,13 @@ int ttts_diff_loss_bwd(const float* dL, const float* model_out, const float* x_s
 /* Layout conversion around the tensor-core convolutions of the training tapes (the wide nn.Conv1d / Conv2d-(k,1) layers of aa_model.py:97-118,
  * 198-233 and vq2.py:341-416,418-496 as split-bf16 GEMMs on ttts_gemm_bf16): x [B,C,T] fp32 (optionally through leaky_relu 0.1) -> rows
  * [hi(x[b,:,t]) | lo(x[b,:,t])] (2C bf16) at row row_off + b rows_per_clip + t of a ZERO-INITIALISED buffer (the untouched rows are the zero
- * padding around and between the clips); and back: D fp32 (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T]. */
-int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu, void* stream);
+ * padding around and between the clips); and back: D fp32 (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T].
+ * dil > 1: sample t of clip b lives at row row_off + (b dil + t mod dil) rows_per_clip + t / dil instead -- de-interleaved, every residue class of
+ * the time index a clip of its own, so that a convolution with dilation dil becomes an ordinary convolution over B dil clips. */
+int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu, int32_t dil,
+                  void* stream);
 int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off,
-                   const float* lrelu_x /* NULL, or [B,C,T]: y *= leaky_relu'(lrelu_x), slope 0.1 */, void* stream);
+                   const float* lrelu_x /* NULL, or [B,C,T]: y *= leaky_relu'(lrelu_x), slope 0.1 */, int32_t dil, void* stream);
 
 #ifdef __cplusplus
 }

@@ -126,3 +126,23 @@ def test_layout_conversion_kernels(K, B, C, T):
         want3[3 + b * (T + 5):3 + b * (T + 5) + T, :C] = hi[b].t()
         want3[3 + b * (T + 5):3 + b * (T + 5) + T, C:] = lo[b].t()
     assert torch.equal(buf3, want3)
+    # de-interleaved order (dilation d): sample t of clip b -> sub-clip b d + t mod d, position t // d; and back
+    for d in (3, 5):
+        Ts = (T + d - 1) // d
+        rpc = Ts + 2
+        buf4 = K._cl_split("d%d" % d, x, rpc, 1, 1 + B * d * rpc + 1, False, d)
+        want4 = torch.zeros_like(buf4)
+        for b in range(B):
+            for r in range(d):
+                n = len(range(r, T, d))
+                want4[1 + (b * d + r) * rpc:1 + (b * d + r) * rpc + n, :C] = hi[b, :, r::d].t()
+                want4[1 + (b * d + r) * rpc:1 + (b * d + r) * rpc + n, C:] = lo[b, :, r::d].t()
+        assert torch.equal(buf4, want4)
+        D4 = torch.randn(1 + B * d * rpc + 1, C + 4, generator=g)
+        y4 = K._cl_unpack(D4, B, C, T, rpc, 1, None, d)
+        want_y4 = torch.empty(B, C, T)
+        for b in range(B):
+            for r in range(d):
+                n = len(range(r, T, d))
+                want_y4[b, :, r::d] = D4[1 + (b * d + r) * rpc:1 + (b * d + r) * rpc + n, :C].t()
+        assert torch.equal(y4, want_y4)

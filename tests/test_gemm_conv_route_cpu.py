@@ -52,7 +52,10 @@ def K(tmp_path_factory):
 @pytest.mark.parametrize("B,Cin,T,Cout,Kw,stride,dil,pad,lrelu", [
     (2, 64, 50, 128, 3, 1, 1, 1, False), (2, 128, 40, 64, 5, 3, 1, 2, False), (1, 64, 45, 64, 7, 1, 1, 3, True), (2, 64, 33, 64, 1, 1, 1, 0, False),
     (1, 64, 60, 64, 7, 2, 3, 9, True), (2, 64, 37, 128, 5, 1, 1, 0, False), (1, 64, 41, 64, 4, 1, 1, 3, False),
-    (2, 32, 50, 32, 7, 1, 1, 3, True), (1, 32, 70, 128, 5, 3, 1, 2, False), (2, 64, 31, 32, 3, 1, 1, 1, False)])
+    (2, 32, 50, 32, 7, 1, 1, 3, True), (1, 32, 70, 128, 5, 3, 1, 2, False), (2, 64, 31, 32, 3, 1, 1, 1, False),
+    # dilated stride-1 layers whose padding is a multiple of the dilation: de-interleaved sub-clips, tap-concatenated like dilation 1
+    (1, 64, 60, 64, 7, 1, 3, 9, True), (2, 64, 50, 128, 3, 1, 5, 5, False), (1, 32, 48, 32, 5, 1, 3, 6, True), (1, 64, 45, 64, 3, 1, 3, 0, False),
+    (2, 64, 40, 64, 3, 1, 5, 10, True), (2, 64, 41, 64, 7, 1, 3, 9, True), (1, 32, 53, 64, 3, 1, 5, 5, True), (1, 64, 44, 64, 3, 1, 3, 0, False)])
 def test_gemm_route_geometry(K, monkeypatch, tapcat, B, Cin, T, Cout, Kw, stride, dil, pad, lrelu):
     F = torch.nn.functional
     g = torch.Generator().manual_seed(Cin + T + Kw)
@@ -79,7 +82,7 @@ def test_gemm_route_geometry(K, monkeypatch, tapcat, B, Cin, T, Cout, Kw, stride
     assert rel(dx, xr.grad) <= 3e-5, rel(dx, xr.grad)
     assert rel(dw, wr.grad) <= 3e-5, rel(dw, wr.grad)
     assert rel(db, br.grad) <= 1e-5
-    if tapcat and dil == 1 and Kw > 1:
+    if tapcat and Kw > 1 and (dil == 1 or (stride == 1 and pad % dil == 0)):
         assert n_fwd == 2                                            # one GEMM pair for all taps
     else:
         assert n_fwd == 2 * Kw

@@ -260,7 +260,11 @@ def test_trainer_surface_save_load(K, tmp_path):
     (3, 64, 1700, 64, 11, 1, 1, 5, True),         # narrow layers (tap-concatenated form only): Generator ResBlocks at 64 ...
     (3, 32, 2100, 32, 7, 1, 1, 3, True),          # ... and 32 channels
     (4, 32, 1500, 128, 5, 3, 1, 2, False),        # DiscriminatorP 32 -> 128, stride 3
-    (2, 64, 1203, 32, 3, 1, 1, 1, False)])
+    (2, 64, 1203, 32, 3, 1, 1, 1, False),
+    (3, 64, 1700, 64, 7, 1, 3, 9, True),          # dilated narrow layers: de-interleaved sub-clips (1700 is not a multiple of 3)
+    (3, 32, 2100, 32, 3, 1, 5, 5, True),
+    (2, 128, 1001, 256, 11, 1, 3, 15, True),      # dilated wide layer, de-interleaved
+    (2, 128, 1000, 128, 3, 1, 3, 2, False)])      # padding not a multiple of the dilation: one GEMM pair per tap
 def test_tensor_core_convolution_vs_torch(K, monkeypatch, B, Cin, T, Cout, Kw, stride, dil, pad, lrelu):
     """the split-bf16 tcgen05 GEMM route of the wide convolutions (forward, input gradient, weight and bias gradient; any kernel size, stride,
     dilation, padding, optional leaky ReLU on the input) against torch's fp64 convolution: fp32-grade agreement (three bf16 products per fp32

@@ -533,9 +533,17 @@ __global__ void diff_loss_bwd_kernel(const float* __restrict__ dL, const float* 
 // 64 x 64 tiles through shared memory (16 KB in, 16 KB out per CTA), 128-byte warp requests on both sides: the [B, C, T] side along time, the
 // position-major side along channels -- cl_split packs two neighbouring channels per lane into one 32-bit store.  The first version (32 x 32
 // tiles, one 2-byte store per thread and part) ran at 2.4 (split) / 3.0 (unpack) TB/s and was 30 % of a routed 128-channel layer (r2ah).
+// dil > 1: the clip is DE-INTERLEAVED on the position-major side -- sample t goes to sub-clip b dil + t mod dil, position t / dil (row
+// row_off + (b dil + t mod dil) rows_per_clip + t / dil): on each residue class of the time index a dilated convolution is an ordinary one, so the
+// dilated layers take the tap-concatenated route too; the [B, C, T] side is untouched and rows stay whole, so the kernels move the same bytes.
 constexpr int CL_TILE = 64;
+TTTS_DEVICE size_t cl_row(int b, int t, int rows_per_clip, int row_off, int dil) {
+    if (dil <= 1) return (size_t)row_off + (size_t)b * rows_per_clip + t;
+    const int q = t / dil, r = t - q * dil;
+    return (size_t)row_off + ((size_t)b * dil + r) * rows_per_clip + q;
+}
 __global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int C, int T, int rows_per_clip,
-                                                       int row_off, int lrelu) {
+                                                       int row_off, int lrelu, int dil) {
     __shared__ float tile[CL_TILE][CL_TILE + 1];
     const int t0 = blockIdx.x * CL_TILE, c0 = blockIdx.y * CL_TILE, b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__
         const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
         const uint16_t uh0 = *reinterpret_cast<const uint16_t*>(&h0), uh1 = *reinterpret_cast<const uint16_t*>(&h1);
         const uint16_t ul0 = *reinterpret_cast<const uint16_t*>(&l0), ul1 = *reinterpret_cast<const uint16_t*>(&l1);
-        uint16_t* row = out + ((size_t)row_off + (size_t)b * rows_per_clip + t) * (2 * (size_t)C);
+        uint16_t* row = out + cl_row(b, t, rows_per_clip, row_off, dil) * (2 * (size_t)C);
         if (packed) {                                                  // C even, c even: c + 1 < C
             *reinterpret_cast<uint32_t*>(row + c) = (uint32_t)uh0 | ((uint32_t)uh1 << 16);
             *reinterpret_cast<uint32_t*>(row + C + c) = (uint32_t)ul0 | ((uint32_t)ul1 << 16);
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(256) cl_split_kernel(const float* __restrict__
     }
 }
 __global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict__ D, float* __restrict__ y, int C, int T, int ld, int rows_per_clip,
-                                                        int row_off, const float* __restrict__ lrelu_x) {
+                                                        int row_off, const float* __restrict__ lrelu_x, int dil) {
     __shared__ float tile[CL_TILE][CL_TILE + 1];
     const int t0 = blockIdx.x * CL_TILE, c0 = blockIdx.y * CL_TILE, b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -579,7 +587,7 @@ __global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict_
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = c0 + lane + 32 * h;
-            tile[i][lane + 32 * h] = (t < T && c < C) ? D[((size_t)row_off + (size_t)b * rows_per_clip + t) * ld + c] : 0.f;
+            tile[i][lane + 32 * h] = (t < T && c < C) ? D[cl_row(b, t, rows_per_clip, row_off, dil) * ld + c] : 0.f;
         }
     }
     __syncthreads();
@@ -752,24 +760,25 @@ extern "C" int ttts_diff_loss_bwd(const float* dL, const float* model_out, const
     return TTTS_OK;
 }
 
-/* x [B,C,T] fp32 -> split-bf16 position-major rows [hi | lo] of a zero-initialised [rows, 2C] bf16 buffer: row row_off + b rows_per_clip + t */
+/* x [B,C,T] fp32 -> split-bf16 position-major rows [hi | lo] of a zero-initialised [rows, 2C] bf16 buffer: row row_off + b rows_per_clip + t
+ * (dil > 1: row_off + (b dil + t mod dil) rows_per_clip + t / dil, the de-interleaved order in which a dilated convolution is an ordinary one) */
 extern "C" int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t T, int32_t rows_per_clip, int32_t row_off, int32_t lrelu,
-                             void* stream) {
-    TTTS_CHECK_ARG(x && out_bf16 && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && (C + CL_TILE - 1) / CL_TILE <= 65535 && rows_per_clip >= T && row_off >= 0,
-                   "cl_split: bad args");
+                             int32_t dil, void* stream) {
+    TTTS_CHECK_ARG(x && out_bf16 && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && (C + CL_TILE - 1) / CL_TILE <= 65535 && dil >= 1 &&
+                   rows_per_clip >= (T + dil - 1) / dil && row_off >= 0, "cl_split: bad args");
     TTTS_CHECK_ARG(((uintptr_t)out_bf16 & 3) == 0, "cl_split: output not 4-byte aligned");
     TTTS_CUDA(launch_plain(cl_split_kernel, dim3((T + CL_TILE - 1) / CL_TILE, (C + CL_TILE - 1) / CL_TILE, B), dim3(256), 0, (cudaStream_t)stream, x,
-                           (uint16_t*)out_bf16, C, T, rows_per_clip, row_off, lrelu));
+                           (uint16_t*)out_bf16, C, T, rows_per_clip, row_off, lrelu, dil));
     TTTS_LAUNCH_CHECK("cl_split");
     return TTTS_OK;
 }
 /* D fp32 position-major (row row_off + b rows_per_clip + t, pitch ld) -> y [B,C,T]; lrelu_x (may be NULL): y *= leaky_relu'(lrelu_x), slope 0.1 */
 extern "C" int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off,
-                              const float* lrelu_x, void* stream) {
-    TTTS_CHECK_ARG(D && y && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && ld >= C && (C + CL_TILE - 1) / CL_TILE <= 65535 && rows_per_clip >= T && row_off >= 0,
-                   "cl_unpack: bad args");
+                              const float* lrelu_x, int32_t dil, void* stream) {
+    TTTS_CHECK_ARG(D && y && B >= 1 && B <= 65535 && C >= 1 && T >= 1 && ld >= C && (C + CL_TILE - 1) / CL_TILE <= 65535 && dil >= 1 &&
+                   rows_per_clip >= (T + dil - 1) / dil && row_off >= 0, "cl_unpack: bad args");
     TTTS_CUDA(launch_plain(cl_unpack_kernel, dim3((T + CL_TILE - 1) / CL_TILE, (C + CL_TILE - 1) / CL_TILE, B), dim3(256), 0, (cudaStream_t)stream, D, y, C, T,
-                           ld, rows_per_clip, row_off, lrelu_x));
+                           ld, rows_per_clip, row_off, lrelu_x, dil));
     TTTS_LAUNCH_CHECK("cl_unpack");
     return TTTS_OK;
 }

@@ -537,6 +537,8 @@ class CudaKernels:
         # 44 ms and the layout conversions around such thin GEMMs ate the rest (549 vs 541 ms); with the conversions on 64 x 64 tiles / packed
         # stores and the 16-byte-load bias gradient (r2ai) the route wins: 501 vs 521 ms per step
         self.gemm_narrow = os.environ.get("TTTS_GEMM_NARROW", "1") != "0"
+        # dilated stride-1 layers as ordinary convolutions over de-interleaved sub-clips (TTTS_GEMM_DEINT=0: one GEMM pair per tap / fp32 kernels)
+        self.deinterleave = os.environ.get("TTTS_GEMM_DEINT", "1") != "0"
 
     @staticmethod
     def _train_protos(lib):
@@ -575,8 +577,8 @@ class CudaKernels:
             lib.ttts_masked_mean_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
             lib.ttts_posterior_sample_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
             try:
-                lib.ttts_cl_split.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
-                lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+                lib.ttts_cl_split.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+                lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
             except AttributeError:
                 pass                                                  # an emulation set without csrc/diffusion_kernels.cu
             lib._train_protos = True
@@ -625,8 +627,8 @@ class CudaKernels:
         # narrow layers (the Generator's 64- and 32-channel ResBlock convolutions on 5 120 / 10 240 positions per clip): only in the
         # tap-concatenated form, where every product reduces over K 2 Cin >= 64 and the accumulator is swept twice instead of 2 K times
         # (per tap these layers were bound by that traffic and lost to the fp32 kernels)
-        return (self.gemm_narrow and self.tap_concat and self.wgrad_concat and dil == 1 and K > 1 and Cin % 32 == 0 and Cout % 32 == 0
-                and pad <= K - 1 and (stride == 1 or Cout % 64 == 0))
+        return (self.gemm_narrow and self.tap_concat and self.wgrad_concat and (dil == 1 or self._deinterleaved(T, K, stride, dil, pad)) and K > 1
+                and Cin % 32 == 0 and Cout % 32 == 0 and pad <= dil * (K - 1) and (stride == 1 or Cout % 64 == 0))
 
     def _buf(self, key, shape, dtype, dev, zero=False):
         """transient buffers, one per key: every use is ordered on the current stream"""
@@ -636,22 +638,22 @@ class CudaKernels:
             pool[key] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
         return pool[key]
 
-    def _cl_split(self, tag, x, rows_per_clip=None, row_off=1, rows=None, lrelu=False):
+    def _cl_split(self, tag, x, rows_per_clip=None, row_off=1, rows=None, lrelu=False, dil=1):
         """x [B,C,T] -> [rows, 2C] bf16 rows [hi | lo]; the rows the kernel never writes are the zero padding (default geometry: one zero row
-        before every clip and one after the last)"""
+        before every clip and one after the last).  dil > 1: de-interleaved, B dil sub-clips of T / dil positions (include/ttts_b200.h)"""
         B, C, T = x.shape
         rows_per_clip = T + 1 if rows_per_clip is None else rows_per_clip
         rows = 2 + B * rows_per_clip if rows is None else rows
-        buf = self._buf((tag, B, C, T, rows_per_clip, row_off), (rows, 2 * C), torch.bfloat16, x.device, zero=True)
-        self._chk(self.lib.ttts_cl_split(self._p(x), self._p(buf), B, C, T, rows_per_clip, row_off, int(bool(lrelu)), self._st()), "ttts_cl_split")
+        buf = self._buf((tag, B, C, T, rows_per_clip, row_off, dil), (rows, 2 * C), torch.bfloat16, x.device, zero=True)
+        self._chk(self.lib.ttts_cl_split(self._p(x), self._p(buf), B, C, T, rows_per_clip, row_off, int(bool(lrelu)), dil, self._st()), "ttts_cl_split")
         return buf
 
-    def _cl_unpack(self, D, B, C, T, rows_per_clip=None, row_off=0, lrelu_x=None):
+    def _cl_unpack(self, D, B, C, T, rows_per_clip=None, row_off=0, lrelu_x=None, dil=1):
         """D (position-major fp32 rows) -> [B,C,T]; lrelu_x: multiply by leaky_relu'(lrelu_x) on the way (the input gradient of a layer that
         applies the activation to its input)"""
         y = torch.empty(B, C, T, dtype=torch.float32, device=D.device)
         rows_per_clip = T + 1 if rows_per_clip is None else rows_per_clip
-        self._chk(self.lib.ttts_cl_unpack(self._p(D), self._p(y), B, C, T, D.stride(0), rows_per_clip, row_off, self._p(lrelu_x), self._st()), "ttts_cl_unpack")
+        self._chk(self.lib.ttts_cl_unpack(self._p(D), self._p(y), B, C, T, D.stride(0), rows_per_clip, row_off, self._p(lrelu_x), dil, self._st()), "ttts_cl_unpack")
         return y
 
     @staticmethod
@@ -684,14 +686,26 @@ class CudaKernels:
         self._req(x, w, b)
         B, Cin, T = x.shape
         Cout, _, K = w.shape
-        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
-        X = self._cl_split(split_tag, x, Tp, pad, rows, pre_lrelu)
-        return self._gemm_conv_core(X, B, Cin, T, w, b, stride, dil, pad, lrelu_x), X
+        d = dil if self._deinterleaved(T, K, stride, dil, pad) else 1
+        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B * d, (T + d - 1) // d, K, stride, dil // d, pad // d)
+        X = self._cl_split(split_tag, x, Tp, pad // d, rows, pre_lrelu, d)
+        return self._gemm_conv_core(X, B, Cin, T, w, b, stride, dil, pad, lrelu_x, d), X
 
-    def _gemm_conv_core(self, X, B, Cin, T, w, b, stride, dil, pad, lrelu_x=None):
+    def _deinterleaved(self, T, K, stride, dil, pad):
+        """a dilated stride-1 layer whose padding is a multiple of the dilation runs as an ordinary convolution over B dil sub-clips (one per
+        residue class of the time index, ceil(T / dil) positions each -- the shorter ones end in zero rows; the layout kernels write / read
+        that order), i.e. in the tap-concatenated form"""
+        return dil > 1 and K > 1 and stride == 1 and pad % dil == 0 and self.tap_concat and self.deinterleave
+
+    def _gemm_conv_core(self, X, B, Cin, T, w, b, stride, dil, pad, lrelu_x=None, d=1):
+        """X = the split activation; d > 1: de-interleaved (then B, T, dil, pad are still the layer's own; the GEMMs see B d clips of T / d)"""
         L = self.L
         Cout, _, K = w.shape
+        Tout_full = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        B_out, T_out = B, Tout_full
+        B, T, dil, pad = B * d, (T + d - 1) // d, dil // d, pad // d
         Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
+        assert Tout == (T_out + d - 1) // d
         D = self._buf("D", (M, Cout), torch.float32, X.device)
         bias = b.clone() if (b is not None and b.data_ptr() % 16) else b
         if dil == 1 and K > 1 and self.tap_concat:
@@ -704,7 +718,7 @@ class CudaKernels:
             W1, W2 = self._concat_weights(w)
             L.gemm(A, W1, D, epi=L.EPI_F32, bias=bias)
             L.gemm(A, W2, D, epi=L.EPI_F32_ADD)
-            return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0, lrelu_x)
+            return self._cl_unpack(D, B_out, Cout, T_out, Tout_p, 0, lrelu_x, d)
         wh, wl = self._split_weights(w)
         first = True
         for k in range(K):
@@ -712,7 +726,7 @@ class CudaKernels:
             L.gemm(A, torch.cat([wh[k], wh[k]], dim=1), D, epi=L.EPI_F32 if first else L.EPI_F32_ADD, bias=bias if first else None)
             L.gemm(A[:, :Cin], wl[k], D, epi=L.EPI_F32_ADD)
             first = False
-        return self._cl_unpack(D, B, Cout, Tout, Tout_p, 0, lrelu_x)
+        return self._cl_unpack(D, B_out, Cout, T_out, Tout_p, 0, lrelu_x, d)
 
     def _gemm_conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db):
         L = self.L
@@ -720,22 +734,27 @@ class CudaKernels:
         self._req(dy, x, w)
         B, Cin, T = x.shape
         Cout, _, K = w.shape
-        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B, T, K, stride, dil, pad)
+        Tout_full = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        # a de-interleaved dilated layer: from here on B d sub-clips of T / d positions, dilation 1 (the layout kernels are told d)
+        d = dil if self._deinterleaved(T, K, stride, dil, pad) else 1
+        Be, Te, dile, pade = B * d, (T + d - 1) // d, dil // d, pad // d
+        Tout, Tout_p, Tp, M, rows = self._gemm_geometry(Be, Te, K, stride, dile, pade)
         dx, DY = None, None
-        if need_dx and stride == 1 and dil == 1 and K > 1 and pad <= K - 1 and self.tap_concat:
+        if need_dx and stride == 1 and (dil == 1 or d > 1) and K > 1 and pad <= dil * (K - 1) and self.tap_concat:
             # input gradient of a stride-1 convolution = the forward route on dy with the taps flipped and the channel roles swapped
-            # (padding K - 1 - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer; the derivative of a
-            # leaky ReLU on the layer's input is applied by the conversion back to [B, C, T]
-            dx, DYp = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, 1, K - 1 - pad, False,
+            # (padding dil (K - 1) - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer; the derivative of
+            # a leaky ReLU on the layer's input is applied by the conversion back to [B, C, T]
+            dx, DYp = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, dil, dil * (K - 1) - pad, False,
                                           lrelu_x=x if pre_lrelu else None, split_tag="dyp")
             assert dx.shape == x.shape
-            if 2 * pad == K - 1:
+            if 2 * pade == K - 1:
                 # a "same" convolution: the padded rows of dy just written have the clip pitch the weight gradient needs (T + K - 1), shifted
                 # by the padding -- one split of dy serves both gradients
-                DY = DYp[K - 1 - pad:K - 1 - pad + M]
+                DY = DYp[K - 1 - pade:K - 1 - pade + M]
             need_dx = False
         if DY is None:
-            DY = self._cl_split("dy", dy, Tout_p, 0, M)
+            DY = self._cl_split("dy", dy, Tout_p, 0, M, False, d)
+        dil, pad = dile, pade                                         # the GEMMs below see the effective layer
         if need_dx:
             wh, wl = self._split_weights(w)
             Dx = self._buf("Dx", (rows, Cin), torch.float32, x.device)
@@ -744,8 +763,8 @@ class CudaKernels:
                 O = Dx[k * dil:k * dil + stride * (M - 1) + 1:stride]
                 L.gemm(DY, torch.cat([wh[k], wh[k]], dim=0), O, b_mn=True, epi=L.EPI_F32_ADD)
                 L.gemm(DY[:, :Cout], wl[k], O, b_mn=True, epi=L.EPI_F32_ADD)
-            dx = self._cl_unpack(Dx, B, Cin, T, Tp, pad, x if pre_lrelu else None)
-        X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu)
+            dx = self._cl_unpack(Dx, B, Cin, T, Tp, pad, x if pre_lrelu else None, d)
+        X = self._cl_split("x", x, Tp, pad, rows, pre_lrelu, d)
         if dil == 1 and K > 1 and self.wgrad_concat:
             # all taps as column blocks of ONE product: the overlapped view again, now as the MN-major B operand [positions, K 2 Cin]; dy is read
             # once per product instead of once per tap.  Both halves of dy meet the whole view, so the lo . lo term comes along for free.
@@ -765,7 +784,7 @@ class CudaKernels:
         db = None
         if need_db:
             db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
-            self._chk(self.lib.ttts_bias_grad(self._p(dy), self._p(db), B, Cout, Tout, self._st()), "ttts_bias_grad")
+            self._chk(self.lib.ttts_bias_grad(self._p(dy), self._p(db), B, Cout, Tout_full, self._st()), "ttts_bias_grad")
         return dx, dw, db
 
     # ---- convolution / weight norm ----
