@@ -421,6 +421,9 @@ int ttts_cl_split(const float* x, void* out_bf16, int32_t B, int32_t C, int32_t 
                   void* stream);
 int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t rows_per_clip, int32_t row_off,
                    const float* lrelu_x /* NULL, or [B,C,T]: y *= leaky_relu'(lrelu_x), slope 0.1 */, int32_t dil, void* stream);
+/* Weight side of the same route: w [Cout,Cin,K] fp32 -> W1, W2 [R, K 2 Cr] bf16, per tap W1 = [hi | hi], W2 = [lo | 0] (the B operands of the GEMM
+ * pair that reduces over all taps at once).  flip_transpose = 0: R = Cout, Cr = Cin; 1: the input-gradient form, R = Cin, Cr = Cout, taps reversed. */
+int ttts_conv_w_concat(const float* w, void* W1, void* W2, int32_t Cout, int32_t Cin, int32_t K, int32_t flip_transpose, void* stream);
 
 #ifdef __cplusplus
 }

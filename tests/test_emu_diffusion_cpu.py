@@ -146,3 +146,20 @@ def test_layout_conversion_kernels(K, B, C, T):
                 n = len(range(r, T, d))
                 want_y4[b, :, r::d] = D4[1 + (b * d + r) * rpc:1 + (b * d + r) * rpc + n, :C].t()
         assert torch.equal(y4, want_y4)
+
+
+@pytest.mark.parametrize("Cout,Cin,Kw", [(5, 7, 3), (64, 32, 11), (3, 130, 1)])
+def test_weight_operands_of_the_tap_concatenated_route(K, Cout, Cin, Kw):
+    """ttts_conv_w_concat: w [Cout,Cin,K] -> W1 = per tap [hi | hi], W2 = per tap [lo | 0]; the input-gradient form has the channel roles swapped
+    and the taps reversed -- against the torch formulation the kernel replaced"""
+    g = torch.Generator().manual_seed(Cout + Cin + Kw)
+    w = torch.randn(Cout, Cin, Kw, generator=g)
+    assert hasattr(K.lib, "ttts_conv_w_concat") and K.fused_wprep
+    for flip_t in (False, True):
+        W1, W2 = K._concat_weights(w, flip_t)
+        K.fused_wprep = False
+        try:
+            R1, R2 = K._concat_weights(w, flip_t)
+        finally:
+            K.fused_wprep = True
+        assert W1.shape == R1.shape and torch.equal(W1, R1) and torch.equal(W2, R2)

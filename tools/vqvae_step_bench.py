@@ -55,12 +55,13 @@ def run(B=64, iters=3, with_cpu=False, cpu_batch=2):
     for _ in range(iters):
         out = step()
     e1.record()
+    enqueue = (time.perf_counter() - t0) / iters * 1e3              # host time to ENQUEUE a step (no synchronisation inside the loop)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / iters * 1e3
     ms = e0.elapsed_time(e1) / iters
     launches = (lib.ttts_launch_count() - l0) // iters
     res = {"workload": "VQ-VAE-GAN train step (BASELINE config 4): enc + VQ + dec + disc, generator + discriminator AdamW, segment 20480, aug = identity",
-           "batch": B, "samples_per_clip": 23040, "ms_per_step": ms, "host_ms_per_step": wall, "msamples_per_s": B * 23040 / ms / 1e3,
+           "batch": B, "samples_per_clip": 23040, "ms_per_step": ms, "host_ms_per_step": wall, "host_enqueue_ms_per_step": enqueue, "msamples_per_s": B * 23040 / ms / 1e3,
            "gpu_launches_per_step": int(launches), "dtype": "f32 (wide convolutions: split-bf16 tcgen05, 3 bf16 products per fp32 product)",
            "step_tflops": FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12,
            "flop_model": "3.87e11 FLOP per clip and step (SURVEY.md section 6, FlopCounterMode over the reference's step)",

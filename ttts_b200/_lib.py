@@ -57,7 +57,15 @@ def check(rc, what=""):
         raise TTTSError("%s failed (%d): %s" % (what or "ttts call", rc, msg))
 
 
+# torch.cuda.current_stream() builds a Stream object and resolves the device index through several Python layers (~10 us); the training tapes
+# ask for the stream once per kernel call, ~12 000 times per VQ-VAE-GAN step, and that step is bound by the host (r2al: enqueue time = step
+# time, current_stream() 20 % of the profile).  The raw-stream accessor torch's own launchers use returns the same pointer in < 1 us.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -606,6 +606,29 @@ __global__ void __launch_bounds__(256) cl_unpack_kernel(const float* __restrict_
     }
 }
 
+// Weights of a routed convolution for the tap-concatenated GEMM pair, in one pass: w [Cout, Cin, K] fp32 -> W1, W2 [R, K 2 Cr] bf16 with, per tap,
+// W1 = [hi | hi], W2 = [lo | 0].  flip_t = 0: rows = output channels (R = Cout, Cr = Cin), tap order as stored (forward, weight gradient);
+// flip_t = 1: the input-gradient form -- rows = input channels (R = Cin, Cr = Cout), taps reversed.  One thread per (row, column channel) walks the
+// K taps of its weight (K contiguous floats).  Replaces ~8 torch kernels per call on a host-bound tape (r2al).
+__global__ void __launch_bounds__(256) conv_w_concat_kernel(const float* __restrict__ w, uint16_t* __restrict__ W1, uint16_t* __restrict__ W2, int Cout,
+                                                            int Cin, int K, int flip_t) {
+    const int R = flip_t ? Cin : Cout, Cr = flip_t ? Cout : Cin;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)R * Cr) return;
+    const int r = (int)(idx / Cr), c = (int)(idx - (size_t)r * Cr);
+    const float* src = flip_t ? w + ((size_t)c * Cin + r) * K : w + ((size_t)r * Cin + c) * K;
+    const size_t row = (size_t)r * K * 2 * Cr;
+    for (int k = 0; k < K; ++k) {
+        const float v = src[flip_t ? K - 1 - k : k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        const uint16_t uh = *reinterpret_cast<const uint16_t*>(&h), ul = *reinterpret_cast<const uint16_t*>(&l);
+        const size_t o = row + (size_t)k * 2 * Cr + c;
+        W1[o] = uh; W1[o + Cr] = uh;
+        W2[o] = ul; W2[o + Cr] = 0;
+    }
+}
+
 static inline unsigned df_blocks(size_t n) {
     size_t b = (n + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -780,5 +803,14 @@ extern "C" int ttts_cl_unpack(const float* D, float* y, int32_t B, int32_t C, in
     TTTS_CUDA(launch_plain(cl_unpack_kernel, dim3((T + CL_TILE - 1) / CL_TILE, (C + CL_TILE - 1) / CL_TILE, B), dim3(256), 0, (cudaStream_t)stream, D, y, C, T,
                            ld, rows_per_clip, row_off, lrelu_x, dil));
     TTTS_LAUNCH_CHECK("cl_unpack");
+    return TTTS_OK;
+}
+/* w [Cout,Cin,K] fp32 -> the two bf16 B operands of the tap-concatenated GEMM pair (see conv_w_concat_kernel) */
+extern "C" int ttts_conv_w_concat(const float* w, void* W1, void* W2, int32_t Cout, int32_t Cin, int32_t K, int32_t flip_transpose, void* stream) {
+    TTTS_CHECK_ARG(w && W1 && W2 && Cout >= 1 && Cin >= 1 && K >= 1 && (size_t)Cout * Cin <= ((size_t)1 << 31), "conv_w_concat: bad args");
+    const size_t n = (size_t)Cout * Cin;
+    TTTS_CUDA(launch_plain(conv_w_concat_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, w, (uint16_t*)W1, (uint16_t*)W2,
+                           Cout, Cin, K, flip_transpose));
+    TTTS_LAUNCH_CHECK("conv_w_concat");
     return TTTS_OK;
 }

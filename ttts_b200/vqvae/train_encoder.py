@@ -539,6 +539,7 @@ class CudaKernels:
         self.gemm_narrow = os.environ.get("TTTS_GEMM_NARROW", "1") != "0"
         # dilated stride-1 layers as ordinary convolutions over de-interleaved sub-clips (TTTS_GEMM_DEINT=0: one GEMM pair per tap / fp32 kernels)
         self.deinterleave = os.environ.get("TTTS_GEMM_DEINT", "1") != "0"
+        self.fused_wprep = os.environ.get("TTTS_GEMM_WPREP", "1") != "0"          # one kernel for the routed layers' weight operands (0: torch ops)
 
     @staticmethod
     def _train_protos(lib):
@@ -579,6 +580,7 @@ class CudaKernels:
             try:
                 lib.ttts_cl_split.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
                 lib.ttts_cl_unpack.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+                lib.ttts_conv_w_concat.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
             except AttributeError:
                 pass                                                  # an emulation set without csrc/diffusion_kernels.cu
             lib._train_protos = True
@@ -663,10 +665,20 @@ class CudaKernels:
         wl = (wk - wh.float()).bfloat16()
         return wh, wl
 
-    def _concat_weights(self, w):
-        """w [Cout, Cin, K] -> the two B operands of the tap-concatenated GEMM pair, [Cout, K 2 Cin] bf16 each: taps side by side, per tap
-        [wh | wh] and [wl | 0]"""
+    def _concat_weights(self, w, flip_t=False):
+        """w [Cout, Cin, K] -> the two B operands of the tap-concatenated GEMM pair, [R, K 2 Cr] bf16 each: taps side by side, per tap
+        [wh | wh] and [wl | 0].  flip_t: the input-gradient form (rows = input channels, taps reversed).  One kernel (ttts_conv_w_concat);
+        the buffers are per shape and reused in stream order"""
         Cout, Cin, K = w.shape
+        if self.fused_wprep and hasattr(self.lib, "ttts_conv_w_concat"):
+            R, Cr = (Cin, Cout) if flip_t else (Cout, Cin)
+            W1 = self._buf(("W1", flip_t), (R, K * 2 * Cr), torch.bfloat16, w.device)
+            W2 = self._buf(("W2", flip_t), (R, K * 2 * Cr), torch.bfloat16, w.device)
+            self._chk(self.lib.ttts_conv_w_concat(self._p(w), self._p(W1), self._p(W2), Cout, Cin, K, int(flip_t), self._st()), "ttts_conv_w_concat")
+            return W1, W2
+        if flip_t:
+            w = w.flip(2).transpose(0, 1).contiguous()
+            Cout, Cin, K = w.shape
         wk = w.permute(0, 2, 1)                                       # [Cout, K, Cin] (a view)
         wh = wk.bfloat16()                                            # contiguous [Cout, K, Cin]
         wl = (wk - wh).bfloat16()                                     # bf16 promotes to fp32 in the subtraction
@@ -680,16 +692,17 @@ class CudaKernels:
         Tp = stride * Tout_p                                          # input rows per clip (>= T + 2 pad)
         return Tout, Tout_p, Tp, B * Tout_p, B * Tp + dil * (K - 1) + 1
 
-    def _gemm_conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, lrelu_x=None, split_tag="x"):
-        """lrelu_x: see _cl_unpack (used when this is the input gradient of another layer); returns (y, X) with split_tag given back so that a
-        caller can reuse the split buffer -- plain callers take [0]"""
+    def _gemm_conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, lrelu_x=None, split_tag="x", w_flip_t=False):
+        """lrelu_x: see _cl_unpack (used when this is the input gradient of another layer); w_flip_t: w is the weight of the layer whose INPUT
+        gradient this is ([x channels out, x channels in, K] read transposed with the taps reversed); returns (y, X) so that a caller can
+        reuse the split buffer -- plain callers take [0]"""
         self._req(x, w, b)
         B, Cin, T = x.shape
-        Cout, _, K = w.shape
+        K = w.shape[2]
         d = dil if self._deinterleaved(T, K, stride, dil, pad) else 1
         Tout, Tout_p, Tp, M, rows = self._gemm_geometry(B * d, (T + d - 1) // d, K, stride, dil // d, pad // d)
         X = self._cl_split(split_tag, x, Tp, pad // d, rows, pre_lrelu, d)
-        return self._gemm_conv_core(X, B, Cin, T, w, b, stride, dil, pad, lrelu_x, d), X
+        return self._gemm_conv_core(X, B, Cin, T, w, b, stride, dil, pad, lrelu_x, d, w_flip_t), X
 
     def _deinterleaved(self, T, K, stride, dil, pad):
         """a dilated stride-1 layer whose padding is a multiple of the dilation runs as an ordinary convolution over B dil sub-clips (one per
@@ -697,10 +710,11 @@ class CudaKernels:
         that order), i.e. in the tap-concatenated form"""
         return dil > 1 and K > 1 and stride == 1 and pad % dil == 0 and self.tap_concat and self.deinterleave
 
-    def _gemm_conv_core(self, X, B, Cin, T, w, b, stride, dil, pad, lrelu_x=None, d=1):
+    def _gemm_conv_core(self, X, B, Cin, T, w, b, stride, dil, pad, lrelu_x=None, d=1, w_flip_t=False):
         """X = the split activation; d > 1: de-interleaved (then B, T, dil, pad are still the layer's own; the GEMMs see B d clips of T / d)"""
         L = self.L
-        Cout, _, K = w.shape
+        K = w.shape[2]
+        Cout = w.shape[1] if w_flip_t else w.shape[0]
         Tout_full = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
         B_out, T_out = B, Tout_full
         B, T, dil, pad = B * d, (T + d - 1) // d, dil // d, pad // d
@@ -715,11 +729,11 @@ class CudaKernels:
             # GEMMs of a 128-channel K = 11 layer were bound by that fp32 accumulator traffic, not by the tensor cores).  The hi . lo
             # product reads the same operand against [wl_k | 0] (the zero half costs MMA time, which is not what bounds these layers).
             A = X.as_strided((M, K * 2 * Cin), (stride * 2 * Cin, 1))
-            W1, W2 = self._concat_weights(w)
+            W1, W2 = self._concat_weights(w, w_flip_t)
             L.gemm(A, W1, D, epi=L.EPI_F32, bias=bias)
             L.gemm(A, W2, D, epi=L.EPI_F32_ADD)
             return self._cl_unpack(D, B_out, Cout, T_out, Tout_p, 0, lrelu_x, d)
-        wh, wl = self._split_weights(w)
+        wh, wl = self._split_weights(w.flip(2).transpose(0, 1).contiguous() if w_flip_t else w)
         first = True
         for k in range(K):
             A = X[k * dil:k * dil + stride * (M - 1) + 1:stride]
@@ -744,8 +758,8 @@ class CudaKernels:
             # input gradient of a stride-1 convolution = the forward route on dy with the taps flipped and the channel roles swapped
             # (padding dil (K - 1) - pad): one reduction over all taps instead of 2 K red.add sweeps over a zeroed buffer; the derivative of
             # a leaky ReLU on the layer's input is applied by the conversion back to [B, C, T]
-            dx, DYp = self._gemm_conv_fwd(dy, w.flip(2).transpose(0, 1).contiguous(), None, 1, dil, dil * (K - 1) - pad, False,
-                                          lrelu_x=x if pre_lrelu else None, split_tag="dyp")
+            dx, DYp = self._gemm_conv_fwd(dy, w, None, 1, dil, dil * (K - 1) - pad, False, lrelu_x=x if pre_lrelu else None, split_tag="dyp",
+                                          w_flip_t=True)
             assert dx.shape == x.shape
             if 2 * pade == K - 1:
                 # a "same" convolution: the padded rows of dy just written have the clip pitch the weight gradient needs (T + K - 1), shifted
