@@ -632,8 +632,13 @@ class CudaKernels:
         return (self.gemm_narrow and self.tap_concat and self.wgrad_concat and (dil == 1 or self._deinterleaved(T, K, stride, dil, pad)) and K > 1
                 and Cin % 32 == 0 and Cout % 32 == 0 and pad <= dil * (K - 1) and (stride == 1 or Cout % 64 == 0))
 
+    def release_buffers(self):
+        """drop the transient buffers of the GEMM route (position-major activations, accumulators, weight operands: one set per distinct
+        layer shape, a few GB at B = 64; they are kept between steps so that a step allocates nothing)"""
+        self.__dict__.pop("_gemm_pool", None)
+
     def _buf(self, key, shape, dtype, dev, zero=False):
-        """transient buffers, one per key: every use is ordered on the current stream"""
+        """transient buffers, one per key: every use is ordered on the current stream (never freed: see release_buffers)"""
         pool = self.__dict__.setdefault("_gemm_pool", {})
         key = (key, tuple(shape), dtype, dev)
         if key not in pool:
