@@ -9,6 +9,8 @@ import subprocess
 
 import torch
 
+from emu_build import compile_emu
+
 from ref_kernels import TorchRefKernels
 from ttts_b200.vqvae.train_encoder import CudaKernels
 
@@ -20,10 +22,7 @@ def build_all(outdir):
     libs = []
     for src in SOURCES:
         so = os.path.join(outdir, "lib" + src[:-4] + ".so")
-        cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-               "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", src), "-o", so]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr
+        compile_emu(src, so)
         libs.append(ctypes.CDLL(so))
     return libs
 

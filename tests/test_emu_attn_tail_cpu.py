@@ -7,6 +7,7 @@ import ctypes
 import os
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -15,6 +16,8 @@ import torch
 from oracle import gpt_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -22,10 +25,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("emu") / "libattn_tail_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "attn_tail_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("attn_tail_emu.cpp", so)
     lib = ctypes.CDLL(so)
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     lib.emu_attn_tail_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.c_uint32, ctypes.c_float, ctypes.c_uint64]

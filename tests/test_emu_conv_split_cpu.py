@@ -7,12 +7,15 @@ import ctypes
 import os
 import shutil
 import subprocess
+import sys
 
 import pytest
 import torch
 import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -22,11 +25,7 @@ def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libconv_split_emu.so")
     # TTTS_EMU_CXXFLAGS="-g -fsanitize=address" (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0) turns every
     # out-of-bounds shared / global access of the emulated kernels into a hard error
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"),
-           os.path.join(ROOT, "tests", "emu", "conv_split_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("conv_split_emu.cpp", so)
     lib = ctypes.CDLL(so)
     vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.emu_conv1d_split.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, f32, i32, vp, i32, vp, i32, i32]

@@ -7,6 +7,7 @@ import ctypes
 import os
 import shutil
 import subprocess
+import sys
 
 import pytest
 import torch
@@ -15,6 +16,8 @@ from oracle import gpt_oracle as O
 from ttts_b200.gpt.engine import GptConfig, GptDecode, tensor_table
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -24,11 +27,7 @@ def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libdecode_emu.so")
     # TTTS_EMU_CXXFLAGS="-g -fsanitize=address" (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0) turns every
     # out-of-bounds shared / global access of the emulated kernels into a hard error
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"),
-           os.path.join(ROOT, "tests", "emu", "decode_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("decode_emu.cpp", so)
     lib = ctypes.CDLL(so)
     lib.emu_param_off.restype = ctypes.c_longlong
     lib.emu_param_off.argtypes = [ctypes.POINTER(GptConfig), ctypes.c_int, ctypes.c_int]

@@ -13,6 +13,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from ref_kernels import TorchRefKernels  # noqa: E402
 from ttts_b200.vqvae.train_encoder import kaiser_sinc_filter12  # noqa: E402
 
@@ -25,10 +27,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("emu") / "libenc_bwd_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "encoder_bwd_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("encoder_bwd_emu.cpp", so)
     lib = ctypes.CDLL(so)
     lib.ttts_ew_add.argtypes = [vp, vp, vp, i64, vp]
     lib.ttts_ew_scale.argtypes = [vp, f32, vp, i64, vp]

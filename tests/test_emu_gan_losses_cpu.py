@@ -11,6 +11,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from ref_kernels import TorchRefKernels  # noqa: E402
 
 R = TorchRefKernels()
@@ -21,10 +23,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("emu") / "libgan_losses_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "gan_losses_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("gan_losses_emu.cpp", so)
     lib = ctypes.CDLL(so)
     vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
     lib.ttts_lsgan_loss.argtypes = [vp, f32, i64, vp, vp, vp]

@@ -4,12 +4,15 @@ import ctypes
 import os
 import shutil
 import subprocess
+import sys
 
 import pytest
 import torch
 import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -17,10 +20,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("emu") / "libgconv_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "gconv_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("gconv_emu.cpp", so)
     lib = ctypes.CDLL(so)
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.ttts_gconv1d.argtypes = [vp] * 4 + [i32] * 8 + [vp]

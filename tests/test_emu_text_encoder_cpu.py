@@ -11,6 +11,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_build import compile_emu  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from ref_kernels import TorchRefKernels  # noqa: E402
 
 R = TorchRefKernels()
@@ -22,10 +24,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("emu") / "libte_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC"] + os.environ.get("TTTS_EMU_CXXFLAGS", "").split() + [
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "text_encoder_emu.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    compile_emu("text_encoder_emu.cpp", so)
     lib = ctypes.CDLL(so)
     lib.ttts_attn_small.argtypes = [vp] * 8 + [i32] * 6 + [vp]
     lib.ttts_attn_small_bwd.argtypes = [vp] * 13 + [i32] * 6 + [vp]
