@@ -44,7 +44,9 @@ def K(tmp_path_factory):
     import shutil
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    k = EK.EmuKernels(EK.build_all(str(tmp_path_factory.mktemp("emu"))))
+    libs = EK.build_all(str(tmp_path_factory.mktemp("emu")))
+    k = EK.EmuKernels(libs)
+    k._libs_for_route = libs
     return k
 
 
@@ -86,3 +88,88 @@ def test_gemm_route_geometry(K, monkeypatch, tapcat, B, Cin, T, Cout, Kw, stride
         assert n_fwd == 2                                            # one GEMM pair for all taps
     else:
         assert n_fwd == 2 * Kw
+
+
+class RouteKernels(EK.EmuKernels):
+    """the emulation backend with EVERY eligible convolution of a training graph sent down the product's GEMM route (host code of
+    ttts_b200/vqvae/train_encoder.py, layout / weight / bias-gradient kernels from their CUDA source on the emulation, the tcgen05 GEMM as a
+    torch matmul on the same bf16 operands): the route's shape rule applies from one output position, the device check is the only thing skipped"""
+
+    def __init__(self, libs):
+        super().__init__(libs)
+        self.L = TorchGemm()
+        self.GEMM_MIN_POSITIONS = 1
+        self.routed = {"fwd": 0, "bwd": 0, "dilated": 0, "narrow": 0}
+
+    def conv_fwd(self, x, w, b, stride, dil, pad, pre_lrelu, groups=1):
+        if groups == 1 and self._gemm_shape_ok(x, w, stride, dil, pad):
+            self.routed["fwd"] += 1
+            self.routed["dilated"] += dil > 1
+            self.routed["narrow"] += min(w.shape[0], w.shape[1]) < 128
+            return self._gemm_conv_fwd(x.contiguous(), w.contiguous(), b, stride, dil, pad, pre_lrelu)[0]
+        return super().conv_fwd(x, w, b, stride, dil, pad, pre_lrelu, groups)
+
+    def conv_bwd(self, dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups=1):
+        if groups == 1 and self._gemm_shape_ok(x, w, stride, dil, pad):
+            self.routed["bwd"] += 1
+            return self._gemm_conv_bwd(dy, x.contiguous(), w.contiguous(), stride, dil, pad, pre_lrelu, need_dx, need_db)
+        return super().conv_bwd(dy, x, w, stride, dil, pad, pre_lrelu, need_dx, need_db, groups)
+
+
+@pytest.mark.skipif(os.environ.get("TTTS_SLOW_TESTS") != "1", reason="minutes on the emulation (one OS thread per CUDA thread): TTTS_SLOW_TESTS=1")
+def test_decoder_training_graph_through_the_route(K, golden_dir):
+    """The Generator's training graph (ResBlock1 stacks with dilations 1 / 3 / 5 at 256 ... 32 channels, conv_pre / conv_post; vq2.py Generator,
+    modules.py:224-318) with every eligible convolution on the route -- dilated layers de-interleaved, narrow layers, the leaky-ReLU derivative
+    folded into the conversion, one split of dy for both gradients -- against the REAL reference's waveform and parameter gradients
+    (tests/golden/decoder.npz).  Tolerances: 2e-4 on the waveform (2e-5 in the fp32 graph test, tests/test_train_decoder_cpu.py: three bf16
+    products per fp32 product through ~40 layers in sequence), gradients as in the GPU tests.  ~12 minutes on the emulation."""
+    import numpy as np
+    from oracle import decoder_oracle as DO
+    from ttts_b200.vqvae.train_decoder import DecoderGraph
+    dec = np.load(os.path.join(golden_dir, "decoder.npz"))
+    P = DO.init_params(seed=9)
+    RK = RouteKernels(K._libs_for_route)
+    graph = DecoderGraph(RK, P)
+    y = graph.forward(torch.tensor(dec["z"]), torch.tensor(dec["g"]))
+    assert np.linalg.norm(y.v.numpy() - dec["y"]) <= 2e-4 * np.linalg.norm(dec["y"])
+    R = torch.randn(y.v.shape, generator=torch.Generator().manual_seed(32))
+    grads = graph.backward(R)
+    assert RK.routed["fwd"] >= 30 and RK.routed["bwd"] >= 30 and RK.routed["dilated"] >= 8 and RK.routed["narrow"] >= 8, RK.routed
+    _check_routed_grads(grads, [str(n) for n in dec["names"]], dec["norm"], dec["proj"])
+
+
+def _check_routed_grads(grads, names, norms, projs):
+    """The kink-aware comparison of the GPU tests (tests/test_gpu_encoder.py::check_param_grads) with a wider kink allowance: the route's
+    arithmetic is fp32-GRADE (1e-5 relative per layer), not fp32 (1e-7 between summation orders), so at the golden shapes (a few hundred positions
+    per level) a leaky-ReLU input lands within rounding of zero ~100x more often; one such flip moves the gradient rows of one channel through
+    the convolutions of its ResBlock.  Every tensor must be within 6 %, the tensors of at most 8 convolutions may be looser than 2e-3 / 1e-2,
+    and the root-mean-square norm error over ALL tensors must stay below 1e-3.  (First run: decoder 4 convolutions loose, worst norm error 7e-4.)"""
+    import numpy as np
+    from test_gpu_encoder import check_param_grads
+    check_param_grads(grads, names, norms, projs, kink_layers=8)
+    num = sum((float(grads[k].norm()) - float(n)) ** 2 for k, n in zip(names, norms))
+    den = sum(float(n) ** 2 for n in norms)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+@pytest.mark.skipif(os.environ.get("TTTS_SLOW_TESTS") != "1", reason="minutes on the emulation (one OS thread per CUDA thread): TTTS_SLOW_TESTS=1")
+def test_encoder_training_graph_through_the_route(K, golden_dir):
+    """The encode half's training graph (MelStyleEncoder, PosteriorAudioEncoder with its dilated 96 / 128 / 192-channel ResBlock1 stacks and the
+    WN layers, proj; vq2.py:667-745, modules.py:136-318) with every eligible convolution on the route, against the REAL reference's outputs and
+    its 414 parameter gradients (tests/golden/encoder.npz, encoder_grads.npz) -- the path the quantizer's codes and kl_ssl hang on."""
+    import numpy as np
+    from oracle import encoder_oracle as EO
+    from oracle import vq_mel_oracle as V
+    from ttts_b200.vqvae.train_encoder import EncoderGraph
+    enc = np.load(os.path.join(golden_dir, "encoder.npz"))
+    g = np.load(os.path.join(golden_dir, "encoder_grads.npz"))
+    P = EO.init_params(seed=5)
+    RK = RouteKernels(K._libs_for_route)
+    graph = EncoderGraph(RK, P)
+    z, x = graph.forward(torch.tensor(V.spectrogram(enc["wav"])), torch.tensor(enc["wav"]), lengths=torch.tensor(enc["lengths"]), eps=torch.tensor(enc["eps"]))
+    assert np.abs(z.v.numpy() - enc["z"]).max() <= 5e-4 * np.abs(enc["z"]).max()
+    assert np.abs(x.v.numpy() - enc["x"]).max() <= 5e-4 * np.abs(enc["x"]).max()
+    R = torch.randn(3, 192, 36, generator=torch.Generator().manual_seed(123))
+    grads = graph.backward(dz=R, dx=x.v / x.v.numel())
+    assert RK.routed["fwd"] >= 30 and RK.routed["bwd"] >= 30 and RK.routed["dilated"] >= 8, RK.routed
+    _check_routed_grads(grads, [str(n) for n in g["names"]], g["norm"], g["proj"])

@@ -619,6 +619,10 @@ class CudaKernels:
     def _gemm_ok(self, x, w, stride, dil, pad, groups):
         if not self.conv_gemm or not x.is_cuda or groups != 1 or not hasattr(self.lib, "ttts_cl_split"):
             return False
+        return self._gemm_shape_ok(x, w, stride, dil, pad)
+
+    def _gemm_shape_ok(self, x, w, stride, dil, pad):
+        """the shape rule of the route (device-independent: tests/test_gemm_conv_route_cpu.py drives whole training graphs through it on CPU)"""
         B, Cin, T = x.shape
         Cout, _, K = w.shape
         Tout = (T + 2 * pad - dil * (K - 1) - 1) // stride + 1
